@@ -1,0 +1,198 @@
+/*
+ * vmp_b200.h — C ABI of the B200-native voxel_plus hot path.
+ *
+ * One handle = one trajectory = one voxel map + one filter state, resident on ONE
+ * B200, driven by one CUDA stream / one CUDA graph per scan.  Handles are not
+ * thread-safe; different handles are independent (no process-wide statics, unlike
+ * the reference's VoxelGrid::merge_thresh_* / VoxelGrid::count, voxel_map.cpp:6-9).
+ *
+ * Every entry point names the reference interface it replaces
+ * (paths relative to the reference repo, voxel_plus/src/map_builder/...).
+ * All pointers are HOST pointers unless the name says `_dev`.  All matrices are
+ * row-major fp64.  Return value: 0 = ok, negative = vmp_status; the message of the
+ * last failure on this thread is available through vmp_last_error().
+ * No C++ types, no torch types, no exceptions cross this boundary.
+ */
+#ifndef VMP_B200_H
+#define VMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vmp_status {
+    VMP_OK = 0,
+    VMP_ERR_INVALID_ARG = -1,   /* null pointer, n < 0, n > max_points_per_scan, bad config */
+    VMP_ERR_NO_DEVICE = -2,     /* no CUDA device / wrong architecture: there is NO CPU fallback */
+    VMP_ERR_CUDA = -3,          /* a CUDA runtime call failed; see vmp_last_error() */
+    VMP_ERR_CAPACITY = -4,      /* voxel coordinate outside the packable range, slot pool exhausted */
+    VMP_ERR_STATE = -5          /* call sequence error (e.g. scan before build) */
+} vmp_status;
+
+/* mirrors lio::LIOConfig (lio_builder.h:17-42) field for field; the last block is
+ * what a device implementation additionally has to know. */
+typedef struct vmp_config {
+    int    opti_max_iter;            /* 5. The reference reads it but never applies it (always 5, ieskf.h:101); we honour it. */
+    double na, ng, nba, nbg;         /* 0.01 0.01 1e-4 1e-4 */
+    int    imu_init_num;             /* 20 */
+    double r_il[9];                  /* identity */
+    double p_il[3];                  /* zero */
+    int    gravity_align;            /* 1 */
+    int    estimate_ext;             /* 0 */
+    double scan_resolution;          /* 0.1; <=0 means "no downsample" (lio_builder.cpp:215-223) */
+    double voxel_size;               /* 0.5 */
+    int    update_size_thresh;       /* 10 */
+    int    max_point_thresh;         /* 100 */
+    double plane_thresh;             /* 0.01 */
+    double ranging_cov;              /* 0.04 */
+    double angle_cov;                /* 0.1 */
+    double merge_thresh_for_angle;   /* 0.1 */
+    double merge_thresh_for_distance;/* 0.04 */
+    int    map_capacity;             /* 100000 */
+    /* ---- device-side additions ---- */
+    int    max_points_per_scan;      /* size of the persistent residual buffer (reference: hard 10000, lio_builder.cpp:25) */
+    int    device;                   /* CUDA device ordinal */
+} vmp_config;
+
+/* mirrors kf::State (ieskf.h:31-62); rot / rot_ext row-major 3x3 */
+typedef struct vmp_state {
+    double pos[3];
+    double rot[9];
+    double rot_ext[9];
+    double pos_ext[3];
+    double vel[3];
+    double bg[3];
+    double ba[3];
+    double g[3];
+} vmp_state;
+
+/* mirrors lio::Plane (voxel_map.h:43-51) + the VoxelGrid fields that are observable
+ * from outside (voxel_map.h:84-100; utils.cpp:161-195) */
+#define VMP_F_INIT          1u   /* VoxelGrid::is_init        */
+#define VMP_F_PLANE         2u   /* VoxelGrid::is_plane       */
+#define VMP_F_UPDATE_ENABLE 4u   /* VoxelGrid::update_enable  */
+#define VMP_F_MERGED        8u   /* VoxelGrid::merged         */
+typedef struct vmp_plane {
+    int64_t  key[3];             /* VoxelGrid::position */
+    double   mean[3];
+    double   ppt[9];
+    double   norm[3];
+    double   cov[36];
+    double   center[3];
+    int32_t  n;                  /* Plane::n */
+    int32_t  n_temp;             /* temp_points.size() */
+    int32_t  newly_add_point;
+    uint32_t flags;
+    uint64_t group;              /* group_id: only equality between voxels is meaningful (Q22) */
+    uint64_t lru_rank;           /* 0 = front of VoxelMap::cache (most recently inserted-into) */
+} vmp_plane;
+
+/* counters of one map update: the terms of the algorithmic-byte model */
+typedef struct vmp_update_stats {
+    int64_t n_points;      /* points offered                              */
+    int64_t n_ins;         /* points appended to a filling voxel          */
+    int64_t n_touch;       /* distinct voxels touched                     */
+    int64_t n_created;     /* voxels created (incl. re-creations)         */
+    int64_t n_refit;       /* updatePlane() calls that reached the eigen solve */
+    int64_t refit_points;  /* sum over those of the number of stored points looped */
+    int64_t n_full;        /* points landing in full voxels (merge() or nothing)   */
+    int64_t n_mergeprobe;  /* merge() invocations                         */
+    int64_t n_merge;       /* successful pair merges                      */
+    int64_t n_evicted;     /* LRU victims                                 */
+    int64_t map_size;      /* live voxels afterwards                      */
+} vmp_update_stats;
+
+typedef struct vmp_scan_stats {
+    int32_t iters;              /* IEKF iterations executed (<= opti_max_iter)          */
+    int32_t effect_num[8];      /* valid correspondences per executed iteration         */
+    int32_t converged;          /* 1 if the loop left through the eps test (ieskf.cpp:148) */
+    vmp_update_stats map;
+    float   gpu_ms;             /* device time of the scan graph (CUDA events), 0 if not measured */
+} vmp_scan_stats;
+
+typedef struct vmp_handle_t* vmp_handle;
+
+/* thread-local description of the last failure */
+const char* vmp_last_error(void);
+/* library / build identification, e.g. "vmp_b200 0.1 sm_100a" */
+const char* vmp_version(void);
+
+/* lio::LIOConfig default member initialisers (lio_builder.h:19-41) */
+void vmp_config_default(vmp_config* cfg);
+
+/* LIOBuilder::loadConfig (lio_builder.cpp:5-26): builds the VoxelMap, sizes the residual buffer */
+int vmp_create(const vmp_config* cfg, vmp_handle* out);
+int vmp_destroy(vmp_handle h);
+
+/* VoxelMap::build (voxel_map.cpp:200-230).  pts_world N x 3, cov N x 9 (PointWithCov, voxel_map.h:36-41) */
+int vmp_map_build(vmp_handle h, const double* pts_world, const double* cov, int n, vmp_update_stats* stats);
+/* VoxelMap::update (voxel_map.cpp:232-256) */
+int vmp_map_update(vmp_handle h, const double* pts_world, const double* cov, int n, vmp_update_stats* stats);
+
+/* One call of the measurement plug-in kf::measure_func = LIOBuilder::sharedUpdateFunc
+ * (ieskf.h:74, lio_builder.cpp:250-311) on the scan last given to vmp_set_scan().
+ * P_prior is the full 23x23 kf.P(); only its [0:6,0:6] corner is read (lio_builder.cpp:266-267).
+ * H 12x12, b 12 as kf::SharedState (ieskf.h:22-29). */
+int vmp_measure(vmp_handle h, const vmp_state* x, const double* P_prior,
+                double* H, double* b, int* effect_num);
+
+/* lio_builder.cpp:224-229: copies the scan (N x 3 float32 lidar-frame xyz) into the
+ * persistent residual buffer and evaluates calcBodyCov (commons.cpp:18-45) per point. */
+int vmp_set_scan(vmp_handle h, const float* pts_lidar, int n);
+
+/* The whole timed region lio_builder.cpp:224-246 as ONE CUDA graph launch:
+ * set_scan + IESKF::update (ieskf.cpp:125-156, all iterations, measurement model
+ * on device) + lidarToWorld/pv_list (lio_builder.cpp:231-245) + VoxelMap::update.
+ * x / P: prior in, posterior out. */
+int vmp_scan(vmp_handle h, vmp_state* x_inout, double* P_inout,
+             const float* pts_lidar, int n, vmp_scan_stats* stats);
+
+/* Same work with the scan already resident in device memory (dev pointer to N x 3
+ * float32) and state/P kept on the device between calls: used for the
+ * "inputs resident in HBM" throughput figure.  x/P may be NULL to keep the
+ * device-resident state; when given they are uploaded before / downloaded after. */
+int vmp_scan_dev(vmp_handle h, const float* pts_lidar_dev, int n, vmp_scan_stats* stats);
+int vmp_set_state(vmp_handle h, const vmp_state* x, const double* P);
+int vmp_get_state(vmp_handle h, vmp_state* x, double* P);
+
+/* MAP_INIT branch, lio_builder.cpp:185-211: float32 world transform + covariances of
+ * the raw cloud with the current state/P, then VoxelMap::build. */
+int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P,
+                   const float* pts_lidar, int n, vmp_update_stats* stats);
+
+/* ---- observation / parity hooks ---- */
+/* ResidualData records after the last measure call: keys N x 3 (VoxelMap::index of
+ * point_world), status bit0 = voxel found, bit1 = is_plane, bit2 = is_valid (after Q2
+ * staleness), residual N, plane_norm N x 3. Any pointer may be NULL. */
+int vmp_dump_correspondences(vmp_handle h, int64_t* keys, uint8_t* status, double* residual, double* plane_norm, int n);
+/* pv_list of the last vmp_scan / vmp_first_scan: points N x 3 (float32 world widened), cov N x 9 */
+int vmp_dump_world_points(vmp_handle h, double* pts_world, double* cov, int n);
+/* All live voxels in LRU order (front first), as utils.cpp:161-195 walks map->cache. */
+int vmp_dump_map(vmp_handle h, vmp_plane* out, int cap, int* count);
+/* keys (M x 3) evicted by the last build/update/scan, in eviction order */
+int vmp_dump_evicted(vmp_handle h, int64_t* keys, int cap, int* count);
+int vmp_map_size(vmp_handle h, int* count);
+/* number of kernel launches (graph kernel nodes included) issued by this handle so far */
+int64_t vmp_launch_count(vmp_handle h);
+
+/* ---- host-side LIOBuilder (C++ class lio::LIOBuilder in vmp_lio.hpp) through C ---- */
+typedef struct vmp_lio_t* vmp_lio;
+typedef struct vmp_imu { double acc[3]; double gyro[3]; double timestamp; } vmp_imu;   /* lio::IMUData, commons.h:12-20 */
+/* LIOBuilder::loadConfig */
+int vmp_lio_create(const vmp_config* cfg, vmp_lio* out);
+int vmp_lio_destroy(vmp_lio l);
+/* LIOBuilder::process(SyncPackage&) (lio_builder.cpp:175-248). cloud: N x 4 float32
+ * (x,y,z,curvature[ms]); sorted and undistorted IN PLACE like the reference. */
+int vmp_lio_process(vmp_lio l, const vmp_imu* imus, int n_imu, float* cloud_xyzc, int n,
+                    double cloud_start_time, double cloud_end_time, vmp_scan_stats* stats);
+/* kf.x(), kf.P(), status (0 IMU_INIT, 1 MAP_INIT, 2 LIO_MAPPING) */
+int vmp_lio_state(vmp_lio l, vmp_state* x, double* P, int* status);
+/* the device handle behind builder->map */
+vmp_handle vmp_lio_map(vmp_lio l);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMP_B200_H */

@@ -1,0 +1,237 @@
+// oracle.h — TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+//
+// CPU restatement of the per-scan hot path of the reference's voxel_plus package,
+// written from scratch (the reference needs Eigen/Sophus/PCL/ROS, none of which exist
+// in this image, so it cannot be compiled here: SURVEY.md §8c).  PARITY UNPINNED: the
+// reference ships no tests / golden vectors; the evaluation order in this file and in
+// oracle_math.h is the definition the CUDA path is checked against.
+//
+// Data structures deliberately follow the reference (AoS records, std::unordered_map +
+// std::list LRU, shared_ptr voxels, serial point loop) so that this is also the honest
+// CPU timing baseline.  Behavioural quirks Q1..Q25 are replicated as
+// written.  Reference files followed (voxel_plus/src/map_builder/):
+//   commons.cpp:18-45, ieskf.h:22-110, ieskf.cpp:6-156, voxel_map.h:11-128,
+//   voxel_map.cpp:6-276, lio_builder.h:17-83, lio_builder.cpp:5-311
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <list>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+#include "oracle_math.h"
+
+namespace orc {
+
+// ------------------------------------------------------------------ ieskf.h / ieskf.cpp
+const double GRAVITY = 9.81;
+typedef Mat<3, 2> M32;
+typedef Mat<2, 3> M23x;
+typedef Mat<2, 1> V2;
+typedef Mat<24, 1> V24;
+typedef Mat<23, 12> M23x12;
+
+struct SharedState {          // ieskf.h:22-29
+    M12 H;
+    V12 b;
+    size_t iter_num = 0;
+};
+
+struct State {                // ieskf.h:31-62
+    V3 pos = V3::zero();
+    M3 rot = M3::identity();
+    M3 rot_ext = M3::identity();
+    V3 pos_ext = V3::zero();
+    V3 vel = V3::zero();
+    V3 bg = V3::zero();
+    V3 ba = V3::zero();
+    V3 g = v3(0.0, 0.0, -GRAVITY);
+
+    void initG(const V3& dir) { g = scale(normalized(dir), GRAVITY); }
+    void plus(const V23& delta);      // operator+=(Vector23d) ieskf.cpp:11-21
+    void plus24(const V24& delta);    // operator+=(Vector24d) ieskf.cpp:23-33
+    V23 minus(const State& other) const;  // operator-  ieskf.cpp:35-67
+    M32 getBx() const;                // ieskf.cpp:69-77
+    M32 getMx() const;                // ieskf.cpp:79-83
+    M32 getMx(const V2& res) const;   // ieskf.cpp:85-90
+    M23x getNx() const;               // ieskf.cpp:92-95
+};
+
+struct Input { V3 acc, gyro; };
+
+typedef std::function<void(State&, SharedState&)> measure_func;   // ieskf.h:74
+
+class IESKF {                 // ieskf.h:76-110
+public:
+    void setMaxIter(int m) { max_iter_ = m; }
+    State& x() { return x_; }
+    M23& P() { return P_; }
+    void set_share_function(measure_func f) { func_ = f; }
+    void predict(const Input& inp, double dt, const M12& Q);   // ieskf.cpp:101-123
+    void update();                                             // ieskf.cpp:125-156
+    // observation hooks (not in the reference)
+    int last_iters = 0;
+    bool last_converged = false;
+private:
+    size_t max_iter_ = 5;
+    double eps_ = 0.001;
+    State x_;
+    M23 P_ = M23::zero();
+    measure_func func_;
+    M23 H_;
+    V23 b_;
+};
+
+// ------------------------------------------------------------------ commons.h
+struct IMUData { V3 acc, gyro; double timestamp; };
+struct CloudPoint { float x, y, z, curvature; };   // the fields of pcl::PointXYZINormal the path reads
+struct Pose { double offset; V3 acc, gyro, vel, pos; M3 rot; };
+struct SyncPackage {
+    std::vector<IMUData> imus;
+    std::vector<CloudPoint> cloud;
+    double cloud_start_time = 0.0, cloud_end_time = 0.0;
+};
+void calcBodyCov(V3& pb, double range_inc, double degree_inc, M3& cov);   // commons.cpp:18-45
+
+// ------------------------------------------------------------------ voxel_map.h
+struct VoxelKey {             // voxel_map.h:17-34
+    int64_t x, y, z;
+    bool operator==(const VoxelKey& o) const { return x == o.x && y == o.y && z == o.z; }
+    struct Hasher {
+        int64_t operator()(const VoxelKey& k) const {
+            return ((((k.z) * 116101) % 10000000000LL + (k.y)) * 116101) % 10000000000LL + (k.x);
+        }
+    };
+};
+struct PointWithCov { V3 point; M3 cov; };    // voxel_map.h:36-41
+struct Plane {                                // voxel_map.h:43-51 (make_shared<Plane>() value-initialises cov -> 0, Q7)
+    V3 mean = V3::zero();
+    M3 ppt = M3::zero();
+    V3 norm = V3::zero();
+    M6 cov = M6::zero();
+    int n = 0;
+};
+struct ResidualData {                         // voxel_map.h:53-65
+    V3 point_lidar = V3::zero(), point_world = V3::zero(), plane_mean = V3::zero(), plane_norm = V3::zero();
+    M6 plane_cov = M6::zero();                // never assigned anywhere (Q1)
+    M3 cov_lidar = M3::zero(), cov_world = M3::zero();
+    bool is_valid = false;
+    double residual = 0.0;
+    // observation hooks (not in the reference): refreshed by every measurement pass
+    VoxelKey key{0, 0, 0};
+    uint8_t status = 0;                       // bit0 found, bit1 is_plane, bit2 is_valid
+};
+
+struct MapCounters {                          // terms of the algorithmic-byte model
+    int64_t n_points = 0, n_ins = 0, n_touch = 0, n_created = 0, n_refit = 0, refit_points = 0,
+            n_full = 0, n_mergeprobe = 0, n_merge = 0, n_evicted = 0;
+};
+
+class VoxelMap;
+class VoxelGrid {                             // voxel_map.h:69-103
+public:
+    VoxelGrid(int max_point_thresh, int update_point_thresh, double plane_thresh, VoxelKey position, VoxelMap* map);
+    void updatePlane();                       // voxel_map.cpp:97-136
+    void addToPlane(const PointWithCov& pv);  // voxel_map.cpp:29-34
+    void addPoint(const PointWithCov& pv);    // voxel_map.cpp:36-40
+    void pushPoint(const PointWithCov& pv);   // voxel_map.cpp:42-95
+    void merge();                             // voxel_map.cpp:138-186
+
+    int max_point_thresh, update_point_thresh;
+    double plane_thresh;
+    bool is_init, is_plane, update_enable;
+    int newly_add_point;
+    bool merged;
+    uint64_t group_id;
+    std::vector<PointWithCov> temp_points;
+    VoxelKey position;
+    VoxelMap* map;
+    std::shared_ptr<Plane> plane;
+    V3 center = V3::zero();
+    std::list<VoxelKey>::iterator cache_it;
+    uint64_t touch_epoch = 0;                 // instrumentation: last update() call that touched it
+};
+typedef std::unordered_map<VoxelKey, std::shared_ptr<VoxelGrid>, VoxelKey::Hasher> Featmap;
+
+class VoxelMap {                              // voxel_map.h:107-128
+public:
+    VoxelMap(int max_point_thresh, int update_point_thresh, double plane_thresh, double voxel_size, int capacity = 2000000);
+    VoxelKey index(const V3& point) const;    // voxel_map.cpp:194-198
+    void build(std::vector<PointWithCov>& pvs);    // voxel_map.cpp:200-230
+    void update(std::vector<PointWithCov>& pvs);   // voxel_map.cpp:232-256
+    bool buildResidual(ResidualData& data, std::shared_ptr<VoxelGrid> voxel_grid);   // voxel_map.cpp:258-276
+
+    int max_point_thresh, update_point_thresh;
+    double plane_thresh, voxel_size;
+    Featmap featmap;
+    std::list<VoxelKey> cache;
+    int capacity;
+    // per-map copies of what the reference keeps in process-wide statics (Q25)
+    uint64_t count = 0;
+    double merge_thresh_for_angle = 0.1, merge_thresh_for_distance = 0.04;
+    // instrumentation
+    MapCounters counters;
+    std::vector<VoxelKey> evicted;            // victims of the last build/update, in order
+    uint64_t epoch = 0;
+};
+
+// ------------------------------------------------------------------ lio_builder.h
+enum LIOStatus { IMU_INIT = 0, MAP_INIT = 1, LIO_MAPPING = 2 };
+struct LIOConfig {            // lio_builder.h:17-42
+    int opti_max_iter = 5;
+    double na = 0.01, ng = 0.01, nba = 0.0001, nbg = 0.0001;
+    int imu_init_num = 20;
+    M3 r_il = M3::identity();
+    V3 p_il = V3::zero();
+    bool gravity_align = true;
+    bool estimate_ext = false;
+    double scan_resolution = 0.1;
+    double voxel_size = 0.5;
+    int update_size_thresh = 10;
+    int max_point_thresh = 100;
+    double plane_thresh = 0.01;
+    double ranging_cov = 0.04, angle_cov = 0.1;
+    double merge_thresh_for_angle = 0.1, merge_thresh_for_distance = 0.04;
+    int map_capacity = 100000;
+    // deviation, stated: the reference hard-codes 10000 (lio_builder.cpp:25, Q3)
+    int max_points_per_scan = 10000;
+};
+struct LIODataGroup {         // lio_builder.h:43-54
+    IMUData last_imu;
+    std::vector<IMUData> imu_cache;
+    std::vector<Pose> imu_poses_cache;
+    V3 last_acc = V3::zero(), last_gyro = V3::zero();
+    double last_cloud_end_time = 0.0;
+    double gravity_norm = 0.0;
+    M12 Q = M12::identity();
+    std::vector<ResidualData> residual_info;
+};
+
+class LIOBuilder {            // lio_builder.h:56-83
+public:
+    void loadConfig(const LIOConfig& cfg);                 // lio_builder.cpp:5-26
+    bool initializeImu(std::vector<IMUData>& imus);        // lio_builder.cpp:28-63
+    void undistortCloud(SyncPackage& package);             // lio_builder.cpp:65-153
+    void process(SyncPackage& package);                    // lio_builder.cpp:175-248
+    void sharedUpdateFunc(State& state, SharedState& shared);   // lio_builder.cpp:250-311
+    std::vector<CloudPoint> lidarToWorld(const std::vector<CloudPoint>& cloud);   // lio_builder.cpp:155-163
+
+    // the pieces of process() the C ABI exposes separately
+    void firstScan(const std::vector<CloudPoint>& cloud);  // MAP_INIT body, lio_builder.cpp:188-208
+    void setScan(const std::vector<CloudPoint>& cloud);    // lio_builder.cpp:224-229 (lidar_cloud := cloud)
+    void hotPath();                                        // lio_builder.cpp:230-246 (needs setScan)
+
+    IESKF kf;
+    LIOConfig config;
+    LIODataGroup data_group;
+    LIOStatus status = IMU_INIT;
+    std::vector<CloudPoint> lidar_cloud;
+    std::shared_ptr<VoxelMap> map;
+    // observation hooks
+    std::vector<int> effect_nums;                 // per measurement call of the last update()
+    std::vector<PointWithCov> last_pv_list;       // what was handed to map->build / update
+    int omp_threads = 1;                          // MP_PROC_NUM (voxel_plus/CMakeLists.txt:15)
+};
+
+}  // namespace orc
