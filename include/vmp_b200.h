@@ -149,11 +149,12 @@ int vmp_set_scan(vmp_handle h, const float* pts_lidar, int n);
 int vmp_scan(vmp_handle h, vmp_state* x_inout, double* P_inout,
              const float* pts_lidar, int n, vmp_scan_stats* stats);
 
-/* Same work with the scan already resident in device memory (dev pointer to N x 3
- * float32) and state/P kept on the device between calls: used for the
- * "inputs resident in HBM" throughput figure.  x/P may be NULL to keep the
- * device-resident state; when given they are uploaded before / downloaded after. */
-int vmp_scan_dev(vmp_handle h, const float* pts_lidar_dev, int n, vmp_scan_stats* stats);
+/* Same work with every input already resident in device memory: pts_lidar_dev = device
+ * pointer to N x 3 float32; prior_dev = device pointer to 36 + 529 doubles (vmp_state
+ * followed by the 23x23 P), or NULL to continue from the state left on the device by the
+ * previous call.  The posterior stays on the device (read it with vmp_get_state).  Used
+ * for the "inputs resident in HBM" throughput figure. */
+int vmp_scan_dev(vmp_handle h, const float* pts_lidar_dev, const double* prior_dev, int n, vmp_scan_stats* stats);
 int vmp_set_state(vmp_handle h, const vmp_state* x, const double* P);
 int vmp_get_state(vmp_handle h, vmp_state* x, double* P);
 

@@ -589,6 +589,8 @@ std::vector<CloudPoint> LIOBuilder::lidarToWorld(const std::vector<CloudPoint>& 
 
 // MAP_INIT body, lio_builder.cpp:188-208
 void LIOBuilder::firstScan(const std::vector<CloudPoint>& cloud) {
+    prior_x = kf.x();
+    prior_P = kf.P();
     std::vector<CloudPoint> point_world = lidarToWorld(cloud);
     std::vector<PointWithCov> pv_list;
     pv_list.reserve(cloud.size());
@@ -628,6 +630,11 @@ void LIOBuilder::setScan(const std::vector<CloudPoint>& cloud) {
 void LIOBuilder::hotPath() {
     const int size = (int)lidar_cloud.size();
     effect_nums.clear();
+    iter_states.clear();
+    iter_H.clear();
+    iter_b.clear();
+    prior_x = kf.x();
+    prior_P = kf.P();
     kf.update();
     std::vector<CloudPoint> point_world = lidarToWorld(lidar_cloud);
     std::vector<PointWithCov> pv_list;
@@ -671,6 +678,7 @@ void LIOBuilder::process(SyncPackage& package) {
 
 // lio_builder.cpp:250-311
 void LIOBuilder::sharedUpdateFunc(State& state, SharedState& shared) {
+    iter_states.push_back(state);
     const M3 r_wl = mul(state.rot, state.rot_ext);
     const V3 p_wl = add(mul(state.rot, state.pos_ext), state.pos);
     const int size = (int)lidar_cloud.size();
@@ -728,6 +736,8 @@ void LIOBuilder::sharedUpdateFunc(State& state, SharedState& shared) {
         }
     }
     effect_nums.push_back(effect_num);
+    iter_H.push_back(shared.H);
+    iter_b.push_back(shared.b);
     if (effect_num < 1) std::fprintf(stderr, "NO EFFECTIVE POINT\n");
 }
 

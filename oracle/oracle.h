@@ -230,6 +230,11 @@ public:
     std::shared_ptr<VoxelMap> map;
     // observation hooks
     std::vector<int> effect_nums;                 // per measurement call of the last update()
+    std::vector<State> iter_states;               // state handed to each measurement call of the last update()
+    std::vector<M12> iter_H;                      // H / b returned by each measurement call of the last update()
+    std::vector<V12> iter_b;
+    State prior_x;                                // kf.x() / kf.P() right before the last hotPath()/firstScan()
+    M23 prior_P = M23::zero();
     std::vector<PointWithCov> last_pv_list;       // what was handed to map->build / update
     int omp_threads = 1;                          // MP_PROC_NUM (voxel_plus/CMakeLists.txt:15)
 };

@@ -253,6 +253,25 @@ int orc_lio_state(void* h, vmp_state* x, double* P, int* status) {
     return VMP_OK;
 }
 
+// prior of the last hotPath()/firstScan() and the state of measurement call k of the last update()
+int orc_get_prior(void* h, vmp_state* x, double* P) {
+    if (x) from_state(H(h)->lio.prior_x, x);
+    if (P) std::memcpy(P, H(h)->lio.prior_P.a, sizeof(double) * 529);
+    return VMP_OK;
+}
+int orc_get_iter_state(void* h, int k, vmp_state* x) {
+    if (k < 0 || (size_t)k >= H(h)->lio.iter_states.size()) return VMP_ERR_INVALID_ARG;
+    from_state(H(h)->lio.iter_states[k], x);
+    return VMP_OK;
+}
+
+int orc_get_iter_Hb(void* h, int k, double* Hout, double* bout) {
+    if (k < 0 || (size_t)k >= H(h)->lio.iter_H.size()) return VMP_ERR_INVALID_ARG;
+    std::memcpy(Hout, H(h)->lio.iter_H[k].a, sizeof(double) * 144);
+    std::memcpy(bout, H(h)->lio.iter_b[k].a, sizeof(double) * 12);
+    return VMP_OK;
+}
+
 // ---- small-math exports for unit tests against numpy ----
 void orc_eig3(const double* A, double* evals, double* evecs) {
     M3 a; std::memcpy(a.a, A, 72);

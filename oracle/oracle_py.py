@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
         _lib.orc_lio_state.argtypes = [C.c_void_p, C.POINTER(VmpState), dp, C.POINTER(C.c_int)]
         _lib.orc_map_update_timed.argtypes = [C.c_void_p, dp, dp, C.c_int, C.POINTER(VmpUpdateStats)]
         _lib.orc_map_update_timed.restype = C.c_double
+        _lib.orc_get_prior.argtypes = [C.c_void_p, C.POINTER(VmpState), dp]
+        _lib.orc_get_iter_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(VmpState)]
     return _lib
 
 
@@ -82,6 +84,26 @@ class Oracle(HotPath):
         s = C.c_int(0)
         self._lib.orc_lio_state(self._h, C.byref(x), dptr(P), C.byref(s))
         return x, P, s.value
+
+    def get_prior(self):
+        x = VmpState()
+        P = np.zeros((23, 23))
+        self._lib.orc_get_prior(self._h, C.byref(x), dptr(P))
+        return x, P
+
+    def get_iter_state(self, k: int):
+        x = VmpState()
+        if self._lib.orc_get_iter_state(self._h, k, C.byref(x)) != 0:
+            raise IndexError(k)
+        return x
+
+    def get_iter_Hb(self, k: int):
+        H = np.zeros((12, 12))
+        b = np.zeros(12)
+        self._lib.orc_get_iter_Hb.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        if self._lib.orc_get_iter_Hb(self._h, k, dptr(H), dptr(b)) != 0:
+            raise IndexError(k)
+        return H, b
 
     def predict(self, acc, gyro, dt):
         a = np.ascontiguousarray(acc, np.float64)

@@ -1,0 +1,78 @@
+"""Shared helpers of the parity tests: comparison of map dumps, synthetic map-update workloads."""
+from __future__ import annotations
+
+import numpy as np
+
+from voxelmapplus_fastlio2_b200.ctypes_defs import F_INIT, F_MERGED, F_PLANE, F_UPDATE_ENABLE  # noqa: F401
+
+
+def keyset(dump):
+    return {tuple(k) for k in dump["key"].tolist()}
+
+
+def sort_by_key(dump):
+    k = dump["key"]
+    order = np.lexsort((k[:, 2], k[:, 1], k[:, 0]))
+    return dump[order]
+
+
+def groups_partition(dump):
+    """group ids are arbitrary numbers (Q22): compare the partition they induce, keyed by voxel key."""
+    part = {}
+    for k, g in zip(dump["key"].tolist(), dump["group"].tolist()):
+        part.setdefault(g, []).append(tuple(k))
+    return sorted(sorted(v) for v in part.values())
+
+
+def assert_maps_equal(a, b, exact=True, rtol=1e-9, what=""):
+    """a, b: HotPath.dump_map() arrays (LRU order).  Tier 1: keys, LRU order, flags, counts bit-exact;
+    plane parameters bit-exact when `exact` (same inputs, same evaluation order) else within rtol."""
+    assert len(a) == len(b), f"{what}: map sizes differ {len(a)} vs {len(b)}"
+    assert np.array_equal(a["key"], b["key"]), f"{what}: keys / LRU order differ"
+    for f in ("n", "n_temp", "newly_add_point", "flags"):
+        if not np.array_equal(a[f], b[f]):
+            bad = np.nonzero(a[f] != b[f])[0][:5]
+            raise AssertionError(f"{what}: field {f} differs at {bad}: {a[f][bad]} vs {b[f][bad]} keys {a['key'][bad].tolist()}")
+    assert groups_partition(a) == groups_partition(b), f"{what}: group partition differs"
+    for f in ("mean", "ppt", "norm", "cov", "center"):
+        if exact:
+            if not np.array_equal(a[f], b[f]):
+                d = np.abs(a[f] - b[f]).reshape(len(a), -1).max(axis=1)
+                bad = np.argsort(-d)[:3]
+                raise AssertionError(f"{what}: field {f} not bit-exact, worst abs diff {d[bad]} at keys {a['key'][bad].tolist()} "
+                                     f"flags {a['flags'][bad]} n {a['n'][bad]}")
+        else:
+            np.testing.assert_allclose(a[f], b[f], rtol=rtol, atol=1e-12, err_msg=f"{what}: field {f}")
+
+
+def plane_cloud(rng, n, origin, u, v, extent, noise):
+    """n points on the rectangle origin + a u + b v, a,b in [0,extent), with gaussian noise along the normal."""
+    u = np.asarray(u, float); v = np.asarray(v, float)
+    nrm = np.cross(u, v); nrm /= np.linalg.norm(nrm)
+    a = rng.uniform(0, extent[0], n); b = rng.uniform(0, extent[1], n)
+    return np.asarray(origin, float) + a[:, None] * u + b[:, None] * v + rng.normal(0, noise, n)[:, None] * nrm
+
+
+def random_cov(rng, n, scale=1e-3):
+    """n mildly non-symmetric positive 3x3 matrices (pv.cov is not exactly symmetric in the reference either)."""
+    A = rng.normal(0, 1, (n, 3, 3))
+    S = np.einsum("nij,nkj->nik", A, A) * scale + np.eye(3) * scale
+    S[:, 0, 1] *= (1 + 1e-12)
+    return S.reshape(n, 9)
+
+
+def wall_workload(seed, scans=12, pts=1500, voxel=0.5):
+    """A few coplanar walls + clutter, revisited over several scans so that voxels fill, close and merge."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    out = []
+    for s in range(scans):
+        parts = [plane_cloud(rng, pts // 3, (0.1, 0.2, 0.0), (1, 0, 0), (0, 0, 1), (4.0, 2.0), 0.01),
+                 plane_cloud(rng, pts // 3, (0.0, 0.3, 0.1), (0, 1, 0), (0, 0, 1), (3.0, 2.0), 0.01),
+                 plane_cloud(rng, pts // 6, (0.2, 0.1, 0.02), (1, 0, 0), (0, 1, 0), (4.0, 3.0), 0.01),
+                 rng.uniform(-1, 5, (pts - pts // 3 * 2 - pts // 6, 3))]
+        p = np.concatenate(parts)
+        p = p[rng.permutation(len(p))]
+        # the reference inserts float32-rounded world points (Q15)
+        p = p.astype(np.float32).astype(np.float64)
+        out.append((p, random_cov(rng, len(p))))
+    return out

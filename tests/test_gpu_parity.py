@@ -1,0 +1,202 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tiers (BASELINE.json north_star):
+  1  voxel keys, point->plane correspondences (found / is_plane / is_valid), eviction sets,
+     map flags / counts / LRU order                                  -> bit-exact
+  2  residuals, H, b (fp64)                                          -> 1e-9 relative
+  3  trajectory over a run                                           -> 1 mm / 0.01 deg
+With teacher forcing (the oracle's point/cov lists handed to vmp_map_update) the plane
+parameters themselves are compared bit for bit as well.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_maps_equal, wall_workload
+from voxelmapplus_fastlio2_b200 import synth
+from voxelmapplus_fastlio2_b200.bindings import HotPath, VmpError
+from voxelmapplus_fastlio2_b200.ctypes_defs import default_config
+from voxelmapplus_fastlio2_b200.lio import LIOBuilder
+
+pytestmark = pytest.mark.gpu
+
+RTOL_T2 = 1e-9      # tier 2 tolerance (relative), stated by north_star
+
+
+def _pair(oracle_mod, **kw):
+    cfg = default_config(**kw)
+    return oracle_mod.Oracle(cfg), HotPath(cfg)
+
+
+# --------------------------------------------------------------------------- map update
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_map_update_bitexact_merge(oracle_mod, seed):
+    """fill -> refit cadence -> close -> merge (Q7-Q13), planes compared bit for bit."""
+    o, g = _pair(oracle_mod, max_point_thresh=30, update_size_thresh=5, map_capacity=100000, max_points_per_scan=4096)
+    work = wall_workload(seed)
+    merges = 0
+    for s, (p, c) in enumerate(work):
+        if s == 0:
+            so, sg = o.map_build(p, c), g.map_build(p, c)
+        else:
+            so, sg = o.map_update(p, c), g.map_update(p, c)
+        assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"
+        merges += so["n_merge"]
+        assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"seed {seed} scan {s}")
+    assert merges > 0, "workload did not exercise merge()"
+
+
+def test_map_update_default_thresholds(oracle_mod):
+    o, g = _pair(oracle_mod, max_points_per_scan=4096)
+    for s, (p, c) in enumerate(wall_workload(11, scans=25, pts=3000)):
+        so, sg = (o.map_update(p, c), g.map_update(p, c)) if s else (o.map_build(p, c), g.map_build(p, c))
+        assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"
+    assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what="default thresholds")
+
+
+def _moving_workload(seed, scans, pts):
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    out = []
+    for s in range(scans):
+        # a corridor that advances 1 m per scan: old voxels fall out of view and get evicted
+        x0 = 1.0 * s
+        p = np.concatenate([
+            np.stack([rng.uniform(x0, x0 + 6, pts // 2), rng.normal(0.25, 0.01, pts // 2), rng.uniform(0, 2, pts // 2)], 1),
+            np.stack([rng.uniform(x0, x0 + 6, pts // 2), rng.uniform(0, 3, pts // 2), rng.normal(0.1, 0.01, pts // 2)], 1)])
+        p = p[rng.permutation(len(p))].astype(np.float32).astype(np.float64)
+        c = np.tile((np.eye(3) * 1e-4).reshape(1, 9), (len(p), 1))
+        out.append((p, c))
+    return out
+
+
+def test_map_update_lru_eviction(oracle_mod):
+    """capacity smaller than the trajectory's voxel count: eviction order must be the reference's (Q17)."""
+    o, g = _pair(oracle_mod, max_point_thresh=20, update_size_thresh=5, map_capacity=400, max_points_per_scan=4096)
+    evicted_total = 0
+    for s, (p, c) in enumerate(_moving_workload(5, 40, 1200)):
+        so, sg = (o.map_update(p, c), g.map_update(p, c)) if s else (o.map_build(p, c), g.map_build(p, c))
+        assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"
+        eo, eg = o.dump_evicted(), g.dump_evicted()
+        assert np.array_equal(eo, eg), f"scan {s}: eviction order differs"
+        evicted_total += len(eo)
+        assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"eviction scan {s}")
+    assert evicted_total > 100
+
+
+def test_map_update_evict_and_recreate_same_scan(oracle_mod):
+    """a voxel that is the LRU victim early in a scan and is hit again later in the same scan."""
+    o, g = _pair(oracle_mod, max_point_thresh=20, update_size_thresh=5, map_capacity=60, max_points_per_scan=4096)
+    rng = np.random.Generator(np.random.Philox(key=9))
+    cov = lambda n: np.tile((np.eye(3) * 1e-4).reshape(1, 9), (n, 1))
+    # scan 0: 60 distinct voxels along x (fills the map exactly), oldest = voxel 0
+    p0 = np.stack([np.arange(60) * 0.5 + 0.25, np.full(60, 0.25), np.full(60, 0.25)], 1)
+    # scan 1: 10 new voxels first (evicting voxels 0..9), then points into voxels 3 and 5 again, then old ones
+    new = np.stack([np.arange(100, 110) * 0.5 + 0.25, np.full(10, 0.25), np.full(10, 0.25)], 1)
+    again = np.stack([np.array([3, 5, 3, 20, 21]) * 0.5 + 0.3, np.full(5, 0.3), np.full(5, 0.2)], 1)
+    p1 = np.concatenate([new, again, new + 0.01])
+    for s, p in enumerate([p0, p1, p0[::-1].copy(), rng.uniform(0, 30, (200, 3))]):
+        p = p.astype(np.float32).astype(np.float64)
+        so, sg = o.map_update(p, cov(len(p))), g.map_update(p, cov(len(p)))
+        assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"
+        assert np.array_equal(o.dump_evicted(), g.dump_evicted()), f"scan {s}: eviction order differs"
+        assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"recreate scan {s}")
+
+
+def test_capacity_smaller_than_scan_fails_loudly(oracle_mod):
+    """documented restriction: the LRU victim must not have been touched in the same scan."""
+    cfg = default_config(map_capacity=8, max_points_per_scan=1024)
+    g = HotPath(cfg)
+    p = np.stack([np.arange(64) * 0.5 + 0.25, np.zeros(64), np.zeros(64)], 1)
+    p = np.concatenate([p, p])
+    with pytest.raises(VmpError, match="map_capacity"):
+        g.map_update(p, np.tile(np.eye(3).reshape(1, 9) * 1e-4, (len(p), 1)))
+
+
+# --------------------------------------------------------------------------- measurement model + whole scan
+def _sequence(pts=3000, scans=14):
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=pts))
+    return list(seq.packages(scans))
+
+
+@pytest.mark.parametrize("estimate_ext", [0, 1])
+def test_measure_and_scan_teacher_forced(oracle_mod, estimate_ext):
+    """Every measurement pass of every scan replayed with the oracle's states: correspondences bit-exact,
+    H / b to 1e-9; map fed with the oracle's pv_list: bit-exact planes; vmp_scan posterior vs oracle."""
+    kw = dict(max_points_per_scan=4096, estimate_ext=estimate_ext)
+    cfg = default_config(**kw)
+    o = oracle_mod.Oracle(cfg)
+    g_tf = HotPath(cfg)          # teacher-forced: measure + map_update with the oracle's data
+    g_fr = HotPath(cfg)          # vmp_scan with the oracle's prior, its own posterior / map
+    checked_iters = 0
+    for pk in _sequence():
+        st = o.lio_process(pk.imus, pk.cloud, pk.t0, pk.t1)
+        x_post, P_post, status = o.lio_state()
+        if status == 1:
+            continue
+        xyz = np.ascontiguousarray(pk.cloud[:, :3])          # undistorted in place by the oracle
+        x0, P0 = o.get_prior()
+        if st.iters == 0:                                    # MAP_INIT scan
+            so = st.map
+            sg = g_tf.first_scan(x0, P0, xyz)
+            g_fr.first_scan(x0, P0, xyz)
+            assert sg["n_touch"] == so.n_touch and sg["n_refit"] == so.n_refit
+            pw_o, pc_o = o.dump_world_points()
+            pw_g, pc_g = g_tf.dump_world_points()
+            assert np.array_equal(pw_o, pw_g), "float32 world points differ"
+            assert np.array_equal(pc_o, pc_g), "world covariances differ"
+            assert_maps_equal(o.dump_map(), g_tf.dump_map(), exact=True, what="first scan")
+            continue
+        # --- teacher-forced measurement passes
+        g_tf.set_scan(xyz)
+        for k in range(st.iters):
+            xk = o.get_iter_state(k)
+            H, b, eff = g_tf.measure(xk, P0)
+            assert eff == st.effect_num[k], f"scan {pk.index} iter {k}: effect_num {eff} vs {st.effect_num[k]}"
+            Ho, bo = o.get_iter_Hb(k)            # what the oracle's sharedUpdateFunc returned for this pass
+            scale = np.abs(Ho).max()
+            assert np.abs(H - Ho).max() <= RTOL_T2 * scale, f"H differs: {np.abs(H - Ho).max() / scale:.3e}"
+            assert np.abs(b - bo).max() <= RTOL_T2 * max(np.abs(bo).max(), 1e-300), "b differs"
+            checked_iters += 1
+        # records after the last pass must agree with the oracle's records
+        co, cg = o.dump_correspondences(), g_tf.dump_correspondences()
+        assert np.array_equal(co["keys"], cg["keys"]), "voxel keys differ"
+        assert np.array_equal(co["status"], cg["status"]), "found/is_plane/is_valid differ"
+        v = (co["status"] & 4) != 0
+        np.testing.assert_allclose(cg["residual"][v], co["residual"][v], rtol=RTOL_T2, atol=1e-12)
+        assert np.array_equal(co["plane_norm"][v], cg["plane_norm"][v])
+        # --- teacher-forced map update
+        pw, pc = o.dump_world_points()
+        sg = g_tf.map_update(pw, pc)
+        for f in ("n_ins", "n_touch", "n_created", "n_refit", "refit_points", "n_full", "n_mergeprobe", "n_merge", "n_evicted", "map_size"):
+            assert sg[f] == getattr(st.map, f), f"scan {pk.index}: {f} {sg[f]} vs {getattr(st.map, f)}"
+        assert_maps_equal(o.dump_map(), g_tf.dump_map(), exact=True, what=f"scan {pk.index}")
+        # --- vmp_scan from the oracle's prior
+        xg, Pg, sgs = g_fr.scan(x0, P0, xyz)
+        assert sgs.iters == st.iters and list(sgs.effect_num[:st.iters]) == list(st.effect_num[:st.iters])
+        assert np.abs(np.array(xg.pos[:]) - np.array(x_post.pos[:])).max() < 1e-9
+        assert np.abs(np.array(xg.rot[:]) - np.array(x_post.rot[:])).max() < 1e-10
+        np.testing.assert_allclose(Pg, P_post, rtol=1e-6, atol=1e-12)
+    assert checked_iters > 15
+
+
+def test_lio_trajectory(oracle_mod):
+    """Tier 3: free-running estimators (host predict/undistort + device update) stay within 1 mm / 0.01 deg."""
+    cfg = default_config(max_points_per_scan=8192)
+    o = oracle_mod.Oracle(cfg)
+    b = LIOBuilder(cfg)
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=6000))
+    worst_p, worst_r = 0.0, 0.0
+    for pk in seq.packages(60):
+        c1, c2 = pk.cloud.copy(), pk.cloud.copy()
+        so = o.lio_process(pk.imus, c1, pk.t0, pk.t1)
+        sb = b.process(pk.imus, c2, pk.t0, pk.t1)
+        xo, Po, s1 = o.lio_state()
+        xb, Pb, s2 = b.state()
+        assert s1 == s2
+        assert np.array_equal(c1, c2), "undistorted clouds differ"
+        if s1 == 2 and so.iters:
+            assert sb.iters == so.iters
+            worst_p = max(worst_p, float(np.linalg.norm(np.array(xo.pos[:]) - np.array(xb.pos[:]))))
+            worst_r = max(worst_r, synth.rot_angle_deg(np.array(xo.rot[:]).reshape(3, 3), np.array(xb.rot[:]).reshape(3, 3)))
+    assert worst_p < 1e-3, f"trajectory deviates {worst_p} m"
+    assert worst_r < 1e-2, f"attitude deviates {worst_r} deg"
+    assert_maps_equal(o.dump_map(), b.map.dump_map(), exact=False, rtol=1e-6, what="free-running map")

@@ -87,7 +87,7 @@ class HotPath:
             f.restype = C.c_int
         if self._p == "vmp_":
             self._lib.vmp_last_error.restype = C.c_char_p
-            self._lib.vmp_scan_dev.argtypes = [vp, C.c_void_p, C.c_int, C.POINTER(VmpScanStats)]
+            self._lib.vmp_scan_dev.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(VmpScanStats)]
             self._lib.vmp_scan_dev.restype = C.c_int
             self._lib.vmp_launch_count.argtypes = [vp]
             self._lib.vmp_launch_count.restype = C.c_int64
@@ -210,11 +210,12 @@ class HotPath:
         return keys[:c.value].copy()
 
     # -- product-only ------------------------------------------------------------
-    def scan_dev(self, dev_ptr: int, n: int) -> VmpScanStats:
-        """vmp_scan_dev: scan already resident in HBM (device pointer to n x 3 float32)."""
+    def scan_dev(self, pts_dev_ptr: int, n: int, prior_dev_ptr: int | None = None) -> VmpScanStats:
+        """vmp_scan_dev: scan (n x 3 float32) and optionally the prior (36+529 float64) already resident in HBM."""
         st = VmpScanStats()
         self._n = n
-        self._check(self._lib.vmp_scan_dev(self._h, C.c_void_p(dev_ptr), n, C.byref(st)))
+        self._check(self._lib.vmp_scan_dev(self._h, C.c_void_p(pts_dev_ptr),
+                                           C.c_void_p(prior_dev_ptr) if prior_dev_ptr else None, n, C.byref(st)))
         return st
 
     def launch_count(self) -> int:

@@ -1,0 +1,584 @@
+// vmp_capi.cu — the C ABI of include/vmp_b200.h over the sm_100a kernels: handle
+// life-cycle, HBM allocation, per-scan CUDA graph, host<->device staging.
+//
+// One handle owns: the voxel map (DevMap), the persistent residual buffer (DevScan), the
+// filter (DevFilter), a control block (DevCtl), one stream and one instantiated CUDA graph
+// that contains every kernel of a scan: set_scan, update_begin, max_iter x (measure,
+// solve), world_points and the 17 map-update kernels.  Later IEKF iterations become
+// no-ops through the device-side `done` flag (ieskf.cpp:148 early break), so the graph
+// topology never changes and a scan is: 2 small H2D copies, 1 graph launch, 1 D2H copy.
+//
+// There is no CPU implementation behind this file: without a B200 every call fails.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/vmp_b200.h"
+#include "vmp_device.cuh"
+#include "vmp_kernels.h"
+#include "vmp_state.cuh"
+
+namespace vmp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// header uploaded per scan / result downloaded per scan (pinned on the host side)
+struct ScanIn { int n; int has_state; double x[36]; double P[529]; };
+struct ScanOut {
+    double x[36]; double P[529];
+    int iter, converged, effect[8], err, pad;
+    DevStats st;
+};
+
+__global__ void k_scan_in(const ScanIn* in, DevFilter* f, DevCtl* ctl) {
+    const int tid = threadIdx.x;
+    if (tid == 0) ctl->n = in->n;
+    if (in->has_state) {
+        for (int q = tid; q < 529; q += blockDim.x) f->P[q] = in->P[q];
+        if (tid < 36) f->x[tid] = in->x[tid];
+    }
+}
+__global__ void k_scan_out(const DevFilter* f, const DevCtl* ctl, ScanOut* out) {
+    const int tid = threadIdx.x;
+    for (int q = tid; q < 529; q += blockDim.x) out->P[q] = f->P[q];
+    if (tid < 36) out->x[tid] = f->x[tid];
+    if (tid < 8) out->effect[tid] = ctl->effect[tid];
+    if (tid == 0) { out->iter = ctl->iter; out->converged = ctl->converged; out->err = ctl->err; out->st = ctl->st; }
+}
+// H (12x12) / b (12) / effect of one measurement pass from the block partials (vmp_measure)
+__global__ void k_reduce_partials(const double* partials, int nblocks, int ext, double* out /*144+12+1*/) {
+    const int D = ext ? 12 : 6;
+    const int NH = D * (D + 1) / 2, NV = NH + D + 1;
+    __shared__ double v[96];
+    const int tid = threadIdx.x;
+    if (tid < NV) {
+        double t = partials[tid];
+        for (int b = 1; b < nblocks; b++) t += partials[(size_t)b * PARTIAL_STRIDE + tid];
+        v[tid] = t;
+    }
+    __syncthreads();
+    if (tid < 144) {
+        const int i = tid / 12, j = tid % 12;
+        double h = 0.0;
+        if (i < D && j < D) { const int a = i < j ? i : j, c = i < j ? j : i; h = v[a * D - a * (a - 1) / 2 + (c - a)]; }
+        out[tid] = h;
+    } else if (tid < 156) {
+        const int a = tid - 144;
+        out[tid] = a < D ? v[NH + a] : 0.0;
+    } else if (tid == 156) out[156] = v[NH + D];
+}
+__global__ void k_reset_iter(DevCtl* ctl) { ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
+
+}  // namespace vmp
+
+using namespace vmp;
+
+struct vmp_handle_t {
+    vmp_config cfg;
+    int device = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaGraphExec_t graph = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevMap m{};
+    DevScan s{};
+    DevFilter* f = nullptr;
+    DevCtl* ctl = nullptr;
+    double* partials = nullptr;
+    double* meas_out = nullptr;          // 157 doubles
+    ScanIn* d_in = nullptr;  ScanIn* h_in = nullptr;
+    ScanOut* d_out = nullptr; ScanOut* h_out = nullptr;
+    float* h_raw = nullptr;              // pinned staging for the scan
+    double* d_up = nullptr;              // staging for vmp_map_update uploads (reuses s.pw / s.pcov)
+    std::vector<void*> allocs;
+    int grid_pts = 148, grid_meas = 148;
+    int n_last = 0;
+    bool map_built = false;
+    int64_t launches = 0;
+    int graph_kernels = 0;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(vmp_handle_t* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e)); return VMP_ERR_CUDA; }
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return VMP_OK;
+}
+#define DALLOC(ptr, count) do { int _r = dalloc(h, &(ptr), (size_t)(count)); if (_r) return _r; } while (0)
+
+int check_device_err(vmp_handle_t* h, int err) {
+    if (!err) return VMP_OK;
+    set_error("device reported error bits 0x%x:%s%s%s%s%s%s", err,
+              (err & E_KEY_RANGE) ? " voxel coordinate outside +-2^20;" : "",
+              (err & E_POOL) ? " voxel slot pool exhausted;" : "",
+              (err & E_LRU_EXHAUSTED) ? " map_capacity smaller than the voxels one scan touches (LRU victim was touched in the same scan);" : "",
+              (err & E_REFIT_OVERFLOW) ? " refit of a voxel holding more than max_point_thresh points;" : "",
+              (err & E_QUEUE) ? " internal queue overflow;" : "",
+              (err & E_HASH_FULL) ? " hash table full;" : "");
+    (void)h;
+    return VMP_ERR_CAPACITY;
+}
+
+void fill_update_stats(const DevStats& d, vmp_update_stats* st) {
+    if (!st) return;
+    st->n_points = d.n_points; st->n_ins = d.n_ins; st->n_touch = d.n_touch; st->n_created = d.n_created;
+    st->n_refit = d.n_refit; st->refit_points = d.refit_points; st->n_full = d.n_full;
+    st->n_mergeprobe = d.n_mergeprobe; st->n_merge = d.n_merge; st->n_evicted = d.n_evicted; st->map_size = d.map_size;
+}
+
+// enqueue every kernel of one scan on h->stream (used both for graph capture and directly)
+int enqueue_scan(vmp_handle_t* h) {
+    cudaStream_t st = h->stream;
+    const bool ext = h->cfg.estimate_ext != 0;
+    int k = 0;
+    k_scan_in<<<1, 256, 0, st>>>(h->d_in, h->f, h->ctl); k++;
+    launch_set_scan(st, h->grid_pts, h->s, h->ctl); k++;
+    launch_update_begin(st, h->f, h->ctl); k++;
+    for (int it = 0; it < h->cfg.opti_max_iter; it++) {
+        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials); k++;
+        launch_solve(st, ext, h->f, h->ctl, h->partials, h->grid_meas); k++;
+    }
+    launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++;
+    k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false);
+    k_scan_out<<<1, 256, 0, st>>>(h->f, h->ctl, h->d_out); k++;
+    return k;
+}
+
+int build_graph(vmp_handle_t* h) {
+    cudaGraph_t g = nullptr;
+    VMP_CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->graph_kernels = enqueue_scan(h);
+    VMP_CUDA_CHECK(cudaStreamEndCapture(h->stream, &g));
+    VMP_CUDA_CHECK(cudaGraphInstantiate(&h->graph, g, 0));
+    VMP_CUDA_CHECK(cudaGraphDestroy(g));
+    return VMP_OK;
+}
+
+int finish_scan(vmp_handle_t* h, vmp_state* x, double* P, vmp_scan_stats* stats) {
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    const ScanOut& o = *h->h_out;
+    if (x) std::memcpy(x, o.x, sizeof(double) * 36);
+    if (P) std::memcpy(P, o.P, sizeof(double) * 529);
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->iters = o.iter; stats->converged = o.converged;
+        for (int i = 0; i < 8; i++) stats->effect_num[i] = o.effect[i];
+        fill_update_stats(o.st, &stats->map);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        stats->gpu_ms = ms;
+    }
+    return check_device_err(h, o.err);
+}
+
+template <typename T>
+int d2h(vmp_handle h, std::vector<T>& dst, const T* src, size_t count) {
+    dst.resize(count);
+    if (count == 0) return VMP_OK;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(dst.data(), src, sizeof(T) * count, cudaMemcpyDeviceToHost, h->stream));
+    return VMP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vmp_last_error(void) { return g_err; }
+const char* vmp_version(void) { return "vmp_b200 0.1 (sm_100a, fp64, -fmad=false)"; }
+
+void vmp_config_default(vmp_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->opti_max_iter = 5;
+    c->na = 0.01; c->ng = 0.01; c->nba = 0.0001; c->nbg = 0.0001;
+    c->imu_init_num = 20;
+    c->r_il[0] = c->r_il[4] = c->r_il[8] = 1.0;
+    c->gravity_align = 1; c->estimate_ext = 0;
+    c->scan_resolution = 0.1; c->voxel_size = 0.5;
+    c->update_size_thresh = 10; c->max_point_thresh = 100; c->plane_thresh = 0.01;
+    c->ranging_cov = 0.04; c->angle_cov = 0.1;
+    c->merge_thresh_for_angle = 0.1; c->merge_thresh_for_distance = 0.04;
+    c->map_capacity = 100000;
+    c->max_points_per_scan = 32768;
+    c->device = 0;
+}
+
+int vmp_create(const vmp_config* cfg, vmp_handle* out) {
+    if (!cfg || !out) { set_error("vmp_create: null argument"); return VMP_ERR_INVALID_ARG; }
+    if (cfg->max_points_per_scan < 1 || cfg->map_capacity < 1 || cfg->max_point_thresh < 1 || cfg->update_size_thresh < 1 ||
+        cfg->update_size_thresh > cfg->max_point_thresh || !(cfg->voxel_size > 0.0) || cfg->opti_max_iter < 1 || cfg->opti_max_iter > 8) {
+        set_error("vmp_create: invalid configuration (need max_points_per_scan>=1, map_capacity>=1, 1<=update_size_thresh<=max_point_thresh, voxel_size>0, 1<=opti_max_iter<=8)");
+        return VMP_ERR_INVALID_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        set_error("vmp_create: no CUDA device %d available (there is no CPU fallback)", cfg->device);
+        return VMP_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    VMP_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        set_error("vmp_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+        return VMP_ERR_NO_DEVICE;
+    }
+    VMP_CUDA_CHECK(cudaSetDevice(cfg->device));
+    vmp_handle_t* h = new vmp_handle_t();
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;       // so that a failed create can still be destroyed by the caller
+    VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    VMP_CUDA_CHECK(cudaEventCreate(&h->ev0));
+    VMP_CUDA_CHECK(cudaEventCreate(&h->ev1));
+
+    const int nmax = cfg->max_points_per_scan;
+    DevMap& m = h->m;
+    m.nmax = nmax;
+    m.pool = cfg->map_capacity + nmax + 1024;
+    m.maxpt = cfg->max_point_thresh; m.upt = cfg->update_size_thresh; m.capacity = cfg->map_capacity;
+    m.plane_thresh = cfg->plane_thresh; m.voxel_size = cfg->voxel_size;
+    m.th_angle = cfg->merge_thresh_for_angle; m.th_dist = cfg->merge_thresh_for_distance;
+    size_t hs = 1024;
+    while (hs < (size_t)m.pool * 4) hs <<= 1;
+    m.hmask = (unsigned)(hs - 1);
+    DALLOC(m.tkey, hs); DALLOC(m.tval, hs);
+    DALLOC(m.hot, (size_t)m.pool * 8); DALLOC(m.ppt, (size_t)m.pool * 6); DALLOC(m.cov, (size_t)m.pool * 36);
+    DALLOC(m.center, (size_t)m.pool * 3); DALLOC(m.tp, (size_t)m.pool * 12 * m.maxpt);
+    DALLOC(m.skey, m.pool); DALLOC(m.sgroup, m.pool); DALLOC(m.stamp, m.pool);
+    DALLOC(m.n_temp, m.pool); DALLOC(m.newly, m.pool); DALLOC(m.born_scan, m.pool); DALLOC(m.full_scan, m.pool); DALLOC(m.full_idx, m.pool);
+    DALLOC(m.cnt, m.pool); DALLOC(m.cursor, m.pool); DALLOC(m.ft, m.pool); DALLOC(m.lt, m.pool); DALLOC(m.seg_off, m.pool);
+    DALLOC(m.evict_t, m.pool); DALLOC(m.ghost, m.pool); DALLOC(m.evn, m.pool); DALLOC(m.free_slots, m.pool);
+    DALLOC(m.tpos, nmax); DALLOC(m.pslot, nmax); DALLOC(m.seg, nmax);
+    DALLOC(m.touched, nmax); DALLOC(m.hotlist, nmax); DALLOC(m.ev_slot, nmax); DALLOC(m.ev_time, nmax); DALLOC(m.ev_key, nmax);
+    DALLOC(m.ct, nmax); DALLOC(m.act_slot, nmax); DALLOC(m.act_t, nmax);
+    const int nblk = (nmax + PT_BLOCK - 1) / PT_BLOCK;
+    DALLOC(m.blk_last, nblk); DALLOC(m.blk_new, nblk);
+    m.log_cap = std::max<long long>(8ll * m.pool, 8ll * nmax + 4096);
+    for (int b = 0; b < 2; b++) { DALLOC(m.log_slot[b], m.log_cap); DALLOC(m.log_stamp[b], m.log_cap); }
+    DALLOC(m.log_blk, m.log_cap / 1024 + 2);
+
+    DevScan& s = h->s;
+    s.nmax = nmax;
+    DALLOC(s.pl, (size_t)3 * nmax); DALLOC(s.cl, (size_t)9 * nmax);
+    DALLOC(s.rnorm, (size_t)3 * nmax); DALLOC(s.rmean, (size_t)3 * nmax); DALLOC(s.rres, nmax);
+    DALLOC(s.rvalid, nmax); DALLOC(s.rstatus, nmax); DALLOC(s.rkey, nmax);
+    DALLOC(s.pw, (size_t)3 * nmax); DALLOC(s.pcov, (size_t)9 * nmax); DALLOC(s.raw, (size_t)3 * nmax);
+    s.range_var = cfg->ranging_cov * cfg->ranging_cov;
+    const double sn = sin(cfg->angle_cov * 0.017453293);      // PCL's DEG2RAD (commons.cpp:27-28)
+    s.sn2 = sn * sn;
+    // ResidualData() value-initialised by vector::resize (lio_builder.cpp:25)
+    VMP_CUDA_CHECK(cudaMemsetAsync(s.rnorm, 0, sizeof(double) * 3 * nmax, h->stream));
+    VMP_CUDA_CHECK(cudaMemsetAsync(s.rmean, 0, sizeof(double) * 3 * nmax, h->stream));
+    VMP_CUDA_CHECK(cudaMemsetAsync(s.rres, 0, sizeof(double) * nmax, h->stream));
+    VMP_CUDA_CHECK(cudaMemsetAsync(s.rvalid, 0, nmax, h->stream));
+    VMP_CUDA_CHECK(cudaMemsetAsync(s.rstatus, 0, nmax, h->stream));
+    VMP_CUDA_CHECK(cudaMemsetAsync(s.pl, 0, sizeof(double) * 3 * nmax, h->stream));
+    VMP_CUDA_CHECK(cudaMemsetAsync(s.cl, 0, sizeof(double) * 9 * nmax, h->stream));
+
+    DALLOC(h->f, 1); DALLOC(h->ctl, 1);
+    VMP_CUDA_CHECK(cudaMemsetAsync(h->f, 0, sizeof(DevFilter), h->stream));
+    VMP_CUDA_CHECK(cudaMemsetAsync(h->ctl, 0, sizeof(DevCtl), h->stream));
+    h->grid_pts = std::max(1, std::min(h->sm_count * 2, (nmax + 255) / 256));
+    h->grid_meas = std::max(1, std::min(h->sm_count * 2, (nmax + 255) / 256));
+    DALLOC(h->partials, (size_t)h->grid_meas * PARTIAL_STRIDE);
+    DALLOC(h->meas_out, 160);
+    DALLOC(h->d_in, 1); DALLOC(h->d_out, 1);
+    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_in, sizeof(ScanIn)));
+    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_out, sizeof(ScanOut)));
+    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_raw, sizeof(float) * 3 * nmax));
+    std::memset(h->h_in, 0, sizeof(ScanIn));
+
+    launch_map_init(h->stream, m, h->ctl);
+    h->launches += 1;
+    const int mi = cfg->opti_max_iter;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(&h->ctl->max_iter, &mi, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    int r = build_graph(h);
+    if (r) return r;
+    VMP_CUDA_CHECK(cudaGetLastError());
+    return VMP_OK;
+}
+
+int vmp_destroy(vmp_handle h) {
+    if (!h) return VMP_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->graph) cudaGraphExecDestroy(h->graph);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_raw) cudaFreeHost(h->h_raw);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return VMP_OK;
+}
+
+static int check_n(vmp_handle h, int n, const char* who) {
+    if (!h) { set_error("%s: null handle", who); return VMP_ERR_INVALID_ARG; }
+    if (n < 0 || n > h->cfg.max_points_per_scan) {
+        set_error("%s: n=%d outside [0, max_points_per_scan=%d]", who, n, h->cfg.max_points_per_scan);
+        return VMP_ERR_INVALID_ARG;
+    }
+    cudaSetDevice(h->device);
+    return VMP_OK;
+}
+
+static int upload_n(vmp_handle h, int n) {
+    VMP_CUDA_CHECK(cudaMemcpyAsync(&h->ctl->n, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->n_last = n;
+    return VMP_OK;
+}
+
+static int map_update_common(vmp_handle h, const double* pts, const double* cov, int n, vmp_update_stats* st, bool build) {
+    int r = check_n(h, n, build ? "vmp_map_build" : "vmp_map_update");
+    if (r) return r;
+    if (n > 0 && (!pts || !cov)) { set_error("vmp_map_update: null input"); return VMP_ERR_INVALID_ARG; }
+    if (build && h->map_built) { set_error("vmp_map_build: the map was already built"); return VMP_ERR_STATE; }
+    r = upload_n(h, n);
+    if (r) return r;
+    VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+    if (n > 0) {
+        VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.pw, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+        VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.pcov, cov, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build);
+    k_scan_out<<<1, 256, 0, h->stream>>>(h->f, h->ctl, h->d_out);
+    h->launches += 1;
+    h->map_built = true;
+    r = finish_scan(h, nullptr, nullptr, nullptr);
+    fill_update_stats(h->h_out->st, st);
+    return r;
+}
+
+int vmp_map_build(vmp_handle h, const double* pts, const double* cov, int n, vmp_update_stats* st) {
+    return map_update_common(h, pts, cov, n, st, true);
+}
+int vmp_map_update(vmp_handle h, const double* pts, const double* cov, int n, vmp_update_stats* st) {
+    return map_update_common(h, pts, cov, n, st, false);
+}
+
+int vmp_set_state(vmp_handle h, const vmp_state* x, const double* P) {
+    int r = check_n(h, 0, "vmp_set_state");
+    if (r) return r;
+    if (x) VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->x, x, sizeof(double) * 36, cudaMemcpyHostToDevice, h->stream));
+    if (P) VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, P, sizeof(double) * 529, cudaMemcpyHostToDevice, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return VMP_OK;
+}
+int vmp_get_state(vmp_handle h, vmp_state* x, double* P) {
+    int r = check_n(h, 0, "vmp_get_state");
+    if (r) return r;
+    if (x) VMP_CUDA_CHECK(cudaMemcpyAsync(x, h->f->x, sizeof(double) * 36, cudaMemcpyDeviceToHost, h->stream));
+    if (P) VMP_CUDA_CHECK(cudaMemcpyAsync(P, h->f->P, sizeof(double) * 529, cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return VMP_OK;
+}
+
+int vmp_set_scan(vmp_handle h, const float* pts, int n) {
+    int r = check_n(h, n, "vmp_set_scan");
+    if (r) return r;
+    if (n > 0 && !pts) { set_error("vmp_set_scan: null input"); return VMP_ERR_INVALID_ARG; }
+    r = upload_n(h, n);
+    if (r) return r;
+    if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    launch_set_scan(h->stream, h->grid_pts, h->s, h->ctl);
+    h->launches += 1;
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return VMP_OK;
+}
+
+int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, double* b, int* effect_num) {
+    int r = check_n(h, 0, "vmp_measure");
+    if (r) return r;
+    if (!x || !P) { set_error("vmp_measure: null state"); return VMP_ERR_INVALID_ARG; }
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->x, x, sizeof(double) * 36, cudaMemcpyHostToDevice, h->stream));
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, P, sizeof(double) * 529, cudaMemcpyHostToDevice, h->stream));
+    k_reset_iter<<<1, 1, 0, h->stream>>>(h->ctl);
+    const bool ext = h->cfg.estimate_ext != 0;
+    launch_measure(h->stream, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials);
+    k_reduce_partials<<<1, 160, 0, h->stream>>>(h->partials, h->grid_meas, ext ? 1 : 0, h->meas_out);
+    h->launches += 3;
+    double out[157];
+    VMP_CUDA_CHECK(cudaMemcpyAsync(out, h->meas_out, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (H) std::memcpy(H, out, sizeof(double) * 144);
+    if (b) std::memcpy(b, out + 144, sizeof(double) * 12);
+    if (effect_num) *effect_num = (int)out[156];
+    return VMP_OK;
+}
+
+int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp_scan_stats* stats) {
+    int r = check_n(h, n, "vmp_scan");
+    if (r) return r;
+    if (!x || !P || (n > 0 && !pts)) { set_error("vmp_scan: null argument"); return VMP_ERR_INVALID_ARG; }
+    if (!h->map_built) { set_error("vmp_scan: no map yet (call vmp_first_scan or vmp_map_build first)"); return VMP_ERR_STATE; }
+    // stage through pinned memory so that both copies are truly asynchronous
+    std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);
+    h->h_in->n = n; h->h_in->has_state = 1;
+    std::memcpy(h->h_in->x, x, sizeof(double) * 36);
+    std::memcpy(h->h_in->P, P, sizeof(double) * 529);
+    VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+    if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, h->h_raw, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_in, h->h_in, sizeof(ScanIn), cudaMemcpyHostToDevice, h->stream));
+    VMP_CUDA_CHECK(cudaGraphLaunch(h->graph, h->stream));
+    h->launches += h->graph_kernels;
+    h->n_last = n;
+    return finish_scan(h, x, P, stats);
+}
+
+int vmp_scan_dev(vmp_handle h, const float* pts_dev, const double* prior_dev, int n, vmp_scan_stats* stats) {
+    int r = check_n(h, n, "vmp_scan_dev");
+    if (r) return r;
+    if (!h->map_built) { set_error("vmp_scan_dev: no map yet"); return VMP_ERR_STATE; }
+    h->h_in->n = n; h->h_in->has_state = 0;
+    VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+    if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts_dev, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, h->stream));
+    if (prior_dev) {
+        VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->x, prior_dev, sizeof(double) * 36, cudaMemcpyDeviceToDevice, h->stream));
+        VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, prior_dev + 36, sizeof(double) * 529, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_in, h->h_in, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    VMP_CUDA_CHECK(cudaGraphLaunch(h->graph, h->stream));
+    h->launches += h->graph_kernels;
+    h->n_last = n;
+    return finish_scan(h, nullptr, nullptr, stats);
+}
+
+int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const float* pts, int n, vmp_update_stats* st) {
+    int r = check_n(h, n, "vmp_first_scan");
+    if (r) return r;
+    if (!x || !P || (n > 0 && !pts)) { set_error("vmp_first_scan: null argument"); return VMP_ERR_INVALID_ARG; }
+    if (h->map_built) { set_error("vmp_first_scan: the map was already built"); return VMP_ERR_STATE; }
+    r = upload_n(h, n);
+    if (r) return r;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->x, x, sizeof(double) * 36, cudaMemcpyHostToDevice, h->stream));
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, P, sizeof(double) * 529, cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+    launch_world_points(h->stream, h->grid_pts, h->s, h->f, h->ctl, 1);
+    h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true);
+    k_scan_out<<<1, 256, 0, h->stream>>>(h->f, h->ctl, h->d_out);
+    h->launches += 1;
+    h->map_built = true;
+    r = finish_scan(h, nullptr, nullptr, nullptr);
+    fill_update_stats(h->h_out->st, st);
+    return r;
+}
+
+// ---------------------------------------------------------------- observation hooks
+int vmp_dump_correspondences(vmp_handle h, int64_t* keys, uint8_t* status, double* residual, double* plane_norm, int n) {
+    int r = check_n(h, n, "vmp_dump_correspondences");
+    if (r) return r;
+    const size_t NM = (size_t)h->s.nmax;
+    std::vector<unsigned long long> k; std::vector<uint8_t> s; std::vector<double> res, nx, ny, nz;
+    if ((r = d2h(h, k, h->s.rkey, n)) || (r = d2h(h, s, h->s.rstatus, n)) || (r = d2h(h, res, h->s.rres, n)) ||
+        (r = d2h(h, nx, h->s.rnorm, n)) || (r = d2h(h, ny, h->s.rnorm + NM, n)) || (r = d2h(h, nz, h->s.rnorm + 2 * NM, n))) return r;
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; i++) {
+        if (keys) {
+            long long x = 0, y = 0, z = 0;
+            if (k[i] != KEY_EMPTY) unpack_key(k[i], x, y, z);
+            keys[3 * i] = x; keys[3 * i + 1] = y; keys[3 * i + 2] = z;
+        }
+        if (status) status[i] = s[i];
+        if (residual) residual[i] = res[i];
+        if (plane_norm) { plane_norm[3 * i] = nx[i]; plane_norm[3 * i + 1] = ny[i]; plane_norm[3 * i + 2] = nz[i]; }
+    }
+    return VMP_OK;
+}
+
+int vmp_dump_world_points(vmp_handle h, double* pts, double* cov, int n) {
+    int r = check_n(h, n, "vmp_dump_world_points");
+    if (r) return r;
+    if (pts && n) VMP_CUDA_CHECK(cudaMemcpyAsync(pts, h->s.pw, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (cov && n) VMP_CUDA_CHECK(cudaMemcpyAsync(cov, h->s.pcov, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return VMP_OK;
+}
+
+int vmp_map_size(vmp_handle h, int* count) {
+    int r = check_n(h, 0, "vmp_map_size");
+    if (r) return r;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(count, &h->ctl->n_live, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return VMP_OK;
+}
+
+int vmp_dump_map(vmp_handle h, vmp_plane* out, int cap, int* count) {
+    int r = check_n(h, 0, "vmp_dump_map");
+    if (r) return r;
+    const DevMap& m = h->m;
+    const size_t P = (size_t)m.pool;
+    std::vector<unsigned long long> stamp, skey, sgroup;
+    std::vector<double> hot, ppt, cov, center;
+    std::vector<int> n_temp, newly;
+    if ((r = d2h(h, stamp, m.stamp, P)) || (r = d2h(h, skey, m.skey, P)) || (r = d2h(h, sgroup, m.sgroup, P)) ||
+        (r = d2h(h, hot, m.hot, P * 8)) || (r = d2h(h, ppt, m.ppt, P * 6)) || (r = d2h(h, cov, m.cov, P * 36)) ||
+        (r = d2h(h, center, m.center, P * 3)) || (r = d2h(h, n_temp, m.n_temp, P)) || (r = d2h(h, newly, m.newly, P))) return r;
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    std::vector<int> live;
+    for (size_t s = 0; s < P; s++) if (stamp[s] != 0) live.push_back((int)s);
+    std::sort(live.begin(), live.end(), [&](int a, int b) { return stamp[a] > stamp[b]; });   // front of cache = most recent
+    if (count) *count = (int)live.size();
+    for (size_t i = 0; i < live.size() && (int)i < cap; i++) {
+        const int s = live[i];
+        vmp_plane& p = out[i];
+        std::memset(&p, 0, sizeof(p));
+        long long x, y, z;
+        unpack_key(skey[s], x, y, z);
+        p.key[0] = x; p.key[1] = y; p.key[2] = z;
+        const double* hr = &hot[(size_t)s * 8];
+        for (int k = 0; k < 3; k++) { p.mean[k] = hr[k]; p.norm[k] = hr[3 + k]; p.center[k] = center[(size_t)s * 3 + k]; }
+        const double* pp = &ppt[(size_t)s * 6];
+        p.ppt[0] = pp[0]; p.ppt[1] = pp[1]; p.ppt[2] = pp[3]; p.ppt[3] = pp[1]; p.ppt[4] = pp[2]; p.ppt[5] = pp[4];
+        p.ppt[6] = pp[3]; p.ppt[7] = pp[4]; p.ppt[8] = pp[5];
+        std::memcpy(p.cov, &cov[(size_t)s * 36], sizeof(double) * 36);
+        long long w;
+        std::memcpy(&w, &hr[6], 8);
+        p.flags = (uint32_t)(w & 0xFFFFFFFFll);
+        p.n = (int32_t)(w >> 32);
+        p.n_temp = n_temp[s]; p.newly_add_point = newly[s];
+        p.group = sgroup[s];
+        p.lru_rank = i;
+    }
+    return VMP_OK;
+}
+
+int vmp_dump_evicted(vmp_handle h, int64_t* keys, int cap, int* count) {
+    int r = check_n(h, 0, "vmp_dump_evicted");
+    if (r) return r;
+    int ne = 0;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(&ne, &h->ctl->n_evict, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    std::vector<unsigned long long> k;
+    if ((r = d2h(h, k, h->m.ev_key, ne))) return r;
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < ne && i < cap; i++) {
+        long long x, y, z;
+        unpack_key(k[i], x, y, z);
+        keys[3 * i] = x; keys[3 * i + 1] = y; keys[3 * i + 2] = z;
+    }
+    if (count) *count = ne;
+    return VMP_OK;
+}
+
+int64_t vmp_launch_count(vmp_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// vmp_device.cuh — device-resident data layout of one trajectory (map + filter + scan).
+//
+// Everything lives in HBM for the lifetime of the handle; nothing is re-uploaded per
+// scan except the raw scan (N x 12 B) and, when the caller keeps the filter on the host,
+// the state/P (4.5 KB).  Layout:
+//
+//   voxel hash      open addressing, linear probing; tkey[] packed 3x21-bit voxel
+//                   coordinate (uint64), tval[] slot id.  Replaces
+//                   std::unordered_map<VoxelKey, shared_ptr<VoxelGrid>> (voxel_map.h:105).
+//   voxel slots     SoA indexed by slot id (pool = map_capacity + max_points_per_scan + slack):
+//                     hot[slot][8]   64-byte record {mean xyz, norm xyz, (flags,n), pad}: the
+//                                    only thing the IEKF measurement kernel gathers per point
+//                     ppt[slot][6]   sum p p^T (exactly symmetric -> 6 values)
+//                     cov[slot][36]  Plane::cov (6x6, accumulated, not exactly symmetric)
+//                     tp[slot][12][MAXPT] stored points of a filling voxel, component-major
+//                     skey, sgroup, stamp (LRU), n_temp, newly, born/full bookkeeping
+//   per-scan scratch  cnt/cursor/ft/lt/seg_off per slot, tpos/pslot/seg per point
+//   LRU log         append-only (slot, stamp) pairs in last-touch order with lazy deletion;
+//                   replaces std::list<VoxelKey> cache (voxel_map.h:126)
+//   scan buffers    persistent lio::ResidualData (voxel_map.h:53-65) as SoA
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+#include "vmp_math.cuh"
+
+namespace vmp {
+
+// ---- flags (same bit values as VMP_F_* in include/vmp_b200.h) ----
+constexpr uint32_t F_INIT = 1u, F_PLANE = 2u, F_UE = 4u, F_MERGED = 8u;
+
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned long long KEY_TOMB = 0xFFFFFFFFFFFFFFFEull;
+constexpr int T_INF = INT_MAX;          // "never" for per-scan times (point indices)
+constexpr unsigned SCAN_NEVER = 0xFFFFFFFFu;
+
+// error bits reported through DevCtl::err
+constexpr int E_KEY_RANGE = 1;          // voxel coordinate outside +-2^20
+constexpr int E_POOL = 2;               // slot pool exhausted
+constexpr int E_LRU_EXHAUSTED = 4;      // eviction would have to take a voxel touched in the same scan
+constexpr int E_REFIT_OVERFLOW = 8;     // refit of a voxel holding more than max_point_thresh points (build overflow + thresh 1)
+constexpr int E_QUEUE = 16;             // internal queue overflow in the serial merge / eviction kernels
+constexpr int E_HASH_FULL = 32;
+
+struct DevStats {                       // == vmp_update_stats order
+    long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size;
+};
+
+struct DevCtl {
+    // scan
+    int n;                              // points in the current scan
+    unsigned scan_id;                   // increments per map update
+    unsigned long long stamp_base;      // stamp of point i of this scan = stamp_base + i (>= 1)
+    // map bookkeeping
+    int n_live;                         // live voxels
+    int n_touched, n_new, n_evict, n_hot, n_ghost;
+    int free_top;                       // free-slot stack height
+    int tombstones;
+    int need_rehash;
+    int need_log_compact;
+    int log_sel;                        // which of the two log buffers is current
+    long long log_head, log_tail;       // positions in the current log buffer
+    unsigned long long group_counter;
+    int err;
+    int pad0;
+    DevStats st;
+    // IEKF
+    int iter;                           // executed iterations
+    int done;                           // loop left (eps test or max_iter)
+    int converged;
+    int effect[8];
+    int max_iter;
+};
+
+struct DevFilter {
+    double x[36];                       // vmp_state layout: pos3 rot9 rot_ext9 pos_ext3 vel3 bg3 ba3 g3
+    double xpred[36];
+    double P[529];
+    double Pinv[529];
+};
+
+struct DevMap {
+    // hash
+    unsigned long long* tkey;
+    int* tval;
+    unsigned hmask;
+    // parameters
+    int pool, maxpt, upt, capacity;
+    double plane_thresh, voxel_size, th_angle, th_dist;
+    // slots
+    double* hot;                        // [pool][8]
+    double* ppt;                        // [pool][6]
+    double* cov;                        // [pool][36]
+    double* center;                     // [pool][3]
+    double* tp;                         // [pool][12][maxpt]
+    unsigned long long* skey;
+    unsigned long long* sgroup;
+    unsigned long long* stamp;
+    int* n_temp;
+    int* newly;
+    unsigned* born_scan;
+    unsigned* full_scan;
+    int* full_idx;
+    // per-slot per-scan scratch
+    int* cnt; int* cursor; int* ft; int* lt; int* seg_off; int* evict_t; int* ghost; int* evn;
+    // free list
+    int* free_slots;
+    // per-point per-scan
+    unsigned* tpos; int* pslot; int* seg;
+    // lists
+    int* touched;                       // [nmax]
+    int* hotlist;                       // [nmax]
+    int* ev_slot; int* ev_time; unsigned long long* ev_key;   // eviction list [nmax]
+    int* ct;                            // creation times (sorted) [nmax]
+    int* blk_last; int* blk_new;        // per 1024-point block counts
+    int* act_slot; int* act_t;          // serial merge active set [nmax]
+    // LRU log (two buffers for compaction)
+    int* log_slot[2];
+    unsigned long long* log_stamp[2];
+    long long log_cap;
+    int* log_blk;                       // block counts for compaction
+    int nmax;
+};
+
+struct DevScan {                        // persistent residual buffer, SoA over point index
+    int nmax;
+    double* pl;                         // [3][nmax] point_lidar (after calcBodyCov's z edit)
+    double* cl;                         // [9][nmax] cov_lidar
+    double* rnorm;                      // [3][nmax] plane_norm (persistent, Q2)
+    double* rmean;                      // [3][nmax] plane_mean
+    double* rres;                       // [nmax] residual
+    uint8_t* rvalid;                    // [nmax] is_valid
+    uint8_t* rstatus;                   // [nmax] bit0 found bit1 plane bit2 valid
+    unsigned long long* rkey;           // [nmax] packed key of point_world
+    double* pw;                         // [nmax][3] pv.point  (float32 world widened), AoS: gathered per voxel
+    double* pcov;                       // [nmax][9] pv.cov
+    float* raw;                         // [nmax][3] staged raw scan
+    double range_var, sn2;
+};
+
+// ---- key packing / hashing -----------------------------------------------------------
+__host__ __device__ __forceinline__ bool key_in_range(long long k) { return k >= -(1ll << 20) && k < (1ll << 20); }
+__host__ __device__ __forceinline__ unsigned long long pack_key(long long x, long long y, long long z) {
+    return ((unsigned long long)(x + (1ll << 20)) << 42) | ((unsigned long long)(y + (1ll << 20)) << 21) |
+           (unsigned long long)(z + (1ll << 20));
+}
+__host__ __device__ __forceinline__ void unpack_key(unsigned long long k, long long& x, long long& y, long long& z) {
+    x = (long long)((k >> 42) & 0x1FFFFF) - (1ll << 20);
+    y = (long long)((k >> 21) & 0x1FFFFF) - (1ll << 20);
+    z = (long long)(k & 0x1FFFFF) - (1ll << 20);
+}
+// any hash is allowed: bucket order is never observable in the reference
+__host__ __device__ __forceinline__ unsigned hash_key(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (unsigned)k;
+}
+
+// VoxelMap::index (voxel_map.cpp:194-198): true division, floor, cast
+__device__ __forceinline__ bool voxel_index(double x, double y, double z, double vs, unsigned long long& pk) {
+    const long long kx = (long long)floor(x / vs), ky = (long long)floor(y / vs), kz = (long long)floor(z / vs);
+    if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) { pk = KEY_EMPTY; return false; }
+    pk = pack_key(kx, ky, kz);
+    return true;
+}
+
+// featmap.find(k): slot id or -1
+__device__ __forceinline__ int hash_find(const DevMap& m, unsigned long long pk) {
+    unsigned h = hash_key(pk) & m.hmask;
+    for (unsigned probe = 0; probe <= m.hmask; probe++) {
+        const unsigned long long cur = m.tkey[h];
+        if (cur == pk) return m.tval[h];
+        if (cur == KEY_EMPTY) return -1;
+        h = (h + 1) & m.hmask;
+    }
+    return -1;
+}
+
+// hot record access
+__device__ __forceinline__ void hot_get_fn(const double* hot, int slot, uint32_t& flags, int& n) {
+    const long long w = __double_as_longlong(hot[(size_t)slot * 8 + 6]);
+    flags = (uint32_t)(w & 0xFFFFFFFFll);
+    n = (int)(w >> 32);
+}
+__device__ __forceinline__ void hot_set_fn(double* hot, int slot, uint32_t flags, int n) {
+    const long long w = ((long long)n << 32) | (long long)flags;
+    hot[(size_t)slot * 8 + 6] = __longlong_as_double(w);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#define VMP_CUDA_CHECK(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) { vmp::set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); return VMP_ERR_CUDA; } \
+    } while (0)
+
+void set_error(const char* fmt, ...);
+
+}  // namespace vmp

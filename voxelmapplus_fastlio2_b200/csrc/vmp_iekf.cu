@@ -1,0 +1,389 @@
+// vmp_iekf.cu — IEKF measurement update on the device (sm_100a, fp64, no FMA contraction).
+//
+//   k_set_scan      lio_builder.cpp:224-229 + calcBodyCov (commons.cpp:18-45)
+//   k_measure       LIOBuilder::sharedUpdateFunc (lio_builder.cpp:250-311) +
+//                   VoxelMap::index / featmap.find / buildResidual (voxel_map.cpp:194-198,258-276):
+//                   one thread per point, gather through the voxel hash, warp-shuffle ->
+//                   shared-memory block reduction -> per-block partials (no fp atomics)
+//   k_ieskf_solve   IESKF::update body (ieskf.cpp:134-155): fixed-order final reduction of
+//                   the partials, 23x23 LU inverses, boxplus / boxminus, convergence flag,
+//                   posterior covariance — one CTA, every 23x23 product one thread per entry
+//   k_world_points  lidarToWorld + pv_list loop (lio_builder.cpp:155-163, 231-245)
+//
+// Why no tensor cores: per point this is a 64-byte gather and ~1 kflop of 3x3 fp64
+// algebra followed by a 27-value reduction; there is no dense contraction to tile.
+#include "vmp_device.cuh"
+#include "vmp_kernels.h"
+#include "vmp_state.cuh"
+
+namespace vmp {
+
+// ---------------------------------------------------------------------------- K0
+__global__ void __launch_bounds__(256) k_set_scan(DevScan s, const DevCtl* __restrict__ ctl) {
+    const int n = ctl->n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 p = v3((double)s.raw[3 * i], (double)s.raw[3 * i + 1], (double)s.raw[3 * i + 2]);
+        M3 c;
+        calc_body_cov(p, s.range_var, s.sn2, c);
+#pragma unroll
+        for (int k = 0; k < 3; k++) s.pl[(size_t)k * s.nmax + i] = p[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) s.cl[(size_t)k * s.nmax + i] = c.a[k];
+    }
+}
+
+// ---------------------------------------------------------------------------- K1
+struct MeasState {
+    M3 r_wl, R, Rext, Prr, Ppp;
+    V3 p_wl, pext;
+};
+
+template <bool EXT>
+__global__ void __launch_bounds__(EXT ? 128 : 256)
+k_measure(DevMap m, DevScan s, const DevFilter* __restrict__ f, DevCtl* ctl, double* __restrict__ partials) {
+    constexpr int D = EXT ? 12 : 6;
+    constexpr int NH = D * (D + 1) / 2;
+    constexpr int NV = NH + D + 1;                 // upper triangle of H, b, effect count
+    __shared__ MeasState ms;
+    __shared__ double red[8][NV];
+    if (ctl->done) return;
+    if (threadIdx.x == 0) {
+        const St x = st_load(f->x);
+        ms.R = x.rot; ms.Rext = x.rot_ext; ms.pext = x.pos_ext;
+        ms.r_wl = mul(x.rot, x.rot_ext);
+        ms.p_wl = add(mul(x.rot, x.pos_ext), x.pos);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) { ms.Prr(i, j) = f->P[(3 + i) * 23 + 3 + j]; ms.Ppp(i, j) = f->P[i * 23 + j]; }
+    }
+    __syncthreads();
+    const M3 r_wl = ms.r_wl;
+    const V3 p_wl = ms.p_wl;
+    const int n = ctl->n;
+    const size_t NM = (size_t)s.nmax;
+
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) acc[v] = 0.0;
+
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const V3 pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
+        const V3 pw = add(mul(r_wl, pl), p_wl);
+        unsigned long long pk;
+        int slot = -1;
+        if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk)) slot = hash_find(m, pk);
+        M3 cl;
+        bool have_cl = false;
+        bool valid;
+        V3 nrm;
+        double res;
+        uint8_t status = 0;
+        if (slot >= 0) {
+            status = 1;
+            valid = false;
+            const double* h = m.hot + (size_t)slot * 8;
+            uint32_t flags; int nn;
+            hot_get_fn(m.hot, slot, flags, nn);
+            if (flags & F_PLANE) {
+                status |= 2;
+                const V3 mean = v3(h[0], h[1], h[2]);
+                nrm = v3(h[3], h[4], h[5]);
+                const V3 p2m = sub(pw, mean);
+                res = dot(nrm, p2m);
+#pragma unroll
+                for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
+                have_cl = true;
+                const M3 cw = world_cov(r_wl, cl, pl, ms.Prr, ms.Ppp);
+                // sigma_l = J_nq plane_cov J_nq^T (plane_cov is never assigned -> 0, Q1) + n^T C_w n
+                const double sigma = mul(mul(tr(nrm), cw), nrm)[0];
+                valid = fabs(res) < 3.0 * sqrt(sigma);
+#pragma unroll
+                for (int k = 0; k < 3; k++) { s.rnorm[(size_t)k * NM + i] = nrm[k]; s.rmean[(size_t)k * NM + i] = mean[k]; }
+                s.rres[i] = res;
+            }
+            s.rvalid[i] = valid ? 1 : 0;
+        } else {
+            // Q2: voxel not in the map -> the record keeps whatever an earlier pass left in it
+            valid = s.rvalid[i] != 0;
+            if (valid) {
+                nrm = v3(s.rnorm[i], s.rnorm[NM + i], s.rnorm[2 * NM + i]);
+                res = s.rres[i];
+            }
+        }
+        if (valid) status |= 4;
+        s.rstatus[i] = status;
+        s.rkey[i] = pk;
+        if (!valid) continue;
+        if (!have_cl) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
+        }
+        // lio_builder.cpp:294-297
+        const Mat<1, 3> nt = tr(nrm);
+        const double r_cov = mul(mul(mul(mul(nt, r_wl), cl), tr(r_wl)), nrm)[0];
+        const double r_info = r_cov < 0.0002 ? 5000 : 1.0 / r_cov;
+        double J[D];
+        J[0] = nrm[0]; J[1] = nrm[1]; J[2] = nrm[2];
+        const Mat<1, 3> jr = mul(mul(neg(nt), ms.R), hat(add(mul(ms.Rext, pl), ms.pext)));
+        J[3] = jr[0]; J[4] = jr[1]; J[5] = jr[2];
+        if (EXT) {
+            const Mat<1, 3> je = mul(mul(neg(nt), r_wl), hat(pl));
+            const Mat<1, 3> jp = mul(nt, ms.R);
+            J[6] = je[0]; J[7] = je[1]; J[8] = je[2];
+            J[D - 3] = jp[0]; J[D - 2] = jp[1]; J[D - 1] = jp[2];
+        }
+        int v = 0;
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+            const double ja = J[a] * r_info;
+#pragma unroll
+            for (int c = a; c < D; c++) acc[v++] += ja * J[c];
+        }
+#pragma unroll
+        for (int a = 0; a < D; a++) acc[NH + a] += (J[a] * r_info) * res;
+        acc[NH + D] += 1.0;
+    }
+
+    // warp shuffle -> shared -> one partial vector per block; fixed order everywhere
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const double t = warp_sum(acc[v]);
+        if (lane == 0) red[wid][v] = t;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < NV; v += blockDim.x) {
+        double t = red[0][v];
+        for (int w = 1; w < nw; w++) t += red[w][v];
+        partials[(size_t)blockIdx.x * PARTIAL_STRIDE + v] = t;
+    }
+}
+
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, const DevFilter* f, DevCtl* ctl, double* partials) {
+    if (ext) k_measure<true><<<grid, 128, 0, st>>>(m, s, f, ctl, partials);
+    else k_measure<false><<<grid, 256, 0, st>>>(m, s, f, ctl, partials);
+}
+void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const DevCtl* ctl) { k_set_scan<<<grid, 256, 0, st>>>(s, ctl); }
+
+// ---------------------------------------------------------------------------- K2
+// In-place LU with partial pivoting of A (23x23, shared) followed by substitution against
+// the permuted identity: one thread per matrix entry, the per-entry operation order is
+// exactly the serial one (lu_inverse in vmp_math.cuh), so the result is bit-identical to it.
+constexpr int NS = 23;
+__device__ void block_lu_inverse(double* A /*NS*NS in, destroyed*/, double* inv /*NS*NS out*/, int* perm, int* piv_sh) {
+    const int tid = threadIdx.x;
+    const int i = tid / NS, j = tid % NS;
+    const bool act = tid < NS * NS;
+    if (tid < NS) perm[tid] = tid;
+    __syncthreads();
+    for (int k = 0; k < NS; k++) {
+        if (tid == 0) {
+            int piv = k; double best = fabs(A[k * NS + k]);
+            for (int r = k + 1; r < NS; r++) { const double v = fabs(A[r * NS + k]); if (v > best) { best = v; piv = r; } }
+            *piv_sh = piv;
+        }
+        __syncthreads();
+        const int piv = *piv_sh;
+        if (piv != k) {
+            if (tid < NS) { const double t = A[k * NS + tid]; A[k * NS + tid] = A[piv * NS + tid]; A[piv * NS + tid] = t; }
+            if (tid == NS) { const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
+            __syncthreads();
+        }
+        const double d = A[k * NS + k];
+        if (tid > k && tid < NS) A[tid * NS + k] = A[tid * NS + k] / d;
+        __syncthreads();
+        if (act && i > k && j > k) A[i * NS + j] = A[i * NS + j] - A[i * NS + k] * A[k * NS + j];
+        __syncthreads();
+    }
+    // forward substitution L y = P e_c for all columns c at once; thread (i, c=j)
+    if (act) inv[i * NS + j] = (perm[i] == j) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int k = 0; k < NS; k++) {
+        if (act && i > k) inv[i * NS + j] = inv[i * NS + j] - A[i * NS + k] * inv[k * NS + j];
+        __syncthreads();
+    }
+    // backward substitution U x = y
+    for (int k = NS - 1; k >= 0; k--) {
+        if (act && i == k) inv[i * NS + j] = inv[i * NS + j] / A[k * NS + k];
+        __syncthreads();
+        if (act && i < k) inv[i * NS + j] = inv[i * NS + j] - A[i * NS + k] * inv[k * NS + j];
+        __syncthreads();
+    }
+}
+
+// C = A * B (all NS x NS, shared), thread per entry, left-to-right accumulation
+__device__ __forceinline__ void block_mm(const double* A, const double* B, double* C, bool transA, bool transB) {
+    const int tid = threadIdx.x;
+    if (tid < NS * NS) {
+        const int i = tid / NS, j = tid % NS;
+        double s = (transA ? A[0 * NS + i] : A[i * NS + 0]) * (transB ? B[j * NS + 0] : B[0 * NS + j]);
+        for (int k = 1; k < NS; k++) s += (transA ? A[k * NS + i] : A[i * NS + k]) * (transB ? B[j * NS + k] : B[k * NS + j]);
+        C[i * NS + j] = s;
+    }
+}
+
+// J / L of ieskf.cpp:136-139 and 151-154: identity with three small blocks
+__device__ void build_jac(double* J, const double* delta, const V3& g_cur, const V3& g_pred) {
+    for (int q = 0; q < NS * NS; q++) J[q] = 0.0;
+    for (int q = 0; q < NS; q++) J[q * NS + q] = 1.0;
+    const M3 j1 = right_jacobian(v3(delta[3], delta[4], delta[5]));
+    const M3 j2 = right_jacobian(v3(delta[6], delta[7], delta[8]));
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) { J[(3 + a) * NS + 3 + b] = j1(a, b); J[(6 + a) * NS + 6 + b] = j2(a, b); }
+    Mat<2, 1> dg; dg[0] = delta[21]; dg[1] = delta[22];
+    const Mat<2, 2> jg = mul(st_Nx(g_cur), st_Mx_res(g_pred, dg));
+    J[21 * NS + 21] = jg(0, 0); J[21 * NS + 22] = jg(0, 1); J[22 * NS + 21] = jg(1, 0); J[22 * NS + 22] = jg(1, 1);
+}
+
+template <bool EXT>
+__global__ void __launch_bounds__(576) k_ieskf_solve(DevFilter* f, DevCtl* ctl, const double* __restrict__ partials, int nblocks) {
+    constexpr int D = EXT ? 12 : 6;
+    constexpr int NH = D * (D + 1) / 2;
+    constexpr int NV = NH + D + 1;
+    __shared__ double sA[NS * NS], sB[NS * NS], sC[NS * NS], sJ[NS * NS], sHinv[NS * NS];
+    __shared__ double sHm[NV], sdelta[NS], sb[NS], sdx[NS];
+    __shared__ int perm[NS], piv_sh, s_last;
+    const int tid = threadIdx.x;
+    if (ctl->done) return;
+    const int it = ctl->iter;
+
+    // (1) final reduction of the per-block partials, ascending block order
+    if (tid < NV) {
+        double t = partials[tid];
+        for (int b = 1; b < nblocks; b++) t += partials[(size_t)b * PARTIAL_STRIDE + tid];
+        sHm[tid] = t;
+    }
+    // (2) boxminus and J (ieskf.cpp:136-139)
+    if (tid == 32) {
+        const St x = st_load(f->x), xp = st_load(f->xpred);
+        st_boxminus(x, xp, sdelta);
+        build_jac(sJ, sdelta, x.g, xp.g);
+    }
+    // (3) P^-1 : P_ does not change inside update(), evaluate once per scan (Q6)
+    if (it == 0) {
+        for (int q = tid; q < NS * NS; q += blockDim.x) sA[q] = f->P[q];
+        __syncthreads();
+        block_lu_inverse(sA, sB, perm, &piv_sh);
+        for (int q = tid; q < NS * NS; q += blockDim.x) f->Pinv[q] = sB[q];
+    } else {
+        for (int q = tid; q < NS * NS; q += blockDim.x) sB[q] = f->Pinv[q];
+    }
+    __syncthreads();
+    // (4) JtPinv = J^T P^-1 -> sC ; b_ = JtPinv delta ; H_ = JtPinv J -> sA
+    block_mm(sJ, sB, sC, true, false);
+    __syncthreads();
+    if (tid < NS) {
+        double t = sC[tid * NS + 0] * sdelta[0];
+        for (int k = 1; k < NS; k++) t += sC[tid * NS + k] * sdelta[k];
+        sb[tid] = 0.0 + t;
+    }
+    block_mm(sC, sJ, sA, false, false);
+    __syncthreads();
+    if (tid < NS * NS) {
+        const int i = tid / NS, j = tid % NS;
+        double h = 0.0 + sA[tid];
+        if (i < D && j < D) {
+            const int a = i < j ? i : j, c = i < j ? j : i;
+            h += sHm[a * D - a * (a - 1) / 2 + (c - a)];
+        }
+        sA[tid] = h;
+    }
+    if (tid < D) sb[tid] += sHm[NH + tid];
+    __syncthreads();
+    // keep H_ for nothing else: the posterior uses H_^-1 of the last executed iteration
+    block_lu_inverse(sA, sHinv, perm, &piv_sh);
+    // (5) delta = -H^-1 b
+    if (tid < NS) {
+        double t = (-sHinv[tid * NS + 0]) * sb[0];
+        for (int k = 1; k < NS; k++) t += (-sHinv[tid * NS + k]) * sb[k];
+        sdx[tid] = t;
+    }
+    __syncthreads();
+    // (6) boxplus, iteration bookkeeping, convergence (signed max, Q5)
+    if (tid == 0) {
+        St x = st_load(f->x);
+        st_boxplus(x, sdx);
+        st_store(x, f->x);
+        ctl->effect[it & 7] = (int)sHm[NH + D];
+        const int nit = it + 1;
+        ctl->iter = nit;
+        double mx = sdx[0];
+        for (int k = 1; k < NS; k++) if (sdx[k] > mx) mx = sdx[k];
+        int last = 0;
+        if (mx < 0.001) { ctl->converged = 1; last = 1; }
+        if (nit >= ctl->max_iter) last = 1;
+        if (last) ctl->done = 1;
+        s_last = last;
+        if (last) {
+            const St xp = st_load(f->xpred);
+            build_jac(sJ, sdx, x.g, xp.g);          // L (ieskf.cpp:151-154), x is the updated state
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // (7) P = L H^-1 L^T
+    block_mm(sJ, sHinv, sC, false, false);
+    __syncthreads();
+    block_mm(sC, sJ, sB, false, true);
+    __syncthreads();
+    for (int q = tid; q < NS * NS; q += blockDim.x) f->P[q] = sB[q];
+}
+
+void launch_solve(cudaStream_t st, bool ext, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
+    if (ext) k_ieskf_solve<true><<<1, 576, 0, st>>>(f, ctl, partials, nblocks);
+    else k_ieskf_solve<false><<<1, 576, 0, st>>>(f, ctl, partials, nblocks);
+}
+
+// start of IESKF::update (ieskf.cpp:127-130): predict_x = x_, iteration counter
+__global__ void k_update_begin(DevFilter* f, DevCtl* ctl) {
+    const int tid = threadIdx.x;
+    if (tid < 36) f->xpred[tid] = f->x[tid];
+    if (tid == 0) { ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
+    if (tid < 8) ctl->effect[tid] = 0;
+}
+void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl) { k_update_begin<<<1, 64, 0, st>>>(f, ctl); }
+
+// ---------------------------------------------------------------------------- K3
+// float32 world transform with the association of PCL's SSE Transformer::se3
+// (x' = m00 x + (m01 y + (m02 z + tx)), separate mul/add), widened to fp64, plus
+// pv.cov with the posterior R and P.  first_scan: calcBodyCov on a local copy (lio_builder.cpp:196-198).
+__global__ void __launch_bounds__(256) k_world_points(DevScan s, const DevFilter* __restrict__ f, const DevCtl* __restrict__ ctl, int first_scan) {
+    __shared__ MeasState ms;
+    __shared__ float mf[12];
+    if (threadIdx.x == 0) {
+        const St x = st_load(f->x);
+        ms.r_wl = mul(x.rot, x.rot_ext);
+        ms.p_wl = add(mul(x.rot, x.pos_ext), x.pos);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) { ms.Prr(i, j) = f->P[(3 + i) * 23 + 3 + j]; ms.Ppp(i, j) = f->P[i * 23 + j]; }
+        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) mf[i * 4 + j] = (float)ms.r_wl(i, j); mf[i * 4 + 3] = (float)ms.p_wl[i]; }
+    }
+    __syncthreads();
+    const int n = ctl->n;
+    const size_t NM = (size_t)s.nmax;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = s.raw[3 * i], y = s.raw[3 * i + 1], z = s.raw[3 * i + 2];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const float p0 = __fmul_rn(mf[r * 4 + 0], x), p1 = __fmul_rn(mf[r * 4 + 1], y), p2 = __fmul_rn(mf[r * 4 + 2], z);
+            const float o = __fadd_rn(p0, __fadd_rn(p1, __fadd_rn(p2, mf[r * 4 + 3])));
+            s.pw[3 * (size_t)i + r] = (double)o;
+        }
+        V3 pl; M3 cl;
+        if (first_scan) {
+            pl = v3((double)x, (double)y, (double)z);
+            calc_body_cov(pl, s.range_var, s.sn2, cl);
+        } else {
+            pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
+#pragma unroll
+            for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
+        }
+        const M3 cw = world_cov(ms.r_wl, cl, pl, ms.Prr, ms.Ppp);
+#pragma unroll
+        for (int k = 0; k < 9; k++) s.pcov[9 * (size_t)i + k] = cw.a[k];
+    }
+}
+void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, const DevCtl* ctl, int first_scan) {
+    k_world_points<<<grid, 256, 0, st>>>(s, f, ctl, first_scan);
+}
+
+}  // namespace vmp

@@ -1,0 +1,23 @@
+// vmp_kernels.h — host-callable launchers of the device kernels (vmp_iekf.cu, vmp_map.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "vmp_device.cuh"
+
+namespace vmp {
+
+constexpr int PARTIAL_STRIDE = 96;      // doubles per block partial (>= 78 + 12 + 1)
+constexpr int PT_BLOCK = 1024;          // points per block in the order-preserving passes
+
+// IEKF
+void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const DevCtl* ctl);
+void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl);
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, const DevFilter* f, DevCtl* ctl, double* partials);
+void launch_solve(cudaStream_t st, bool ext, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks);
+void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, const DevCtl* ctl, int first_scan);
+
+// map: returns the number of kernels launched
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build);
+void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl);
+
+}  // namespace vmp

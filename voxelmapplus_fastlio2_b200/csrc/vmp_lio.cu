@@ -1,0 +1,248 @@
+// vmp_lio.cu — host side of the estimator: IMU init, IMU propagation, undistortion,
+// the process() state machine, and the vmp_lio_* C wrappers.  No device code in here; the
+// measurement update and the map live behind vmp_scan / vmp_first_scan.
+#include "vmp_lio.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace vmp {
+
+void set_error(const char* fmt, ...);
+
+namespace {
+// C = A(ra x ca) * B(ca x cb), row-major, left-to-right accumulation (same as mul<>)
+void mm(const double* A, const double* B, double* C, int ra, int ca, int cb) {
+    for (int i = 0; i < ra; i++)
+        for (int j = 0; j < cb; j++) {
+            double s = A[i * ca] * B[j];
+            for (int k = 1; k < ca; k++) s += A[i * ca + k] * B[k * cb + j];
+            C[i * cb + j] = s;
+        }
+}
+void mt(const double* A, double* T, int r, int c) { for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) T[j * r + i] = A[i * c + j]; }
+template <int BR, int BC>
+void put(double* M, int ld, int r0, int c0, const Mat<BR, BC>& b) { for (int i = 0; i < BR; i++) for (int j = 0; j < BC; j++) M[(r0 + i) * ld + c0 + j] = b(i, j); }
+}  // namespace
+
+IESKF::IESKF() {
+    x_.pos = zeros<3, 1>(); x_.rot = eye<3>(); x_.rot_ext = eye<3>(); x_.pos_ext = zeros<3, 1>();
+    x_.vel = zeros<3, 1>(); x_.bg = zeros<3, 1>(); x_.ba = zeros<3, 1>(); x_.g = v3(0.0, 0.0, -GRAVITY);
+    std::memset(P_, 0, sizeof(P_));
+}
+
+// ieskf.cpp:101-123
+void IESKF::predict(const V3& acc_in, const V3& gyro_in, double dt, const double* Q) {
+    const V3 w = sub(gyro_in, x_.bg);
+    const V3 a = sub(acc_in, x_.ba);
+    const V3 dpos = scale(x_.vel, dt);
+    const V3 drot = scale(w, dt);
+    const V3 dvel = scale(add(mul(x_.rot, a), x_.g), dt);
+
+    static thread_local double F[529], G[23 * 12], T1[529], T2[529], Ft[529], Gt[12 * 23], T3[23 * 12];
+    std::memset(F, 0, sizeof(F));
+    for (int i = 0; i < 23; i++) F[i * 23 + i] = 1.0;
+    put(F, 23, 0, 12, scale(eye<3>(), dt));
+    put(F, 23, 3, 3, so3_exp(scale(neg(w), dt)));
+    put(F, 23, 3, 15, scale(neg(right_jacobian(scale(w, dt))), dt));
+    put(F, 23, 12, 3, scale(mul(neg(x_.rot), hat(a)), dt));
+    put(F, 23, 12, 18, scale(neg(x_.rot), dt));
+    put(F, 23, 12, 21, scale(st_Mx(x_.g), dt));
+    put(F, 23, 21, 21, mul(st_Nx(x_.g), st_Mx(x_.g)));
+    std::memset(G, 0, sizeof(G));
+    put(G, 12, 3, 0, scale(neg(right_jacobian(scale(w, dt))), dt));
+    put(G, 12, 12, 3, scale(neg(x_.rot), dt));
+    put(G, 12, 15, 6, scale(eye<3>(), dt));
+    put(G, 12, 18, 9, scale(eye<3>(), dt));
+    // x_ += delta (Vector24d variant, ieskf.cpp:23-33): only pos, rot, vel are non-zero
+    x_.pos = add(x_.pos, dpos);
+    x_.rot = mul(x_.rot, so3_exp(drot));
+    x_.rot_ext = mul(x_.rot_ext, so3_exp(zeros<3, 1>()));
+    x_.pos_ext = add(x_.pos_ext, zeros<3, 1>());
+    x_.vel = add(x_.vel, dvel);
+    x_.bg = add(x_.bg, zeros<3, 1>());
+    x_.ba = add(x_.ba, zeros<3, 1>());
+    x_.g = mul(so3_exp(zeros<3, 1>()), x_.g);
+    // P = F P F^T + G Q G^T
+    mm(F, P_, T1, 23, 23, 23);
+    mt(F, Ft, 23, 23);
+    mm(T1, Ft, T2, 23, 23, 23);
+    mm(G, Q, T3, 23, 12, 12);
+    mt(G, Gt, 23, 12);
+    mm(T3, Gt, T1, 23, 12, 23);
+    for (int i = 0; i < 529; i++) P_[i] = T2[i] + T1[i];
+}
+
+LIOBuilder::~LIOBuilder() { if (map) vmp_destroy(map); }
+
+// lio_builder.cpp:5-26
+int LIOBuilder::loadConfig(const vmp_config& cfg) {
+    config = cfg;
+    status = IMU_INIT;
+    std::memset(Q, 0, sizeof(Q));
+    for (int i = 0; i < 12; i++) Q[i * 12 + i] = 1.0;
+    for (int i = 0; i < 3; i++) {
+        Q[i * 12 + i] = cfg.ng; Q[(3 + i) * 12 + 3 + i] = cfg.na;
+        Q[(6 + i) * 12 + 6 + i] = cfg.nbg; Q[(9 + i) * 12 + 9 + i] = cfg.nba;
+    }
+    if (cfg.scan_resolution > 0.0) {
+        set_error("LIOBuilder::loadConfig: scan_resolution > 0 (pcl::VoxelGrid downsample) is a SURVEY.md 8(f) 'next' row; use scan_resolution <= 0");
+        return VMP_ERR_INVALID_ARG;
+    }
+    if (map) { vmp_destroy(map); map = nullptr; }
+    return vmp_create(&cfg, &map);
+}
+
+// lio_builder.cpp:28-63
+bool LIOBuilder::initializeImu(std::vector<IMUData>& imus) {
+    imu_cache.insert(imu_cache.end(), imus.begin(), imus.end());
+    if (imu_cache.size() < (size_t)config.imu_init_num) return false;
+    V3 acc_mean = zeros<3, 1>(), gyro_mean = zeros<3, 1>();
+    for (const auto& imu : imu_cache) { acc_mean = add(acc_mean, imu.acc); gyro_mean = add(gyro_mean, imu.gyro); }
+    acc_mean = divs(acc_mean, static_cast<double>(imu_cache.size()));
+    gyro_mean = divs(gyro_mean, static_cast<double>(imu_cache.size()));
+    gravity_norm = norm(acc_mean);
+    St& x = kf.x();
+    std::memcpy(x.rot_ext.a, config.r_il, sizeof(double) * 9);
+    std::memcpy(x.pos_ext.a, config.p_il, sizeof(double) * 3);
+    x.bg = gyro_mean;
+    if (config.gravity_align) {
+        x.rot = rot_from_two_vectors(normalized(neg(acc_mean)), v3(0.0, 0.0, -1.0));
+        x.g = scale(normalized(v3(0, 0, -1.0)), GRAVITY);
+    } else {
+        x.g = scale(normalized(neg(acc_mean)), GRAVITY);
+    }
+    double* P = kf.P();
+    std::memset(P, 0, sizeof(double) * 529);
+    for (int i = 0; i < 23; i++) P[i * 23 + i] = 1.0;
+    for (int i = 0; i < 3; i++) {
+        P[(6 + i) * 23 + 6 + i] = 0.00001; P[(9 + i) * 23 + 9 + i] = 0.00001;
+        P[(15 + i) * 23 + 15 + i] = 0.0001; P[(18 + i) * 23 + 18 + i] = 0.0001;
+    }
+    P[21 * 23 + 21] = 0.00001; P[22 * 23 + 22] = 0.00001;
+    last_imu = imus.back();
+    return true;
+}
+
+// lio_builder.cpp:65-153
+void LIOBuilder::undistortCloud(SyncPackage& package) {
+    imu_cache.clear();
+    imu_cache.push_back(last_imu);
+    imu_cache.insert(imu_cache.end(), package.imus.begin(), package.imus.end());
+    const double imu_time_end = imu_cache.back().timestamp;
+    const double cloud_time_begin = package.cloud_start_time, cloud_time_end = package.cloud_end_time;
+    std::stable_sort(package.cloud.begin(), package.cloud.end(),
+                     [](const CloudPoint& a, const CloudPoint& b) { return a.curvature < b.curvature; });
+    imu_poses_cache.clear();
+    imu_poses_cache.push_back(Pose{0.0, last_acc, last_gyro, kf.x().vel, kf.x().pos, kf.x().rot});
+    V3 acc_val = zeros<3, 1>(), gyro_val = zeros<3, 1>();
+    double dt = 0.0;
+    for (size_t i = 0; i + 1 < imu_cache.size(); i++) {
+        const IMUData& head = imu_cache[i];
+        const IMUData& tail = imu_cache[i + 1];
+        if (tail.timestamp < last_cloud_end_time) continue;
+        gyro_val = scale(add(head.gyro, tail.gyro), 0.5);
+        acc_val = scale(add(head.acc, tail.acc), 0.5);
+        acc_val = divs(scale(acc_val, 9.81), gravity_norm);
+        if (head.timestamp < last_cloud_end_time) dt = tail.timestamp - last_cloud_end_time;
+        else dt = tail.timestamp - head.timestamp;
+        kf.predict(acc_val, gyro_val, dt, Q);
+        last_gyro = sub(gyro_val, kf.x().bg);
+        last_acc = add(mul(kf.x().rot, sub(acc_val, kf.x().ba)), kf.x().g);
+        imu_poses_cache.push_back(Pose{tail.timestamp - cloud_time_begin, last_acc, last_gyro, kf.x().vel, kf.x().pos, kf.x().rot});
+    }
+    dt = cloud_time_end - imu_time_end;
+    kf.predict(acc_val, gyro_val, dt, Q);
+    last_imu = package.imus.back();
+    last_cloud_end_time = cloud_time_end;
+
+    const M3 cur_rot = kf.x().rot, cur_rot_ext = kf.x().rot_ext;
+    const V3 cur_pos = kf.x().pos, cur_pos_ext = kf.x().pos_ext;
+    if (package.cloud.empty()) return;
+    std::vector<CloudPoint>& pts = package.cloud;
+    size_t ip = pts.size() - 1;
+    for (size_t kp = imu_poses_cache.size() - 1; kp != 0; kp--) {
+        const Pose& head = imu_poses_cache[kp - 1];
+        const Pose& tail = imu_poses_cache[kp];
+        for (; pts[ip].curvature / double(1000) > head.offset; ip--) {
+            dt = pts[ip].curvature / double(1000) - head.offset;
+            const V3 point = v3(pts[ip].x, pts[ip].y, pts[ip].z);
+            const M3 point_rot = mul(head.rot, so3_exp(scale(tail.gyro, dt)));
+            const V3 point_pos = add(add(head.pos, scale(head.vel, dt)), scale(scale(scale(tail.acc, 0.5), dt), dt));
+            const V3 inner = sub(add(mul(point_rot, add(mul(cur_rot_ext, point), cur_pos_ext)), point_pos), cur_pos);
+            const V3 pc = mul(tr(cur_rot_ext), sub(mul(tr(cur_rot), inner), cur_pos_ext));
+            pts[ip].x = (float)pc[0]; pts[ip].y = (float)pc[1]; pts[ip].z = (float)pc[2];
+            if (ip == 0) break;
+        }
+    }
+}
+
+// lio_builder.cpp:175-248
+int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (status == IMU_INIT) {
+        if (initializeImu(package.imus)) { status = MAP_INIT; last_cloud_end_time = package.cloud_end_time; }
+        return VMP_OK;
+    }
+    undistortCloud(package);
+    const int n = (int)package.cloud.size();
+    xyz_.resize((size_t)n * 3);
+    for (int i = 0; i < n; i++) { xyz_[3 * i] = package.cloud[i].x; xyz_[3 * i + 1] = package.cloud[i].y; xyz_[3 * i + 2] = package.cloud[i].z; }
+    vmp_state xs;
+    st_store(kf.x(), reinterpret_cast<double*>(&xs));
+    if (status == MAP_INIT) {
+        vmp_update_stats us;
+        const int r = vmp_first_scan(map, &xs, kf.P(), xyz_.data(), n, &us);
+        if (r) return r;
+        if (stats) stats->map = us;
+        status = LIO_MAPPING;
+        return VMP_OK;
+    }
+    const int r = vmp_scan(map, &xs, kf.P(), xyz_.data(), n, stats);     // posterior written back into xs / kf.P()
+    if (r) return r;
+    kf.x() = st_load(reinterpret_cast<const double*>(&xs));
+    return VMP_OK;
+}
+
+}  // namespace vmp
+
+struct vmp_lio_t { vmp::LIOBuilder b; };
+
+extern "C" {
+
+int vmp_lio_create(const vmp_config* cfg, vmp_lio* out) {
+    if (!cfg || !out) { vmp::set_error("vmp_lio_create: null argument"); return VMP_ERR_INVALID_ARG; }
+    vmp_lio_t* l = new vmp_lio_t();
+    const int r = l->b.loadConfig(*cfg);
+    if (r) { delete l; *out = nullptr; return r; }
+    *out = l;
+    return VMP_OK;
+}
+int vmp_lio_destroy(vmp_lio l) { delete l; return VMP_OK; }
+
+int vmp_lio_process(vmp_lio l, const vmp_imu* imus, int n_imu, float* cloud_xyzc, int n, double t0, double t1, vmp_scan_stats* stats) {
+    if (!l || (n_imu > 0 && !imus) || (n > 0 && !cloud_xyzc) || n_imu < 1) { vmp::set_error("vmp_lio_process: invalid argument"); return VMP_ERR_INVALID_ARG; }
+    vmp::SyncPackage pk;
+    pk.imus.resize((size_t)n_imu);
+    for (int i = 0; i < n_imu; i++) {
+        std::memcpy(pk.imus[i].acc.a, imus[i].acc, 24);
+        std::memcpy(pk.imus[i].gyro.a, imus[i].gyro, 24);
+        pk.imus[i].timestamp = imus[i].timestamp;
+    }
+    pk.cloud.resize((size_t)n);
+    std::memcpy(pk.cloud.data(), cloud_xyzc, sizeof(float) * 4 * (size_t)n);
+    pk.cloud_start_time = t0; pk.cloud_end_time = t1;
+    const int r = l->b.process(pk, stats);
+    std::memcpy(cloud_xyzc, pk.cloud.data(), sizeof(float) * 4 * (size_t)n);     // process() edits the cloud in place
+    return r;
+}
+int vmp_lio_state(vmp_lio l, vmp_state* x, double* P, int* status) {
+    if (!l) return VMP_ERR_INVALID_ARG;
+    if (x) vmp::st_store(l->b.kf.x(), reinterpret_cast<double*>(x));
+    if (P) std::memcpy(P, l->b.kf.P(), sizeof(double) * 529);
+    if (status) *status = (int)l->b.status;
+    return VMP_OK;
+}
+vmp_handle vmp_lio_map(vmp_lio l) { return l ? l->b.map : nullptr; }
+
+}  // extern "C"

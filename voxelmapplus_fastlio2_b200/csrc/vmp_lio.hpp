@@ -1,0 +1,63 @@
+// vmp_lio.hpp — host-side mirror of the reference's estimator API (C++), above the C ABI.
+//
+//   vmp::IESKF        <-> kf::IESKF        (ieskf.h:76-110): x(), P(), predict(); update() runs on the device
+//   vmp::LIOBuilder   <-> lio::LIOBuilder  (lio_builder.h:56-83): loadConfig(), process(), status, kf, map
+//
+// IMU initialisation, IMU propagation and motion undistortion stay on the host exactly as
+// in the reference (lio_builder.cpp:28-153; they are SURVEY.md §8f "next" rows); the timed
+// region lio_builder.cpp:224-246 is one vmp_scan() call, i.e. one CUDA graph launch.
+#pragma once
+#include <vector>
+
+#include "../../include/vmp_b200.h"
+#include "vmp_state.cuh"
+
+namespace vmp {
+
+struct IMUData { V3 acc, gyro; double timestamp; };          // lio::IMUData   commons.h:12-20
+struct CloudPoint { float x, y, z, curvature; };               // fields of pcl::PointXYZINormal the path reads
+struct Pose { double offset; V3 acc, gyro, vel, pos; M3 rot; };    // lio::Pose      commons.h:30-43
+struct SyncPackage {                                           // lio::SyncPackage commons.h:22-28
+    std::vector<IMUData> imus;
+    std::vector<CloudPoint> cloud;
+    double cloud_start_time = 0.0, cloud_end_time = 0.0;
+};
+enum LIOStatus { IMU_INIT = 0, MAP_INIT = 1, LIO_MAPPING = 2 };    // lio_builder.h:10-16
+
+class IESKF {
+public:
+    IESKF();
+    St& x() { return x_; }
+    double* P() { return P_; }                                 // 23 x 23 row-major
+    void predict(const V3& acc, const V3& gyro, double dt, const double* Q /*12x12*/);   // ieskf.cpp:101-123
+private:
+    St x_;
+    double P_[529];
+};
+
+class LIOBuilder {
+public:
+    LIOBuilder() = default;
+    ~LIOBuilder();
+    int loadConfig(const vmp_config& cfg);                     // lio_builder.cpp:5-26  (creates the device map)
+    bool initializeImu(std::vector<IMUData>& imus);            // lio_builder.cpp:28-63
+    void undistortCloud(SyncPackage& package);                 // lio_builder.cpp:65-153
+    int process(SyncPackage& package, vmp_scan_stats* stats);  // lio_builder.cpp:175-248
+
+    IESKF kf;
+    vmp_config config;
+    LIOStatus status = IMU_INIT;
+    vmp_handle map = nullptr;                                  // std::shared_ptr<VoxelMap> map in the reference
+    // LIODataGroup (lio_builder.h:43-54)
+    IMUData last_imu;
+    std::vector<IMUData> imu_cache;
+    std::vector<Pose> imu_poses_cache;
+    V3 last_acc = zeros<3, 1>(), last_gyro = zeros<3, 1>();
+    double last_cloud_end_time = 0.0;
+    double gravity_norm = 0.0;
+    double Q[144];
+private:
+    std::vector<float> xyz_;
+};
+
+}  // namespace vmp
