@@ -109,8 +109,17 @@ typedef struct vmp_scan_stats {
     int32_t effect_num[8];      /* valid correspondences per executed iteration         */
     int32_t converged;          /* 1 if the loop left through the eps test (ieskf.cpp:148) */
     vmp_update_stats map;
-    float   gpu_ms;             /* device time of the scan graph (CUDA events), 0 if not measured */
+    float   gpu_ms;             /* device time of the call: CUDA events on the launching stream around copies + graph */
+    float   host_ms;            /* wall clock of the call measured inside the library (entry to return)           */
 } vmp_scan_stats;
+
+/* kernel classes of one scan, for vmp_profile_* (order = launch order inside a scan) */
+typedef enum vmp_kernel_id {
+    VMP_K_SCAN_IN = 0, VMP_K_SET_SCAN, VMP_K_UPDATE_BEGIN, VMP_K_MEASURE, VMP_K_SOLVE, VMP_K_WORLD_POINTS,
+    VMP_K_MAP_BEGIN, VMP_K_MAP_INSERT, VMP_K_MAP_COUNT, VMP_K_SEG_SCAN, VMP_K_SEG_FILL, VMP_K_LRU_EVICT,
+    VMP_K_MAP_FILL, VMP_K_MERGE_PREFILTER, VMP_K_MERGE_SERIAL, VMP_K_LOG_APPEND, VMP_K_MAP_FINALIZE,
+    VMP_K_MAP_END, VMP_K_REHASH, VMP_K_LOG_COMPACT, VMP_K_SCAN_OUT, VMP_K_COUNT
+} vmp_kernel_id;
 
 typedef struct vmp_handle_t* vmp_handle;
 
@@ -178,6 +187,15 @@ int vmp_map_size(vmp_handle h, int* count);
 /* number of kernel launches (graph kernel nodes included) issued by this handle so far */
 int64_t vmp_launch_count(vmp_handle h);
 
+/* Per-kernel device timing.  With profiling on, vmp_scan / vmp_scan_dev launch the very same
+ * kernels one by one on the handle's stream with a CUDA event after each (instead of the graph)
+ * and accumulate the elapsed time per kernel class.  vmp_profile_read returns, per vmp_kernel_id,
+ * the accumulated milliseconds and the number of launches since the last reset. */
+int vmp_profile_enable(vmp_handle h, int on);
+int vmp_profile_reset(vmp_handle h);
+int vmp_profile_read(vmp_handle h, double* ms /*VMP_K_COUNT*/, int64_t* launches /*VMP_K_COUNT*/);
+const char* vmp_kernel_name(int id);
+
 /* ---- host-side LIOBuilder (C++ class lio::LIOBuilder in vmp_lio.hpp) through C ---- */
 typedef struct vmp_lio_t* vmp_lio;
 typedef struct vmp_imu { double acc[3]; double gyro[3]; double timestamp; } vmp_imu;   /* lio::IMUData, commons.h:12-20 */
@@ -192,6 +210,8 @@ int vmp_lio_process(vmp_lio l, const vmp_imu* imus, int n_imu, float* cloud_xyzc
 int vmp_lio_state(vmp_lio l, vmp_state* x, double* P, int* status);
 /* the device handle behind builder->map */
 vmp_handle vmp_lio_map(vmp_lio l);
+/* the prior (x, P after IMU propagation) that the last process() handed to the device update */
+int vmp_lio_prior(vmp_lio l, vmp_state* x, double* P);
 
 #ifdef __cplusplus
 }

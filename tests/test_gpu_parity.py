@@ -93,7 +93,8 @@ def test_map_update_evict_and_recreate_same_scan(oracle_mod):
     new = np.stack([np.arange(100, 110) * 0.5 + 0.25, np.full(10, 0.25), np.full(10, 0.25)], 1)
     again = np.stack([np.array([3, 5, 3, 20, 21]) * 0.5 + 0.3, np.full(5, 0.3), np.full(5, 0.2)], 1)
     p1 = np.concatenate([new, again, new + 0.01])
-    for s, p in enumerate([p0, p1, p0[::-1].copy(), rng.uniform(0, 30, (200, 3))]):
+    p3 = np.stack([rng.integers(200, 230, 90) * 0.5 + 0.25, np.full(90, 0.25), rng.integers(0, 2, 90) * 0.5 + 0.25], 1)
+    for s, p in enumerate([p0, p1, p0[::-1].copy(), p3, p1, p0]):
         p = p.astype(np.float32).astype(np.float64)
         so, sg = o.map_update(p, cov(len(p))), g.map_update(p, cov(len(p)))
         assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"

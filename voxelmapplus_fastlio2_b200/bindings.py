@@ -221,6 +221,26 @@ class HotPath:
     def launch_count(self) -> int:
         return int(self._lib.vmp_launch_count(self._h))
 
+    def profile_enable(self, on: bool = True):
+        """Per-kernel CUDA-event timing: scans run the same kernels one by one instead of the graph."""
+        self._lib.vmp_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        self._check(self._lib.vmp_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._lib.vmp_profile_reset.argtypes = [C.c_void_p]
+        self._check(self._lib.vmp_profile_reset(self._h))
+
+    def profile_read(self) -> dict:
+        """{kernel name: (accumulated ms, launches)} since the last reset."""
+        from .ctypes_defs import K_COUNT
+        ms = np.zeros(K_COUNT)
+        cnt = np.zeros(K_COUNT, np.int64)
+        self._lib.vmp_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        self._lib.vmp_kernel_name.argtypes = [C.c_int]
+        self._lib.vmp_kernel_name.restype = C.c_char_p
+        self._check(self._lib.vmp_profile_read(self._h, dptr(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+        return {self._lib.vmp_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(K_COUNT)}
+
 
 def imu_array(n: int) -> np.ndarray:
     return np.zeros(n, IMU_DTYPE)

@@ -9,6 +9,7 @@
 // topology never changes and a scan is: 2 small H2D copies, 1 graph launch, 1 D2H copy.
 //
 // There is no CPU implementation behind this file: without a B200 every call fails.
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -103,6 +104,13 @@ struct vmp_handle_t {
     bool map_built = false;
     int64_t launches = 0;
     int graph_kernels = 0;
+    // profiling mode: direct launches with an event after each kernel
+    bool prof_on = false;
+    std::vector<cudaEvent_t> pev;        // pev[0] = start, pev[k] after the k-th kernel
+    std::vector<int> pev_id;
+    int pev_n = 0;
+    double prof_ms[VMP_K_COUNT] = {};
+    int64_t prof_cnt[VMP_K_COUNT] = {};
 };
 
 namespace {
@@ -138,28 +146,64 @@ void fill_update_stats(const DevStats& d, vmp_update_stats* st) {
     st->n_mergeprobe = d.n_mergeprobe; st->n_merge = d.n_merge; st->n_evicted = d.n_evicted; st->map_size = d.map_size;
 }
 
-// enqueue every kernel of one scan on h->stream (used both for graph capture and directly)
-int enqueue_scan(vmp_handle_t* h) {
+void prof_mark(void* ctx, int id) {
+    vmp_handle_t* h = (vmp_handle_t*)ctx;
+    if (h->pev_n + 1 >= (int)h->pev.size()) return;
+    h->pev_n++;
+    cudaEventRecord(h->pev[h->pev_n], h->stream);
+    h->pev_id[h->pev_n] = id;
+}
+
+// enqueue every kernel of one scan on h->stream (used both for graph capture and, in
+// profiling mode, directly with an event after each launch)
+int enqueue_scan(vmp_handle_t* h, const Marker* mk) {
     cudaStream_t st = h->stream;
     const bool ext = h->cfg.estimate_ext != 0;
     int k = 0;
-    k_scan_in<<<1, 256, 0, st>>>(h->d_in, h->f, h->ctl); k++;
-    launch_set_scan(st, h->grid_pts, h->s, h->ctl); k++;
-    launch_update_begin(st, h->f, h->ctl); k++;
+    k_scan_in<<<1, 256, 0, st>>>(h->d_in, h->f, h->ctl); k++; mark(mk, VMP_K_SCAN_IN);
+    launch_set_scan(st, h->grid_pts, h->s, h->ctl); k++; mark(mk, VMP_K_SET_SCAN);
+    launch_update_begin(st, h->f, h->ctl); k++; mark(mk, VMP_K_UPDATE_BEGIN);
     for (int it = 0; it < h->cfg.opti_max_iter; it++) {
-        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials); k++;
-        launch_solve(st, ext, h->f, h->ctl, h->partials, h->grid_meas); k++;
+        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials); k++; mark(mk, VMP_K_MEASURE);
+        launch_solve(st, ext, h->f, h->ctl, h->partials, h->grid_meas); k++; mark(mk, VMP_K_SOLVE);
     }
-    launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++;
-    k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false);
-    k_scan_out<<<1, 256, 0, st>>>(h->f, h->ctl, h->d_out); k++;
+    launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++; mark(mk, VMP_K_WORLD_POINTS);
+    k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false, mk);
+    k_scan_out<<<1, 256, 0, st>>>(h->f, h->ctl, h->d_out); k++; mark(mk, VMP_K_SCAN_OUT);
     return k;
+}
+
+// run one scan: the instantiated graph, or (profiling) the same kernels one by one
+int run_scan(vmp_handle_t* h) {
+    if (!h->prof_on) {
+        VMP_CUDA_CHECK(cudaGraphLaunch(h->graph, h->stream));
+        h->launches += h->graph_kernels;
+        return VMP_OK;
+    }
+    Marker mk{prof_mark, h};
+    h->pev_n = 0;
+    VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream));
+    h->launches += enqueue_scan(h, &mk);
+    VMP_CUDA_CHECK(cudaGetLastError());
+    return VMP_OK;
+}
+
+void prof_collect(vmp_handle_t* h) {      // after the stream has been synchronised
+    if (!h->prof_on) return;
+    for (int k = 1; k <= h->pev_n; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->pev[k - 1], h->pev[k]) == cudaSuccess) {
+            h->prof_ms[h->pev_id[k]] += ms;
+            h->prof_cnt[h->pev_id[k]] += 1;
+        }
+    }
+    h->pev_n = 0;
 }
 
 int build_graph(vmp_handle_t* h) {
     cudaGraph_t g = nullptr;
     VMP_CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    h->graph_kernels = enqueue_scan(h);
+    h->graph_kernels = enqueue_scan(h, nullptr);
     VMP_CUDA_CHECK(cudaStreamEndCapture(h->stream, &g));
     VMP_CUDA_CHECK(cudaGraphInstantiate(&h->graph, g, 0));
     VMP_CUDA_CHECK(cudaGraphDestroy(g));
@@ -170,6 +214,7 @@ int finish_scan(vmp_handle_t* h, vmp_state* x, double* P, vmp_scan_stats* stats)
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
     VMP_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
     VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    prof_collect(h);
     const ScanOut& o = *h->h_out;
     if (x) std::memcpy(x, o.x, sizeof(double) * 36);
     if (P) std::memcpy(P, o.P, sizeof(double) * 529);
@@ -323,6 +368,7 @@ int vmp_destroy(vmp_handle h) {
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_raw) cudaFreeHost(h->h_raw);
+    for (auto& e : h->pev) if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -358,7 +404,7 @@ static int map_update_common(vmp_handle h, const double* pts, const double* cov,
         VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.pw, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
         VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.pcov, cov, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, h->stream));
     }
-    h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build);
+    h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, nullptr);
     k_scan_out<<<1, 256, 0, h->stream>>>(h->f, h->ctl, h->d_out);
     h->launches += 1;
     h->map_built = true;
@@ -425,6 +471,7 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
 }
 
 int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp_scan_stats* stats) {
+    const auto t_enter = std::chrono::steady_clock::now();
     int r = check_n(h, n, "vmp_scan");
     if (r) return r;
     if (!x || !P || (n > 0 && !pts)) { set_error("vmp_scan: null argument"); return VMP_ERR_INVALID_ARG; }
@@ -437,13 +484,15 @@ int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp
     VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
     if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, h->h_raw, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_in, h->h_in, sizeof(ScanIn), cudaMemcpyHostToDevice, h->stream));
-    VMP_CUDA_CHECK(cudaGraphLaunch(h->graph, h->stream));
-    h->launches += h->graph_kernels;
+    { const int rr = run_scan(h); if (rr) return rr; }
     h->n_last = n;
-    return finish_scan(h, x, P, stats);
+    r = finish_scan(h, x, P, stats);
+    if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+    return r;
 }
 
 int vmp_scan_dev(vmp_handle h, const float* pts_dev, const double* prior_dev, int n, vmp_scan_stats* stats) {
+    const auto t_enter = std::chrono::steady_clock::now();
     int r = check_n(h, n, "vmp_scan_dev");
     if (r) return r;
     if (!h->map_built) { set_error("vmp_scan_dev: no map yet"); return VMP_ERR_STATE; }
@@ -455,10 +504,11 @@ int vmp_scan_dev(vmp_handle h, const float* pts_dev, const double* prior_dev, in
         VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, prior_dev + 36, sizeof(double) * 529, cudaMemcpyDeviceToDevice, h->stream));
     }
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_in, h->h_in, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    VMP_CUDA_CHECK(cudaGraphLaunch(h->graph, h->stream));
-    h->launches += h->graph_kernels;
+    { const int rr = run_scan(h); if (rr) return rr; }
     h->n_last = n;
-    return finish_scan(h, nullptr, nullptr, stats);
+    r = finish_scan(h, nullptr, nullptr, stats);
+    if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+    return r;
 }
 
 int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const float* pts, int n, vmp_update_stats* st) {
@@ -473,7 +523,7 @@ int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const floa
     if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
     VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
     launch_world_points(h->stream, h->grid_pts, h->s, h->f, h->ctl, 1);
-    h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true);
+    h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true, nullptr);
     k_scan_out<<<1, 256, 0, h->stream>>>(h->f, h->ctl, h->d_out);
     h->launches += 1;
     h->map_built = true;
@@ -580,5 +630,34 @@ int vmp_dump_evicted(vmp_handle h, int64_t* keys, int cap, int* count) {
 }
 
 int64_t vmp_launch_count(vmp_handle h) { return h ? h->launches : 0; }
+
+int vmp_profile_enable(vmp_handle h, int on) {
+    int r = check_n(h, 0, "vmp_profile_enable");
+    if (r) return r;
+    if (on && h->pev.empty()) {
+        h->pev.resize(64); h->pev_id.assign(64, 0);
+        for (auto& e : h->pev) VMP_CUDA_CHECK(cudaEventCreate(&e));
+    }
+    h->prof_on = on != 0;
+    return VMP_OK;
+}
+int vmp_profile_reset(vmp_handle h) {
+    if (!h) return VMP_ERR_INVALID_ARG;
+    for (int k = 0; k < VMP_K_COUNT; k++) { h->prof_ms[k] = 0.0; h->prof_cnt[k] = 0; }
+    return VMP_OK;
+}
+int vmp_profile_read(vmp_handle h, double* ms, int64_t* launches) {
+    if (!h) return VMP_ERR_INVALID_ARG;
+    for (int k = 0; k < VMP_K_COUNT; k++) { if (ms) ms[k] = h->prof_ms[k]; if (launches) launches[k] = h->prof_cnt[k]; }
+    return VMP_OK;
+}
+const char* vmp_kernel_name(int id) {
+    static const char* names[VMP_K_COUNT] = {
+        "k_scan_in", "k_set_scan", "k_update_begin", "k_measure", "k_ieskf_solve", "k_world_points",
+        "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
+        "k_map_fill", "k_merge_prefilter", "k_merge_serial", "k_log_append", "k_map_finalize",
+        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out"};
+    return (id >= 0 && id < VMP_K_COUNT) ? names[id] : "?";
+}
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "../../include/vmp_b200.h"
 #include "vmp_device.cuh"
 
 namespace vmp {
@@ -16,8 +17,12 @@ void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const 
 void launch_solve(cudaStream_t st, bool ext, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks);
 void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, const DevCtl* ctl, int first_scan);
 
+// optional per-launch hook (profiling mode records a CUDA event after each kernel)
+struct Marker { void (*fn)(void* ctx, int id); void* ctx; };
+inline void mark(const Marker* mk, int id) { if (mk && mk->fn) mk->fn(mk->ctx, id); }
+
 // map: returns the number of kernels launched
-int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build);
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, const Marker* mk);
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl);
 
 }  // namespace vmp

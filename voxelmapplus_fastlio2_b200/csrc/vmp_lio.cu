@@ -190,6 +190,8 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
     for (int i = 0; i < n; i++) { xyz_[3 * i] = package.cloud[i].x; xyz_[3 * i + 1] = package.cloud[i].y; xyz_[3 * i + 2] = package.cloud[i].z; }
     vmp_state xs;
     st_store(kf.x(), reinterpret_cast<double*>(&xs));
+    prior_x = xs;
+    std::memcpy(prior_P, kf.P(), sizeof(prior_P));
     if (status == MAP_INIT) {
         vmp_update_stats us;
         const int r = vmp_first_scan(map, &xs, kf.P(), xyz_.data(), n, &us);
@@ -244,5 +246,11 @@ int vmp_lio_state(vmp_lio l, vmp_state* x, double* P, int* status) {
     return VMP_OK;
 }
 vmp_handle vmp_lio_map(vmp_lio l) { return l ? l->b.map : nullptr; }
+int vmp_lio_prior(vmp_lio l, vmp_state* x, double* P) {
+    if (!l) return VMP_ERR_INVALID_ARG;
+    if (x) *x = l->b.prior_x;
+    if (P) std::memcpy(P, l->b.prior_P, sizeof(double) * 529);
+    return VMP_OK;
+}
 
 }  // extern "C"

@@ -56,6 +56,8 @@ public:
     double last_cloud_end_time = 0.0;
     double gravity_norm = 0.0;
     double Q[144];
+    vmp_state prior_x{};                                       // what the last process() handed to the device update
+    double prior_P[529] = {};
 private:
     std::vector<float> xyz_;
 };

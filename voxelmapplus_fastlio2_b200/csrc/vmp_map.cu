@@ -793,29 +793,29 @@ __global__ void __launch_bounds__(256) k_map_finalize(DevMap m, DevCtl* ctl) {
 }
 
 // ------------------------------------------------------------------------- launcher
-int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build) {
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, const Marker* mk) {
     const int gpt = (m.nmax + PT_BLOCK - 1) / PT_BLOCK;               // order-preserving passes: 1024 points / block
     const int gstride = sm_count * 2;
     int launches = 0;
-    k_map_begin<<<1, 1, 0, st>>>(ctl); launches++;
-    k_map_insert<<<gstride, 256, 0, st>>>(m, s, ctl); launches++;
-    k_map_count<<<gstride, 256, 0, st>>>(m, ctl); launches++;
-    k_seg_scan<<<1, 1024, 0, st>>>(m, ctl); launches++;
-    k_seg_fill<<<gpt, 1024, 0, st>>>(m, ctl); launches++;
-    k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++;
-    k_map_fill<<<sm_count * 4, 128, 0, st>>>(m, s, ctl, build ? 1 : 0); launches++;
+    k_map_begin<<<1, 1, 0, st>>>(ctl); launches++; mark(mk, VMP_K_MAP_BEGIN);
+    k_map_insert<<<gstride, 256, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_INSERT);
+    k_map_count<<<gstride, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_COUNT);
+    k_seg_scan<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_SCAN);
+    k_seg_fill<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_FILL);
+    k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LRU_EVICT);
+    k_map_fill<<<sm_count * 4, 128, 0, st>>>(m, s, ctl, build ? 1 : 0); launches++; mark(mk, VMP_K_MAP_FILL);
     if (!build) {
-        k_merge_prefilter<<<sm_count, 128, 0, st>>>(m, ctl); launches++;
-        k_merge_serial<<<1, 32, 0, st>>>(m, ctl); launches++;
+        k_merge_prefilter<<<sm_count, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
+        k_merge_serial<<<1, 32, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
     }
-    k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++;
-    k_map_finalize<<<sm_count, 256, 0, st>>>(m, ctl); launches++;
-    k_map_end<<<1, 1, 0, st>>>(m, ctl); launches++;
+    k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND);
+    k_map_finalize<<<sm_count, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_FINALIZE);
+    k_map_end<<<1, 1, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_END);
     k_rehash_clear<<<sm_count * 2, 256, 0, st>>>(m, ctl); launches++;
-    k_rehash_insert<<<sm_count * 2, 256, 0, st>>>(m, ctl); launches++;
+    k_rehash_insert<<<sm_count * 2, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_REHASH);
     k_logc_count<<<sm_count, 1024, 0, st>>>(m, ctl); launches++;
     k_logc_scatter<<<sm_count, 1024, 0, st>>>(m, ctl); launches++;
-    k_logc_end<<<1, 1, 0, st>>>(m, ctl); launches++;
+    k_logc_end<<<1, 1, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_COMPACT);
     return launches;
 }
 

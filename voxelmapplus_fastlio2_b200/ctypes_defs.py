@@ -116,7 +116,10 @@ class VmpUpdateStats(C.Structure):
 
 class VmpScanStats(C.Structure):
     _fields_ = [("iters", C.c_int32), ("effect_num", C.c_int32 * 8), ("converged", C.c_int32),
-                ("map", VmpUpdateStats), ("gpu_ms", C.c_float)]
+                ("map", VmpUpdateStats), ("gpu_ms", C.c_float), ("host_ms", C.c_float)]
+
+
+K_COUNT = 21        # VMP_K_COUNT in include/vmp_b200.h
 
 
 class VmpImu(C.Structure):

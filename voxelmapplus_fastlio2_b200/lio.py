@@ -64,6 +64,14 @@ class LIOBuilder:
         self._check(self._lib.vmp_lio_state(self._h, C.byref(x), dptr(P), C.byref(s)))
         return x, P, s.value
 
+    def prior(self):
+        """The (x, P) that the last process() handed to the device update (after IMU propagation)."""
+        x = VmpState()
+        P = np.zeros((23, 23))
+        self._lib.vmp_lio_prior.argtypes = [C.c_void_p, C.POINTER(VmpState), C.POINTER(C.c_double)]
+        self._check(self._lib.vmp_lio_prior(self._h, C.byref(x), dptr(P)))
+        return x, P
+
     def close(self):
         if self._h:
             self.map.close()
