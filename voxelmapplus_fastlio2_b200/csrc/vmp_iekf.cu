@@ -164,183 +164,7 @@ void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const 
 }
 void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const DevCtl* ctl) { k_set_scan<<<grid, 256, 0, st>>>(s, ctl); }
 
-// ---------------------------------------------------------------------------- K2
-// In-place LU with partial pivoting of A (23x23, shared) followed by substitution against
-// the permuted identity: one thread per matrix entry, the per-entry operation order is
-// exactly the serial one (lu_inverse in vmp_math.cuh), so the result is bit-identical to it.
-constexpr int NS = 23;
-__device__ void block_lu_inverse(double* A /*NS*NS in, destroyed*/, double* inv /*NS*NS out*/, int* perm, int* piv_sh) {
-    const int tid = threadIdx.x;
-    const int i = tid / NS, j = tid % NS;
-    const bool act = tid < NS * NS;
-    if (tid < NS) perm[tid] = tid;
-    __syncthreads();
-    for (int k = 0; k < NS; k++) {
-        if (tid == 0) {
-            int piv = k; double best = fabs(A[k * NS + k]);
-            for (int r = k + 1; r < NS; r++) { const double v = fabs(A[r * NS + k]); if (v > best) { best = v; piv = r; } }
-            *piv_sh = piv;
-        }
-        __syncthreads();
-        const int piv = *piv_sh;
-        if (piv != k) {
-            if (tid < NS) { const double t = A[k * NS + tid]; A[k * NS + tid] = A[piv * NS + tid]; A[piv * NS + tid] = t; }
-            if (tid == NS) { const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
-            __syncthreads();
-        }
-        const double d = A[k * NS + k];
-        if (tid > k && tid < NS) A[tid * NS + k] = A[tid * NS + k] / d;
-        __syncthreads();
-        if (act && i > k && j > k) A[i * NS + j] = A[i * NS + j] - A[i * NS + k] * A[k * NS + j];
-        __syncthreads();
-    }
-    // forward substitution L y = P e_c for all columns c at once; thread (i, c=j)
-    if (act) inv[i * NS + j] = (perm[i] == j) ? 1.0 : 0.0;
-    __syncthreads();
-    for (int k = 0; k < NS; k++) {
-        if (act && i > k) inv[i * NS + j] = inv[i * NS + j] - A[i * NS + k] * inv[k * NS + j];
-        __syncthreads();
-    }
-    // backward substitution U x = y
-    for (int k = NS - 1; k >= 0; k--) {
-        if (act && i == k) inv[i * NS + j] = inv[i * NS + j] / A[k * NS + k];
-        __syncthreads();
-        if (act && i < k) inv[i * NS + j] = inv[i * NS + j] - A[i * NS + k] * inv[k * NS + j];
-        __syncthreads();
-    }
-}
-
-// C = A * B (all NS x NS, shared), thread per entry, left-to-right accumulation
-__device__ __forceinline__ void block_mm(const double* A, const double* B, double* C, bool transA, bool transB) {
-    const int tid = threadIdx.x;
-    if (tid < NS * NS) {
-        const int i = tid / NS, j = tid % NS;
-        double s = (transA ? A[0 * NS + i] : A[i * NS + 0]) * (transB ? B[j * NS + 0] : B[0 * NS + j]);
-        for (int k = 1; k < NS; k++) s += (transA ? A[k * NS + i] : A[i * NS + k]) * (transB ? B[j * NS + k] : B[k * NS + j]);
-        C[i * NS + j] = s;
-    }
-}
-
-// J / L of ieskf.cpp:136-139 and 151-154: identity with three small blocks
-__device__ void build_jac(double* J, const double* delta, const V3& g_cur, const V3& g_pred) {
-    for (int q = 0; q < NS * NS; q++) J[q] = 0.0;
-    for (int q = 0; q < NS; q++) J[q * NS + q] = 1.0;
-    const M3 j1 = right_jacobian(v3(delta[3], delta[4], delta[5]));
-    const M3 j2 = right_jacobian(v3(delta[6], delta[7], delta[8]));
-    for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) { J[(3 + a) * NS + 3 + b] = j1(a, b); J[(6 + a) * NS + 6 + b] = j2(a, b); }
-    Mat<2, 1> dg; dg[0] = delta[21]; dg[1] = delta[22];
-    const Mat<2, 2> jg = mul(st_Nx(g_cur), st_Mx_res(g_pred, dg));
-    J[21 * NS + 21] = jg(0, 0); J[21 * NS + 22] = jg(0, 1); J[22 * NS + 21] = jg(1, 0); J[22 * NS + 22] = jg(1, 1);
-}
-
-template <bool EXT>
-__global__ void __launch_bounds__(576) k_ieskf_solve(DevFilter* f, DevCtl* ctl, const double* __restrict__ partials, int nblocks) {
-    constexpr int D = EXT ? 12 : 6;
-    constexpr int NH = D * (D + 1) / 2;
-    constexpr int NV = NH + D + 1;
-    __shared__ double sA[NS * NS], sB[NS * NS], sC[NS * NS], sJ[NS * NS], sHinv[NS * NS];
-    __shared__ double sHm[NV], sdelta[NS], sb[NS], sdx[NS];
-    __shared__ int perm[NS], piv_sh, s_last;
-    const int tid = threadIdx.x;
-    if (ctl->done) return;
-    const int it = ctl->iter;
-
-    // (1) final reduction of the per-block partials, ascending block order
-    if (tid < NV) {
-        double t = partials[tid];
-        for (int b = 1; b < nblocks; b++) t += partials[(size_t)b * PARTIAL_STRIDE + tid];
-        sHm[tid] = t;
-    }
-    // (2) boxminus and J (ieskf.cpp:136-139)
-    if (tid == 32) {
-        const St x = st_load(f->x), xp = st_load(f->xpred);
-        st_boxminus(x, xp, sdelta);
-        build_jac(sJ, sdelta, x.g, xp.g);
-    }
-    // (3) P^-1 : P_ does not change inside update(), evaluate once per scan (Q6)
-    if (it == 0) {
-        for (int q = tid; q < NS * NS; q += blockDim.x) sA[q] = f->P[q];
-        __syncthreads();
-        block_lu_inverse(sA, sB, perm, &piv_sh);
-        for (int q = tid; q < NS * NS; q += blockDim.x) f->Pinv[q] = sB[q];
-    } else {
-        for (int q = tid; q < NS * NS; q += blockDim.x) sB[q] = f->Pinv[q];
-    }
-    __syncthreads();
-    // (4) JtPinv = J^T P^-1 -> sC ; b_ = JtPinv delta ; H_ = JtPinv J -> sA
-    block_mm(sJ, sB, sC, true, false);
-    __syncthreads();
-    if (tid < NS) {
-        double t = sC[tid * NS + 0] * sdelta[0];
-        for (int k = 1; k < NS; k++) t += sC[tid * NS + k] * sdelta[k];
-        sb[tid] = 0.0 + t;
-    }
-    block_mm(sC, sJ, sA, false, false);
-    __syncthreads();
-    if (tid < NS * NS) {
-        const int i = tid / NS, j = tid % NS;
-        double h = 0.0 + sA[tid];
-        if (i < D && j < D) {
-            const int a = i < j ? i : j, c = i < j ? j : i;
-            h += sHm[a * D - a * (a - 1) / 2 + (c - a)];
-        }
-        sA[tid] = h;
-    }
-    if (tid < D) sb[tid] += sHm[NH + tid];
-    __syncthreads();
-    // keep H_ for nothing else: the posterior uses H_^-1 of the last executed iteration
-    block_lu_inverse(sA, sHinv, perm, &piv_sh);
-    // (5) delta = -H^-1 b
-    if (tid < NS) {
-        double t = (-sHinv[tid * NS + 0]) * sb[0];
-        for (int k = 1; k < NS; k++) t += (-sHinv[tid * NS + k]) * sb[k];
-        sdx[tid] = t;
-    }
-    __syncthreads();
-    // (6) boxplus, iteration bookkeeping, convergence (signed max, Q5)
-    if (tid == 0) {
-        St x = st_load(f->x);
-        st_boxplus(x, sdx);
-        st_store(x, f->x);
-        ctl->effect[it & 7] = (int)sHm[NH + D];
-        const int nit = it + 1;
-        ctl->iter = nit;
-        double mx = sdx[0];
-        for (int k = 1; k < NS; k++) if (sdx[k] > mx) mx = sdx[k];
-        int last = 0;
-        if (mx < 0.001) { ctl->converged = 1; last = 1; }
-        if (nit >= ctl->max_iter) last = 1;
-        if (last) ctl->done = 1;
-        s_last = last;
-        if (last) {
-            const St xp = st_load(f->xpred);
-            build_jac(sJ, sdx, x.g, xp.g);          // L (ieskf.cpp:151-154), x is the updated state
-        }
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // (7) P = L H^-1 L^T
-    block_mm(sJ, sHinv, sC, false, false);
-    __syncthreads();
-    block_mm(sC, sJ, sB, false, true);
-    __syncthreads();
-    for (int q = tid; q < NS * NS; q += blockDim.x) f->P[q] = sB[q];
-}
-
-void launch_solve(cudaStream_t st, bool ext, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
-    if (ext) k_ieskf_solve<true><<<1, 576, 0, st>>>(f, ctl, partials, nblocks);
-    else k_ieskf_solve<false><<<1, 576, 0, st>>>(f, ctl, partials, nblocks);
-}
-
-// start of IESKF::update (ieskf.cpp:127-130): predict_x = x_, iteration counter
-__global__ void k_update_begin(DevFilter* f, DevCtl* ctl) {
-    const int tid = threadIdx.x;
-    if (tid < 36) f->xpred[tid] = f->x[tid];
-    if (tid == 0) { ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
-    if (tid < 8) ctl->effect[tid] = 0;
-}
-void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl) { k_update_begin<<<1, 64, 0, st>>>(f, ctl); }
+#include "vmp_solve.cuh"
 
 // ---------------------------------------------------------------------------- K3
 // float32 world transform with the association of PCL's SSE Transformer::se3

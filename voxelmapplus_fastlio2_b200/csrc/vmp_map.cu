@@ -545,197 +545,7 @@ __global__ void __launch_bounds__(128) k_map_fill(DevMap m, DevScan s, DevCtl* c
     }
 }
 
-// ------------------------------------------------------------------------- merge()
-__device__ __forceinline__ unsigned long long nbr_key(unsigned long long pk, int d, bool& ok) {
-    long long x, y, z;
-    unpack_key(pk, x, y, z);
-    // order of VoxelGrid::merge: -x -y -z +x +y +z (voxel_map.cpp:141-146, Q10)
-    switch (d) {
-        case 0: x -= 1; break; case 1: y -= 1; break; case 2: z -= 1; break;
-        case 3: x += 1; break; case 4: y += 1; break; default: z += 1; break;
-    }
-    ok = key_in_range(x) && key_in_range(y) && key_in_range(z);
-    return ok ? pack_key(x, y, z) : KEY_EMPTY;
-}
-
-// thresholds of voxel_map.cpp:156-160 on the current planes
-__device__ __forceinline__ bool pair_thresholds(const DevMap& m, int A, int B) {
-    const double* ha = m.hot + (size_t)A * 8;
-    const double* hb = m.hot + (size_t)B * 8;
-    const V3 mA = v3(ha[0], ha[1], ha[2]), nA = v3(ha[3], ha[4], ha[5]);
-    const V3 mB = v3(hb[0], hb[1], hb[2]), nB = v3(hb[3], hb[4], hb[5]);
-    const double norm_distance = 1.0 - dot(nB, nA);
-    const double axis_distance = fabs(dot(nB, mB) - dot(nA, mA));
-    return !(norm_distance > m.th_angle || axis_distance > m.th_dist);
-}
-
-// could merge(A) succeed with some incarnation of some neighbour at ANY time of this scan,
-// given the current planes / groups?  (timing ignored -> superset of what can happen)
-__device__ bool merge_static_test(const DevMap& m, int A) {
-    const unsigned long long pk = m.skey[A];
-    const unsigned long long gA = m.sgroup[A];
-    for (int d = 0; d < 6; d++) {
-        bool ok;
-        const unsigned long long nk = nbr_key(pk, d, ok);
-        if (!ok) continue;
-        for (int B = hash_find(m, nk); B >= 0; B = m.ghost[B]) {
-            uint32_t fb; int nb;
-            hot_get_fn(m.hot, B, fb, nb);
-            if ((fb & F_UE) || !(fb & F_PLANE)) continue;
-            if (m.sgroup[B] == gA) continue;
-            if (pair_thresholds(m, A, B)) return true;
-        }
-    }
-    return false;
-}
-
-__global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) {
-    const int V = ctl->n_touched;
-    for (int vi = blockIdx.x * blockDim.x + threadIdx.x; vi < V; vi += gridDim.x * blockDim.x) {
-        const int A = m.touched[vi];
-        if (m.evn[A] == 0) continue;
-        if (merge_static_test(m, A)) m.hotlist[atomicAdd(&ctl->n_hot, 1)] = A;
-    }
-}
-
-// first point index of voxel A in this scan that is > after (warp-parallel), T_INF if none
-__device__ int warp_next_event(const DevMap& m, int A, int after) {
-    const int lane = threadIdx.x & 31;
-    const int c = m.cnt[A], off = m.seg_off[A];
-    int best = T_INF;
-    for (int q = lane; q < c; q += 32) { const int i = m.seg[off + q]; if (i > after && i < best) best = i; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
-    return best;
-}
-__device__ __forceinline__ int event_floor(const DevMap& m, int A, unsigned scan_id) {
-    return (m.full_scan[A] == scan_id) ? m.full_idx[A] : -1;     // merge() runs only for points after the closing one
-}
-
-// VoxelGrid::merge() of voxel A at time t (voxel_map.cpp:138-186); returns #successful pairs,
-// changed[] receives the neighbour slots that were modified
-__device__ int merge_at(const DevMap& m, DevCtl* ctl, int A, int t, unsigned scan_id, int* changed) {
-    int nchg = 0;
-    const unsigned long long pk = m.skey[A];
-    double* ha = m.hot + (size_t)A * 8;
-    double* ca = m.cov + (size_t)A * 36;
-    for (int d = 0; d < 6; d++) {
-        bool ok;
-        const unsigned long long nk = nbr_key(pk, d, ok);
-        if (!ok) continue;
-        int B = -1;
-        for (int X = hash_find(m, nk); X >= 0; X = m.ghost[X]) {          // incarnation alive at time t
-            const int born = (m.born_scan[X] == scan_id) ? m.ft[X] : -1;
-            if (born <= t && t < m.evict_t[X]) { B = X; break; }
-        }
-        if (B < 0) continue;
-        uint32_t fb; int nb;
-        hot_get_fn(m.hot, B, fb, nb);
-        if (m.sgroup[B] == m.sgroup[A]) continue;
-        const bool closed = !(fb & F_UE) && (m.full_scan[B] != scan_id || m.full_idx[B] < t);
-        if (!closed || !(fb & F_PLANE)) continue;
-        if (!pair_thresholds(m, A, B)) continue;
-        double* hb = m.hot + (size_t)B * 8;
-        double* cb = m.cov + (size_t)B * 36;
-        const double tn0 = ca[0] + ca[7] + ca[14], tm0 = ca[21] + ca[28] + ca[35];
-        const double tn1 = cb[0] + cb[7] + cb[14], tm1 = cb[21] + cb[28] + cb[35];
-        const double tc0 = tn0 + tm0, tc1 = tn1 + tm1;
-        // Q9: operator precedence exactly as in voxel_map.cpp:166-167
-        double nm[3], nn[3];
-        for (int k = 0; k < 3; k++) {
-            nm[k] = hb[k] * tm0 + (ha[k] * tm1) / (tm0 + tm1);
-            nn[k] = hb[3 + k] * tn0 + (ha[3 + k] * tn1) / (tn0 + tn1);
-        }
-        const double w0 = tc0 * tc0, w1 = tc1 * tc1, den = (tc0 + tc1) * (tc0 + tc1);
-        for (int k = 0; k < 36; k++) { const double c = (cb[k] * w0 + ca[k] * w1) / den; ca[k] = c; cb[k] = c; }
-        m.sgroup[B] = m.sgroup[A];
-        if (-(nm[0] * nn[0] + nm[1] * nn[1] + nm[2] * nn[2]) < 0.0) { nn[0] = -nn[0]; nn[1] = -nn[1]; nn[2] = -nn[2]; }
-        for (int k = 0; k < 3; k++) { ha[k] = nm[k]; hb[k] = nm[k]; ha[3 + k] = nn[k]; hb[3 + k] = nn[k]; }
-        uint32_t fa; int na;
-        hot_get_fn(m.hot, A, fa, na);
-        hot_set_fn(m.hot, A, fa | F_MERGED, na);
-        hot_set_fn(m.hot, B, fb | F_MERGED, nb);
-        changed[nchg++] = B;
-        ctl->st.n_merge += 1;
-    }
-    return nchg;
-}
-
-// Ordered simulation of the merge() calls that can have an effect.  One warp; lane 0 runs
-// the scalar logic, the warp cooperates on the searches.
-__global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
-    const int lane = threadIdx.x;
-    const int nh = ctl->n_hot;
-    if (nh == 0) return;
-    const unsigned scan_id = ctl->scan_id;
-    int na = 0;
-    for (int k = 0; k < nh; k++) {
-        const int A = m.hotlist[k];
-        const int t = warp_next_event(m, A, event_floor(m, A, scan_id));
-        if (t != T_INF) { if (lane == 0) { m.act_slot[na] = A; m.act_t[na] = t; } na++; }
-    }
-    __syncwarp();
-    while (na > 0) {
-        // earliest pending event
-        int bt = T_INF, bk = -1;
-        for (int k = lane; k < na; k += 32) { const int t = m.act_t[k]; if (t < bt) { bt = t; bk = k; } }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int yt = __shfl_xor_sync(0xffffffffu, bt, o), yk = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (yt < bt) { bt = yt; bk = yk; }
-        }
-        const int A = m.act_slot[bk], t = bt;
-        int changed[6];
-        int nchg = 0;
-        if (lane == 0) nchg = merge_at(m, ctl, A, t, scan_id, changed);
-        nchg = __shfl_sync(0xffffffffu, nchg, 0);
-        __syncwarp();
-        if (nchg > 0) {
-            // planes / groups of A and changed[] moved: re-examine them and all their neighbours
-            for (int ci = 0; ci <= nchg; ci++) {
-                int X = ci == 0 ? A : changed[ci - 1];
-                X = __shfl_sync(0xffffffffu, X, 0);
-                const unsigned long long pk = m.skey[X];
-                for (int d = -1; d < 6; d++) {
-                    int Y = X;
-                    if (d >= 0) {
-                        bool ok;
-                        const unsigned long long nk = nbr_key(pk, d, ok);
-                        Y = ok ? hash_find(m, nk) : -1;
-                    }
-                    if (Y < 0 || Y == A) continue;
-                    if (m.cnt[Y] == 0 || m.evn[Y] == 0) continue;          // no merge() call of Y in this scan
-                    int hot = 0;
-                    if (lane == 0) hot = merge_static_test(m, Y) ? 1 : 0;
-                    hot = __shfl_sync(0xffffffffu, hot, 0);
-                    if (!hot) continue;
-                    const int fl = event_floor(m, Y, scan_id);
-                    const int nt = warp_next_event(m, Y, t > fl ? t : fl);
-                    if (nt == T_INF) continue;
-                    int found = -1;
-                    for (int k = lane; k < na; k += 32) if (m.act_slot[k] == Y) found = k;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, found, o); found = y > found ? y : found; }
-                    if (found >= 0) { if (lane == 0 && nt < m.act_t[found]) m.act_t[found] = nt; }
-                    else {
-                        if (na >= m.nmax) { if (lane == 0) atomicOr(&ctl->err, E_QUEUE); }
-                        else { if (lane == 0) { m.act_slot[na] = Y; m.act_t[na] = nt; } na++; }
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-        // advance A
-        int again = 0;
-        if (lane == 0) again = merge_static_test(m, A) ? 1 : 0;
-        again = __shfl_sync(0xffffffffu, again, 0);
-        int nt = T_INF;
-        if (again) nt = warp_next_event(m, A, t);
-        if (nt != T_INF) { if (lane == 0) m.act_t[bk] = nt; }
-        else { if (lane == 0) { m.act_slot[bk] = m.act_slot[na - 1]; m.act_t[bk] = m.act_t[na - 1]; } na--; }
-        __syncwarp();
-    }
-}
+#include "vmp_merge.cuh"
 
 // ------------------------------------------------------------------------- M7a: LRU log append
 __global__ void __launch_bounds__(1024) k_log_append(DevMap m, DevCtl* ctl) {

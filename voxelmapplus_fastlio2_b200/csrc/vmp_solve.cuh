@@ -1,0 +1,215 @@
+// vmp_solve.cuh — the 23-dof algebra of IESKF::update (ieskf.cpp:125-156) on the device.
+// Included by vmp_iekf.cu inside namespace vmp.
+//
+//   k_update_begin   predict_x = x_ (ieskf.cpp:127), iteration counters, and P_^-1: P_ does not change
+//                    inside update(), so the inverse the reference evaluates twice per iteration (Q6) is
+//                    computed once per scan here
+//   k_ieskf_solve    one CTA per iteration: fixed-order reduction of the measurement partials, boxminus,
+//                    J, H_ = J^T P^-1 J + H, b_, delta = -H_^-1 b_, boxplus, convergence flag; on the
+//                    last executed iteration also P_ = L H_^-1 L^T
+//
+// The 23x23 inverse is LU with partial pivoting + substitution against the permuted identity
+// (what Eigen's PartialPivLU-based inverse() does).  One warp, one matrix row per lane held in
+// registers, pivot search and row broadcast through shuffles, no block barriers; the per-entry
+// operation order is exactly the serial one (lu_inverse<> in vmp_math.cuh).
+#pragma once
+
+constexpr int NS = 23;
+
+// A, inv, lu: NS*NS doubles in shared memory; perm: NS ints in shared memory.  Whole warp must call.
+__device__ void warp_lu_inverse(const double* A, double* inv, double* lu, int* perm) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double a[NS];
+    int pos = lane < NS ? lane : 1000 + lane;          // conceptual row index held by this lane
+#pragma unroll
+    for (int j = 0; j < NS; j++) a[j] = lane < NS ? A[lane * NS + j] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        // pivot: first row (in conceptual order) of maximal |a_ik|, i >= k
+        double v = (lane < NS && pos >= k) ? fabs(a[k]) : -1.0;
+        int p = pos;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double vo = __shfl_xor_sync(FULL, v, o);
+            const int po = __shfl_xor_sync(FULL, p, o);
+            if (vo > v || (vo == v && po < p)) { v = vo; p = po; }
+        }
+        if (pos == p) pos = k; else if (pos == k) pos = p;          // row swap k <-> p
+        const int L = __ffs(__ballot_sync(FULL, pos == k)) - 1;
+        const double d = __shfl_sync(FULL, a[k], L);
+        const bool below = lane < NS && pos > k;
+        const double l = a[k] / d;
+        if (below) a[k] = l;
+#pragma unroll
+        for (int j = k + 1; j < NS; j++) {
+            const double u = __shfl_sync(FULL, a[j], L);
+            if (below) a[j] = a[j] - l * u;
+        }
+    }
+    if (lane < NS) {
+#pragma unroll
+        for (int j = 0; j < NS; j++) lu[pos * NS + j] = a[j];
+        perm[pos] = lane;
+    }
+    __syncwarp();
+    if (lane < NS) {
+        double y[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) {                               // L y = P e_c
+            double s = (perm[i] == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 0; j < i; j++) s = s - lu[i * NS + j] * y[j];
+            y[i] = s;
+        }
+#pragma unroll
+        for (int i = NS - 1; i >= 0; i--) {                          // U x = y
+            double s = y[i];
+#pragma unroll
+            for (int j = i + 1; j < NS; j++) s = s - lu[i * NS + j] * y[j];
+            y[i] = s / lu[i * NS + i];
+        }
+#pragma unroll
+        for (int i = 0; i < NS; i++) inv[i * NS + lane] = y[i];
+    }
+    __syncwarp();
+}
+
+// C = op(A) * op(B), NS x NS in shared memory, entries strided over the block, left-to-right sums
+__device__ __forceinline__ void block_mm(const double* A, const double* B, double* C, bool transA, bool transB) {
+    for (int q = threadIdx.x; q < NS * NS; q += blockDim.x) {
+        const int i = q / NS, j = q % NS;
+        double s = (transA ? A[i] : A[i * NS]) * (transB ? B[j * NS] : B[j]);
+        for (int k = 1; k < NS; k++) s += (transA ? A[k * NS + i] : A[i * NS + k]) * (transB ? B[j * NS + k] : B[k * NS + j]);
+        C[q] = s;
+    }
+}
+
+// the three non-identity blocks of J / L (ieskf.cpp:136-139, 151-154), one lane each
+__device__ __forceinline__ void jac_blocks(double* J, const double* delta, const V3& g_cur, const V3& g_pred, int which) {
+    if (which == 0 || which == 1) {
+        const int o = which == 0 ? 3 : 6;
+        const M3 j = right_jacobian(v3(delta[o], delta[o + 1], delta[o + 2]));
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) J[(o + a) * NS + o + b] = j(a, b);
+    } else {
+        Mat<2, 1> dg; dg[0] = delta[21]; dg[1] = delta[22];
+        const Mat<2, 2> jg = mul(st_Nx(g_cur), st_Mx_res(g_pred, dg));
+        J[21 * NS + 21] = jg(0, 0); J[21 * NS + 22] = jg(0, 1); J[22 * NS + 21] = jg(1, 0); J[22 * NS + 22] = jg(1, 1);
+    }
+}
+__device__ __forceinline__ void block_identity(double* J) {
+    for (int q = threadIdx.x; q < NS * NS; q += blockDim.x) J[q] = (q / NS == q % NS) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(64) k_update_begin(DevFilter* f, DevCtl* ctl) {
+    __shared__ double sA[NS * NS], sInv[NS * NS], sLU[NS * NS];
+    __shared__ int perm[NS];
+    const int tid = threadIdx.x;
+    if (tid >= 32) {
+        const int t = tid - 32;
+        f->xpred[t] = f->x[t];
+        if (t < 4) f->xpred[32 + t] = f->x[32 + t];
+        if (t == 0) { ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
+        if (t < 8) ctl->effect[t] = 0;
+        return;
+    }
+    for (int q = tid; q < NS * NS; q += 32) sA[q] = f->P[q];
+    __syncwarp();
+    warp_lu_inverse(sA, sInv, sLU, perm);
+    for (int q = tid; q < NS * NS; q += 32) f->Pinv[q] = sInv[q];
+}
+void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl) { k_update_begin<<<1, 64, 0, st>>>(f, ctl); }
+
+template <bool EXT>
+__global__ void __launch_bounds__(256) k_ieskf_solve(DevFilter* f, DevCtl* ctl, const double* __restrict__ partials, int nblocks) {
+    constexpr int D = EXT ? 12 : 6;
+    constexpr int NH = D * (D + 1) / 2;
+    constexpr int NV = NH + D + 1;
+    __shared__ double sA[NS * NS], sB[NS * NS], sC[NS * NS], sJ[NS * NS], sHinv[NS * NS];
+    __shared__ double sHm[NV], sdelta[NS], sb[NS], sdx[NS], sx[36], sxp[36];
+    __shared__ int perm[NS], s_last;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    if (ctl->done) return;
+    const int it = ctl->iter;
+
+    // (1) final reduction of the per-block partials in ascending block order; state; P^-1; J := I
+    if (tid < NV) {
+        double t = partials[tid];
+        for (int b = 1; b < nblocks; b++) t += partials[(size_t)b * PARTIAL_STRIDE + tid];
+        sHm[tid] = t;
+    }
+    if (tid >= 128 && tid < 164) { sx[tid - 128] = f->x[tid - 128]; sxp[tid - 128] = f->xpred[tid - 128]; }
+    for (int q = tid; q < NS * NS; q += blockDim.x) sB[q] = f->Pinv[q];
+    block_identity(sJ);
+    __syncthreads();
+    // (2) delta = x [-] predict_x, then the blocks of J (ieskf.cpp:135-139)
+    if (wid == 7) {
+        if (lane == 0) { const St x = st_load(sx), xp = st_load(sxp); st_boxminus(x, xp, sdelta); }
+        __syncwarp();
+        if (lane < 3) jac_blocks(sJ, sdelta, v3(sx[33], sx[34], sx[35]), v3(sxp[33], sxp[34], sxp[35]), lane);
+    }
+    __syncthreads();
+    // (3) JtPinv = J^T P^-1 ; b_ = JtPinv delta ; H_ = JtPinv J (+ measurement H, b in the top-left corner)
+    block_mm(sJ, sB, sC, true, false);
+    __syncthreads();
+    if (tid < NS) {
+        double t = sC[tid * NS] * sdelta[0];
+        for (int k = 1; k < NS; k++) t += sC[tid * NS + k] * sdelta[k];
+        t = 0.0 + t;
+        if (tid < D) t += sHm[NH + tid];
+        sb[tid] = t;
+    }
+    block_mm(sC, sJ, sA, false, false);
+    __syncthreads();
+    for (int q = tid; q < NS * NS; q += blockDim.x) {
+        const int i = q / NS, j = q % NS;
+        double h = 0.0 + sA[q];
+        if (i < D && j < D) { const int a = i < j ? i : j, c = i < j ? j : i; h += sHm[a * D - a * (a - 1) / 2 + (c - a)]; }
+        sA[q] = h;
+    }
+    __syncthreads();
+    // (4) H_^-1 (one warp), delta = -H_^-1 b_
+    if (wid == 0) {
+        warp_lu_inverse(sA, sHinv, sC, perm);
+        if (lane < NS) {
+            double t = (-sHinv[lane * NS]) * sb[0];
+            for (int k = 1; k < NS; k++) t += (-sHinv[lane * NS + k]) * sb[k];
+            sdx[lane] = t;
+        }
+        __syncwarp();
+        // (5) x_ += delta, counters, convergence on the signed maximum (Q5)
+        if (lane == 0) {
+            St x = st_load(sx);
+            st_boxplus(x, sdx);
+            st_store(x, sx);
+            st_store(x, f->x);
+            ctl->effect[it & 7] = (int)sHm[NH + D];
+            const int nit = it + 1;
+            ctl->iter = nit;
+            double mx = sdx[0];
+            for (int k = 1; k < NS; k++) if (sdx[k] > mx) mx = sdx[k];
+            int last = 0;
+            if (mx < 0.001) { ctl->converged = 1; last = 1; }
+            if (nit >= ctl->max_iter) last = 1;
+            if (last) ctl->done = 1;
+            s_last = last;
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // (6) P_ = L H_^-1 L^T with L from the final delta and the updated state (ieskf.cpp:151-155)
+    block_identity(sJ);
+    __syncthreads();
+    if (wid == 7 && lane < 3) jac_blocks(sJ, sdx, v3(sx[33], sx[34], sx[35]), v3(sxp[33], sxp[34], sxp[35]), lane);
+    __syncthreads();
+    block_mm(sJ, sHinv, sC, false, false);
+    __syncthreads();
+    block_mm(sC, sJ, sB, false, true);
+    __syncthreads();
+    for (int q = tid; q < NS * NS; q += blockDim.x) f->P[q] = sB[q];
+}
+
+void launch_solve(cudaStream_t st, bool ext, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
+    if (ext) k_ieskf_solve<true><<<1, 256, 0, st>>>(f, ctl, partials, nblocks);
+    else k_ieskf_solve<false><<<1, 256, 0, st>>>(f, ctl, partials, nblocks);
+}
