@@ -5,10 +5,17 @@
 // always.  Phase 1 (k_merge_prefilter, parallel, 8 lanes per voxel): which of the voxels that
 // received such points could merge with some neighbour at all, given the current planes and
 // groups, ignoring when during the scan the neighbour becomes eligible.  Phase 2
-// (k_merge_serial, one warp): an event simulation in point order over those voxels only; the
-// six neighbour look-ups of an event, the 6x6 covariance blend and the re-examination of the
-// voxels around a changed plane are spread over the lanes, the accept/reject decisions are
-// taken strictly in the reference's order (-x -y -z +x +y +z, own plane updated in between, Q10).
+// (k_merge_serial, one warp): an event simulation in point order over those voxels only.
+// Per event the six neighbour look-ups run on six lanes; the accept/reject decisions are taken
+// strictly in the reference's order (-x -y -z +x +y +z, own plane updated in between, Q10); the
+// 6x6 covariance blend is spread over the lanes.  Exactness argument:
+//   * an event is a no-op unless some neighbour pair passes the thresholds on the CURRENT planes
+//     and groups while that neighbour is alive, full and a plane AT THAT TIME;
+//   * planes / groups change only through a successful merge; after one, the pairs (Y, X) of every
+//     voxel Y adjacent to a changed voxel X are re-examined, and the changed voxels themselves are
+//     re-examined against all their neighbours;
+//   * a voxel whose only passing pairs become eligible later in the scan (neighbour not yet created
+//     / not yet full) sleeps until the earliest such time instead of replaying every point.
 #pragma once
 
 __device__ __forceinline__ unsigned long long nbr_key(unsigned long long pk, int d, bool& ok) {
@@ -34,40 +41,53 @@ __device__ __forceinline__ void load_plane(const DevMap& m, int s, V3& mean, V3&
     nrm = v3(h[3], h[4], h[5]);
 }
 
-// one neighbour direction of "could merge(A) ever succeed in this scan" (timing ignored)
-__device__ bool static_test_dir(const DevMap& m, int A, int d) {
+// could merge(A) succeed against the (final state of) incarnation B at some time of this scan?
+__device__ __forceinline__ bool pair_static(const DevMap& m, int A, int B) {
+    uint32_t fb; int nb;
+    hot_get_fn(m.hot, B, fb, nb);
+    if ((fb & F_UE) || !(fb & F_PLANE)) return false;
+    if (m.sgroup[B] == m.sgroup[A]) return false;
+    V3 mA, nA, mB, nB;
+    load_plane(m, A, mA, nA);
+    load_plane(m, B, mB, nB);
+    return plane_thresholds(m, mA, nA, mB, nB);
+}
+// window (start, end) of point indices t of this scan at which B is alive and full: start < t < end
+__device__ __forceinline__ void pair_window(const DevMap& m, int B, unsigned scan_id, int& start, int& end) {
+    const int born = (m.born_scan[B] == scan_id) ? m.ft[B] : -1;
+    const int full = (m.full_scan[B] == scan_id) ? m.full_idx[B] : -1;
+    start = born > full ? born : full;
+    end = m.evict_t[B];
+}
+
+// one neighbour direction of "could merge(A) succeed after time `after`": returns the earliest time
+// bound (events with t > bound may succeed), T_INF if never.  after = -1 gives the plain static test.
+__device__ int wake_dir(const DevMap& m, int A, int d, int after, unsigned scan_id) {
     bool ok;
     const unsigned long long nk = nbr_key(m.skey[A], d, ok);
-    if (!ok) return false;
-    const unsigned long long gA = m.sgroup[A];
-    V3 mA, nA;
-    load_plane(m, A, mA, nA);
+    if (!ok) return T_INF;
+    int best = T_INF;
     for (int B = hash_find(m, nk); B >= 0; B = m.ghost[B]) {
-        uint32_t fb; int nb;
-        hot_get_fn(m.hot, B, fb, nb);
-        if ((fb & F_UE) || !(fb & F_PLANE)) continue;
-        if (m.sgroup[B] == gA) continue;
-        V3 mB, nB;
-        load_plane(m, B, mB, nB);
-        if (plane_thresholds(m, mA, nA, mB, nB)) return true;
+        if (!pair_static(m, A, B)) continue;
+        int s, e;
+        pair_window(m, B, scan_id, s, e);
+        const int bound = s > after ? s : after;                 // first usable events are those with t > bound
+        if (bound + 1 < e && bound < best) best = bound;
     }
-    return false;
+    return best;
 }
-// all six directions by one lane
-__device__ bool static_test_lane(const DevMap& m, int A) {
-    for (int d = 0; d < 6; d++) if (static_test_dir(m, A, d)) return true;
-    return false;
-}
-// all six directions by six lanes of the calling warp
-__device__ __forceinline__ bool static_test_warp(const DevMap& m, int A) {
+__device__ __forceinline__ int wake_warp(const DevMap& m, int A, int after, unsigned scan_id) {
     const int lane = threadIdx.x & 31;
-    const bool p = lane < 6 ? static_test_dir(m, A, lane) : false;
-    return __any_sync(0xffffffffu, p);
+    int w = lane < 6 ? wake_dir(m, A, lane, after, scan_id) : T_INF;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, w, o); w = y < w ? y : w; }
+    return __shfl_sync(0xffffffffu, w, 0);
 }
 
 // 8 lanes per touched voxel, lanes 0..5 take one neighbour each
 __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) {
     const int V = ctl->n_touched;
+    const unsigned scan_id = ctl->scan_id;
     const int sub = threadIdx.x & 7;
     const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
     const int ngroups = (gridDim.x * blockDim.x) >> 3;
@@ -77,14 +97,14 @@ __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) 
         int A = -1;
         if (vi < V) {
             A = m.touched[vi];
-            if (m.evn[A] > 0 && sub < 6) p = static_test_dir(m, A, sub);
+            if (m.evn[A] > 0 && sub < 6) p = wake_dir(m, A, sub, -1, scan_id) != T_INF;
         }
         const bool any = __any_sync(gmask, p);
         if (any && sub == 0) m.hotlist[atomicAdd(&ctl->n_hot, 1)] = A;
     }
 }
 
-// first point index of voxel A in this scan that is > after: warp-parallel / single lane
+// first point index of voxel A in this scan that is > after (warp-parallel), T_INF if none
 __device__ int next_event_warp(const DevMap& m, int A, int after) {
     const int lane = threadIdx.x & 31;
     const int c = m.cnt[A], off = m.seg_off[A];
@@ -175,8 +195,7 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
             hot_set_fn(m.hot, A, fa | F_MERGED, na);
             ctl->st.n_merge += 1;
         }
-        // neighbour's MERGED flag: written by the lane that loaded it
-        if (lane == d) hot_set_fn(m.hot, Bd, fB | F_MERGED, cntB);
+        if (lane == d) hot_set_fn(m.hot, Bd, fB | F_MERGED, cntB);      // neighbour's MERGED flag, by the lane that loaded it
         __syncwarp();
         changed[nchg++] = Bd;
     }
@@ -192,7 +211,10 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
     int na = 0;
     for (int k = 0; k < nh; k++) {
         const int A = m.hotlist[k];
-        const int t = next_event_warp(m, A, event_floor(m, A, scan_id));
+        const int fl = event_floor(m, A, scan_id);
+        const int w = wake_warp(m, A, fl, scan_id);
+        if (w == T_INF) continue;
+        const int t = next_event_warp(m, A, w);
         if (t != T_INF) { if (lane == 0) { m.act_slot[na] = A; m.act_t[na] = t; } na++; }
     }
     __syncwarp();
@@ -209,29 +231,47 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
         int changed[6];
         const int nchg = merge_at_warp(m, ctl, A, t, scan_id, changed);
         if (nchg > 0) {
-            // planes / groups of A and changed[] moved: re-examine them and all their neighbours.
-            // candidate c = (xi, d): xi in [0, nchg] selects A or a changed neighbour, d = -1 is the voxel
-            // itself, d = 0..5 its neighbours; one candidate per lane, two rounds at most.
-            const int ncand = (nchg + 1) * 7;
+            // planes / groups of A and changed[] moved.  (a) every voxel Y adjacent to a changed voxel X:
+            // only its pair with X can have flipped; (b) a changed neighbour itself: all of its pairs.
+            // One (X, direction) or one changed voxel per lane.
+            const int nx = nchg + 1;
+            const int ncand = nx * 6 + nchg;
             for (int c0 = 0; c0 < ncand; c0 += 32) {
                 const int c = c0 + lane;
-                int Y = -1, nt = T_INF;
-                if (c < ncand) {
-                    const int xi = c / 7, d = c % 7 - 1;
-                    const int X = xi == 0 ? A : changed[xi - 1];
-                    Y = X;
-                    if (d >= 0) { bool ok; const unsigned long long nk = nbr_key(m.skey[X], d, ok); Y = ok ? hash_find(m, nk) : -1; }
-                    if (Y == A) Y = -1;                                   // A itself is advanced below
-                    if (Y >= 0 && (m.cnt[Y] == 0 || m.evn[Y] == 0)) Y = -1;   // no merge() call of Y in this scan
-                    if (Y >= 0 && !static_test_lane(m, Y)) Y = -1;
+                int Y = -1, w = T_INF;
+                if (c < nx * 6) {
+                    const int X = (c / 6 == 0) ? A : changed[c / 6 - 1];
+                    bool ok;
+                    const unsigned long long nk = nbr_key(m.skey[X], c % 6, ok);
+                    Y = ok ? hash_find(m, nk) : -1;
+                    if (Y == A || (Y >= 0 && (m.cnt[Y] == 0 || m.evn[Y] == 0))) Y = -1;   // no merge() call of Y in this scan
+                    for (int q = 0; q < nchg && Y >= 0; q++) if (changed[q] == Y) Y = -1;  // handled by (b)
+                    if (Y >= 0 && pair_static(m, Y, X)) {
+                        int s, e;
+                        pair_window(m, X, scan_id, s, e);
+                        const int fl = event_floor(m, Y, scan_id);
+                        int bound = s > t ? s : t;
+                        bound = fl > bound ? fl : bound;
+                        if (bound + 1 < e) w = bound;
+                    }
+                    if (w == T_INF) Y = -1;
+                } else if (c < ncand) {
+                    Y = changed[c - nx * 6];
+                    if (m.cnt[Y] == 0 || m.evn[Y] == 0) Y = -1;
+                    if (Y >= 0) {
+                        const int fl = event_floor(m, Y, scan_id);
+                        const int after = t > fl ? t : fl;
+                        for (int d = 0; d < 6; d++) { const int wd = wake_dir(m, Y, d, after, scan_id); w = wd < w ? wd : w; }
+                        if (w == T_INF) Y = -1;
+                    }
                 }
                 unsigned hotmask = __ballot_sync(0xffffffffu, Y >= 0);
                 while (hotmask) {
                     const int src = __ffs(hotmask) - 1;
                     hotmask &= hotmask - 1;
                     const int Yh = __shfl_sync(0xffffffffu, Y, src);
-                    const int fl = event_floor(m, Yh, scan_id);
-                    nt = next_event_warp(m, Yh, t > fl ? t : fl);
+                    const int wh = __shfl_sync(0xffffffffu, w, src);
+                    const int nt = next_event_warp(m, Yh, wh);
                     if (nt == T_INF) continue;
                     int found = -1;
                     for (int k = lane; k < na; k += 32) if (m.act_slot[k] == Yh) found = k;
@@ -244,9 +284,10 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
                 }
             }
         }
-        // advance A: it stays active only while some neighbour pair could still pass
+        // advance A: sleep until the earliest time one of its pairs can pass again, drop it if none can
         int nt = T_INF;
-        if (static_test_warp(m, A)) nt = next_event_warp(m, A, t);
+        const int w = wake_warp(m, A, t, scan_id);
+        if (w != T_INF) nt = next_event_warp(m, A, w);
         if (nt != T_INF) { if (lane == 0) m.act_t[bk] = nt; }
         else { if (lane == 0) { m.act_slot[bk] = m.act_slot[na - 1]; m.act_t[bk] = m.act_t[na - 1]; } na--; }
         __syncwarp();

@@ -16,18 +16,21 @@
 
 constexpr int NS = 23;
 
-// A, inv, lu: NS*NS doubles in shared memory; perm: NS ints in shared memory.  Whole warp must call.
-__device__ void warp_lu_inverse(const double* A, double* inv, double* lu, int* perm) {
+// A (NS*NS, destroyed: ends up holding L\U in physical row order), inv (NS*NS out), perm (NS ints),
+// all in shared memory.  Whole warp must call.  Lane r owns physical row r; rows are never moved,
+// `pos` is the row's index in the pivoted order.  Loops are deliberately NOT unrolled: the code is
+// executed once per launch by one warp, so its size (instruction fetch), not its arithmetic, is
+// what costs time.  Row stride NS = 23 doubles is odd -> conflict-free 64-bit shared accesses.
+__device__ void warp_lu_inverse(double* A, double* inv, int* perm) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    double a[NS];
-    int pos = lane < NS ? lane : 1000 + lane;          // conceptual row index held by this lane
-#pragma unroll
-    for (int j = 0; j < NS; j++) a[j] = lane < NS ? A[lane * NS + j] : 0.0;
-#pragma unroll
+    const bool act = lane < NS;
+    double* row = A + (act ? lane : 0) * NS;
+    int pos = act ? lane : 1000 + lane;
+#pragma unroll 1
     for (int k = 0; k < NS; k++) {
-        // pivot: first row (in conceptual order) of maximal |a_ik|, i >= k
-        double v = (lane < NS && pos >= k) ? fabs(a[k]) : -1.0;
+        // pivot: first row (in pivoted order) of maximal |a_ik|, i >= k
+        double v = (act && pos >= k) ? fabs(row[k]) : -1.0;
         int p = pos;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -37,50 +40,51 @@ __device__ void warp_lu_inverse(const double* A, double* inv, double* lu, int* p
         }
         if (pos == p) pos = k; else if (pos == k) pos = p;          // row swap k <-> p
         const int L = __ffs(__ballot_sync(FULL, pos == k)) - 1;
-        const double d = __shfl_sync(FULL, a[k], L);
-        const bool below = lane < NS && pos > k;
-        const double l = a[k] / d;
-        if (below) a[k] = l;
-#pragma unroll
-        for (int j = k + 1; j < NS; j++) {
-            const double u = __shfl_sync(FULL, a[j], L);
-            if (below) a[j] = a[j] - l * u;
+        const double* prow = A + L * NS;
+        const bool below = act && pos > k;
+        if (below) {
+            const double l = row[k] / prow[k];
+            row[k] = l;
+#pragma unroll 1
+            for (int j = k + 1; j < NS; j++) row[j] = row[j] - l * prow[j];
         }
+        __syncwarp();
     }
-    if (lane < NS) {
-#pragma unroll
-        for (int j = 0; j < NS; j++) lu[pos * NS + j] = a[j];
-        perm[pos] = lane;
-    }
+    if (act) perm[pos] = lane;                                       // pivoted row i lives in physical row perm[i]
     __syncwarp();
-    if (lane < NS) {
-        double y[NS];
-#pragma unroll
+    // substitution against the permuted identity, lane c = column c of the inverse; y lives in inv[:, c]
+    if (act) {
+#pragma unroll 1
         for (int i = 0; i < NS; i++) {                               // L y = P e_c
-            double s = (perm[i] == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int j = 0; j < i; j++) s = s - lu[i * NS + j] * y[j];
-            y[i] = s;
+            const int pi = perm[i];
+            const double* r = A + pi * NS;
+            double s = (pi == lane) ? 1.0 : 0.0;
+#pragma unroll 1
+            for (int j = 0; j < i; j++) s = s - r[j] * inv[j * NS + lane];
+            inv[i * NS + lane] = s;
         }
-#pragma unroll
+#pragma unroll 1
         for (int i = NS - 1; i >= 0; i--) {                          // U x = y
-            double s = y[i];
-#pragma unroll
-            for (int j = i + 1; j < NS; j++) s = s - lu[i * NS + j] * y[j];
-            y[i] = s / lu[i * NS + i];
+            const double* r = A + perm[i] * NS;
+            double s = inv[i * NS + lane];
+#pragma unroll 1
+            for (int j = i + 1; j < NS; j++) s = s - r[j] * inv[j * NS + lane];
+            inv[i * NS + lane] = s / r[i];
         }
-#pragma unroll
-        for (int i = 0; i < NS; i++) inv[i * NS + lane] = y[i];
     }
     __syncwarp();
 }
 
 // C = op(A) * op(B), NS x NS in shared memory, entries strided over the block, left-to-right sums
 __device__ __forceinline__ void block_mm(const double* A, const double* B, double* C, bool transA, bool transB) {
+    const int sa = transA ? NS : 1, sb = transB ? 1 : NS;            // strides along k
     for (int q = threadIdx.x; q < NS * NS; q += blockDim.x) {
         const int i = q / NS, j = q % NS;
-        double s = (transA ? A[i] : A[i * NS]) * (transB ? B[j * NS] : B[j]);
-        for (int k = 1; k < NS; k++) s += (transA ? A[k * NS + i] : A[i * NS + k]) * (transB ? B[j * NS + k] : B[k * NS + j]);
+        const double* a = A + (transA ? i : i * NS);
+        const double* b = B + (transB ? j * NS : j);
+        double s = a[0] * b[0];
+#pragma unroll 2
+        for (int k = 1; k < NS; k++) s += a[k * sa] * b[k * sb];
         C[q] = s;
     }
 }
@@ -102,7 +106,7 @@ __device__ __forceinline__ void block_identity(double* J) {
 }
 
 __global__ void __launch_bounds__(64) k_update_begin(DevFilter* f, DevCtl* ctl) {
-    __shared__ double sA[NS * NS], sInv[NS * NS], sLU[NS * NS];
+    __shared__ double sA[NS * NS], sInv[NS * NS];
     __shared__ int perm[NS];
     const int tid = threadIdx.x;
     if (tid >= 32) {
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(64) k_update_begin(DevFilter* f, DevCtl* ctl) 
     }
     for (int q = tid; q < NS * NS; q += 32) sA[q] = f->P[q];
     __syncwarp();
-    warp_lu_inverse(sA, sInv, sLU, perm);
+    warp_lu_inverse(sA, sInv, perm);
     for (int q = tid; q < NS * NS; q += 32) f->Pinv[q] = sInv[q];
 }
 void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl) { k_update_begin<<<1, 64, 0, st>>>(f, ctl); }
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(256) k_ieskf_solve(DevFilter* f, DevCtl* ctl, 
     __syncthreads();
     // (4) H_^-1 (one warp), delta = -H_^-1 b_
     if (wid == 0) {
-        warp_lu_inverse(sA, sHinv, sC, perm);
+        warp_lu_inverse(sA, sHinv, perm);
         if (lane < NS) {
             double t = (-sHinv[lane * NS]) * sb[0];
             for (int k = 1; k < NS; k++) t += (-sHinv[lane * NS + k]) * sb[k];
