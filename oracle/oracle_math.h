@@ -358,10 +358,10 @@ inline Mat<N, N> inverse(const Mat<N, N>& Ain) {
             for (int j = 0; j < i; j++) s = s - lu(i, j) * y[j];
             y[i] = s;
         }
-        // backward: U x = y
+        // backward: U x = y; terms subtracted in the order the unknowns become available (j = N-1 first)
         for (int i = N - 1; i >= 0; i--) {
             double s = y[i];
-            for (int j = i + 1; j < N; j++) s = s - lu(i, j) * y[j];
+            for (int j = N - 1; j > i; j--) s = s - lu(i, j) * y[j];
             y[i] = s / lu(i, i);
         }
         for (int i = 0; i < N; i++) inv(i, c) = y[i];

@@ -338,9 +338,9 @@ VMP_HD void lu_inverse(const double* Ain, double* inv, double* lu /*N*N scratch*
             for (int j = 0; j < i; j++) s = s - lu[i * N + j] * y[j];
             y[i] = s;
         }
-        for (int i = N - 1; i >= 0; i--) {
+        for (int i = N - 1; i >= 0; i--) {       // terms subtracted in the order the unknowns become available
             double s = y[i];
-            for (int j = i + 1; j < N; j++) s = s - lu[i * N + j] * y[j];
+            for (int j = N - 1; j > i; j--) s = s - lu[i * N + j] * y[j];
             y[i] = s / lu[i * N + i];
         }
         for (int i = 0; i < N; i++) inv[i * N + c] = y[i];

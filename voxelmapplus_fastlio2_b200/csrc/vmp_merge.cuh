@@ -84,7 +84,12 @@ __device__ __forceinline__ int wake_warp(const DevMap& m, int A, int after, unsi
     return __shfl_sync(0xffffffffu, w, 0);
 }
 
-// 8 lanes per touched voxel, lanes 0..5 take one neighbour each
+__device__ __forceinline__ int event_floor(const DevMap& m, int A, unsigned scan_id) {
+    return (m.full_scan[A] == scan_id) ? m.full_idx[A] : -1;     // merge() runs only for points after the closing one
+}
+
+// 8 lanes per touched voxel, lanes 0..5 take one neighbour each; voxels whose merge() can succeed at
+// some time of this scan go into the active set of k_merge_serial with their first relevant event
 __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) {
     const int V = ctl->n_touched;
     const unsigned scan_id = ctl->scan_id;
@@ -93,14 +98,25 @@ __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) 
     const int ngroups = (gridDim.x * blockDim.x) >> 3;
     const int vend = (V + ngroups - 1) / ngroups * ngroups;          // keep the 8-lane groups converged
     for (int vi = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; vi < vend; vi += ngroups) {
-        bool p = false;
-        int A = -1;
+        int w = T_INF, A = -1;
         if (vi < V) {
             A = m.touched[vi];
-            if (m.evn[A] > 0 && sub < 6) p = wake_dir(m, A, sub, -1, scan_id) != T_INF;
+            if (m.evn[A] > 0 && sub < 6) w = wake_dir(m, A, sub, event_floor(m, A, scan_id), scan_id);
         }
-        const bool any = __any_sync(gmask, p);
-        if (any && sub == 0) m.hotlist[atomicAdd(&ctl->n_hot, 1)] = A;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { const int y = __shfl_xor_sync(gmask, w, o); w = y < w ? y : w; }
+        if (w == T_INF) continue;                                   // uniform within the 8-lane group
+        // first merge() call of A after the earliest time one of its pairs can pass
+        const int c = m.cnt[A], off = m.seg_off[A];
+        int best = T_INF;
+        for (int q = sub; q < c; q += 8) { const int i = m.seg[off + q]; if (i > w && i < best) best = i; }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { const int y = __shfl_xor_sync(gmask, best, o); best = y < best ? y : best; }
+        if (best != T_INF && sub == 0) {
+            const int k = atomicAdd(&ctl->n_hot, 1);
+            m.act_slot[k] = A;
+            m.act_t[k] = best;
+        }
     }
 }
 
@@ -113,9 +129,6 @@ __device__ int next_event_warp(const DevMap& m, int A, int after) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
     return best;
-}
-__device__ __forceinline__ int event_floor(const DevMap& m, int A, unsigned scan_id) {
-    return (m.full_scan[A] == scan_id) ? m.full_idx[A] : -1;     // merge() runs only for points after the closing one
 }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -205,19 +218,9 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
 // Ordered simulation of the merge() calls that can have an effect (one warp).
 __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
     const int lane = threadIdx.x;
-    const int nh = ctl->n_hot;
-    if (nh == 0) return;
+    int na = ctl->n_hot;                 // active set (voxel, first relevant event) prepared by k_merge_prefilter
+    if (na == 0) return;
     const unsigned scan_id = ctl->scan_id;
-    int na = 0;
-    for (int k = 0; k < nh; k++) {
-        const int A = m.hotlist[k];
-        const int fl = event_floor(m, A, scan_id);
-        const int w = wake_warp(m, A, fl, scan_id);
-        if (w == T_INF) continue;
-        const int t = next_event_warp(m, A, w);
-        if (t != T_INF) { if (lane == 0) { m.act_slot[na] = A; m.act_t[na] = t; } na++; }
-    }
-    __syncwarp();
     while (na > 0) {
         // earliest pending event
         int bt = T_INF, bk = -1;
@@ -235,7 +238,25 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
             // only its pair with X can have flipped; (b) a changed neighbour itself: all of its pairs.
             // One (X, direction) or one changed voxel per lane.
             const int nx = nchg + 1;
-            const int ncand = nx * 6 + nchg;
+            const int ncand = nx * 6;
+            // (b) first: the changed neighbours themselves, six directions on six lanes each
+            for (int q = 0; q < nchg; q++) {
+                const int Yb = changed[q];
+                if (m.cnt[Yb] == 0 || m.evn[Yb] == 0) continue;
+                const int fl = event_floor(m, Yb, scan_id);
+                const int wb = wake_warp(m, Yb, t > fl ? t : fl, scan_id);
+                if (wb == T_INF) continue;
+                const int nt = next_event_warp(m, Yb, wb);
+                if (nt == T_INF) continue;
+                int found = -1;
+                for (int k = lane; k < na; k += 32) if (m.act_slot[k] == Yb) found = k;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, found, o); found = y > found ? y : found; }
+                if (found >= 0) { if (lane == 0 && nt < m.act_t[found]) m.act_t[found] = nt; }
+                else if (na >= m.nmax) { if (lane == 0) atomicOr(&ctl->err, E_QUEUE); }
+                else { if (lane == 0) { m.act_slot[na] = Yb; m.act_t[na] = nt; } na++; }
+                __syncwarp();
+            }
             for (int c0 = 0; c0 < ncand; c0 += 32) {
                 const int c = c0 + lane;
                 int Y = -1, w = T_INF;
@@ -255,15 +276,6 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
                         if (bound + 1 < e) w = bound;
                     }
                     if (w == T_INF) Y = -1;
-                } else if (c < ncand) {
-                    Y = changed[c - nx * 6];
-                    if (m.cnt[Y] == 0 || m.evn[Y] == 0) Y = -1;
-                    if (Y >= 0) {
-                        const int fl = event_floor(m, Y, scan_id);
-                        const int after = t > fl ? t : fl;
-                        for (int d = 0; d < 6; d++) { const int wd = wake_dir(m, Y, d, after, scan_id); w = wd < w ? wd : w; }
-                        if (w == T_INF) Y = -1;
-                    }
                 }
                 unsigned hotmask = __ballot_sync(0xffffffffu, Y >= 0);
                 while (hotmask) {
