@@ -8,97 +8,80 @@
 //                    J, H_ = J^T P^-1 J + H, b_, delta = -H_^-1 b_, boxplus, convergence flag; on the
 //                    last executed iteration also P_ = L H_^-1 L^T
 //
-// The 23x23 inverse is LU with partial pivoting + substitution against the permuted identity
-// (what Eigen's PartialPivLU-based inverse() does), by ONE warp: lane r keeps matrix row r in
-// registers, the pivot search and the pivot-row broadcast go through shuffles.  To index the
-// current column with a compile-time register index inside a ROLLED loop (the code runs once
-// per launch: its size, i.e. instruction fetch, matters as much as its arithmetic) the row is
-// rotated left by one element per elimination step, so the pivot column is always a[0]; the
-// substitutions use the same trick on the right-hand-side columns (lane c = column c).  The
-// per-entry operation order equals the serial lu_inverse<> in vmp_math.cuh, bit for bit.
+// The 23x23 inverse is LU with partial pivoting + substitution against the permuted identity (what
+// Eigen's PartialPivLU-based inverse() does).  ncu on the first versions showed that a single warp
+// doing this is bound by its own instruction count (23k warp-instructions, ~4.6 cycles each), so the
+// work is spread one matrix entry per thread (529 of the CTA's threads): per elimination step one
+// pivot search by warp 0 and one rank-1 update by everybody, two barriers; per substitution step one
+// barrier.  Rows are never moved (a position array tracks the pivot order), and each entry sees
+// exactly the serial sequence of operations of lu_inverse<> in vmp_math.cuh -> bit-identical results.
 #pragma once
 
 constexpr int NS = 23;
+constexpr int SOLVE_THREADS = 544;      // 17 warps >= 23*23
 
-// A: NS*NS input (shared), inv: NS*NS output (shared), w1/w2: NS*NS scratch each (shared), perm: NS ints.
-// A may alias w1.  Whole warp must call.
-__device__ void warp_lu_inverse(const double* A, double* inv, double* w1, double* w2, int* perm) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const bool act = lane < NS;
-    double a[NS];
-#pragma unroll
-    for (int j = 0; j < NS; j++) a[j] = act ? A[lane * NS + j] : 0.0;
-    __syncwarp();
-    double* Lm = w1;            // multipliers by PHYSICAL row: Lm[r][k]
-    double* U = w2;             // U[k][j], j >= k, by pivoted row
-    int pos = act ? lane : 1000 + lane;                              // index of this lane's row in the pivoted order
-#pragma unroll 1
+struct LuShared {
+    double Lm[NS * NS];                 // multipliers by physical row
+    int pos[NS];                        // physical row -> index in pivot order
+    int perm[NS];                       // pivot order -> physical row
+    int piv;                            // physical pivot row of the current step
+};
+
+// A: NS*NS in shared, destroyed (ends as U by physical row); inv: NS*NS out.  Whole CTA must call.
+__device__ void block_lu_inverse(double* A, double* inv, LuShared& w) {
+    const int tid = threadIdx.x;
+    const int r = tid / NS, c = tid % NS;               // thread = entry (physical row r, column c)
+    const bool ent = tid < NS * NS;
+    if (tid < NS) w.pos[tid] = tid;
+    __syncthreads();
     for (int k = 0; k < NS; k++) {
-        // pivot: first row (in pivoted order) of maximal |a_ik|, i >= k
-        double v = (act && pos >= k) ? fabs(a[0]) : -1.0;
-        int p = pos;
+        if (tid < 32) {
+            // pivot: first row (in pivot order) of maximal |a_ik|, i >= k
+            const bool act = tid < NS;
+            int p = act ? w.pos[tid] : 1000 + tid;
+            const int mypos = p;
+            double v = (act && p >= k) ? fabs(A[tid * NS + k]) : -1.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double vo = __shfl_xor_sync(FULL, v, o);
-            const int po = __shfl_xor_sync(FULL, p, o);
-            if (vo > v || (vo == v && po < p)) { v = vo; p = po; }
-        }
-        if (pos == p) pos = k; else if (pos == k) pos = p;          // row swap k <-> p
-        const int L = __ffs(__ballot_sync(FULL, pos == k)) - 1;
-        const double d = __shfl_sync(FULL, a[0], L);
-        const bool below = act && pos > k;
-        const double l = a[0] / d;
-        if (below) Lm[lane * NS + k] = l;
-        if (lane == L) U[k * NS + k] = a[0];
-#pragma unroll
-        for (int j = 1; j < NS; j++) {
-            const double u = __shfl_sync(FULL, a[j], L);
-            if (lane == L && k + j < NS) U[k * NS + k + j] = a[j];
-            a[j - 1] = below ? a[j] - l * u : a[j];                  // eliminate and rotate left
-        }
-        a[NS - 1] = 0.0;
-    }
-    if (act) perm[pos] = lane;                                       // pivoted row i is physical row perm[i]
-    __syncwarp();
-    if (act) {
-        // forward substitution L y = P e_c (column c = lane), rotating right-hand side
-        double s[NS];
-#pragma unroll
-        for (int i = 0; i < NS; i++) s[i] = (perm[i] == lane) ? 1.0 : 0.0;
-#pragma unroll 1
-        for (int j = 0; j < NS; j++) {
-            const double y = s[0];
-            inv[j * NS + lane] = y;
-#pragma unroll
-            for (int i = 1; i < NS; i++) {
-                const int r = j + i;
-                const double lv = (r < NS) ? Lm[perm[r < NS ? r : 0] * NS + j] : 0.0;
-                s[i - 1] = s[i] - lv * y;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double vo = __shfl_xor_sync(0xffffffffu, v, o);
+                const int po = __shfl_xor_sync(0xffffffffu, p, o);
+                if (vo > v || (vo == v && po < p)) { v = vo; p = po; }
             }
-            s[NS - 1] = 0.0;
-        }
-        // backward substitution U x = y, from the last unknown, rotating the same way
-#pragma unroll
-        for (int i = 0; i < NS; i++) s[i] = inv[(NS - 1 - i) * NS + lane];
-#pragma unroll 1
-        for (int q = 0; q < NS; q++) {
-            const int i0 = NS - 1 - q;
-            const double x = s[0] / U[i0 * NS + i0];
-            inv[i0 * NS + lane] = x;
-#pragma unroll
-            for (int i = 1; i < NS; i++) {
-                const int r = i0 - i;
-                const double uv = (r >= 0) ? U[(r >= 0 ? r : 0) * NS + i0] : 0.0;
-                s[i - 1] = s[i] - uv * x;
+            if (act) {
+                if (mypos == p) { w.pos[tid] = k; w.piv = tid; }   // row swap k <-> p in the pivot order
+                else if (mypos == k) w.pos[tid] = p;
             }
-            s[NS - 1] = 0.0;
         }
+        __syncthreads();
+        if (ent && w.pos[r] > k && c >= k) {
+            const int L = w.piv;
+            const double l = A[r * NS + k] / A[L * NS + k];
+            if (c == k) w.Lm[r * NS + k] = l;
+            else A[r * NS + c] = A[r * NS + c] - l * A[L * NS + c];
+        }
+        __syncthreads();
     }
-    __syncwarp();
+    if (tid < NS) w.perm[w.pos[tid]] = tid;
+    __syncthreads();
+    // thread (i, c): entry i (pivot order) of column c of the inverse
+    const int i = r;
+    const int pr = ent ? w.perm[i] : 0;
+    double s = (ent && pr == c) ? 1.0 : 0.0;
+    for (int j = 0; j < NS; j++) {                       // L y = P e_c
+        if (ent && i == j) inv[j * NS + c] = s;
+        __syncthreads();
+        if (ent && i > j) s = s - w.Lm[pr * NS + j] * inv[j * NS + c];
+    }
+    __syncthreads();
+    for (int j = NS - 1; j >= 0; j--) {                  // U x = y, unknowns in the order they become available
+        if (ent && i == j) inv[j * NS + c] = s / A[pr * NS + j];
+        __syncthreads();
+        if (ent && i < j) s = s - A[pr * NS + j] * inv[j * NS + c];
+    }
+    __syncthreads();
 }
 
-// C = op(A) * op(B), NS x NS in shared memory, entries strided over the block, left-to-right sums
+// C = op(A) * op(B), NS x NS in shared memory, one entry per thread, left-to-right sums
 __device__ __forceinline__ void block_mm(const double* A, const double* B, double* C, bool transA, bool transB) {
     const int sa = transA ? NS : 1, sb = transB ? 1 : NS;            // strides along k
     for (int q = threadIdx.x; q < NS * NS; q += blockDim.x) {
@@ -124,59 +107,53 @@ __device__ __noinline__ void jac_blocks(double* J, const double* delta, const do
         J[21 * NS + 21] = jg(0, 0); J[21 * NS + 22] = jg(0, 1); J[22 * NS + 21] = jg(1, 0); J[22 * NS + 22] = jg(1, 1);
     }
 }
-__device__ __forceinline__ void block_identity(double* J) {
-    for (int q = threadIdx.x; q < NS * NS; q += blockDim.x) J[q] = (q / NS == q % NS) ? 1.0 : 0.0;
-}
 
-__global__ void __launch_bounds__(64) k_update_begin(DevFilter* f, DevCtl* ctl) {
-    __shared__ double sA[NS * NS], sInv[NS * NS], sW[NS * NS];
-    __shared__ int perm[NS];
+__global__ void __launch_bounds__(SOLVE_THREADS) k_update_begin(DevFilter* f, DevCtl* ctl) {
+    __shared__ double sA[NS * NS], sInv[NS * NS];
+    __shared__ LuShared lu;
     const int tid = threadIdx.x;
-    if (tid >= 32) {
-        const int t = tid - 32;
-        f->xpred[t] = f->x[t];
-        if (t < 4) f->xpred[32 + t] = f->x[32 + t];
-        if (t == 0) { ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
-        if (t < 8) ctl->effect[t] = 0;
-        return;
-    }
-    for (int q = tid; q < NS * NS; q += 32) sA[q] = f->P[q];
-    __syncwarp();
-    warp_lu_inverse(sA, sInv, sA, sW, perm);
-    for (int q = tid; q < NS * NS; q += 32) f->Pinv[q] = sInv[q];
+    if (tid < 36) f->xpred[tid] = f->x[tid];
+    if (tid == 0) { ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
+    if (tid < 8) ctl->effect[tid] = 0;
+    if (tid < NS * NS) sA[tid] = f->P[tid];
+    __syncthreads();
+    block_lu_inverse(sA, sInv, lu);
+    if (tid < NS * NS) f->Pinv[tid] = sInv[tid];
 }
-void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl) { k_update_begin<<<1, 64, 0, st>>>(f, ctl); }
+void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl) { k_update_begin<<<1, SOLVE_THREADS, 0, st>>>(f, ctl); }
 
-constexpr int RED_CHUNKS = 8;
+constexpr int RED_CHUNKS = 4;
 
 template <bool EXT>
-__global__ void __launch_bounds__(256) k_ieskf_solve(DevFilter* f, DevCtl* ctl, const double* __restrict__ partials, int nblocks) {
+__global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, DevCtl* ctl, const double* __restrict__ partials, int nblocks) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;
+    constexpr int W_MAN = 16;           // the warp that runs the manifold operations
     __shared__ double sA[NS * NS], sB[NS * NS], sC[NS * NS], sJ[NS * NS], sHinv[NS * NS];
     __shared__ double sHm[NV], sRed[RED_CHUNKS][NV], sdelta[NS], sb[NS], sdx[NS], sx[36], sxp[36];
-    __shared__ int perm[NS], s_last;
+    __shared__ LuShared lu;
+    __shared__ int s_last;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     if (ctl->done) return;
     const int it = ctl->iter;
 
     // (1) concurrently: reduction of the per-block partials (fixed order: RED_CHUNKS contiguous block
     //     ranges, then the chunk sums in ascending order) | boxminus | P^-1 load | J := I
-    if (wid == 7) {
+    if (wid == W_MAN) {
         for (int q = lane; q < 36; q += 32) { sx[q] = f->x[q]; sxp[q] = f->xpred[q]; }
         __syncwarp();
         if (lane == 0) { const St x = st_load(sx), xp = st_load(sxp); st_boxminus(x, xp, sdelta); }
     } else {
-        for (int q = tid; q < NV * RED_CHUNKS; q += 224) {
-            const int v = q % NV, c = q / NV;
+        if (tid < NV * RED_CHUNKS) {
+            const int v = tid % NV, c = tid / NV;
             const int b0 = (int)((long long)nblocks * c / RED_CHUNKS), b1 = (int)((long long)nblocks * (c + 1) / RED_CHUNKS);
             double t = 0.0;
 #pragma unroll 4
             for (int b = b0; b < b1; b++) t += partials[(size_t)b * PARTIAL_STRIDE + v];
             sRed[c][v] = t;
         }
-        for (int q = tid; q < NS * NS; q += 224) { sB[q] = f->Pinv[q]; sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0; }
+        for (int q = tid; q < NS * NS; q += 32 * W_MAN) { sB[q] = f->Pinv[q]; sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0; }
     }
     __syncthreads();
     if (tid < NV) {
@@ -186,30 +163,31 @@ __global__ void __launch_bounds__(256) k_ieskf_solve(DevFilter* f, DevCtl* ctl, 
         sHm[tid] = t;
     }
     // (2) the blocks of J (ieskf.cpp:136-139)
-    if (wid == 7 && lane < 3) jac_blocks(sJ, sdelta, sx + 33, sxp + 33, lane);
+    if (wid == W_MAN && lane < 3) jac_blocks(sJ, sdelta, sx + 33, sxp + 33, lane);
     __syncthreads();
     // (3) JtPinv = J^T P^-1 ; b_ = JtPinv delta ; H_ = JtPinv J (+ measurement H, b in the top-left corner)
     block_mm(sJ, sB, sC, true, false);
     __syncthreads();
-    if (tid < NS) {
-        double t = sC[tid * NS] * sdelta[0];
-        for (int k = 1; k < NS; k++) t += sC[tid * NS + k] * sdelta[k];
+    if (wid == W_MAN && lane < NS) {
+        double t = sC[lane * NS] * sdelta[0];
+        for (int k = 1; k < NS; k++) t += sC[lane * NS + k] * sdelta[k];
         t = 0.0 + t;
-        if (tid < D) t += sHm[NH + tid];
-        sb[tid] = t;
+        if (lane < D) t += sHm[NH + lane];
+        sb[lane] = t;
     }
-    block_mm(sC, sJ, sA, false, false);
-    __syncthreads();
-    for (int q = tid; q < NS * NS; q += blockDim.x) {
-        const int i = q / NS, j = q % NS;
-        double h = 0.0 + sA[q];
+    if (tid < NS * NS) {
+        const int i = tid / NS, j = tid % NS;
+        double h = sC[i * NS] * sJ[j];
+#pragma unroll 2
+        for (int k = 1; k < NS; k++) h += sC[i * NS + k] * sJ[k * NS + j];
+        h = 0.0 + h;
         if (i < D && j < D) { const int a = i < j ? i : j, c = i < j ? j : i; h += sHm[a * D - a * (a - 1) / 2 + (c - a)]; }
-        sA[q] = h;
+        sA[tid] = h;
     }
     __syncthreads();
-    // (4) H_^-1 (one warp), delta = -H_^-1 b_
-    if (wid == 0) {
-        warp_lu_inverse(sA, sHinv, sB, sC, perm);
+    // (4) H_^-1, delta = -H_^-1 b_
+    block_lu_inverse(sA, sHinv, lu);
+    if (wid == W_MAN) {
         if (lane < NS) {
             double t = (-sHinv[lane * NS]) * sb[0];
             for (int k = 1; k < NS; k++) t += (-sHinv[lane * NS + k]) * sb[k];
@@ -234,22 +212,21 @@ __global__ void __launch_bounds__(256) k_ieskf_solve(DevFilter* f, DevCtl* ctl, 
             s_last = last;
         }
     } else {
-        // L := I while warp 0 inverts (sJ is free: H_ is formed)
-        for (int q = tid - 32; q < NS * NS; q += 224) sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0;
+        for (int q = tid; q < NS * NS; q += 32 * W_MAN) sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0;     // L := I meanwhile
     }
     __syncthreads();
     if (!s_last) return;
     // (6) P_ = L H_^-1 L^T with L from the final delta and the updated state (ieskf.cpp:151-155)
-    if (wid == 7 && lane < 3) jac_blocks(sJ, sdx, sx + 33, sxp + 33, lane);
+    if (wid == W_MAN && lane < 3) jac_blocks(sJ, sdx, sx + 33, sxp + 33, lane);
     __syncthreads();
     block_mm(sJ, sHinv, sC, false, false);
     __syncthreads();
     block_mm(sC, sJ, sB, false, true);
     __syncthreads();
-    for (int q = tid; q < NS * NS; q += blockDim.x) f->P[q] = sB[q];
+    if (tid < NS * NS) f->P[tid] = sB[tid];
 }
 
 void launch_solve(cudaStream_t st, bool ext, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
-    if (ext) k_ieskf_solve<true><<<1, 256, 0, st>>>(f, ctl, partials, nblocks);
-    else k_ieskf_solve<false><<<1, 256, 0, st>>>(f, ctl, partials, nblocks);
+    if (ext) k_ieskf_solve<true><<<1, SOLVE_THREADS, 0, st>>>(f, ctl, partials, nblocks);
+    else k_ieskf_solve<false><<<1, SOLVE_THREADS, 0, st>>>(f, ctl, partials, nblocks);
 }
