@@ -186,6 +186,9 @@ int vmp_dump_evicted(vmp_handle h, int64_t* keys, int cap, int* count);
 int vmp_map_size(vmp_handle h, int* count);
 /* number of kernel launches (graph kernel nodes included) issued by this handle so far */
 int64_t vmp_launch_count(vmp_handle h);
+/* internal counters of the last map update (8 ints): [0] merge active set after the prefilter,
+ * [1] merge events simulated, [2] voxels activated by re-examination */
+int vmp_debug_counters(vmp_handle h, int* out8);
 
 /* Per-kernel device timing.  With profiling on, vmp_scan / vmp_scan_dev launch the very same
  * kernels one by one on the handle's stream with a CUDA event after each (instead of the graph)

@@ -221,6 +221,12 @@ class HotPath:
     def launch_count(self) -> int:
         return int(self._lib.vmp_launch_count(self._h))
 
+    def debug_counters(self):
+        out = (C.c_int * 8)()
+        self._lib.vmp_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        self._check(self._lib.vmp_debug_counters(self._h, out))
+        return list(out)
+
     def profile_enable(self, on: bool = True):
         """Per-kernel CUDA-event timing: scans run the same kernels one by one instead of the graph."""
         self._lib.vmp_profile_enable.argtypes = [C.c_void_p, C.c_int]

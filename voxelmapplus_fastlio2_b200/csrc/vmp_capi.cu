@@ -36,6 +36,7 @@ struct ScanIn { int n; int has_state; double x[36]; double P[529]; };
 struct ScanOut {
     double x[36]; double P[529];
     int iter, converged, effect[8], err, pad;
+    int dbg[8];
     DevStats st;
 };
 
@@ -52,7 +53,7 @@ __global__ void k_scan_out(const DevFilter* f, const DevCtl* ctl, ScanOut* out) 
     for (int q = tid; q < 529; q += blockDim.x) out->P[q] = f->P[q];
     if (tid < 36) out->x[tid] = f->x[tid];
     if (tid < 8) out->effect[tid] = ctl->effect[tid];
-    if (tid == 0) { out->iter = ctl->iter; out->converged = ctl->converged; out->err = ctl->err; out->st = ctl->st; }
+    if (tid == 0) { out->iter = ctl->iter; out->converged = ctl->converged; out->err = ctl->err; out->st = ctl->st; for (int q = 0; q < 8; q++) out->dbg[q] = ctl->dbg[q]; }
 }
 // H (12x12) / b (12) / effect of one measurement pass from the block partials (vmp_measure)
 __global__ void k_reduce_partials(const double* partials, int nblocks, int ext, double* out /*144+12+1*/) {
@@ -630,6 +631,11 @@ int vmp_dump_evicted(vmp_handle h, int64_t* keys, int cap, int* count) {
 }
 
 int64_t vmp_launch_count(vmp_handle h) { return h ? h->launches : 0; }
+int vmp_debug_counters(vmp_handle h, int* out8) {
+    if (!h || !out8) return VMP_ERR_INVALID_ARG;
+    for (int q = 0; q < 8; q++) out8[q] = h->h_out->dbg[q];
+    return VMP_OK;
+}
 
 int vmp_profile_enable(vmp_handle h, int on) {
     int r = check_n(h, 0, "vmp_profile_enable");

@@ -64,6 +64,7 @@ struct DevCtl {
     unsigned long long group_counter;
     int err;
     int pad0;
+    int dbg[8];                         // debug counters of the last map update: [0] active set after the prefilter, [1] merge events simulated, [2] re-examinations that activated a voxel
     DevStats st;
     // IEKF
     int iter;                           // executed iterations

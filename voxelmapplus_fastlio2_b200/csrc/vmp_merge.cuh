@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
     const int lane = threadIdx.x;
     int na = ctl->n_hot;                 // active set (voxel, first relevant event) prepared by k_merge_prefilter
     if (na == 0) return;
+    if (lane == 0) ctl->dbg[0] = na;
+    int n_events = 0, n_react = 0;
     const unsigned scan_id = ctl->scan_id;
     while (na > 0) {
         // earliest pending event
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
         const int A = m.act_slot[bk], t = bt;
         int changed[6];
         const int nchg = merge_at_warp(m, ctl, A, t, scan_id, changed);
+        n_events++;
         if (nchg > 0) {
             // planes / groups of A and changed[] moved.  (a) every voxel Y adjacent to a changed voxel X:
             // only its pair with X can have flipped; (b) a changed neighbour itself: all of its pairs.
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
                     for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, found, o); found = y > found ? y : found; }
                     if (found >= 0) { if (lane == 0 && nt < m.act_t[found]) m.act_t[found] = nt; }
                     else if (na >= m.nmax) { if (lane == 0) atomicOr(&ctl->err, E_QUEUE); }
-                    else { if (lane == 0) { m.act_slot[na] = Yh; m.act_t[na] = nt; } na++; }
+                    else { if (lane == 0) { m.act_slot[na] = Yh; m.act_t[na] = nt; } na++; n_react++; }
                     __syncwarp();
                 }
             }
@@ -304,4 +307,5 @@ __global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
         else { if (lane == 0) { m.act_slot[bk] = m.act_slot[na - 1]; m.act_t[bk] = m.act_t[na - 1]; } na--; }
         __syncwarp();
     }
+    if (lane == 0) { ctl->dbg[1] = n_events; ctl->dbg[2] = n_react; }
 }
