@@ -129,13 +129,14 @@ int dalloc(vmp_handle_t* h, T** p, size_t count) {
 
 int check_device_err(vmp_handle_t* h, int err) {
     if (!err) return VMP_OK;
-    set_error("device reported error bits 0x%x:%s%s%s%s%s%s", err,
+    set_error("device reported error bits 0x%x:%s%s%s%s%s%s%s", err,
               (err & E_KEY_RANGE) ? " voxel coordinate outside +-2^20;" : "",
               (err & E_POOL) ? " voxel slot pool exhausted;" : "",
               (err & E_LRU_EXHAUSTED) ? " map_capacity smaller than the voxels one scan touches (LRU victim was touched in the same scan);" : "",
               (err & E_REFIT_OVERFLOW) ? " refit of a voxel holding more than max_point_thresh points;" : "",
               (err & E_QUEUE) ? " internal queue overflow;" : "",
-              (err & E_HASH_FULL) ? " hash table full;" : "");
+              (err & E_HASH_FULL) ? " hash table full;" : "",
+              (err & E_MERGE_DEPTH) ? " merge cascade deeper than 2 inside one scan;" : "");
     (void)h;
     return VMP_ERR_CAPACITY;
 }

@@ -42,6 +42,7 @@ constexpr int E_LRU_EXHAUSTED = 4;      // eviction would have to take a voxel t
 constexpr int E_REFIT_OVERFLOW = 8;     // refit of a voxel holding more than max_point_thresh points (build overflow + thresh 1)
 constexpr int E_QUEUE = 16;             // internal queue overflow in the serial merge / eviction kernels
 constexpr int E_HASH_FULL = 32;
+constexpr int E_MERGE_DEPTH = 64;       // a merge succeeded at cascade depth > 2 inside one scan (parallel rounds would not be exact)
 
 struct DevStats {                       // == vmp_update_stats order
     long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size;

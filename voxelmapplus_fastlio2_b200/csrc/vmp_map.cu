@@ -617,7 +617,7 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
     k_map_fill<<<sm_count * 4, 128, 0, st>>>(m, s, ctl, build ? 1 : 0); launches++; mark(mk, VMP_K_MAP_FILL);
     if (!build) {
         k_merge_prefilter<<<sm_count, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
-        k_merge_serial<<<1, 32, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
+        k_merge_rounds<<<1, 512, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
     }
     k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND);
     k_map_finalize<<<sm_count, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_FINALIZE);

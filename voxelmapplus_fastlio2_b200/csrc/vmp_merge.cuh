@@ -206,7 +206,7 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
             uint32_t fa; int na;
             hot_get_fn(m.hot, A, fa, na);
             hot_set_fn(m.hot, A, fa | F_MERGED, na);
-            ctl->st.n_merge += 1;
+            atomicAdd((unsigned long long*)&ctl->st.n_merge, 1ull);
         }
         if (lane == d) hot_set_fn(m.hot, Bd, fB | F_MERGED, cntB);      // neighbour's MERGED flag, by the lane that loaded it
         __syncwarp();
@@ -215,97 +215,188 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
     return nchg;
 }
 
-// Ordered simulation of the merge() calls that can have an effect (one warp).
-__global__ void __launch_bounds__(32) k_merge_serial(DevMap m, DevCtl* ctl) {
-    const int lane = threadIdx.x;
-    int na = ctl->n_hot;                 // active set (voxel, first relevant event) prepared by k_merge_prefilter
-    if (na == 0) return;
-    if (lane == 0) ctl->dbg[0] = na;
-    int n_events = 0, n_react = 0;
-    const unsigned scan_id = ctl->scan_id;
-    while (na > 0) {
-        // earliest pending event
-        int bt = T_INF, bk = -1;
-        for (int k = lane; k < na; k += 32) { const int t = m.act_t[k]; if (t < bt) { bt = t; bk = k; } }
+// ------------------------------------------------------------------------- event simulation in rounds
+// Active set in shared memory.  An entry is READY when no other entry has an earlier event within
+// Manhattan distance MERGE_R of its voxel.  One event touches its voxel and the six neighbours
+// (writes) and looks at the neighbours' neighbours (reads): footprint radius 2.  A voxel that is
+// activated by an event lies within 2 of it, so a cascade of depth l stays within 2l + 2 of the
+// root; with MERGE_R = 8 every event of depth <= 2 of one root is disjoint from the footprint of
+// any entry that ran concurrently with (or before) that root.  Ready entries therefore commute
+// with everything they do not wait for, and processing them in parallel (one warp each) gives the
+// same result as the reference's strictly sequential order.  A successful merge at depth 3 would
+// leave that guarantee; it is reported (E_MERGE_DEPTH) instead of being silently reordered.
+constexpr int MERGE_R = 8;
+constexpr int MERGE_CAP = 2048;
+constexpr int MERGE_MAX_DEPTH = 2;
+
+struct ActiveSet {
+    int slot[MERGE_CAP];        // voxel slot | depth << 28
+    int t[MERGE_CAP];           // next event (point index), T_INF = retired
+    short kx[MERGE_CAP], ky[MERGE_CAP], kz[MERGE_CAP];   // voxel coordinate relative to the first entry (clamped)
+    unsigned char ready[MERGE_CAP];
+    int n;                      // entries (including retired ones until compaction)
+    int ox, oy, oz;
+};
+
+__device__ __forceinline__ void as_set_key(ActiveSet& as, int k, unsigned long long pk) {
+    long long x, y, z;
+    unpack_key(pk, x, y, z);
+    const long long dx = x - as.ox, dy = y - as.oy, dz = z - as.oz;
+    // clamping only ever makes two voxels look closer -> more waiting, never less
+    as.kx[k] = (short)(dx < -30000 ? -30000 : dx > 30000 ? 30000 : dx);
+    as.ky[k] = (short)(dy < -30000 ? -30000 : dy > 30000 ? 30000 : dy);
+    as.kz[k] = (short)(dz < -30000 ? -30000 : dz > 30000 ? 30000 : dz);
+}
+
+// insert voxel Y (first relevant event nt, cascade depth) or pull its pending event earlier; whole warp calls
+__device__ void as_activate(const DevMap& m, DevCtl* ctl, ActiveSet& as, int Y, int nt, int depth) {
+    const int lane = threadIdx.x & 31;
+    const int n = as.n;                                   // entries appended concurrently by other warps are never Y:
+    int found = -1;                                       // they lie > MERGE_R - 4 away from this warp's footprint
+    for (int k = lane; k < n; k += 32) if ((as.slot[k] & 0x0FFFFFFF) == Y && as.t[k] != T_INF) found = k;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int yt = __shfl_xor_sync(0xffffffffu, bt, o), yk = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (yt < bt) { bt = yt; bk = yk; }
+    for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, found, o); found = y > found ? y : found; }
+    if (lane == 0) {
+        if (found >= 0) {
+            atomicMin(&as.t[found], nt);
+            const int d0 = as.slot[found] >> 28;
+            if (depth > d0) as.slot[found] = Y | (depth << 28);
+        } else {
+            const int k = atomicAdd(&as.n, 1);
+            if (k >= MERGE_CAP) { atomicOr(&ctl->err, E_QUEUE); atomicSub(&as.n, 1); }
+            else {
+                as.slot[k] = Y | (depth << 28);
+                as.t[k] = nt;
+                as.ready[k] = 0;
+                as_set_key(as, k, m.skey[Y]);
+                atomicAdd(&ctl->dbg[2], 1);
+            }
         }
-        const int A = m.act_slot[bk], t = bt;
-        int changed[6];
-        const int nchg = merge_at_warp(m, ctl, A, t, scan_id, changed);
-        n_events++;
-        if (nchg > 0) {
-            // planes / groups of A and changed[] moved.  (a) every voxel Y adjacent to a changed voxel X:
-            // only its pair with X can have flipped; (b) a changed neighbour itself: all of its pairs.
-            // One (X, direction) or one changed voxel per lane.
-            const int nx = nchg + 1;
-            const int ncand = nx * 6;
-            // (b) first: the changed neighbours themselves, six directions on six lanes each
-            for (int q = 0; q < nchg; q++) {
-                const int Yb = changed[q];
-                if (m.cnt[Yb] == 0 || m.evn[Yb] == 0) continue;
-                const int fl = event_floor(m, Yb, scan_id);
-                const int wb = wake_warp(m, Yb, t > fl ? t : fl, scan_id);
-                if (wb == T_INF) continue;
-                const int nt = next_event_warp(m, Yb, wb);
-                if (nt == T_INF) continue;
-                int found = -1;
-                for (int k = lane; k < na; k += 32) if (m.act_slot[k] == Yb) found = k;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, found, o); found = y > found ? y : found; }
-                if (found >= 0) { if (lane == 0 && nt < m.act_t[found]) m.act_t[found] = nt; }
-                else if (na >= m.nmax) { if (lane == 0) atomicOr(&ctl->err, E_QUEUE); }
-                else { if (lane == 0) { m.act_slot[na] = Yb; m.act_t[na] = nt; } na++; }
+    }
+    __syncwarp();
+}
+
+// one merge() call of entry j (voxel A at time t) and everything it triggers; whole warp calls
+__device__ void process_event(const DevMap& m, DevCtl* ctl, ActiveSet& as, int j, unsigned scan_id) {
+    const int lane = threadIdx.x & 31;
+    const int A = as.slot[j] & 0x0FFFFFFF, depth = as.slot[j] >> 28, t = as.t[j];
+    int changed[6];
+    const int nchg = merge_at_warp(m, ctl, A, t, scan_id, changed);
+    if (nchg > 0) {
+        if (depth > MERGE_MAX_DEPTH && lane == 0) atomicOr(&ctl->err, E_MERGE_DEPTH);
+        const int dn = depth + 1 > 7 ? 7 : depth + 1;
+        // planes / groups of A and changed[] moved.  (b) a changed neighbour itself: all of its pairs;
+        // (a) every voxel Y adjacent to a changed voxel X: only its pair with X can have flipped.
+        for (int q = 0; q < nchg; q++) {
+            const int Yb = changed[q];
+            if (m.cnt[Yb] == 0 || m.evn[Yb] == 0) continue;
+            const int fl = event_floor(m, Yb, scan_id);
+            const int wb = wake_warp(m, Yb, t > fl ? t : fl, scan_id);
+            if (wb == T_INF) continue;
+            const int nt = next_event_warp(m, Yb, wb);
+            if (nt != T_INF) as_activate(m, ctl, as, Yb, nt, dn);
+        }
+        const int ncand = (nchg + 1) * 6;
+        for (int c0 = 0; c0 < ncand; c0 += 32) {
+            const int c = c0 + lane;
+            int Y = -1, w = T_INF;
+            if (c < ncand) {
+                const int X = (c / 6 == 0) ? A : changed[c / 6 - 1];
+                bool ok;
+                const unsigned long long nk = nbr_key(m.skey[X], c % 6, ok);
+                Y = ok ? hash_find(m, nk) : -1;
+                if (Y == A || (Y >= 0 && (m.cnt[Y] == 0 || m.evn[Y] == 0))) Y = -1;   // no merge() call of Y in this scan
+                for (int q = 0; q < nchg && Y >= 0; q++) if (changed[q] == Y) Y = -1;  // handled by (b)
+                if (Y >= 0 && pair_static(m, Y, X)) {
+                    int s, e;
+                    pair_window(m, X, scan_id, s, e);
+                    const int fl = event_floor(m, Y, scan_id);
+                    int bound = s > t ? s : t;
+                    bound = fl > bound ? fl : bound;
+                    if (bound + 1 < e) w = bound;
+                }
+                if (w == T_INF) Y = -1;
+            }
+            unsigned hotmask = __ballot_sync(0xffffffffu, Y >= 0);
+            while (hotmask) {
+                const int src = __ffs(hotmask) - 1;
+                hotmask &= hotmask - 1;
+                const int Yh = __shfl_sync(0xffffffffu, Y, src);
+                const int wh = __shfl_sync(0xffffffffu, w, src);
+                const int nt = next_event_warp(m, Yh, wh);
+                if (nt != T_INF) as_activate(m, ctl, as, Yh, nt, dn);
+            }
+        }
+    }
+    // advance A: sleep until the earliest time one of its pairs can pass again, retire it if none can
+    int nt = T_INF;
+    const int w = wake_warp(m, A, t, scan_id);
+    if (w != T_INF) nt = next_event_warp(m, A, w);
+    if (lane == 0) { as.t[j] = nt; atomicAdd(&ctl->dbg[1], 1); }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
+    __shared__ ActiveSet as;
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n0 = ctl->n_hot;                       // (voxel, first relevant event) pairs prepared by k_merge_prefilter
+    if (n0 == 0) return;
+    if (n0 > MERGE_CAP) { if (tid == 0) atomicOr(&ctl->err, E_QUEUE); return; }
+    const unsigned scan_id = ctl->scan_id;
+    if (tid == 0) {
+        long long x, y, z;
+        unpack_key(m.skey[m.act_slot[0]], x, y, z);
+        as.ox = (int)x; as.oy = (int)y; as.oz = (int)z;
+        as.n = n0;
+        ctl->dbg[0] = n0;
+    }
+    __syncthreads();
+    for (int k = tid; k < n0; k += blockDim.x) {
+        const int A = m.act_slot[k];
+        as.slot[k] = A;
+        as.t[k] = m.act_t[k];
+        as_set_key(as, k, m.skey[A]);
+    }
+    __syncthreads();
+    for (int round = 0; round < 100000; round++) {
+        const int n = as.n;
+        // readiness: no other entry with an earlier event within MERGE_R
+        for (int j = tid; j < n; j += blockDim.x) {
+            const int tj = as.t[j];
+            bool rdy = tj != T_INF;
+            if (rdy) {
+                const int x = as.kx[j], y = as.ky[j], z = as.kz[j];
+                for (int i = 0; i < n; i++) {
+                    if (as.t[i] < tj && abs(as.kx[i] - x) + abs(as.ky[i] - y) + abs(as.kz[i] - z) <= MERGE_R) { rdy = false; break; }
+                }
+            }
+            as.ready[j] = rdy ? 1 : 0;
+        }
+        __syncthreads();
+        for (int j = wid; j < n; j += (blockDim.x >> 5)) {
+            if (as.ready[j]) process_event(m, ctl, as, j, scan_id);      // warp-uniform branch
+        }
+        __syncthreads();
+        // compaction of retired entries (one warp), keeps the rest in place order
+        if (wid == 0) {
+            const int nn = as.n;
+            int w = 0;
+            for (int base = 0; base < nn; base += 32) {
+                const int k = base + lane;
+                const bool live = k < nn && as.t[k] != T_INF;
+                const int sl = live ? as.slot[k] : 0, tt = live ? as.t[k] : 0;
+                const short kx = live ? as.kx[k] : 0, ky = live ? as.ky[k] : 0, kz = live ? as.kz[k] : 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, live);
+                const int pos = w + __popc(bal & ((1u << lane) - 1));
+                __syncwarp();
+                if (live) { as.slot[pos] = sl; as.t[pos] = tt; as.kx[pos] = kx; as.ky[pos] = ky; as.kz[pos] = kz; }
+                w += __popc(bal);
                 __syncwarp();
             }
-            for (int c0 = 0; c0 < ncand; c0 += 32) {
-                const int c = c0 + lane;
-                int Y = -1, w = T_INF;
-                if (c < nx * 6) {
-                    const int X = (c / 6 == 0) ? A : changed[c / 6 - 1];
-                    bool ok;
-                    const unsigned long long nk = nbr_key(m.skey[X], c % 6, ok);
-                    Y = ok ? hash_find(m, nk) : -1;
-                    if (Y == A || (Y >= 0 && (m.cnt[Y] == 0 || m.evn[Y] == 0))) Y = -1;   // no merge() call of Y in this scan
-                    for (int q = 0; q < nchg && Y >= 0; q++) if (changed[q] == Y) Y = -1;  // handled by (b)
-                    if (Y >= 0 && pair_static(m, Y, X)) {
-                        int s, e;
-                        pair_window(m, X, scan_id, s, e);
-                        const int fl = event_floor(m, Y, scan_id);
-                        int bound = s > t ? s : t;
-                        bound = fl > bound ? fl : bound;
-                        if (bound + 1 < e) w = bound;
-                    }
-                    if (w == T_INF) Y = -1;
-                }
-                unsigned hotmask = __ballot_sync(0xffffffffu, Y >= 0);
-                while (hotmask) {
-                    const int src = __ffs(hotmask) - 1;
-                    hotmask &= hotmask - 1;
-                    const int Yh = __shfl_sync(0xffffffffu, Y, src);
-                    const int wh = __shfl_sync(0xffffffffu, w, src);
-                    const int nt = next_event_warp(m, Yh, wh);
-                    if (nt == T_INF) continue;
-                    int found = -1;
-                    for (int k = lane; k < na; k += 32) if (m.act_slot[k] == Yh) found = k;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, found, o); found = y > found ? y : found; }
-                    if (found >= 0) { if (lane == 0 && nt < m.act_t[found]) m.act_t[found] = nt; }
-                    else if (na >= m.nmax) { if (lane == 0) atomicOr(&ctl->err, E_QUEUE); }
-                    else { if (lane == 0) { m.act_slot[na] = Yh; m.act_t[na] = nt; } na++; n_react++; }
-                    __syncwarp();
-                }
-            }
+            if (lane == 0) { as.n = w; s_cnt = w; }
         }
-        // advance A: sleep until the earliest time one of its pairs can pass again, drop it if none can
-        int nt = T_INF;
-        const int w = wake_warp(m, A, t, scan_id);
-        if (w != T_INF) nt = next_event_warp(m, A, w);
-        if (nt != T_INF) { if (lane == 0) m.act_t[bk] = nt; }
-        else { if (lane == 0) { m.act_slot[bk] = m.act_slot[na - 1]; m.act_t[bk] = m.act_t[na - 1]; } na--; }
-        __syncwarp();
+        __syncthreads();
+        if (s_cnt == 0) break;
     }
-    if (lane == 0) { ctl->dbg[1] = n_events; ctl->dbg[2] = n_react; }
 }
