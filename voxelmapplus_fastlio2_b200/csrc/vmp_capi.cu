@@ -35,17 +35,21 @@ void set_error(const char* fmt, ...) {
 struct ScanIn { int n; int has_state; double x[36]; double P[529]; };
 struct ScanOut {
     double x[36]; double P[529];
-    int iter, converged, effect[8], err, pad;
+    int iter, converged, effect[8], err, need_maint;      // need_maint: bit0 rehash, bit1 LRU-log compaction
     int dbg[8];
     DevStats st;
 };
 
+// stage the prior; start of IESKF::update (ieskf.cpp:127-130): predict_x = x_, iteration counters
 __global__ void k_scan_in(const ScanIn* in, DevFilter* f, DevCtl* ctl) {
     const int tid = threadIdx.x;
-    if (tid == 0) ctl->n = in->n;
+    if (tid == 0) { ctl->n = in->n; ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
+    if (tid < 8) ctl->effect[tid] = 0;
     if (in->has_state) {
         for (int q = tid; q < 529; q += blockDim.x) f->P[q] = in->P[q];
-        if (tid < 36) f->x[tid] = in->x[tid];
+        if (tid < 36) { const double v = in->x[tid]; f->x[tid] = v; f->xpred[tid] = v; }
+    } else if (tid < 36) {
+        f->xpred[tid] = f->x[tid];
     }
 }
 __global__ void k_scan_out(const DevFilter* f, const DevCtl* ctl, ScanOut* out) {
@@ -53,7 +57,11 @@ __global__ void k_scan_out(const DevFilter* f, const DevCtl* ctl, ScanOut* out) 
     for (int q = tid; q < 529; q += blockDim.x) out->P[q] = f->P[q];
     if (tid < 36) out->x[tid] = f->x[tid];
     if (tid < 8) out->effect[tid] = ctl->effect[tid];
-    if (tid == 0) { out->iter = ctl->iter; out->converged = ctl->converged; out->err = ctl->err; out->st = ctl->st; for (int q = 0; q < 8; q++) out->dbg[q] = ctl->dbg[q]; }
+    if (tid == 0) {
+        out->iter = ctl->iter; out->converged = ctl->converged; out->err = ctl->err; out->st = ctl->st;
+        for (int q = 0; q < 8; q++) out->dbg[q] = ctl->dbg[q];
+        out->need_maint = (ctl->need_rehash ? 1 : 0) | (ctl->need_log_compact ? 2 : 0);
+    }
 }
 // H (12x12) / b (12) / effect of one measurement pass from the block partials (vmp_measure)
 __global__ void k_reduce_partials(const double* partials, int nblocks, int ext, double* out /*144+12+1*/) {
@@ -86,7 +94,8 @@ using namespace vmp;
 struct vmp_handle_t {
     vmp_config cfg;
     int device = 0, sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaGraphExec_t graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevMap m{};
@@ -163,10 +172,20 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk) {
     const bool ext = h->cfg.estimate_ext != 0;
     int k = 0;
     k_scan_in<<<1, 256, 0, st>>>(h->d_in, h->f, h->ctl); k++; mark(mk, VMP_K_SCAN_IN);
+    // P^-1 on a forked branch (second stream inside the capture): overlaps k_set_scan and the first k_measure,
+    // joined before the first k_ieskf_solve.  Profiling mode keeps one stream so that events attribute cleanly.
+    const bool fork = (mk == nullptr) && h->stream2 != nullptr;
+    if (fork) {
+        cudaEventRecord(h->ev_fork, st);
+        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+        launch_update_begin(h->stream2, h->f, h->ctl); k++;
+        cudaEventRecord(h->ev_join, h->stream2);
+    }
     launch_set_scan(st, h->grid_pts, h->s, h->ctl); k++; mark(mk, VMP_K_SET_SCAN);
-    launch_update_begin(st, h->f, h->ctl); k++; mark(mk, VMP_K_UPDATE_BEGIN);
+    if (!fork) { launch_update_begin(st, h->f, h->ctl); k++; mark(mk, VMP_K_UPDATE_BEGIN); }
     for (int it = 0; it < h->cfg.opti_max_iter; it++) {
         launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials); k++; mark(mk, VMP_K_MEASURE);
+        if (fork && it == 0) cudaStreamWaitEvent(st, h->ev_join, 0);
         launch_solve(st, ext, h->f, h->ctl, h->partials, h->grid_meas); k++; mark(mk, VMP_K_SOLVE);
     }
     launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++; mark(mk, VMP_K_WORLD_POINTS);
@@ -218,6 +237,7 @@ int finish_scan(vmp_handle_t* h, vmp_state* x, double* P, vmp_scan_stats* stats)
     VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     prof_collect(h);
     const ScanOut& o = *h->h_out;
+    if (o.need_maint) h->launches += launch_map_maintenance(h->stream, h->m, h->ctl, h->sm_count, o.need_maint);   // rare; runs before the next scan
     if (x) std::memcpy(x, o.x, sizeof(double) * 36);
     if (P) std::memcpy(P, o.P, sizeof(double) * 529);
     if (stats) {
@@ -290,6 +310,9 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     h->sm_count = prop.multiProcessorCount;
     *out = h;       // so that a failed create can still be destroyed by the caller
     VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    VMP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    VMP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev0));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev1));
 
@@ -373,6 +396,9 @@ int vmp_destroy(vmp_handle h) {
     for (auto& e : h->pev) if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VMP_OK;

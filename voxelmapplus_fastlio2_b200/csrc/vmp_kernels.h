@@ -23,6 +23,7 @@ inline void mark(const Marker* mk, int id) { if (mk && mk->fn) mk->fn(mk->ctx, i
 
 // map: returns the number of kernels launched
 int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, const Marker* mk);
+int launch_map_maintenance(cudaStream_t st, const DevMap& m, DevCtl* ctl, int sm_count, int what);
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl);
 
 }  // namespace vmp

@@ -622,11 +622,22 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
     k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND);
     k_map_finalize<<<sm_count, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_FINALIZE);
     k_map_end<<<1, 1, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_END);
-    k_rehash_clear<<<sm_count * 2, 256, 0, st>>>(m, ctl); launches++;
-    k_rehash_insert<<<sm_count * 2, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_REHASH);
-    k_logc_count<<<sm_count, 1024, 0, st>>>(m, ctl); launches++;
-    k_logc_scatter<<<sm_count, 1024, 0, st>>>(m, ctl); launches++;
-    k_logc_end<<<1, 1, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_COMPACT);
+    return launches;
+}
+
+// Rare maintenance, launched by the host between scans only when the previous scan asked for it
+// (tombstone purge of the hash, compaction of the LRU log); every kernel re-checks its device flag.
+int launch_map_maintenance(cudaStream_t st, const DevMap& m, DevCtl* ctl, int sm_count, int what) {
+    int launches = 0;
+    if (what & 1) {
+        k_rehash_clear<<<sm_count * 2, 256, 0, st>>>(m, ctl); launches++;
+        k_rehash_insert<<<sm_count * 2, 256, 0, st>>>(m, ctl); launches++;
+    }
+    if (what & 2) {
+        k_logc_count<<<sm_count, 1024, 0, st>>>(m, ctl); launches++;
+        k_logc_scatter<<<sm_count, 1024, 0, st>>>(m, ctl); launches++;
+        k_logc_end<<<1, 1, 0, st>>>(m, ctl); launches++;
+    }
     return launches;
 }
 

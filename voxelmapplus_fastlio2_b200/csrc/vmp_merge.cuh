@@ -292,9 +292,16 @@ __device__ void process_event(const DevMap& m, DevCtl* ctl, ActiveSet& as, int j
             if (m.cnt[Yb] == 0 || m.evn[Yb] == 0) continue;
             const int fl = event_floor(m, Yb, scan_id);
             const int wb = wake_warp(m, Yb, t > fl ? t : fl, scan_id);
-            if (wb == T_INF) continue;
-            const int nt = next_event_warp(m, Yb, wb);
+            const int nt = wb == T_INF ? T_INF : next_event_warp(m, Yb, wb);
             if (nt != T_INF) as_activate(m, ctl, as, Yb, nt, dn);
+            else {
+                // the partner has no pair left that can pass (typically: it now shares A's group): retire its
+                // pending entry right away instead of spending a round on a no-op.  Its entry is not being
+                // processed concurrently: it lies within 1 of A and has a later event.
+                const int n = as.n;
+                for (int k = lane; k < n; k += 32) if ((as.slot[k] & 0x0FFFFFFF) == Yb) as.t[k] = T_INF;
+                __syncwarp();
+            }
         }
         const int ncand = (nchg + 1) * 6;
         for (int c0 = 0; c0 < ncand; c0 += 32) {

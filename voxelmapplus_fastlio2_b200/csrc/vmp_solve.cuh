@@ -3,7 +3,7 @@
 //
 //   k_update_begin   predict_x = x_ (ieskf.cpp:127), iteration counters, and P_^-1: P_ does not change
 //                    inside update(), so the inverse the reference evaluates twice per iteration (Q6) is
-//                    computed once per scan here
+//                    computed once per scan here (on a forked branch of the scan graph)
 //   k_ieskf_solve    one CTA per iteration: fixed-order reduction of the measurement partials, boxminus,
 //                    J, H_ = J^T P^-1 J + H, b_, delta = -H_^-1 b_, boxplus, convergence flag; on the
 //                    last executed iteration also P_ = L H_^-1 L^T
@@ -11,27 +11,31 @@
 // The 23x23 inverse is LU with partial pivoting + substitution against the permuted identity (what
 // Eigen's PartialPivLU-based inverse() does).  ncu on the first versions showed that a single warp
 // doing this is bound by its own instruction count (23k warp-instructions, ~4.6 cycles each), so the
-// work is spread one matrix entry per thread (529 of the CTA's threads): per elimination step one
-// pivot search by warp 0 and one rank-1 update by everybody, two barriers; per substitution step one
-// barrier.  Rows are never moved (a position array tracks the pivot order), and each entry sees
-// exactly the serial sequence of operations of lu_inverse<> in vmp_math.cuh -> bit-identical results.
+// work is spread over the CTA, two matrix entries per thread: per elimination step one pivot search
+// by warp 0 and one rank-1 update by everybody (two barriers), per substitution step one barrier.
+// Rows are never moved (a position array tracks the pivot order), and each entry sees exactly the
+// serial sequence of operations of lu_inverse<> in vmp_math.cuh -> bit-identical results.
 #pragma once
 
 constexpr int NS = 23;
-constexpr int SOLVE_THREADS = 544;      // 17 warps >= 23*23
+constexpr int NE = NS * NS;
+constexpr int SOLVE_THREADS = 288;      // 9 warps; entries tid and tid + 288 (< 529) per thread
+constexpr int W_MAN = 8;                // the warp that runs the manifold operations
+constexpr int N_WORK = 32 * W_MAN;      // threads of the other warps
 
 struct LuShared {
-    double Lm[NS * NS];                 // multipliers by physical row
+    double Lm[NE];                      // multipliers by physical row
     int pos[NS];                        // physical row -> index in pivot order
     int perm[NS];                       // pivot order -> physical row
     int piv;                            // physical pivot row of the current step
 };
 
-// A: NS*NS in shared, destroyed (ends as U by physical row); inv: NS*NS out.  Whole CTA must call.
+// A: NE doubles in shared, destroyed (ends as U by physical row); inv: NE out.  Whole CTA must call.
 __device__ void block_lu_inverse(double* A, double* inv, LuShared& w) {
     const int tid = threadIdx.x;
-    const int r = tid / NS, c = tid % NS;               // thread = entry (physical row r, column c)
-    const bool ent = tid < NS * NS;
+    const int e0 = tid, e1 = tid + SOLVE_THREADS;
+    const bool h1 = e1 < NE;
+    const int r0 = e0 / NS, c0 = e0 % NS, r1 = h1 ? e1 / NS : 0, c1 = h1 ? e1 % NS : 0;
     if (tid < NS) w.pos[tid] = tid;
     __syncthreads();
     for (int k = 0; k < NS; k++) {
@@ -53,38 +57,47 @@ __device__ void block_lu_inverse(double* A, double* inv, LuShared& w) {
             }
         }
         __syncthreads();
-        if (ent && w.pos[r] > k && c >= k) {
-            const int L = w.piv;
-            const double l = A[r * NS + k] / A[L * NS + k];
-            if (c == k) w.Lm[r * NS + k] = l;
-            else A[r * NS + c] = A[r * NS + c] - l * A[L * NS + c];
+        const int L = w.piv;
+        const double d = A[L * NS + k];
+        // rank-1 update.  No hazard inside the phase: column k (read by everybody) is only ever written to
+        // Lm, the pivot row L is not written at all, and A[r][c] is read and written by its own thread only.
+        if (w.pos[r0] > k && c0 >= k) {
+            const double l = A[r0 * NS + k] / d;
+            if (c0 == k) w.Lm[e0] = l; else A[e0] = A[e0] - l * A[L * NS + c0];
+        }
+        if (h1 && w.pos[r1] > k && c1 >= k) {
+            const double l = A[r1 * NS + k] / d;
+            if (c1 == k) w.Lm[e1] = l; else A[e1] = A[e1] - l * A[L * NS + c1];
         }
         __syncthreads();
     }
     if (tid < NS) w.perm[w.pos[tid]] = tid;
     __syncthreads();
-    // thread (i, c): entry i (pivot order) of column c of the inverse
-    const int i = r;
-    const int pr = ent ? w.perm[i] : 0;
-    double s = (ent && pr == c) ? 1.0 : 0.0;
+    // thread entries (i, c): entry i (pivot order) of column c of the inverse
+    const int p0 = w.perm[r0], p1 = h1 ? w.perm[r1] : 0;
+    double s0 = (p0 == c0) ? 1.0 : 0.0, s1 = (h1 && p1 == c1) ? 1.0 : 0.0;
     for (int j = 0; j < NS; j++) {                       // L y = P e_c
-        if (ent && i == j) inv[j * NS + c] = s;
+        if (r0 == j) inv[j * NS + c0] = s0;
+        if (h1 && r1 == j) inv[j * NS + c1] = s1;
         __syncthreads();
-        if (ent && i > j) s = s - w.Lm[pr * NS + j] * inv[j * NS + c];
+        if (r0 > j) s0 = s0 - w.Lm[p0 * NS + j] * inv[j * NS + c0];
+        if (h1 && r1 > j) s1 = s1 - w.Lm[p1 * NS + j] * inv[j * NS + c1];
     }
     __syncthreads();
     for (int j = NS - 1; j >= 0; j--) {                  // U x = y, unknowns in the order they become available
-        if (ent && i == j) inv[j * NS + c] = s / A[pr * NS + j];
+        if (r0 == j) inv[j * NS + c0] = s0 / A[p0 * NS + j];
+        if (h1 && r1 == j) inv[j * NS + c1] = s1 / A[p1 * NS + j];
         __syncthreads();
-        if (ent && i < j) s = s - A[pr * NS + j] * inv[j * NS + c];
+        if (r0 < j) s0 = s0 - A[p0 * NS + j] * inv[j * NS + c0];
+        if (h1 && r1 < j) s1 = s1 - A[p1 * NS + j] * inv[j * NS + c1];
     }
     __syncthreads();
 }
 
-// C = op(A) * op(B), NS x NS in shared memory, one entry per thread, left-to-right sums
+// C = op(A) * op(B), NS x NS in shared memory, entries strided over the block, left-to-right sums
 __device__ __forceinline__ void block_mm(const double* A, const double* B, double* C, bool transA, bool transB) {
     const int sa = transA ? NS : 1, sb = transB ? 1 : NS;            // strides along k
-    for (int q = threadIdx.x; q < NS * NS; q += blockDim.x) {
+    for (int q = threadIdx.x; q < NE; q += blockDim.x) {
         const int i = q / NS, j = q % NS;
         const double* a = A + (transA ? i : i * NS);
         const double* b = B + (transB ? j * NS : j);
@@ -108,29 +121,29 @@ __device__ __noinline__ void jac_blocks(double* J, const double* delta, const do
     }
 }
 
+// P_^-1 only; runs on a forked branch of the scan graph, concurrently with k_set_scan and the first
+// k_measure (predict_x / counters are initialised by k_scan_in)
 __global__ void __launch_bounds__(SOLVE_THREADS) k_update_begin(DevFilter* f, DevCtl* ctl) {
-    __shared__ double sA[NS * NS], sInv[NS * NS];
+    __shared__ double sA[NE], sInv[NE];
     __shared__ LuShared lu;
     const int tid = threadIdx.x;
-    if (tid < 36) f->xpred[tid] = f->x[tid];
-    if (tid == 0) { ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
-    if (tid < 8) ctl->effect[tid] = 0;
-    if (tid < NS * NS) sA[tid] = f->P[tid];
+    (void)ctl;
+    for (int q = tid; q < NE; q += SOLVE_THREADS) sA[q] = f->P[q];
     __syncthreads();
     block_lu_inverse(sA, sInv, lu);
-    if (tid < NS * NS) f->Pinv[tid] = sInv[tid];
+    for (int q = tid; q < NE; q += SOLVE_THREADS) f->Pinv[q] = sInv[q];
 }
 void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl) { k_update_begin<<<1, SOLVE_THREADS, 0, st>>>(f, ctl); }
 
-constexpr int RED_CHUNKS = 4;
+constexpr int RED_CHUNKS = 2;
 
 template <bool EXT>
 __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, DevCtl* ctl, const double* __restrict__ partials, int nblocks) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;
-    constexpr int W_MAN = 16;           // the warp that runs the manifold operations
-    __shared__ double sA[NS * NS], sB[NS * NS], sC[NS * NS], sJ[NS * NS], sHinv[NS * NS];
+    static_assert(NV * RED_CHUNKS <= N_WORK, "reduction does not fit the worker threads");
+    __shared__ double sA[NE], sB[NE], sC[NE], sJ[NE], sHinv[NE];
     __shared__ double sHm[NV], sRed[RED_CHUNKS][NV], sdelta[NS], sb[NS], sdx[NS], sx[36], sxp[36];
     __shared__ LuShared lu;
     __shared__ int s_last;
@@ -149,11 +162,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
             const int v = tid % NV, c = tid / NV;
             const int b0 = (int)((long long)nblocks * c / RED_CHUNKS), b1 = (int)((long long)nblocks * (c + 1) / RED_CHUNKS);
             double t = 0.0;
-#pragma unroll 4
+#pragma unroll 8
             for (int b = b0; b < b1; b++) t += partials[(size_t)b * PARTIAL_STRIDE + v];
             sRed[c][v] = t;
         }
-        for (int q = tid; q < NS * NS; q += 32 * W_MAN) { sB[q] = f->Pinv[q]; sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0; }
+        for (int q = tid; q < NE; q += N_WORK) { sB[q] = f->Pinv[q]; sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0; }
     }
     __syncthreads();
     if (tid < NV) {
@@ -175,14 +188,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
         if (lane < D) t += sHm[NH + lane];
         sb[lane] = t;
     }
-    if (tid < NS * NS) {
-        const int i = tid / NS, j = tid % NS;
+    for (int q = tid; q < NE; q += SOLVE_THREADS) {
+        const int i = q / NS, j = q % NS;
         double h = sC[i * NS] * sJ[j];
 #pragma unroll 2
         for (int k = 1; k < NS; k++) h += sC[i * NS + k] * sJ[k * NS + j];
         h = 0.0 + h;
         if (i < D && j < D) { const int a = i < j ? i : j, c = i < j ? j : i; h += sHm[a * D - a * (a - 1) / 2 + (c - a)]; }
-        sA[tid] = h;
+        sA[q] = h;
     }
     __syncthreads();
     // (4) H_^-1, delta = -H_^-1 b_
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
             s_last = last;
         }
     } else {
-        for (int q = tid; q < NS * NS; q += 32 * W_MAN) sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0;     // L := I meanwhile
+        for (int q = tid; q < NE; q += N_WORK) sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0;     // L := I meanwhile
     }
     __syncthreads();
     if (!s_last) return;
@@ -223,7 +236,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
     __syncthreads();
     block_mm(sC, sJ, sB, false, true);
     __syncthreads();
-    if (tid < NS * NS) f->P[tid] = sB[tid];
+    for (int q = tid; q < NE; q += SOLVE_THREADS) f->P[q] = sB[q];
 }
 
 void launch_solve(cudaStream_t st, bool ext, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
