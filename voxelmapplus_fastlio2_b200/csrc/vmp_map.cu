@@ -99,7 +99,7 @@ __global__ void k_map_begin(DevCtl* ctl) {
     DevStats z = {};
     ctl->st = z;
     ctl->n_touched = 0; ctl->n_new = 0; ctl->n_evict = 0; ctl->n_hot = 0; ctl->n_ghost = 0;
-    for (int q = 0; q < 8; q++) ctl->dbg[q] = 0;
+    for (int q = 0; q < 3; q++) ctl->dbg[q] = 0;          // [3..7] belong to the solve kernel
 }
 
 __global__ void k_map_end(DevMap m, DevCtl* ctl) {

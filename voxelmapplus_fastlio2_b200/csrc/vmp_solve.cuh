@@ -36,42 +36,41 @@ __device__ void block_lu_inverse(double* A, double* inv, LuShared& w) {
     const int e0 = tid, e1 = tid + SOLVE_THREADS;
     const bool h1 = e1 < NE;
     const int r0 = e0 / NS, c0 = e0 % NS, r1 = h1 ? e1 / NS : 0, c1 = h1 ? e1 % NS : 0;
-    if (tid < NS) w.pos[tid] = tid;
-    __syncthreads();
+    // Every warp runs the (cheap) pivot search redundantly on lanes 0..22, so there is no barrier between the
+    // search and the rank-1 update; each thread tracks the pivot-order position of "its" rows in registers.
+    const int lane = tid & 31;
+    const bool act = lane < NS;
+    int lpos = act ? lane : 1000 + lane;                 // position of physical row `lane`
+    int pos0 = r0, pos1 = r1;                            // positions of the rows of this thread's two entries
     for (int k = 0; k < NS; k++) {
-        if (tid < 32) {
-            // pivot: first row (in pivot order) of maximal |a_ik|, i >= k
-            const bool act = tid < NS;
-            int p = act ? w.pos[tid] : 1000 + tid;
-            const int mypos = p;
-            double v = (act && p >= k) ? fabs(A[tid * NS + k]) : -1.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double vo = __shfl_xor_sync(0xffffffffu, v, o);
-                const int po = __shfl_xor_sync(0xffffffffu, p, o);
-                if (vo > v || (vo == v && po < p)) { v = vo; p = po; }
-            }
-            if (act) {
-                if (mypos == p) { w.pos[tid] = k; w.piv = tid; }   // row swap k <-> p in the pivot order
-                else if (mypos == k) w.pos[tid] = p;
-            }
-        }
-        __syncthreads();
-        const int L = w.piv;
+        // pivot: first row (in pivot order) of maximal |a_ik|, i >= k.  |a| >= 0 orders like its bit pattern:
+        // three warp reductions (high word, low word, smallest position) instead of a 5-deep shuffle chain.
+        const bool cand = act && lpos >= k;
+        const unsigned long long bits = cand ? (unsigned long long)__double_as_longlong(fabs(A[lane * NS + k])) : 0ull;
+        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        const bool c1_ = cand && hi == mhi;
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, c1_ ? lo : 0u);
+        const bool c2_ = c1_ && lo == mlo;
+        const int p = (int)__reduce_min_sync(0xffffffffu, c2_ ? (unsigned)lpos : 0x7fffffffu);
+        const int L = __ffs(__ballot_sync(0xffffffffu, act && lpos == p)) - 1;      // physical pivot row
+        if (lpos == p) lpos = k; else if (lpos == k) lpos = p;                        // row swap k <-> p in the pivot order
+        if (pos0 == p) pos0 = k; else if (pos0 == k) pos0 = p;
+        if (pos1 == p) pos1 = k; else if (pos1 == k) pos1 = p;
         const double d = A[L * NS + k];
         // rank-1 update.  No hazard inside the phase: column k (read by everybody) is only ever written to
         // Lm, the pivot row L is not written at all, and A[r][c] is read and written by its own thread only.
-        if (w.pos[r0] > k && c0 >= k) {
+        if (pos0 > k && c0 >= k) {
             const double l = A[r0 * NS + k] / d;
             if (c0 == k) w.Lm[e0] = l; else A[e0] = A[e0] - l * A[L * NS + c0];
         }
-        if (h1 && w.pos[r1] > k && c1 >= k) {
+        if (h1 && pos1 > k && c1 >= k) {
             const double l = A[r1 * NS + k] / d;
             if (c1 == k) w.Lm[e1] = l; else A[e1] = A[e1] - l * A[L * NS + c1];
         }
         __syncthreads();
     }
-    if (tid < NS) w.perm[w.pos[tid]] = tid;
+    if (tid < NS) w.perm[lpos] = tid;
     __syncthreads();
     // thread entries (i, c): entry i (pivot order) of column c of the inverse
     const int p0 = w.perm[r0], p1 = h1 ? w.perm[r1] : 0;
@@ -102,7 +101,7 @@ __device__ __forceinline__ void block_mm(const double* A, const double* B, doubl
         const double* a = A + (transA ? i : i * NS);
         const double* b = B + (transB ? j * NS : j);
         double s = a[0] * b[0];
-#pragma unroll 2
+#pragma unroll
         for (int k = 1; k < NS; k++) s += a[k * sa] * b[k * sb];
         C[q] = s;
     }
@@ -150,6 +149,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     if (ctl->done) return;
     const int it = ctl->iter;
+    long long tk0 = clock64(), tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;
 
     // (1) concurrently: reduction of the per-block partials (fixed order: RED_CHUNKS contiguous block
     //     ranges, then the chunk sums in ascending order) | boxminus | P^-1 load | J := I
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
         for (int q = tid; q < NE; q += N_WORK) { sB[q] = f->Pinv[q]; sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0; }
     }
     __syncthreads();
+    tk1 = clock64();
     if (tid < NV) {
         double t = sRed[0][tid];
 #pragma unroll
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
     // (2) the blocks of J (ieskf.cpp:136-139)
     if (wid == W_MAN && lane < 3) jac_blocks(sJ, sdelta, sx + 33, sxp + 33, lane);
     __syncthreads();
+    tk2 = clock64();
     // (3) JtPinv = J^T P^-1 ; b_ = JtPinv delta ; H_ = JtPinv J (+ measurement H, b in the top-left corner)
     block_mm(sJ, sB, sC, true, false);
     __syncthreads();
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
     for (int q = tid; q < NE; q += SOLVE_THREADS) {
         const int i = q / NS, j = q % NS;
         double h = sC[i * NS] * sJ[j];
-#pragma unroll 2
+#pragma unroll
         for (int k = 1; k < NS; k++) h += sC[i * NS + k] * sJ[k * NS + j];
         h = 0.0 + h;
         if (i < D && j < D) { const int a = i < j ? i : j, c = i < j ? j : i; h += sHm[a * D - a * (a - 1) / 2 + (c - a)]; }
@@ -199,7 +201,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
     }
     __syncthreads();
     // (4) H_^-1, delta = -H_^-1 b_
+    tk3 = clock64();
     block_lu_inverse(sA, sHinv, lu);
+    tk4 = clock64();
     if (wid == W_MAN) {
         if (lane < NS) {
             double t = (-sHinv[lane * NS]) * sb[0];
@@ -228,6 +232,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_ieskf_solve(DevFilter* f, Dev
         for (int q = tid; q < NE; q += N_WORK) sJ[q] = (q / NS == q % NS) ? 1.0 : 0.0;     // L := I meanwhile
     }
     __syncthreads();
+    tk5 = clock64();
+    if (tid == 0 && it == 0) {      // phase cycles of the first iteration: reduce|boxminus, J blocks, products, LU inverse, boxplus
+        ctl->dbg[3] = (int)(tk1 - tk0); ctl->dbg[4] = (int)(tk2 - tk1); ctl->dbg[5] = (int)(tk3 - tk2); ctl->dbg[6] = (int)(tk4 - tk3); ctl->dbg[7] = (int)(tk5 - tk4);
+    }
     if (!s_last) return;
     // (6) P_ = L H_^-1 L^T with L from the final delta and the updated state (ieskf.cpp:151-155)
     if (wid == W_MAN && lane < 3) jac_blocks(sJ, sdx, sx + 33, sxp + 33, lane);
