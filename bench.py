@@ -54,23 +54,32 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
 
     def run(self):
+        # one streaming nvidia-smi (-lms 20): the timed region of the default run is only ~0.1 s long
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._halt.is_set():
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        for line in self.proc.stdout:
+            out = line.strip().split(",")
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.samples.append((float(out[0]), float(out[1])))
                 for n, v in zip(names, out[2:]):
                     if v.strip().lower().startswith("active"):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            if self._halt.is_set():
+                break
 
     def stop(self):
         self._halt.set()
+        if getattr(self, "proc", None) is not None:
+            self.proc.terminate()
         self.join(timeout=5)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
