@@ -179,6 +179,38 @@ def test_measure_and_scan_teacher_forced(oracle_mod, estimate_ext):
     assert checked_iters > 15
 
 
+def test_dense_scan_c2_size(oracle_mod):
+    """BASELINE.json configs[1] size: 200 000 pts/scan, 0.25 m voxels, 4 iterations — every tier at full size for two scans
+    (heavy voxels with > 1000 points per scan exercise the in-place bitonic sort and the build overflow path, Q18)."""
+    n = 200000
+    cfg = default_config(max_points_per_scan=n + 64, voxel_size=0.25, opti_max_iter=4, map_capacity=400000)
+    o = oracle_mod.Oracle(cfg)
+    g = HotPath(cfg)
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=n))
+    scans = 0
+    for pk in seq.packages(4):
+        st = o.lio_process(pk.imus, pk.cloud, pk.t0, pk.t1)
+        x_post, P_post, status = o.lio_state()
+        if status == 1:
+            continue
+        xyz = np.ascontiguousarray(pk.cloud[:, :3])
+        x0, P0 = o.get_prior()
+        if st.iters == 0:
+            sg = g.first_scan(x0, P0, xyz)
+            assert sg["n_touch"] == st.map.n_touch and sg["n_refit"] == st.map.n_refit and sg["refit_points"] == st.map.refit_points
+            continue
+        xg, Pg, sgs = g.scan(x0, P0, xyz)
+        assert sgs.iters == st.iters and list(sgs.effect_num[:st.iters]) == list(st.effect_num[:st.iters])
+        co, cg = o.dump_correspondences(), g.dump_correspondences()
+        assert np.array_equal(co["keys"], cg["keys"]) and np.array_equal(co["status"], cg["status"])
+        assert np.abs(np.array(xg.pos[:]) - np.array(x_post.pos[:])).max() < 1e-9
+        for f in ("n_ins", "n_touch", "n_created", "n_refit", "refit_points", "n_full", "n_mergeprobe", "n_merge", "map_size"):
+            assert getattr(sgs.map, f) == getattr(st.map, f), f
+        scans += 1
+    assert scans == 2
+    assert_maps_equal(o.dump_map(), g.dump_map(), exact=False, rtol=1e-6, what="dense scan map")
+
+
 def test_lio_trajectory(oracle_mod):
     """Tier 3: free-running estimators (host predict/undistort + device update) stay within 1 mm / 0.01 deg."""
     cfg = default_config(max_points_per_scan=8192)
