@@ -118,9 +118,13 @@ def algo_bytes(kernel, st_sum, n_pts_sum, iters_sum):
         return (4 + 4 + 4) * n_pts_sum
     if kernel == "k_log_append":
         return 4 * n_pts_sum + 20 * st_sum["n_touch"]
-    if kernel == "k_map_fill":
-        return 144 * st_sum["n_ins"] + 160 * st_sum["n_touch"] + 72 * st_sum["refit_points"] + 432 * st_sum["n_refit"] + 4 * n_pts_sum
-    if kernel in ("k_merge_prefilter", "k_merge_serial"):
+    if kernel == "k_fill_state":
+        return 144 * st_sum["n_ins"] + 160 * st_sum["n_touch"] + 4 * n_pts_sum
+    if kernel == "k_fill_refit":
+        return 72 * st_sum["refit_points"] + 432 * st_sum["n_refit"]
+    if kernel == "k_fill_acc":
+        return 288 * st_sum["refit_points"] + 288 * st_sum["n_refit"]
+    if kernel in ("k_merge_prefilter", "k_merge_rounds"):
         return 192 * st_sum["n_merge_voxels"] + 672 * st_sum["n_merge"]
     if kernel == "k_ieskf_solve":
         return iters_sum * (148 * 28 * 8 + 3 * 529 * 8)

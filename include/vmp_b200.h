@@ -118,7 +118,7 @@ typedef enum vmp_kernel_id {
     VMP_K_SCAN_IN = 0, VMP_K_SET_SCAN, VMP_K_UPDATE_BEGIN, VMP_K_MEASURE, VMP_K_SOLVE, VMP_K_WORLD_POINTS,
     VMP_K_MAP_BEGIN, VMP_K_MAP_INSERT, VMP_K_MAP_COUNT, VMP_K_SEG_SCAN, VMP_K_SEG_FILL, VMP_K_LRU_EVICT,
     VMP_K_MAP_FILL, VMP_K_MERGE_PREFILTER, VMP_K_MERGE_SERIAL, VMP_K_LOG_APPEND, VMP_K_MAP_FINALIZE,
-    VMP_K_MAP_END, VMP_K_REHASH, VMP_K_LOG_COMPACT, VMP_K_SCAN_OUT, VMP_K_COUNT
+    VMP_K_MAP_END, VMP_K_REHASH, VMP_K_LOG_COMPACT, VMP_K_SCAN_OUT, VMP_K_FILL_REFIT, VMP_K_FILL_ACC, VMP_K_COUNT
 } vmp_kernel_id;
 
 typedef struct vmp_handle_t* vmp_handle;

@@ -336,6 +336,14 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     DALLOC(m.tpos, nmax); DALLOC(m.pslot, nmax); DALLOC(m.seg, nmax);
     DALLOC(m.touched, nmax); DALLOC(m.hotlist, nmax); DALLOC(m.ev_slot, nmax); DALLOC(m.ev_time, nmax); DALLOC(m.ev_key, nmax);
     DALLOC(m.ct, nmax); DALLOC(m.act_slot, nmax); DALLOC(m.act_t, nmax);
+    m.job_cap = 2 * nmax + 64;
+    m.contrib_cap = (long long)nmax * (m.maxpt / m.upt + 2) + 1024;
+    m.bat_cap = (int)(m.contrib_cap / 32) + m.job_cap + 64;
+    DALLOC(m.job_slot, m.job_cap); DALLOC(m.job_n, m.job_cap); DALLOC(m.job_nt, m.job_cap); DALLOC(m.job_off, m.job_cap);
+    DALLOC(m.job_src, m.job_cap); DALLOC(m.job_next, m.job_cap); DALLOC(m.job_plane, m.job_cap);
+    DALLOC(m.job_mean, (size_t)3 * m.job_cap); DALLOC(m.job_ppt, (size_t)6 * m.job_cap); DALLOC(m.job_norm, (size_t)3 * m.job_cap);
+    DALLOC(m.bat_job, m.bat_cap); DALLOC(m.bat_idx, m.bat_cap); DALLOC(m.vox_job, nmax);
+    DALLOC(m.contrib, (size_t)m.contrib_cap * 36);
     const int nblk = (nmax + PT_BLOCK - 1) / PT_BLOCK;
     DALLOC(m.blk_last, nblk); DALLOC(m.blk_new, nblk);
     m.log_cap = std::max<long long>(8ll * m.pool, 8ll * nmax + 4096);
@@ -688,8 +696,8 @@ const char* vmp_kernel_name(int id) {
     static const char* names[VMP_K_COUNT] = {
         "k_scan_in", "k_set_scan", "k_update_begin", "k_measure", "k_ieskf_solve", "k_world_points",
         "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
-        "k_map_fill", "k_merge_prefilter", "k_merge_serial", "k_log_append", "k_map_finalize",
-        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out"};
+        "k_fill_state", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
+        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_refit", "k_fill_acc"};
     return (id >= 0 && id < VMP_K_COUNT) ? names[id] : "?";
 }
 

@@ -65,6 +65,8 @@ struct DevCtl {
     unsigned long long group_counter;
     int err;
     int pad0;
+    int n_jobs, n_batches;              // refit jobs / 32-point batches of this map update
+    unsigned long long contrib_top;     // staged contributions (points)
     int dbg[8];                         // debug counters of the last map update: [0] active set after the prefilter, [1] merge events simulated, [2] re-examinations that activated a voxel
     DevStats st;
     // IEKF
@@ -117,6 +119,12 @@ struct DevMap {
     int* ct;                            // creation times (sorted) [nmax]
     int* blk_last; int* blk_new;        // per 1024-point block counts
     int* act_slot; int* act_t;          // serial merge active set [nmax]
+    // refit jobs of one map update (vmp_fill.cuh)
+    int* job_slot; int* job_n; int* job_nt; long long* job_off; int* job_src; int* job_next; int* job_plane;
+    double* job_mean; double* job_ppt; double* job_norm;
+    int* bat_job; int* bat_idx; int* vox_job;
+    double* contrib;                    // [contrib_cap][36] staged J Sigma J^T
+    int job_cap, bat_cap; long long contrib_cap;
     // LRU log (two buffers for compaction)
     int* log_slot[2];
     unsigned long long* log_stamp[2];

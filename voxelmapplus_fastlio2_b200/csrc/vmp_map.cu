@@ -99,6 +99,7 @@ __global__ void k_map_begin(DevCtl* ctl) {
     DevStats z = {};
     ctl->st = z;
     ctl->n_touched = 0; ctl->n_new = 0; ctl->n_evict = 0; ctl->n_hot = 0; ctl->n_ghost = 0;
+    ctl->n_jobs = 0; ctl->n_batches = 0; ctl->contrib_top = 0;
     for (int q = 0; q < 3; q++) ctl->dbg[q] = 0;          // [3..7] belong to the solve kernel
 }
 
@@ -106,6 +107,7 @@ __global__ void k_map_end(DevMap m, DevCtl* ctl) {
     ctl->st.n_points = ctl->n;
     ctl->st.n_touch = ctl->n_touched;
     ctl->st.map_size = ctl->n_live;
+    ctl->st.n_refit = ctl->n_jobs;                    // every job is one updatePlane() that reached the eigen solve
     ctl->log_tail += ctl->n_touched;                  // exactly one last-touch entry per touched voxel
     ctl->stamp_base += (unsigned long long)ctl->n;
     ctl->scan_id += 1;
@@ -341,210 +343,7 @@ __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
     ctl->st.n_evicted = ne; ctl->st.n_created = created;
 }
 
-// ------------------------------------------------------------------------- M4: per-voxel fill + refit
-// ascending in-place sort of a[0..c) by one warp (point indices are distinct)
-__device__ void warp_sort(int* a, int c) {
-    const int lane = threadIdx.x & 31;
-    if (c <= 1) return;
-    if (c <= 32) {
-        const int v = lane < c ? a[lane] : INT_MAX;
-        int rank = 0;
-#pragma unroll
-        for (int l = 0; l < 32; l++) { const int o = __shfl_sync(0xffffffffu, v, l); rank += (o < v) ? 1 : 0; }
-        __syncwarp();
-        if (lane < c) a[rank] = v;
-        __syncwarp();
-        return;
-    }
-    int npow = 64;
-    while (npow < c) npow <<= 1;
-    const int half = npow >> 1;
-    for (int k = 2; k <= npow; k <<= 1) {
-        const int hk = k >> 1;
-        for (int t = lane; t < half; t += 32) {                 // flip stage: all comparators ascending
-            const int blk = t / hk, o = t % hk;
-            const int lo = blk * k + o, hi = blk * k + k - 1 - o;
-            if (hi < c) { const int x = a[lo], y = a[hi]; if (x > y) { a[lo] = y; a[hi] = x; } }
-        }
-        __syncwarp();
-        for (int j = k >> 2; j >= 1; j >>= 1) {
-            for (int t = lane; t < half; t += 32) {
-                const int lo = (t / j) * 2 * j + (t % j), hi = lo + j;
-                if (hi < c) { const int x = a[lo], y = a[hi]; if (x > y) { a[lo] = y; a[hi] = x; } }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// J Sigma J^T of one stored point (voxel_map.cpp:115-129)
-__device__ __forceinline__ void plane_contrib(const V3& p, const M3& S, const V3& mean, int n, const double* evals,
-                                              const M3& evecs, const V3& nrm, double* out /*36, stride 1*/) {
-    M3 F = zeros<3, 3>();
-#pragma unroll
-    for (int mm = 1; mm < 3; mm++) {
-        const V3 vm = v3(evecs(0, mm), evecs(1, mm), evecs(2, mm));
-        const Mat<1, 3> lhs = divs(tr(sub(p, mean)), n * (evals[0] - evals[mm]));
-        const M3 Sm = add(outer(vm, nrm), outer(nrm, vm));
-        const Mat<1, 3> Fm = mul(lhs, Sm);
-        F(mm, 0) = Fm[0]; F(mm, 1) = Fm[1]; F(mm, 2) = Fm[2];
-    }
-    Mat<6, 3> J;
-    set_block(J, 0, 0, mul(evecs, F));
-    set_block(J, 3, 0, divs(eye<3>(), (double)n));
-    const Mat<6, 6> C = mul(mul(J, S), tr(J));
-#pragma unroll
-    for (int k = 0; k < 36; k++) out[k] = C.a[k];
-}
-
-constexpr int CONTRIB_STRIDE = 37;
-
-struct VoxelRun {            // warp-uniform running state of the voxel being filled
-    V3 mean; double ppt[6]; int n; uint32_t flags; int nt, nw;
-    unsigned full_scan; int full_idx;
-};
-
-// updatePlane() body after the "n >= update_point_thresh" test (voxel_map.cpp:100-135).
-// idx != nullptr: read the points through seg indices from the scan arrays (build()),
-// else from the voxel's stored points.
-__device__ void warp_refit(const DevMap& m, const DevScan& s, DevCtl* ctl, int slot, VoxelRun& v, const int* idx,
-                           double* shc /*32*CONTRIB_STRIDE*/, long long& c_refit, long long& c_refit_pts) {
-    const int lane = threadIdx.x & 31;
-    v.flags |= F_INIT;
-    const double nd = (double)v.n;
-    const double c00 = v.ppt[0] / nd - v.mean[0] * v.mean[0];
-    const double c10 = v.ppt[1] / nd - v.mean[1] * v.mean[0];
-    const double c11 = v.ppt[2] / nd - v.mean[1] * v.mean[1];
-    const double c20 = v.ppt[3] / nd - v.mean[2] * v.mean[0];
-    const double c21 = v.ppt[4] / nd - v.mean[2] * v.mean[1];
-    const double c22 = v.ppt[5] / nd - v.mean[2] * v.mean[2];
-    double evals[3];
-    M3 evecs;
-    eig3_sym(c00, c10, c11, c20, c21, c22, evals, evecs);
-    c_refit++;
-    if (evals[0] > m.plane_thresh) { v.flags &= ~F_PLANE; return; }     // Q13: norm / cov stay
-    v.flags |= F_PLANE;
-    V3 nrm = v3(evecs(0, 0), evecs(1, 0), evecs(2, 0));
-    const int np = v.nt;
-    c_refit_pts += np;
-    if (!idx && np > m.maxpt) { if (lane == 0) atomicOr(&ctl->err, E_REFIT_OVERFLOW); }
-    double* cv = m.cov + (size_t)slot * 36;
-    double acc0 = cv[lane];
-    double acc1 = lane < 4 ? cv[32 + lane] : 0.0;
-    const double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
-    for (int base = 0; base < np; base += 32) {
-        const int j = base + lane;
-        if (j < np) {
-            V3 p; M3 S;
-            if (idx) {
-                const int i = idx[j];
-                p = v3(s.pw[3 * (size_t)i], s.pw[3 * (size_t)i + 1], s.pw[3 * (size_t)i + 2]);
-#pragma unroll
-                for (int k = 0; k < 9; k++) S.a[k] = s.pcov[9 * (size_t)i + k];
-            } else {
-                const int jj = j < m.maxpt ? j : m.maxpt - 1;
-                p = v3(tp[jj], tp[m.maxpt + jj], tp[2 * m.maxpt + jj]);
-#pragma unroll
-                for (int k = 0; k < 9; k++) S.a[k] = tp[(size_t)(3 + k) * m.maxpt + jj];
-            }
-            plane_contrib(p, S, v.mean, v.n, evals, evecs, nrm, shc + lane * CONTRIB_STRIDE);
-        }
-        __syncwarp();
-        const int cb = np - base < 32 ? np - base : 32;
-        for (int q = 0; q < cb; q++) {                      // ordered accumulation (Q7: never reset)
-            acc0 += shc[q * CONTRIB_STRIDE + lane];
-            if (lane < 4) acc1 += shc[q * CONTRIB_STRIDE + 32 + lane];
-        }
-        __syncwarp();
-    }
-    cv[lane] = acc0;
-    if (lane < 4) cv[32 + lane] = acc1;
-    const double axis_distance = -dot(v.mean, nrm);
-    if (axis_distance < 0.0) nrm = neg(nrm);
-    if (lane < 3) {
-        m.hot[(size_t)slot * 8 + 3 + lane] = nrm[lane];
-        m.center[(size_t)slot * 3 + lane] = v.mean[lane];
-    }
-}
-
-__global__ void __launch_bounds__(128) k_map_fill(DevMap m, DevScan s, DevCtl* ctl, int build) {
-    __shared__ double shc_all[4][32 * CONTRIB_STRIDE];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* shc = shc_all[wib];
-    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
-    const int V = ctl->n_touched;
-    const unsigned scan_id = ctl->scan_id;
-    long long c_ins = 0, c_refit = 0, c_refit_pts = 0, c_full = 0, c_probe = 0;
-    for (int vi = wg; vi < V; vi += nW) {
-        const int slot = m.touched[vi];
-        const int c = m.cnt[slot], off = m.seg_off[slot];
-        VoxelRun v;
-        hot_get_fn(m.hot, slot, v.flags, v.n);
-        int events = 0;
-        if (!(v.flags & F_UE)) {
-            events = c;                                     // full before this scan: merge() or nothing per point
-        } else {
-            int* sg = m.seg + off;
-            warp_sort(sg, c);
-            const double* h = m.hot + (size_t)slot * 8;
-            v.mean = v3(h[0], h[1], h[2]);
-#pragma unroll
-            for (int k = 0; k < 6; k++) v.ppt[k] = m.ppt[(size_t)slot * 6 + k];
-            v.nt = m.n_temp[slot]; v.nw = m.newly[slot];
-            v.full_scan = SCAN_NEVER; v.full_idx = T_INF;
-            double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
-            int j = 0;
-            for (; j < c; j++) {
-                if (!(v.flags & F_UE)) break;
-                const int i = sg[j];
-                const V3 p = v3(s.pw[3 * (size_t)i], s.pw[3 * (size_t)i + 1], s.pw[3 * (size_t)i + 2]);
-                // addToPlane (voxel_map.cpp:29-34)
-                v.mean = add(v.mean, divs(sub(p, v.mean), v.n + 1.0));
-                v.ppt[0] += p[0] * p[0]; v.ppt[1] += p[1] * p[0]; v.ppt[2] += p[1] * p[1];
-                v.ppt[3] += p[2] * p[0]; v.ppt[4] += p[2] * p[1]; v.ppt[5] += p[2] * p[2];
-                v.n += 1;
-                // temp_points.push_back
-                if (v.nt < m.maxpt) {
-                    if (lane < 3) tp[(size_t)lane * m.maxpt + v.nt] = p[lane];
-                    else if (lane < 12) tp[(size_t)lane * m.maxpt + v.nt] = s.pcov[9 * (size_t)i + (lane - 3)];
-                }
-                v.nt += 1;
-                c_ins++;
-                if (build) continue;                        // addPoint (voxel_map.cpp:36-40)
-                __syncwarp();
-                if (!(v.flags & F_INIT)) {
-                    if (v.n >= m.upt) warp_refit(m, s, ctl, slot, v, nullptr, shc, c_refit, c_refit_pts);
-                } else {
-                    v.nw += 1;
-                    if (v.nw >= m.upt) { warp_refit(m, s, ctl, slot, v, nullptr, shc, c_refit, c_refit_pts); v.nw = 0; }
-                    if (v.nt >= m.maxpt) {                   // update_enable = false; temp_points freed
-                        v.flags &= ~F_UE; v.full_scan = scan_id; v.full_idx = i; v.nt = 0;
-                    }
-                }
-            }
-            events = c - j;
-            if (build && v.n >= m.upt) { __syncwarp(); warp_refit(m, s, ctl, slot, v, sg, shc, c_refit, c_refit_pts); }
-            if (lane == 0) {
-                double* hw = m.hot + (size_t)slot * 8;
-                hw[0] = v.mean[0]; hw[1] = v.mean[1]; hw[2] = v.mean[2];
-                hot_set_fn(m.hot, slot, v.flags, v.n);
-                for (int k = 0; k < 6; k++) m.ppt[(size_t)slot * 6 + k] = v.ppt[k];
-                m.n_temp[slot] = v.nt; m.newly[slot] = v.nw;
-                if (v.full_scan != SCAN_NEVER) { m.full_scan[slot] = v.full_scan; m.full_idx[slot] = v.full_idx; }
-            }
-        }
-        c_full += events;
-        if (!(v.flags & F_UE) && (v.flags & F_PLANE)) c_probe += events; else events = 0;
-        if (lane == 0) m.evn[slot] = events;                // merge() invocations of this voxel in this scan
-    }
-    if (lane == 0) {
-        if (c_ins) atomicAdd((unsigned long long*)&ctl->st.n_ins, (unsigned long long)c_ins);
-        if (c_refit) atomicAdd((unsigned long long*)&ctl->st.n_refit, (unsigned long long)c_refit);
-        if (c_refit_pts) atomicAdd((unsigned long long*)&ctl->st.refit_points, (unsigned long long)c_refit_pts);
-        if (c_full) atomicAdd((unsigned long long*)&ctl->st.n_full, (unsigned long long)c_full);
-        if (c_probe) atomicAdd((unsigned long long*)&ctl->st.n_mergeprobe, (unsigned long long)c_probe);
-    }
-}
+#include "vmp_fill.cuh"
 
 #include "vmp_merge.cuh"
 
@@ -614,7 +413,9 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
     k_seg_scan<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_SCAN);
     k_seg_fill<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_FILL);
     k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LRU_EVICT);
-    k_map_fill<<<sm_count * 4, 128, 0, st>>>(m, s, ctl, build ? 1 : 0); launches++; mark(mk, VMP_K_MAP_FILL);
+    k_fill_state<<<sm_count * 4, 128, 0, st>>>(m, s, ctl, build ? 1 : 0); launches++; mark(mk, VMP_K_MAP_FILL);
+    k_fill_refit<<<sm_count * 4, 128, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_FILL_REFIT);
+    k_fill_acc<<<sm_count * 2, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_FILL_ACC);
     if (!build) {
         k_merge_prefilter<<<sm_count, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
         k_merge_rounds<<<1, 512, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
