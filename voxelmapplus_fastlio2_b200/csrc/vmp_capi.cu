@@ -287,8 +287,8 @@ void vmp_config_default(vmp_config* c) {
 int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     if (!cfg || !out) { set_error("vmp_create: null argument"); return VMP_ERR_INVALID_ARG; }
     if (cfg->max_points_per_scan < 1 || cfg->map_capacity < 1 || cfg->max_point_thresh < 1 || cfg->update_size_thresh < 1 ||
-        cfg->update_size_thresh > cfg->max_point_thresh || !(cfg->voxel_size > 0.0) || cfg->opti_max_iter < 1 || cfg->opti_max_iter > 8) {
-        set_error("vmp_create: invalid configuration (need max_points_per_scan>=1, map_capacity>=1, 1<=update_size_thresh<=max_point_thresh, voxel_size>0, 1<=opti_max_iter<=8)");
+        cfg->update_size_thresh > cfg->max_point_thresh || cfg->max_point_thresh > 256 || !(cfg->voxel_size > 0.0) || cfg->opti_max_iter < 1 || cfg->opti_max_iter > 8) {
+        set_error("vmp_create: invalid configuration (need max_points_per_scan>=1, map_capacity>=1, 1<=update_size_thresh<=max_point_thresh<=256, voxel_size>0, 1<=opti_max_iter<=8)");
         return VMP_ERR_INVALID_ARG;
     }
     int ndev = 0;

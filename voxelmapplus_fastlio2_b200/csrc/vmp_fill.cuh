@@ -106,37 +106,53 @@ __device__ __forceinline__ void plane_contrib(const V3& p, const M3& S, const V3
     for (int k = 0; k < 36; k++) out[k] = C.a[k];
 }
 
-// updatePlane() reached its body: record the job (whole warp calls; returns the job id in every lane)
-__device__ int emit_job(const DevMap& m, DevCtl* ctl, int slot, int n, int nt, const V3& mean, const double* ppt,
-                        int src_off, int prev_job) {
+constexpr int SNAP_MAX = 40;            // refit snapshots buffered per voxel before they are emitted as jobs
+constexpr int SNAP_W = 12;              // doubles per snapshot: n, nt, mean[3], ppt[6], pad
+
+// Emit the buffered snapshots of one voxel as refit jobs: ONE atomic per counter for the whole group
+// (whole warp calls).  Returns the id of the first job (-1 on overflow); chains them after prev_job.
+__device__ int emit_jobs(const DevMap& m, DevCtl* ctl, int slot, const double* snap, int nj, int src_off, int prev_job) {
     const int lane = threadIdx.x & 31;
-    int j = 0, b0 = 0;
-    const int nb = (nt + 31) >> 5;
+    int j0 = 0, b0 = 0;
+    long long off0 = 0;
+    int tot_nt = 0, tot_nb = 0;
+    for (int k = 0; k < nj; k++) { const int nt = (int)snap[k * SNAP_W + 1]; tot_nt += nt; tot_nb += (nt + 31) >> 5; }
     if (lane == 0) {
-        j = atomicAdd(&ctl->n_jobs, 1);
-        const unsigned long long off = atomicAdd(&ctl->contrib_top, (unsigned long long)nt);
-        b0 = atomicAdd(&ctl->n_batches, nb);
-        if (j >= m.job_cap || off + (unsigned long long)nt > (unsigned long long)m.contrib_cap || b0 + nb > m.bat_cap) {
-            atomicOr(&ctl->err, E_QUEUE);
-            j = -1;
-        } else {
-            m.job_slot[j] = slot; m.job_n[j] = n; m.job_nt[j] = nt; m.job_off[j] = (long long)off; m.job_src[j] = src_off;
-            m.job_next[j] = -1; m.job_plane[j] = 0;
-            for (int k = 0; k < 3; k++) m.job_mean[3 * (size_t)j + k] = mean[k];
-            for (int k = 0; k < 6; k++) m.job_ppt[6 * (size_t)j + k] = ppt[k];
-            if (prev_job >= 0) m.job_next[prev_job] = j;
-        }
+        j0 = atomicAdd(&ctl->n_jobs, nj);
+        off0 = (long long)atomicAdd(&ctl->contrib_top, (unsigned long long)tot_nt);
+        b0 = atomicAdd(&ctl->n_batches, tot_nb);
+        if (j0 + nj > m.job_cap || off0 + tot_nt > m.contrib_cap || b0 + tot_nb > m.bat_cap) { atomicOr(&ctl->err, E_QUEUE); j0 = -1; }
+        else if (prev_job >= 0) m.job_next[prev_job] = j0;
     }
-    j = __shfl_sync(0xffffffffu, j, 0);
+    j0 = __shfl_sync(0xffffffffu, j0, 0);
     b0 = __shfl_sync(0xffffffffu, b0, 0);
-    if (j >= 0) for (int b = lane; b < nb; b += 32) { m.bat_job[b0 + b] = j; m.bat_idx[b0 + b] = b; }
-    return j;
+    off0 = __shfl_sync(0xffffffffu, off0, 0);
+    if (j0 < 0) return -1;
+    int acc_nt = 0, acc_nb = 0;
+    for (int k = 0; k < nj; k++) {                                    // nj is small (<= SNAP_MAX), warp-uniform loop
+        const double* sn = snap + k * SNAP_W;
+        const int nt = (int)sn[1], nb = (nt + 31) >> 5, j = j0 + k;
+        if (lane == 0) {
+            m.job_slot[j] = slot; m.job_n[j] = (int)sn[0]; m.job_nt[j] = nt; m.job_off[j] = off0 + acc_nt; m.job_src[j] = src_off;
+            m.job_next[j] = (k + 1 < nj) ? j + 1 : -1; m.job_plane[j] = 0;
+        }
+        if (lane < 3) m.job_mean[3 * (size_t)j + lane] = sn[2 + lane];
+        if (lane < 6) m.job_ppt[6 * (size_t)j + lane] = sn[5 + lane];
+        for (int b = lane; b < nb; b += 32) { m.bat_job[b0 + acc_nb + b] = j; m.bat_idx[b0 + acc_nb + b] = b; }
+        acc_nt += nt; acc_nb += nb;
+    }
+    __syncwarp();                                                     // the caller may overwrite the snapshots now
+    return j0;
 }
 
 __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl* ctl, int build) {
     __shared__ int sel_all[4][SEL_MAX];
+    __shared__ double spt_all[4][SEL_MAX * 3];
+    __shared__ double snap_all[4][SNAP_MAX * SNAP_W];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int* sel = sel_all[wib];
+    double* spt = spt_all[wib];
+    double* snap = snap_all[wib];
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
     const int V = ctl->n_touched, npts = ctl->n;
     const unsigned scan_id = ctl->scan_id;
@@ -151,19 +167,7 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
             events = c;                                     // full before this scan: merge() or nothing per point
         } else {
             int nt = m.n_temp[slot], nw = m.newly[slot];
-            // the voxel consumes at most K points before it closes (never more than its free room, at least one)
-            int K = c;
-            const int* order;
-            if (build) {
-                warp_sort(m.seg + off, c);                  // build() has no cap (Q18): every point, in order
-                order = m.seg + off;
-            } else {
-                const int room = m.maxpt - nt;
-                K = room < 1 ? 1 : room;
-                if (K > c) K = c;
-                if (K <= SEL_MAX) { warp_select_sorted(m.seg + off, c, K, npts, sel); order = sel; }
-                else { warp_sort(m.seg + off, c); order = m.seg + off; }
-            }
+            const int nt0 = nt;
             const double* h = m.hot + (size_t)slot * 8;
             V3 mean = v3(h[0], h[1], h[2]);
             double ppt[6];
@@ -171,48 +175,101 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
             for (int k = 0; k < 6; k++) ppt[k] = m.ppt[(size_t)slot * 6 + k];
             unsigned full_scan = SCAN_NEVER; int full_idx = T_INF;
             double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
-            int prev_job = -1, j = 0;
-            for (; j < K; j++) {
-                if (!(flags & F_UE) && !build) break;
-                const int i = order[j];
-                const V3 p = v3(s.pw[3 * (size_t)i], s.pw[3 * (size_t)i + 1], s.pw[3 * (size_t)i + 2]);
-                // addToPlane (voxel_map.cpp:29-34)
-                mean = add(mean, divs(sub(p, mean), n + 1.0));
-                ppt[0] += p[0] * p[0]; ppt[1] += p[1] * p[0]; ppt[2] += p[1] * p[1];
-                ppt[3] += p[2] * p[0]; ppt[4] += p[2] * p[1]; ppt[5] += p[2] * p[2];
-                n += 1;
-                // temp_points.push_back
-                if (nt < m.maxpt) {
-                    if (lane < 3) tp[(size_t)lane * m.maxpt + nt] = p[lane];
-                    else if (lane < 12) tp[(size_t)lane * m.maxpt + nt] = s.pcov[9 * (size_t)i + (lane - 3)];
+            int consumed = 0;
+            if (build) {
+                // build() has no cap (Q18): every point in order, one updatePlane() at the end.  Runs once per map.
+                int* order = m.seg + off;
+                warp_sort(order, c);
+                for (int j = 0; j < c; j++) {
+                    const int i = order[j];
+                    const V3 p = v3(s.pw[3 * (size_t)i], s.pw[3 * (size_t)i + 1], s.pw[3 * (size_t)i + 2]);
+                    mean = add(mean, divs(sub(p, mean), n + 1.0));
+                    ppt[0] += p[0] * p[0]; ppt[1] += p[1] * p[0]; ppt[2] += p[1] * p[1];
+                    ppt[3] += p[2] * p[0]; ppt[4] += p[2] * p[1]; ppt[5] += p[2] * p[2];
+                    n += 1;
                 }
-                nt += 1;
-                c_ins++;
-                if (build) continue;                        // addPoint (voxel_map.cpp:36-40)
-                bool refit = false;
-                if (!(flags & F_INIT)) {
-                    refit = n >= m.upt;                     // updatePlane() every point, early return while n < thresh
-                } else {
-                    nw += 1;
-                    if (nw >= m.upt) { refit = true; nw = 0; }
+                for (int q = lane; q < c && nt0 + q < m.maxpt; q += 32) {
+                    const int i = order[q];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) tp[(size_t)k * m.maxpt + nt0 + q] = s.pw[3 * (size_t)i + k];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) tp[(size_t)(3 + k) * m.maxpt + nt0 + q] = s.pcov[9 * (size_t)i + k];
                 }
-                const bool was_init = (flags & F_INIT) != 0;
-                if (refit) {
+                nt += c; consumed = c;
+                if (n >= m.upt) {
                     flags |= F_INIT;
-                    const int jb = emit_job(m, ctl, slot, n, nt, mean, ppt, -1, prev_job);
+                    if (lane == 0) { snap[0] = n; snap[1] = nt; for (int k = 0; k < 3; k++) snap[2 + k] = mean[k]; for (int k = 0; k < 6; k++) snap[5 + k] = ppt[k]; }
+                    __syncwarp();
+                    first_job = emit_jobs(m, ctl, slot, snap, 1, off, -1);
+                }
+            } else {
+                // the voxel consumes at most K points before it closes (never more than its free room, at least one)
+                const int room = m.maxpt - nt;
+                int K = room < 1 ? 1 : room;
+                if (K > c) K = c;
+                warp_select_sorted(m.seg + off, c, K, npts, sel);              // K <= max_point_thresh <= SEL_MAX
+                for (int q = lane; q < K; q += 32) {                           // gather the K points once, in parallel
+                    const int i = sel[q];
+                    spt[3 * q] = s.pw[3 * (size_t)i]; spt[3 * q + 1] = s.pw[3 * (size_t)i + 1]; spt[3 * q + 2] = s.pw[3 * (size_t)i + 2];
+                }
+                __syncwarp();
+                int nsnap = 0, prev_job = -1, j = 0;
+                for (; j < K; j++) {                                           // pushPoint state machine, point order
+                    if (!(flags & F_UE)) break;
+                    const V3 p = v3(spt[3 * j], spt[3 * j + 1], spt[3 * j + 2]);
+                    // addToPlane (voxel_map.cpp:29-34)
+                    mean = add(mean, divs(sub(p, mean), n + 1.0));
+                    ppt[0] += p[0] * p[0]; ppt[1] += p[1] * p[0]; ppt[2] += p[1] * p[1];
+                    ppt[3] += p[2] * p[0]; ppt[4] += p[2] * p[1]; ppt[5] += p[2] * p[2];
+                    n += 1;
+                    nt += 1;                                                   // temp_points.push_back (stored below)
+                    bool refit = false;
+                    if (!(flags & F_INIT)) {
+                        refit = n >= m.upt;                                    // updatePlane() every point, early return while n < thresh
+                    } else {
+                        nw += 1;
+                        if (nw >= m.upt) { refit = true; nw = 0; }
+                    }
+                    const bool was_init = (flags & F_INIT) != 0;
+                    if (refit) {
+                        flags |= F_INIT;
+                        if (nsnap == SNAP_MAX) {
+                            __syncwarp();
+                            const int jb = emit_jobs(m, ctl, slot, snap, nsnap, -1, prev_job);
+                            if (first_job < 0) first_job = jb;
+                            prev_job = jb < 0 ? -1 : jb + nsnap - 1;
+                            nsnap = 0;
+                        }
+                        if (lane == 0) {
+                            double* sn = snap + nsnap * SNAP_W;
+                            sn[0] = n; sn[1] = nt;
+                            for (int k = 0; k < 3; k++) sn[2 + k] = mean[k];
+                            for (int k = 0; k < 6; k++) sn[5 + k] = ppt[k];
+                        }
+                        nsnap++;
+                    }
+                    if (was_init && nt >= m.maxpt) {                           // update_enable = false; temp_points freed
+                        flags &= ~F_UE; full_scan = scan_id; full_idx = sel[j]; nt = 0;
+                    }
+                }
+                consumed = j;
+                if (j == K && K < c && (flags & F_UE) && lane == 0) atomicOr(&ctl->err, E_QUEUE);   // cannot happen: K points always close the voxel
+                __syncwarp();
+                if (nsnap > 0) {
+                    const int jb = emit_jobs(m, ctl, slot, snap, nsnap, -1, prev_job);
                     if (first_job < 0) first_job = jb;
-                    prev_job = jb;
                 }
-                if (was_init && nt >= m.maxpt) {            // update_enable = false; temp_points freed
-                    flags &= ~F_UE; full_scan = scan_id; full_idx = i; nt = 0;
+                // store the consumed points (xyz + cov) behind the nt0 already stored ones, one point per lane
+                for (int q = lane; q < consumed && nt0 + q < m.maxpt; q += 32) {
+                    const int i = sel[q];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) tp[(size_t)k * m.maxpt + nt0 + q] = spt[3 * q + k];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) tp[(size_t)(3 + k) * m.maxpt + nt0 + q] = s.pcov[9 * (size_t)i + k];
                 }
             }
-            events = c - j;
-            if (!build && j == K && K < c && (flags & F_UE) && lane == 0) atomicOr(&ctl->err, E_QUEUE);   // cannot happen: K points always close the voxel
-            if (build && n >= m.upt) {                       // one updatePlane() per voxel at the end of build()
-                flags |= F_INIT;
-                first_job = emit_job(m, ctl, slot, n, nt, mean, ppt, off, -1);
-            }
+            c_ins += consumed;
+            events = c - consumed;
             __syncwarp();
             if (lane == 0) {
                 double* hw = m.hot + (size_t)slot * 8;
@@ -229,6 +286,7 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
             if (!(flags & F_UE) && (flags & F_PLANE)) c_probe += events; else events = 0;
         }
         if (lane == 0) { m.evn[slot] = events; m.vox_job[vi] = first_job; }
+        __syncwarp();
     }
     if (lane == 0) {
         if (c_ins) atomicAdd((unsigned long long*)&ctl->st.n_ins, (unsigned long long)c_ins);
@@ -294,9 +352,14 @@ __global__ void __launch_bounds__(128) k_fill_refit(DevMap m, DevScan s, DevCtl*
     }
 }
 
-// plane->cov += J Sigma J^T, jobs in refit order, points in stored order; final normal / centre / is_plane
-__global__ void __launch_bounds__(128) k_fill_acc(DevMap m, DevCtl* ctl) {
-    const int lane = threadIdx.x & 31;
+// plane->cov += J Sigma J^T, jobs in refit order, points in stored order; final normal / centre / is_plane.
+// The adds of one entry form one dependent chain (that IS the reference's order); the loads do not: the
+// contributions are streamed through shared memory in chunks of 32 points, the next chunk's loads are in
+// flight while the current chunk is being added.
+constexpr int ACC_CHUNK = 32;
+__global__ void __launch_bounds__(64) k_fill_acc(DevMap m, DevCtl* ctl) {
+    __shared__ double buf_all[2][2][ACC_CHUNK * 36];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
     const int V = ctl->n_touched;
     long long c_probe = 0;
@@ -314,20 +377,33 @@ __global__ void __launch_bounds__(128) k_fill_acc(DevMap m, DevCtl* ctl) {
             last_plane = j;
             const double* src = m.contrib + (size_t)m.job_off[j] * 36;
             const int nt = m.job_nt[j];
-            int q = 0;
-            for (; q + 4 <= nt; q += 4) {                                  // loads batched, adds strictly in order
-                const double a0 = src[(size_t)q * 36 + lane], a1 = src[(size_t)(q + 1) * 36 + lane];
-                const double a2 = src[(size_t)(q + 2) * 36 + lane], a3 = src[(size_t)(q + 3) * 36 + lane];
-                double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-                if (lane < 4) { b0 = src[(size_t)q * 36 + 32 + lane]; b1 = src[(size_t)(q + 1) * 36 + 32 + lane];
-                                b2 = src[(size_t)(q + 2) * 36 + 32 + lane]; b3 = src[(size_t)(q + 3) * 36 + 32 + lane]; }
-                acc0 += a0; acc0 += a1; acc0 += a2; acc0 += a3;
-                if (lane < 4) { acc1 += b0; acc1 += b1; acc1 += b2; acc1 += b3; }
+            const int nch = (nt + ACC_CHUNK - 1) / ACC_CHUNK;
+            double r[36];
+            // prologue: chunk 0 -> registers (36 coalesced loads per lane)
+            {
+                const int tot = (nt < ACC_CHUNK ? nt : ACC_CHUNK) * 36;
+#pragma unroll
+                for (int k = 0; k < 36; k++) { const int e = k * 32 + lane; r[k] = e < tot ? src[e] : 0.0; }
             }
-            for (; q < nt; q++) {
-                acc0 += src[(size_t)q * 36 + lane];
-                if (lane < 4) acc1 += src[(size_t)q * 36 + 32 + lane];
+            for (int ch = 0; ch < nch; ch++) {
+                double* buf = buf_all[wib][ch & 1];
+#pragma unroll
+                for (int k = 0; k < 36; k++) buf[k * 32 + lane] = r[k];
+                __syncwarp();
+                if (ch + 1 < nch) {                                        // next chunk's loads fly during the adds
+                    const int base = (ch + 1) * ACC_CHUNK;
+                    const int tot = ((nt - base) < ACC_CHUNK ? (nt - base) : ACC_CHUNK) * 36;
+                    const double* sc = src + (size_t)base * 36;
+#pragma unroll
+                    for (int k = 0; k < 36; k++) { const int e = k * 32 + lane; r[k] = e < tot ? sc[e] : 0.0; }
+                }
+                const int cb = (nt - ch * ACC_CHUNK) < ACC_CHUNK ? (nt - ch * ACC_CHUNK) : ACC_CHUNK;
+                for (int q = 0; q < cb; q++) {                             // strictly in stored-point order (Q7)
+                    acc0 += buf[q * 36 + lane];
+                    if (lane < 4) acc1 += buf[q * 36 + 32 + lane];
+                }
             }
+            __syncwarp();
         }
         cv[lane] = acc0;
         if (lane < 4) cv[32 + lane] = acc1;

@@ -415,7 +415,7 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
     k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LRU_EVICT);
     k_fill_state<<<sm_count * 4, 128, 0, st>>>(m, s, ctl, build ? 1 : 0); launches++; mark(mk, VMP_K_MAP_FILL);
     k_fill_refit<<<sm_count * 4, 128, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_FILL_REFIT);
-    k_fill_acc<<<sm_count * 2, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_FILL_ACC);
+    k_fill_acc<<<sm_count * 8, 64, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_FILL_ACC);
     if (!build) {
         k_merge_prefilter<<<sm_count, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
         k_merge_rounds<<<1, 512, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
