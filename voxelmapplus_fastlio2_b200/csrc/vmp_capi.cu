@@ -440,7 +440,14 @@ static int map_update_common(vmp_handle h, const double* pts, const double* cov,
         VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.pw, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
         VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.pcov, cov, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, h->stream));
     }
-    h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, nullptr);
+    if (h->prof_on) {                       // per-kernel CUDA events (vmp_profile_*)
+        Marker mk{prof_mark, h};
+        h->pev_n = 0;
+        VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream));
+        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, &mk);
+    } else {
+        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, nullptr);
+    }
     k_scan_out<<<1, 256, 0, h->stream>>>(h->f, h->ctl, h->d_out);
     h->launches += 1;
     h->map_built = true;
