@@ -334,7 +334,7 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     DALLOC(m.cnt, m.pool); DALLOC(m.cursor, m.pool); DALLOC(m.ft, m.pool); DALLOC(m.lt, m.pool); DALLOC(m.seg_off, m.pool);
     DALLOC(m.evict_t, m.pool); DALLOC(m.ghost, m.pool); DALLOC(m.evn, m.pool); DALLOC(m.free_slots, m.pool);
     DALLOC(m.tpos, nmax); DALLOC(m.pslot, nmax); DALLOC(m.seg, nmax);
-    DALLOC(m.touched, nmax); DALLOC(m.hotlist, nmax); DALLOC(m.ev_slot, nmax); DALLOC(m.ev_time, nmax); DALLOC(m.ev_key, nmax);
+    DALLOC(m.touched, nmax); DALLOC(m.newlist, nmax); DALLOC(m.hotlist, nmax); DALLOC(m.ev_slot, nmax); DALLOC(m.ev_time, nmax); DALLOC(m.ev_key, nmax);
     DALLOC(m.ct, nmax); DALLOC(m.act_slot, nmax); DALLOC(m.act_t, nmax);
     m.job_cap = 2 * nmax + 64;
     m.contrib_cap = (long long)nmax * (m.maxpt / m.upt + 2) + 1024;

@@ -114,6 +114,7 @@ struct DevMap {
     unsigned* tpos; int* pslot; int* seg;
     // lists
     int* touched;                       // [nmax]
+    int* newlist;                       // [nmax] slots created by this map update
     int* hotlist;                       // [nmax]
     int* ev_slot; int* ev_time; unsigned long long* ev_key;   // eviction list [nmax]
     int* ct;                            // creation times (sorted) [nmax]

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) k_map_insert(DevMap m, DevScan s, DevCtl*
             const int slot = pop_free(m, ctl);
             if (slot >= 0) slot_init_fresh(m, ctl, slot, pk);
             m.tval[h] = slot;
-            atomicAdd(&ctl->n_new, 1);
+            if (slot >= 0) m.newlist[atomicAdd(&ctl->n_new, 1)] = slot;
         }
     }
 }
@@ -263,41 +263,44 @@ __global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl) {
 }
 
 // ------------------------------------------------------------------------- M2: exact LRU eviction
-// cache.push_front / splice / "if (cache.size() > capacity) erase(cache.back())"
-// (voxel_map.cpp:242-253).  One CTA: ordered compaction of the creation times, then a
-// short serial walk over the head of the LRU log.
-__global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
-    __shared__ int sh[34];
-    __shared__ int rq[64];
-    const int n = ctl->n;
-    const int n_live0 = ctl->n_live, n_new = ctl->n_new;
-    if (n_live0 + n_new <= m.capacity) {
-        if (threadIdx.x == 0) { ctl->n_live = n_live0 + n_new; ctl->st.n_created = n_new; }
-        return;
+// cache.push_front / splice / "if (cache.size() > capacity) erase(cache.back())" (voxel_map.cpp:242-253).
+// The k-th over-capacity creation (at point index t_k) evicts the oldest LRU-log entry that is neither
+// stale nor was spliced to the front earlier in this scan (touched with first touch < t_k).
+//   fast path (one CTA, parallel): sort the creation times of the new voxels; rank the valid untouched
+//     entries of the log head with block scans: the r-th of them is the victim of eviction r, PROVIDED every
+//     touched entry met on the way was indeed touched before the eviction it was examined for - checked
+//     in the same pass.
+//   slow path (thread 0, serial walk): when that check fails, i.e. a victim is touched again later in the
+//     same scan (it is then re-created fresh; its old incarnation stays visible to merge() as a ghost slot).
+constexpr int LRU_SORT_MAX = 8192;
+
+__device__ void block_bitonic_sort(int* a, int npow) {            // ascending, shared memory, whole CTA
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < npow; t += blockDim.x) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const int x = a[t], y = a[u];
+                    const bool up = (t & k) == 0;
+                    if ((x > y) == up) { a[t] = y; a[u] = x; }
+                }
+            }
+            __syncthreads();
+        }
     }
-    const unsigned scan_id = ctl->scan_id;
-    int base = 0;
-    for (int b = 0; b * PT_BLOCK < n; b++) {
-        const int nb = m.blk_new[b];
-        if (nb == 0) continue;
-        const int i = b * PT_BLOCK + threadIdx.x;
-        int f = 0;
-        if (i < n) { const int slot = m.pslot[i]; if (slot >= 0) f = (m.ft[slot] == i && m.born_scan[slot] == scan_id); }
-        int total;
-        const int r = block_excl_scan(f, &total, sh);
-        if (f) m.ct[base + r] = i;
-        base += nb;
-    }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+}
+
+// serial walk (one thread): creation times ct[0..n_new) ascending
+__device__ void lru_serial_walk(const DevMap& m, DevCtl* ctl, const int* ct, int n_live0, int n_new) {
+    int rq[64];
     int size = n_live0, ne = 0, rqn = 0, ci = 0, created = n_new;
     long long h = ctl->log_head;
     const long long tail = ctl->log_tail;
     const int sel = ctl->log_sel;
     while (ci < n_new || rqn > 0) {
         int t;
-        if (rqn > 0 && (ci >= n_new || rq[0] < m.ct[ci])) { t = rq[0]; for (int q = 1; q < rqn; q++) rq[q - 1] = rq[q]; rqn--; }
-        else t = m.ct[ci++];
+        if (rqn > 0 && (ci >= n_new || rq[0] < ct[ci])) { t = rq[0]; for (int q = 1; q < rqn; q++) rq[q - 1] = rq[q]; rqn--; }
+        else t = ct[ci++];
         size += 1;
         if (size <= m.capacity) continue;
         int victim = -1;
@@ -341,6 +344,88 @@ __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
     }
     ctl->n_evict = ne; ctl->n_live = size; ctl->log_head = h;
     ctl->st.n_evicted = ne; ctl->st.n_created = created;
+}
+
+__global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
+    __shared__ int sct[LRU_SORT_MAX];
+    __shared__ int sh[34];
+    __shared__ int s_bad;
+    __shared__ long long s_headpos;
+    const int tid = threadIdx.x;
+    const int n = ctl->n;
+    const int n_live0 = ctl->n_live, n_new = ctl->n_new;
+    if (n_live0 + n_new <= m.capacity) {
+        if (tid == 0) { ctl->n_live = n_live0 + n_new; ctl->st.n_created = n_new; }
+        return;
+    }
+    const unsigned scan_id = ctl->scan_id;
+    if (n_new > LRU_SORT_MAX) {
+        // very many new voxels: creation times by ordered compaction over the points, then the serial walk
+        int base = 0;
+        for (int b = 0; b * PT_BLOCK < n; b++) {
+            const int nb = m.blk_new[b];
+            if (nb == 0) continue;
+            const int i = b * PT_BLOCK + tid;
+            int f = 0;
+            if (i < n) { const int slot = m.pslot[i]; if (slot >= 0) f = (m.ft[slot] == i && m.born_scan[slot] == scan_id); }
+            int total;
+            const int r = block_excl_scan(f, &total, sh);
+            if (f) m.ct[base + r] = i;
+            base += nb;
+        }
+        __syncthreads();
+        if (tid == 0) lru_serial_walk(m, ctl, m.ct, n_live0, n_new);
+        return;
+    }
+    // creation times = first touches of the voxels created by k_map_insert, sorted
+    int npow = 2;
+    while (npow < n_new) npow <<= 1;
+    for (int q = tid; q < npow; q += blockDim.x) sct[q] = q < n_new ? m.ft[m.newlist[q]] : INT_MAX;
+    if (tid == 0) { s_bad = 0; s_headpos = ctl->log_head; }
+    __syncthreads();
+    block_bitonic_sort(sct, npow);
+    const int slack = m.capacity - n_live0;                 // creations that still fit
+    const int E = n_new - slack;                            // evictions if no victim is re-created
+    const int sel = ctl->log_sel;
+    const long long tail = ctl->log_tail;
+    int base_u = 0;
+    for (long long pos = ctl->log_head; base_u < E && pos < tail; pos += blockDim.x) {
+        const long long p = pos + tid;
+        int sl = -1;
+        bool live = false, touched = false;
+        if (p < tail) {
+            sl = m.log_slot[sel][p];
+            live = m.stamp[sl] == m.log_stamp[sel][p];
+            touched = live && m.cnt[sl] > 0;
+        }
+        const int U = (live && !touched) ? 1 : 0;
+        int total;
+        const int r = base_u + block_excl_scan(U, &total, sh);          // victim index this entry is examined for
+        if (r < E) {
+            const int t = sct[slack + r];
+            if (U) {
+                m.ev_slot[r] = sl; m.ev_time[r] = t; m.ev_key[r] = m.skey[sl];
+                if (r == E - 1) s_headpos = p + 1;
+            } else if (touched && !(m.ft[sl] < t)) {
+                s_bad = 1;                                  // this entry would be evicted and re-created later in the scan
+            }
+        }
+        base_u += total;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (s_bad) {
+        for (int q = tid; q < n_new; q += blockDim.x) m.ct[q] = sct[q];
+        __syncthreads();
+        if (tid == 0) lru_serial_walk(m, ctl, m.ct, n_live0, n_new);
+        return;
+    }
+    if (base_u < E) { if (tid == 0) atomicOr(&ctl->err, E_LRU_EXHAUSTED); return; }
+    for (int r = tid; r < E; r += blockDim.x) m.evict_t[m.ev_slot[r]] = m.ev_time[r];
+    if (tid == 0) {
+        ctl->n_evict = E; ctl->n_live = m.capacity; ctl->log_head = s_headpos;
+        ctl->st.n_evicted = E; ctl->st.n_created = n_new;
+    }
 }
 
 #include "vmp_fill.cuh"
