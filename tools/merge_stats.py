@@ -23,6 +23,6 @@ for pk in seq.packages(n_scans):
     rows.append((pk.index, st.iters, st.map.n_touch, st.map.n_full, st.map.n_merge, d[0], d[1], d[2], st.gpu_ms, st.host_ms))
     if pk.index % 5 == 0:
         print("scan %3d iters %d touch %5d full %6d merges %3d | active0 %4d events %4d react %3d | gpu %.3f ms host %.3f ms" % rows[-1])
-print("solve kernel phase cycles (first iteration of the last scan): reduce|boxminus %d, J blocks %d, products %d, LU inverse %d, dx+boxplus %d" % tuple(d[3:8]))
+print("solve kernel phase cycles (first iteration of the last scan): A reduce|boxminus|J %d, B DxD algebra + boxplus %d, C posterior %d" % tuple(d[3:6]))
 a = np.array(rows, float)
 print("mean: merges %.1f active0 %.1f events %.1f react %.1f gpu_ms %.3f" % (a[:, 4].mean(), a[:, 5].mean(), a[:, 6].mean(), a[:, 7].mean(), a[10:, 8].mean()))

@@ -172,21 +172,9 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk) {
     const bool ext = h->cfg.estimate_ext != 0;
     int k = 0;
     k_scan_in<<<1, 256, 0, st>>>(h->d_in, h->f, h->ctl); k++; mark(mk, VMP_K_SCAN_IN);
-    // P^-1 on a forked branch (second stream inside the capture): overlaps k_set_scan and the first k_measure,
-    // joined before the first k_ieskf_solve.  Profiling mode keeps one stream so that events attribute cleanly.
-    const bool fork = (mk == nullptr) && h->stream2 != nullptr;
-    if (fork) {
-        cudaEventRecord(h->ev_fork, st);
-        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-        launch_update_begin(h->stream2, h->f, h->ctl); k++;
-        cudaEventRecord(h->ev_join, h->stream2);
-    }
     launch_set_scan(st, h->grid_pts, h->s, h->ctl); k++; mark(mk, VMP_K_SET_SCAN);
-    if (!fork) { launch_update_begin(st, h->f, h->ctl); k++; mark(mk, VMP_K_UPDATE_BEGIN); }
     for (int it = 0; it < h->cfg.opti_max_iter; it++) {
-        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials); k++; mark(mk, VMP_K_MEASURE);
-        if (fork && it == 0) cudaStreamWaitEvent(st, h->ev_join, 0);
-        launch_solve(st, ext, h->f, h->ctl, h->partials, h->grid_meas); k++; mark(mk, VMP_K_SOLVE);
+        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1); k++; mark(mk, VMP_K_MEASURE);
     }
     launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++; mark(mk, VMP_K_WORLD_POINTS);
     k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false, mk);
@@ -501,7 +489,7 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, P, sizeof(double) * 529, cudaMemcpyHostToDevice, h->stream));
     k_reset_iter<<<1, 1, 0, h->stream>>>(h->ctl);
     const bool ext = h->cfg.estimate_ext != 0;
-    launch_measure(h->stream, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials);
+    launch_measure(h->stream, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 0);
     k_reduce_partials<<<1, 160, 0, h->stream>>>(h->partials, h->grid_meas, ext ? 1 : 0, h->meas_out);
     h->launches += 3;
     double out[157];

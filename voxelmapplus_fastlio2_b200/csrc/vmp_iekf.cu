@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256) k_set_scan(DevScan s, const DevCtl* __res
     }
 }
 
+#include "vmp_solve.cuh"
+
 // ---------------------------------------------------------------------------- K1
 struct MeasState {
     M3 r_wl, R, Rext, Prr, Ppp;
@@ -40,7 +42,7 @@ struct MeasState {
 
 template <bool EXT>
 __global__ void __launch_bounds__(EXT ? 128 : 256)
-k_measure(DevMap m, DevScan s, const DevFilter* __restrict__ f, DevCtl* ctl, double* __restrict__ partials) {
+k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;                 // upper triangle of H, b, effect count
@@ -156,15 +158,27 @@ k_measure(DevMap m, DevScan s, const DevFilter* __restrict__ f, DevCtl* ctl, dou
         for (int w = 1; w < nw; w++) t += red[w][v];
         partials[(size_t)blockIdx.x * PARTIAL_STRIDE + v] = t;
     }
+    if (!solve) return;
+    // the last CTA to arrive runs the 23-dof solve of this iteration (IESKF::update body, vmp_solve.cuh)
+    __shared__ int s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(&ctl->ticket, 1u);
+        s_is_last = (ticket == gridDim.x - 1) ? 1 : 0;
+        if (s_is_last) ctl->ticket = 0;
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    ieskf_solve_block<EXT, EXT ? 128 : 256>(f, ctl, partials, (int)gridDim.x);
 }
 
-void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, const DevFilter* f, DevCtl* ctl, double* partials) {
-    if (ext) k_measure<true><<<grid, 128, 0, st>>>(m, s, f, ctl, partials);
-    else k_measure<false><<<grid, 256, 0, st>>>(m, s, f, ctl, partials);
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
+    if (ext) k_measure<true><<<grid, 128, 0, st>>>(m, s, f, ctl, partials, solve);
+    else k_measure<false><<<grid, 256, 0, st>>>(m, s, f, ctl, partials, solve);
 }
 void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const DevCtl* ctl) { k_set_scan<<<grid, 256, 0, st>>>(s, ctl); }
-
-#include "vmp_solve.cuh"
 
 // ---------------------------------------------------------------------------- K3
 // float32 world transform with the association of PCL's SSE Transformer::se3
