@@ -44,7 +44,19 @@ def assert_maps_equal(a, b, exact=True, rtol=1e-9, what=""):
                 raise AssertionError(f"{what}: field {f} not bit-exact, worst abs diff {d[bad]} at keys {a['key'][bad].tolist()} "
                                      f"flags {a['flags'][bad]} n {a['n'][bad]}")
         else:
-            np.testing.assert_allclose(a[f], b[f], rtol=rtol, atol=1e-12, err_msg=f"{what}: field {f}")
+            # Q15: world points are float32.  A posterior that differs from the oracle's in the 9th digit flips the
+            # float32 rounding of a few coordinates by one ulp (2.4e-7 at 4 m).  Voxels that hold such a point differ
+            # in the 7th digit, all others agree to rtol: at most 0.5 % of the voxels may be of the first kind, and
+            # those must still agree to 1e-3 relative (or 100 float32 ulps of the field's typical magnitude).
+            x, y = a[f].reshape(len(a), -1), b[f].reshape(len(b), -1)
+            if len(x) == 0:
+                continue
+            fin = np.where(np.isfinite(y), np.abs(y), 0.0).max(axis=1)
+            scale = float(np.median(fin))                  # typical magnitude of the field (inf / NaN of degenerate voxels aside)
+            tight = np.all(np.isclose(x, y, rtol=rtol, atol=1e-12, equal_nan=True), axis=1)
+            loose = np.all(np.isclose(x, y, rtol=1e-3, atol=100 * float(np.finfo(np.float32).eps) * scale, equal_nan=True), axis=1)
+            assert loose.all(), f"{what}: field {f} differs beyond float32-rounding effects at keys {a['key'][~loose][:5].tolist()}"
+            assert (~tight).sum() <= max(3, 0.005 * len(x)), f"{what}: field {f}: {(~tight).sum()} of {len(x)} voxels differ beyond rtol {rtol}"
 
 
 def plane_cloud(rng, n, origin, u, v, extent, noise):

@@ -373,6 +373,11 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     h->launches += 1;
     const int mi = cfg->opti_max_iter;
     VMP_CUDA_CHECK(cudaMemcpyAsync(&h->ctl->max_iter, &mi, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (const char* e = getenv("VMP_DEBUG_ITER")) {          // diagnostics: which iteration's solver phase cycles to record
+        const int di = atoi(e);
+        VMP_CUDA_CHECK(cudaMemcpyAsync(&h->ctl->dbg_it, &di, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
     VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     int r = build_graph(h);
     if (r) return r;

@@ -65,9 +65,10 @@ struct DevCtl {
     unsigned long long group_counter;
     int err;
     int pad0;
-    unsigned ticket;                    // arrival counter of k_measure's CTAs (the last one runs the solve)
+    unsigned ticket;                    // arrival counter of k_measure's measurement CTAs (the solver CTA waits on it)
     int n_jobs, n_batches;              // refit jobs / 32-point batches of this map update
     unsigned long long contrib_top;     // staged contributions (points)
+    int dbg_it;                         // which IEKF iteration's solver phase cycles go to dbg[3..6]
     int dbg[8];                         // debug counters of the last map update: [0] active set after the prefilter, [1] merge events simulated, [2] re-examinations that activated a voxel
     DevStats st;
     // IEKF

@@ -49,6 +49,13 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     __shared__ MeasState ms;
     __shared__ double red[8][NV];
     if (ctl->done) return;
+    // launched with solve = 1 the grid has one more CTA: block 0 runs this iteration's 23-dof solve (IESKF::update body,
+    // vmp_solve.cuh), starting with the part that needs no measurement while the other CTAs measure
+    if (solve && blockIdx.x == 0) {
+        ieskf_solve_cta<EXT, EXT ? 128 : 256>(f, ctl, partials, (int)gridDim.x - 1);
+        return;
+    }
+    const int pb = (int)blockIdx.x - solve, npb = (int)gridDim.x - solve;      // measurement CTA index / count
     if (threadIdx.x == 0) {
         const St x = st_load(f->x);
         ms.R = x.rot; ms.Rext = x.rot_ext; ms.pext = x.pos_ext;
@@ -67,7 +74,7 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
 #pragma unroll
     for (int v = 0; v < NV; v++) acc[v] = 0.0;
 
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = pb * blockDim.x + threadIdx.x; i < n; i += npb * blockDim.x) {
         const V3 pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
         const V3 pw = add(mul(r_wl, pl), p_wl);
         unsigned long long pk;
@@ -156,27 +163,19 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     for (int v = threadIdx.x; v < NV; v += blockDim.x) {
         double t = red[0][v];
         for (int w = 1; w < nw; w++) t += red[w][v];
-        partials[(size_t)blockIdx.x * PARTIAL_STRIDE + v] = t;
+        partials[(size_t)pb * PARTIAL_STRIDE + v] = t;
     }
     if (!solve) return;
-    // the last CTA to arrive runs the 23-dof solve of this iteration (IESKF::update body, vmp_solve.cuh)
-    __shared__ int s_is_last;
+    // release this CTA's partial sums to the solver CTA
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(&ctl->ticket, 1u);
-        s_is_last = (ticket == gridDim.x - 1) ? 1 : 0;
-        if (s_is_last) ctl->ticket = 0;
-    }
-    __syncthreads();
-    if (!s_is_last) return;
-    __threadfence();
-    ieskf_solve_block<EXT, EXT ? 128 : 256>(f, ctl, partials, (int)gridDim.x);
+    if (threadIdx.x == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
 void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
-    if (ext) k_measure<true><<<grid, 128, 0, st>>>(m, s, f, ctl, partials, solve);
-    else k_measure<false><<<grid, 256, 0, st>>>(m, s, f, ctl, partials, solve);
+    const int g = grid + (solve ? 1 : 0);
+    if (ext) k_measure<true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve);
+    else k_measure<false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve);
 }
 void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const DevCtl* ctl) { k_set_scan<<<grid, 256, 0, st>>>(s, ctl); }
 

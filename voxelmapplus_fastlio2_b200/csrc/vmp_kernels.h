@@ -12,7 +12,6 @@ constexpr int PT_BLOCK = 1024;          // points per block in the order-preserv
 
 // IEKF
 void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const DevCtl* ctl);
-void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl);
 // solve != 0: the last-arriving CTA also runs the 23-dof solve of the iteration (one launch per IEKF iteration)
 void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve);
 void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, const DevCtl* ctl, int first_scan);

@@ -19,39 +19,77 @@
 constexpr int NS = 23;
 constexpr int NE = NS * NS;
 
-// the three non-identity blocks of J / L (ieskf.cpp:136-139, 151-154): jb[0..8] rows 3-5, jb[9..17] rows 6-8, jb[18..21] rows 21-22
-__device__ __noinline__ void jac_blocks(double* jb, const double* delta, const double* g_cur, const double* g_pred, int which) {
-    if (which == 0 || which == 1) {
-        const int o = which == 0 ? 3 : 6;
-        const M3 j = right_jacobian(v3(delta[o], delta[o + 1], delta[o + 2]));
-        for (int a = 0; a < 9; a++) jb[which * 9 + a] = j.a[a];
-    } else {
-        Mat<2, 1> dg; dg[0] = delta[21]; dg[1] = delta[22];
-        const Mat<2, 2> jg = mul(st_Nx(v3(g_cur[0], g_cur[1], g_cur[2])), st_Mx_res(v3(g_pred[0], g_pred[1], g_pred[2]), dg));
-        jb[18] = jg(0, 0); jb[19] = jg(0, 1); jb[20] = jg(1, 0); jb[21] = jg(1, 1);
-    }
+// ---- manifold pieces: each runs on ONE lane of its own warp, so the three of them proceed in parallel ----
+// J or L block of a rotation (ieskf.cpp:136-137 / 151-152)
+__device__ __noinline__ void rot_jac(const double* d3, double* jb9) {
+    const M3 j = right_jacobian(v3(d3[0], d3[1], d3[2]));
+    for (int a = 0; a < 9; a++) jb9[a] = j.a[a];
 }
-// inverses of those blocks (3x3 by cofactors, 2x2 closed form)
-__device__ __forceinline__ void inv_blocks(const double* jb, double* ab, int which) {
-    if (which < 2) {
-        const double* m = jb + which * 9;
-        double* o = ab + which * 9;
-        const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
-        const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
-        o[0] = c00 / det; o[1] = (m[2] * m[7] - m[1] * m[8]) / det; o[2] = (m[1] * m[5] - m[2] * m[4]) / det;
-        o[3] = c01 / det; o[4] = (m[0] * m[8] - m[2] * m[6]) / det; o[5] = (m[2] * m[3] - m[0] * m[5]) / det;
-        o[6] = c02 / det; o[7] = (m[1] * m[6] - m[0] * m[7]) / det; o[8] = (m[0] * m[4] - m[1] * m[3]) / det;
-    } else {
-        const double det = jb[18] * jb[21] - jb[19] * jb[20];
-        ab[18] = jb[21] / det; ab[19] = -jb[19] / det; ab[20] = -jb[20] / det; ab[21] = jb[18] / det;
-    }
+// J or L block of the S2 gravity (ieskf.cpp:138-139 / 153-154)
+__device__ __noinline__ void g_jac(const double* g_cur, const double* g_pred, const double* d2, double* jb4) {
+    Mat<2, 1> dg; dg[0] = d2[0]; dg[1] = d2[1];
+    const Mat<2, 2> jg = mul(st_Nx(v3(g_cur[0], g_cur[1], g_cur[2])), st_Mx_res(v3(g_pred[0], g_pred[1], g_pred[2]), dg));
+    jb4[0] = jg(0, 0); jb4[1] = jg(0, 1); jb4[2] = jg(1, 0); jb4[3] = jg(1, 1);
 }
-// entry (i, j) of a block-diagonal 23x23 matrix given by its three blocks (identity elsewhere)
+__device__ __forceinline__ void inv3_cof(const double* m, double* o) {
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    o[0] = c00 / det; o[1] = (m[2] * m[7] - m[1] * m[8]) / det; o[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+    o[3] = c01 / det; o[4] = (m[0] * m[8] - m[2] * m[6]) / det; o[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+    o[6] = c02 / det; o[7] = (m[1] * m[6] - m[0] * m[7]) / det; o[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+}
+// delta = Log(Rp^T R) (ieskf.cpp:41-47), J = right jacobian, A = J^-1
+__device__ __noinline__ void man_rot_piece(const double* R, const double* Rp, double* delta3, double* jb9, double* ab9) {
+    M3 a, b;
+    for (int k = 0; k < 9; k++) { a.a[k] = R[k]; b.a[k] = Rp[k]; }
+    const V3 t = so3_log(mul(tr(b), a));
+    delta3[0] = t[0]; delta3[1] = t[1]; delta3[2] = t[2];
+    rot_jac(delta3, jb9);
+    inv3_cof(jb9, ab9);
+}
+__device__ __noinline__ void man_g_piece(const double* g, const double* gp, double* delta2, double* jb4, double* ab4) {
+    st_boxminus_g(v3(g[0], g[1], g[2]), v3(gp[0], gp[1], gp[2]), delta2);
+    g_jac(g, gp, delta2, jb4);
+    const double det = jb4[0] * jb4[3] - jb4[1] * jb4[2];
+    ab4[0] = jb4[3] / det; ab4[1] = -jb4[1] / det; ab4[2] = -jb4[2] / det; ab4[3] = jb4[0] / det;
+}
+// rot <- rot Exp(d) (ieskf.cpp:14-15)
+__device__ __noinline__ void plus_rot_piece(double* R, const double* d3) {
+    M3 a;
+    for (int k = 0; k < 9; k++) a.a[k] = R[k];
+    const M3 r = mul(a, so3_exp(v3(d3[0], d3[1], d3[2])));
+    for (int k = 0; k < 9; k++) R[k] = r.a[k];
+}
+// g <- Exp(Bx(g) d) g (ieskf.cpp:20)
+__device__ __noinline__ void plus_g_piece(double* g, const double* d2) {
+    const V3 gv = v3(g[0], g[1], g[2]);
+    Mat<2, 1> dg; dg[0] = d2[0]; dg[1] = d2[1];
+    const V3 r = mul(so3_exp(mul(st_Bx(gv), dg)), gv);
+    g[0] = r[0]; g[1] = r[1]; g[2] = r[2];
+}
+// entry (i, j) of a block-diagonal 23x23 matrix given by its three blocks (identity elsewhere):
+// blk[0..8] rows 3-5, blk[9..17] rows 6-8, blk[18..21] rows 21-22
 __device__ __forceinline__ double bd_at(const double* blk, int i, int j) {
     if (i >= 3 && i < 6 && j >= 3 && j < 6) return blk[(i - 3) * 3 + (j - 3)];
     if (i >= 6 && i < 9 && j >= 6 && j < 9) return blk[9 + (i - 6) * 3 + (j - 6)];
     if (i >= 21 && j >= 21) return blk[18 + (i - 21) * 2 + (j - 21)];
     return i == j ? 1.0 : 0.0;
+}
+// column range of the non-zeros of row i of such a matrix
+__device__ __forceinline__ void bd_range(int i, int& lo, int& hi) {
+    lo = i < 3 ? i : i < 6 ? 3 : i < 9 ? 6 : i < 21 ? i : 21;
+    hi = i < 3 ? i + 1 : i < 6 ? 6 : i < 9 ? 9 : i < 21 ? i + 1 : 23;
+}
+// time stamp that cannot be issued before the preceding barrier has really released the warp
+__device__ __forceinline__ long long stamp(const volatile int* flag) {
+    long long t = 0;
+    if (*flag == 0) t = clock64();
+    return t;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // G = T^-1 for a small D x D matrix in shared memory (LU with partial pivoting + substitution), by one warp:
@@ -99,135 +137,168 @@ __device__ void warp_small_inverse(double* T, double* G, int* perm) {
     __syncwarp();
 }
 
-// kept as a no-op stage id for the profiler; P^-1 is not needed any more
-__global__ void k_update_begin(DevFilter* f, DevCtl* ctl) { (void)f; (void)ctl; }
-void launch_update_begin(cudaStream_t st, DevFilter* f, DevCtl* ctl) { (void)st; (void)f; (void)ctl; }
-
-constexpr int RED_CHUNKS = 2;
-
-// Phases: (A) all warps: partial sums of the measurement blocks + P load | manifold warp: boxminus, J, A = J^-1
-//         (B) manifold warp alone, warp-synchronous: every D x D quantity, Q, delta_x, boxplus, convergence, L A
-//         (C) only on the last executed iteration, all warps: P = (L A)(P - Q P_D)(L A)^T
-// Runs inside k_measure's LAST-arriving CTA (vmp_iekf.cu): THREADS = that kernel's CTA size.
+// The solver CTA of k_measure (block 0 of a launch with solve = 1, vmp_iekf.cu): THREADS = that kernel's CTA size (>= 128).
+//   (A) while the other CTAs measure: x, x_pred, P -> shared; boxminus, J, A = J^-1 (three warps, one manifold piece each)
+//   (W) wait for the nblocks measurement CTAs (ctl->ticket), then reduce their partial sums in a fixed order
+//   (B) the D x D algebra, delta_x, boxplus, convergence
+//   (C) only on the last executed iteration: P = (L A)(P - Q P_D)(L A)^T
 template <bool EXT, int THREADS>
-__device__ void ieskf_solve_block(DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
-    constexpr int SOLVE_THREADS = THREADS;
-    constexpr int W_MAN = THREADS / 32 - 1;        // the warp that runs the manifold operations
-    constexpr int N_WORK = 32 * W_MAN;             // threads of the other warps
+__device__ void ieskf_solve_cta(DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
+    static_assert(THREADS >= 128, "the manifold pieces use four warps");
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;
-    __shared__ double sP[NE], sPn[NE], sT1[NE];
-    __shared__ double sHm[NV], sRed[RED_CHUNKS][NV];
-    __shared__ double sM[D * D], sS[D * D], sTm[D * D], sG[D * D], sW[D * D], sMA[D * D];
+    __shared__ double sP[NE], sPn[NE], sT1[NE], sA[NE], sB[NE];
+    constexpr int NVP = (NV + 31) / 32 * 32;           // values padded to whole warps
+    constexpr int RP = EXT ? 4 : 8;                   // block subsets of the partial-sum reduction
+    __shared__ double sHm[NV], sRed[RP][NVP];
+    __shared__ double sMA[D * D], sS[D * D], sTm[D * D], sG[D * D], sW[D * D];
     __shared__ double sQ[NS * D], smm[D], sPm[D], sv[NS];
     __shared__ double sdelta[NS], sdx[NS], sx[36], sxp[36], sJb[22], sAb[22], sLb[22], sBb[22];
-    __shared__ int sperm[D], s_last;
+    __shared__ int sperm[D], s_last, s_zero;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int it = ctl->iter;
-    const long long tk0 = clock64();
-    long long tk1 = 0, tk2 = 0, tk3 = 0;
+    const long long t0 = clock64();
 
     // ---- (A)
-    if (wid == W_MAN) {
-        for (int q = lane; q < 36; q += 32) { sx[q] = f->x[q]; sxp[q] = f->xpred[q]; }
-        __syncwarp();
-        if (lane == 0) { const St x = st_load(sx), xp = st_load(sxp); st_boxminus(x, xp, sdelta); }
-        __syncwarp();
-        if (lane < 3) { jac_blocks(sJb, sdelta, sx + 33, sxp + 33, lane); inv_blocks(sJb, sAb, lane); }
-    } else {
-        for (int q = tid; q < NV * RED_CHUNKS; q += N_WORK) {
-            const int v = q % NV, c = q / NV;
-            const int b0 = (int)((long long)nblocks * c / RED_CHUNKS), b1 = (int)((long long)nblocks * (c + 1) / RED_CHUNKS);
-            double t = 0.0;
-#pragma unroll 8
-            for (int b = b0; b < b1; b++) t += __ldcg(&partials[(size_t)b * PARTIAL_STRIDE + v]);
-            sRed[c][v] = t;
-        }
-        for (int q = tid; q < NE; q += N_WORK) sP[q] = f->P[q];
+    for (int q = tid; q < 36; q += THREADS) { sx[q] = f->x[q]; sxp[q] = f->xpred[q]; }
+    for (int q = tid; q < NE; q += THREADS) sP[q] = f->P[q];
+    if (tid == 0) s_zero = 0;
+    __syncthreads();
+    if (lane == 0) {
+        if (wid == 0) man_rot_piece(sx + 3, sxp + 3, sdelta + 3, sJb, sAb);
+        else if (wid == 1) man_rot_piece(sx + 12, sxp + 12, sdelta + 6, sJb + 9, sAb + 9);
+        else if (wid == 2) man_g_piece(sx + 33, sxp + 33, sdelta + 21, sJb + 18, sAb + 18);
+    }
+    if (wid == 3 && lane < 15) {                    // the vector-space coordinates (ieskf.cpp:39-53)
+        const int g = lane / 3, c = lane % 3;
+        const int dst = g == 0 ? c : 9 + (g - 1) * 3 + c, src = g == 0 ? c : 21 + (g - 1) * 3 + c;
+        sdelta[dst] = sx[src] - sxp[src];
     }
     __syncthreads();
-    tk1 = clock64();
-    // ---- (B) one warp, no block barriers
-    if (wid == W_MAN) {
-        for (int v = lane; v < NV; v += 32) {
-            double t = sRed[0][v];
+    for (int q = tid; q < NE; q += THREADS) sA[q] = bd_at(sAb, q / NS, q % NS);
+    const long long tA = stamp(&s_zero);
+
+    // ---- (W)
+    if (tid == 0) {
+        while (ld_acquire_u32(&ctl->ticket) < (unsigned)nblocks) __nanosleep(40);
+        ctl->ticket = 0;
+    }
+    __syncthreads();
+    const long long tW = stamp(&s_zero);
+    // fixed-order reduction of the per-CTA partial sums: RP interleaved block subsets per value, all loads independent
+    for (int q = tid; q < NVP * RP; q += THREADS) {
+        const int v = q % NVP, part = q / NVP;
+        double t0s = 0.0, t1s = 0.0;
+        if (v < NV) {
+            int b = part;
+            for (; b + RP < nblocks; b += 2 * RP) {
+                t0s += __ldcg(&partials[(size_t)b * PARTIAL_STRIDE + v]);
+                t1s += __ldcg(&partials[(size_t)(b + RP) * PARTIAL_STRIDE + v]);
+            }
+            if (b < nblocks) t0s += __ldcg(&partials[(size_t)b * PARTIAL_STRIDE + v]);
+        }
+        sRed[part][v] = t0s + t1s;
+    }
+    __syncthreads();
+    for (int v = tid; v < NV; v += THREADS) {
+        double t = sRed[0][v];
 #pragma unroll
-            for (int c = 1; c < RED_CHUNKS; c++) t += sRed[c][v];
-            sHm[v] = t;
-        }
-        __syncwarp();
-        for (int q = lane; q < D * D; q += 32) {             // M (symmetric, from the upper triangle)
-            const int i = q / D, j = q % D, a = i < j ? i : j, c = i < j ? j : i;
-            sM[q] = sHm[a * D - a * (a - 1) / 2 + (c - a)];
-        }
-        __syncwarp();
-        for (int q = lane; q < D * D; q += 32) {             // MA = M A_D
+        for (int c = 1; c < RP; c++) t += sRed[c][v];
+        sHm[v] = t;
+    }
+    __syncthreads();
+
+    // ---- (B)
+    for (int q = tid; q < D * D + D; q += THREADS) {
+        if (q < D * D) {                                    // MA = M A_D (M symmetric, from its upper triangle)
             const int i = q / D, j = q % D;
             double s2 = 0.0;
-            for (int k = 0; k < D; k++) s2 += sM[i * D + k] * bd_at(sAb, k, j);
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const int a = i < k ? i : k, c = i < k ? k : i;
+                s2 += sHm[a * D - a * (a - 1) / 2 + (c - a)] * sA[k * NS + j];
+            }
             sMA[q] = s2;
-        }
-        if (lane < D) {                                      // mm = A_D^T m
+        } else {                                            // mm = A_D^T m
+            const int l = q - D * D;
             double s2 = 0.0;
-            for (int k = 0; k < D; k++) s2 += bd_at(sAb, k, lane) * sHm[NH + k];
-            smm[lane] = s2;
+#pragma unroll
+            for (int k = 0; k < D; k++) s2 += sA[k * NS + l] * sHm[NH + k];
+            smm[l] = s2;
         }
-        __syncwarp();
-        for (int q = lane; q < D * D; q += 32) {             // S = A_D^T (M A_D)
+    }
+    __syncthreads();
+    for (int q = tid; q < D * D + D; q += THREADS) {
+        if (q < D * D) {                                    // S = A_D^T (M A_D)
             const int i = q / D, j = q % D;
             double s2 = 0.0;
-            for (int k = 0; k < D; k++) s2 += bd_at(sAb, k, i) * sMA[k * D + j];
+#pragma unroll
+            for (int k = 0; k < D; k++) s2 += sA[k * NS + i] * sMA[k * D + j];
             sS[q] = s2;
-        }
-        if (lane < D) {                                      // Pm = P_DD mm
+        } else {                                            // Pm = P_DD mm
+            const int l = q - D * D;
             double s2 = 0.0;
-            for (int k = 0; k < D; k++) s2 += sP[lane * NS + k] * smm[k];
-            sPm[lane] = s2;
+#pragma unroll
+            for (int k = 0; k < D; k++) s2 += sP[l * NS + k] * smm[k];
+            sPm[l] = s2;
         }
-        __syncwarp();
-        for (int q = lane; q < D * D; q += 32) {             // T = I + P_DD S
-            const int i = q / D, j = q % D;
-            double s2 = (i == j) ? 1.0 : 0.0;
-            for (int k = 0; k < D; k++) s2 += sP[i * NS + k] * sS[k * D + j];
-            sTm[q] = s2;
-        }
-        __syncwarp();
-        warp_small_inverse<D>(sTm, sG, sperm);               // G = (I + P_DD S)^-1
-        for (int q = lane; q < D * D; q += 32) {             // W = S G
-            const int i = q / D, j = q % D;
-            double s2 = 0.0;
-            for (int k = 0; k < D; k++) s2 += sS[i * D + k] * sG[k * D + j];
-            sW[q] = s2;
-        }
-        __syncwarp();
-        for (int q = lane; q < NS * D; q += 32) {            // Q = P_{:,D} W   (23 x D)
-            const int i = q / D, j = q % D;
-            double s2 = 0.0;
-            for (int k = 0; k < D; k++) s2 += sP[i * NS + k] * sW[k * D + j];
-            sQ[q] = s2;
-        }
-        __syncwarp();
-        if (lane < NS) {                                     // y = (delta - Q delta_D) + (P_{:,D} mm - Q Pm)
-            double q1 = 0.0, q2 = 0.0, pm = 0.0;
-            for (int k = 0; k < D; k++) { q1 += sQ[lane * D + k] * sdelta[k]; q2 += sQ[lane * D + k] * sPm[k]; pm += sP[lane * NS + k] * smm[k]; }
-            sv[lane] = (sdelta[lane] - q1) + (pm - q2);
-        }
-        __syncwarp();
-        if (lane < NS) {                                     // delta_x = -A y
-            const int lo = lane < 3 ? lane : lane < 6 ? 3 : lane < 9 ? 6 : lane < 21 ? lane : 21;
-            const int hi = lane < 3 ? lane + 1 : lane < 6 ? 6 : lane < 9 ? 9 : lane < 21 ? lane + 1 : 23;
-            double s2 = 0.0;
-            for (int k = lo; k < hi; k++) s2 += bd_at(sAb, lane, k) * sv[k];
-            sdx[lane] = -s2;
-        }
-        __syncwarp();
-        // x_ += delta, counters, convergence on the signed maximum (Q5)
-        if (lane == 0) {
-            St x = st_load(sx);
-            st_boxplus(x, sdx);
-            st_store(x, sx);
-            st_store(x, f->x);
+    }
+    __syncthreads();
+    for (int q = tid; q < D * D; q += THREADS) {            // T = I + P_DD S
+        const int i = q / D, j = q % D;
+        double s2 = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s2 += sP[i * NS + k] * sS[k * D + j];
+        sTm[q] = s2;
+    }
+    __syncthreads();
+    if (wid == 0) warp_small_inverse<D>(sTm, sG, sperm);    // G = (I + P_DD S)^-1
+    __syncthreads();
+    for (int q = tid; q < D * D; q += THREADS) {            // W = S G
+        const int i = q / D, j = q % D;
+        double s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s2 += sS[i * D + k] * sG[k * D + j];
+        sW[q] = s2;
+    }
+    __syncthreads();
+    for (int q = tid; q < NS * D; q += THREADS) {           // Q = P_{:,D} W   (23 x D)
+        const int i = q / D, j = q % D;
+        double s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s2 += sP[i * NS + k] * sW[k * D + j];
+        sQ[q] = s2;
+    }
+    __syncthreads();
+    if (tid < NS) {                                         // y = (delta - Q delta_D) + (P_{:,D} mm - Q Pm)
+        double q1 = 0.0, q2 = 0.0, pm = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) { q1 += sQ[tid * D + k] * sdelta[k]; q2 += sQ[tid * D + k] * sPm[k]; pm += sP[tid * NS + k] * smm[k]; }
+        sv[tid] = (sdelta[tid] - q1) + (pm - q2);
+    }
+    __syncthreads();
+    if (tid < NS) {                                         // delta_x = -A y
+        int lo, hi;
+        bd_range(tid, lo, hi);
+        double s2 = 0.0;
+        for (int k = lo; k < hi; k++) s2 += sA[tid * NS + k] * sv[k];
+        sdx[tid] = -s2;
+    }
+    __syncthreads();
+    const long long tD = stamp(&s_zero);
+    // x_ += delta_x (ieskf.cpp:11-21), counters, convergence on the signed maximum (Q5)
+    if (lane == 0) {
+        if (wid == 0) plus_rot_piece(sx + 3, sdx + 3);
+        else if (wid == 1) plus_rot_piece(sx + 12, sdx + 6);
+        else if (wid == 2) plus_g_piece(sx + 33, sdx + 21);
+    }
+    if (wid == 3) {
+        if (lane < 15) {
+            const int g = lane / 3, c = lane % 3;
+            const int src = g == 0 ? c : 9 + (g - 1) * 3 + c, dst = g == 0 ? c : 21 + (g - 1) * 3 + c;
+            sx[dst] = sx[dst] + sdx[src];
+        } else if (lane == 15) {
             ctl->effect[it & 7] = (int)sHm[NH + D];
             const int nit = it + 1;
             ctl->iter = nit;
@@ -239,27 +310,32 @@ __device__ void ieskf_solve_block(DevFilter* f, DevCtl* ctl, const double* parti
             if (last) ctl->done = 1;
             s_last = last;
         }
-        __syncwarp();
-        // L blocks from the final delta and the updated state (ieskf.cpp:151-154), B = L A
-        if (s_last && lane < 3) jac_blocks(sLb, sdx, sx + 33, sxp + 33, lane);
-        __syncwarp();
-        if (s_last && lane < 22) {
-            if (lane < 18) {
-                const int w = lane / 9, e = lane % 9, i = e / 3, j = e % 3;
-                double s2 = 0.0;
-                for (int k = 0; k < 3; k++) s2 += sLb[w * 9 + i * 3 + k] * sAb[w * 9 + k * 3 + j];
-                sBb[lane] = s2;
-            } else {
-                const int e = lane - 18, i = e / 2, j = e % 2;
-                sBb[lane] = sLb[18 + i * 2] * sAb[18 + j] + sLb[18 + i * 2 + 1] * sAb[20 + j];
-            }
-        }
     }
     __syncthreads();
-    tk2 = clock64();
+    const long long tX = stamp(&s_zero);
+    if (tid < 36) f->x[tid] = sx[tid];
+    long long tC = tX;
     if (s_last) {
-        // ---- (C) P_ = B (P - Q P_{D,:}) B^T with B = L A block diagonal
-        for (int q = tid; q < NE; q += SOLVE_THREADS) {
+        // ---- (C) L blocks from the final delta_x and the updated state (ieskf.cpp:151-154), B = L A,
+        //          P_ = B (P - Q P_{D,:}) B^T
+        if (lane == 0 && wid < 3) {
+            if (wid < 2) {
+                rot_jac(sdx + 3 + 3 * wid, sLb + 9 * wid);
+                for (int e = 0; e < 9; e++) {
+                    const int i = e / 3, j = e % 3;
+                    double s2 = 0.0;
+                    for (int k = 0; k < 3; k++) s2 += sLb[wid * 9 + i * 3 + k] * sAb[wid * 9 + k * 3 + j];
+                    sBb[wid * 9 + e] = s2;
+                }
+            } else {
+                g_jac(sx + 33, sxp + 33, sdx + 21, sLb + 18);
+                for (int e = 0; e < 4; e++) {
+                    const int i = e / 2, j = e % 2;
+                    sBb[18 + e] = sLb[18 + i * 2] * sAb[18 + j] + sLb[18 + i * 2 + 1] * sAb[20 + j];
+                }
+            }
+        }
+        for (int q = tid; q < NE; q += THREADS) {            // Pn = P - Q P_{D,:}
             const int i = q / NS, j = q % NS;
             double s2 = 0.0;
 #pragma unroll
@@ -267,27 +343,29 @@ __device__ void ieskf_solve_block(DevFilter* f, DevCtl* ctl, const double* parti
             sPn[q] = sP[q] - s2;
         }
         __syncthreads();
-        for (int q = tid; q < NE; q += SOLVE_THREADS) {      // T1 = B Pn
+        for (int q = tid; q < NE; q += THREADS) sB[q] = bd_at(sBb, q / NS, q % NS);
+        __syncthreads();
+        for (int q = tid; q < NE; q += THREADS) {            // T1 = B Pn
             const int i = q / NS, j = q % NS;
-            const int lo = i < 3 ? i : i < 6 ? 3 : i < 9 ? 6 : i < 21 ? i : 21;
-            const int hi = i < 3 ? i + 1 : i < 6 ? 6 : i < 9 ? 9 : i < 21 ? i + 1 : 23;
+            int lo, hi;
+            bd_range(i, lo, hi);
             double s2 = 0.0;
-            for (int k = lo; k < hi; k++) s2 += bd_at(sBb, i, k) * sPn[k * NS + j];
+            for (int k = lo; k < hi; k++) s2 += sB[i * NS + k] * sPn[k * NS + j];
             sT1[q] = s2;
         }
         __syncthreads();
-        for (int q = tid; q < NE; q += SOLVE_THREADS) {      // P = T1 B^T
+        for (int q = tid; q < NE; q += THREADS) {            // P = T1 B^T
             const int i = q / NS, j = q % NS;
-            const int lo = j < 3 ? j : j < 6 ? 3 : j < 9 ? 6 : j < 21 ? j : 21;
-            const int hi = j < 3 ? j + 1 : j < 6 ? 6 : j < 9 ? 9 : j < 21 ? j + 1 : 23;
+            int lo, hi;
+            bd_range(j, lo, hi);
             double s2 = 0.0;
-            for (int k = lo; k < hi; k++) s2 += sT1[i * NS + k] * bd_at(sBb, j, k);
+            for (int k = lo; k < hi; k++) s2 += sT1[i * NS + k] * sB[j * NS + k];
             f->P[q] = s2;
         }
+        tC = clock64();
     }
-    tk3 = clock64();
-    if (tid == 0 && it == 0) {      // phase cycles of the first iteration (debug counters): A, B, C
-        ctl->dbg[3] = (int)(tk1 - tk0); ctl->dbg[4] = (int)(tk2 - tk1); ctl->dbg[5] = (int)(tk3 - tk2); ctl->dbg[6] = 0; ctl->dbg[7] = 0;
+    if (tid == 0) {      // phase cycles (debug counters): first iteration, and the posterior of the last one
+        if (it == ctl->dbg_it) { ctl->dbg[3] = (int)(tA - t0); ctl->dbg[4] = (int)(tW - tA); ctl->dbg[5] = (int)(tD - tW); ctl->dbg[6] = (int)(tX - tD); }
+        if (s_last) ctl->dbg[7] = (int)(tC - tX);
     }
 }
-

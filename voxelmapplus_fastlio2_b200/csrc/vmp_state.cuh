@@ -63,6 +63,23 @@ VMP_HD void st_boxplus(St& s, const double* d) {
     s.g = mul(so3_exp(mul(st_Bx(s.g), dg)), s.g);
 }
 
+// S2 part of State::operator-  ieskf.cpp:55-65   (ag = gravity of the left operand, bg = of the right operand)
+VMP_HD void st_boxminus_g(const V3& ag, const V3& bg, double* out2) {
+    const double v_sin = norm(mul(hat(ag), bg));
+    const double v_cos = dot(ag, bg);
+    const double theta = atan2(v_sin, v_cos);
+    Mat<2, 1> res;
+    if (v_sin < 1e-11) {
+        if (fabs(theta) > 1e-11) { res[0] = 3.1415926; res[1] = 0.0; }
+        else { res[0] = 0.0; res[1] = 0.0; }
+    } else {
+        const Mat<2, 3> p = scale(tr(st_Bx(bg)), theta / v_sin);
+        const Mat<2, 3> q = mul(p, hat(bg));
+        res = mul(q, ag);
+    }
+    out2[0] = res[0]; out2[1] = res[1];
+}
+
 // State::operator-  ieskf.cpp:35-67   (delta = a [-] b, 23 entries)
 VMP_HD void st_boxminus(const St& a, const St& b, double* delta) {
     V3 t;
@@ -73,19 +90,7 @@ VMP_HD void st_boxminus(const St& a, const St& b, double* delta) {
     t = sub(a.vel, b.vel);                         delta[12] = t[0]; delta[13] = t[1]; delta[14] = t[2];
     t = sub(a.bg, b.bg);                           delta[15] = t[0]; delta[16] = t[1]; delta[17] = t[2];
     t = sub(a.ba, b.ba);                           delta[18] = t[0]; delta[19] = t[1]; delta[20] = t[2];
-    const double v_sin = norm(mul(hat(a.g), b.g));
-    const double v_cos = dot(a.g, b.g);
-    const double theta = atan2(v_sin, v_cos);
-    Mat<2, 1> res;
-    if (v_sin < 1e-11) {
-        if (fabs(theta) > 1e-11) { res[0] = 3.1415926; res[1] = 0.0; }
-        else { res[0] = 0.0; res[1] = 0.0; }
-    } else {
-        const Mat<2, 3> p = scale(tr(st_Bx(b.g)), theta / v_sin);
-        const Mat<2, 3> q = mul(p, hat(b.g));
-        res = mul(q, a.g);
-    }
-    delta[21] = res[0]; delta[22] = res[1];
+    st_boxminus_g(a.g, b.g, delta + 21);
 }
 
 }  // namespace vmp
