@@ -45,18 +45,24 @@ def assert_maps_equal(a, b, exact=True, rtol=1e-9, what=""):
                                      f"flags {a['flags'][bad]} n {a['n'][bad]}")
         else:
             # Q15: world points are float32.  A posterior that differs from the oracle's in the 9th digit flips the
-            # float32 rounding of a few coordinates by one ulp (2.4e-7 at 4 m).  Voxels that hold such a point differ
-            # in the 7th digit, all others agree to rtol: at most 0.5 % of the voxels may be of the first kind, and
-            # those must still agree to 1e-3 relative (or 100 float32 ulps of the field's typical magnitude).
+            # float32 rounding of some coordinates by one ulp (2.4e-7 at 4 m; at 200 000 points per scan that is
+            # every 7th voxel), so free-running maps are compared statistically; the bit-exact statement is made by
+            # the tests that feed both sides the same world points.
             x, y = a[f].reshape(len(a), -1), b[f].reshape(len(b), -1)
             if len(x) == 0:
                 continue
+            eps32 = float(np.finfo(np.float32).eps)
             fin = np.where(np.isfinite(y), np.abs(y), 0.0).max(axis=1)
-            scale = float(np.median(fin))                  # typical magnitude of the field (inf / NaN of degenerate voxels aside)
-            tight = np.all(np.isclose(x, y, rtol=rtol, atol=1e-12, equal_nan=True), axis=1)
-            loose = np.all(np.isclose(x, y, rtol=1e-3, atol=100 * float(np.finfo(np.float32).eps) * scale, equal_nan=True), axis=1)
-            assert loose.all(), f"{what}: field {f} differs beyond float32-rounding effects at keys {a['key'][~loose][:5].tolist()}"
-            assert (~tight).sum() <= max(3, 0.005 * len(x)), f"{what}: field {f}: {(~tight).sum()} of {len(x)} voxels differ beyond rtol {rtol}"
+            if f in ("mean", "ppt", "center"):
+                # moments: every voxel within rtol, or 4 float32 ulps of the field's largest magnitude
+                ok = np.all(np.isclose(x, y, rtol=rtol, atol=4 * eps32 * float(fin.max()), equal_nan=True), axis=1)
+                assert ok.all(), f"{what}: field {f} differs beyond float32-rounding effects at keys {a['key'][~ok][:5].tolist()}"
+            else:
+                # normals / covariances go through an eigen-decomposition whose conditioning is the eigenvalue gap:
+                # 99 % of the voxels within 1e-4 of the voxel's own largest entry
+                vmax = np.maximum(fin, 1e-300)[:, None]
+                ok = np.all(np.isclose(x / vmax, y / vmax, rtol=0, atol=1e-4, equal_nan=True), axis=1)
+                assert (~ok).sum() <= 0.01 * len(x), f"{what}: field {f}: {(~ok).sum()} of {len(x)} voxels differ by more than 1e-4 relative"
 
 
 def plane_cloud(rng, n, origin, u, v, extent, noise):
