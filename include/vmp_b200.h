@@ -164,6 +164,16 @@ int vmp_scan(vmp_handle h, vmp_state* x_inout, double* P_inout,
  * previous call.  The posterior stays on the device (read it with vmp_get_state).  Used
  * for the "inputs resident in HBM" throughput figure. */
 int vmp_scan_dev(vmp_handle h, const float* pts_lidar_dev, const double* prior_dev, int n, vmp_scan_stats* stats);
+
+/* Pipelined mode (off by default).  The reference publishes the pose of a scan and then updates the map
+ * (lio_builder.cpp:224-246 is one synchronous block only because it is single-threaded).  With pipelining on,
+ * vmp_scan / vmp_scan_dev return as soon as the IEKF posterior of the scan is out; the map update of that scan keeps
+ * running on the device while the caller prepares the next scan (IMU propagation, undistortion).  Results are
+ * identical; what changes is when they are reported: stats->map and stats->gpu_ms describe the PREVIOUS scan, and a
+ * capacity error raised by a map update is returned by the next call on the handle.  Every other entry point (and
+ * vmp_sync) first waits for the pending map update. */
+int vmp_set_pipelined(vmp_handle h, int on);
+int vmp_sync(vmp_handle h);
 int vmp_set_state(vmp_handle h, const vmp_state* x, const double* P);
 int vmp_get_state(vmp_handle h, vmp_state* x, double* P);
 

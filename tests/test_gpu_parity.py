@@ -244,3 +244,42 @@ def test_lio_trajectory(oracle_mod):
     assert worst_p < 1e-3, f"trajectory deviates {worst_p} m"
     assert worst_r < 1e-2, f"attitude deviates {worst_r} deg"
     assert_maps_equal(o.dump_map(), b.map.dump_map(), exact=False, rtol=1e-6, what="free-running map")
+
+
+def test_pipelined_mode_is_identical():
+    """vmp_set_pipelined: the same posteriors and the same map bit for bit; map counters arrive one scan late."""
+    cfg = default_config(max_points_per_scan=8192)
+    a = LIOBuilder(cfg)
+    b = LIOBuilder(cfg, pipelined=True)
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=6000))
+    prev = None
+    for pk in seq.packages(40):
+        sa = a.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        sb = b.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        xa, Pa, s1 = a.state()
+        xb, Pb, s2 = b.state()
+        assert s1 == s2 and bytes(xa) == bytes(xb) and np.array_equal(Pa, Pb)
+        assert sa.iters == sb.iters and list(sa.effect_num) == list(sb.effect_num)
+        if sa.iters:
+            if prev is not None and prev.iters:
+                assert sb.map.as_dict() == prev.map.as_dict()      # lagging by exactly one scan
+            prev = sa
+    b.map.sync()
+    assert_maps_equal(a.map.dump_map(), b.map.dump_map(), exact=True, what="pipelined map")
+
+
+def test_pipelined_reports_capacity_error_late():
+    """a map update that exhausts the capacity while pipelined surfaces on the next call on the handle"""
+    cfg = default_config(max_points_per_scan=4096, map_capacity=64)
+    g = HotPath(cfg)
+    rng = np.random.default_rng(5)
+    from voxelmapplus_fastlio2_b200.ctypes_defs import VmpState
+    x = VmpState(); x.rot[0] = x.rot[4] = x.rot[8] = 1.0; x.rot_ext[0] = x.rot_ext[4] = x.rot_ext[8] = 1.0; x.g[2] = -9.81
+    P = np.eye(23) * 1e-4
+    pts = rng.uniform(-4, 4, (32, 3)).astype(np.float32)
+    g.first_scan(x, P, pts)
+    g.set_pipelined(True)
+    big = rng.uniform(-30, 30, (4000, 3)).astype(np.float32)          # touches far more than 64 voxels in one scan
+    g.scan(x, P, big)                                                 # posterior delivered, the update fails behind it
+    with pytest.raises(VmpError):
+        g.sync()

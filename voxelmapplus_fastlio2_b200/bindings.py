@@ -218,6 +218,15 @@ class HotPath:
                                            C.c_void_p(prior_dev_ptr) if prior_dev_ptr else None, n, C.byref(st)))
         return st
 
+    def set_pipelined(self, on: bool = True):
+        """vmp_set_pipelined: scan() returns with the posterior while the map update of that scan is still running."""
+        self._lib.vmp_set_pipelined.argtypes = [C.c_void_p, C.c_int]
+        self._check(self._lib.vmp_set_pipelined(self._h, 1 if on else 0))
+
+    def sync(self):
+        self._lib.vmp_sync.argtypes = [C.c_void_p]
+        self._check(self._lib.vmp_sync(self._h))
+
     def launch_count(self) -> int:
         return int(self._lib.vmp_launch_count(self._h))
 

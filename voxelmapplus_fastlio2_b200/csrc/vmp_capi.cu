@@ -31,38 +31,6 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-// header uploaded per scan / result downloaded per scan (pinned on the host side)
-struct ScanIn { int n; int has_state; double x[36]; double P[529]; };
-struct ScanOut {
-    double x[36]; double P[529];
-    int iter, converged, effect[8], err, need_maint;      // need_maint: bit0 rehash, bit1 LRU-log compaction
-    int dbg[8];
-    DevStats st;
-};
-
-// stage the prior; start of IESKF::update (ieskf.cpp:127-130): predict_x = x_, iteration counters
-__global__ void k_scan_in(const ScanIn* in, DevFilter* f, DevCtl* ctl) {
-    const int tid = threadIdx.x;
-    if (tid == 0) { ctl->n = in->n; ctl->iter = 0; ctl->done = 0; ctl->converged = 0; }
-    if (tid < 8) ctl->effect[tid] = 0;
-    if (in->has_state) {
-        for (int q = tid; q < 529; q += blockDim.x) f->P[q] = in->P[q];
-        if (tid < 36) { const double v = in->x[tid]; f->x[tid] = v; f->xpred[tid] = v; }
-    } else if (tid < 36) {
-        f->xpred[tid] = f->x[tid];
-    }
-}
-__global__ void k_scan_out(const DevFilter* f, const DevCtl* ctl, ScanOut* out) {
-    const int tid = threadIdx.x;
-    for (int q = tid; q < 529; q += blockDim.x) out->P[q] = f->P[q];
-    if (tid < 36) out->x[tid] = f->x[tid];
-    if (tid < 8) out->effect[tid] = ctl->effect[tid];
-    if (tid == 0) {
-        out->iter = ctl->iter; out->converged = ctl->converged; out->err = ctl->err; out->st = ctl->st;
-        for (int q = 0; q < 8; q++) out->dbg[q] = ctl->dbg[q];
-        out->need_maint = (ctl->need_rehash ? 1 : 0) | (ctl->need_log_compact ? 2 : 0);
-    }
-}
 // H (12x12) / b (12) / effect of one measurement pass from the block partials (vmp_measure)
 __global__ void k_reduce_partials(const double* partials, int nblocks, int ext, double* out /*144+12+1*/) {
     const int D = ext ? 12 : 6;
@@ -91,11 +59,13 @@ __global__ void k_reset_iter(DevCtl* ctl) { ctl->iter = 0; ctl->done = 0; ctl->c
 
 using namespace vmp;
 
+constexpr size_t IN_HDR = 4608;          // ScanIn rounded up; the points follow at this offset
+static_assert(sizeof(ScanIn) <= IN_HDR, "ScanIn outgrew its slot");
+
 struct vmp_handle_t {
     vmp_config cfg;
     int device = 0, sm_count = 148;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream = nullptr;
     cudaGraphExec_t graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevMap m{};
@@ -104,9 +74,19 @@ struct vmp_handle_t {
     DevCtl* ctl = nullptr;
     double* partials = nullptr;
     double* meas_out = nullptr;          // 157 doubles
-    ScanIn* d_in = nullptr;  ScanIn* h_in = nullptr;
-    ScanOut* d_out = nullptr; ScanOut* h_out = nullptr;
-    float* h_raw = nullptr;              // pinned staging for the scan
+    // mailboxes in pinned, mapped host memory (h_*) and their device aliases (a_*): the kernels read the scan and write
+    // the results directly, one scan is one graph launch
+    // scan upload: [ScanIn header | points] contiguous in pinned memory, ONE DMA copy into the same layout on the device
+    unsigned char* h_stage = nullptr; unsigned char* d_stage = nullptr;
+    ScanIn* h_in = nullptr;     ScanIn* d_in = nullptr;
+    StateOut* h_sout = nullptr; StateOut* a_sout = nullptr;
+    MapOut* h_mout = nullptr;   MapOut* a_mout = nullptr;
+    float* h_raw = nullptr;              // = h_stage + IN_HDR
+    unsigned long long seq = 0;
+    bool pipelined = false;              // vmp_set_pipelined: vmp_scan returns when the posterior is out, the map update runs on
+    bool map_pending = false;            // a map update whose MapOut has not been consumed yet
+    cudaEvent_t pe0[2] = {nullptr, nullptr}, pe1[2] = {nullptr, nullptr};
+    vmp_update_stats lag_map{};          // pipelined mode: counters of the previous scan's map update
     double* d_up = nullptr;              // staging for vmp_map_update uploads (reuses s.pw / s.pcov)
     std::vector<void*> allocs;
     int grid_pts = 148, grid_meas = 148;
@@ -171,14 +151,12 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk) {
     cudaStream_t st = h->stream;
     const bool ext = h->cfg.estimate_ext != 0;
     int k = 0;
-    k_scan_in<<<1, 256, 0, st>>>(h->d_in, h->f, h->ctl); k++; mark(mk, VMP_K_SCAN_IN);
-    launch_set_scan(st, h->grid_pts, h->s, h->ctl); k++; mark(mk, VMP_K_SET_SCAN);
+    launch_set_scan(st, h->grid_pts, h->s, h->d_in, h->f, h->ctl); k++; mark(mk, VMP_K_SET_SCAN);
     for (int it = 0; it < h->cfg.opti_max_iter; it++) {
-        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1); k++; mark(mk, VMP_K_MEASURE);
+        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1, h->a_sout); k++; mark(mk, VMP_K_MEASURE);
     }
     launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++; mark(mk, VMP_K_WORLD_POINTS);
-    k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false, mk);
-    k_scan_out<<<1, 256, 0, st>>>(h->f, h->ctl, h->d_out); k++; mark(mk, VMP_K_SCAN_OUT);
+    k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false, true, h->a_mout, mk);
     return k;
 }
 
@@ -219,25 +197,50 @@ int build_graph(vmp_handle_t* h) {
     return VMP_OK;
 }
 
-int finish_scan(vmp_handle_t* h, vmp_state* x, double* P, vmp_scan_stats* stats) {
-    VMP_CUDA_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
-    VMP_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
-    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    prof_collect(h);
-    const ScanOut& o = *h->h_out;
-    if (o.need_maint) h->launches += launch_map_maintenance(h->stream, h->m, h->ctl, h->sm_count, o.need_maint);   // rare; runs before the next scan
+// consume the MapOut mailbox of the last map update (the stream has passed it): maintenance, error bits
+int finish_map(vmp_handle_t* h) {
+    const MapOut& o = *h->h_mout;
+    h->map_pending = false;
+    if (o.need_maint) h->launches += launch_map_maintenance(h->stream, h->m, h->ctl, h->sm_count, o.need_maint);   // rare; runs before the next update
+    return check_device_err(h, o.err);
+}
+void read_state(vmp_handle_t* h, vmp_state* x, double* P, vmp_scan_stats* stats) {
+    const StateOut& o = *h->h_sout;
     if (x) std::memcpy(x, o.x, sizeof(double) * 36);
     if (P) std::memcpy(P, o.P, sizeof(double) * 529);
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->iters = o.iter; stats->converged = o.converged;
         for (int i = 0; i < 8; i++) stats->effect_num[i] = o.effect[i];
-        fill_update_stats(o.st, &stats->map);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-        stats->gpu_ms = ms;
     }
-    return check_device_err(h, o.err);
+}
+// everything enqueued so far has finished when this returns
+int finish_sync(vmp_handle_t* h) {
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    prof_collect(h);
+    return finish_map(h);
+}
+// pipelined mode: wait for the posterior of scan `seq` only (the mailbox is written by the solver CTA)
+int wait_state(vmp_handle_t* h, unsigned long long seq) {
+    const unsigned long long* p = &h->h_sout->seq;
+    for (unsigned long spins = 1;; spins++) {
+        if (__atomic_load_n(p, __ATOMIC_ACQUIRE) == seq) return VMP_OK;
+        if ((spins & 0x3FFF) == 0) {
+            const cudaError_t e = cudaStreamQuery(h->stream);
+            if (e == cudaSuccess) {
+                if (__atomic_load_n(p, __ATOMIC_ACQUIRE) == seq) return VMP_OK;
+                set_error("scan %llu finished without a posterior", seq);
+                return VMP_ERR_CUDA;
+            }
+            if (e != cudaErrorNotReady) { set_error("CUDA error while waiting for the posterior: %s", cudaGetErrorString(e)); return VMP_ERR_CUDA; }
+        }
+        __builtin_ia32_pause();
+    }
+}
+// before any call that looks at device state: let a pipelined map update finish and consume its mailbox
+int drain(vmp_handle_t* h) {
+    if (!h->map_pending) return VMP_OK;
+    return finish_sync(h);
 }
 
 template <typename T>
@@ -298,9 +301,6 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     h->sm_count = prop.multiProcessorCount;
     *out = h;       // so that a failed create can still be destroyed by the caller
     VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    VMP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    VMP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev0));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev1));
 
@@ -343,7 +343,10 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     DALLOC(s.pl, (size_t)3 * nmax); DALLOC(s.cl, (size_t)9 * nmax);
     DALLOC(s.rnorm, (size_t)3 * nmax); DALLOC(s.rmean, (size_t)3 * nmax); DALLOC(s.rres, nmax);
     DALLOC(s.rvalid, nmax); DALLOC(s.rstatus, nmax); DALLOC(s.rkey, nmax);
-    DALLOC(s.pw, (size_t)3 * nmax); DALLOC(s.pcov, (size_t)9 * nmax); DALLOC(s.raw, (size_t)3 * nmax);
+    DALLOC(s.pw, (size_t)3 * nmax); DALLOC(s.pcov, (size_t)9 * nmax);
+    DALLOC(h->d_stage, IN_HDR + sizeof(float) * 3 * (size_t)nmax + 64);
+    h->d_in = (ScanIn*)h->d_stage;
+    s.raw = (float*)(h->d_stage + IN_HDR);
     s.range_var = cfg->ranging_cov * cfg->ranging_cov;
     const double sn = sin(cfg->angle_cov * 0.017453293);      // PCL's DEG2RAD (commons.cpp:27-28)
     s.sn2 = sn * sn;
@@ -363,11 +366,17 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     h->grid_meas = std::max(1, std::min(h->sm_count * 2, (nmax + 255) / 256));
     DALLOC(h->partials, (size_t)h->grid_meas * PARTIAL_STRIDE);
     DALLOC(h->meas_out, 160);
-    DALLOC(h->d_in, 1); DALLOC(h->d_out, 1);
-    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_in, sizeof(ScanIn)));
-    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_out, sizeof(ScanOut)));
-    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_raw, sizeof(float) * 3 * nmax));
+    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_stage, IN_HDR + sizeof(float) * 3 * (size_t)nmax + 64));
+    h->h_in = (ScanIn*)h->h_stage;
+    h->h_raw = (float*)(h->h_stage + IN_HDR);
+    VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_sout, sizeof(StateOut), cudaHostAllocMapped));
+    VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_mout, sizeof(MapOut), cudaHostAllocMapped));
+    VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_sout, h->h_sout, 0));
+    VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_mout, h->h_mout, 0));
     std::memset(h->h_in, 0, sizeof(ScanIn));
+    std::memset(h->h_sout, 0, sizeof(StateOut));
+    std::memset(h->h_mout, 0, sizeof(MapOut));
+    for (int b = 0; b < 2; b++) { VMP_CUDA_CHECK(cudaEventCreate(&h->pe0[b])); VMP_CUDA_CHECK(cudaEventCreate(&h->pe1[b])); }
 
     launch_map_init(h->stream, m, h->ctl);
     h->launches += 1;
@@ -391,21 +400,19 @@ int vmp_destroy(vmp_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->graph) cudaGraphExecDestroy(h->graph);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->h_in) cudaFreeHost(h->h_in);
-    if (h->h_out) cudaFreeHost(h->h_out);
-    if (h->h_raw) cudaFreeHost(h->h_raw);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_sout) cudaFreeHost(h->h_sout);
+    if (h->h_mout) cudaFreeHost(h->h_mout);
+    for (int b = 0; b < 2; b++) { if (h->pe0[b]) cudaEventDestroy(h->pe0[b]); if (h->pe1[b]) cudaEventDestroy(h->pe1[b]); }
     for (auto& e : h->pev) if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VMP_OK;
 }
 
-static int check_n(vmp_handle h, int n, const char* who) {
+static int check_args(vmp_handle h, int n, const char* who) {
     if (!h) { set_error("%s: null handle", who); return VMP_ERR_INVALID_ARG; }
     if (n < 0 || n > h->cfg.max_points_per_scan) {
         set_error("%s: n=%d outside [0, max_points_per_scan=%d]", who, n, h->cfg.max_points_per_scan);
@@ -413,6 +420,11 @@ static int check_n(vmp_handle h, int n, const char* who) {
     }
     cudaSetDevice(h->device);
     return VMP_OK;
+}
+// every entry point but the pipelined scan itself first lets a pending map update finish
+static int check_n(vmp_handle h, int n, const char* who) {
+    const int r = check_args(h, n, who);
+    return r ? r : drain(h);
 }
 
 static int upload_n(vmp_handle h, int n) {
@@ -437,15 +449,13 @@ static int map_update_common(vmp_handle h, const double* pts, const double* cov,
         Marker mk{prof_mark, h};
         h->pev_n = 0;
         VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream));
-        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, &mk);
+        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, &mk);
     } else {
-        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, nullptr);
+        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, nullptr);
     }
-    k_scan_out<<<1, 256, 0, h->stream>>>(h->f, h->ctl, h->d_out);
-    h->launches += 1;
     h->map_built = true;
-    r = finish_scan(h, nullptr, nullptr, nullptr);
-    fill_update_stats(h->h_out->st, st);
+    r = finish_sync(h);
+    fill_update_stats(h->h_mout->st, st);
     return r;
 }
 
@@ -477,10 +487,11 @@ int vmp_set_scan(vmp_handle h, const float* pts, int n) {
     int r = check_n(h, n, "vmp_set_scan");
     if (r) return r;
     if (n > 0 && !pts) { set_error("vmp_set_scan: null input"); return VMP_ERR_INVALID_ARG; }
-    r = upload_n(h, n);
-    if (r) return r;
-    if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
-    launch_set_scan(h->stream, h->grid_pts, h->s, h->ctl);
+    std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);
+    h->h_in->pts = h->s.raw; h->h_in->prior = nullptr; h->h_in->seq = ++h->seq; h->h_in->n = n; h->h_in->mode = 0;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, IN_HDR + sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    h->n_last = n;
+    launch_set_scan(h->stream, h->grid_pts, h->s, h->d_in, h->f, h->ctl);
     h->launches += 1;
     VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     return VMP_OK;
@@ -494,7 +505,7 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, P, sizeof(double) * 529, cudaMemcpyHostToDevice, h->stream));
     k_reset_iter<<<1, 1, 0, h->stream>>>(h->ctl);
     const bool ext = h->cfg.estimate_ext != 0;
-    launch_measure(h->stream, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 0);
+    launch_measure(h->stream, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 0, nullptr);
     k_reduce_partials<<<1, 160, 0, h->stream>>>(h->partials, h->grid_meas, ext ? 1 : 0, h->meas_out);
     h->launches += 3;
     double out[157];
@@ -506,46 +517,86 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
     return VMP_OK;
 }
 
+// launch the scan that h->h_in describes and collect its results: everything (default), or - pipelined - the posterior
+// only, with the map update still running and its counters / errors delivered by the next call
+static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t upload_bytes, vmp_scan_stats* stats) {
+    const bool pipe = h->pipelined && !h->prof_on;
+    const unsigned long long seq = ++h->seq;
+    h->h_in->seq = seq; h->h_in->n = n;
+    const int eb = (int)(seq & 1);
+    VMP_CUDA_CHECK(cudaEventRecord(h->pe0[eb], h->stream));
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
+    { const int rr = run_scan(h); if (rr) return rr; }
+    VMP_CUDA_CHECK(cudaEventRecord(h->pe1[eb], h->stream));
+    h->n_last = n;
+    if (!pipe) {
+        const bool had_pending = h->map_pending;        // (only right after pipelining was switched off)
+        int r = finish_sync(h);
+        (void)had_pending;
+        read_state(h, x, P, stats);
+        if (stats) {
+            fill_update_stats(h->h_mout->st, &stats->map);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->pe0[eb], h->pe1[eb]);
+            stats->gpu_ms = ms;
+        }
+        return r;
+    }
+    int r = wait_state(h, seq);
+    if (r) return r;
+    read_state(h, x, P, stats);
+    // the stream has passed the previous scan's map update: its mailbox is complete (this scan's is not written before
+    // its own map update ends, long after this call returns)
+    if (h->map_pending) {
+        fill_update_stats(h->h_mout->st, &h->lag_map);
+        r = finish_map(h);
+        if (stats) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->pe0[eb ^ 1], h->pe1[eb ^ 1]) == cudaSuccess) stats->gpu_ms = ms;
+        }
+    }
+    if (stats) stats->map = h->lag_map;
+    h->map_pending = true;
+    return r;
+}
+
 int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp_scan_stats* stats) {
     const auto t_enter = std::chrono::steady_clock::now();
-    int r = check_n(h, n, "vmp_scan");
+    int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan") : check_n(h, n, "vmp_scan");
     if (r) return r;
     if (!x || !P || (n > 0 && !pts)) { set_error("vmp_scan: null argument"); return VMP_ERR_INVALID_ARG; }
     if (!h->map_built) { set_error("vmp_scan: no map yet (call vmp_first_scan or vmp_map_build first)"); return VMP_ERR_STATE; }
-    // stage through pinned memory so that both copies are truly asynchronous
+    // header + prior + points go up in ONE DMA copy from pinned staging (SM reads of host memory reach a fraction of the
+    // copy engine's PCIe rate, small ones cost a round trip each); the previous scan's copy is long done
     std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);
-    h->h_in->n = n; h->h_in->has_state = 1;
+    h->h_in->pts = h->s.raw; h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
     std::memcpy(h->h_in->x, x, sizeof(double) * 36);
     std::memcpy(h->h_in->P, P, sizeof(double) * 529);
-    VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-    if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, h->h_raw, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
-    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_in, h->h_in, sizeof(ScanIn), cudaMemcpyHostToDevice, h->stream));
-    { const int rr = run_scan(h); if (rr) return rr; }
-    h->n_last = n;
-    r = finish_scan(h, x, P, stats);
+    r = scan_common(h, x, P, n, IN_HDR + sizeof(float) * 3 * (size_t)n, stats);
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
 }
 
 int vmp_scan_dev(vmp_handle h, const float* pts_dev, const double* prior_dev, int n, vmp_scan_stats* stats) {
     const auto t_enter = std::chrono::steady_clock::now();
-    int r = check_n(h, n, "vmp_scan_dev");
+    int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan_dev") : check_n(h, n, "vmp_scan_dev");
     if (r) return r;
+    if (n > 0 && !pts_dev) { set_error("vmp_scan_dev: null points"); return VMP_ERR_INVALID_ARG; }
     if (!h->map_built) { set_error("vmp_scan_dev: no map yet"); return VMP_ERR_STATE; }
-    h->h_in->n = n; h->h_in->has_state = 0;
-    VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-    if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts_dev, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, h->stream));
-    if (prior_dev) {
-        VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->x, prior_dev, sizeof(double) * 36, cudaMemcpyDeviceToDevice, h->stream));
-        VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, prior_dev + 36, sizeof(double) * 529, cudaMemcpyDeviceToDevice, h->stream));
-    }
-    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_in, h->h_in, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    { const int rr = run_scan(h); if (rr) return rr; }
-    h->n_last = n;
-    r = finish_scan(h, nullptr, nullptr, stats);
+    h->h_in->pts = pts_dev; h->h_in->prior = prior_dev;
+    h->h_in->mode = (prior_dev ? SCAN_STATE_DEV : 0) | SCAN_BEGIN_UPDATE;
+    r = scan_common(h, nullptr, nullptr, n, offsetof(ScanIn, x), stats);
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
 }
+
+int vmp_set_pipelined(vmp_handle h, int on) {
+    int r = check_n(h, 0, "vmp_set_pipelined");
+    if (r) return r;
+    h->pipelined = on != 0;
+    return VMP_OK;
+}
+int vmp_sync(vmp_handle h) { return check_n(h, 0, "vmp_sync"); }
 
 int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const float* pts, int n, vmp_update_stats* st) {
     int r = check_n(h, n, "vmp_first_scan");
@@ -559,12 +610,10 @@ int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const floa
     if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
     VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
     launch_world_points(h->stream, h->grid_pts, h->s, h->f, h->ctl, 1);
-    h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true, nullptr);
-    k_scan_out<<<1, 256, 0, h->stream>>>(h->f, h->ctl, h->d_out);
-    h->launches += 1;
+    h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true, true, h->a_mout, nullptr);
     h->map_built = true;
-    r = finish_scan(h, nullptr, nullptr, nullptr);
-    fill_update_stats(h->h_out->st, st);
+    r = finish_sync(h);
+    fill_update_stats(h->h_mout->st, st);
     return r;
 }
 
@@ -668,7 +717,8 @@ int vmp_dump_evicted(vmp_handle h, int64_t* keys, int cap, int* count) {
 int64_t vmp_launch_count(vmp_handle h) { return h ? h->launches : 0; }
 int vmp_debug_counters(vmp_handle h, int* out8) {
     if (!h || !out8) return VMP_ERR_INVALID_ARG;
-    for (int q = 0; q < 8; q++) out8[q] = h->h_out->dbg[q];
+    if (drain(h)) return VMP_ERR_CUDA;
+    for (int q = 0; q < 8; q++) out8[q] = h->h_mout->dbg[q];
     return VMP_OK;
 }
 

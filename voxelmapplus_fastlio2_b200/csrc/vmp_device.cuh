@@ -77,13 +77,49 @@ struct DevCtl {
     int converged;
     int effect[8];
     int max_iter;
+    unsigned long long seq;             // sequence number of the current scan (echoed in StateOut / MapOut)
+    unsigned fin_ticket;                // arrival counter of k_map_finalize's CTAs (the last one closes the update)
+};
+
+// start of a map update: per-update counters (single thread)
+__device__ __forceinline__ void map_begin_reset(DevCtl* ctl) {
+    DevStats z = {};
+    ctl->st = z;
+    ctl->n_touched = 0; ctl->n_new = 0; ctl->n_evict = 0; ctl->n_hot = 0; ctl->n_ghost = 0;
+    ctl->n_jobs = 0; ctl->n_batches = 0; ctl->contrib_top = 0;
+    for (int q = 0; q < 3; q++) ctl->dbg[q] = 0;          // [3..7] belong to the solver CTA
+}
+
+// ---- per-scan mailboxes.  ScanIn travels with the points in one DMA copy; StateOut / MapOut live in PINNED, MAPPED
+//      host memory and are written by the kernels directly (posted PCIe writes), so no copy-back operation is needed ----
+constexpr int SCAN_STATE_HDR = 1;       // ScanIn::x / P hold the prior (vmp_scan)
+constexpr int SCAN_STATE_DEV = 2;       // ScanIn::prior points at 36 + 529 doubles in device memory (vmp_scan_dev)
+constexpr int SCAN_BEGIN_UPDATE = 4;    // start of IESKF::update: predict_x = x_, iteration counters (ieskf.cpp:127-130)
+struct ScanIn {
+    const float* pts;                   // 3n floats, device-accessible (pinned staging or the caller's device buffer)
+    const double* prior;
+    unsigned long long seq;
+    int n, mode;
+    double x[36];
+    double P[529];
+};
+struct StateOut {                       // written by the solver CTA when the IEKF loop ends
+    double x[36];
+    double P[529];
+    int iter, converged, effect[8];
+    unsigned long long seq;             // written last, after a system-scope fence
+};
+struct MapOut {                         // written by the last CTA of k_map_finalize
+    DevStats st;
+    int err, need_maint;                // need_maint: bit0 rehash, bit1 LRU-log compaction
+    int dbg[8];
+    unsigned long long seq;
 };
 
 struct DevFilter {
     double x[36];                       // vmp_state layout: pos3 rot9 rot_ext9 pos_ext3 vel3 bg3 ba3 g3
     double xpred[36];
     double P[529];
-    double Pinv[529];
 };
 
 struct DevMap {

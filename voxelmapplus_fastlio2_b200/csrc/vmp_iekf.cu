@@ -19,16 +19,59 @@
 namespace vmp {
 
 // ---------------------------------------------------------------------------- K0
-__global__ void __launch_bounds__(256) k_set_scan(DevScan s, const DevCtl* __restrict__ ctl) {
-    const int n = ctl->n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        V3 p = v3((double)s.raw[3 * i], (double)s.raw[3 * i + 1], (double)s.raw[3 * i + 2]);
-        M3 c;
-        calc_body_cov(p, s.range_var, s.sn2, c);
+// One kernel stages the whole scan: the header and the points are read straight from the mailbox (pinned host memory or
+// the caller's device buffer), block 0 stages the prior and the counters of IESKF::update (ieskf.cpp:127-130).
+__global__ void __launch_bounds__(256) k_set_scan(DevScan s, const ScanIn* __restrict__ in, DevFilter* f, DevCtl* ctl) {
+    __shared__ float sh[768];
+    __shared__ int s_n, s_mode;
+    __shared__ const float* s_pts;
+    __shared__ const double* s_prior;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_n = in->n; s_mode = in->mode; s_pts = in->pts; s_prior = in->prior; }
+    __syncthreads();
+    const int n = s_n, mode = s_mode;
+    const float* pts = s_pts;                      // == s.raw when the host copied the points there itself
+    const bool copy_raw = pts != s.raw;
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            ctl->n = n; ctl->seq = in->seq;
+            if (mode & SCAN_BEGIN_UPDATE) { ctl->iter = 0; ctl->done = 0; ctl->converged = 0; ctl->ticket = 0; }
+        }
+        if ((mode & SCAN_BEGIN_UPDATE) && tid < 8) ctl->effect[tid] = 0;
+        if (mode & (SCAN_STATE_HDR | SCAN_STATE_DEV)) {
+            const double* xs = (mode & SCAN_STATE_HDR) ? in->x : s_prior;
+            const double* Ps = (mode & SCAN_STATE_HDR) ? in->P : s_prior + 36;
+            for (int q = tid; q < 529; q += 256) f->P[q] = Ps[q];
+            if (tid < 36) { const double v = xs[tid]; f->x[tid] = v; f->xpred[tid] = v; }
+        } else if ((mode & SCAN_BEGIN_UPDATE) && tid < 36) {
+            f->xpred[tid] = f->x[tid];
+        }
+    }
+    const bool al16 = (((size_t)pts) & 15) == 0;
+    for (int b = blockIdx.x; b * 256 < n; b += gridDim.x) {
+        const int base = b * 256;
+        const int cnt = n - base < 256 ? n - base : 256, nfl = cnt * 3;
+        const float* src = pts + (size_t)base * 3;                   // 3072 b bytes past pts: keeps the 16-byte alignment
+        if (al16) {
+            const int n4 = nfl >> 2;
+            if (tid < n4) reinterpret_cast<float4*>(sh)[tid] = reinterpret_cast<const float4*>(src)[tid];
+            if (tid < (nfl & 3)) sh[n4 * 4 + tid] = src[n4 * 4 + tid];
+        } else {
+            for (int q = tid; q < nfl; q += 256) sh[q] = src[q];
+        }
+        __syncthreads();
+        if (copy_raw) for (int q = tid; q < nfl; q += 256) s.raw[(size_t)base * 3 + q] = sh[q];
+        if (tid < cnt) {
+            const int i = base + tid;
+            V3 p = v3((double)sh[3 * tid], (double)sh[3 * tid + 1], (double)sh[3 * tid + 2]);
+            M3 c;
+            calc_body_cov(p, s.range_var, s.sn2, c);
 #pragma unroll
-        for (int k = 0; k < 3; k++) s.pl[(size_t)k * s.nmax + i] = p[k];
+            for (int k = 0; k < 3; k++) s.pl[(size_t)k * s.nmax + i] = p[k];
 #pragma unroll
-        for (int k = 0; k < 9; k++) s.cl[(size_t)k * s.nmax + i] = c.a[k];
+            for (int k = 0; k < 9; k++) s.cl[(size_t)k * s.nmax + i] = c.a[k];
+        }
+        __syncthreads();
     }
 }
 
@@ -42,7 +85,7 @@ struct MeasState {
 
 template <bool EXT>
 __global__ void __launch_bounds__(EXT ? 128 : 256)
-k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
+k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve, StateOut* sout) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;                 // upper triangle of H, b, effect count
@@ -52,7 +95,7 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     // launched with solve = 1 the grid has one more CTA: block 0 runs this iteration's 23-dof solve (IESKF::update body,
     // vmp_solve.cuh), starting with the part that needs no measurement while the other CTAs measure
     if (solve && blockIdx.x == 0) {
-        ieskf_solve_cta<EXT, EXT ? 128 : 256>(f, ctl, partials, (int)gridDim.x - 1);
+        ieskf_solve_cta<EXT, EXT ? 128 : 256>(f, ctl, partials, (int)gridDim.x - 1, sout);
         return;
     }
     const int pb = (int)blockIdx.x - solve, npb = (int)gridDim.x - solve;      // measurement CTA index / count
@@ -172,20 +215,21 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     if (threadIdx.x == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
-void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve, StateOut* sout) {
     const int g = grid + (solve ? 1 : 0);
-    if (ext) k_measure<true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve);
-    else k_measure<false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve);
+    if (ext) k_measure<true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, sout);
+    else k_measure<false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, sout);
 }
-void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const DevCtl* ctl) { k_set_scan<<<grid, 256, 0, st>>>(s, ctl); }
+void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const ScanIn* in, DevFilter* f, DevCtl* ctl) { k_set_scan<<<grid, 256, 0, st>>>(s, in, f, ctl); }
 
 // ---------------------------------------------------------------------------- K3
 // float32 world transform with the association of PCL's SSE Transformer::se3
 // (x' = m00 x + (m01 y + (m02 z + tx)), separate mul/add), widened to fp64, plus
 // pv.cov with the posterior R and P.  first_scan: calcBodyCov on a local copy (lio_builder.cpp:196-198).
-__global__ void __launch_bounds__(256) k_world_points(DevScan s, const DevFilter* __restrict__ f, const DevCtl* __restrict__ ctl, int first_scan) {
+__global__ void __launch_bounds__(256) k_world_points(DevScan s, const DevFilter* __restrict__ f, DevCtl* ctl, int first_scan) {
     __shared__ MeasState ms;
     __shared__ float mf[12];
+    if (blockIdx.x == 0 && threadIdx.x == 32) map_begin_reset(ctl);     // the map update that follows starts here
     if (threadIdx.x == 0) {
         const St x = st_load(f->x);
         ms.r_wl = mul(x.rot, x.rot_ext);
@@ -219,7 +263,7 @@ __global__ void __launch_bounds__(256) k_world_points(DevScan s, const DevFilter
         for (int k = 0; k < 9; k++) s.pcov[9 * (size_t)i + k] = cw.a[k];
     }
 }
-void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, const DevCtl* ctl, int first_scan) {
+void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, DevCtl* ctl, int first_scan) {
     k_world_points<<<grid, 256, 0, st>>>(s, f, ctl, first_scan);
 }
 

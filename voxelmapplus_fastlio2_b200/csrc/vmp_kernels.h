@@ -11,17 +11,21 @@ constexpr int PARTIAL_STRIDE = 96;      // doubles per block partial (>= 78 + 12
 constexpr int PT_BLOCK = 1024;          // points per block in the order-preserving passes
 
 // IEKF
-void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const DevCtl* ctl);
-// solve != 0: the last-arriving CTA also runs the 23-dof solve of the iteration (one launch per IEKF iteration)
-void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve);
-void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, const DevCtl* ctl, int first_scan);
+// stages one scan from the mailbox `in` (device-accessible): points -> raw / body points / body covariances, prior, counters
+void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const ScanIn* in, DevFilter* f, DevCtl* ctl);
+// solve != 0: one extra CTA runs the 23-dof solve of the iteration (one launch per IEKF iteration) and, when the loop ends,
+// writes the posterior to the mailbox `sout` (may be null)
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve, StateOut* sout);
+// also resets the per-update counters of the map update that follows (begun = true for launch_map_update)
+void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, DevCtl* ctl, int first_scan);
 
 // optional per-launch hook (profiling mode records a CUDA event after each kernel)
 struct Marker { void (*fn)(void* ctx, int id); void* ctx; };
 inline void mark(const Marker* mk, int id) { if (mk && mk->fn) mk->fn(mk->ctx, id); }
 
 // map: returns the number of kernels launched
-int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, const Marker* mk);
+// `out`: mailbox written by the update's last kernel (counters, error bits, maintenance requests); may be null
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk);
 int launch_map_maintenance(cudaStream_t st, const DevMap& m, DevCtl* ctl, int sm_count, int what);
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl);
 

@@ -95,15 +95,10 @@ __global__ void k_map_init(DevMap m, DevCtl* ctl) {
 }
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl) { k_map_init<<<592, 256, 0, st>>>(m, ctl); }
 
-__global__ void k_map_begin(DevCtl* ctl) {
-    DevStats z = {};
-    ctl->st = z;
-    ctl->n_touched = 0; ctl->n_new = 0; ctl->n_evict = 0; ctl->n_hot = 0; ctl->n_ghost = 0;
-    ctl->n_jobs = 0; ctl->n_batches = 0; ctl->contrib_top = 0;
-    for (int q = 0; q < 3; q++) ctl->dbg[q] = 0;          // [3..7] belong to the solve kernel
-}
+__global__ void k_map_begin(DevCtl* ctl) { map_begin_reset(ctl); }     // only for updates that do not start with k_world_points
 
-__global__ void k_map_end(DevMap m, DevCtl* ctl) {
+// end of VoxelMap::update (single thread, the last CTA of k_map_finalize): counters, maintenance requests, host mailbox
+__device__ void map_end(const DevMap& m, DevCtl* ctl, MapOut* out) {
     ctl->st.n_points = ctl->n;
     ctl->st.n_touch = ctl->n_touched;
     ctl->st.map_size = ctl->n_live;
@@ -111,8 +106,18 @@ __global__ void k_map_end(DevMap m, DevCtl* ctl) {
     ctl->log_tail += ctl->n_touched;                  // exactly one last-touch entry per touched voxel
     ctl->stamp_base += (unsigned long long)ctl->n;
     ctl->scan_id += 1;
-    ctl->need_rehash = (ctl->tombstones > (int)((m.hmask + 1) / 8)) ? 1 : 0;
-    ctl->need_log_compact = (ctl->log_tail + 2ll * m.nmax + 2 > m.log_cap) ? 1 : 0;
+    // requested early enough that they may be served one update late (pipelined mode): an update adds at most nmax
+    // tombstones and nmax log entries
+    ctl->need_rehash = (atomicAdd(&ctl->tombstones, 0) > (int)((m.hmask + 1) / 8)) ? 1 : 0;     // (other CTAs' atomics)
+    ctl->need_log_compact = (ctl->log_tail + 4ll * m.nmax + 4 > m.log_cap) ? 1 : 0;
+    if (out) {
+        out->st = ctl->st;
+        out->err = ctl->err;
+        out->need_maint = (ctl->need_rehash ? 1 : 0) | (ctl->need_log_compact ? 2 : 0);
+        for (int q = 0; q < 8; q++) out->dbg[q] = ctl->dbg[q];
+        __threadfence_system();
+        *(volatile unsigned long long*)&out->seq = ctl->seq;
+    }
 }
 
 // ------------------------------------------------------------------------- rehash (tombstone purge)
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(1024) k_log_append(DevMap m, DevCtl* ctl) {
 }
 
 // ------------------------------------------------------------------------- M7b: finalize
-__global__ void __launch_bounds__(256) k_map_finalize(DevMap m, DevCtl* ctl) {
+__global__ void __launch_bounds__(256) k_map_finalize(DevMap m, DevCtl* ctl, MapOut* out) {
     const int V = ctl->n_touched, E = ctl->n_evict;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int vi = tid; vi < V; vi += nth) {
@@ -485,14 +490,25 @@ __global__ void __launch_bounds__(256) k_map_finalize(DevMap m, DevCtl* ctl) {
         m.stamp[slot] = 0; m.evict_t[slot] = T_INF; m.ghost[slot] = -1;
         m.free_slots[atomicAdd(&ctl->free_top, 1)] = slot;
     }
+    // the last CTA to get here closes the update
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&ctl->fin_ticket, 1u);
+        if (t == gridDim.x - 1) {
+            ctl->fin_ticket = 0;
+            __threadfence();
+            map_end(m, ctl, out);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------- launcher
-int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, const Marker* mk) {
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk) {
     const int gpt = (m.nmax + PT_BLOCK - 1) / PT_BLOCK;               // order-preserving passes: 1024 points / block
     const int gstride = sm_count * 2;
     int launches = 0;
-    k_map_begin<<<1, 1, 0, st>>>(ctl); launches++; mark(mk, VMP_K_MAP_BEGIN);
+    if (!begun) { k_map_begin<<<1, 1, 0, st>>>(ctl); launches++; mark(mk, VMP_K_MAP_BEGIN); }
     k_map_insert<<<gstride, 256, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_INSERT);
     k_map_count<<<gstride, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_COUNT);
     k_seg_scan<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_SCAN);
@@ -506,8 +522,7 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
         k_merge_rounds<<<1, 512, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
     }
     k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND);
-    k_map_finalize<<<sm_count, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_FINALIZE);
-    k_map_end<<<1, 1, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_END);
+    k_map_finalize<<<sm_count, 256, 0, st>>>(m, ctl, out); launches++; mark(mk, VMP_K_MAP_FINALIZE);
     return launches;
 }
 

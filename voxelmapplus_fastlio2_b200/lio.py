@@ -28,7 +28,9 @@ class _BorrowedHotPath(HotPath):
 
 
 class LIOBuilder:
-    def __init__(self, cfg: VmpConfig):
+    def __init__(self, cfg: VmpConfig, pipelined: bool = False):
+        """pipelined: process() returns with the posterior of the scan while its map update still runs on the device
+        (vmp_set_pipelined); the map counters in the returned stats then describe the previous scan."""
         self._lib = load_library()
         L = self._lib
         L.vmp_lio_create.argtypes = [C.POINTER(VmpConfig), C.POINTER(C.c_void_p)]
@@ -43,6 +45,8 @@ class LIOBuilder:
         self._h = C.c_void_p()
         self._check(L.vmp_lio_create(C.byref(cfg), C.byref(self._h)))
         self.map = _BorrowedHotPath(L, cfg, L.vmp_lio_map(self._h))
+        if pipelined:
+            self.map.set_pipelined(True)
 
     def _check(self, rc):
         if rc != 0:
