@@ -213,14 +213,22 @@ __device__ __forceinline__ bool voxel_index(double x, double y, double z, double
     return true;
 }
 
-// featmap.find(k): slot id or -1
+// featmap.find(k): slot id or -1.  Linear probing examines consecutive entries, so a window of four keys and values is
+// fetched with independent loads and scanned in probe order: one memory latency per four probes (every caller is a
+// chain of dependent look-ups, and probes past tombstones / to the terminating EMPTY are common).
 __device__ __forceinline__ int hash_find(const DevMap& m, unsigned long long pk) {
     unsigned h = hash_key(pk) & m.hmask;
-    for (unsigned probe = 0; probe <= m.hmask; probe++) {
-        const unsigned long long cur = m.tkey[h];
-        if (cur == pk) return m.tval[h];
-        if (cur == KEY_EMPTY) return -1;
-        h = (h + 1) & m.hmask;
+    for (unsigned probe = 0; probe <= m.hmask; probe += 4) {
+        unsigned long long k[4];
+        int v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const unsigned hq = (h + q) & m.hmask; k[q] = m.tkey[hq]; v[q] = m.tval[hq]; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (k[q] == pk) return v[q];
+            if (k[q] == KEY_EMPTY) return -1;
+        }
+        h = (h + 4) & m.hmask;
     }
     return -1;
 }

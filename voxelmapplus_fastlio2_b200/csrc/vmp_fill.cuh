@@ -168,11 +168,14 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
         } else {
             int nt = m.n_temp[slot], nw = m.newly[slot];
             const int nt0 = nt;
-            const double* h = m.hot + (size_t)slot * 8;
-            V3 mean = v3(h[0], h[1], h[2]);
-            double ppt[6];
-#pragma unroll
-            for (int k = 0; k < 6; k++) ppt[k] = m.ppt[(size_t)slot * 6 + k];
+            // addToPlane (voxel_map.cpp:29-34) is a dependent chain per point; its nine scalar updates run on nine
+            // lanes' worth of registers instead of one lane's: lane l < 3 owns mean[l], lane l < 6 owns ppt[l]
+            // (xx, yx, yy, zx, zy, zz).  A lone warp pays per instruction, and the three divisions become one.
+            const int cm = lane < 3 ? lane : 0;
+            const int ia = lane == 0 ? 0 : lane < 3 ? 1 : lane < 6 ? 2 : 0;
+            const int ib = (lane == 2 || lane == 4) ? 1 : lane == 5 ? 2 : 0;
+            double mean_l = m.hot[(size_t)slot * 8 + cm];
+            double ppt_l = m.ppt[(size_t)slot * 6 + (lane < 6 ? lane : 0)];
             unsigned full_scan = SCAN_NEVER; int full_idx = T_INF;
             double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
             int consumed = 0;
@@ -181,11 +184,10 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
                 int* order = m.seg + off;
                 warp_sort(order, c);
                 for (int j = 0; j < c; j++) {
-                    const int i = order[j];
-                    const V3 p = v3(s.pw[3 * (size_t)i], s.pw[3 * (size_t)i + 1], s.pw[3 * (size_t)i + 2]);
-                    mean = add(mean, divs(sub(p, mean), n + 1.0));
-                    ppt[0] += p[0] * p[0]; ppt[1] += p[1] * p[0]; ppt[2] += p[1] * p[1];
-                    ppt[3] += p[2] * p[0]; ppt[4] += p[2] * p[1]; ppt[5] += p[2] * p[2];
+                    const size_t i3 = 3 * (size_t)order[j];
+                    const double pm = s.pw[i3 + cm], pa = s.pw[i3 + ia], pb = s.pw[i3 + ib];
+                    mean_l = mean_l + (pm - mean_l) / (n + 1.0);
+                    ppt_l += pa * pb;
                     n += 1;
                 }
                 for (int q = lane; q < c && nt0 + q < m.maxpt; q += 32) {
@@ -198,7 +200,9 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
                 nt += c; consumed = c;
                 if (n >= m.upt) {
                     flags |= F_INIT;
-                    if (lane == 0) { snap[0] = n; snap[1] = nt; for (int k = 0; k < 3; k++) snap[2 + k] = mean[k]; for (int k = 0; k < 6; k++) snap[5 + k] = ppt[k]; }
+                    if (lane == 0) { snap[0] = n; snap[1] = nt; }
+                    if (lane < 3) snap[2 + lane] = mean_l;
+                    if (lane < 6) snap[5 + lane] = ppt_l;
                     __syncwarp();
                     first_job = emit_jobs(m, ctl, slot, snap, 1, off, -1);
                 }
@@ -216,11 +220,9 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
                 int nsnap = 0, prev_job = -1, j = 0;
                 for (; j < K; j++) {                                           // pushPoint state machine, point order
                     if (!(flags & F_UE)) break;
-                    const V3 p = v3(spt[3 * j], spt[3 * j + 1], spt[3 * j + 2]);
-                    // addToPlane (voxel_map.cpp:29-34)
-                    mean = add(mean, divs(sub(p, mean), n + 1.0));
-                    ppt[0] += p[0] * p[0]; ppt[1] += p[1] * p[0]; ppt[2] += p[1] * p[1];
-                    ppt[3] += p[2] * p[0]; ppt[4] += p[2] * p[1]; ppt[5] += p[2] * p[2];
+                    const double pm = spt[3 * j + cm], pa = spt[3 * j + ia], pb = spt[3 * j + ib];
+                    mean_l = mean_l + (pm - mean_l) / (n + 1.0);
+                    ppt_l += pa * pb;
                     n += 1;
                     nt += 1;                                                   // temp_points.push_back (stored below)
                     bool refit = false;
@@ -240,12 +242,10 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
                             prev_job = jb < 0 ? -1 : jb + nsnap - 1;
                             nsnap = 0;
                         }
-                        if (lane == 0) {
-                            double* sn = snap + nsnap * SNAP_W;
-                            sn[0] = n; sn[1] = nt;
-                            for (int k = 0; k < 3; k++) sn[2 + k] = mean[k];
-                            for (int k = 0; k < 6; k++) sn[5 + k] = ppt[k];
-                        }
+                        double* sn = snap + nsnap * SNAP_W;
+                        if (lane == 0) { sn[0] = n; sn[1] = nt; }
+                        if (lane < 3) sn[2 + lane] = mean_l;
+                        if (lane < 6) sn[5 + lane] = ppt_l;
                         nsnap++;
                     }
                     if (was_init && nt >= m.maxpt) {                           // update_enable = false; temp_points freed
@@ -271,11 +271,10 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
             c_ins += consumed;
             events = c - consumed;
             __syncwarp();
+            if (lane < 3) m.hot[(size_t)slot * 8 + lane] = mean_l;
+            if (lane < 6) m.ppt[(size_t)slot * 6 + lane] = ppt_l;
             if (lane == 0) {
-                double* hw = m.hot + (size_t)slot * 8;
-                hw[0] = mean[0]; hw[1] = mean[1]; hw[2] = mean[2];
                 hot_set_fn(m.hot, slot, flags, n);
-                for (int k = 0; k < 6; k++) m.ppt[(size_t)slot * 6 + k] = ppt[k];
                 m.n_temp[slot] = nt; m.newly[slot] = nw;
                 if (full_scan != SCAN_NEVER) { m.full_scan[slot] = full_scan; m.full_idx[slot] = full_idx; }
             }

@@ -41,51 +41,66 @@ __device__ __forceinline__ void load_plane(const DevMap& m, int s, V3& mean, V3&
     nrm = v3(h[3], h[4], h[5]);
 }
 
+// Everything the merge logic wants to know about one voxel, fetched with INDEPENDENT loads (one memory latency);
+// these kernels are chains of dependent look-ups, so the number of round trips is what they cost.
+struct VoxRec {
+    V3 mean, nrm;
+    unsigned long long group;
+    uint32_t flags;
+    long long w6;                       // raw flags | n word of the hot record
+    unsigned born_scan, full_scan;
+    int ft, full_idx, evict_t, ghost;
+};
+__device__ __forceinline__ VoxRec load_rec(const DevMap& m, int s) {
+    VoxRec r;
+    const double2* h2 = reinterpret_cast<const double2*>(m.hot + (size_t)s * 8);        // 64-byte records
+    const double2 q0 = h2[0], q1 = h2[1], q2 = h2[2], q3 = h2[3];
+    r.group = m.sgroup[s];
+    r.born_scan = m.born_scan[s]; r.full_scan = m.full_scan[s];
+    r.ft = m.ft[s]; r.full_idx = m.full_idx[s]; r.evict_t = m.evict_t[s]; r.ghost = m.ghost[s];
+    r.mean = v3(q0.x, q0.y, q1.x);
+    r.nrm = v3(q1.y, q2.x, q2.y);
+    r.w6 = __double_as_longlong(q3.x);
+    r.flags = (uint32_t)(r.w6 & 0xFFFFFFFFll);
+    return r;
+}
 // could merge(A) succeed against the (final state of) incarnation B at some time of this scan?
-__device__ __forceinline__ bool pair_static(const DevMap& m, int A, int B) {
-    uint32_t fb; int nb;
-    hot_get_fn(m.hot, B, fb, nb);
-    if ((fb & F_UE) || !(fb & F_PLANE)) return false;
-    if (m.sgroup[B] == m.sgroup[A]) return false;
-    V3 mA, nA, mB, nB;
-    load_plane(m, A, mA, nA);
-    load_plane(m, B, mB, nB);
-    return plane_thresholds(m, mA, nA, mB, nB);
+__device__ __forceinline__ bool pair_static(const DevMap& m, const V3& mA, const V3& nA, unsigned long long gA, const VoxRec& B) {
+    if ((B.flags & F_UE) || !(B.flags & F_PLANE)) return false;
+    if (B.group == gA) return false;
+    return plane_thresholds(m, mA, nA, B.mean, B.nrm);
 }
 // window (start, end) of point indices t of this scan at which B is alive and full: start < t < end
-__device__ __forceinline__ void pair_window(const DevMap& m, int B, unsigned scan_id, int& start, int& end) {
-    const int born = (m.born_scan[B] == scan_id) ? m.ft[B] : -1;
-    const int full = (m.full_scan[B] == scan_id) ? m.full_idx[B] : -1;
+__device__ __forceinline__ void pair_window(const VoxRec& B, unsigned scan_id, int& start, int& end) {
+    const int born = (B.born_scan == scan_id) ? B.ft : -1;
+    const int full = (B.full_scan == scan_id) ? B.full_idx : -1;
     start = born > full ? born : full;
-    end = m.evict_t[B];
+    end = B.evict_t;
+}
+__device__ __forceinline__ int event_floor(const VoxRec& A, unsigned scan_id) {
+    return (A.full_scan == scan_id) ? A.full_idx : -1;           // merge() runs only for points after the closing one
 }
 
 // one neighbour direction of "could merge(A) succeed after time `after`": returns the earliest time
-// bound (events with t > bound may succeed), T_INF if never.  after = -1 gives the plain static test.
-__device__ int wake_dir(const DevMap& m, int A, int d, int after, unsigned scan_id) {
+// bound (events with t > bound may succeed), T_INF if never.  keyA / mA / nA / gA: A's key, plane and group.
+__device__ __forceinline__ int wake_dir(const DevMap& m, unsigned long long keyA, const V3& mA, const V3& nA, unsigned long long gA,
+                                        int d, int after, unsigned scan_id) {
     bool ok;
-    const unsigned long long nk = nbr_key(m.skey[A], d, ok);
+    const unsigned long long nk = nbr_key(keyA, d, ok);
     if (!ok) return T_INF;
     int best = T_INF;
-    for (int B = hash_find(m, nk); B >= 0; B = m.ghost[B]) {
-        if (!pair_static(m, A, B)) continue;
-        int s, e;
-        pair_window(m, B, scan_id, s, e);
-        const int bound = s > after ? s : after;                 // first usable events are those with t > bound
-        if (bound + 1 < e && bound < best) best = bound;
+    int B = hash_find(m, nk);
+    while (B >= 0) {
+        const VoxRec r = load_rec(m, B);
+        if (pair_static(m, mA, nA, gA, r)) {
+            int s, e;
+            pair_window(r, scan_id, s, e);
+            const int bound = s > after ? s : after;             // first usable events are those with t > bound
+            if (bound + 1 < e && bound < best) best = bound;
+        }
+        B = r.ghost;
     }
     return best;
-}
-__device__ __forceinline__ int wake_warp(const DevMap& m, int A, int after, unsigned scan_id) {
-    const int lane = threadIdx.x & 31;
-    int w = lane < 6 ? wake_dir(m, A, lane, after, scan_id) : T_INF;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, w, o); w = y < w ? y : w; }
-    return __shfl_sync(0xffffffffu, w, 0);
-}
-
-__device__ __forceinline__ int event_floor(const DevMap& m, int A, unsigned scan_id) {
-    return (m.full_scan[A] == scan_id) ? m.full_idx[A] : -1;     // merge() runs only for points after the closing one
 }
 
 // 8 lanes per touched voxel, lanes 0..5 take one neighbour each; voxels whose merge() can succeed at
@@ -101,7 +116,11 @@ __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) 
         int w = T_INF, A = -1;
         if (vi < V) {
             A = m.touched[vi];
-            if (m.evn[A] > 0 && sub < 6) w = wake_dir(m, A, sub, event_floor(m, A, scan_id), scan_id);
+            if (m.evn[A] > 0 && sub < 6) {
+                const unsigned long long keyA = m.skey[A];
+                const VoxRec ra = load_rec(m, A);
+                w = wake_dir(m, keyA, ra.mean, ra.nrm, ra.group, sub, event_floor(ra, scan_id), scan_id);
+            }
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) { const int y = __shfl_xor_sync(gmask, w, o); w = y < w ? y : w; }
@@ -120,98 +139,108 @@ __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) 
     }
 }
 
-// first point index of voxel A in this scan that is > after (warp-parallel), T_INF if none
-__device__ int next_event_warp(const DevMap& m, int A, int after) {
-    const int lane = threadIdx.x & 31;
-    const int c = m.cnt[A], off = m.seg_off[A];
-    int best = T_INF;
-    for (int q = lane; q < c; q += 32) { const int i = m.seg[off + q]; if (i > after && i < best) best = i; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
-    return best;
-}
-
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // VoxelGrid::merge() of voxel A at time t, executed by the whole warp.  Returns the number of
 // successful pair merges; changed[0..n) (warp-uniform) are the neighbour slots that were modified.
 __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigned scan_id, int* changed) {
     const int lane = threadIdx.x & 31;
-    // ---- parallel part: lane d < 6 resolves neighbour d as of time t and loads its record
+    // A's own record and covariance (issued first: these loads overlap the neighbour look-ups below);
+    // lanes hold the 36 covariance entries (lane e: entry e, lanes 0..3 also entry 32+e)
+    const unsigned long long keyA = m.skey[A];
+    const VoxRec ra = load_rec(m, A);
+    double* ca = m.cov + (size_t)A * 36;
+    double a0 = ca[lane], a1 = lane < 4 ? ca[32 + lane] : 0.0;
+    const unsigned long long gA = ra.group;
+    V3 mA = ra.mean, nA = ra.nrm;
+    // ---- parallel part: lane d < 6 resolves neighbour d as of time t (one record fetch per incarnation)
     int B = -1;
     bool elig = false;
-    unsigned long long gB = 0;
-    V3 mB = v3(0, 0, 0), nB = v3(0, 0, 0);
-    uint32_t fB = 0; int cntB = 0;
+    VoxRec rb;
+    rb.mean = v3(0, 0, 0); rb.nrm = v3(0, 0, 0); rb.w6 = 0;
     if (lane < 6) {
         bool ok;
-        const unsigned long long nk = nbr_key(m.skey[A], lane, ok);
+        const unsigned long long nk = nbr_key(keyA, lane, ok);
         if (ok) {
-            for (int X = hash_find(m, nk); X >= 0; X = m.ghost[X]) {          // incarnation alive at time t
-                const int born = (m.born_scan[X] == scan_id) ? m.ft[X] : -1;
-                if (born <= t && t < m.evict_t[X]) { B = X; break; }
+            int X = hash_find(m, nk);
+            while (X >= 0) {                                          // incarnation alive at time t
+                const VoxRec r = load_rec(m, X);
+                const int born = (r.born_scan == scan_id) ? r.ft : -1;
+                if (born <= t && t < r.evict_t) { B = X; rb = r; break; }
+                X = r.ghost;
             }
         }
         if (B >= 0) {
-            hot_get_fn(m.hot, B, fB, cntB);
-            const bool closed = !(fB & F_UE) && (m.full_scan[B] != scan_id || m.full_idx[B] < t);
-            elig = closed && (fB & F_PLANE);
-            gB = m.sgroup[B];
-            load_plane(m, B, mB, nB);
+            const bool closed = !(rb.flags & F_UE) && (rb.full_scan != scan_id || rb.full_idx < t);
+            // the neighbours are distinct voxels and gA does not change: group test once, up front
+            elig = closed && (rb.flags & F_PLANE) && rb.group != gA;
         }
     }
-    // ---- ordered part (warp-uniform control flow)
-    V3 mA, nA;
-    load_plane(m, A, mA, nA);
-    const unsigned long long gA = m.sgroup[A];
-    double* ca = m.cov + (size_t)A * 36;
-    int nchg = 0;
+    const unsigned elmask = __ballot_sync(0xffffffffu, elig) & 0x3Fu;
+    // covariances of every eligible neighbour, fetched together
+    double b0p[6], b1p[6];
+#pragma unroll
     for (int d = 0; d < 6; d++) {
+        b0p[d] = 0.0; b1p[d] = 0.0;
         const int Bd = __shfl_sync(0xffffffffu, B, d);
-        const int el = __shfl_sync(0xffffffffu, elig ? 1 : 0, d);
-        const unsigned long long g = __shfl_sync(0xffffffffu, gB, d);
-        if (Bd < 0 || !el || g == gA) continue;
+        if ((elmask >> d) & 1u) {
+            const double* cb = m.cov + (size_t)Bd * 36;
+            b0p[d] = cb[lane];
+            if (lane < 4) b1p[d] = cb[32 + lane];
+        }
+    }
+    // ---- ordered part (warp-uniform control flow): -x -y -z +x +y +z, own plane updated in between (Q10)
+    int nchg = 0;
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+        if (!((elmask >> d) & 1u)) continue;
+        const int Bd = __shfl_sync(0xffffffffu, B, d);
         V3 mb, nb;
 #pragma unroll
-        for (int k = 0; k < 3; k++) { mb[k] = shfl_d(mB[k], d); nb[k] = shfl_d(nB[k], d); }
+        for (int k = 0; k < 3; k++) { mb[k] = shfl_d(rb.mean[k], d); nb[k] = shfl_d(rb.nrm[k], d); }
         if (!plane_thresholds(m, mA, nA, mb, nb)) continue;
-        // lanes hold the 36 covariance entries of both voxels (lane e: entry e, lanes 0..3 also entry 32+e)
         double* cb = m.cov + (size_t)Bd * 36;
-        const double a0 = ca[lane], b0 = cb[lane];
-        const double a1 = lane < 4 ? ca[32 + lane] : 0.0, b1 = lane < 4 ? cb[32 + lane] : 0.0;
+        const double b0 = b0p[d], b1 = b1p[d];
         const double tn0 = shfl_d(a0, 0) + shfl_d(a0, 7) + shfl_d(a0, 14);
         const double tm0 = shfl_d(a0, 21) + shfl_d(a0, 28) + shfl_d(a1, 3);
         const double tn1 = shfl_d(b0, 0) + shfl_d(b0, 7) + shfl_d(b0, 14);
         const double tm1 = shfl_d(b0, 21) + shfl_d(b0, 28) + shfl_d(b1, 3);
         const double tc0 = tn0 + tm0, tc1 = tn1 + tm1;
-        // Q9: operator precedence exactly as in voxel_map.cpp:166-167
+        // Q9: operator precedence exactly as in voxel_map.cpp:166-167.  The six divisions run on six lanes (lane k:
+        // mean[k], lane 3 + k: normal[k]) and are broadcast: a single warp pays per instruction, not per lane
         V3 nm, nn;
+        {
+            const int kk = lane % 3;
+            const bool isn = lane >= 3;
+            const double xb = isn ? (kk == 0 ? nb[0] : kk == 1 ? nb[1] : nb[2]) : (kk == 0 ? mb[0] : kk == 1 ? mb[1] : mb[2]);
+            const double xa = isn ? (kk == 0 ? nA[0] : kk == 1 ? nA[1] : nA[2]) : (kk == 0 ? mA[0] : kk == 1 ? mA[1] : mA[2]);
+            const double t0 = isn ? tn0 : tm0, t1 = isn ? tn1 : tm1;
+            const double v = xb * t0 + (xa * t1) / (t0 + t1);
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            nm[k] = mb[k] * tm0 + (mA[k] * tm1) / (tm0 + tm1);
-            nn[k] = nb[k] * tn0 + (nA[k] * tn1) / (tn0 + tn1);
+            for (int k = 0; k < 3; k++) { nm[k] = shfl_d(v, k); nn[k] = shfl_d(v, 3 + k); }
         }
         const double w0 = tc0 * tc0, w1 = tc1 * tc1, den = (tc0 + tc1) * (tc0 + tc1);
         const double c0 = (b0 * w0 + a0 * w1) / den;
-        ca[lane] = c0; cb[lane] = c0;
-        if (lane < 4) { const double c1 = (b1 * w0 + a1 * w1) / den; ca[32 + lane] = c1; cb[32 + lane] = c1; }
+        a0 = c0; cb[lane] = c0;                                    // A's copy stays in registers until the end
+        if (lane < 4) { const double c1 = (b1 * w0 + a1 * w1) / den; a1 = c1; cb[32 + lane] = c1; }
         if (-dot(nm, nn) < 0.0) nn = neg(nn);
-        mA = nm; nA = nn;                                         // own plane is updated before the next neighbour (Q10)
-        if (lane < 3) {
-            m.hot[(size_t)A * 8 + lane] = nm[lane];  m.hot[(size_t)A * 8 + 3 + lane] = nn[lane];
-            m.hot[(size_t)Bd * 8 + lane] = nm[lane]; m.hot[(size_t)Bd * 8 + 3 + lane] = nn[lane];
-        }
+        mA = nm; nA = nn;
+        if (lane < 3) { m.hot[(size_t)Bd * 8 + lane] = nm[lane]; m.hot[(size_t)Bd * 8 + 3 + lane] = nn[lane]; }
         if (lane == 0) {
             m.sgroup[Bd] = gA;
-            uint32_t fa; int na;
-            hot_get_fn(m.hot, A, fa, na);
-            hot_set_fn(m.hot, A, fa | F_MERGED, na);
             atomicAdd((unsigned long long*)&ctl->st.n_merge, 1ull);
+            changed[nchg] = Bd;
         }
-        if (lane == d) hot_set_fn(m.hot, Bd, fB | F_MERGED, cntB);      // neighbour's MERGED flag, by the lane that loaded it
-        __syncwarp();
-        changed[nchg++] = Bd;
+        if (lane == d) m.hot[(size_t)Bd * 8 + 6] = __longlong_as_double(rb.w6 | (long long)F_MERGED);   // by the lane that loaded it
+        nchg++;
     }
+    if (nchg > 0) {
+        ca[lane] = a0;
+        if (lane < 4) ca[32 + lane] = a1;
+        if (lane < 3) { m.hot[(size_t)A * 8 + lane] = mA[lane]; m.hot[(size_t)A * 8 + 3 + lane] = nA[lane]; }
+        if (lane == 0) m.hot[(size_t)A * 8 + 6] = __longlong_as_double(ra.w6 | (long long)F_MERGED);
+    }
+    __syncwarp();
     return nchg;
 }
 
@@ -233,7 +262,7 @@ struct ActiveSet {
     int slot[MERGE_CAP];        // voxel slot | depth << 28
     int t[MERGE_CAP];           // next event (point index), T_INF = retired
     short kx[MERGE_CAP], ky[MERGE_CAP], kz[MERGE_CAP];   // voxel coordinate relative to the first entry (clamped)
-    unsigned char ready[MERGE_CAP];
+    short rlist[MERGE_CAP];     // entries that are ready in the current round
     int n;                      // entries (including retired ones until compaction)
     int ox, oy, oz;
 };
@@ -267,7 +296,6 @@ __device__ void as_activate(const DevMap& m, DevCtl* ctl, ActiveSet& as, int Y, 
             else {
                 as.slot[k] = Y | (depth << 28);
                 as.t[k] = nt;
-                as.ready[k] = 0;
                 as_set_key(as, k, m.skey[Y]);
                 atomicAdd(&ctl->dbg[2], 1);
             }
@@ -276,76 +304,129 @@ __device__ void as_activate(const DevMap& m, DevCtl* ctl, ActiveSet& as, int Y, 
     __syncwarp();
 }
 
-// one merge() call of entry j (voxel A at time t) and everything it triggers; whole warp calls
-__device__ void process_event(const DevMap& m, DevCtl* ctl, ActiveSet& as, int j, unsigned scan_id) {
-    const int lane = threadIdx.x & 31;
+// per-warp scratch of the follow-up work of one event
+constexpr int FOLLOW_CAP = 52;          // (nchg + 1) wakes + 6 (nchg + 1) candidates, nchg <= 6
+struct WarpScratch {
+    int chg[8];                         // neighbour slots modified by the event
+    int tgt[FOLLOW_CAP], aft[FOLLOW_CAP], res[FOLLOW_CAP];
+    unsigned char kind[FOLLOW_CAP];     // 0: the event's own voxel, 1: a modified neighbour, 2: a voxel next to a modified one
+};
+
+// one merge() call of entry j (voxel A at time t) and everything it triggers; whole warp calls.
+// The follow-up look-ups are independent chains of dependent global loads (hash probe -> slot -> plane ...), so
+// they run one per lane, eight lanes per voxel: which voxels around the event can merge now, and when is their
+// next merge() call.  The results are applied afterwards in the order of the reference.
+__device__ void process_event(const DevMap& m, DevCtl* ctl, ActiveSet& as, WarpScratch& ws, int j, unsigned scan_id) {
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
     const int A = as.slot[j] & 0x0FFFFFFF, depth = as.slot[j] >> 28, t = as.t[j];
-    int changed[6];
-    const int nchg = merge_at_warp(m, ctl, A, t, scan_id, changed);
-    if (nchg > 0) {
-        if (depth > MERGE_MAX_DEPTH && lane == 0) atomicOr(&ctl->err, E_MERGE_DEPTH);
-        const int dn = depth + 1 > 7 ? 7 : depth + 1;
-        // planes / groups of A and changed[] moved.  (b) a changed neighbour itself: all of its pairs;
-        // (a) every voxel Y adjacent to a changed voxel X: only its pair with X can have flipped.
-        for (int q = 0; q < nchg; q++) {
-            const int Yb = changed[q];
-            if (m.cnt[Yb] == 0 || m.evn[Yb] == 0) continue;
-            const int fl = event_floor(m, Yb, scan_id);
-            const int wb = wake_warp(m, Yb, t > fl ? t : fl, scan_id);
-            const int nt = wb == T_INF ? T_INF : next_event_warp(m, Yb, wb);
-            if (nt != T_INF) as_activate(m, ctl, as, Yb, nt, dn);
-            else {
-                // the partner has no pair left that can pass (typically: it now shares A's group): retire its
-                // pending entry right away instead of spending a round on a no-op.  Its entry is not being
-                // processed concurrently: it lies within 1 of A and has a later event.
-                const int n = as.n;
-                for (int k = lane; k < n; k += 32) if ((as.slot[k] & 0x0FFFFFFF) == Yb) as.t[k] = T_INF;
-                __syncwarp();
-            }
-        }
-        const int ncand = (nchg + 1) * 6;
-        for (int c0 = 0; c0 < ncand; c0 += 32) {
-            const int c = c0 + lane;
-            int Y = -1, w = T_INF;
-            if (c < ncand) {
-                const int X = (c / 6 == 0) ? A : changed[c / 6 - 1];
+    const int nchg = merge_at_warp(m, ctl, A, t, scan_id, ws.chg);
+    if (nchg > 0 && depth > MERGE_MAX_DEPTH && lane == 0) atomicOr(&ctl->err, E_MERGE_DEPTH);
+    const int dn = depth + 1 > 7 ? 7 : depth + 1;
+    // task groups of 8 lanes (6 used, one neighbour direction each):
+    //   g = 0            the event's own voxel: earliest time one of its pairs can pass again
+    //   g = 1..nchg      (b) a modified neighbour itself: all of its pairs
+    //   g > nchg         (a) the voxels Y adjacent to X = A / a modified neighbour: only the pair (Y, X) can have flipped
+    const int ngroups = nchg > 0 ? 2 * nchg + 2 : 1;
+    int nq = 0;
+    for (int g0 = 0; g0 < ngroups; g0 += 4) {
+        const int g = g0 + grp;
+        const bool wake_grp = g <= nchg;
+        int Y = -1, w = T_INF;
+        if (g < ngroups && sub < 6) {
+            if (wake_grp) {
+                const int X = g == 0 ? A : ws.chg[g - 1];
+                const unsigned long long keyX = m.skey[X];
+                const VoxRec rx = load_rec(m, X);
+                const int cx = m.cnt[X], ex = m.evn[X];
+                if (g == 0 || (cx != 0 && ex != 0)) {
+                    int after = t;
+                    if (g > 0) { const int fl = event_floor(rx, scan_id); after = t > fl ? t : fl; }
+                    w = wake_dir(m, keyX, rx.mean, rx.nrm, rx.group, sub, after, scan_id);
+                    Y = X;
+                }
+            } else {
+                const int xi = g - nchg - 1;
+                const int X = xi == 0 ? A : ws.chg[xi - 1];
+                const unsigned long long keyX = m.skey[X];
+                const VoxRec rx = load_rec(m, X);
                 bool ok;
-                const unsigned long long nk = nbr_key(m.skey[X], c % 6, ok);
+                const unsigned long long nk = nbr_key(keyX, sub, ok);
                 Y = ok ? hash_find(m, nk) : -1;
-                if (Y == A || (Y >= 0 && (m.cnt[Y] == 0 || m.evn[Y] == 0))) Y = -1;   // no merge() call of Y in this scan
-                for (int q = 0; q < nchg && Y >= 0; q++) if (changed[q] == Y) Y = -1;  // handled by (b)
-                if (Y >= 0 && pair_static(m, Y, X)) {
-                    int s, e;
-                    pair_window(m, X, scan_id, s, e);
-                    const int fl = event_floor(m, Y, scan_id);
-                    int bound = s > t ? s : t;
-                    bound = fl > bound ? fl : bound;
-                    if (bound + 1 < e) w = bound;
+                if (Y == A) Y = -1;
+                for (int q = 0; q < nchg && Y >= 0; q++) if (ws.chg[q] == Y) Y = -1;  // handled by (b)
+                if (Y >= 0) {
+                    const int cy = m.cnt[Y], ey = m.evn[Y];
+                    const VoxRec ry = load_rec(m, Y);
+                    if (cy == 0 || ey == 0) Y = -1;                                   // no merge() call of Y in this scan
+                    else if (pair_static(m, ry.mean, ry.nrm, ry.group, rx)) {
+                        int s0, e0;
+                        pair_window(rx, scan_id, s0, e0);
+                        const int fl = event_floor(ry, scan_id);
+                        int bound = s0 > t ? s0 : t;
+                        bound = fl > bound ? fl : bound;
+                        if (bound + 1 < e0) w = bound;
+                    }
                 }
                 if (w == T_INF) Y = -1;
             }
-            unsigned hotmask = __ballot_sync(0xffffffffu, Y >= 0);
-            while (hotmask) {
-                const int src = __ffs(hotmask) - 1;
-                hotmask &= hotmask - 1;
-                const int Yh = __shfl_sync(0xffffffffu, Y, src);
-                const int wh = __shfl_sync(0xffffffffu, w, src);
-                const int nt = next_event_warp(m, Yh, wh);
-                if (nt != T_INF) as_activate(m, ctl, as, Yh, nt, dn);
+        }
+        int wmin = w;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, wmin, o); wmin = y < wmin ? y : wmin; }
+        // queue the voxels whose next merge() call has to be looked up
+        const bool q_me = g < ngroups && Y >= 0 && (wake_grp ? sub == 0 : true);
+        const unsigned bal = __ballot_sync(0xffffffffu, q_me);
+        if (q_me) {
+            const int pos = nq + __popc(bal & ((1u << lane) - 1));
+            if (pos < FOLLOW_CAP) {
+                ws.tgt[pos] = Y;
+                ws.aft[pos] = wake_grp ? wmin : w;
+                ws.kind[pos] = (unsigned char)(g == 0 ? 0 : wake_grp ? 1 : 2);
             }
         }
+        nq += __popc(bal);
     }
-    // advance A: sleep until the earliest time one of its pairs can pass again, retire it if none can
-    int nt = T_INF;
-    const int w = wake_warp(m, A, t, scan_id);
-    if (w != T_INF) nt = next_event_warp(m, A, w);
-    if (lane == 0) { as.t[j] = nt; atomicAdd(&ctl->dbg[1], 1); }
+    if (nq > FOLLOW_CAP) { if (lane == 0) atomicOr(&ctl->err, E_QUEUE); nq = FOLLOW_CAP; }
+    __syncwarp();
+    // first point index of each queued voxel after its bound: four voxels at a time, eight lanes each
+    for (int q0 = 0; q0 < nq; q0 += 4) {
+        const int q = q0 + grp;
+        int best = T_INF;
+        if (q < nq) {
+            const int Yq = ws.tgt[q], aq = ws.aft[q];
+            if (aq != T_INF) {
+                const int c = m.cnt[Yq], off = m.seg_off[Yq];
+                for (int k = sub; k < c; k += 8) { const int i = m.seg[off + k]; if (i > aq && i < best) best = i; }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
+        if (q < nq && sub == 0) ws.res[q] = best;
+    }
+    __syncwarp();
+    // apply: activations / retirements of the neighbourhood, then A's own next event
+    int ntA = T_INF;
+    for (int q = 0; q < nq; q++) {
+        const int kind = ws.kind[q], Yq = ws.tgt[q], nt = ws.res[q];
+        if (kind == 0) ntA = nt;
+        else if (nt != T_INF) as_activate(m, ctl, as, Yq, nt, dn);
+        else if (kind == 1) {
+            // the partner has no pair left that can pass (typically: it now shares A's group): retire its
+            // pending entry right away instead of spending a round on a no-op.  Its entry is not being
+            // processed concurrently: it lies within 1 of A and has a later event.
+            const int n = as.n;
+            for (int k = lane; k < n; k += 32) if ((as.slot[k] & 0x0FFFFFFF) == Yq) as.t[k] = T_INF;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) { as.t[j] = ntA; atomicAdd(&ctl->dbg[1], 1); }
     __syncwarp();
 }
 
 __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
     __shared__ ActiveSet as;
-    __shared__ int s_cnt;
+    __shared__ WarpScratch wsc[16];
+    __shared__ int s_cnt, s_nready;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = ctl->n_hot;                       // (voxel, first relevant event) pairs prepared by k_merge_prefilter
     if (n0 == 0) return;
@@ -355,7 +436,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
         long long x, y, z;
         unpack_key(m.skey[m.act_slot[0]], x, y, z);
         as.ox = (int)x; as.oy = (int)y; as.oz = (int)z;
-        as.n = n0;
+        as.n = n0; s_nready = 0;
         ctl->dbg[0] = n0;
     }
     __syncthreads();
@@ -368,22 +449,19 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
     __syncthreads();
     for (int round = 0; round < 100000; round++) {
         const int n = as.n;
-        // readiness: no other entry with an earlier event within MERGE_R
-        for (int j = tid; j < n; j += blockDim.x) {
+        // readiness (one warp per entry, lanes over the others): no other entry with an earlier event within MERGE_R
+        for (int j = wid; j < n; j += 16) {
             const int tj = as.t[j];
-            bool rdy = tj != T_INF;
-            if (rdy) {
-                const int x = as.kx[j], y = as.ky[j], z = as.kz[j];
-                for (int i = 0; i < n; i++) {
-                    if (as.t[i] < tj && abs(as.kx[i] - x) + abs(as.ky[i] - y) + abs(as.kz[i] - z) <= MERGE_R) { rdy = false; break; }
-                }
-            }
-            as.ready[j] = rdy ? 1 : 0;
+            if (tj == T_INF) continue;
+            const int x = as.kx[j], y = as.ky[j], z = as.kz[j];
+            bool conflict = false;
+            for (int i = lane; i < n; i += 32)
+                if (as.t[i] < tj && abs(as.kx[i] - x) + abs(as.ky[i] - y) + abs(as.kz[i] - z) <= MERGE_R) conflict = true;
+            if (!__any_sync(0xffffffffu, conflict) && lane == 0) as.rlist[atomicAdd(&s_nready, 1)] = (short)j;
         }
         __syncthreads();
-        for (int j = wid; j < n; j += (blockDim.x >> 5)) {
-            if (as.ready[j]) process_event(m, ctl, as, j, scan_id);      // warp-uniform branch
-        }
+        const int nr = s_nready;
+        for (int q = wid; q < nr; q += 16) process_event(m, ctl, as, wsc[wid], as.rlist[q], scan_id);   // one ready event per warp
         __syncthreads();
         // compaction of retired entries (one warp), keeps the rest in place order
         if (wid == 0) {
@@ -401,7 +479,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
                 w += __popc(bal);
                 __syncwarp();
             }
-            if (lane == 0) { as.n = w; s_cnt = w; }
+            if (lane == 0) { as.n = w; s_cnt = w; s_nready = 0; }
         }
         __syncthreads();
         if (s_cnt == 0) break;
