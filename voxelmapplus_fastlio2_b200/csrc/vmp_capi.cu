@@ -66,6 +66,7 @@ struct vmp_handle_t {
     vmp_config cfg;
     int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
+    SideStream side{};                   // second stream of the map update's side branches
     cudaGraphExec_t graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevMap m{};
@@ -156,7 +157,7 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk) {
         launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1, h->a_sout); k++; mark(mk, VMP_K_MEASURE);
     }
     launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++; mark(mk, VMP_K_WORLD_POINTS);
-    k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false, true, h->a_mout, mk);
+    k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false, true, h->a_mout, mk, &h->side);
     return k;
 }
 
@@ -301,6 +302,8 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     h->sm_count = prop.multiProcessorCount;
     *out = h;       // so that a failed create can still be destroyed by the caller
     VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side.st, cudaStreamNonBlocking));
+    for (auto& e : h->side.ev) VMP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev0));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev1));
 
@@ -407,6 +410,8 @@ int vmp_destroy(vmp_handle h) {
     for (auto& e : h->pev) if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (auto& e : h->side.ev) if (e) cudaEventDestroy(e);
+    if (h->side.st) cudaStreamDestroy(h->side.st);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VMP_OK;
@@ -449,9 +454,9 @@ static int map_update_common(vmp_handle h, const double* pts, const double* cov,
         Marker mk{prof_mark, h};
         h->pev_n = 0;
         VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream));
-        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, &mk);
+        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, &mk, nullptr);
     } else {
-        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, nullptr);
+        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, nullptr, &h->side);
     }
     h->map_built = true;
     r = finish_sync(h);
@@ -610,7 +615,7 @@ int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const floa
     if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
     VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
     launch_world_points(h->stream, h->grid_pts, h->s, h->f, h->ctl, 1);
-    h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true, true, h->a_mout, nullptr);
+    h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true, true, h->a_mout, nullptr, &h->side);
     h->map_built = true;
     r = finish_sync(h);
     fill_update_stats(h->h_mout->st, st);

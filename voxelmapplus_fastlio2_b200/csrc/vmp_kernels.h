@@ -23,9 +23,14 @@ void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevF
 struct Marker { void (*fn)(void* ctx, int id); void* ctx; };
 inline void mark(const Marker* mk, int id) { if (mk && mk->fn) mk->fn(mk->ctx, id); }
 
+// second stream + events for the two side branches of a map update (eviction next to the segment build, LRU-log append
+// next to the merge simulation); null = everything on one stream
+struct SideStream { cudaStream_t st; cudaEvent_t ev[4]; };
+
 // map: returns the number of kernels launched
 // `out`: mailbox written by the update's last kernel (counters, error bits, maintenance requests); may be null
-int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk);
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk,
+                      const SideStream* side);
 int launch_map_maintenance(cudaStream_t st, const DevMap& m, DevCtl* ctl, int sm_count, int what);
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl);
 

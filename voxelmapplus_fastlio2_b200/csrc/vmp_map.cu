@@ -248,22 +248,19 @@ __global__ void __launch_bounds__(1024) k_seg_scan(DevMap m, const DevCtl* ctl) 
 // ------------------------------------------------------------------------- M3b: fill segments
 __global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl) {
     const int n = ctl->n;
-    const unsigned scan_id = ctl->scan_id;
     for (int b = blockIdx.x; b * PT_BLOCK < n; b += gridDim.x) {
         const int i = b * PT_BLOCK + threadIdx.x;
-        int is_last = 0, is_new = 0;
+        int is_last = 0;
         if (i < n) {
             const int slot = m.pslot[i];
             if (slot >= 0) {
                 const int pos = m.seg_off[slot] + atomicAdd(&m.cursor[slot], 1);
                 m.seg[pos] = i;
                 is_last = (m.lt[slot] == i);
-                is_new = (m.ft[slot] == i && m.born_scan[slot] == scan_id);
             }
         }
         const int cl = __syncthreads_count(is_last);
-        const int cn = __syncthreads_count(is_new);
-        if (threadIdx.x == 0) { m.blk_last[b] = cl; m.blk_new[b] = cn; }
+        if (threadIdx.x == 0) m.blk_last[b] = cl;
     }
 }
 
@@ -368,15 +365,13 @@ __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
         // very many new voxels: creation times by ordered compaction over the points, then the serial walk
         int base = 0;
         for (int b = 0; b * PT_BLOCK < n; b++) {
-            const int nb = m.blk_new[b];
-            if (nb == 0) continue;
             const int i = b * PT_BLOCK + tid;
             int f = 0;
             if (i < n) { const int slot = m.pslot[i]; if (slot >= 0) f = (m.ft[slot] == i && m.born_scan[slot] == scan_id); }
             int total;
             const int r = block_excl_scan(f, &total, sh);
             if (f) m.ct[base + r] = i;
-            base += nb;
+            base += total;
         }
         __syncthreads();
         if (tid == 0) lru_serial_walk(m, ctl, m.ct, n_live0, n_new);
@@ -504,24 +499,40 @@ __global__ void __launch_bounds__(256) k_map_finalize(DevMap m, DevCtl* ctl, Map
 }
 
 // ------------------------------------------------------------------------- launcher
-int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk) {
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk,
+                      const SideStream* side) {
     const int gpt = (m.nmax + PT_BLOCK - 1) / PT_BLOCK;               // order-preserving passes: 1024 points / block
     const int gstride = sm_count * 2;
     int launches = 0;
     if (!begun) { k_map_begin<<<1, 1, 0, st>>>(ctl); launches++; mark(mk, VMP_K_MAP_BEGIN); }
     k_map_insert<<<gstride, 256, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_INSERT);
     k_map_count<<<gstride, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_COUNT);
+    // the LRU eviction (one CTA) is independent of the segment build: side branch of the graph
+    const bool fork = side != nullptr && mk == nullptr;
+    if (fork) {
+        cudaEventRecord(side->ev[0], st); cudaStreamWaitEvent(side->st, side->ev[0], 0);
+        k_lru_evict<<<1, 1024, 0, side->st>>>(m, ctl); launches++;
+        cudaEventRecord(side->ev[1], side->st);
+    }
     k_seg_scan<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_SCAN);
     k_seg_fill<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_FILL);
-    k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LRU_EVICT);
+    if (fork) cudaStreamWaitEvent(st, side->ev[1], 0);
+    else { k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LRU_EVICT); }
     k_fill_state<<<sm_count * 4, 128, 0, st>>>(m, s, ctl, build ? 1 : 0); launches++; mark(mk, VMP_K_MAP_FILL);
     k_fill_refit<<<sm_count * 4, 128, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_FILL_REFIT);
     k_fill_acc<<<sm_count * 8, 64, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_FILL_ACC);
+    // the LRU-log append only needs the last-touch times: side branch next to the merge simulation
+    if (fork && !build) {
+        cudaEventRecord(side->ev[2], st); cudaStreamWaitEvent(side->st, side->ev[2], 0);
+        k_log_append<<<gpt, 1024, 0, side->st>>>(m, ctl); launches++;
+        cudaEventRecord(side->ev[3], side->st);
+    }
     if (!build) {
         k_merge_prefilter<<<sm_count, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
         k_merge_rounds<<<1, 512, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
     }
-    k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND);
+    if (fork && !build) cudaStreamWaitEvent(st, side->ev[3], 0);
+    else { k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND); }
     k_map_finalize<<<sm_count, 256, 0, st>>>(m, ctl, out); launches++; mark(mk, VMP_K_MAP_FINALIZE);
     return launches;
 }
