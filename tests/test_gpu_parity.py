@@ -236,7 +236,7 @@ def test_lio_trajectory(oracle_mod):
         assert s1 == s2
         # undistortion is float32 arithmetic on the (1e-9-close) posteriors: identical up to single float32 ulps
         assert np.allclose(c1, c2, rtol=0, atol=2 * float(np.finfo(np.float32).eps) * float(np.abs(c1[:, :3]).max())), "undistorted clouds differ"
-        assert (c1 != c2).mean() < 0.01
+        assert (c1 != c2).mean() < 0.1          # flip rate ~ posterior difference / float32 ulp ~ 1e-9 / 6e-8
         if s1 == 2 and so.iters:
             assert sb.iters == so.iters
             worst_p = max(worst_p, float(np.linalg.norm(np.array(xo.pos[:]) - np.array(xb.pos[:]))))

@@ -99,13 +99,28 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
         return;
     }
     const int pb = (int)blockIdx.x - solve, npb = (int)gridDim.x - solve;      // measurement CTA index / count
-    if (threadIdx.x == 0) {
-        const St x = st_load(f->x);
-        ms.R = x.rot; ms.Rext = x.rot_ext; ms.pext = x.pos_ext;
-        ms.r_wl = mul(x.rot, x.rot_ext);
-        ms.p_wl = add(mul(x.rot, x.pos_ext), x.pos);
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) { ms.Prr(i, j) = f->P[(3 + i) * 23 + 3 + j]; ms.Ppp(i, j) = f->P[i * 23 + j]; }
+    // the pose products and the two covariance blocks every point needs, one entry per thread (same evaluation order
+    // as mul(): s = a0 b0; s += a1 b1; s += a2 b2)
+    {
+        const int t = threadIdx.x;
+        const double* x = f->x;                    // pos3 rot9 rot_ext9 pos_ext3 ...
+        if (t < 9) {
+            const int i = t / 3, j = t % 3;
+            double sacc = x[3 + 3 * i] * x[12 + j];
+            sacc += x[3 + 3 * i + 1] * x[15 + j];
+            sacc += x[3 + 3 * i + 2] * x[18 + j];
+            ms.r_wl.a[t] = sacc;
+        } else if (t < 12) {
+            const int i = t - 9;
+            double sacc = x[3 + 3 * i] * x[21];
+            sacc += x[3 + 3 * i + 1] * x[22];
+            sacc += x[3 + 3 * i + 2] * x[23];
+            ms.p_wl[i] = sacc + x[i];
+        } else if (t < 21) ms.R.a[t - 12] = x[3 + (t - 12)];
+        else if (t < 30) ms.Rext.a[t - 21] = x[12 + (t - 21)];
+        else if (t < 33) ms.pext[t - 30] = x[21 + (t - 30)];
+        else if (t < 42) { const int e = t - 33; ms.Prr.a[e] = f->P[(3 + e / 3) * 23 + 3 + e % 3]; }
+        else if (t < 51) { const int e = t - 42; ms.Ppp.a[e] = f->P[(e / 3) * 23 + e % 3]; }
     }
     __syncthreads();
     const M3 r_wl = ms.r_wl;
@@ -123,8 +138,9 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
         unsigned long long pk;
         int slot = -1;
         if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk)) slot = hash_find(m, pk);
-        M3 cl;
-        bool have_cl = false;
+        M3 cl;                                         // fetched up front: one memory latency less on the chain
+#pragma unroll
+        for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
         bool valid;
         V3 nrm;
         double res;
@@ -141,9 +157,6 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
                 nrm = v3(h[3], h[4], h[5]);
                 const V3 p2m = sub(pw, mean);
                 res = dot(nrm, p2m);
-#pragma unroll
-                for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
-                have_cl = true;
                 const M3 cw = world_cov(r_wl, cl, pl, ms.Prr, ms.Ppp);
                 // sigma_l = J_nq plane_cov J_nq^T (plane_cov is never assigned -> 0, Q1) + n^T C_w n
                 const double sigma = mul(mul(tr(nrm), cw), nrm)[0];
@@ -165,10 +178,6 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
         s.rstatus[i] = status;
         s.rkey[i] = pk;
         if (!valid) continue;
-        if (!have_cl) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
-        }
         // lio_builder.cpp:294-297
         const Mat<1, 3> nt = tr(nrm);
         const double r_cov = mul(mul(mul(mul(nt, r_wl), cl), tr(r_wl)), nrm)[0];

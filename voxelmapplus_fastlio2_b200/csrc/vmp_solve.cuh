@@ -92,47 +92,35 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
-// G = T^-1 for a small D x D matrix in shared memory (LU with partial pivoting + substitution), by one warp:
-// lane i owns row i during the elimination and column i of G during the substitution.  T is destroyed.
+// G = T^-1 for a small D x D matrix in shared memory by one warp: Gauss-Jordan with partial pivoting on the augmented
+// matrix [T | I], lane j < 2D keeps column j in registers (all indices static after unrolling).  One sweep, no
+// substitution phase; a lone warp pays per instruction and per dependent division, and this has D of each.
 template <int D>
-__device__ void warp_small_inverse(double* T, double* G, int* perm) {
+__device__ void warp_small_inverse(const double* T, double* G) {
     const int lane = threadIdx.x & 31;
-    if (lane < D) perm[lane] = lane;
-    __syncwarp();
+    double c[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) c[i] = lane < D ? T[i * D + lane] : (lane - D == i ? 1.0 : 0.0);
+#pragma unroll
     for (int k = 0; k < D; k++) {
-        int piv = k; double best = fabs(T[k * D + k]);           // every lane finds the same pivot
-        for (int i = k + 1; i < D; i++) { const double v = fabs(T[i * D + k]); if (v > best) { best = v; piv = i; } }
-        __syncwarp();
-        if (piv != k) {
-            if (lane < D) { const double t = T[k * D + lane]; T[k * D + lane] = T[piv * D + lane]; T[piv * D + lane] = t; }
-            if (lane == 0) { const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
-            __syncwarp();
-        }
-        if (lane > k && lane < D) {
-            const double l = T[lane * D + k] / T[k * D + k];
-            T[lane * D + k] = l;
-            for (int j = k + 1; j < D; j++) T[lane * D + j] -= l * T[k * D + j];
-        }
-        __syncwarp();
+        int p = k;
+        double best = fabs(c[k]);
+#pragma unroll
+        for (int i = k + 1; i < D; i++) { const double v = fabs(c[i]); if (v > best) { best = v; p = i; } }
+        p = __shfl_sync(0xffffffffu, p, k);                      // the pivot row is decided by the lane that owns column k
+#pragma unroll
+        for (int i = k + 1; i < D; i++) if (i == p) { const double t = c[i]; c[i] = c[k]; c[k] = t; }
+        const double piv = __shfl_sync(0xffffffffu, c[k], k);
+        double fct[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) fct[i] = __shfl_sync(0xffffffffu, c[i], k);   // column k before it is eliminated
+        c[k] = c[k] / piv;
+#pragma unroll
+        for (int i = 0; i < D; i++) if (i != k) c[i] = c[i] - fct[i] * c[k];
     }
-    if (lane < D) {
-        double y[D];
+    if (lane >= D && lane < 2 * D) {
 #pragma unroll
-        for (int i = 0; i < D; i++) {
-            double sacc = (perm[i] == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int j = 0; j < i; j++) sacc -= T[i * D + j] * y[j];
-            y[i] = sacc;
-        }
-#pragma unroll
-        for (int i = D - 1; i >= 0; i--) {
-            double sacc = y[i];
-#pragma unroll
-            for (int j = i + 1; j < D; j++) sacc -= T[i * D + j] * y[j];
-            y[i] = sacc / T[i * D + i];
-        }
-#pragma unroll
-        for (int i = 0; i < D; i++) G[i * D + lane] = y[i];
+        for (int i = 0; i < D; i++) G[i * D + (lane - D)] = c[i];
     }
     __syncwarp();
 }
@@ -155,7 +143,7 @@ __device__ void ieskf_solve_cta(DevFilter* f, DevCtl* ctl, const double* partial
     __shared__ double sMA[D * D], sS[D * D], sTm[D * D], sG[D * D], sW[D * D];
     __shared__ double sQ[NS * D], smm[D], sPm[D], sv[NS];
     __shared__ double sdelta[NS], sdx[NS], sx[36], sxp[36], sJb[22], sAb[22], sLb[22], sBb[22];
-    __shared__ int sperm[D], s_last, s_zero;
+    __shared__ int s_last, s_zero;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int it = ctl->iter;
     const long long t0 = clock64();
@@ -253,7 +241,7 @@ __device__ void ieskf_solve_cta(DevFilter* f, DevCtl* ctl, const double* partial
         sTm[q] = s2;
     }
     __syncthreads();
-    if (wid == 0) warp_small_inverse<D>(sTm, sG, sperm);    // G = (I + P_DD S)^-1
+    if (wid == 0) warp_small_inverse<D>(sTm, sG);           // G = (I + P_DD S)^-1
     __syncthreads();
     for (int q = tid; q < D * D; q += THREADS) {            // W = S G
         const int i = q / D, j = q % D;
