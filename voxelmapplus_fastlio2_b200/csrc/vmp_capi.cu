@@ -67,6 +67,7 @@ struct vmp_handle_t {
     int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
     SideStream side{};                   // second stream of the map update's side branches
+    cudaEvent_t ev_so[2] = {nullptr, nullptr};   // fork / join of the posterior write-out
     cudaGraphExec_t graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevMap m{};
@@ -154,10 +155,21 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk) {
     int k = 0;
     launch_set_scan(st, h->grid_pts, h->s, h->d_in, h->f, h->ctl); k++; mark(mk, VMP_K_SET_SCAN);
     for (int it = 0; it < h->cfg.opti_max_iter; it++) {
-        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1, h->a_sout); k++; mark(mk, VMP_K_MEASURE);
+        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1); k++; mark(mk, VMP_K_MEASURE);
+    }
+    // posterior -> host mailbox on the side stream (joined after the map update, which must not overwrite anything it
+    // reads: f->x / f->P / the iteration counters are only written by the next scan)
+    const bool fork = mk == nullptr;
+    if (fork) {
+        cudaEventRecord(h->ev_so[0], st); cudaStreamWaitEvent(h->side.st, h->ev_so[0], 0);
+        launch_state_out(h->side.st, h->f, h->ctl, h->a_sout); k++;
+        cudaEventRecord(h->ev_so[1], h->side.st);
+    } else {
+        launch_state_out(st, h->f, h->ctl, h->a_sout); k++; mark(mk, VMP_K_SCAN_OUT);
     }
     launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++; mark(mk, VMP_K_WORLD_POINTS);
     k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false, true, h->a_mout, mk, &h->side);
+    if (fork) cudaStreamWaitEvent(st, h->ev_so[1], 0);
     return k;
 }
 
@@ -304,6 +316,7 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side.st, cudaStreamNonBlocking));
     for (auto& e : h->side.ev) VMP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : h->ev_so) VMP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev0));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev1));
 
@@ -411,6 +424,7 @@ int vmp_destroy(vmp_handle h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (auto& e : h->side.ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_so) if (e) cudaEventDestroy(e);
     if (h->side.st) cudaStreamDestroy(h->side.st);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -510,7 +524,7 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, P, sizeof(double) * 529, cudaMemcpyHostToDevice, h->stream));
     k_reset_iter<<<1, 1, 0, h->stream>>>(h->ctl);
     const bool ext = h->cfg.estimate_ext != 0;
-    launch_measure(h->stream, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 0, nullptr);
+    launch_measure(h->stream, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 0);
     k_reduce_partials<<<1, 160, 0, h->stream>>>(h->partials, h->grid_meas, ext ? 1 : 0, h->meas_out);
     h->launches += 3;
     double out[157];

@@ -85,7 +85,7 @@ struct MeasState {
 
 template <bool EXT>
 __global__ void __launch_bounds__(EXT ? 128 : 256)
-k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve, StateOut* sout) {
+k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;                 // upper triangle of H, b, effect count
@@ -95,7 +95,7 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     // launched with solve = 1 the grid has one more CTA: block 0 runs this iteration's 23-dof solve (IESKF::update body,
     // vmp_solve.cuh), starting with the part that needs no measurement while the other CTAs measure
     if (solve && blockIdx.x == 0) {
-        ieskf_solve_cta<EXT, EXT ? 128 : 256>(f, ctl, partials, (int)gridDim.x - 1, sout);
+        ieskf_solve_cta<EXT, EXT ? 128 : 256>(f, ctl, partials, (int)gridDim.x - 1);
         return;
     }
     const int pb = (int)blockIdx.x - solve, npb = (int)gridDim.x - solve;      // measurement CTA index / count
@@ -224,11 +224,28 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     if (threadIdx.x == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
-void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve, StateOut* sout) {
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
     const int g = grid + (solve ? 1 : 0);
-    if (ext) k_measure<true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, sout);
-    else k_measure<false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, sout);
+    if (ext) k_measure<true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve);
+    else k_measure<false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve);
 }
+// The posterior goes to the host mailbox from a side branch of the graph (posted PCIe writes + a system-scope fence cost
+// ~2 us that the map update need not wait for); seq is written last.
+__global__ void __launch_bounds__(256) k_state_out(const DevFilter* __restrict__ f, const DevCtl* __restrict__ ctl, StateOut* out) {
+    const int tid = threadIdx.x;
+    for (int q = tid; q < 529; q += 256) out->P[q] = f->P[q];
+    if (tid < 36) out->x[tid] = f->x[tid];
+    if (tid < 8) out->effect[tid] = ctl->effect[tid];
+    __syncthreads();
+    if (tid == 0) {
+        out->iter = ctl->iter;
+        out->converged = ctl->converged;
+        __threadfence_system();
+        *(volatile unsigned long long*)&out->seq = ctl->seq;
+    }
+}
+void launch_state_out(cudaStream_t st, const DevFilter* f, const DevCtl* ctl, StateOut* out) { k_state_out<<<1, 256, 0, st>>>(f, ctl, out); }
+
 void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const ScanIn* in, DevFilter* f, DevCtl* ctl) { k_set_scan<<<grid, 256, 0, st>>>(s, in, f, ctl); }
 
 // ---------------------------------------------------------------------------- K3

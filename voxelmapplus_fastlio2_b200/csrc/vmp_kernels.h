@@ -13,9 +13,10 @@ constexpr int PT_BLOCK = 1024;          // points per block in the order-preserv
 // IEKF
 // stages one scan from the mailbox `in` (device-accessible): points -> raw / body points / body covariances, prior, counters
 void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const ScanIn* in, DevFilter* f, DevCtl* ctl);
-// solve != 0: one extra CTA runs the 23-dof solve of the iteration (one launch per IEKF iteration) and, when the loop ends,
-// writes the posterior to the mailbox `sout` (may be null)
-void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve, StateOut* sout);
+// solve != 0: one extra CTA runs the 23-dof solve of the iteration (one launch per IEKF iteration)
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve);
+// posterior -> host mailbox (x, P, iteration counters, then seq behind a system-scope fence)
+void launch_state_out(cudaStream_t st, const DevFilter* f, const DevCtl* ctl, StateOut* out);
 // also resets the per-update counters of the map update that follows (begun = true for launch_map_update)
 void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, DevCtl* ctl, int first_scan);
 

@@ -131,7 +131,7 @@ __device__ void warp_small_inverse(const double* T, double* G) {
 //   (B) the D x D algebra, delta_x, boxplus, convergence
 //   (C) only on the last executed iteration: P = (L A)(P - Q P_D)(L A)^T
 template <bool EXT, int THREADS>
-__device__ void ieskf_solve_cta(DevFilter* f, DevCtl* ctl, const double* partials, int nblocks, StateOut* sout) {
+__device__ void ieskf_solve_cta(DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
     static_assert(THREADS >= 128, "the manifold pieces use four warps");
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
@@ -349,19 +349,6 @@ __device__ void ieskf_solve_cta(DevFilter* f, DevCtl* ctl, const double* partial
             double s2 = 0.0;
             for (int k = lo; k < hi; k++) s2 += sT1[i * NS + k] * sB[j * NS + k];
             f->P[q] = s2;
-            if (sout) sout->P[q] = s2;
-        }
-        // the posterior goes straight to the host mailbox; seq is written last, behind a system-scope fence
-        if (sout) {
-            if (tid < 36) sout->x[tid] = sx[tid];
-            if (tid < 8) sout->effect[tid] = ctl->effect[tid];
-            __syncthreads();
-            if (tid == 0) {
-                sout->iter = it + 1;
-                sout->converged = ctl->converged;
-                __threadfence_system();
-                *(volatile unsigned long long*)&sout->seq = ctl->seq;
-            }
         }
         tC = clock64();
     }
