@@ -126,8 +126,6 @@ def algo_bytes(kernel, st_sum, n_pts_sum, iters_sum):
         return 288 * st_sum["refit_points"] + 288 * st_sum["n_refit"]
     if kernel in ("k_merge_prefilter", "k_merge_rounds"):
         return 192 * st_sum["n_merge_voxels"] + 672 * st_sum["n_merge"]
-    if kernel == "k_ieskf_solve":
-        return iters_sum * (148 * 28 * 8 + 3 * 529 * 8)
     return 0
 
 
@@ -182,8 +180,29 @@ def run_ours(args):
     assert n_scans >= W + K, (n_scans, W, K)
     x_e2e, _, _ = lio.state()
     lio.close()
-    h2d = int(clouds[W].nbytes + 8 + 565 * 8)
-    d2h = int(565 * 8 + 48 + 88)
+    h2d = int(4608 + clouds[W].nbytes)           # ScanIn header (prior included) + points, one DMA copy
+    d2h = int(565 * 8 + 56 + 144)                # StateOut + MapOut mailboxes, written by the kernels
+
+    # ---------------- pass 1b: the whole host loop (IMU propagation + undistortion + vmp_scan), synchronous vs pipelined
+    def lio_loop(pipelined):
+        lb = LIOBuilder(cfg, pipelined=pipelined)
+        cl = [pk.cloud.copy() for pk in pkgs]
+        t0 = None
+        done = 0
+        for k, pk in enumerate(pkgs):
+            st = lb.process(pk.imus, cl[k], pk.t0, pk.t1)
+            if t0 is None and st.iters > 0:
+                done += 1
+                if done == W:
+                    lb.map.sync()
+                    t0, k0 = time.perf_counter(), k
+        lb.map.sync()
+        dt = time.perf_counter() - t0
+        n = len(pkgs) - 1 - k0
+        lb.close()
+        return n / dt
+    loop_sync = lio_loop(False)
+    loop_pipe = lio_loop(True)
 
     # ---------------- pass 2: resident replay (scan + prior already in HBM), timed per step with CUDA events
     g = HotPath(cfg)
@@ -253,7 +272,7 @@ def run_ours(args):
         ranked = sorted(prof.items(), key=lambda kv: -kv[1][0])
         top, (top_ms, top_launches) = ranked[0]
         # launches that do work: early-exited IEKF iterations are counted with the executed ones
-        eff_launches = iters_sum if top in ("k_measure", "k_ieskf_solve") else max(1, top_launches)
+        eff_launches = iters_sum if top == "k_measure" else max(1, top_launches)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,7 +316,9 @@ def run_ours(args):
             "e2e": {"value": round(world * K / (e2e_ms_max * 1e-3), 2), "unit": "scans/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "p50_ms": round(float(np.median(e2e_host_ms[W:W + K])), 4),
-                    "timing": "wall clock inside vmp_scan (pinned staging + H2D + graph + D2H + sync)"},
+                    "timing": "wall clock inside the synchronous vmp_scan (pinned staging + one H2D copy + graph + mailbox write-back + sync)"},
+            "host_loop": {"sync_scans_per_s": round(loop_sync, 1), "pipelined_scans_per_s": round(loop_pipe, 1),
+                          "what": "wall clock of the whole LIOBuilder.process loop (host IMU propagation + undistortion + vmp_scan), vmp_set_pipelined off / on"},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
             "roofline": roof,
