@@ -118,7 +118,7 @@ typedef enum vmp_kernel_id {
     VMP_K_SCAN_IN = 0, VMP_K_SET_SCAN, VMP_K_UPDATE_BEGIN, VMP_K_MEASURE, VMP_K_SOLVE, VMP_K_WORLD_POINTS,
     VMP_K_MAP_BEGIN, VMP_K_MAP_INSERT, VMP_K_MAP_COUNT, VMP_K_SEG_SCAN, VMP_K_SEG_FILL, VMP_K_LRU_EVICT,
     VMP_K_MAP_FILL, VMP_K_MERGE_PREFILTER, VMP_K_MERGE_SERIAL, VMP_K_LOG_APPEND, VMP_K_MAP_FINALIZE,
-    VMP_K_MAP_END, VMP_K_REHASH, VMP_K_LOG_COMPACT, VMP_K_SCAN_OUT, VMP_K_FILL_REFIT, VMP_K_FILL_ACC, VMP_K_COUNT
+    VMP_K_MAP_END, VMP_K_REHASH, VMP_K_LOG_COMPACT, VMP_K_SCAN_OUT, VMP_K_FILL_REFIT, VMP_K_FILL_ACC, VMP_K_UNDISTORT, VMP_K_COUNT
 } vmp_kernel_id;
 
 typedef struct vmp_handle_t* vmp_handle;
@@ -174,6 +174,16 @@ int vmp_scan_dev(vmp_handle h, const float* pts_lidar_dev, const double* prior_d
  * vmp_sync) first waits for the pending map update. */
 int vmp_set_pipelined(vmp_handle h, int on);
 int vmp_sync(vmp_handle h);
+
+/* lio::Pose (commons.h:30-43): IMU pose at `offset` seconds after the start of the scan, world-frame acceleration and
+ * body rate valid up to that pose; produced by the IMU propagation loop of LIOBuilder::undistortCloud (lio_builder.cpp:78-112). */
+typedef struct vmp_pose { double offset; double acc[3], gyro[3], vel[3], pos[3], rot[9]; } vmp_pose;
+/* the motion compensation of LIOBuilder::undistortCloud (lio_builder.cpp:75, 127-152) in front of
+ * vmp_scan, on the device, in the same graph.  cloud_xyzt: N x 4 float32 (x, y, z, time offset in ms = the `curvature`
+ * field of pcl::PointXYZINormal), edited in place like the reference edits package.cloud (sorted by time, compensated to
+ * the end-of-scan pose = x, the propagated prior).  poses: 2 <= n_poses <= 64.  Then exactly vmp_scan. */
+int vmp_scan_raw(vmp_handle h, vmp_state* x_inout, double* P_inout, float* cloud_xyzt, int n,
+                 const vmp_pose* poses, int n_poses, vmp_scan_stats* stats);
 int vmp_set_state(vmp_handle h, const vmp_state* x, const double* P);
 int vmp_get_state(vmp_handle h, vmp_state* x, double* P);
 
@@ -223,6 +233,8 @@ int vmp_lio_process(vmp_lio l, const vmp_imu* imus, int n_imu, float* cloud_xyzc
 int vmp_lio_state(vmp_lio l, vmp_state* x, double* P, int* status);
 /* the device handle behind builder->map */
 vmp_handle vmp_lio_map(vmp_lio l);
+/* motion compensation on the device (vmp_scan_raw; default) or on the host like the reference */
+int vmp_lio_set_device_undistort(vmp_lio l, int on);
 /* the prior (x, P after IMU propagation) that the last process() handed to the device update */
 int vmp_lio_prior(vmp_lio l, vmp_state* x, double* P);
 

@@ -283,3 +283,36 @@ def test_pipelined_reports_capacity_error_late():
     g.scan(x, P, big)                                                 # posterior delivered, the update fails behind it
     with pytest.raises(VmpError):
         g.sync()
+
+
+def test_device_undistortion_matches_host(oracle_mod):
+    """SURVEY 8(f) row 1: the point loop of undistortCloud on the device (vmp_scan_raw) against the host loop and the oracle;
+    the second half of the run feeds time-shuffled clouds (the sort of lio_builder.cpp:75)."""
+    cfg = default_config(max_points_per_scan=8192)
+    o = oracle_mod.Oracle(cfg)
+    dev = LIOBuilder(cfg)                                # device compensation (default)
+    host = LIOBuilder(cfg, device_undistort=False)       # host compensation, as before
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=5000))
+    rng = np.random.default_rng(11)
+    eps = float(np.finfo(np.float32).eps)
+    for pk in seq.packages(30):
+        cloud = pk.cloud.copy()
+        if pk.index >= 15:
+            cloud = np.ascontiguousarray(cloud[rng.permutation(len(cloud))])
+        c0, c1, c2 = cloud.copy(), cloud.copy(), cloud.copy()
+        so = o.lio_process(pk.imus, c0, pk.t0, pk.t1)
+        sd = dev.process(pk.imus, c1, pk.t0, pk.t1)
+        sh = host.process(pk.imus, c2, pk.t0, pk.t1)
+        xo, _, s0 = o.lio_state()
+        xd, _, s1 = dev.state()
+        xh, _, s2 = host.state()
+        assert s0 == s1 == s2
+        if s0 < 2 or so.iters == 0:
+            continue
+        assert sd.iters == so.iters == sh.iters
+        tol = 2 * eps * float(np.abs(c0[:, :3]).max())
+        assert np.array_equal(c0[:, 3], c1[:, 3]) and np.array_equal(c0[:, 3], c2[:, 3])      # same time order
+        assert np.allclose(c1, c0, rtol=0, atol=tol) and np.allclose(c1, c2, rtol=0, atol=tol)
+        assert np.linalg.norm(np.array(xd.pos[:]) - np.array(xo.pos[:])) < 1e-3
+        assert np.linalg.norm(np.array(xd.pos[:]) - np.array(xh.pos[:])) < 1e-3
+    assert_maps_equal(o.dump_map(), dev.map.dump_map(), exact=False, rtol=1e-6, what="device-undistorted map")

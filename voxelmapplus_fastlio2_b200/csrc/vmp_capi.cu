@@ -59,7 +59,9 @@ __global__ void k_reset_iter(DevCtl* ctl) { ctl->iter = 0; ctl->done = 0; ctl->c
 
 using namespace vmp;
 
-constexpr size_t IN_HDR = 4608;          // ScanIn rounded up; the points follow at this offset
+constexpr size_t IN_HDR = 4608;          // ScanIn rounded up
+constexpr size_t POSE_BYTES = sizeof(DevPose) * MAX_POSES;
+constexpr size_t PTS_OFF = IN_HDR + POSE_BYTES;      // staging layout: [ScanIn | IMU poses | points (xyz or xyz+time)]
 static_assert(sizeof(ScanIn) <= IN_HDR, "ScanIn outgrew its slot");
 
 struct vmp_handle_t {
@@ -83,7 +85,10 @@ struct vmp_handle_t {
     ScanIn* h_in = nullptr;     ScanIn* d_in = nullptr;
     StateOut* h_sout = nullptr; StateOut* a_sout = nullptr;
     MapOut* h_mout = nullptr;   MapOut* a_mout = nullptr;
-    float* h_raw = nullptr;              // = h_stage + IN_HDR
+    float* h_raw = nullptr;              // = h_stage + PTS_OFF
+    float4* h_cloud = nullptr; float4* a_cloud = nullptr;    // undistorted cloud written by k_undistort (pinned, mapped)
+    cudaGraphExec_t graph_raw = nullptr; // the scan graph with the motion compensation in front
+    int graph_raw_kernels = 0;
     unsigned long long seq = 0;
     bool pipelined = false;              // vmp_set_pipelined: vmp_scan returns when the posterior is out, the map update runs on
     bool map_pending = false;            // a map update whose MapOut has not been consumed yet
@@ -149,10 +154,13 @@ void prof_mark(void* ctx, int id) {
 
 // enqueue every kernel of one scan on h->stream (used both for graph capture and, in
 // profiling mode, directly with an event after each launch)
-int enqueue_scan(vmp_handle_t* h, const Marker* mk) {
+int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw) {
     cudaStream_t st = h->stream;
     const bool ext = h->cfg.estimate_ext != 0;
     int k = 0;
+    if (raw) {      // lio_builder.cpp:127-152 in front of the timed region: the points are compensated where they were uploaded
+        launch_undistort(st, h->grid_pts, h->d_in, (const DevPose*)(h->d_stage + IN_HDR), (float4*)(h->d_stage + PTS_OFF), h->a_cloud); k++; mark(mk, VMP_K_UNDISTORT);
+    }
     launch_set_scan(st, h->grid_pts, h->s, h->d_in, h->f, h->ctl); k++; mark(mk, VMP_K_SET_SCAN);
     for (int it = 0; it < h->cfg.opti_max_iter; it++) {
         launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1); k++; mark(mk, VMP_K_MEASURE);
@@ -174,16 +182,16 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk) {
 }
 
 // run one scan: the instantiated graph, or (profiling) the same kernels one by one
-int run_scan(vmp_handle_t* h) {
+int run_scan(vmp_handle_t* h, bool raw) {
     if (!h->prof_on) {
-        VMP_CUDA_CHECK(cudaGraphLaunch(h->graph, h->stream));
-        h->launches += h->graph_kernels;
+        VMP_CUDA_CHECK(cudaGraphLaunch(raw ? h->graph_raw : h->graph, h->stream));
+        h->launches += raw ? h->graph_raw_kernels : h->graph_kernels;
         return VMP_OK;
     }
     Marker mk{prof_mark, h};
     h->pev_n = 0;
     VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream));
-    h->launches += enqueue_scan(h, &mk);
+    h->launches += enqueue_scan(h, &mk, raw);
     VMP_CUDA_CHECK(cudaGetLastError());
     return VMP_OK;
 }
@@ -203,9 +211,14 @@ void prof_collect(vmp_handle_t* h) {      // after the stream has been synchroni
 int build_graph(vmp_handle_t* h) {
     cudaGraph_t g = nullptr;
     VMP_CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    h->graph_kernels = enqueue_scan(h, nullptr);
+    h->graph_kernels = enqueue_scan(h, nullptr, false);
     VMP_CUDA_CHECK(cudaStreamEndCapture(h->stream, &g));
     VMP_CUDA_CHECK(cudaGraphInstantiate(&h->graph, g, 0));
+    VMP_CUDA_CHECK(cudaGraphDestroy(g));
+    VMP_CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->graph_raw_kernels = enqueue_scan(h, nullptr, true);
+    VMP_CUDA_CHECK(cudaStreamEndCapture(h->stream, &g));
+    VMP_CUDA_CHECK(cudaGraphInstantiate(&h->graph_raw, g, 0));
     VMP_CUDA_CHECK(cudaGraphDestroy(g));
     return VMP_OK;
 }
@@ -360,9 +373,9 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     DALLOC(s.rnorm, (size_t)3 * nmax); DALLOC(s.rmean, (size_t)3 * nmax); DALLOC(s.rres, nmax);
     DALLOC(s.rvalid, nmax); DALLOC(s.rstatus, nmax); DALLOC(s.rkey, nmax);
     DALLOC(s.pw, (size_t)3 * nmax); DALLOC(s.pcov, (size_t)9 * nmax);
-    DALLOC(h->d_stage, IN_HDR + sizeof(float) * 3 * (size_t)nmax + 64);
+    DALLOC(h->d_stage, PTS_OFF + sizeof(float) * 4 * (size_t)nmax + 64);
     h->d_in = (ScanIn*)h->d_stage;
-    s.raw = (float*)(h->d_stage + IN_HDR);
+    DALLOC(s.raw, (size_t)3 * nmax);
     s.range_var = cfg->ranging_cov * cfg->ranging_cov;
     const double sn = sin(cfg->angle_cov * 0.017453293);      // PCL's DEG2RAD (commons.cpp:27-28)
     s.sn2 = sn * sn;
@@ -382,9 +395,11 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     h->grid_meas = std::max(1, std::min(h->sm_count * 2, (nmax + 255) / 256));
     DALLOC(h->partials, (size_t)h->grid_meas * PARTIAL_STRIDE);
     DALLOC(h->meas_out, 160);
-    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_stage, IN_HDR + sizeof(float) * 3 * (size_t)nmax + 64));
+    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_stage, PTS_OFF + sizeof(float) * 4 * (size_t)nmax + 64));
     h->h_in = (ScanIn*)h->h_stage;
-    h->h_raw = (float*)(h->h_stage + IN_HDR);
+    h->h_raw = (float*)(h->h_stage + PTS_OFF);
+    VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_cloud, sizeof(float4) * (size_t)nmax + 64, cudaHostAllocMapped));
+    VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_cloud, h->h_cloud, 0));
     VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_sout, sizeof(StateOut), cudaHostAllocMapped));
     VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_mout, sizeof(MapOut), cudaHostAllocMapped));
     VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_sout, h->h_sout, 0));
@@ -417,6 +432,8 @@ int vmp_destroy(vmp_handle h) {
     if (h->graph) cudaGraphExecDestroy(h->graph);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_cloud) cudaFreeHost(h->h_cloud);
+    if (h->graph_raw) cudaGraphExecDestroy(h->graph_raw);
     if (h->h_sout) cudaFreeHost(h->h_sout);
     if (h->h_mout) cudaFreeHost(h->h_mout);
     for (int b = 0; b < 2; b++) { if (h->pe0[b]) cudaEventDestroy(h->pe0[b]); if (h->pe1[b]) cudaEventDestroy(h->pe1[b]); }
@@ -507,8 +524,9 @@ int vmp_set_scan(vmp_handle h, const float* pts, int n) {
     if (r) return r;
     if (n > 0 && !pts) { set_error("vmp_set_scan: null input"); return VMP_ERR_INVALID_ARG; }
     std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);
-    h->h_in->pts = h->s.raw; h->h_in->prior = nullptr; h->h_in->seq = ++h->seq; h->h_in->n = n; h->h_in->mode = 0;
-    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, IN_HDR + sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->seq = ++h->seq; h->h_in->n = n; h->h_in->mode = 0;
+    h->h_in->n_poses = 0; h->h_in->stride = 3;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, PTS_OFF + sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     h->n_last = n;
     launch_set_scan(h->stream, h->grid_pts, h->s, h->d_in, h->f, h->ctl);
     h->launches += 1;
@@ -538,14 +556,14 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
 
 // launch the scan that h->h_in describes and collect its results: everything (default), or - pipelined - the posterior
 // only, with the map update still running and its counters / errors delivered by the next call
-static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t upload_bytes, vmp_scan_stats* stats) {
+static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t upload_bytes, vmp_scan_stats* stats, bool raw = false) {
     const bool pipe = h->pipelined && !h->prof_on;
     const unsigned long long seq = ++h->seq;
     h->h_in->seq = seq; h->h_in->n = n;
     const int eb = (int)(seq & 1);
     VMP_CUDA_CHECK(cudaEventRecord(h->pe0[eb], h->stream));
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
-    { const int rr = run_scan(h); if (rr) return rr; }
+    { const int rr = run_scan(h, raw); if (rr) return rr; }
     VMP_CUDA_CHECK(cudaEventRecord(h->pe1[eb], h->stream));
     h->n_last = n;
     if (!pipe) {
@@ -588,10 +606,11 @@ int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp
     // header + prior + points go up in ONE DMA copy from pinned staging (SM reads of host memory reach a fraction of the
     // copy engine's PCIe rate, small ones cost a round trip each); the previous scan's copy is long done
     std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);
-    h->h_in->pts = h->s.raw; h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
+    h->h_in->n_poses = 0; h->h_in->stride = 3;
     std::memcpy(h->h_in->x, x, sizeof(double) * 36);
     std::memcpy(h->h_in->P, P, sizeof(double) * 529);
-    r = scan_common(h, x, P, n, IN_HDR + sizeof(float) * 3 * (size_t)n, stats);
+    r = scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 3 * (size_t)n, stats);
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
 }
@@ -604,7 +623,41 @@ int vmp_scan_dev(vmp_handle h, const float* pts_dev, const double* prior_dev, in
     if (!h->map_built) { set_error("vmp_scan_dev: no map yet"); return VMP_ERR_STATE; }
     h->h_in->pts = pts_dev; h->h_in->prior = prior_dev;
     h->h_in->mode = (prior_dev ? SCAN_STATE_DEV : 0) | SCAN_BEGIN_UPDATE;
+    h->h_in->n_poses = 0; h->h_in->stride = 3;
     r = scan_common(h, nullptr, nullptr, n, offsetof(ScanIn, x), stats);
+    if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+    return r;
+}
+
+int vmp_scan_raw(vmp_handle h, vmp_state* x, double* P, float* cloud_xyzt, int n, const vmp_pose* poses, int n_poses, vmp_scan_stats* stats) {
+    const auto t_enter = std::chrono::steady_clock::now();
+    int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan_raw") : check_n(h, n, "vmp_scan_raw");
+    if (r) return r;
+    if (!x || !P || (n > 0 && !cloud_xyzt) || !poses) { set_error("vmp_scan_raw: null argument"); return VMP_ERR_INVALID_ARG; }
+    if (n_poses < 2 || n_poses > MAX_POSES) { set_error("vmp_scan_raw: n_poses=%d outside [2, %d]", n_poses, MAX_POSES); return VMP_ERR_INVALID_ARG; }
+    if (!h->map_built) { set_error("vmp_scan_raw: no map yet (call vmp_first_scan or vmp_map_build first)"); return VMP_ERR_STATE; }
+    static_assert(sizeof(vmp_pose) == sizeof(DevPose), "vmp_pose layout");
+    // one pass over the caller's cloud: copy into the pinned staging and check the time order (lio_builder.cpp:75)
+    float* dst = h->h_raw;
+    bool sorted = true;
+    for (int i = 0; i < n; i++) {
+        const float* p = cloud_xyzt + 4 * (size_t)i;
+        dst[4 * (size_t)i] = p[0]; dst[4 * (size_t)i + 1] = p[1]; dst[4 * (size_t)i + 2] = p[2]; dst[4 * (size_t)i + 3] = p[3];
+        if (i > 0 && p[3] < p[-1]) sorted = false;
+    }
+    if (!sorted) {      // rare for real sensors (points arrive in time order); any order of equal keys is a valid std::sort result
+        struct P4 { float x, y, z, t; };
+        P4* q = reinterpret_cast<P4*>(dst);
+        std::stable_sort(q, q + n, [](const P4& a, const P4& b) { return a.t < b.t; });
+    }
+    std::memcpy(h->h_stage + IN_HDR, poses, sizeof(vmp_pose) * (size_t)n_poses);
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
+    h->h_in->n_poses = n_poses; h->h_in->stride = 4;
+    std::memcpy(h->h_in->x, x, sizeof(double) * 36);
+    std::memcpy(h->h_in->P, P, sizeof(double) * 529);
+    r = scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 4 * (size_t)n, stats, true);
+    // the compensated cloud was written to mapped host memory by the first kernel of the graph, before the posterior
+    std::memcpy(cloud_xyzt, h->h_cloud, sizeof(float) * 4 * (size_t)n);
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
 }
@@ -766,7 +819,7 @@ const char* vmp_kernel_name(int id) {
         "k_scan_in", "k_set_scan", "k_update_begin", "k_measure", "k_ieskf_solve", "k_world_points",
         "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
         "k_fill_state", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
-        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_refit", "k_fill_acc"};
+        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_refit", "k_fill_acc", "k_undistort"};
     return (id >= 0 && id < VMP_K_COUNT) ? names[id] : "?";
 }
 

@@ -96,13 +96,17 @@ constexpr int SCAN_STATE_HDR = 1;       // ScanIn::x / P hold the prior (vmp_sca
 constexpr int SCAN_STATE_DEV = 2;       // ScanIn::prior points at 36 + 529 doubles in device memory (vmp_scan_dev)
 constexpr int SCAN_BEGIN_UPDATE = 4;    // start of IESKF::update: predict_x = x_, iteration counters (ieskf.cpp:127-130)
 struct ScanIn {
-    const float* pts;                   // 3n floats, device-accessible (pinned staging or the caller's device buffer)
+    const float* pts;                   // n points, `stride` floats apart (3: xyz, 4: xyz + time offset), device memory
     const double* prior;
     unsigned long long seq;
     int n, mode;
+    int n_poses, stride;                // raw scans (vmp_scan_raw): IMU poses for the motion compensation follow the header
     double x[36];
     double P[529];
 };
+// lio::Pose (commons.h:30-43) as uploaded for the motion compensation: 22 doubles
+struct DevPose { double offset, acc[3], gyro[3], vel[3], pos[3], rot[9]; };
+constexpr int MAX_POSES = 64;
 struct StateOut {                       // written by the solver CTA when the IEKF loop ends
     double x[36];
     double P[529];

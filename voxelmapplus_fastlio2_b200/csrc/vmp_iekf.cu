@@ -22,14 +22,14 @@ namespace vmp {
 // One kernel stages the whole scan: the header and the points are read straight from the mailbox (pinned host memory or
 // the caller's device buffer), block 0 stages the prior and the counters of IESKF::update (ieskf.cpp:127-130).
 __global__ void __launch_bounds__(256) k_set_scan(DevScan s, const ScanIn* __restrict__ in, DevFilter* f, DevCtl* ctl) {
-    __shared__ float sh[768];
-    __shared__ int s_n, s_mode;
+    __shared__ float sh[1024];
+    __shared__ int s_n, s_mode, s_stride;
     __shared__ const float* s_pts;
     __shared__ const double* s_prior;
     const int tid = threadIdx.x;
-    if (tid == 0) { s_n = in->n; s_mode = in->mode; s_pts = in->pts; s_prior = in->prior; }
+    if (tid == 0) { s_n = in->n; s_mode = in->mode; s_pts = in->pts; s_prior = in->prior; s_stride = in->stride == 4 ? 4 : 3; }
     __syncthreads();
-    const int n = s_n, mode = s_mode;
+    const int n = s_n, mode = s_mode, stride = s_stride;
     const float* pts = s_pts;                      // == s.raw when the host copied the points there itself
     const bool copy_raw = pts != s.raw;
     if (blockIdx.x == 0) {
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(256) k_set_scan(DevScan s, const ScanIn* __res
     const bool al16 = (((size_t)pts) & 15) == 0;
     for (int b = blockIdx.x; b * 256 < n; b += gridDim.x) {
         const int base = b * 256;
-        const int cnt = n - base < 256 ? n - base : 256, nfl = cnt * 3;
-        const float* src = pts + (size_t)base * 3;                   // 3072 b bytes past pts: keeps the 16-byte alignment
+        const int cnt = n - base < 256 ? n - base : 256, nfl = cnt * stride;
+        const float* src = pts + (size_t)base * stride;              // 3072 b or 4096 b bytes past pts: keeps the 16-byte alignment
         if (al16) {
             const int n4 = nfl >> 2;
             if (tid < n4) reinterpret_cast<float4*>(sh)[tid] = reinterpret_cast<const float4*>(src)[tid];
@@ -60,10 +60,10 @@ __global__ void __launch_bounds__(256) k_set_scan(DevScan s, const ScanIn* __res
             for (int q = tid; q < nfl; q += 256) sh[q] = src[q];
         }
         __syncthreads();
-        if (copy_raw) for (int q = tid; q < nfl; q += 256) s.raw[(size_t)base * 3 + q] = sh[q];
+        if (copy_raw) for (int q = tid; q < cnt * 3; q += 256) s.raw[(size_t)base * 3 + q] = sh[(q / 3) * stride + q % 3];
         if (tid < cnt) {
             const int i = base + tid;
-            V3 p = v3((double)sh[3 * tid], (double)sh[3 * tid + 1], (double)sh[3 * tid + 2]);
+            V3 p = v3((double)sh[stride * tid], (double)sh[stride * tid + 1], (double)sh[stride * tid + 2]);
             M3 c;
             calc_body_cov(p, s.range_var, s.sn2, c);
 #pragma unroll
@@ -229,6 +229,50 @@ void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const 
     if (ext) k_measure<true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve);
     else k_measure<false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve);
 }
+// Motion compensation of a raw scan (LIOBuilder::undistortCloud, lio_builder.cpp:127-152) on the device: one thread per
+// point.  The scan is time-sorted; a point at offset t belongs to the last IMU pose `head` with head.offset < t (points at
+// t <= offset of the first pose stay as they are), is carried with head's pose and the next pose's body rates to t and
+// expressed in the lidar frame at the end of the scan (= the propagated prior).  The reference's loop does not stop at
+// the first point: it compensates point 0 once more for every earlier pose interval; reproduced as written.
+// fp64 in the same operation order as the host restatement, result rounded to float like the in-place PCL point.
+__global__ void __launch_bounds__(256) k_undistort(const ScanIn* __restrict__ in, const DevPose* __restrict__ poses, float4* cloud, float4* host_copy) {
+    __shared__ DevPose sp[MAX_POSES];
+    __shared__ double sx[24];
+    const int n = in->n, K = in->n_poses;
+    for (int q = threadIdx.x; q < K * (int)(sizeof(DevPose) / 8); q += blockDim.x) reinterpret_cast<double*>(sp)[q] = reinterpret_cast<const double*>(poses)[q];
+    if (threadIdx.x < 24) sx[threadIdx.x] = in->x[threadIdx.x];          // pos3 rot9 rot_ext9 pos_ext3 of the propagated prior
+    __syncthreads();
+    M3 cur_rot, cur_ext;
+    for (int k = 0; k < 9; k++) { cur_rot.a[k] = sx[3 + k]; cur_ext.a[k] = sx[12 + k]; }
+    const V3 cur_pos = v3(sx[0], sx[1], sx[2]), cur_pext = v3(sx[21], sx[22], sx[23]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = cloud[i];
+        const double t = (double)p.w / double(1000);
+        int h = -1;
+        for (int k = 0; k + 1 < K; k++) if (sp[k].offset < t) h = k;
+        for (; h >= 0; h--) {
+            const DevPose& head = sp[h];
+            const DevPose& tail = sp[h + 1];
+            const double dt = t - head.offset;
+            const V3 point = v3((double)p.x, (double)p.y, (double)p.z);
+            M3 hr;
+            for (int k = 0; k < 9; k++) hr.a[k] = head.rot[k];
+            const M3 point_rot = mul(hr, so3_exp(scale(v3(tail.gyro[0], tail.gyro[1], tail.gyro[2]), dt)));
+            const V3 point_pos = add(add(v3(head.pos[0], head.pos[1], head.pos[2]), scale(v3(head.vel[0], head.vel[1], head.vel[2]), dt)),
+                                     scale(scale(scale(v3(tail.acc[0], tail.acc[1], tail.acc[2]), 0.5), dt), dt));
+            const V3 inner = sub(add(mul(point_rot, add(mul(cur_ext, point), cur_pext)), point_pos), cur_pos);
+            const V3 pc = mul(tr(cur_ext), sub(mul(tr(cur_rot), inner), cur_pext));
+            p.x = (float)pc[0]; p.y = (float)pc[1]; p.z = (float)pc[2];
+            if (i != 0) break;                                        // only the first point is revisited
+        }
+        cloud[i] = p;
+        if (host_copy) host_copy[i] = p;                              // mapped host memory: the caller's cloud is edited in place
+    }
+}
+void launch_undistort(cudaStream_t st, int grid, const ScanIn* in, const DevPose* poses, float4* cloud, float4* host_copy) {
+    k_undistort<<<grid, 256, 0, st>>>(in, poses, cloud, host_copy);
+}
+
 // The posterior goes to the host mailbox from a side branch of the graph (posted PCIe writes + a system-scope fence cost
 // ~2 us that the map update need not wait for); seq is written last.
 __global__ void __launch_bounds__(256) k_state_out(const DevFilter* __restrict__ f, const DevCtl* __restrict__ ctl, StateOut* out) {

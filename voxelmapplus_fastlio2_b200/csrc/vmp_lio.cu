@@ -11,16 +11,15 @@ namespace vmp {
 void set_error(const char* fmt, ...);
 
 namespace {
-// C = A(ra x ca) * B(ca x cb), row-major, left-to-right accumulation (same as mul<>)
-void mm(const double* A, const double* B, double* C, int ra, int ca, int cb) {
-    for (int i = 0; i < ra; i++)
-        for (int j = 0; j < cb; j++) {
-            double s = A[i * ca] * B[j];
-            for (int k = 1; k < ca; k++) s += A[i * ca + k] * B[k * cb + j];
-            C[i * cb + j] = s;
-        }
+// non-zero entries of each row of a small dense matrix, ascending column
+struct SparseRows { int n[23]; int col[23][12]; double val[23][12]; };
+void sparse_rows(const double* M, int rows, int cols, SparseRows& s) {
+    for (int i = 0; i < rows; i++) {
+        int c = 0;
+        for (int j = 0; j < cols; j++) if (M[i * cols + j] != 0.0 && c < 12) { s.col[i][c] = j; s.val[i][c] = M[i * cols + j]; c++; }
+        s.n[i] = c;
+    }
 }
-void mt(const double* A, double* T, int r, int c) { for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) T[j * r + i] = A[i * c + j]; }
 template <int BR, int BC>
 void put(double* M, int ld, int r0, int c0, const Mat<BR, BC>& b) { for (int i = 0; i < BR; i++) for (int j = 0; j < BC; j++) M[(r0 + i) * ld + c0 + j] = b(i, j); }
 }  // namespace
@@ -39,7 +38,7 @@ void IESKF::predict(const V3& acc_in, const V3& gyro_in, double dt, const double
     const V3 drot = scale(w, dt);
     const V3 dvel = scale(add(mul(x_.rot, a), x_.g), dt);
 
-    static thread_local double F[529], G[23 * 12], T1[529], T2[529], Ft[529], Gt[12 * 23], T3[23 * 12];
+    static thread_local double F[529], G[23 * 12], T1[529], T2[529], T3[23 * 12];
     std::memset(F, 0, sizeof(F));
     for (int i = 0; i < 23; i++) F[i * 23 + i] = 1.0;
     put(F, 23, 0, 12, scale(eye<3>(), dt));
@@ -63,14 +62,40 @@ void IESKF::predict(const V3& acc_in, const V3& gyro_in, double dt, const double
     x_.bg = add(x_.bg, zeros<3, 1>());
     x_.ba = add(x_.ba, zeros<3, 1>());
     x_.g = mul(so3_exp(zeros<3, 1>()), x_.g);
-    // P = F P F^T + G Q G^T
-    mm(F, P_, T1, 23, 23, 23);
-    mt(F, Ft, 23, 23);
-    mm(T1, Ft, T2, 23, 23, 23);
-    mm(G, Q, T3, 23, 12, 12);
-    mt(G, Gt, 23, 12);
-    mm(T3, Gt, T1, 23, 12, 23);
-    for (int i = 0; i < 529; i++) P_[i] = T2[i] + T1[i];
+    // P = F P F^T + G Q G^T.  F is the identity plus seven small blocks and G has four, so the products skip the exact
+    // zeros; the remaining terms are taken in the same ascending-k order as the dense left-to-right product
+    // (x + 0*y == x), i.e. the result is the dense one at ~1/8 of the work.
+    static thread_local SparseRows Fs, Gs;
+    sparse_rows(F, 23, 23, Fs);
+    sparse_rows(G, 23, 12, Gs);
+    for (int i = 0; i < 23; i++)                                  // T1 = F P
+        for (int j = 0; j < 23; j++) {
+            double sacc = Fs.val[i][0] * P_[Fs.col[i][0] * 23 + j];
+            for (int e = 1; e < Fs.n[i]; e++) sacc += Fs.val[i][e] * P_[Fs.col[i][e] * 23 + j];
+            T1[i * 23 + j] = sacc;
+        }
+    for (int i = 0; i < 23; i++)                                  // T2 = T1 F^T
+        for (int j = 0; j < 23; j++) {
+            double sacc = T1[i * 23 + Fs.col[j][0]] * Fs.val[j][0];
+            for (int e = 1; e < Fs.n[j]; e++) sacc += T1[i * 23 + Fs.col[j][e]] * Fs.val[j][e];
+            T2[i * 23 + j] = sacc;
+        }
+    std::memset(T3, 0, sizeof(T3));
+    for (int i = 0; i < 23; i++)                                  // T3 = G Q
+        for (int c = 0; c < 12 && Gs.n[i] > 0; c++) {
+            double sacc = Gs.val[i][0] * Q[Gs.col[i][0] * 12 + c];
+            for (int e = 1; e < Gs.n[i]; e++) sacc += Gs.val[i][e] * Q[Gs.col[i][e] * 12 + c];
+            T3[i * 12 + c] = sacc;
+        }
+    for (int i = 0; i < 23; i++)                                  // P = T2 + T3 G^T
+        for (int j = 0; j < 23; j++) {
+            double sacc = 0.0;
+            if (Gs.n[i] > 0 && Gs.n[j] > 0) {
+                sacc = T3[i * 12 + Gs.col[j][0]] * Gs.val[j][0];
+                for (int e = 1; e < Gs.n[j]; e++) sacc += T3[i * 12 + Gs.col[j][e]] * Gs.val[j][e];
+            }
+            P_[i * 23 + j] = T2[i * 23 + j] + sacc;
+        }
 }
 
 LIOBuilder::~LIOBuilder() { if (map) vmp_destroy(map); }
@@ -124,15 +149,16 @@ bool LIOBuilder::initializeImu(std::vector<IMUData>& imus) {
     return true;
 }
 
-// lio_builder.cpp:65-153
-void LIOBuilder::undistortCloud(SyncPackage& package) {
+// lio_builder.cpp:65-153; compensate = false leaves the point loop (:127-152) to the device (vmp_scan_raw)
+void LIOBuilder::undistortCloud(SyncPackage& package, bool compensate) {
     imu_cache.clear();
     imu_cache.push_back(last_imu);
     imu_cache.insert(imu_cache.end(), package.imus.begin(), package.imus.end());
     const double imu_time_end = imu_cache.back().timestamp;
     const double cloud_time_begin = package.cloud_start_time, cloud_time_end = package.cloud_end_time;
-    std::stable_sort(package.cloud.begin(), package.cloud.end(),
-                     [](const CloudPoint& a, const CloudPoint& b) { return a.curvature < b.curvature; });
+    if (compensate)
+        std::stable_sort(package.cloud.begin(), package.cloud.end(),
+                         [](const CloudPoint& a, const CloudPoint& b) { return a.curvature < b.curvature; });
     imu_poses_cache.clear();
     imu_poses_cache.push_back(Pose{0.0, last_acc, last_gyro, kf.x().vel, kf.x().pos, kf.x().rot});
     V3 acc_val = zeros<3, 1>(), gyro_val = zeros<3, 1>();
@@ -158,7 +184,7 @@ void LIOBuilder::undistortCloud(SyncPackage& package) {
 
     const M3 cur_rot = kf.x().rot, cur_rot_ext = kf.x().rot_ext;
     const V3 cur_pos = kf.x().pos, cur_pos_ext = kf.x().pos_ext;
-    if (package.cloud.empty()) return;
+    if (package.cloud.empty() || !compensate) return;
     std::vector<CloudPoint>& pts = package.cloud;
     size_t ip = pts.size() - 1;
     for (size_t kp = imu_poses_cache.size() - 1; kp != 0; kp--) {
@@ -177,6 +203,9 @@ void LIOBuilder::undistortCloud(SyncPackage& package) {
     }
 }
 
+// the device path takes 2..64 poses (one per IMU sample of the scan)
+bool LIOBuilder::imu_poses_fit(const SyncPackage& package) const { return package.imus.size() + 1 >= 2 && package.imus.size() + 1 <= 64; }
+
 // lio_builder.cpp:175-248
 int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
     if (stats) std::memset(stats, 0, sizeof(*stats));
@@ -184,14 +213,32 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
         if (initializeImu(package.imus)) { status = MAP_INIT; last_cloud_end_time = package.cloud_end_time; }
         return VMP_OK;
     }
-    undistortCloud(package);
+    // MAP_INIT (once): everything on the host like the reference.  LIO_MAPPING: IMU propagation on the host, the point
+    // loop of undistortCloud on the device in front of the update, one upload + one graph.
+    const bool on_device = status == LIO_MAPPING && device_undistort && imu_poses_fit(package);
+    undistortCloud(package, !on_device);
     const int n = (int)package.cloud.size();
-    xyz_.resize((size_t)n * 3);
-    for (int i = 0; i < n; i++) { xyz_[3 * i] = package.cloud[i].x; xyz_[3 * i + 1] = package.cloud[i].y; xyz_[3 * i + 2] = package.cloud[i].z; }
     vmp_state xs;
     st_store(kf.x(), reinterpret_cast<double*>(&xs));
     prior_x = xs;
     std::memcpy(prior_P, kf.P(), sizeof(prior_P));
+    if (on_device) {
+        poses_.resize(imu_poses_cache.size());
+        for (size_t k = 0; k < imu_poses_cache.size(); k++) {
+            const Pose& p = imu_poses_cache[k];
+            vmp_pose& q = poses_[k];
+            q.offset = p.offset;
+            for (int c = 0; c < 3; c++) { q.acc[c] = p.acc[c]; q.gyro[c] = p.gyro[c]; q.vel[c] = p.vel[c]; q.pos[c] = p.pos[c]; }
+            for (int c = 0; c < 9; c++) q.rot[c] = p.rot.a[c];
+        }
+        static_assert(sizeof(CloudPoint) == 16, "CloudPoint is x y z t");
+        const int r = vmp_scan_raw(map, &xs, kf.P(), reinterpret_cast<float*>(package.cloud.data()), n, poses_.data(), (int)poses_.size(), stats);
+        if (r) return r;
+        kf.x() = st_load(reinterpret_cast<const double*>(&xs));
+        return VMP_OK;
+    }
+    xyz_.resize((size_t)n * 3);
+    for (int i = 0; i < n; i++) { xyz_[3 * i] = package.cloud[i].x; xyz_[3 * i + 1] = package.cloud[i].y; xyz_[3 * i + 2] = package.cloud[i].z; }
     if (status == MAP_INIT) {
         vmp_update_stats us;
         const int r = vmp_first_scan(map, &xs, kf.P(), xyz_.data(), n, &us);
@@ -246,6 +293,11 @@ int vmp_lio_state(vmp_lio l, vmp_state* x, double* P, int* status) {
     return VMP_OK;
 }
 vmp_handle vmp_lio_map(vmp_lio l) { return l ? l->b.map : nullptr; }
+int vmp_lio_set_device_undistort(vmp_lio l, int on) {
+    if (!l) return VMP_ERR_INVALID_ARG;
+    l->b.device_undistort = on != 0;
+    return VMP_OK;
+}
 int vmp_lio_prior(vmp_lio l, vmp_state* x, double* P) {
     if (!l) return VMP_ERR_INVALID_ARG;
     if (x) *x = l->b.prior_x;

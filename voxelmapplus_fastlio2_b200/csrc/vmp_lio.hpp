@@ -3,9 +3,9 @@
 //   vmp::IESKF        <-> kf::IESKF        (ieskf.h:76-110): x(), P(), predict(); update() runs on the device
 //   vmp::LIOBuilder   <-> lio::LIOBuilder  (lio_builder.h:56-83): loadConfig(), process(), status, kf, map
 //
-// IMU initialisation, IMU propagation and motion undistortion stay on the host exactly as
-// in the reference (lio_builder.cpp:28-153; they are SURVEY.md §8f "next" rows); the timed
-// region lio_builder.cpp:224-246 is one vmp_scan() call, i.e. one CUDA graph launch.
+// IMU initialisation and IMU propagation stay on the host as in the reference (lio_builder.cpp:28-112); the per-point
+// motion compensation (lio_builder.cpp:127-152) and the timed region lio_builder.cpp:224-246 are
+// one vmp_scan_raw() call: one upload, one CUDA graph launch.
 #pragma once
 #include <vector>
 
@@ -41,7 +41,8 @@ public:
     ~LIOBuilder();
     int loadConfig(const vmp_config& cfg);                     // lio_builder.cpp:5-26  (creates the device map)
     bool initializeImu(std::vector<IMUData>& imus);            // lio_builder.cpp:28-63
-    void undistortCloud(SyncPackage& package);                 // lio_builder.cpp:65-153
+    void undistortCloud(SyncPackage& package, bool compensate = true);   // lio_builder.cpp:65-153 (compensate = false: IMU propagation only)
+    bool imu_poses_fit(const SyncPackage& package) const;
     int process(SyncPackage& package, vmp_scan_stats* stats);  // lio_builder.cpp:175-248
 
     IESKF kf;
@@ -56,10 +57,12 @@ public:
     double last_cloud_end_time = 0.0;
     double gravity_norm = 0.0;
     double Q[144];
+    bool device_undistort = true;                              // motion compensation on the device (vmp_scan_raw) once the map exists
     vmp_state prior_x{};                                       // what the last process() handed to the device update
     double prior_P[529] = {};
 private:
     std::vector<float> xyz_;
+    std::vector<vmp_pose> poses_;
 };
 
 }  // namespace vmp
