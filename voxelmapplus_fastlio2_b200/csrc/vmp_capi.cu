@@ -639,12 +639,9 @@ int vmp_scan_raw(vmp_handle h, vmp_state* x, double* P, float* cloud_xyzt, int n
     static_assert(sizeof(vmp_pose) == sizeof(DevPose), "vmp_pose layout");
     // one pass over the caller's cloud: copy into the pinned staging and check the time order (lio_builder.cpp:75)
     float* dst = h->h_raw;
+    std::memcpy(dst, cloud_xyzt, sizeof(float) * 4 * (size_t)n);
     bool sorted = true;
-    for (int i = 0; i < n; i++) {
-        const float* p = cloud_xyzt + 4 * (size_t)i;
-        dst[4 * (size_t)i] = p[0]; dst[4 * (size_t)i + 1] = p[1]; dst[4 * (size_t)i + 2] = p[2]; dst[4 * (size_t)i + 3] = p[3];
-        if (i > 0 && p[3] < p[-1]) sorted = false;
-    }
+    for (int i = 1; i < n; i++) sorted &= !(dst[4 * (size_t)i + 3] < dst[4 * (size_t)i - 1]);
     if (!sorted) {      // rare for real sensors (points arrive in time order); any order of equal keys is a valid std::sort result
         struct P4 { float x, y, z, t; };
         P4* q = reinterpret_cast<P4*>(dst);

@@ -4,6 +4,9 @@
 #include "vmp_lio.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace vmp {
@@ -68,12 +71,17 @@ void IESKF::predict(const V3& acc_in, const V3& gyro_in, double dt, const double
     static thread_local SparseRows Fs, Gs;
     sparse_rows(F, 23, 23, Fs);
     sparse_rows(G, 23, 12, Gs);
-    for (int i = 0; i < 23; i++)                                  // T1 = F P
-        for (int j = 0; j < 23; j++) {
-            double sacc = Fs.val[i][0] * P_[Fs.col[i][0] * 23 + j];
-            for (int e = 1; e < Fs.n[i]; e++) sacc += Fs.val[i][e] * P_[Fs.col[i][e] * 23 + j];
-            T1[i * 23 + j] = sacc;
+    for (int i = 0; i < 23; i++) {                                // T1 = F P, row i as a sum of scaled rows of P (vectorises over j)
+        double* t = T1 + i * 23;
+        const double v0 = Fs.val[i][0];
+        const double* p0 = P_ + Fs.col[i][0] * 23;
+        for (int j = 0; j < 23; j++) t[j] = v0 * p0[j];
+        for (int e = 1; e < Fs.n[i]; e++) {
+            const double v = Fs.val[i][e];
+            const double* pe = P_ + Fs.col[i][e] * 23;
+            for (int j = 0; j < 23; j++) t[j] += v * pe[j];
         }
+    }
     for (int i = 0; i < 23; i++)                                  // T2 = T1 F^T
         for (int j = 0; j < 23; j++) {
             double sacc = T1[i * 23 + Fs.col[j][0]] * Fs.val[j][0];
@@ -157,7 +165,7 @@ void LIOBuilder::undistortCloud(SyncPackage& package, bool compensate) {
     const double imu_time_end = imu_cache.back().timestamp;
     const double cloud_time_begin = package.cloud_start_time, cloud_time_end = package.cloud_end_time;
     if (compensate)
-        std::stable_sort(package.cloud.begin(), package.cloud.end(),
+        std::stable_sort(package.pts(), package.pts() + package.size(),
                          [](const CloudPoint& a, const CloudPoint& b) { return a.curvature < b.curvature; });
     imu_poses_cache.clear();
     imu_poses_cache.push_back(Pose{0.0, last_acc, last_gyro, kf.x().vel, kf.x().pos, kf.x().rot});
@@ -184,9 +192,9 @@ void LIOBuilder::undistortCloud(SyncPackage& package, bool compensate) {
 
     const M3 cur_rot = kf.x().rot, cur_rot_ext = kf.x().rot_ext;
     const V3 cur_pos = kf.x().pos, cur_pos_ext = kf.x().pos_ext;
-    if (package.cloud.empty() || !compensate) return;
-    std::vector<CloudPoint>& pts = package.cloud;
-    size_t ip = pts.size() - 1;
+    if (package.size() == 0 || !compensate) return;
+    CloudPoint* pts = package.pts();
+    size_t ip = package.size() - 1;
     for (size_t kp = imu_poses_cache.size() - 1; kp != 0; kp--) {
         const Pose& head = imu_poses_cache[kp - 1];
         const Pose& tail = imu_poses_cache[kp];
@@ -217,7 +225,7 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
     // loop of undistortCloud on the device in front of the update, one upload + one graph.
     const bool on_device = status == LIO_MAPPING && device_undistort && imu_poses_fit(package);
     undistortCloud(package, !on_device);
-    const int n = (int)package.cloud.size();
+    const int n = (int)package.size();
     vmp_state xs;
     st_store(kf.x(), reinterpret_cast<double*>(&xs));
     prior_x = xs;
@@ -232,13 +240,13 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
             for (int c = 0; c < 9; c++) q.rot[c] = p.rot.a[c];
         }
         static_assert(sizeof(CloudPoint) == 16, "CloudPoint is x y z t");
-        const int r = vmp_scan_raw(map, &xs, kf.P(), reinterpret_cast<float*>(package.cloud.data()), n, poses_.data(), (int)poses_.size(), stats);
+        const int r = vmp_scan_raw(map, &xs, kf.P(), reinterpret_cast<float*>(package.pts()), n, poses_.data(), (int)poses_.size(), stats);
         if (r) return r;
         kf.x() = st_load(reinterpret_cast<const double*>(&xs));
         return VMP_OK;
     }
     xyz_.resize((size_t)n * 3);
-    for (int i = 0; i < n; i++) { xyz_[3 * i] = package.cloud[i].x; xyz_[3 * i + 1] = package.cloud[i].y; xyz_[3 * i + 2] = package.cloud[i].z; }
+    { const CloudPoint* c = package.pts(); for (int i = 0; i < n; i++) { xyz_[3 * i] = c[i].x; xyz_[3 * i + 1] = c[i].y; xyz_[3 * i + 2] = c[i].z; } }
     if (status == MAP_INIT) {
         vmp_update_stats us;
         const int r = vmp_first_scan(map, &xs, kf.P(), xyz_.data(), n, &us);
@@ -278,12 +286,11 @@ int vmp_lio_process(vmp_lio l, const vmp_imu* imus, int n_imu, float* cloud_xyzc
         std::memcpy(pk.imus[i].gyro.a, imus[i].gyro, 24);
         pk.imus[i].timestamp = imus[i].timestamp;
     }
-    pk.cloud.resize((size_t)n);
-    std::memcpy(pk.cloud.data(), cloud_xyzc, sizeof(float) * 4 * (size_t)n);
+    static_assert(sizeof(vmp::CloudPoint) == 4 * sizeof(float), "CloudPoint is x y z t");
+    pk.ext_cloud = reinterpret_cast<vmp::CloudPoint*>(cloud_xyzc);        // process() edits the caller's cloud in place
+    pk.ext_size = (size_t)n;
     pk.cloud_start_time = t0; pk.cloud_end_time = t1;
-    const int r = l->b.process(pk, stats);
-    std::memcpy(cloud_xyzc, pk.cloud.data(), sizeof(float) * 4 * (size_t)n);     // process() edits the cloud in place
-    return r;
+    return l->b.process(pk, stats);
 }
 int vmp_lio_state(vmp_lio l, vmp_state* x, double* P, int* status) {
     if (!l) return VMP_ERR_INVALID_ARG;

@@ -21,6 +21,11 @@ struct SyncPackage {                                           // lio::SyncPacka
     std::vector<IMUData> imus;
     std::vector<CloudPoint> cloud;
     double cloud_start_time = 0.0, cloud_end_time = 0.0;
+    // optional non-owning view used instead of `cloud` (the C wrapper processes the caller's buffer in place, no copies)
+    CloudPoint* ext_cloud = nullptr;
+    size_t ext_size = 0;
+    CloudPoint* pts() { return ext_cloud ? ext_cloud : cloud.data(); }
+    size_t size() const { return ext_cloud ? ext_size : cloud.size(); }
 };
 enum LIOStatus { IMU_INIT = 0, MAP_INIT = 1, LIO_MAPPING = 2 };    // lio_builder.h:10-16
 
