@@ -66,7 +66,8 @@ def full(rep, out):
     lines, traffic = [], {}
     for k, recs in per.items():
         # launches that did work (the IEKF kernels early-exit once the filter has converged)
-        work = [x for x in recs if x.get("warp_inst", 0) > 200] or recs
+        top = max(x.get("warp_inst", 0) for x in recs)
+        work = [x for x in recs if x.get("warp_inst", 0) > 0.1 * top] or recs
         avg = {c: sum(x.get(c, 0.0) for x in work) / len(work) for c in METRICS.values()}
         lines.append([k, len(recs), len(work)] + [round(avg[c], 3) for c in METRICS.values()])
         traffic[k] = round(avg["dram_rd"] + avg["dram_wr"], 1)
