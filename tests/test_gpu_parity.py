@@ -316,3 +316,54 @@ def test_device_undistortion_matches_host(oracle_mod):
         assert np.linalg.norm(np.array(xd.pos[:]) - np.array(xo.pos[:])) < 1e-3
         assert np.linalg.norm(np.array(xd.pos[:]) - np.array(xh.pos[:])) < 1e-3
     assert_maps_equal(o.dump_map(), dev.map.dump_map(), exact=False, rtol=1e-6, what="device-undistorted map")
+
+
+def test_city_run_with_continuous_eviction(oracle_mod):
+    """C3 in small (BASELINE.json configs[2]): drive along a street of scene B at up to 5 m/s with a map capacity far below
+    the voxels seen, so that LRU eviction runs in every scan (tens of thousands of victims over the run).
+    The map is fed with the oracle's world points: counters and evicted keys per scan and the final map are bit-exact.
+    (No free-running comparison here: with so small a map the estimator itself drifts by metres along the street, and two
+    runs that differ in the 9th digit end up in different places; the free-running check under eviction is the next test.)"""
+    cfg = default_config(max_points_per_scan=8192, map_capacity=8000)
+    o = oracle_mod.Oracle(cfg)
+    g = HotPath(cfg)
+    seq = synth.Sequence(scene=synth.scene_city(), traj=synth.Trajectory(centre=(600.0, 612.0, 1.8), ax=80.0, ay=0.5, period=100.0),
+                         sensor=synth.SensorConfig(pts_per_scan=6000))
+    evicted_total = 0
+    for pk in seq.packages(110):
+        c1 = pk.cloud.copy()
+        so = o.lio_process(pk.imus, c1, pk.t0, pk.t1)
+        _, _, s1 = o.lio_state()
+        if s1 < 2 and so.map.n_points == 0:
+            continue
+        pw, pc = o.dump_world_points(len(c1))
+        sg = g.map_build(pw, pc) if so.iters == 0 else g.map_update(pw, pc)
+        for f in ("n_ins", "n_touch", "n_created", "n_refit", "refit_points", "n_full", "n_mergeprobe", "n_merge", "n_evicted", "map_size"):
+            assert sg[f] == getattr(so.map, f), (pk.index, f)
+        assert np.array_equal(o.dump_evicted(), g.dump_evicted()), f"evicted keys differ in scan {pk.index}"
+        evicted_total += sg["n_evicted"]
+    assert evicted_total > 5000, evicted_total
+    assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what="city map, same world points")
+
+
+def test_free_running_with_eviction(oracle_mod):
+    """scene A with a map capacity below the voxels of the hall: eviction active in most scans, free-running estimators
+    (host propagation, device compensation + update) stay within tier 3 and evict the same number of voxels per scan."""
+    cfg = default_config(max_points_per_scan=8192, map_capacity=3000)
+    o = oracle_mod.Oracle(cfg)
+    b = LIOBuilder(cfg)
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=6000))
+    worst_p, evicted_total = 0.0, 0
+    prev = None
+    for pk in seq.packages(80):
+        so = o.lio_process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        sb = b.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        xo, _, s1 = o.lio_state()
+        xb, _, s2 = b.state()
+        assert s1 == s2
+        if s1 == 2 and so.iters:
+            worst_p = max(worst_p, float(np.linalg.norm(np.array(xo.pos[:]) - np.array(xb.pos[:]))))
+            assert sb.map.n_evicted == so.map.n_evicted and sb.map.map_size == so.map.map_size
+            evicted_total += so.map.n_evicted
+    assert evicted_total > 1000, evicted_total
+    assert worst_p < 1e-3, f"trajectory deviates {worst_p} m"
