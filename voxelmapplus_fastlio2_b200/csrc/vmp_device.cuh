@@ -79,6 +79,7 @@ struct DevCtl {
     int max_iter;
     unsigned long long seq;             // sequence number of the current scan (echoed in StateOut / MapOut)
     unsigned fin_ticket;                // arrival counter of k_map_finalize's CTAs (the last one closes the update)
+    unsigned cnt_ticket;                // arrival counter of k_map_count's CTAs (the last one lays out the segments)
 };
 
 // start of a map update: per-update counters (single thread)

@@ -213,8 +213,12 @@ __global__ void __launch_bounds__(256) k_map_insert(DevMap m, DevScan s, DevCtl*
     }
 }
 
-// ------------------------------------------------------------------------- M1b: counts / first / last touch
+// ------------------------------------------------------------------------- M1b: counts / first / last touch, segment offsets
+// The last CTA to finish hands every touched voxel its segment of the per-voxel point lists.  Segments only have to be
+// disjoint (each is selected / sorted by point index later), so there is no ordered scan: warp prefix + one shared
+// atomic per warp.
 __global__ void __launch_bounds__(256) k_map_count(DevMap m, DevCtl* ctl) {
+    __shared__ int s_top, s_last;
     const int n = ctl->n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned h = m.tpos[i];
@@ -227,21 +231,34 @@ __global__ void __launch_bounds__(256) k_map_count(DevMap m, DevCtl* ctl) {
         atomicMin(&m.ft[slot], i);
         atomicMax(&m.lt[slot], i);
     }
-}
-
-// ------------------------------------------------------------------------- M3a: segment offsets
-__global__ void __launch_bounds__(1024) k_seg_scan(DevMap m, const DevCtl* ctl) {
-    __shared__ int sh[34];
-    const int V = ctl->n_touched;
-    int carry = 0;
-    for (int base = 0; base < V; base += 1024) {
-        const int idx = base + threadIdx.x;
-        const int slot = idx < V ? m.touched[idx] : -1;
-        const int v = slot >= 0 ? m.cnt[slot] : 0;
-        int total;
-        const int r = block_excl_scan(v, &total, sh);
-        if (slot >= 0) m.seg_off[slot] = carry + r;
-        carry += total;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&ctl->cnt_ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        if (s_last) { ctl->cnt_ticket = 0; s_top = 0; }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int V = atomicAdd(&ctl->n_touched, 0);
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 4;                                           // voxels per thread per round: independent L2 loads
+    for (int base = 0; base < V; base += blockDim.x * U) {
+        int slot[U], c[U], sum = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int idx = base + threadIdx.x * U + u; slot[u] = idx < V ? __ldcg(&m.touched[idx]) : -1; }
+#pragma unroll
+        for (int u = 0; u < U; u++) { c[u] = slot[u] >= 0 ? __ldcg(&m.cnt[slot[u]]) : 0; sum += c[u]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        int wbase = 0;
+        if (lane == 31) wbase = atomicAdd(&s_top, incl);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        int off = wbase + incl - sum;
+#pragma unroll
+        for (int u = 0; u < U; u++) { if (slot[u] >= 0) m.seg_off[slot[u]] = off; off += c[u]; }
     }
 }
 
@@ -514,7 +531,6 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
         k_lru_evict<<<1, 1024, 0, side->st>>>(m, ctl); launches++;
         cudaEventRecord(side->ev[1], side->st);
     }
-    k_seg_scan<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_SCAN);
     k_seg_fill<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_FILL);
     if (fork) cudaStreamWaitEvent(st, side->ev[1], 0);
     else { k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LRU_EVICT); }
