@@ -296,6 +296,9 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
 
 // updatePlane() body (voxel_map.cpp:100-135) for one batch of 32 stored points of one job
 __global__ void __launch_bounds__(128) k_fill_refit(DevMap m, DevScan s, DevCtl* ctl) {
+    constexpr int TILE_LD = 37;
+    __shared__ double tile_all[4][32 * TILE_LD];
+    double* tile = tile_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
     const int NB = ctl->n_batches < m.bat_cap ? ctl->n_batches : m.bat_cap;
@@ -344,10 +347,16 @@ __global__ void __launch_bounds__(128) k_fill_refit(DevMap m, DevScan s, DevCtl*
             }
             double out[36];
             plane_contrib(p, S, mean, n, evals, evecs, nrm, out);
-            double* dst = m.contrib + ((size_t)m.job_off[j] + q) * 36;
 #pragma unroll
-            for (int k = 0; k < 36; k++) dst[k] = out[k];
+            for (int k = 0; k < 36; k++) tile[lane * TILE_LD + k] = out[k];
         }
+        // the batch's contributions are one contiguous block of <= 32 x 36 doubles: written cooperatively, fully
+        // coalesced (one 288-byte record per lane would touch 36 separate sectors per store instruction)
+        __syncwarp();
+        const int np = (nt - bi * 32) < 32 ? (nt - bi * 32) : 32;
+        double* dst = m.contrib + ((size_t)m.job_off[j] + (size_t)bi * 32) * 36;
+        for (int e = lane; e < np * 36; e += 32) dst[e] = tile[(e / 36) * TILE_LD + e % 36];
+        __syncwarp();
     }
 }
 

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) k_map_count(DevMap m, DevCtl* ctl) {
     __threadfence();
     const int V = atomicAdd(&ctl->n_touched, 0);
     const int lane = threadIdx.x & 31;
-    constexpr int U = 4;                                           // voxels per thread per round: independent L2 loads
+    constexpr int U = 16;                                          // voxels per thread per round: independent L2 loads
     for (int base = 0; base < V; base += blockDim.x * U) {
         int slot[U], c[U], sum = 0;
 #pragma unroll
