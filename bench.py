@@ -44,17 +44,20 @@ def log(*a):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md).
+
+    One streaming nvidia-smi (-lms 20) is started EARLY (its start-up takes longer than the ~50 ms timed region of the
+    default run); every sample is time-stamped and only those inside [mark_begin, stop] are reported.  If the window is
+    shorter than the sampling period the nearest sample on either side (GPU busy with the same steps) is used and flagged."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self.reasons = set()
+        self.samples = []          # (t, sm, sm_max, reasons)
         self._halt = threading.Event()
+        self.t_begin = None
 
     def run(self):
-        # one streaming nvidia-smi (-lms 20): the timed region of the default run is only ~0.1 s long
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -67,24 +70,38 @@ class ClockSampler(threading.Thread):
         for line in self.proc.stdout:
             out = line.strip().split(",")
             try:
-                self.samples.append((float(out[0]), float(out[1])))
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                rs = [n for n, v in zip(names, out[2:]) if v.strip().lower().startswith("active")]
+                self.samples.append((time.perf_counter(), float(out[0]), float(out[1]), rs))
             except Exception:
                 pass
             if self._halt.is_set():
                 break
 
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
     def stop(self):
+        t_end = time.perf_counter()
+        time.sleep(0.03)           # let the sample that covers the end of the window arrive
         self._halt.set()
         if getattr(self, "proc", None) is not None:
             self.proc.terminate()
         self.join(timeout=5)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons), "samples": len(sm)}
+        t0 = self.t_begin if self.t_begin is not None else self.samples[0][0]
+        inside = [x for x in self.samples if t0 <= x[0] <= t_end]
+        note = None
+        if not inside:
+            mid = 0.5 * (t0 + t_end)
+            inside = sorted(self.samples, key=lambda x: abs(x[0] - mid))[:2]
+            note = "timed region shorter than the 20 ms sampling period: nearest samples (same steps running)"
+        sm = sorted(x[1] for x in inside)
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": inside[0][2], "reasons": sorted({r for x in inside for r in x[3]}),
+               "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def make_packages(wl, seed, count):
@@ -201,6 +218,8 @@ def run_ours(args):
         n = len(pkgs) - 1 - k0
         lb.close()
         return n / dt
+    sampler = ClockSampler(local)
+    sampler.start()                      # streaming from here on; the reported window opens at step W of pass 2
     loop_host = lio_loop(False, device_undistort=False)
     loop_sync = lio_loop(False)
     loop_pipe = lio_loop(True)
@@ -213,7 +232,6 @@ def run_ours(args):
     d_priors = [torch.from_numpy(p).to(dev) for p in priors]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
     res_ms, res_stats = [], []
     launches_timed = 0
     for i in range(n_scans):
@@ -221,7 +239,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
-            sampler.start()
+            sampler.mark_begin()
             launches0 = g.launch_count()
             t_wall0 = time.perf_counter()
         if i == W + K:
