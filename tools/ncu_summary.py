@@ -1,6 +1,6 @@
 """Summarise an .ncu-rep (ncu --set full) into a per-kernel table + profiles/traffic.json.
 
-  python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_ncu_full            -> .csv / .md / traffic.json
+  python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_ncu_full [c2]       -> .csv / .md / traffic.json[workload]
   python tools/ncu_summary.py --launches gpurun_out/launches.csv profiles/r01_launches  -> per-kernel share of the step
 """
 import csv
@@ -45,7 +45,7 @@ def short(name):
     return n.split("<")[0] + ("<1>" if "<1>" in n or "<true>" in n else "")
 
 
-def full(rep, out):
+def full(rep, out, key="c2"):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -82,7 +82,7 @@ def full(rep, out):
         f.write("\ntensor_inst = 0 everywhere: the path is a gather/reduction, tensor cores are not used (DESIGN.md §4).\n")
     tpath = os.path.join(os.path.dirname(out), "traffic.json")
     old = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    old.update({k.replace("<1>", ""): v for k, v in traffic.items()})
+    old.setdefault(key, {}).update({k.replace("<1>", ""): v for k, v in traffic.items()})   # keyed by bench workload
     json.dump(old, open(tpath, "w"), indent=1, sort_keys=True)
     print("wrote", out + ".csv", out + ".md", tpath)
 
@@ -111,4 +111,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "--launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        full(sys.argv[1], sys.argv[2])
+        full(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "c2")

@@ -392,7 +392,11 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     VMP_CUDA_CHECK(cudaMemsetAsync(h->f, 0, sizeof(DevFilter), h->stream));
     VMP_CUDA_CHECK(cudaMemsetAsync(h->ctl, 0, sizeof(DevCtl), h->stream));
     h->grid_pts = std::max(1, std::min(h->sm_count * 2, (nmax + 255) / 256));
-    h->grid_meas = std::max(1, std::min(h->sm_count * 2, (nmax + 255) / 256));
+    {
+        const int tpb = cfg->estimate_ext ? 128 : 256;
+        const int occ = cfg->estimate_ext ? 4 : 2;       // resident measurement CTAs per SM (k_measure's launch bounds)
+        h->grid_meas = std::max(1, std::min(h->sm_count * occ, (nmax + tpb - 1) / tpb));
+    }
     DALLOC(h->partials, (size_t)h->grid_meas * PARTIAL_STRIDE);
     DALLOC(h->meas_out, 160);
     VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_stage, PTS_OFF + sizeof(float) * 4 * (size_t)nmax + 64));

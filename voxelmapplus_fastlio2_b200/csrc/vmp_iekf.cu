@@ -83,21 +83,43 @@ struct MeasState {
     V3 p_wl, pext;
 };
 
+// Shared memory of a measurement CTA: the pose products every point needs, the per-warp staging of (J, w J, residual) for
+// the lane-parallel accumulation, and the per-warp sums.  SP is odd, so 64-bit accesses of a half-warp never share a bank.
 template <bool EXT>
-__global__ void __launch_bounds__(EXT ? 128 : 256)
+struct MeasShared {
+    static constexpr int D = EXT ? 12 : 6;
+    static constexpr int NV = D * (D + 1) / 2 + D + 1;
+    static constexpr int SP = 2 * D + 1;
+    static constexpr int NW = (EXT ? 128 : 256) / 32;
+    MeasState ms;
+    double red[NW][NV];
+    double stage[NW][32 * SP];
+};
+
+// Two resident CTAs per SM (four of the 128-thread estimate_ext variant): 128 registers, no spills.  Three (80 registers,
+// 196 B of spills) measured the same at 200 k points and slower at 20 k.
+template <bool EXT>
+__global__ void __launch_bounds__(EXT ? 128 : 256, EXT ? 4 : 2)
 k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;                 // upper triangle of H, b, effect count
-    __shared__ MeasState ms;
-    __shared__ double red[8][NV];
+    constexpr int NA = NV - 1;                     // accumulated products
+    constexpr int SP = MeasShared<EXT>::SP;
+    constexpr int NW = MeasShared<EXT>::NW;
+    constexpr int VPL = (NA + 31) / 32;            // accumulated values per lane
+    // a CTA is either the solver or a measurement CTA: one overlay for both (static shared memory is limited to 48 KB)
+    union Overlay { SolveShared<EXT> sol; MeasShared<EXT> meas; };
+    __shared__ __align__(16) unsigned char sh_raw[sizeof(Overlay)];
     if (ctl->done) return;
     // launched with solve = 1 the grid has one more CTA: block 0 runs this iteration's 23-dof solve (IESKF::update body,
     // vmp_solve.cuh), starting with the part that needs no measurement while the other CTAs measure
     if (solve && blockIdx.x == 0) {
-        ieskf_solve_cta<EXT, EXT ? 128 : 256>(f, ctl, partials, (int)gridDim.x - 1);
+        ieskf_solve_cta<EXT, EXT ? 128 : 256>(*reinterpret_cast<SolveShared<EXT>*>(sh_raw), f, ctl, partials, (int)gridDim.x - 1);
         return;
     }
+    MeasShared<EXT>& sh = *reinterpret_cast<MeasShared<EXT>*>(sh_raw);
+    MeasState& ms = sh.ms;
     const int pb = (int)blockIdx.x - solve, npb = (int)gridDim.x - solve;      // measurement CTA index / count
     // the pose products and the two covariance blocks every point needs, one entry per thread (same evaluation order
     // as mul(): s = a0 b0; s += a1 b1; s += a2 b2)
@@ -122,99 +144,121 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
         else if (t < 42) { const int e = t - 33; ms.Prr.a[e] = f->P[(3 + e / 3) * 23 + 3 + e % 3]; }
         else if (t < 51) { const int e = t - 42; ms.Ppp.a[e] = f->P[(e / 3) * 23 + e % 3]; }
     }
-    __syncthreads();
-    const M3 r_wl = ms.r_wl;
-    const V3 p_wl = ms.p_wl;
     const int n = ctl->n;
+    __syncthreads();
     const size_t NM = (size_t)s.nmax;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* const stg = sh.stage[wid];
 
-    double acc[NV];
+    // H^T R^-1 H / H^T R^-1 z are accumulated by the warp, not by the thread: every lane stages (J, w J, r) of its valid
+    // point in shared memory, then lane v sums ITS entry (a, c) of the upper triangle (or entry a of b) over the staged
+    // points in index order.  One accumulator per lane instead of NV per thread (the kernel was register-bound at one CTA
+    // per SM) and no shuffle tree at the end; the order of the sum is fixed: points in index order inside a warp's batch,
+    // batches in order, warps in order, CTAs in the solver's fixed order.
+    int offA[VPL], offB[VPL];
 #pragma unroll
-    for (int v = 0; v < NV; v++) acc[v] = 0.0;
+    for (int q = 0; q < VPL; q++) {
+        const int v = lane + 32 * q;
+        int a = 0, c = 0, isb = 0;
+        if (v < NH) {
+            int rem = v;
+            while (rem >= D - a) { rem -= D - a; a++; }
+            c = a + rem;
+        } else if (v < NA) { a = v - NH; isb = 1; }
+        offA[q] = D + a;                            // w J[a]
+        offB[q] = isb ? 2 * D : c;                  // J[c] or the residual
+    }
+    double acc[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; q++) acc[q] = 0.0;
+    int cnt = 0;
 
-    for (int i = pb * blockDim.x + threadIdx.x; i < n; i += npb * blockDim.x) {
-        const V3 pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
-        const V3 pw = add(mul(r_wl, pl), p_wl);
-        unsigned long long pk;
-        int slot = -1;
-        if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk)) slot = hash_find(m, pk);
-        M3 cl;                                         // fetched up front: one memory latency less on the chain
+    for (int base = (pb * NW + wid) * 32; base < n; base += npb * NW * 32) {
+        const int i = base + lane;
+        bool valid = false;
+        if (i < n) {
+            const V3 pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
+            const V3 pw = add(mul(ms.r_wl, pl), ms.p_wl);
+            unsigned long long pk;
+            int slot = -1;
+            if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk)) slot = hash_find(m, pk);
+            M3 cl;                                         // fetched up front: one memory latency less on the chain
 #pragma unroll
-        for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
-        bool valid;
-        V3 nrm;
-        double res;
-        uint8_t status = 0;
-        if (slot >= 0) {
-            status = 1;
-            valid = false;
-            const double* h = m.hot + (size_t)slot * 8;
-            uint32_t flags; int nn;
-            hot_get_fn(m.hot, slot, flags, nn);
-            if (flags & F_PLANE) {
-                status |= 2;
-                const V3 mean = v3(h[0], h[1], h[2]);
-                nrm = v3(h[3], h[4], h[5]);
-                const V3 p2m = sub(pw, mean);
-                res = dot(nrm, p2m);
-                const M3 cw = world_cov(r_wl, cl, pl, ms.Prr, ms.Ppp);
-                // sigma_l = J_nq plane_cov J_nq^T (plane_cov is never assigned -> 0, Q1) + n^T C_w n
-                const double sigma = mul(mul(tr(nrm), cw), nrm)[0];
-                valid = fabs(res) < 3.0 * sqrt(sigma);
+            for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
+            V3 nrm;
+            double res;
+            uint8_t status = 0;
+            if (slot >= 0) {
+                status = 1;
+                const double* h = m.hot + (size_t)slot * 8;
+                uint32_t flags; int nn;
+                hot_get_fn(m.hot, slot, flags, nn);
+                if (flags & F_PLANE) {
+                    status |= 2;
+                    const V3 mean = v3(h[0], h[1], h[2]);
+                    nrm = v3(h[3], h[4], h[5]);
+                    const V3 p2m = sub(pw, mean);
+                    res = dot(nrm, p2m);
+                    const M3 cw = world_cov(ms.r_wl, cl, pl, ms.Prr, ms.Ppp);
+                    // sigma_l = J_nq plane_cov J_nq^T (plane_cov is never assigned -> 0, Q1) + n^T C_w n
+                    const double sigma = mul(mul(tr(nrm), cw), nrm)[0];
+                    valid = fabs(res) < 3.0 * sqrt(sigma);
 #pragma unroll
-                for (int k = 0; k < 3; k++) { s.rnorm[(size_t)k * NM + i] = nrm[k]; s.rmean[(size_t)k * NM + i] = mean[k]; }
-                s.rres[i] = res;
+                    for (int k = 0; k < 3; k++) { s.rnorm[(size_t)k * NM + i] = nrm[k]; s.rmean[(size_t)k * NM + i] = mean[k]; }
+                    s.rres[i] = res;
+                }
+                s.rvalid[i] = valid ? 1 : 0;
+            } else {
+                // Q2: voxel not in the map -> the record keeps whatever an earlier pass left in it
+                valid = s.rvalid[i] != 0;
+                if (valid) {
+                    nrm = v3(s.rnorm[i], s.rnorm[NM + i], s.rnorm[2 * NM + i]);
+                    res = s.rres[i];
+                }
             }
-            s.rvalid[i] = valid ? 1 : 0;
-        } else {
-            // Q2: voxel not in the map -> the record keeps whatever an earlier pass left in it
-            valid = s.rvalid[i] != 0;
+            if (valid) status |= 4;
+            s.rstatus[i] = status;
+            s.rkey[i] = pk;
             if (valid) {
-                nrm = v3(s.rnorm[i], s.rnorm[NM + i], s.rnorm[2 * NM + i]);
-                res = s.rres[i];
+                // lio_builder.cpp:294-297
+                const Mat<1, 3> nt = tr(nrm);
+                const double r_cov = mul(mul(mul(mul(nt, ms.r_wl), cl), tr(ms.r_wl)), nrm)[0];
+                const double r_info = r_cov < 0.0002 ? 5000 : 1.0 / r_cov;
+                double J[D];
+                J[0] = nrm[0]; J[1] = nrm[1]; J[2] = nrm[2];
+                const Mat<1, 3> jr = mul(mul(neg(nt), ms.R), hat(add(mul(ms.Rext, pl), ms.pext)));
+                J[3] = jr[0]; J[4] = jr[1]; J[5] = jr[2];
+                if (EXT) {
+                    const Mat<1, 3> je = mul(mul(neg(nt), ms.r_wl), hat(pl));
+                    const Mat<1, 3> jp = mul(nt, ms.R);
+                    J[6] = je[0]; J[7] = je[1]; J[8] = je[2];
+                    J[D - 3] = jp[0]; J[D - 2] = jp[1]; J[D - 1] = jp[2];
+                }
+                double* sp = stg + lane * SP;
+#pragma unroll
+                for (int a = 0; a < D; a++) { sp[a] = J[a]; sp[D + a] = J[a] * r_info; }
+                sp[2 * D] = res;
             }
         }
-        if (valid) status |= 4;
-        s.rstatus[i] = status;
-        s.rkey[i] = pk;
-        if (!valid) continue;
-        // lio_builder.cpp:294-297
-        const Mat<1, 3> nt = tr(nrm);
-        const double r_cov = mul(mul(mul(mul(nt, r_wl), cl), tr(r_wl)), nrm)[0];
-        const double r_info = r_cov < 0.0002 ? 5000 : 1.0 / r_cov;
-        double J[D];
-        J[0] = nrm[0]; J[1] = nrm[1]; J[2] = nrm[2];
-        const Mat<1, 3> jr = mul(mul(neg(nt), ms.R), hat(add(mul(ms.Rext, pl), ms.pext)));
-        J[3] = jr[0]; J[4] = jr[1]; J[5] = jr[2];
-        if (EXT) {
-            const Mat<1, 3> je = mul(mul(neg(nt), r_wl), hat(pl));
-            const Mat<1, 3> jp = mul(nt, ms.R);
-            J[6] = je[0]; J[7] = je[1]; J[8] = je[2];
-            J[D - 3] = jp[0]; J[D - 2] = jp[1]; J[D - 1] = jp[2];
+        unsigned mask = __ballot_sync(0xffffffffu, valid);
+        cnt += __popc(mask);
+        __syncwarp();
+        for (; mask; mask &= mask - 1) {
+            const double* sp = stg + (__ffs(mask) - 1) * SP;
+#pragma unroll
+            for (int q = 0; q < VPL; q++) acc[q] += sp[offA[q]] * sp[offB[q]];
         }
-        int v = 0;
-#pragma unroll
-        for (int a = 0; a < D; a++) {
-            const double ja = J[a] * r_info;
-#pragma unroll
-            for (int c = a; c < D; c++) acc[v++] += ja * J[c];
-        }
-#pragma unroll
-        for (int a = 0; a < D; a++) acc[NH + a] += (J[a] * r_info) * res;
-        acc[NH + D] += 1.0;
+        __syncwarp();
     }
 
-    // warp shuffle -> shared -> one partial vector per block; fixed order everywhere
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // per-warp sums -> shared -> one partial vector per block; fixed order everywhere
 #pragma unroll
-    for (int v = 0; v < NV; v++) {
-        const double t = warp_sum(acc[v]);
-        if (lane == 0) red[wid][v] = t;
-    }
+    for (int q = 0; q < VPL; q++) { const int v = lane + 32 * q; if (v < NA) sh.red[wid][v] = acc[q]; }
+    if (lane == 0) sh.red[wid][NA] = (double)cnt;
     __syncthreads();
     for (int v = threadIdx.x; v < NV; v += blockDim.x) {
-        double t = red[0][v];
-        for (int w = 1; w < nw; w++) t += red[w][v];
+        double t = sh.red[0][v];
+        for (int w = 1; w < NW; w++) t += sh.red[w][v];
         partials[(size_t)pb * PARTIAL_STRIDE + v] = t;
     }
     if (!solve) return;

@@ -130,20 +130,37 @@ __device__ void warp_small_inverse(const double* T, double* G) {
 //   (W) wait for the nblocks measurement CTAs (ctl->ticket), then reduce their partial sums in a fixed order
 //   (B) the D x D algebra, delta_x, boxplus, convergence
 //   (C) only on the last executed iteration: P = (L A)(P - Q P_D)(L A)^T
+// shared memory of the solver CTA; k_measure overlays it with the staging of its measurement CTAs (a CTA is one or the other)
+template <bool EXT>
+struct SolveShared {
+    static constexpr int D = EXT ? 12 : 6;
+    static constexpr int NH = D * (D + 1) / 2;
+    static constexpr int NV = NH + D + 1;
+    static constexpr int NVP = (NV + 31) / 32 * 32;           // values padded to whole warps
+    static constexpr int RP = EXT ? 4 : 8;                   // block subsets of the partial-sum reduction
+    double sP[NE], sPn[NE], sT1[NE], sA[NE], sB[NE];
+    double sHm[NV], sRed[RP][NVP];
+    double sMA[D * D], sS[D * D], sTm[D * D], sG[D * D], sW[D * D];
+    double sQ[NS * D], smm[D], sPm[D], sv[NS];
+    double sdelta[NS], sdx[NS], sx[36], sxp[36], sJb[22], sAb[22], sLb[22], sBb[22];
+    int s_last, s_zero;
+};
+
 template <bool EXT, int THREADS>
-__device__ void ieskf_solve_cta(DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
+__device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
     static_assert(THREADS >= 128, "the manifold pieces use four warps");
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;
-    __shared__ double sP[NE], sPn[NE], sT1[NE], sA[NE], sB[NE];
-    constexpr int NVP = (NV + 31) / 32 * 32;           // values padded to whole warps
-    constexpr int RP = EXT ? 4 : 8;                   // block subsets of the partial-sum reduction
-    __shared__ double sHm[NV], sRed[RP][NVP];
-    __shared__ double sMA[D * D], sS[D * D], sTm[D * D], sG[D * D], sW[D * D];
-    __shared__ double sQ[NS * D], smm[D], sPm[D], sv[NS];
-    __shared__ double sdelta[NS], sdx[NS], sx[36], sxp[36], sJb[22], sAb[22], sLb[22], sBb[22];
-    __shared__ int s_last, s_zero;
+    constexpr int NVP = SolveShared<EXT>::NVP;
+    constexpr int RP = SolveShared<EXT>::RP;
+    auto& sP = S.sP; auto& sPn = S.sPn; auto& sT1 = S.sT1; auto& sA = S.sA; auto& sB = S.sB;
+    auto& sHm = S.sHm; auto& sRed = S.sRed;
+    auto& sMA = S.sMA; auto& sS = S.sS; auto& sTm = S.sTm; auto& sG = S.sG; auto& sW = S.sW;
+    auto& sQ = S.sQ; auto& smm = S.smm; auto& sPm = S.sPm; auto& sv = S.sv;
+    auto& sdelta = S.sdelta; auto& sdx = S.sdx; auto& sx = S.sx; auto& sxp = S.sxp;
+    auto& sJb = S.sJb; auto& sAb = S.sAb; auto& sLb = S.sLb; auto& sBb = S.sBb;
+    int& s_last = S.s_last; int& s_zero = S.s_zero;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int it = ctl->iter;
     const long long t0 = clock64();
@@ -174,19 +191,24 @@ __device__ void ieskf_solve_cta(DevFilter* f, DevCtl* ctl, const double* partial
     }
     __syncthreads();
     const long long tW = stamp(&s_zero);
-    // fixed-order reduction of the per-CTA partial sums: RP interleaved block subsets per value, all loads independent
+    // fixed-order reduction of the per-CTA partial sums: RP interleaved block subsets per value; a subset is summed in
+    // block order, eight independent loads in flight at a time (the loop used to wait for one L2 round trip per two blocks)
     for (int q = tid; q < NVP * RP; q += THREADS) {
         const int v = q % NVP, part = q / NVP;
-        double t0s = 0.0, t1s = 0.0;
+        double t = 0.0;
         if (v < NV) {
-            int b = part;
-            for (; b + RP < nblocks; b += 2 * RP) {
-                t0s += __ldcg(&partials[(size_t)b * PARTIAL_STRIDE + v]);
-                t1s += __ldcg(&partials[(size_t)(b + RP) * PARTIAL_STRIDE + v]);
+            for (int b = part; b < nblocks; b += 8 * RP) {
+                double xs[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int bb = b + u * RP;
+                    xs[u] = bb < nblocks ? __ldcg(&partials[(size_t)bb * PARTIAL_STRIDE + v]) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) t += xs[u];
             }
-            if (b < nblocks) t0s += __ldcg(&partials[(size_t)b * PARTIAL_STRIDE + v]);
         }
-        sRed[part][v] = t0s + t1s;
+        sRed[part][v] = t;
     }
     __syncthreads();
     for (int v = tid; v < NV; v += THREADS) {

@@ -277,12 +277,13 @@ class Sequence:
         cloud[:, 3] = (off[ok] * 1000.0).astype(np.float32)
         return cloud, t0
 
-    def packages(self, n: int, start: int = 0):
-        """Generator over packages start..start+n-1 (keeps the IMU hand-over consistent and cheap)."""
+    def packages(self, n: int, start: int = 0, clouds: dict | None = None):
+        """Generator over packages start..start+n-1 (keeps the IMU hand-over consistent and cheap).
+        `clouds` may hold precomputed `cloud(i)` results (index -> (cloud, t0)), e.g. made by a process pool."""
         s = self.sensor
         prev_end = None
         for i in range(start, start + n):
-            cloud, t0 = self.cloud(i)
+            cloud, t0 = clouds[i] if clouds is not None and i in clouds else self.cloud(i)
             t1 = t0 + float(cloud[-1, 3]) / 1000.0
             if prev_end is None:
                 if i == 0:
