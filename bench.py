@@ -273,7 +273,7 @@ def measure_workload(args, wl, pkgs, W, K, rank, world, local, full=True):
     sampler = ClockSampler(local)
     sampler.start()                      # streaming from here on; the reported window opens at step W of pass 2
     loop_host = loop_sync = loop_pipe = None
-    if full:
+    if full and not args.no_loops:
         loop_host = lio_loop(False, device_undistort=False)
         loop_sync = lio_loop(False)
         loop_pipe = lio_loop(True)
@@ -391,7 +391,7 @@ def measure_workload(args, wl, pkgs, W, K, rank, world, local, full=True):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "p50_ms": round(float(np.median(e2e_host_ms[W:W + K])), 4),
                     "timing": "wall clock inside the synchronous vmp_scan (pinned staging + one H2D copy + graph + mailbox write-back + sync)"},
-            "host_loop": None if not full else {
+            "host_loop": None if loop_host is None else {
                           "host_undistort_scans_per_s": round(loop_host, 1), "sync_scans_per_s": round(loop_sync, 1),
                           "pipelined_scans_per_s": round(loop_pipe, 1),
                           "what": "wall clock of the whole LIOBuilder.process loop, lio_builder.cpp:65-246 (host IMU propagation, motion "
@@ -478,6 +478,7 @@ def main():
     ap.add_argument("--c1-steps", type=int, default=None)
     ap.add_argument("--cpu-scans", type=int, default=300, help="bound of the CPU sample (scans)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-loops", action="store_true", help="skip the whole-host-loop pass (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -41,7 +41,8 @@ typedef struct vmp_config {
     double p_il[3];                  /* zero */
     int    gravity_align;            /* 1 */
     int    estimate_ext;             /* 0 */
-    double scan_resolution;          /* 0.1; <=0 means "no downsample" (lio_builder.cpp:215-223) */
+    double scan_resolution;          /* 0.1; <=0 means "no downsample" (lio_builder.cpp:215-223); > 0: pcl::VoxelGrid leaf size,
+                                        applied by vmp_scan_raw / vmp_lio_process on the device (vmp_downsample) */
     double voxel_size;               /* 0.5 */
     int    update_size_thresh;       /* 10 */
     int    max_point_thresh;         /* 100 */
@@ -118,7 +119,7 @@ typedef enum vmp_kernel_id {
     VMP_K_SCAN_IN = 0, VMP_K_SET_SCAN, VMP_K_UPDATE_BEGIN, VMP_K_MEASURE, VMP_K_SOLVE, VMP_K_WORLD_POINTS,
     VMP_K_MAP_BEGIN, VMP_K_MAP_INSERT, VMP_K_MAP_COUNT, VMP_K_SEG_SCAN, VMP_K_SEG_FILL, VMP_K_LRU_EVICT,
     VMP_K_MAP_FILL, VMP_K_MERGE_PREFILTER, VMP_K_MERGE_SERIAL, VMP_K_LOG_APPEND, VMP_K_MAP_FINALIZE,
-    VMP_K_MAP_END, VMP_K_REHASH, VMP_K_LOG_COMPACT, VMP_K_SCAN_OUT, VMP_K_FILL_REFIT, VMP_K_FILL_ACC, VMP_K_UNDISTORT, VMP_K_COUNT
+    VMP_K_MAP_END, VMP_K_REHASH, VMP_K_LOG_COMPACT, VMP_K_SCAN_OUT, VMP_K_FILL_REFIT, VMP_K_FILL_ACC, VMP_K_UNDISTORT, VMP_K_DOWNSAMPLE, VMP_K_COUNT
 } vmp_kernel_id;
 
 typedef struct vmp_handle_t* vmp_handle;
@@ -184,6 +185,14 @@ typedef struct vmp_pose { double offset; double acc[3], gyro[3], vel[3], pos[3],
  * the end-of-scan pose = x, the propagated prior).  poses: 2 <= n_poses <= 64.  Then exactly vmp_scan. */
 int vmp_scan_raw(vmp_handle h, vmp_state* x_inout, double* P_inout, float* cloud_xyzt, int n,
                  const vmp_pose* poses, int n_poses, vmp_scan_stats* stats);
+/* SURVEY.md 8(f) row 1, second half: scan_filter.filter() = pcl::VoxelGrid<PointXYZINormal>::filter with leaf size
+ * (leaf, leaf, leaf) (lio_builder.cpp:13-14, 215-219) on the device.  cloud_xyzc: N x 4 float32 (x, y, z, curvature).
+ * out_xyzc: up to cap leaf centroids (x, y, z, mean curvature) in ascending leaf-index order, *m = number of leaves.
+ * Points inside a leaf are summed in their original order (PCL's std::sort leaves that order unspecified).  With
+ * cfg.scan_resolution > 0, vmp_scan_raw runs this between the motion compensation and the update, and the filter sees
+ * the leaf centroids; vmp_get_lidar_cloud returns them (LIOBuilder::lidar_cloud, lio_builder.h:83). */
+int vmp_downsample(vmp_handle h, const float* cloud_xyzc, int n, double leaf, float* out_xyzc, int cap, int* m);
+int vmp_get_lidar_cloud(vmp_handle h, float* out_xyzc, int cap, int* m);
 int vmp_set_state(vmp_handle h, const vmp_state* x, const double* P);
 int vmp_get_state(vmp_handle h, vmp_state* x, double* P);
 

@@ -2,6 +2,9 @@
 // CPU restatement of the reference hot path; every function cites what it follows.
 #include "oracle.h"
 
+#include <cfloat>
+#include <climits>
+
 #include <algorithm>
 #include <cassert>
 #include <cstdio>
@@ -587,6 +590,63 @@ std::vector<CloudPoint> LIOBuilder::lidarToWorld(const std::vector<CloudPoint>& 
     return out;
 }
 
+// pcl::VoxelGrid<PointT>::applyFilter (PCL 1.10 filters/impl/voxel_grid.hpp, restated from its published algorithm; PCL is
+// not in this image and the reference does not pin its version: "parity unpinned").  Call site: lio_builder.cpp:215-219.
+//   * bounding box of the finite points (getMinMax3D), float32
+//   * if the leaf grid would overflow int32 PCL warns and returns the input unchanged
+//   * leaf index ijk = floor(p * inverse_leaf) - min_b per axis, linear idx = i + j*dx + k*dx*dy
+//   * std::sort by idx; the order of equal keys is unspecified in PCL -> this restatement keeps the original point
+//     order inside a leaf (a valid outcome of std::sort and the one the device reproduces)
+//   * one output point per leaf in ascending idx order = CentroidPoint: float32 sums in that order, divided by n
+//     (AccumulatorXYZ / AccumulatorCurvature; intensity and normal are not read downstream and not carried here)
+std::vector<CloudPoint> LIOBuilder::voxelGridFilter(const std::vector<CloudPoint>& cloud, float leaf) {
+    const float inv = 1.0f / leaf;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    size_t n_finite = 0;
+    for (const CloudPoint& p : cloud) {
+        if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+        const float v[3] = {p.x, p.y, p.z};
+        for (int a = 0; a < 3; a++) { if (v[a] < mn[a]) mn[a] = v[a]; if (v[a] > mx[a]) mx[a] = v[a]; }
+        n_finite++;
+    }
+    std::vector<CloudPoint> out;
+    if (n_finite == 0) return out;
+    int64_t d[3];
+    for (int a = 0; a < 3; a++) d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
+    if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) return cloud;       // "Leaf size is too small": output = input
+    int min_b[3], max_b[3], div_b[3];
+    for (int a = 0; a < 3; a++) {
+        min_b[a] = (int)std::floor(mn[a] * inv);
+        max_b[a] = (int)std::floor(mx[a] * inv);
+        div_b[a] = max_b[a] - min_b[a] + 1;
+    }
+    const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];
+    std::vector<std::pair<unsigned, unsigned>> iv;                   // (idx, cloud_point_index)
+    iv.reserve(cloud.size());
+    for (size_t i = 0; i < cloud.size(); i++) {
+        const CloudPoint& p = cloud[i];
+        if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+        const int i0 = (int)(std::floor(p.x * inv) - (float)min_b[0]);
+        const int i1 = (int)(std::floor(p.y * inv) - (float)min_b[1]);
+        const int i2 = (int)(std::floor(p.z * inv) - (float)min_b[2]);
+        iv.emplace_back((unsigned)(i0 + i1 * mul1 + i2 * mul2), (unsigned)i);
+    }
+    std::stable_sort(iv.begin(), iv.end(), [](const std::pair<unsigned, unsigned>& a, const std::pair<unsigned, unsigned>& b) { return a.first < b.first; });
+    for (size_t first = 0; first < iv.size();) {
+        size_t last = first + 1;
+        while (last < iv.size() && iv[last].first == iv[first].first) last++;
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f, sc = 0.0f;
+        for (size_t l = first; l < last; l++) {
+            const CloudPoint& p = cloud[iv[l].second];
+            sx += p.x; sy += p.y; sz += p.z; sc += p.curvature;
+        }
+        const float cnt = (float)(last - first);
+        out.push_back(CloudPoint{sx / cnt, sy / cnt, sz / cnt, sc / cnt});
+        first = last;
+    }
+    return out;
+}
+
 // MAP_INIT body, lio_builder.cpp:188-208
 void LIOBuilder::firstScan(const std::vector<CloudPoint>& cloud) {
     prior_x = kf.x();
@@ -666,12 +726,11 @@ void LIOBuilder::process(SyncPackage& package) {
     } else {
         undistortCloud(package);
         if (config.scan_resolution > 0.0) {
-            // pcl::VoxelGrid leaf-centroid downsample: intra-leaf float accumulation order is
-            // implementation-defined in PCL -> not part of the parity path.
-            std::fprintf(stderr, "oracle: scan_resolution > 0 is not on the parity path; use scan_resolution <= 0\n");
-            std::abort();
+            // scan_filter.setLeafSize(r, r, r) takes floats (lio_builder.cpp:13-14)
+            setScan(voxelGridFilter(package.cloud, (float)config.scan_resolution));
+        } else {
+            setScan(package.cloud);                     // pcl::copyPointCloud
         }
-        setScan(package.cloud);
         hotPath();
     }
 }

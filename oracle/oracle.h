@@ -216,6 +216,8 @@ public:
     void process(SyncPackage& package);                    // lio_builder.cpp:175-248
     void sharedUpdateFunc(State& state, SharedState& shared);   // lio_builder.cpp:250-311
     std::vector<CloudPoint> lidarToWorld(const std::vector<CloudPoint>& cloud);   // lio_builder.cpp:155-163
+    // scan_filter.filter() = pcl::VoxelGrid<PointXYZINormal>::applyFilter (lio_builder.cpp:13-14, 215-219)
+    static std::vector<CloudPoint> voxelGridFilter(const std::vector<CloudPoint>& cloud, float leaf);
 
     // the pieces of process() the C ABI exposes separately
     void firstScan(const std::vector<CloudPoint>& cloud);  // MAP_INIT body, lio_builder.cpp:188-208

@@ -235,8 +235,11 @@ int orc_lio_process(void* h, const vmp_imu* imus, int n_imu, float* cloud_xyzc, 
         // same as process(), with the clock around the timed region lio_builder.cpp:224-246
         l.undistortCloud(pk);
         if (n > l.config.max_points_per_scan) return VMP_ERR_INVALID_ARG;
+        std::vector<CloudPoint> filtered;                 // scan_filter.filter (lio_builder.cpp:215-219), outside the timed region
+        const bool ds = l.config.scan_resolution > 0.0;
+        if (ds) filtered = LIOBuilder::voxelGridFilter(pk.cloud, (float)l.config.scan_resolution);
         auto c0 = std::chrono::steady_clock::now();
-        l.setScan(pk.cloud);
+        l.setScan(ds ? filtered : pk.cloud);
         l.hotPath();
         auto c1 = std::chrono::steady_clock::now();
         ms = std::chrono::duration<double, std::milli>(c1 - c0).count();
@@ -245,6 +248,23 @@ int orc_lio_process(void* h, const vmp_imu* imus, int n_imu, float* cloud_xyzc, 
     }
     for (int i = 0; i < n; i++) { cloud_xyzc[4 * i] = pk.cloud[i].x; cloud_xyzc[4 * i + 1] = pk.cloud[i].y; cloud_xyzc[4 * i + 2] = pk.cloud[i].z; cloud_xyzc[4 * i + 3] = pk.cloud[i].curvature; }
     fill_scan_stats(l, st, ms);
+    return VMP_OK;
+}
+// pcl::VoxelGrid leaf-centroid filter on an N x 4 float cloud (x y z curvature); out: up to cap points, *m = leaf count
+int orc_downsample(void* h, const float* cloud_xyzc, int n, double leaf, float* out_xyzc, int cap, int* m) {
+    (void)h;
+    std::vector<CloudPoint> c((size_t)n);
+    for (int i = 0; i < n; i++) c[i] = CloudPoint{cloud_xyzc[4 * i], cloud_xyzc[4 * i + 1], cloud_xyzc[4 * i + 2], cloud_xyzc[4 * i + 3]};
+    const std::vector<CloudPoint> o = LIOBuilder::voxelGridFilter(c, (float)leaf);
+    for (size_t i = 0; i < o.size() && (int)i < cap; i++) { out_xyzc[4 * i] = o[i].x; out_xyzc[4 * i + 1] = o[i].y; out_xyzc[4 * i + 2] = o[i].z; out_xyzc[4 * i + 3] = o[i].curvature; }
+    if (m) *m = (int)o.size();
+    return VMP_OK;
+}
+// LIOBuilder::lidar_cloud of the last scan (the filter input; downsampled when scan_resolution > 0)
+int orc_get_lidar_cloud(void* h, float* out_xyzc, int cap, int* m) {
+    const std::vector<CloudPoint>& o = H(h)->lio.lidar_cloud;
+    for (size_t i = 0; i < o.size() && (int)i < cap; i++) { out_xyzc[4 * i] = o[i].x; out_xyzc[4 * i + 1] = o[i].y; out_xyzc[4 * i + 2] = o[i].z; out_xyzc[4 * i + 3] = o[i].curvature; }
+    if (m) *m = (int)o.size();
     return VMP_OK;
 }
 int orc_lio_state(void* h, vmp_state* x, double* P, int* status) {

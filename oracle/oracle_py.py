@@ -76,6 +76,8 @@ class Oracle(HotPath):
         self._n = cloud_xyzc.shape[0]
         self._check(self._lib.orc_lio_process(self._h, imus.ctypes.data_as(C.POINTER(VmpImu)), imus.shape[0],
                                               fptr(cloud_xyzc), cloud_xyzc.shape[0], t0, t1, C.byref(st)))
+        if self.cfg.scan_resolution > 0 and st.iters > 0:
+            self._n = self.lidar_cloud().shape[0]
         return st
 
     def lio_state(self):

@@ -71,7 +71,7 @@ def test_struct_layouts_match_header():
     lib.vmp_kernel_name.restype = C.c_char_p
     lib.vmp_kernel_name.argtypes = [C.c_int]
     names = [lib.vmp_kernel_name(k).decode() for k in range(K_COUNT)]
-    assert names[0] == "k_scan_in" and names[-1] == "k_undistort" and "?" not in names
+    assert names[0] == "k_scan_in" and names[-1] == "k_downsample" and names[-2] == "k_undistort" and "?" not in names
     assert lib.vmp_kernel_name(K_COUNT).decode() == "?"
 
 

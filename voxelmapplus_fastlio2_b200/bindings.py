@@ -80,6 +80,8 @@ class HotPath:
             "dump_map": [vp, C.POINTER(VmpPlane), C.c_int, ip],
             "dump_evicted": [vp, C.POINTER(C.c_int64), C.c_int, ip],
             "map_size": [vp, ip],
+            "downsample": [vp, fp, C.c_int, C.c_double, fp, C.c_int, ip],
+            "get_lidar_cloud": [vp, fp, C.c_int, ip],
         }
         for name, args in sig.items():
             f = self._fn(name)
@@ -170,6 +172,23 @@ class HotPath:
         P = np.zeros((23, 23))
         self._check(self._fn("get_state")(self._h, C.byref(x), dptr(P)))
         return x, P
+
+    # -- pre-processing ----------------------------------------
+    def downsample(self, cloud_xyzc, leaf: float) -> np.ndarray:
+        """scan_filter.filter(): pcl::VoxelGrid leaf-centroid filter (lio_builder.cpp:13-14, 215-219) -> M x 4 float32."""
+        c = np.ascontiguousarray(cloud_xyzc, dtype=np.float32).reshape(-1, 4)
+        out = np.zeros((max(c.shape[0], 1), 4), np.float32)
+        m = C.c_int(0)
+        self._check(self._fn("downsample")(self._h, fptr(c), c.shape[0], float(leaf), fptr(out), c.shape[0], C.byref(m)))
+        return out[:m.value].copy()
+
+    def lidar_cloud(self, cap: int | None = None) -> np.ndarray:
+        """LIOBuilder::lidar_cloud of the last raw scan (the filter input; leaf centroids when scan_resolution > 0)."""
+        cap = self.cfg.max_points_per_scan if cap is None else cap
+        out = np.zeros((max(cap, 1), 4), np.float32)
+        m = C.c_int(0)
+        self._check(self._fn("get_lidar_cloud")(self._h, fptr(out), cap, C.byref(m)))
+        return out[:m.value].copy()
 
     # -- observation -------------------------------------------------------------
     def dump_correspondences(self, n=None):

@@ -87,6 +87,11 @@ struct vmp_handle_t {
     MapOut* h_mout = nullptr;   MapOut* a_mout = nullptr;
     float* h_raw = nullptr;              // = h_stage + PTS_OFF
     float4* h_cloud = nullptr; float4* a_cloud = nullptr;    // undistorted cloud written by k_undistort (pinned, mapped)
+    DevDown ds{};                        // pcl::VoxelGrid downsample scratch (vmp_downsample.cu)
+    float4* h_ds = nullptr; float4* a_ds = nullptr;          // filtered cloud = LIOBuilder::lidar_cloud (pinned, mapped)
+    int* h_ds_m = nullptr; int* a_ds_m = nullptr;
+    bool ds_valid = false;               // the last scan went through the downsample
+    bool last_raw = false;               // the last scan was a vmp_scan_raw (its compensated cloud is in h_cloud)
     cudaGraphExec_t graph_raw = nullptr; // the scan graph with the motion compensation in front
     int graph_raw_kernels = 0;
     unsigned long long seq = 0;
@@ -182,7 +187,27 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw) {
 }
 
 // run one scan: the instantiated graph, or (profiling) the same kernels one by one
-int run_scan(vmp_handle_t* h, bool raw) {
+int run_scan(vmp_handle_t* h, bool raw, int n_raw = 0) {
+    const bool ds = raw && h->cfg.scan_resolution > 0.0;
+    h->ds_valid = ds;
+    h->last_raw = raw;
+    if (ds) {
+        // lio_builder.cpp:127-152 + 215-219 in front of the update: the sort inside the filter is sized by the caller's point
+        // count, so these launches are not part of the instantiated graph; the filter's last kernel redirects the scan header
+        // (n, points, stride) to the leaf centroids and the plain scan graph follows
+        Marker mk{prof_mark, h};
+        if (h->prof_on) { h->pev_n = 0; VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream)); }
+        launch_undistort(h->stream, h->grid_pts, h->d_in, (const DevPose*)(h->d_stage + IN_HDR), (float4*)(h->d_stage + PTS_OFF), h->a_cloud);
+        if (h->prof_on) mark(&mk, VMP_K_UNDISTORT);
+        h->launches += 1 + launch_downsample(h->stream, h->ds, (const float4*)(h->d_stage + PTS_OFF), &h->d_in->n, n_raw, (float)h->cfg.scan_resolution,
+                                             h->grid_pts, h->a_ds, h->a_ds_m, h->d_in, h->prof_on ? &mk : nullptr);
+        raw = false;
+        if (h->prof_on) {
+            h->launches += enqueue_scan(h, &mk, false);
+            VMP_CUDA_CHECK(cudaGetLastError());
+            return VMP_OK;
+        }
+    }
     if (!h->prof_on) {
         VMP_CUDA_CHECK(cudaGraphLaunch(raw ? h->graph_raw : h->graph, h->stream));
         h->launches += raw ? h->graph_raw_kernels : h->graph_kernels;
@@ -388,6 +413,21 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     VMP_CUDA_CHECK(cudaMemsetAsync(s.pl, 0, sizeof(double) * 3 * nmax, h->stream));
     VMP_CUDA_CHECK(cudaMemsetAsync(s.cl, 0, sizeof(double) * 9 * nmax, h->stream));
 
+    {
+        DevDown& d = h->ds;
+        DALLOC(d.mm, 8); DALLOC(d.keys[0], nmax); DALLOC(d.keys[1], nmax); DALLOC(d.vals[0], nmax); DALLOC(d.vals[1], nmax);
+        DALLOC(d.head, nmax); DALLOC(d.rank, nmax); DALLOC(d.out, nmax); DALLOC(d.m, 1);
+        d.temp_bytes = downsample_temp_bytes(nmax);
+        unsigned char* tmp = nullptr;
+        DALLOC(tmp, d.temp_bytes);
+        d.temp = tmp;
+        VMP_CUDA_CHECK(cudaMemsetAsync(d.mm, 0, sizeof(unsigned) * 8, h->stream));
+        VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_ds, sizeof(float4) * (size_t)nmax + 64, cudaHostAllocMapped));
+        VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_ds, h->h_ds, 0));
+        VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_ds_m, 64, cudaHostAllocMapped));
+        VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_ds_m, h->h_ds_m, 0));
+        *h->h_ds_m = 0;
+    }
     DALLOC(h->f, 1); DALLOC(h->ctl, 1);
     VMP_CUDA_CHECK(cudaMemsetAsync(h->f, 0, sizeof(DevFilter), h->stream));
     VMP_CUDA_CHECK(cudaMemsetAsync(h->ctl, 0, sizeof(DevCtl), h->stream));
@@ -437,6 +477,8 @@ int vmp_destroy(vmp_handle h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_cloud) cudaFreeHost(h->h_cloud);
+    if (h->h_ds) cudaFreeHost(h->h_ds);
+    if (h->h_ds_m) cudaFreeHost(h->h_ds_m);
     if (h->graph_raw) cudaGraphExecDestroy(h->graph_raw);
     if (h->h_sout) cudaFreeHost(h->h_sout);
     if (h->h_mout) cudaFreeHost(h->h_mout);
@@ -567,7 +609,7 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
     const int eb = (int)(seq & 1);
     VMP_CUDA_CHECK(cudaEventRecord(h->pe0[eb], h->stream));
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
-    { const int rr = run_scan(h, raw); if (rr) return rr; }
+    { const int rr = run_scan(h, raw, n); if (rr) return rr; }
     VMP_CUDA_CHECK(cudaEventRecord(h->pe1[eb], h->stream));
     h->n_last = n;
     if (!pipe) {
@@ -661,6 +703,36 @@ int vmp_scan_raw(vmp_handle h, vmp_state* x, double* P, float* cloud_xyzt, int n
     std::memcpy(cloud_xyzt, h->h_cloud, sizeof(float) * 4 * (size_t)n);
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
+}
+
+int vmp_downsample(vmp_handle h, const float* cloud_xyzc, int n, double leaf, float* out_xyzc, int cap, int* m) {
+    int r = check_n(h, n, "vmp_downsample");
+    if (r) return r;
+    if ((n > 0 && !cloud_xyzc) || !(leaf > 0.0) || cap < 0 || (cap > 0 && !out_xyzc)) { set_error("vmp_downsample: invalid argument"); return VMP_ERR_INVALID_ARG; }
+    std::memcpy(h->h_raw, cloud_xyzc, sizeof(float) * 4 * (size_t)n);
+    h->h_in->n = n; h->h_in->stride = 4; h->h_in->n_poses = 0; h->h_in->mode = 0;
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, PTS_OFF + sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_downsample(h->stream, h->ds, (const float4*)(h->d_stage + PTS_OFF), &h->d_in->n, n, (float)leaf, h->grid_pts,
+                                     h->a_ds, h->a_ds_m, nullptr, nullptr);
+    VMP_CUDA_CHECK(cudaGetLastError());
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    const int mm = *h->h_ds_m;
+    if (m) *m = mm;
+    if (cap > 0) std::memcpy(out_xyzc, h->h_ds, sizeof(float) * 4 * (size_t)std::min(mm, cap));
+    return VMP_OK;
+}
+int vmp_get_lidar_cloud(vmp_handle h, float* out_xyzc, int cap, int* m) {
+    int r = check_n(h, 0, "vmp_get_lidar_cloud");
+    if (r) return r;
+    if (cap < 0 || (cap > 0 && !out_xyzc)) { set_error("vmp_get_lidar_cloud: invalid argument"); return VMP_ERR_INVALID_ARG; }
+    if (!h->last_raw) { set_error("vmp_get_lidar_cloud: the last scan was not a vmp_scan_raw (the caller holds the filter input)"); return VMP_ERR_STATE; }
+    // with the downsample on, the filter input of the last vmp_scan_raw are the leaf centroids; otherwise the compensated cloud
+    const int mm = h->ds_valid ? *h->h_ds_m : h->n_last;
+    const float* src = h->ds_valid ? reinterpret_cast<const float*>(h->h_ds) : reinterpret_cast<const float*>(h->h_cloud);
+    if (m) *m = mm;
+    if (cap > 0) std::memcpy(out_xyzc, src, sizeof(float) * 4 * (size_t)std::min(mm, cap));
+    return VMP_OK;
 }
 
 int vmp_set_pipelined(vmp_handle h, int on) {
@@ -820,7 +892,7 @@ const char* vmp_kernel_name(int id) {
         "k_scan_in", "k_set_scan", "k_update_begin", "k_measure", "k_ieskf_solve", "k_world_points",
         "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
         "k_fill_state", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
-        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_refit", "k_fill_acc", "k_undistort"};
+        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_refit", "k_fill_acc", "k_undistort", "k_downsample"};
     return (id >= 0 && id < VMP_K_COUNT) ? names[id] : "?";
 }
 

@@ -193,6 +193,16 @@ struct DevScan {                        // persistent residual buffer, SoA over 
     double range_var, sn2;
 };
 
+// scratch of the pcl::VoxelGrid downsample (vmp_downsample.cu), sized for max_points_per_scan
+struct DevDown {
+    unsigned* mm;                       // [8] order-encoded bounding box + finite count (zero between scans)
+    unsigned* keys[2]; int* vals[2];    // (leaf idx, point index) before / after the stable sort
+    int* head; int* rank;               // leaf starts of the sorted list and their inclusive scan
+    float4* out;                        // filtered cloud (centroid xyz, mean curvature), ascending leaf idx
+    int* m;                             // number of leaves
+    void* temp; size_t temp_bytes;      // CUB scratch
+};
+
 // ---- key packing / hashing -----------------------------------------------------------
 __host__ __device__ __forceinline__ bool key_in_range(long long k) { return k >= -(1ll << 20) && k < (1ll << 20); }
 __host__ __device__ __forceinline__ unsigned long long pack_key(long long x, long long y, long long z) {

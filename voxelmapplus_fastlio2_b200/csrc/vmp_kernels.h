@@ -30,6 +30,12 @@ inline void mark(const Marker* mk, int id) { if (mk && mk->fn) mk->fn(mk->ctx, i
 // next to the merge simulation); null = everything on one stream
 struct SideStream { cudaStream_t st; cudaEvent_t ev[4]; };
 
+// pcl::VoxelGrid leaf-centroid filter of `cloud` (n_sort points, the same count on the device at *n_ptr) -> d.out / d.m
+// (+ mapped host copies); patch != null: the scan header is redirected to the filtered cloud.  Returns the kernel count.
+size_t downsample_temp_bytes(int nmax);
+int launch_downsample(cudaStream_t st, const DevDown& d, const float4* cloud, const int* n_ptr, int n_sort, float leaf, int grid,
+                      float4* host_out, int* host_m, ScanIn* patch, const Marker* mk);
+
 // map: returns the number of kernels launched
 // `out`: mailbox written by the update's last kernel (counters, error bits, maintenance requests); may be null
 int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk,

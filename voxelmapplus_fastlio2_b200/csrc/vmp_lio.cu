@@ -118,10 +118,7 @@ int LIOBuilder::loadConfig(const vmp_config& cfg) {
         Q[i * 12 + i] = cfg.ng; Q[(3 + i) * 12 + 3 + i] = cfg.na;
         Q[(6 + i) * 12 + 6 + i] = cfg.nbg; Q[(9 + i) * 12 + 9 + i] = cfg.nba;
     }
-    if (cfg.scan_resolution > 0.0) {
-        set_error("LIOBuilder::loadConfig: scan_resolution > 0 (pcl::VoxelGrid downsample) is a SURVEY.md 8(f) 'next' row; use scan_resolution <= 0");
-        return VMP_ERR_INVALID_ARG;
-    }
+    // scan_filter.setLeafSize (lio_builder.cpp:13-14): the filter runs on the device (vmp_downsample / inside vmp_scan_raw)
     if (map) { vmp_destroy(map); map = nullptr; }
     return vmp_create(&cfg, &map);
 }
@@ -253,6 +250,18 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
         if (r) return r;
         if (stats) stats->map = us;
         status = LIO_MAPPING;
+        return VMP_OK;
+    }
+    if (config.scan_resolution > 0.0) {     // lio_builder.cpp:215-219 after a host-side compensation: filter, then the update
+        ds_.resize((size_t)n * 4);
+        int m = 0;
+        const int rd = vmp_downsample(map, reinterpret_cast<const float*>(package.pts()), n, config.scan_resolution, ds_.data(), n, &m);
+        if (rd) return rd;
+        xyz_.resize((size_t)m * 3);
+        for (int i = 0; i < m; i++) { xyz_[3 * i] = ds_[4 * i]; xyz_[3 * i + 1] = ds_[4 * i + 1]; xyz_[3 * i + 2] = ds_[4 * i + 2]; }
+        const int r = vmp_scan(map, &xs, kf.P(), xyz_.data(), m, stats);
+        if (r) return r;
+        kf.x() = st_load(reinterpret_cast<const double*>(&xs));
         return VMP_OK;
     }
     const int r = vmp_scan(map, &xs, kf.P(), xyz_.data(), n, stats);     // posterior written back into xs / kf.P()

@@ -66,7 +66,7 @@ public:
     vmp_state prior_x{};                                       // what the last process() handed to the device update
     double prior_P[529] = {};
 private:
-    std::vector<float> xyz_;
+    std::vector<float> xyz_, ds_;
     std::vector<vmp_pose> poses_;
 };
 

@@ -119,7 +119,7 @@ class VmpScanStats(C.Structure):
                 ("map", VmpUpdateStats), ("gpu_ms", C.c_float), ("host_ms", C.c_float)]
 
 
-K_COUNT = 24        # VMP_K_COUNT in include/vmp_b200.h
+K_COUNT = 25        # VMP_K_COUNT in include/vmp_b200.h
 
 
 class VmpImu(C.Structure):

@@ -62,6 +62,8 @@ class LIOBuilder:
         self.map._n = cloud_xyzc.shape[0]
         self._check(self._lib.vmp_lio_process(self._h, imus.ctypes.data_as(C.POINTER(VmpImu)), imus.shape[0],
                                               fptr(cloud_xyzc), cloud_xyzc.shape[0], t0, t1, C.byref(st)))
+        if self.cfg.scan_resolution > 0 and st.iters > 0 and st.map.n_points > 0:
+            self.map._n = int(st.map.n_points)      # the filter saw the leaf centroids (synchronous mode)
         return st
 
     def state(self):
