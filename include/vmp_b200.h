@@ -159,6 +159,14 @@ int vmp_set_scan(vmp_handle h, const float* pts_lidar, int n);
 int vmp_scan(vmp_handle h, vmp_state* x_inout, double* P_inout,
              const float* pts_lidar, int n, vmp_scan_stats* stats);
 
+/* vmp_scan without the intermediate copy: vmp_scan_buffer returns the handle's PINNED staging area (room for
+ * max_points_per_scan x 3 float32); the caller writes the filter input there — in the loop that extracts x y z from its own
+ * point type, e.g. pcl::PointXYZINormal in lio_builder.cpp:224-229 — and vmp_scan_staged uploads it from there (one DMA copy
+ * with the header and the prior) and runs the scan.  The buffer may be refilled as soon as the call has returned
+ * (also in pipelined mode). */
+float* vmp_scan_buffer(vmp_handle h);
+int vmp_scan_staged(vmp_handle h, vmp_state* x_inout, double* P_inout, int n, vmp_scan_stats* stats);
+
 /* Same work with every input already resident in device memory: pts_lidar_dev = device
  * pointer to N x 3 float32; prior_dev = device pointer to 36 + 529 doubles (vmp_state
  * followed by the 23x23 P), or NULL to continue from the state left on the device by the

@@ -268,6 +268,36 @@ def test_pipelined_mode_is_identical():
     assert_maps_equal(a.map.dump_map(), b.map.dump_map(), exact=True, what="pipelined map")
 
 
+def test_staged_scan_is_identical():
+    """vmp_scan_buffer + vmp_scan_staged (points written straight into the pinned staging) == vmp_scan, bit for bit."""
+    cfg = default_config(max_points_per_scan=8192)
+    a, b = HotPath(cfg), HotPath(cfg)
+    lio = LIOBuilder(cfg, device_undistort=False)          # produces priors and compensated clouds
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=5000))
+    n = 0
+    for pk in seq.packages(10):
+        cloud = pk.cloud.copy()
+        st = lio.process(pk.imus, cloud, pk.t0, pk.t1)
+        _, _, status = lio.state()
+        if status < 2:
+            continue
+        x0, P0 = lio.prior()
+        xyz = np.ascontiguousarray(cloud[:, :3])
+        if st.iters == 0:
+            a.first_scan(x0, P0, xyz); b.first_scan(x0, P0, xyz)
+            continue
+        xa, Pa, sa = a.scan(x0, P0, xyz)
+        xb, Pb, sb = b.scan_staged(x0, P0, xyz)
+        assert bytes(xa) == bytes(xb) and np.array_equal(Pa, Pb) and sa.iters == sb.iters
+        assert sa.map.as_dict() == sb.map.as_dict()
+        # ... and the host LIOBuilder, which stages its scans the same way, got the same posterior
+        xl, Pl, _ = lio.state()
+        assert bytes(xl) == bytes(xa) and np.array_equal(Pl, Pa)
+        n += 1
+    assert n >= 5
+    assert_maps_equal(a.dump_map(), b.dump_map(), exact=True, what="staged vs copied scan")
+
+
 def test_pipelined_reports_capacity_error_late():
     """a map update that exhausts the capacity while pipelined surfaces on the next call on the handle"""
     cfg = default_config(max_points_per_scan=4096, map_capacity=64)

@@ -154,6 +154,23 @@ class HotPath:
         self._check(self._fn("scan")(self._h, C.byref(x), dptr(P), fptr(p), p.shape[0], C.byref(st)))
         return x, P, st
 
+    def scan_staged(self, x: VmpState, P, pts_lidar):
+        """vmp_scan_buffer + vmp_scan_staged: the points are written straight into the handle's pinned staging area."""
+        p = np.asarray(pts_lidar, dtype=np.float32).reshape(-1, 3)
+        n = p.shape[0]
+        self._lib.vmp_scan_buffer.argtypes = [C.c_void_p]
+        self._lib.vmp_scan_buffer.restype = C.POINTER(C.c_float)
+        self._lib.vmp_scan_staged.argtypes = [C.c_void_p, C.POINTER(VmpState), C.POINTER(C.c_double), C.c_int, C.POINTER(VmpScanStats)]
+        self._lib.vmp_scan_staged.restype = C.c_int
+        buf = self._lib.vmp_scan_buffer(self._h)
+        np.ctypeslib.as_array(buf, shape=(max(n, 1), 3))[:n] = p
+        self._n = n
+        x = x.copy()
+        P = _f64(P, (23, 23)).copy()
+        st = VmpScanStats()
+        self._check(self._lib.vmp_scan_staged(self._h, C.byref(x), dptr(P), n, C.byref(st)))
+        return x, P, st
+
     def first_scan(self, x: VmpState, P, pts_lidar) -> dict:
         """MAP_INIT branch (lio_builder.cpp:185-211)."""
         p = np.ascontiguousarray(pts_lidar, dtype=np.float32).reshape(-1, 3)

@@ -90,6 +90,8 @@ struct vmp_handle_t {
     DevDown ds{};                        // pcl::VoxelGrid downsample scratch (vmp_downsample.cu)
     float4* h_ds = nullptr; float4* a_ds = nullptr;          // filtered cloud = LIOBuilder::lidar_cloud (pinned, mapped)
     int* h_ds_m = nullptr; int* a_ds_m = nullptr;
+    DevDump dump{};                      // map read-back scratch, allocated by the first vmp_dump_map
+    bool dump_ready = false;
     bool ds_valid = false;               // the last scan went through the downsample
     bool last_raw = false;               // the last scan was a vmp_scan_raw (its compensated cloud is in h_cloud)
     cudaGraphExec_t graph_raw = nullptr; // the scan graph with the motion compensation in front
@@ -643,20 +645,36 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
     return r;
 }
 
-int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp_scan_stats* stats) {
-    const auto t_enter = std::chrono::steady_clock::now();
-    int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan") : check_n(h, n, "vmp_scan");
-    if (r) return r;
-    if (!x || !P || (n > 0 && !pts)) { set_error("vmp_scan: null argument"); return VMP_ERR_INVALID_ARG; }
-    if (!h->map_built) { set_error("vmp_scan: no map yet (call vmp_first_scan or vmp_map_build first)"); return VMP_ERR_STATE; }
-    // header + prior + points go up in ONE DMA copy from pinned staging (SM reads of host memory reach a fraction of the
-    // copy engine's PCIe rate, small ones cost a round trip each); the previous scan's copy is long done
-    std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);
+// the scan is already in the pinned staging buffer (vmp_scan_buffer): header + prior + points go up in ONE DMA copy (SM
+// reads of host memory reach a fraction of the copy engine's PCIe rate, small ones cost a round trip each)
+static int scan_staged(vmp_handle h, vmp_state* x, double* P, int n, vmp_scan_stats* stats, const char* who) {
+    if (!x || !P) { set_error("%s: null argument", who); return VMP_ERR_INVALID_ARG; }
+    if (!h->map_built) { set_error("%s: no map yet (call vmp_first_scan or vmp_map_build first)", who); return VMP_ERR_STATE; }
     h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
     h->h_in->n_poses = 0; h->h_in->stride = 3;
     std::memcpy(h->h_in->x, x, sizeof(double) * 36);
     std::memcpy(h->h_in->P, P, sizeof(double) * 529);
-    r = scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 3 * (size_t)n, stats);
+    return scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 3 * (size_t)n, stats);
+}
+
+int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp_scan_stats* stats) {
+    const auto t_enter = std::chrono::steady_clock::now();
+    int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan") : check_n(h, n, "vmp_scan");
+    if (r) return r;
+    if (n > 0 && !pts) { set_error("vmp_scan: null argument"); return VMP_ERR_INVALID_ARG; }
+    std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);          // the previous scan's copy out of this buffer is long done
+    r = scan_staged(h, x, P, n, stats, "vmp_scan");
+    if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+    return r;
+}
+
+float* vmp_scan_buffer(vmp_handle h) { return h ? h->h_raw : nullptr; }
+
+int vmp_scan_staged(vmp_handle h, vmp_state* x, double* P, int n, vmp_scan_stats* stats) {
+    const auto t_enter = std::chrono::steady_clock::now();
+    int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan_staged") : check_n(h, n, "vmp_scan_staged");
+    if (r) return r;
+    r = scan_staged(h, x, P, n, stats, "vmp_scan_staged");
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
 }
@@ -804,40 +822,33 @@ int vmp_map_size(vmp_handle h, int* count) {
 int vmp_dump_map(vmp_handle h, vmp_plane* out, int cap, int* count) {
     int r = check_n(h, 0, "vmp_dump_map");
     if (r) return r;
+    if (cap < 0 || (cap > 0 && !out)) { set_error("vmp_dump_map: invalid argument"); return VMP_ERR_INVALID_ARG; }
     const DevMap& m = h->m;
-    const size_t P = (size_t)m.pool;
-    std::vector<unsigned long long> stamp, skey, sgroup;
-    std::vector<double> hot, ppt, cov, center;
-    std::vector<int> n_temp, newly;
-    if ((r = d2h(h, stamp, m.stamp, P)) || (r = d2h(h, skey, m.skey, P)) || (r = d2h(h, sgroup, m.sgroup, P)) ||
-        (r = d2h(h, hot, m.hot, P * 8)) || (r = d2h(h, ppt, m.ppt, P * 6)) || (r = d2h(h, cov, m.cov, P * 36)) ||
-        (r = d2h(h, center, m.center, P * 3)) || (r = d2h(h, n_temp, m.n_temp, P)) || (r = d2h(h, newly, m.newly, P))) return r;
-    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    std::vector<int> live;
-    for (size_t s = 0; s < P; s++) if (stamp[s] != 0) live.push_back((int)s);
-    std::sort(live.begin(), live.end(), [&](int a, int b) { return stamp[a] > stamp[b]; });   // front of cache = most recent
-    if (count) *count = (int)live.size();
-    for (size_t i = 0; i < live.size() && (int)i < cap; i++) {
-        const int s = live[i];
-        vmp_plane& p = out[i];
-        std::memset(&p, 0, sizeof(p));
-        long long x, y, z;
-        unpack_key(skey[s], x, y, z);
-        p.key[0] = x; p.key[1] = y; p.key[2] = z;
-        const double* hr = &hot[(size_t)s * 8];
-        for (int k = 0; k < 3; k++) { p.mean[k] = hr[k]; p.norm[k] = hr[3 + k]; p.center[k] = center[(size_t)s * 3 + k]; }
-        const double* pp = &ppt[(size_t)s * 6];
-        p.ppt[0] = pp[0]; p.ppt[1] = pp[1]; p.ppt[2] = pp[3]; p.ppt[3] = pp[1]; p.ppt[4] = pp[2]; p.ppt[5] = pp[4];
-        p.ppt[6] = pp[3]; p.ppt[7] = pp[4]; p.ppt[8] = pp[5];
-        std::memcpy(p.cov, &cov[(size_t)s * 36], sizeof(double) * 36);
-        long long w;
-        std::memcpy(&w, &hr[6], 8);
-        p.flags = (uint32_t)(w & 0xFFFFFFFFll);
-        p.n = (int32_t)(w >> 32);
-        p.n_temp = n_temp[s]; p.newly_add_point = newly[s];
-        p.group = sgroup[s];
-        p.lru_rank = i;
+    if (!h->dump_ready) {
+        DevDump& d = h->dump;
+        const size_t P = (size_t)m.pool;
+        DALLOC(d.keys[0], P); DALLOC(d.keys[1], P); DALLOC(d.vals[0], P); DALLOC(d.vals[1], P); DALLOC(d.count, 1);
+        DALLOC(d.records, P * 61);
+        d.temp_bytes = dump_temp_bytes(m.pool);
+        unsigned char* tmp = nullptr;
+        DALLOC(tmp, d.temp_bytes);
+        d.temp = tmp;
+        h->dump_ready = true;
     }
+    // the walk over VoxelMap::cache (utils.cpp:161-195) on the device: collect live slots, sort by LRU stamp (front of the
+    // list = most recent insertion first), assemble the records, one copy of live x sizeof(vmp_plane) bytes
+    const int grid = h->sm_count * 4;
+    launch_dump_collect(h->stream, grid, m, h->dump);
+    int n_live = 0;
+    VMP_CUDA_CHECK(cudaMemcpyAsync(&n_live, h->dump.count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (count) *count = n_live;
+    const int n_out = std::min(n_live, cap);
+    launch_dump_sort_gather(h->stream, grid, m, h->dump, n_live);
+    h->launches += 3;
+    if (n_out > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(out, h->dump.records, sizeof(vmp_plane) * (size_t)n_out, cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    VMP_CUDA_CHECK(cudaGetLastError());
     return VMP_OK;
 }
 

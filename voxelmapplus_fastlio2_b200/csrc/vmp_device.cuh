@@ -203,6 +203,14 @@ struct DevDown {
     void* temp; size_t temp_bytes;      // CUB scratch
 };
 
+// scratch of the device-side map read-back (vmp_readback.cu), allocated by the first vmp_dump_map
+struct DevDump {
+    unsigned long long* keys[2]; int* vals[2];      // (LRU stamp, slot) of the live voxels before / after the sort
+    int* count;
+    unsigned long long* records;                    // [pool][61] assembled vmp_plane records
+    void* temp; size_t temp_bytes;
+};
+
 // ---- key packing / hashing -----------------------------------------------------------
 __host__ __device__ __forceinline__ bool key_in_range(long long k) { return k >= -(1ll << 20) && k < (1ll << 20); }
 __host__ __device__ __forceinline__ unsigned long long pack_key(long long x, long long y, long long z) {

@@ -36,6 +36,11 @@ size_t downsample_temp_bytes(int nmax);
 int launch_downsample(cudaStream_t st, const DevDown& d, const float4* cloud, const int* n_ptr, int n_sort, float leaf, int grid,
                       float4* host_out, int* host_m, ScanIn* patch, const Marker* mk);
 
+// map read-back in LRU order: live slots -> (stamp, slot); then sort by stamp (descending) + one vmp_plane record per voxel
+size_t dump_temp_bytes(int pool);
+void launch_dump_collect(cudaStream_t st, int grid, const DevMap& m, const DevDump& d);
+void launch_dump_sort_gather(cudaStream_t st, int grid, const DevMap& m, const DevDump& d, int n_live);
+
 // map: returns the number of kernels launched
 // `out`: mailbox written by the update's last kernel (counters, error bits, maintenance requests); may be null
 int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk,

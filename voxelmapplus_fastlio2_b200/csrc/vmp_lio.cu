@@ -242,9 +242,9 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
         kf.x() = st_load(reinterpret_cast<const double*>(&xs));
         return VMP_OK;
     }
-    xyz_.resize((size_t)n * 3);
-    { const CloudPoint* c = package.pts(); for (int i = 0; i < n; i++) { xyz_[3 * i] = c[i].x; xyz_[3 * i + 1] = c[i].y; xyz_[3 * i + 2] = c[i].z; } }
     if (status == MAP_INIT) {
+        xyz_.resize((size_t)n * 3);
+        { const CloudPoint* c = package.pts(); for (int i = 0; i < n; i++) { xyz_[3 * i] = c[i].x; xyz_[3 * i + 1] = c[i].y; xyz_[3 * i + 2] = c[i].z; } }
         vmp_update_stats us;
         const int r = vmp_first_scan(map, &xs, kf.P(), xyz_.data(), n, &us);
         if (r) return r;
@@ -264,7 +264,10 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
         kf.x() = st_load(reinterpret_cast<const double*>(&xs));
         return VMP_OK;
     }
-    const int r = vmp_scan(map, &xs, kf.P(), xyz_.data(), n, stats);     // posterior written back into xs / kf.P()
+    // lio_builder.cpp:224-229 reads x y z out of the PCL points; here they go straight into the pinned staging of the scan
+    if (n > config.max_points_per_scan) { set_error("LIOBuilder::process: %d points exceed max_points_per_scan=%d", n, config.max_points_per_scan); return VMP_ERR_INVALID_ARG; }
+    { float* dst = vmp_scan_buffer(map); const CloudPoint* c = package.pts(); for (int i = 0; i < n; i++) { dst[3 * i] = c[i].x; dst[3 * i + 1] = c[i].y; dst[3 * i + 2] = c[i].z; } }
+    const int r = vmp_scan_staged(map, &xs, kf.P(), n, stats);           // posterior written back into xs / kf.P()
     if (r) return r;
     kf.x() = st_load(reinterpret_cast<const double*>(&xs));
     return VMP_OK;
