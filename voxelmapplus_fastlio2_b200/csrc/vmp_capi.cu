@@ -132,14 +132,17 @@ int dalloc(vmp_handle_t* h, T** p, size_t count) {
 
 int check_device_err(vmp_handle_t* h, int err) {
     if (!err) return VMP_OK;
-    set_error("device reported error bits 0x%x:%s%s%s%s%s%s%s", err,
+    set_error("device reported error bits 0x%x:%s%s%s%s%s%s%s%s%s%s", err,
               (err & E_KEY_RANGE) ? " voxel coordinate outside +-2^20;" : "",
               (err & E_POOL) ? " voxel slot pool exhausted;" : "",
               (err & E_LRU_EXHAUSTED) ? " map_capacity smaller than the voxels one scan touches (LRU victim was touched in the same scan);" : "",
               (err & E_REFIT_OVERFLOW) ? " refit of a voxel holding more than max_point_thresh points;" : "",
               (err & E_QUEUE) ? " internal queue overflow;" : "",
               (err & E_HASH_FULL) ? " hash table full;" : "",
-              (err & E_MERGE_DEPTH) ? " merge cascade deeper than 2 inside one scan;" : "");
+              (err & E_MERGE_DEPTH) ? " merge cascade deeper than 2 inside one scan;" : "",
+              (err & E_MERGE_CAP) ? " merge simulation: active set overflow;" : "",
+              (err & E_LOG_CAP) ? " LRU log full;" : "",
+              (err & E_FILL_CAP) ? " refit job / contribution staging exhausted;" : "");
     (void)h;
     return VMP_ERR_CAPACITY;
 }
@@ -437,7 +440,9 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     {
         const int tpb = cfg->estimate_ext ? 128 : 256;
         const int occ = cfg->estimate_ext ? 4 : 2;       // resident measurement CTAs per SM (k_measure's launch bounds)
-        h->grid_meas = std::max(1, std::min(h->sm_count * occ, (nmax + tpb - 1) / tpb));
+        // one slot is left for the solver CTA: with sm_count * occ measurement CTAs the last of them waited for a free slot
+        // and ran as a second wave of its own (the measurement of 200 000 points took twice as long as it had to)
+        h->grid_meas = std::max(1, std::min(h->sm_count * occ - 1, (nmax + tpb - 1) / tpb));
     }
     DALLOC(h->partials, (size_t)h->grid_meas * PARTIAL_STRIDE);
     DALLOC(h->meas_out, 160);

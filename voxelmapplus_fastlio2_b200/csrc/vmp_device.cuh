@@ -43,6 +43,9 @@ constexpr int E_REFIT_OVERFLOW = 8;     // refit of a voxel holding more than ma
 constexpr int E_QUEUE = 16;             // internal queue overflow in the serial merge / eviction kernels
 constexpr int E_HASH_FULL = 32;
 constexpr int E_MERGE_DEPTH = 64;       // a merge succeeded at cascade depth > 2 inside one scan (parallel rounds would not be exact)
+constexpr int E_MERGE_CAP = 128;        // more than MERGE_CAP voxels in the active set of the merge simulation
+constexpr int E_LOG_CAP = 256;          // LRU log full (compaction was not served in time)
+constexpr int E_FILL_CAP = 512;         // refit job / contribution staging exhausted
 
 struct DevStats {                       // == vmp_update_stats order
     long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size;

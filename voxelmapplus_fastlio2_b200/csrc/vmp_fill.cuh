@@ -121,7 +121,7 @@ __device__ int emit_jobs(const DevMap& m, DevCtl* ctl, int slot, const double* s
         j0 = atomicAdd(&ctl->n_jobs, nj);
         off0 = (long long)atomicAdd(&ctl->contrib_top, (unsigned long long)tot_nt);
         b0 = atomicAdd(&ctl->n_batches, tot_nb);
-        if (j0 + nj > m.job_cap || off0 + tot_nt > m.contrib_cap || b0 + tot_nb > m.bat_cap) { atomicOr(&ctl->err, E_QUEUE); j0 = -1; }
+        if (j0 + nj > m.job_cap || off0 + tot_nt > m.contrib_cap || b0 + tot_nb > m.bat_cap) { atomicOr(&ctl->err, E_FILL_CAP); j0 = -1; }
         else if (prev_job >= 0) m.job_next[prev_job] = j0;
     }
     j0 = __shfl_sync(0xffffffffu, j0, 0);

@@ -311,14 +311,18 @@ __device__ void block_bitonic_sort(int* a, int npow) {            // ascending, 
 
 // serial walk (one thread): creation times ct[0..n_new) ascending
 __device__ void lru_serial_walk(const DevMap& m, DevCtl* ctl, const int* ct, int n_live0, int n_new) {
-    int rq[64];
-    int size = n_live0, ne = 0, rqn = 0, ci = 0, created = n_new;
+    // re-creation times of victims that are touched again later in the scan, ascending.  In global scratch (act_t is not
+    // used before the merge prefilter): when a drive turns back into the oldest part of the map, a single scan can re-create
+    // hundreds of the voxels it evicts (a 64-entry local queue overflowed on the C3 city drive)
+    int* rq = m.act_t;
+    const int rq_cap = m.nmax;
+    int size = n_live0, ne = 0, rqh = 0, rqn = 0, ci = 0, created = n_new;     // queue = rq[rqh .. rqn)
     long long h = ctl->log_head;
     const long long tail = ctl->log_tail;
     const int sel = ctl->log_sel;
-    while (ci < n_new || rqn > 0) {
+    while (ci < n_new || rqn > rqh) {
         int t;
-        if (rqn > 0 && (ci >= n_new || rq[0] < ct[ci])) { t = rq[0]; for (int q = 1; q < rqn; q++) rq[q - 1] = rq[q]; rqn--; }
+        if (rqn > rqh && (ci >= n_new || rq[rqh] < ct[ci])) t = rq[rqh++];
         else t = ct[ci++];
         size += 1;
         if (size <= m.capacity) continue;
@@ -349,10 +353,10 @@ __device__ void lru_serial_walk(const DevMap& m, DevCtl* ctl, const int* ct, int
             slot_init_fresh(m, ctl, victim, m.skey[g]);
             m.ghost[victim] = g;
             m.ev_slot[ne] = g | 0x40000000;
-            if (rqn >= 64) { atomicOr(&ctl->err, E_QUEUE); break; }
+            if (rqn >= rq_cap) { atomicOr(&ctl->err, E_QUEUE); break; }
             int q = rqn++;
             const int tt = m.ft[victim];
-            while (q > 0 && rq[q - 1] > tt) { rq[q] = rq[q - 1]; q--; }
+            while (q > rqh && rq[q - 1] > tt) { rq[q] = rq[q - 1]; q--; }
             rq[q] = tt;
             created++;
         } else {
@@ -405,27 +409,44 @@ __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
     const int E = n_new - slack;                            // evictions if no victim is re-created
     const int sel = ctl->log_sel;
     const long long tail = ctl->log_tail;
+    // The log is append-only with lazy deletion: a voxel touched in k scans has k entries of which only the last is live, so
+    // the walk from the head passes many stale entries per victim (C4: ~50 per victim).  Every thread takes EPT consecutive
+    // entries per step (independent loads, one block scan per blockDim.x * EPT entries).
+    constexpr int EPT = 8;
     int base_u = 0;
-    for (long long pos = ctl->log_head; base_u < E && pos < tail; pos += blockDim.x) {
-        const long long p = pos + tid;
-        int sl = -1;
-        bool live = false, touched = false;
-        if (p < tail) {
-            sl = m.log_slot[sel][p];
-            live = m.stamp[sl] == m.log_stamp[sel][p];
-            touched = live && m.cnt[sl] > 0;
+    for (long long pos = ctl->log_head; base_u < E && pos < tail; pos += (long long)blockDim.x * EPT) {
+        const long long p0 = pos + (long long)tid * EPT;
+        int sl[EPT];
+        unsigned long long lst[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const long long p = p0 + e;
+            sl[e] = p < tail ? m.log_slot[sel][p] : -1;
+            lst[e] = p < tail ? m.log_stamp[sel][p] : 0ull;
         }
-        const int U = (live && !touched) ? 1 : 0;
+        unsigned umask = 0, tmask = 0;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            if (sl[e] < 0) continue;
+            const bool live = m.stamp[sl[e]] == lst[e];
+            const bool touched = live && m.cnt[sl[e]] > 0;
+            if (live && !touched) umask |= 1u << e;
+            if (touched) tmask |= 1u << e;
+        }
         int total;
-        const int r = base_u + block_excl_scan(U, &total, sh);          // victim index this entry is examined for
-        if (r < E) {
-            const int t = sct[slack + r];
-            if (U) {
-                m.ev_slot[r] = sl; m.ev_time[r] = t; m.ev_key[r] = m.skey[sl];
-                if (r == E - 1) s_headpos = p + 1;
-            } else if (touched && !(m.ft[sl] < t)) {
-                s_bad = 1;                                  // this entry would be evicted and re-created later in the scan
+        int r = base_u + block_excl_scan(__popc(umask), &total, sh);       // victim index the thread's first entry is examined for
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            if (r < E) {
+                const int t = sct[slack + r];
+                if ((umask >> e) & 1u) {
+                    m.ev_slot[r] = sl[e]; m.ev_time[r] = t; m.ev_key[r] = m.skey[sl[e]];
+                    if (r == E - 1) s_headpos = p0 + e + 1;
+                } else if (((tmask >> e) & 1u) && !(m.ft[sl[e]] < t)) {
+                    s_bad = 1;                              // this entry would be evicted and re-created later in the scan
+                }
             }
+            r += (umask >> e) & 1u;
         }
         base_u += total;
         __syncthreads();
@@ -467,7 +488,7 @@ __global__ void __launch_bounds__(1024) k_log_append(DevMap m, DevCtl* ctl) {
         if (f) {
             const long long pos = tail + base_sh + r;
             if (pos < m.log_cap) { m.log_slot[sel][pos] = slot; m.log_stamp[sel][pos] = sb + (unsigned long long)i; }
-            else atomicOr(&ctl->err, E_QUEUE);
+            else atomicOr(&ctl->err, E_LOG_CAP);
             m.stamp[slot] = sb + (unsigned long long)i;
         }
         __syncthreads();

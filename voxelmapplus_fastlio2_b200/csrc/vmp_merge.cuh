@@ -292,7 +292,7 @@ __device__ void as_activate(const DevMap& m, DevCtl* ctl, ActiveSet& as, int Y, 
             if (depth > d0) as.slot[found] = Y | (depth << 28);
         } else {
             const int k = atomicAdd(&as.n, 1);
-            if (k >= MERGE_CAP) { atomicOr(&ctl->err, E_QUEUE); atomicSub(&as.n, 1); }
+            if (k >= MERGE_CAP) { atomicOr(&ctl->err, E_MERGE_CAP); atomicSub(&as.n, 1); }
             else {
                 as.slot[k] = Y | (depth << 28);
                 as.t[k] = nt;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = ctl->n_hot;                       // (voxel, first relevant event) pairs prepared by k_merge_prefilter
     if (n0 == 0) return;
-    if (n0 > MERGE_CAP) { if (tid == 0) atomicOr(&ctl->err, E_QUEUE); return; }
+    if (n0 > MERGE_CAP) { if (tid == 0) atomicOr(&ctl->err, E_MERGE_CAP); return; }
     const unsigned scan_id = ctl->scan_id;
     if (tid == 0) {
         long long x, y, z;
