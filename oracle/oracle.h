@@ -123,6 +123,16 @@ struct ResidualData {                         // voxel_map.h:53-65
     uint8_t status = 0;                       // bit0 found, bit1 is_plane, bit2 is_valid
 };
 
+// smallest |margin| to the threshold of every gate decision taken so far (SURVEY.md 8c safeguard iii): a parity
+// disagreement at a margin below ~1e-10 is a tie of the arithmetic, not a bug.  Instrumentation only.
+struct GateMargins {
+    double plane = 1e300;        // |lambda0 - plane_thresh|                          voxel_map.cpp:107
+    double gate = 1e300;         // | |r| - 3 sqrt(sigma) |                            voxel_map.cpp:272
+    double merge_angle = 1e300;  // | (1 - nB.nA) - merge_thresh_for_angle |           voxel_map.cpp:158
+    double merge_dist = 1e300;   // | |nB.mB - nA.mA| - merge_thresh_for_distance |    voxel_map.cpp:158
+    void reset() { *this = GateMargins(); }
+};
+
 struct MapCounters {                          // terms of the algorithmic-byte model
     int64_t n_points = 0, n_ins = 0, n_touch = 0, n_created = 0, n_refit = 0, refit_points = 0,
             n_full = 0, n_mergeprobe = 0, n_merge = 0, n_evicted = 0;
@@ -172,6 +182,7 @@ public:
     double merge_thresh_for_angle = 0.1, merge_thresh_for_distance = 0.04;
     // instrumentation
     MapCounters counters;
+    GateMargins margins;
     std::vector<VoxelKey> evicted;            // victims of the last build/update, in order
     uint64_t epoch = 0;
 };

@@ -267,6 +267,12 @@ int orc_get_lidar_cloud(void* h, float* out_xyzc, int cap, int* m) {
     if (m) *m = (int)o.size();
     return VMP_OK;
 }
+// smallest margins of the gate decisions since creation: plane fit, 3-sigma gate, merge angle, merge distance
+int orc_gate_margins(void* h, double* out4) {
+    const GateMargins& g = H(h)->lio.map->margins;
+    out4[0] = g.plane; out4[1] = g.gate; out4[2] = g.merge_angle; out4[3] = g.merge_dist;
+    return VMP_OK;
+}
 int orc_lio_state(void* h, vmp_state* x, double* P, int* status) {
     orc_get_state(h, x, P);
     if (status) *status = (int)H(h)->lio.status;

@@ -80,6 +80,13 @@ class Oracle(HotPath):
             self._n = self.lidar_cloud().shape[0]
         return st
 
+    def gate_margins(self) -> dict:
+        """Smallest |margin| to the threshold over every gate decision so far (plane fit, 3-sigma gate, merge angle / distance)."""
+        out = np.zeros(4)
+        self._lib.orc_gate_margins.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self._lib.orc_gate_margins(self._h, dptr(out))
+        return dict(zip(("plane", "gate", "merge_angle", "merge_dist"), out.tolist()))
+
     def lio_state(self):
         x = VmpState()
         P = np.zeros((23, 23))

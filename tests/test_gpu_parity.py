@@ -179,6 +179,8 @@ def test_measure_and_scan_teacher_forced(oracle_mod, estimate_ext):
         # both forms are conditioned like cond(P^-1 + H) * eps ~ 1e-6, so that is the meaningful tolerance on P
         np.testing.assert_allclose(Pg, P_post, rtol=2e-5, atol=1e-12)
     assert checked_iters > 15
+    # SURVEY.md 8(c) safeguard (iii): none of the bit-exact decisions above was a tie of the arithmetic
+    assert min(o.gate_margins().values()) > 1e-10, o.gate_margins()
 
 
 def test_dense_scan_c2_size(oracle_mod):

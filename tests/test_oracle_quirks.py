@@ -195,3 +195,21 @@ def test_stale_residual_records_q2_and_weight_clamp_q19(mk, oracle_mod):
     assert ec == 8
     np.testing.assert_allclose(np.trace(Hc[:3, :3]), 5000.0 * np.sum(nc * nc), rtol=1e-9)
     assert np.allclose(H1[6:, :], 0) and np.allclose(H1[:, 6:], 0), "estimate_ext = false leaves rows/cols 6..11 zero"
+
+
+def test_gate_margins_of_the_parity_workload_are_not_ties(oracle_mod):
+    """SURVEY.md 8(c) safeguard (iii): every gate decision of the path (plane fit lambda0 vs plane_thresh, the 3-sigma gate,
+    the two merge thresholds) records its margin to the threshold.  The bit-exact tier-1 comparisons of the GPU tests are
+    only meaningful where the decisions are not ties of the arithmetic (|margin| >= 1e-10); this pins that for the
+    synthetic sequence those tests use."""
+    from voxelmapplus_fastlio2_b200 import synth
+    from voxelmapplus_fastlio2_b200.ctypes_defs import default_config
+    o = oracle_mod.Oracle(default_config(max_points_per_scan=4096))
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=3000))
+    for pk in seq.packages(14):
+        o.lio_process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+    m = o.gate_margins()
+    assert set(m) == {"plane", "gate", "merge_angle", "merge_dist"}
+    for k, v in m.items():
+        assert v > 1e-10, f"gate '{k}' was decided at a margin of {v}: a tie, pick another seed for the parity tests"
+    assert m["gate"] < 1.0 and m["plane"] < 1.0          # the gates were exercised at all

@@ -285,29 +285,13 @@ __global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl) {
 // cache.push_front / splice / "if (cache.size() > capacity) erase(cache.back())" (voxel_map.cpp:242-253).
 // The k-th over-capacity creation (at point index t_k) evicts the oldest LRU-log entry that is neither
 // stale nor was spliced to the front earlier in this scan (touched with first touch < t_k).
-//   fast path (one CTA, parallel): sort the creation times of the new voxels; rank the valid untouched
+//   fast path (one CTA, parallel): creation times of the new voxels in ascending order (bitmap over the point indices +
+//     prefix popcount); rank the valid untouched
 //     entries of the log head with block scans: the r-th of them is the victim of eviction r, PROVIDED every
 //     touched entry met on the way was indeed touched before the eviction it was examined for - checked
 //     in the same pass.
 //   slow path (thread 0, serial walk): when that check fails, i.e. a victim is touched again later in the
 //     same scan (it is then re-created fresh; its old incarnation stays visible to merge() as a ghost slot).
-constexpr int LRU_SORT_MAX = 8192;
-
-__device__ void block_bitonic_sort(int* a, int npow) {            // ascending, shared memory, whole CTA
-    for (int k = 2; k <= npow; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < npow; t += blockDim.x) {
-                const int u = t ^ j;
-                if (u > t) {
-                    const int x = a[t], y = a[u];
-                    const bool up = (t & k) == 0;
-                    if ((x > y) == up) { a[t] = y; a[u] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
 
 // serial walk (one thread): creation times ct[0..n_new) ascending
 __device__ void lru_serial_walk(const DevMap& m, DevCtl* ctl, const int* ct, int n_live0, int n_new) {
@@ -369,8 +353,10 @@ __device__ void lru_serial_walk(const DevMap& m, DevCtl* ctl, const int* ct, int
     ctl->st.n_evicted = ne; ctl->st.n_created = created;
 }
 
+constexpr int LRU_BITMAP_WORDS = 8192;            // creation-time bitmap in shared memory: scans of up to 262 144 points
+
 __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
-    __shared__ int sct[LRU_SORT_MAX];
+    __shared__ unsigned bm[LRU_BITMAP_WORDS];
     __shared__ int sh[34];
     __shared__ int s_bad;
     __shared__ long long s_headpos;
@@ -382,8 +368,8 @@ __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
         return;
     }
     const unsigned scan_id = ctl->scan_id;
-    if (n_new > LRU_SORT_MAX) {
-        // very many new voxels: creation times by ordered compaction over the points, then the serial walk
+    if (n > LRU_BITMAP_WORDS * 32) {
+        // scans beyond the bitmap: creation times by ordered compaction over the points, then the serial walk
         int base = 0;
         for (int b = 0; b * PT_BLOCK < n; b++) {
             const int i = b * PT_BLOCK + tid;
@@ -398,13 +384,28 @@ __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
         if (tid == 0) lru_serial_walk(m, ctl, m.ct, n_live0, n_new);
         return;
     }
-    // creation times = first touches of the voxels created by k_map_insert, sorted
-    int npow = 2;
-    while (npow < n_new) npow <<= 1;
-    for (int q = tid; q < npow; q += blockDim.x) sct[q] = q < n_new ? m.ft[m.newlist[q]] : INT_MAX;
+    // creation times = first touches of the voxels created by k_map_insert, ascending.  They are distinct point indices
+    // below n, so "sorting" them is a bitmap over the point indices + a prefix popcount (a shared-memory bitonic sort of up
+    // to 8192 keys was 0.19 ms per 200 k-point batch at C4, a quarter of the whole map update)
+    const int nw = (n + 31) >> 5;
+    for (int q = tid; q < nw; q += blockDim.x) bm[q] = 0u;
     if (tid == 0) { s_bad = 0; s_headpos = ctl->log_head; }
     __syncthreads();
-    block_bitonic_sort(sct, npow);
+    for (int q = tid; q < n_new; q += blockDim.x) { const int t = m.ft[m.newlist[q]]; atomicOr(&bm[t >> 5], 1u << (t & 31)); }
+    __syncthreads();
+    {
+        const int W = (nw + (int)blockDim.x - 1) / (int)blockDim.x, w0 = tid * W;
+        int c = 0;
+        for (int k = 0; k < W; k++) if (w0 + k < nw) c += __popc(bm[w0 + k]);
+        int total;
+        int pos = block_excl_scan(c, &total, sh);
+        for (int k = 0; k < W; k++) {
+            if (w0 + k >= nw) break;
+            for (unsigned word = bm[w0 + k]; word; word &= word - 1) m.ct[pos++] = (w0 + k) * 32 + (__ffs(word) - 1);
+        }
+    }
+    __syncthreads();
+    const int* sct = m.ct;                                  // sorted creation times (global scratch, read back through L2)
     const int slack = m.capacity - n_live0;                 // creations that still fit
     const int E = n_new - slack;                            // evictions if no victim is re-created
     const int sel = ctl->log_sel;
@@ -453,8 +454,6 @@ __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
     }
     __syncthreads();
     if (s_bad) {
-        for (int q = tid; q < n_new; q += blockDim.x) m.ct[q] = sct[q];
-        __syncthreads();
         if (tid == 0) lru_serial_walk(m, ctl, m.ct, n_live0, n_new);
         return;
     }
