@@ -42,6 +42,14 @@ class Scene:
             c.append(np.asarray(cc, float)); u.append(uu); v.append(vv); n.append(np.cross(uu, vv)); hu.append(a); hv.append(b)
         return Scene(np.array(c), np.array(n), np.array(u), np.array(v), np.array(hu, float), np.array(hv, float))
 
+    def near(self, o: np.ndarray, rmax: float) -> "Scene":
+        """The rectangles that rays starting at the origins `o` can reach within rmax (bounding-sphere test).  Only used
+        when a caller asks for culling (large scenes: C3 / C4 tools); the default path casts against every rectangle."""
+        ctr = o.mean(axis=0)
+        spread = float(np.linalg.norm(o - ctr, axis=1).max())
+        keep = np.linalg.norm(self.c - ctr, axis=1) - np.sqrt(self.hu ** 2 + self.hv ** 2) <= rmax + spread + 1e-6
+        return Scene(self.c[keep], self.n[keep], self.u[keep], self.v[keep], self.hu[keep], self.hv[keep])
+
     def cast(self, o: np.ndarray, d: np.ndarray, rmin: float, rmax: float) -> np.ndarray:
         """Range of the first hit of rays o + t d (N x 3 each); inf where nothing is hit in [rmin, rmax]."""
         denom = d @ self.n.T                                    # N x S
@@ -225,7 +233,8 @@ class Sequence:
     """Deterministic stream of SyncPackages. `package(i)` is a pure function of (seed, i)."""
 
     def __init__(self, scene: Scene | None = None, traj: Trajectory | None = None,
-                 sensor: SensorConfig | None = None, seed: int = 0xC0FFEE):
+                 sensor: SensorConfig | None = None, seed: int = 0xC0FFEE, cull: bool = False):
+        self.cull = cull                  # cast only against the rectangles within range of the scan (large scenes)
         self.scene = scene if scene is not None else scene_room()
         self.traj = traj if traj is not None else Trajectory()
         self.sensor = sensor if sensor is not None else SensorConfig()
@@ -264,7 +273,7 @@ class Sequence:
         R_wl = R @ s.r_il
         o = p + R @ s.p_il
         d_w = np.einsum("nij,nj->ni", R_wl, d_l)
-        rng_m = self.scene.cast(o, d_w, s.range_min, s.range_max)
+        rng_m = (self.scene.near(o, s.range_max) if self.cull else self.scene).cast(o, d_w, s.range_min, s.range_max)
         ok = np.isfinite(rng_m)
         # measurement noise: range + small bearing perturbation
         rr = rng_m + rng.normal(0, s.range_noise, n)
