@@ -423,6 +423,18 @@ __device__ void process_event(const DevMap& m, DevCtl* ctl, ActiveSet& as, WarpS
     __syncwarp();
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// pull everything merge() will ask about slot s into L2 (the fields of VoxRec, the covariance, the per-scan lists)
+__device__ __forceinline__ void prefetch_slot(const DevMap& m, int s) {
+    const char* h = reinterpret_cast<const char*>(m.hot + (size_t)s * 8);
+    prefetch_l2(h); prefetch_l2(h + 32);
+    const char* c = reinterpret_cast<const char*>(m.cov + (size_t)s * 36);
+    prefetch_l2(c); prefetch_l2(c + 128); prefetch_l2(c + 256);
+    prefetch_l2(m.sgroup + s); prefetch_l2(m.born_scan + s); prefetch_l2(m.full_scan + s); prefetch_l2(m.ft + s);
+    prefetch_l2(m.full_idx + s); prefetch_l2(m.evict_t + s); prefetch_l2(m.cnt + s); prefetch_l2(m.evn + s); prefetch_l2(m.seg_off + s);
+    prefetch_l2(m.skey + s);
+}
+
 __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
     __shared__ ActiveSet as;
     __shared__ WarpScratch wsc[16];
@@ -447,6 +459,20 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
         as_set_key(as, k, m.skey[A]);
     }
     __syncthreads();
+    // The rounds below are chains of dependent look-ups (neighbour key -> hash -> slot -> record -> covariance) by a
+    // single CTA; after the fill kernels have streamed hundreds of MB through the L2 (200 k-point scans) every link of the
+    // chain is a DRAM round trip.  One parallel pass first resolves the six neighbours of every active voxel and
+    // prefetches what merge() reads about them, so that the serial part runs out of the L2.
+    for (int k = tid; k < n0 * 8; k += blockDim.x) {
+        const int j = k >> 3, d = k & 7;
+        const int A = as.slot[j];
+        if (d == 6) { prefetch_slot(m, A); continue; }
+        if (d == 7) continue;
+        bool ok;
+        const unsigned long long nk = nbr_key(m.skey[A], d, ok);
+        if (!ok) continue;
+        for (int X = hash_find(m, nk); X >= 0; X = m.ghost[X]) prefetch_slot(m, X);
+    }
     for (int round = 0; round < 100000; round++) {
         const int n = as.n;
         // readiness (one warp per entry, lanes over the others): no other entry with an earlier event within MERGE_R
