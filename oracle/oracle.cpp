@@ -281,7 +281,7 @@ void VoxelGrid::updatePlane() {
     M3 evecs;
     eig3_sym(cov, evals, evecs);
     map->counters.n_refit++;
-    if (map) { const double mg = std::abs(evals[0] - plane_thresh); if (mg < map->margins.plane) map->margins.plane = mg; }
+    if (map->track_margins) { const double mg = std::abs(evals[0] - plane_thresh); if (mg < map->margins.plane) map->margins.plane = mg; }
     if (evals[0] > plane_thresh) {
         is_plane = false;                                           // Q13: old norm / cov stay
         return;
@@ -327,7 +327,7 @@ void VoxelGrid::merge() {
         if (nb->group_id == group_id || nb->update_enable || !nb->is_plane) continue;
         const double norm_distance = 1.0 - dot(nb->plane->norm, plane->norm);
         const double axis_distance = std::abs(dot(nb->plane->norm, nb->plane->mean) - dot(plane->norm, plane->mean));
-        {
+        if (map->track_margins) {
             const double ma = std::abs(norm_distance - map->merge_thresh_for_angle), md = std::abs(axis_distance - map->merge_thresh_for_distance);
             if (ma < map->margins.merge_angle) map->margins.merge_angle = ma;
             if (md < map->margins.merge_dist) map->margins.merge_dist = md;
@@ -437,7 +437,7 @@ bool VoxelMap::buildResidual(ResidualData& data, std::shared_ptr<VoxelGrid> vg) 
         double sigma_l = mul(mul(J_nq, data.plane_cov), tr(J_nq))[0];                 // == 0 (Q1)
         sigma_l += mul(mul(tr(data.plane_norm), data.cov_world), data.plane_norm)[0];
         if (std::abs(data.residual) < 3.0 * std::sqrt(sigma_l)) data.is_valid = true;
-        {
+        if (track_margins) {          // instrumentation, off by default (the timed baselines run without it)
             const double mg = std::abs(std::abs(data.residual) - 3.0 * std::sqrt(sigma_l));
 #ifdef _OPENMP
 #pragma omp critical(orc_margin)

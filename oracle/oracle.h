@@ -183,6 +183,7 @@ public:
     // instrumentation
     MapCounters counters;
     GateMargins margins;
+    bool track_margins = false;
     std::vector<VoxelKey> evicted;            // victims of the last build/update, in order
     uint64_t epoch = 0;
 };

@@ -268,6 +268,7 @@ int orc_get_lidar_cloud(void* h, float* out_xyzc, int cap, int* m) {
     return VMP_OK;
 }
 // smallest margins of the gate decisions since creation: plane fit, 3-sigma gate, merge angle, merge distance
+int orc_track_margins(void* h, int on) { H(h)->lio.map->track_margins = on != 0; return VMP_OK; }
 int orc_gate_margins(void* h, double* out4) {
     const GateMargins& g = H(h)->lio.map->margins;
     out4[0] = g.plane; out4[1] = g.gate; out4[2] = g.merge_angle; out4[3] = g.merge_dist;

@@ -80,6 +80,11 @@ class Oracle(HotPath):
             self._n = self.lidar_cloud().shape[0]
         return st
 
+    def track_margins(self, on: bool = True):
+        """Switch the gate-margin instrumentation on (off by default: the timed CPU baselines run without it)."""
+        self._lib.orc_track_margins.argtypes = [C.c_void_p, C.c_int]
+        self._lib.orc_track_margins(self._h, 1 if on else 0)
+
     def gate_margins(self) -> dict:
         """Smallest |margin| to the threshold over every gate decision so far (plane fit, 3-sigma gate, merge angle / distance)."""
         out = np.zeros(4)

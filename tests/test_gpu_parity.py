@@ -125,6 +125,7 @@ def test_measure_and_scan_teacher_forced(oracle_mod, estimate_ext):
     kw = dict(max_points_per_scan=4096, estimate_ext=estimate_ext)
     cfg = default_config(**kw)
     o = oracle_mod.Oracle(cfg)
+    o.track_margins(True)
     g_tf = HotPath(cfg)          # teacher-forced: measure + map_update with the oracle's data
     g_fr = HotPath(cfg)          # vmp_scan with the oracle's prior, its own posterior / map
     checked_iters = 0

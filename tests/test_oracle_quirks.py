@@ -205,6 +205,7 @@ def test_gate_margins_of_the_parity_workload_are_not_ties(oracle_mod):
     from voxelmapplus_fastlio2_b200 import synth
     from voxelmapplus_fastlio2_b200.ctypes_defs import default_config
     o = oracle_mod.Oracle(default_config(max_points_per_scan=4096))
+    o.track_margins(True)
     seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=3000))
     for pk in seq.packages(14):
         o.lio_process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
