@@ -102,6 +102,27 @@ def test_map_update_evict_and_recreate_same_scan(oracle_mod):
         assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"recreate scan {s}")
 
 
+def test_many_recreations_in_one_scan(oracle_mod):
+    """150 voxels are LRU victims early in a scan and are all hit again later in the same scan (a drive that turns back into
+    the oldest part of its map: the C3 city run overflowed a 64-entry queue here).  Every re-creation evicts a further voxel."""
+    o, g = _pair(oracle_mod, max_point_thresh=20, update_size_thresh=5, map_capacity=400, max_points_per_scan=4096)
+    cov = lambda n: np.tile((np.eye(3) * 1e-4).reshape(1, 9), (n, 1))
+    line = lambda idx, y=0.25: np.stack([np.asarray(idx) * 0.5 + 0.25, np.full(len(idx), y), np.full(len(idx), 0.25)], 1)
+    p0 = line(np.arange(400))                                     # fills the map exactly; oldest = voxel 0
+    p1 = np.concatenate([line(np.arange(1000, 1150)),             # 150 creations evict voxels 0..149 ...
+                         line(np.arange(150), 0.3),               # ... which are then hit again (re-created, evicting 150..299)
+                         line(np.arange(1000, 1150), 0.2)])
+    p2 = np.concatenate([line(np.arange(2000, 2100)), line(np.arange(300, 400), 0.3), line(np.arange(0, 150, 2), 0.35)])
+    for s, p in enumerate([p0, p1, p2, p0]):
+        p = p.astype(np.float32).astype(np.float64)
+        so, sg = o.map_update(p, cov(len(p))), g.map_update(p, cov(len(p)))
+        assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"
+        assert np.array_equal(o.dump_evicted(), g.dump_evicted()), f"scan {s}: eviction order differs"
+        assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"many re-creations, scan {s}")
+        if s == 1:
+            assert so["n_evicted"] == 300 and so["n_created"] == 300
+
+
 def test_capacity_smaller_than_scan_fails_loudly(oracle_mod):
     """documented restriction: the LRU victim must not have been touched in the same scan."""
     cfg = default_config(map_capacity=8, max_points_per_scan=1024)

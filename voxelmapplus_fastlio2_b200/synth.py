@@ -121,8 +121,12 @@ def scene_room(seed: int = 7, clutter: int = 14) -> Scene:
     return Scene.from_list(r)
 
 
-def scene_city(blocks: int = 6, block: float = 200.0, street: float = 24.0, height: float = 30.0) -> Scene:
-    """Scene B: Manhattan grid of facade planes + ground; streets between blocks."""
+def scene_city(blocks: int = 6, block: float = 200.0, street: float = 24.0, height: float = 30.0, pilasters: bool = False) -> Scene:
+    """Scene B: Manhattan grid of facade planes + ground; streets between blocks.
+    pilasters=True adds shallow boxes (0.6-1.0 m deep, ~1 m wide, 8-12 m high, every ~9.5 m) on both facades of the street
+    y = blocks/2 * block, the one tools/bench_c3.py drives: between cross streets the bare scene is two parallel planes and the
+    ground, which leaves the along-street direction unobservable for any point-to-plane matcher (the reference's estimator
+    picks up a spurious velocity in the first scans and never loses it)."""
     r = []
     ext = blocks * block
     r.append(((ext / 2, ext / 2, 0.0), (1, 0, 0), (0, 1, 0), ext, ext))          # ground
@@ -131,6 +135,17 @@ def scene_city(blocks: int = 6, block: float = 200.0, street: float = 24.0, heig
             lo = [i * block + street / 2, j * block + street / 2, 0]
             hi = [(i + 1) * block - street / 2, (j + 1) * block - street / 2, height]
             r += _box_faces(lo, hi, skip_bottom=True)[:4]
+    if pilasters:
+        y0 = (blocks // 2) * block
+        x, k = 6.0, 0
+        while x < ext - 6.0:
+            for side in (-1.0, 1.0):
+                yf = y0 + side * street / 2                      # facade plane
+                d = 0.6 + 0.2 * ((k + (side > 0)) % 3)
+                w = 1.0 + 0.3 * (k % 2)
+                r += _box_faces([x - w / 2, min(yf, yf - side * d), 0], [x + w / 2, max(yf, yf - side * d), 8.0 + 2.0 * (k % 3)], skip_bottom=True)
+            x += 8.0 + 1.5 * (k % 3)
+            k += 1
     return Scene.from_list(r)
 
 
