@@ -1,0 +1,55 @@
+"""Host-side pieces around the measurement: the synthetic driver (culling, parallel generation) and bench.py's accounting."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from voxelmapplus_fastlio2_b200 import synth  # noqa: E402
+
+
+def test_culled_cast_equals_full_cast():
+    """Scene.near() only drops rectangles no ray of the scan can reach: the culled cast returns the same ranges."""
+    sc = synth.scene_city(pilasters=True)
+    traj = synth.Trajectory(centre=(600.0, 600.0, 1.8), ax=560.0, ay=2.0, period=448.0)
+    full = synth.Sequence(scene=sc, traj=traj, sensor=synth.SensorConfig(pts_per_scan=1500), seed=7)
+    cull = synth.Sequence(scene=sc, traj=traj, sensor=synth.SensorConfig(pts_per_scan=1500), seed=7, cull=True)
+    for idx in (0, 400, 2240, 5000):
+        a, _ = full.cloud(idx)
+        b, _ = cull.cloud(idx)
+        assert a.shape == b.shape and a.shape[0] > 500
+        assert np.allclose(a, b, rtol=0, atol=1e-5)          # same hits (BLAS may round the last bit differently per shape)
+    near = sc.near(np.array([[600.0, 600.0, 1.8]]), 40.0)
+    assert 0 < near.c.shape[0] < sc.c.shape[0] // 4
+
+
+def test_city_pilasters_keep_the_base_scene():
+    a, b = synth.scene_city(), synth.scene_city(pilasters=True)
+    n = a.c.shape[0]
+    assert b.c.shape[0] > n and np.array_equal(a.c, b.c[:n]) and np.array_equal(a.n, b.n[:n])
+
+
+def test_parallel_generation_is_deterministic():
+    import bench
+    wl = dict(bench.WORKLOADS["c1"], pts=800)
+    par = bench.make_packages(wl, 11, 5, workers=2)
+    ser = bench.make_packages(wl, 11, 5, workers=1)
+    assert len(par) == len(ser) == 5
+    for p, q in zip(par, ser):
+        assert np.array_equal(p.cloud, q.cloud) and np.array_equal(p.imus, q.imus) and p.t0 == q.t0 and p.t1 == q.t1
+
+
+def test_algorithmic_bytes_model():
+    """bench.py's per-kernel algorithmic bytes (DESIGN.md §5 / SURVEY.md §8d): 132 B per point per executed iteration etc."""
+    import bench
+    st = dict(pt_iters=3 * 1000, n_ins=100, n_touch=50, refit_points=400, n_refit=10, n_merge=2, n_merge_voxels=50)
+    assert bench.algo_bytes("k_measure", st, 1000, 3) == 132 * 3000
+    assert bench.algo_bytes("k_set_scan", st, 1000, 3) == 108 * 1000
+    assert bench.algo_bytes("k_world_points", st, 1000, 3) == (84 + 96) * 1000
+    assert bench.algo_bytes("k_fill_refit", st, 1000, 3) == 72 * 400 + 432 * 10
+    assert bench.algo_bytes("k_fill_acc", st, 1000, 3) == 288 * 410
+    assert bench.algo_bytes("k_merge_rounds", st, 1000, 3) == 192 * 50 + 672 * 2
+    assert bench.algo_bytes("k_no_such_kernel", st, 1000, 3) == 0
+    assert bench.DEFAULT_WORKLOAD == "c2" and bench.WORKLOADS["c2"]["pts"] == 200000 and bench.WORKLOADS["c2"]["max_iter"] == 4
