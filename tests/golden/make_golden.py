@@ -51,6 +51,29 @@ def map_workload():
     return scans
 
 
+DS_LEAF = 0.2
+
+
+def downsample_cloud():
+    """3000 points (x y z curvature, float32) on two walls, a floor and clutter, incl. two non-finite points; no RNG library."""
+    i = np.arange(3000, dtype=np.float64)
+    a = (i * 0.6180339887498949) % 1.0
+    b = (i * 0.7548776662466927) % 1.0
+    c = (i * 0.5698402909980532) % 1.0
+    kind = np.arange(3000) % 4
+    p = np.empty((3000, 4))
+    w = 0.004 * np.sin(37.0 * i)
+    m = kind == 0; p[m, :3] = np.stack([6 * a[m] - 3, 2.26 + w[m], 2 * b[m]], 1)
+    m = kind == 1; p[m, :3] = np.stack([-3.13 + w[m], 5 * a[m] - 2.5, 2 * b[m]], 1)
+    m = kind == 2; p[m, :3] = np.stack([6 * a[m] - 3, 5 * b[m] - 2.5, -0.93 + w[m]], 1)
+    m = kind == 3; p[m, :3] = np.stack([7 * a[m] - 3.5, 6 * b[m] - 3, 3 * c[m] - 1], 1)
+    p[:, 3] = i / 30.0
+    p = p.astype(np.float32)
+    p[11, 0] = np.nan
+    p[1234, 2] = np.inf
+    return p
+
+
 def lio_packages():
     seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=LIO_PTS), seed=20261017)
     return list(seq.packages(LIO_SCANS))
@@ -90,6 +113,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "lio_golden.npz"), pos=np.array(pos), rot=np.array(rot), iters=np.array(iters),
                         effect=np.array(eff), H_last=H_last, b_last=b_last, P_last=P, digest=np.array(input_digest(pk)),
                         map_size=np.array(o.map_size()))
+    # ---- scan filter golden (pcl::VoxelGrid restatement, lio_builder.cpp:215-219)
+    ds = oracle_py.Oracle(default_config(max_points_per_scan=4096)).downsample(downsample_cloud(), DS_LEAF)
+    np.savez_compressed(os.path.join(HERE, "downsample_golden.npz"), out=ds, leaf=np.array(DS_LEAF))
     print("written", os.listdir(HERE))
 
 
