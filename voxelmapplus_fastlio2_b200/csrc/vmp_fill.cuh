@@ -217,24 +217,26 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
                     spt[3 * q] = s.pw[3 * (size_t)i]; spt[3 * q + 1] = s.pw[3 * (size_t)i + 1]; spt[3 * q + 2] = s.pw[3 * (size_t)i + 2];
                 }
                 __syncwarp();
-                int nsnap = 0, prev_job = -1, j = 0;
-                for (; j < K; j++) {                                           // pushPoint state machine, point order
-                    if (!(flags & F_UE)) break;
+                // pushPoint's control flow (voxel_map.cpp:42-95) depends on the counters only, never on the points: which steps
+                // refit, which step closes the voxel and the final counters have a closed form in (n, n_temp, newly_add_point, K)
+                // (checked against the step-by-step state machine on 6.2e6 parameter combinations).  The per-point loop below is
+                // left with the two recurrences that ARE sequential (running mean, sum p p^T) and the refit snapshots.
+                const bool init0 = (flags & F_INIT) != 0;
+                const int n0 = n, nw0 = nw;
+                const int jA = init0 ? -1 : (m.upt - 1 - n0 > 0 ? m.upt - 1 - n0 : 0);   // first updatePlane() past the early return (voxel not yet initialised)
+                const int j_init = init0 ? 0 : jA + 1;                                   // first step that sees is_init == true
+                int jc = m.maxpt - nt0 - 1;                                              // closing step: is_init before it, temp_points.size() >= max_point_thresh after it
+                if (jc < j_init) jc = j_init;
+                const bool closes = jc <= K - 1;
+                consumed = closes ? jc + 1 : K;
+                int nsnap = 0, prev_job = -1;
+                int next_refit = init0 ? m.upt - nw0 - 1 : jA;
+                for (int j = 0; j < consumed; j++) {                           // point order
                     const double pm = spt[3 * j + cm], pa = spt[3 * j + ia], pb = spt[3 * j + ib];
-                    mean_l = mean_l + (pm - mean_l) / (n + 1.0);
+                    mean_l = mean_l + (pm - mean_l) / (double)(n0 + j + 1);
                     ppt_l += pa * pb;
-                    n += 1;
-                    nt += 1;                                                   // temp_points.push_back (stored below)
-                    bool refit = false;
-                    if (!(flags & F_INIT)) {
-                        refit = n >= m.upt;                                    // updatePlane() every point, early return while n < thresh
-                    } else {
-                        nw += 1;
-                        if (nw >= m.upt) { refit = true; nw = 0; }
-                    }
-                    const bool was_init = (flags & F_INIT) != 0;
-                    if (refit) {
-                        flags |= F_INIT;
+                    if (j == next_refit) {
+                        next_refit = (!init0 && j == jA) ? j_init + (m.upt - nw0) - 1 : next_refit + m.upt;
                         if (nsnap == SNAP_MAX) {
                             __syncwarp();
                             const int jb = emit_jobs(m, ctl, slot, snap, nsnap, -1, prev_job);
@@ -243,17 +245,18 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
                             nsnap = 0;
                         }
                         double* sn = snap + nsnap * SNAP_W;
-                        if (lane == 0) { sn[0] = n; sn[1] = nt; }
+                        if (lane == 0) { sn[0] = n0 + j + 1; sn[1] = nt0 + j + 1; }
                         if (lane < 3) sn[2 + lane] = mean_l;
                         if (lane < 6) sn[5 + lane] = ppt_l;
                         nsnap++;
                     }
-                    if (was_init && nt >= m.maxpt) {                           // update_enable = false; temp_points freed
-                        flags &= ~F_UE; full_scan = scan_id; full_idx = sel[j]; nt = 0;
-                    }
                 }
-                consumed = j;
-                if (j == K && K < c && (flags & F_UE) && lane == 0) atomicOr(&ctl->err, E_QUEUE);   // cannot happen: K points always close the voxel
+                n = n0 + consumed;
+                nt = closes ? 0 : nt0 + consumed;                              // closing frees temp_points
+                { const int sdone = consumed - j_init; nw = (nw0 + (sdone > 0 ? sdone : 0)) % m.upt; }
+                if (!init0 && consumed - 1 >= jA) flags |= F_INIT;
+                if (closes) { flags &= ~F_UE; full_scan = scan_id; full_idx = sel[jc]; }
+                if (!closes && K < c && lane == 0) atomicOr(&ctl->err, E_QUEUE);          // cannot happen: K points always close the voxel
                 __syncwarp();
                 if (nsnap > 0) {
                     const int jb = emit_jobs(m, ctl, slot, snap, nsnap, -1, prev_job);
