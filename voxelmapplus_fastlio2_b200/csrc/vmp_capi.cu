@@ -2,11 +2,13 @@
 // life-cycle, HBM allocation, per-scan CUDA graph, host<->device staging.
 //
 // One handle owns: the voxel map (DevMap), the persistent residual buffer (DevScan), the
-// filter (DevFilter), a control block (DevCtl), one stream and one instantiated CUDA graph
-// that contains every kernel of a scan: set_scan, update_begin, max_iter x (measure,
-// solve), world_points and the 17 map-update kernels.  Later IEKF iterations become
+// filter (DevFilter), a control block (DevCtl), two streams and two instantiated CUDA graphs
+// (with / without the motion compensation in front) that contain every kernel of a scan:
+// set_scan, max_iter x measure (each with its solver CTA), state_out and world_points and the
+// map-update kernels, three of them on side branches.  Later IEKF iterations become
 // no-ops through the device-side `done` flag (ieskf.cpp:148 early break), so the graph
-// topology never changes and a scan is: 2 small H2D copies, 1 graph launch, 1 D2H copy.
+// topology never changes and a scan is: ONE H2D copy (header + prior + points from pinned
+// staging), ONE graph launch; the results are written to mapped host mailboxes by the kernels.
 //
 // There is no CPU implementation behind this file: without a B200 every call fails.
 #include <chrono>

@@ -3,11 +3,13 @@
 //   k_set_scan      lio_builder.cpp:224-229 + calcBodyCov (commons.cpp:18-45)
 //   k_measure       LIOBuilder::sharedUpdateFunc (lio_builder.cpp:250-311) +
 //                   VoxelMap::index / featmap.find / buildResidual (voxel_map.cpp:194-198,258-276):
-//                   one thread per point, gather through the voxel hash, warp-shuffle ->
-//                   shared-memory block reduction -> per-block partials (no fp atomics)
-//   k_ieskf_solve   IESKF::update body (ieskf.cpp:134-155): fixed-order final reduction of
-//                   the partials, 23x23 LU inverses, boxplus / boxminus, convergence flag,
-//                   posterior covariance — one CTA, every 23x23 product one thread per entry
+//                   one thread per point, gather through the voxel hash; H / b accumulated by the warp
+//                   (one entry per lane over the points staged in shared memory) -> per-block
+//                   partials (no fp atomics).  Block 0 of the launch is the solver CTA (vmp_solve.cuh):
+//                   IESKF::update body (ieskf.cpp:134-155) through the matrix-inversion lemma, fixed-order
+//                   reduction of the partials, boxplus / boxminus, convergence flag, posterior covariance
+//   k_undistort     point loop of undistortCloud (lio_builder.cpp:127-152)
+//   k_state_out     posterior -> mapped host mailbox
 //   k_world_points  lidarToWorld + pv_list loop (lio_builder.cpp:155-163, 231-245)
 //
 // Why no tensor cores: per point this is a 64-byte gather and ~1 kflop of 3x3 fp64

@@ -3,18 +3,17 @@
 // addToPlane / updatePlane / merge, voxel_map.cpp:29-186), decomposed into parallel phases:
 //
 //   k_map_insert     key (VoxelMap::index) + find-or-insert in the open-addressing hash
-//   k_map_count      per-voxel point count, first/last touching point index, touched list
-//   k_seg_scan       exclusive scan of the counts -> per-voxel segments
+//   k_map_count      per-voxel point count, first/last touching point index, touched list; its last CTA lays out the
+//                    per-voxel segments (disjoint, unordered: no scan kernel)
 //   k_seg_fill       point indices grouped by voxel (+ per-block counts for ordered compaction)
-//   k_lru_evict      exact LRU victims in creation order (cache.back() semantics, Q17)
-//   k_map_fill       one warp per touched voxel: sort its points by index, run the pushPoint
-//                    state machine in order, warp-parallel refit (3x3 eigen solve + ordered
-//                    accumulation of J Sigma J^T over the stored points)
-//   k_merge_prefilter / k_merge_serial
-//                    merge(): parallel static candidate filter, then an ordered event
-//                    simulation over the (few) voxels whose merge can succeed
-//   k_log_append     LRU log append in last-touch order, new stamps
-//   k_map_finalize   apply evictions (tombstones, free list), reset per-scan scratch
+//   k_lru_evict      exact LRU victims in creation order (cache.back() semantics, Q17); side branch of the graph
+//   k_fill_state / k_fill_refit / k_fill_acc   (vmp_fill.cuh) pushPoint state machine per touched voxel, the refits it
+//                    triggers as concurrent jobs (3x3 eigen solve, J Sigma J^T per stored point), ordered accumulation
+//   k_merge_prefilter / k_merge_rounds          (vmp_merge.cuh) merge(): parallel static candidate filter, then an event
+//                    simulation in rounds of spatially independent events over the (few) voxels whose merge can succeed
+//   k_log_append     LRU log append in last-touch order, new stamps; side branch
+//   k_map_finalize   apply evictions (tombstones, free list), reset per-scan scratch; its last CTA closes the update
+//                    (counters, maintenance requests, host mailbox)
 //
 // Why this is exact: a voxel's fill phase depends only on its own points in order; merge()
 // only involves voxels that are full (update_enable == false) and never refit again, so an

@@ -5,7 +5,8 @@
 // always.  Phase 1 (k_merge_prefilter, parallel, 8 lanes per voxel): which of the voxels that
 // received such points could merge with some neighbour at all, given the current planes and
 // groups, ignoring when during the scan the neighbour becomes eligible.  Phase 2
-// (k_merge_serial, one warp): an event simulation in point order over those voxels only.
+// (k_merge_rounds, one CTA, one warp per event): an event simulation over those voxels only, in
+// rounds of spatially independent events (see the footprint argument further down).
 // Per event the six neighbour look-ups run on six lanes; the accept/reject decisions are taken
 // strictly in the reference's order (-x -y -z +x +y +z, own plane updated in between, Q10); the
 // 6x6 covariance blend is spread over the lanes.  Exactness argument:
@@ -104,7 +105,7 @@ __device__ __forceinline__ int wake_dir(const DevMap& m, unsigned long long keyA
 }
 
 // 8 lanes per touched voxel, lanes 0..5 take one neighbour each; voxels whose merge() can succeed at
-// some time of this scan go into the active set of k_merge_serial with their first relevant event
+// some time of this scan go into the active set of k_merge_rounds with their first relevant event
 __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) {
     const int V = ctl->n_touched;
     const unsigned scan_id = ctl->scan_id;
