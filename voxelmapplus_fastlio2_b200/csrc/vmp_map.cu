@@ -219,16 +219,27 @@ __global__ void __launch_bounds__(256) k_map_insert(DevMap m, DevScan s, DevCtl*
 __global__ void __launch_bounds__(256) k_map_count(DevMap m, DevCtl* ctl) {
     __shared__ int s_top, s_last;
     const int n = ctl->n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned h = m.tpos[i];
-        int slot = -1;
-        if (h != 0xFFFFFFFFu) slot = m.tval[h];
-        m.pslot[i] = slot;
-        if (slot < 0) continue;
-        const int c = atomicAdd(&m.cnt[slot], 1);
-        if (c == 0) m.touched[atomicAdd(&ctl->n_touched, 1)] = slot;
-        atomicMin(&m.ft[slot], i);
-        atomicMax(&m.lt[slot], i);
+    {
+        // consecutive points of a scan fall into the same few voxels (a near voxel collects thousands of a 200 k-point scan):
+        // the lanes of a warp that hit the same voxel are grouped (match.any) and their leader issues ONE count / first /
+        // last-touch update for the group instead of four contended atomics per point
+        const int lane0 = threadIdx.x & 31;
+        for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane0; i0 < n; i0 += gridDim.x * blockDim.x) {    // warp-uniform trip count
+            const int i = i0 + lane0;
+            int slot = -1;
+            if (i < n) {
+                const unsigned h = m.tpos[i];
+                if (h != 0xFFFFFFFFu) slot = m.tval[h];
+                m.pslot[i] = slot;
+            }
+            const unsigned grp = __match_any_sync(0xffffffffu, slot >= 0 ? slot : -1 - lane0);   // lanes without a voxel stay alone
+            if (slot >= 0 && lane0 == __ffs(grp) - 1) {
+                const int c = atomicAdd(&m.cnt[slot], __popc(grp));
+                if (c == 0) m.touched[atomicAdd(&ctl->n_touched, 1)] = slot;
+                atomicMin(&m.ft[slot], i);                         // the leader is the group's lowest lane = lowest point index
+                atomicMax(&m.lt[slot], i0 + 31 - __clz(grp));
+            }
+        }
     }
     __threadfence();
     __syncthreads();
@@ -266,14 +277,19 @@ __global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl) {
     const int n = ctl->n;
     for (int b = blockIdx.x; b * PT_BLOCK < n; b += gridDim.x) {
         const int i = b * PT_BLOCK + threadIdx.x;
+        const int lane = threadIdx.x & 31;
         int is_last = 0;
-        if (i < n) {
-            const int slot = m.pslot[i];
-            if (slot >= 0) {
-                const int pos = m.seg_off[slot] + atomicAdd(&m.cursor[slot], 1);
-                m.seg[pos] = i;
-                is_last = (m.lt[slot] == i);
-            }
+        int slot = -1;
+        if (i < n) slot = m.pslot[i];
+        // one cursor update per (warp, voxel) group; the order inside a segment is irrelevant (it is selected / sorted later)
+        const unsigned grp = __match_any_sync(0xffffffffu, slot >= 0 ? slot : -1 - lane);
+        if (slot >= 0) {
+            const int leader = __ffs(grp) - 1;
+            int base = 0;
+            if (lane == leader) base = m.seg_off[slot] + atomicAdd(&m.cursor[slot], __popc(grp));
+            base = __shfl_sync(grp, base, leader);
+            m.seg[base + __popc(grp & ((1u << lane) - 1u))] = i;
+            is_last = (m.lt[slot] == i);
         }
         const int cl = __syncthreads_count(is_last);
         if (threadIdx.x == 0) m.blk_last[b] = cl;
