@@ -10,8 +10,9 @@ between steps and are outside the timed region on both arms.
 
   value   whole-job scans/s with the scan and the prior already resident in HBM (vmp_scan_dev), timed per
           step with CUDA events on the launching stream, max over ranks
-  e2e     the same through the host-buffer C-ABI call vmp_scan (H2D of scan+prior and D2H of the posterior
-          inside the timed region), wall clock measured inside the library
+  e2e     the same through the host-buffer C-ABI: the host LIOBuilder writes the scan into the handle's PINNED staging
+          area (vmp_scan_buffer) and calls vmp_scan_staged; the timed region (wall clock inside that call) holds the
+          H2D copy of header + prior + points, the graph, and the posterior / counters written back to mapped host memory
   N > 1   replicas only: one independent synthetic sequence (own map) per GPU, no collective on the path
 """
 from __future__ import annotations
@@ -390,7 +391,7 @@ def measure_workload(args, wl, pkgs, W, K, rank, world, local, full=True):
             "e2e": {"value": round(world * K / (e2e_ms_max * 1e-3), 2), "unit": "scans/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "p50_ms": round(float(np.median(e2e_host_ms[W:W + K])), 4),
-                    "timing": "wall clock inside the synchronous vmp_scan (pinned staging + one H2D copy + graph + mailbox write-back + sync)"},
+                    "timing": "wall clock inside the synchronous vmp_scan_staged: one H2D copy (header + prior + points) from the pinned staging area the host LIOBuilder filled, graph, mailbox write-back to mapped host memory, sync"},
             "host_loop": None if loop_host is None else {
                           "host_undistort_scans_per_s": round(loop_host, 1), "sync_scans_per_s": round(loop_sync, 1),
                           "pipelined_scans_per_s": round(loop_pipe, 1),
