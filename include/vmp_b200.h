@@ -103,6 +103,7 @@ typedef struct vmp_update_stats {
     int64_t n_merge;       /* successful pair merges                      */
     int64_t n_evicted;     /* LRU victims                                 */
     int64_t map_size;      /* live voxels afterwards                      */
+    int64_t n_mergevox;    /* distinct full plane voxels for which merge() ran (the N_mergeprobe of the byte model) */
 } vmp_update_stats;
 
 typedef struct vmp_scan_stats {

@@ -316,6 +316,7 @@ static inline double trace3(const M6& c, int o) { return c(o, o) + c(o + 1, o + 
 // voxel_map.cpp:138-186
 void VoxelGrid::merge() {
     map->counters.n_mergeprobe++;
+    if (merge_epoch != map->epoch) { merge_epoch = map->epoch; map->counters.n_mergevox++; }   // distinct (full plane voxel, update) pairs: SURVEY 8(d) N_mergeprobe
     VoxelKey near[6] = {
         {position.x - 1, position.y, position.z}, {position.x, position.y - 1, position.z},
         {position.x, position.y, position.z - 1}, {position.x + 1, position.y, position.z},

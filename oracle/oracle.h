@@ -135,7 +135,7 @@ struct GateMargins {
 
 struct MapCounters {                          // terms of the algorithmic-byte model
     int64_t n_points = 0, n_ins = 0, n_touch = 0, n_created = 0, n_refit = 0, refit_points = 0,
-            n_full = 0, n_mergeprobe = 0, n_merge = 0, n_evicted = 0;
+            n_full = 0, n_mergeprobe = 0, n_merge = 0, n_evicted = 0, n_mergevox = 0;
 };
 
 class VoxelMap;
@@ -161,6 +161,7 @@ public:
     V3 center = V3::zero();
     std::list<VoxelKey>::iterator cache_it;
     uint64_t touch_epoch = 0;                 // instrumentation: last update() call that touched it
+    uint64_t merge_epoch = 0;                 // instrumentation: last update() call in which merge() ran for it
 };
 typedef std::unordered_map<VoxelKey, std::shared_ptr<VoxelGrid>, VoxelKey::Hasher> Featmap;
 

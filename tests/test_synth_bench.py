@@ -42,14 +42,21 @@ def test_parallel_generation_is_deterministic():
 
 
 def test_algorithmic_bytes_model():
-    """bench.py's per-kernel algorithmic bytes (DESIGN.md §5 / SURVEY.md §8d): 132 B per point per executed iteration etc."""
+    """bench.py's algorithmic bytes are SURVEY.md §8(d), strictly: 132 B per point per executed iteration, 84 B per world point,
+    and the map formula split over the kernels that carry each term (the per-kernel terms add up to the formula)."""
     import bench
-    st = dict(pt_iters=3 * 1000, n_ins=100, n_touch=50, refit_points=400, n_refit=10, n_merge=2, n_merge_voxels=50)
-    assert bench.algo_bytes("k_measure", st, 1000, 3) == 132 * 3000
-    assert bench.algo_bytes("k_set_scan", st, 1000, 3) == 108 * 1000
-    assert bench.algo_bytes("k_world_points", st, 1000, 3) == (84 + 96) * 1000
-    assert bench.algo_bytes("k_fill_refit", st, 1000, 3) == 72 * 400 + 432 * 10
-    assert bench.algo_bytes("k_fill_acc", st, 1000, 3) == 288 * 410
-    assert bench.algo_bytes("k_merge_rounds", st, 1000, 3) == 192 * 50 + 672 * 2
-    assert bench.algo_bytes("k_no_such_kernel", st, 1000, 3) == 0
+    st = dict(pt_iters=3 * 1000, n_ins=100, n_touch=50, refit_points=400, n_refit=10, n_merge=2, n_mergevox=7, n_full=300, n_mergeprobe=250)
+    assert bench.algo_bytes("k_measure", st, 1000) == 132 * 3000
+    assert bench.algo_bytes("k_set_scan", st, 1000) == 84 * 1000
+    assert bench.algo_bytes("k_world_points", st, 1000) == 84 * 1000
+    assert bench.algo_bytes("k_fill_planes", st, 1000) == 72 * 400 + 432 * 10
+    assert bench.algo_bytes("k_merge_rounds", st, 1000) == 192 * 7 + 672 * 2          # distinct (voxel, scan) probes, not merge() calls
+    assert bench.algo_bytes("k_no_such_kernel", st, 1000) == 0
+    assert bench.algo_bytes("k_seg_fill", st, 1000) == 0                              # bookkeeping of the implementation: no compulsory bytes
+    total = 144 * 100 + 160 * 50 + 72 * 400 + 432 * 10 + 32 * 300 + 192 * 7 + 672 * 2
+    assert bench.map_bytes(st) == total
+    assert sum(bench.algo_bytes(k, st, 1000) for k in ("k_map_insert", "k_fill_state", "k_fill_planes", "k_merge_rounds")) == total
+    from voxelmapplus_fastlio2_b200.ctypes_defs import map_update_bytes
+    assert map_update_bytes(st) == total
+    assert bench.config_dict(bench.WORKLOADS["c2"], 40) == bench.config_dict(bench.WORKLOADS["c2"], 40)
     assert bench.DEFAULT_WORKLOAD == "c2" and bench.WORKLOADS["c2"]["pts"] == 200000 and bench.WORKLOADS["c2"]["max_iter"] == 4

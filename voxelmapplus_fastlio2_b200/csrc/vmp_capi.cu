@@ -153,7 +153,7 @@ void fill_update_stats(const DevStats& d, vmp_update_stats* st) {
     if (!st) return;
     st->n_points = d.n_points; st->n_ins = d.n_ins; st->n_touch = d.n_touch; st->n_created = d.n_created;
     st->n_refit = d.n_refit; st->refit_points = d.refit_points; st->n_full = d.n_full;
-    st->n_mergeprobe = d.n_mergeprobe; st->n_merge = d.n_merge; st->n_evicted = d.n_evicted; st->map_size = d.map_size;
+    st->n_mergeprobe = d.n_mergeprobe; st->n_merge = d.n_merge; st->n_evicted = d.n_evicted; st->map_size = d.map_size; st->n_mergevox = d.n_mergevox;
 }
 
 void prof_mark(void* ctx, int id) {

@@ -48,7 +48,7 @@ constexpr int E_LOG_CAP = 256;          // LRU log full (compaction was not serv
 constexpr int E_FILL_CAP = 512;         // refit job / contribution staging exhausted
 
 struct DevStats {                       // == vmp_update_stats order
-    long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size;
+    long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size, n_mergevox;
 };
 
 struct DevCtl {

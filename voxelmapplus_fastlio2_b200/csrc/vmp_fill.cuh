@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
     const int V = ctl->n_touched, npts = ctl->n;
     const unsigned scan_id = ctl->scan_id;
-    long long c_ins = 0, c_full = 0, c_probe = 0;
+    long long c_ins = 0, c_full = 0, c_probe = 0, c_pvox = 0;
     for (int vi = wg; vi < V; vi += nW) {
         const int slot = m.touched[vi];
         const int c = m.cnt[slot], off = m.seg_off[slot];
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
         c_full += events;
         if (first_job < 0) {
             // no refit in this scan: is_plane is final, settle the merge() bookkeeping here
-            if (!(flags & F_UE) && (flags & F_PLANE)) c_probe += events; else events = 0;
+            if (!(flags & F_UE) && (flags & F_PLANE)) { c_probe += events; c_pvox += events > 0 ? 1 : 0; } else events = 0;
         }
         if (lane == 0) { m.evn[slot] = events; m.vox_job[vi] = first_job; }
         __syncwarp();
@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(128) k_fill_state(DevMap m, DevScan s, DevCtl*
         if (c_ins) atomicAdd((unsigned long long*)&ctl->st.n_ins, (unsigned long long)c_ins);
         if (c_full) atomicAdd((unsigned long long*)&ctl->st.n_full, (unsigned long long)c_full);
         if (c_probe) atomicAdd((unsigned long long*)&ctl->st.n_mergeprobe, (unsigned long long)c_probe);
+        if (c_pvox) atomicAdd((unsigned long long*)&ctl->st.n_mergevox, (unsigned long long)c_pvox);
     }
 }
 
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(64) k_fill_acc(DevMap m, DevCtl* ctl) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
     const int V = ctl->n_touched;
-    long long c_probe = 0;
+    long long c_probe = 0, c_pvox = 0;
     for (int vi = wg; vi < V; vi += nW) {
         int j = m.vox_job[vi];
         if (j < 0) continue;
@@ -428,8 +429,9 @@ __global__ void __launch_bounds__(64) k_fill_acc(DevMap m, DevCtl* ctl) {
             flags = plane_final ? (flags | F_PLANE) : (flags & ~F_PLANE);
             hot_set_fn(m.hot, slot, flags, n);
             const int events = m.evn[slot];
-            if (!(flags & F_UE) && (flags & F_PLANE)) c_probe += events; else m.evn[slot] = 0;
+            if (!(flags & F_UE) && (flags & F_PLANE)) { c_probe += events; c_pvox += events > 0 ? 1 : 0; } else m.evn[slot] = 0;
         }
     }
     if (lane == 0 && c_probe) atomicAdd((unsigned long long*)&ctl->st.n_mergeprobe, (unsigned long long)c_probe);
+    if (lane == 0 && c_pvox) atomicAdd((unsigned long long*)&ctl->st.n_mergevox, (unsigned long long)c_pvox);
 }

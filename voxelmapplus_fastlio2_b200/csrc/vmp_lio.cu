@@ -266,8 +266,12 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
     }
     // lio_builder.cpp:224-229 reads x y z out of the PCL points; here they go straight into the pinned staging of the scan
     if (n > config.max_points_per_scan) { set_error("LIOBuilder::process: %d points exceed max_points_per_scan=%d", n, config.max_points_per_scan); return VMP_ERR_INVALID_ARG; }
+    // host_ms of this branch covers the whole timed region lio_builder.cpp:224-246 as the caller sees it: reading the points out
+    // of the caller's (pageable) cloud into the pinned staging, the upload, the graph, the results back in host memory
+    const auto t_region = std::chrono::steady_clock::now();
     { float* dst = vmp_scan_buffer(map); const CloudPoint* c = package.pts(); for (int i = 0; i < n; i++) { dst[3 * i] = c[i].x; dst[3 * i + 1] = c[i].y; dst[3 * i + 2] = c[i].z; } }
     const int r = vmp_scan_staged(map, &xs, kf.P(), n, stats);           // posterior written back into xs / kf.P()
+    if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_region).count();
     if (r) return r;
     kf.x() = st_load(reinterpret_cast<const double*>(&xs));
     return VMP_OK;

@@ -108,7 +108,7 @@ F_INIT, F_PLANE, F_UPDATE_ENABLE, F_MERGED = 1, 2, 4, 8
 class VmpUpdateStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "n_points", "n_ins", "n_touch", "n_created", "n_refit", "refit_points", "n_full",
-        "n_mergeprobe", "n_merge", "n_evicted", "map_size")]
+        "n_mergeprobe", "n_merge", "n_evicted", "map_size", "n_mergevox")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -134,7 +134,7 @@ def map_update_bytes(st: "VmpUpdateStats | dict") -> int:
     """Algorithmic bytes of one map update (SURVEY.md §8d / DESIGN.md)."""
     d = st if isinstance(st, dict) else st.as_dict()
     return (144 * d["n_ins"] + 160 * d["n_touch"] + 72 * d["refit_points"] + 432 * d["n_refit"]
-            + 32 * d["n_full"] + 192 * d["n_mergeprobe"] + 672 * d["n_merge"])
+            + 32 * d["n_full"] + 192 * d["n_mergevox"] + 672 * d["n_merge"])
 
 
 def dptr(a):
