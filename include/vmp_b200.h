@@ -27,7 +27,9 @@ typedef enum vmp_status {
     VMP_ERR_INVALID_ARG = -1,   /* null pointer, n < 0, n > max_points_per_scan, bad config */
     VMP_ERR_NO_DEVICE = -2,     /* no CUDA device / wrong architecture: there is NO CPU fallback */
     VMP_ERR_CUDA = -3,          /* a CUDA runtime call failed; see vmp_last_error() */
-    VMP_ERR_CAPACITY = -4,      /* voxel coordinate outside the packable range, slot pool exhausted */
+    VMP_ERR_CAPACITY = -4,      /* slot pool / hash / LRU log exhausted, map_capacity below one scan's voxels.  Reported by the update that hit it;
+                                   error bits are per update (a later update starts clean).  Points that cannot be keyed (non-finite, or voxel
+                                   coordinate outside +-2^20) are NOT errors: they are skipped and counted in vmp_update_stats.n_skipped */
     VMP_ERR_STATE = -5          /* call sequence error (e.g. scan before build) */
 } vmp_status;
 
@@ -53,7 +55,8 @@ typedef struct vmp_config {
     double merge_thresh_for_distance;/* 0.04 */
     int    map_capacity;             /* 100000 */
     /* ---- device-side additions ---- */
-    int    max_points_per_scan;      /* size of the persistent residual buffer (reference: hard 10000, lio_builder.cpp:25) */
+    int    max_points_per_scan;      /* size of the persistent residual buffer (reference: hard 10000, lio_builder.cpp:25); must cover RAW scans too:
+                                        the first scan and the input of the scan filter are staged unfiltered */
     int    device;                   /* CUDA device ordinal */
 } vmp_config;
 
@@ -104,6 +107,7 @@ typedef struct vmp_update_stats {
     int64_t n_evicted;     /* LRU victims                                 */
     int64_t map_size;      /* live voxels afterwards                      */
     int64_t n_mergevox;    /* distinct full plane voxels for which merge() ran (the N_mergeprobe of the byte model) */
+    int64_t n_skipped;     /* points NOT inserted: non-finite, or voxel coordinate outside +-2^20 (the reference would create far-away voxels) */
 } vmp_update_stats;
 
 typedef struct vmp_scan_stats {

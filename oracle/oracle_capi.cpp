@@ -55,6 +55,7 @@ void fill_stats(const VoxelMap& m, vmp_update_stats* st) {
     st->n_mergeprobe = c.n_mergeprobe; st->n_merge = c.n_merge; st->n_evicted = c.n_evicted;
     st->map_size = (int64_t)m.featmap.size();
     st->n_mergevox = c.n_mergevox;
+    st->n_skipped = 0;                        // the reference inserts every point (int64 keys)
 }
 std::vector<CloudPoint> to_cloud3(const float* p, int n) {
     std::vector<CloudPoint> c((size_t)n);

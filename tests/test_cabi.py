@@ -51,9 +51,9 @@ def test_library_does_not_link_the_oracle():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(VmpState) == 36 * 8
-    assert C.sizeof(VmpUpdateStats) == 11 * 8
+    assert C.sizeof(VmpUpdateStats) == 13 * 8
     assert C.sizeof(VmpPlane) == 3 * 8 + (3 + 9 + 3 + 36 + 3) * 8 + 4 * 4 + 2 * 8
-    assert C.sizeof(VmpScanStats) == 4 + 32 + 4 + 88 + 4 + 4
+    assert C.sizeof(VmpScanStats) == 4 + 32 + 4 + 104 + 4 + 4
     lib = bindings.load_library()
     lib.vmp_config_default.argtypes = [C.POINTER(VmpConfig)]
     c = VmpConfig()

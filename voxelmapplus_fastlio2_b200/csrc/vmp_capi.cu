@@ -86,7 +86,8 @@ struct vmp_handle_t {
     unsigned char* h_stage = nullptr; unsigned char* d_stage = nullptr;
     ScanIn* h_in = nullptr;     ScanIn* d_in = nullptr;
     StateOut* h_sout = nullptr; StateOut* a_sout = nullptr;
-    MapOut* h_mout = nullptr;   MapOut* a_mout = nullptr;
+    MapOut* h_mout = nullptr;   MapOut* a_mout = nullptr;      // TWO mailboxes, indexed by scan parity (seq & 1)
+    unsigned long long map_seq = 0;      // sequence number the last launched map update echoes in its mailbox
     float* h_raw = nullptr;              // = h_stage + PTS_OFF
     float4* h_cloud = nullptr; float4* a_cloud = nullptr;    // undistorted cloud written by k_undistort (pinned, mapped)
     DevDown ds{};                        // pcl::VoxelGrid downsample scratch (vmp_downsample.cu)
@@ -135,7 +136,7 @@ int dalloc(vmp_handle_t* h, T** p, size_t count) {
 int check_device_err(vmp_handle_t* h, int err) {
     if (!err) return VMP_OK;
     set_error("device reported error bits 0x%x:%s%s%s%s%s%s%s%s%s%s", err,
-              (err & E_KEY_RANGE) ? " voxel coordinate outside +-2^20;" : "",
+              (err & E_KEY_RANGE) ? " (key range);" : "",
               (err & E_POOL) ? " voxel slot pool exhausted;" : "",
               (err & E_LRU_EXHAUSTED) ? " map_capacity smaller than the voxels one scan touches (LRU victim was touched in the same scan);" : "",
               (err & E_REFIT_OVERFLOW) ? " refit of a voxel holding more than max_point_thresh points;" : "",
@@ -153,7 +154,7 @@ void fill_update_stats(const DevStats& d, vmp_update_stats* st) {
     if (!st) return;
     st->n_points = d.n_points; st->n_ins = d.n_ins; st->n_touch = d.n_touch; st->n_created = d.n_created;
     st->n_refit = d.n_refit; st->refit_points = d.refit_points; st->n_full = d.n_full;
-    st->n_mergeprobe = d.n_mergeprobe; st->n_merge = d.n_merge; st->n_evicted = d.n_evicted; st->map_size = d.map_size; st->n_mergevox = d.n_mergevox;
+    st->n_mergeprobe = d.n_mergeprobe; st->n_merge = d.n_merge; st->n_evicted = d.n_evicted; st->map_size = d.map_size; st->n_mergevox = d.n_mergevox; st->n_skipped = d.n_skipped;
 }
 
 void prof_mark(void* ctx, int id) {
@@ -256,9 +257,11 @@ int build_graph(vmp_handle_t* h) {
 }
 
 // consume the MapOut mailbox of the last map update (the stream has passed it): maintenance, error bits
+const MapOut& last_mout(const vmp_handle_t* h) { return h->h_mout[h->map_seq & 1ull]; }
 int finish_map(vmp_handle_t* h) {
-    const MapOut& o = *h->h_mout;
+    const MapOut& o = last_mout(h);
     h->map_pending = false;
+    if (o.seq != h->map_seq) { set_error("map update mailbox out of sequence (%llu, expected %llu)", o.seq, h->map_seq); return VMP_ERR_CUDA; }
     if (o.need_maint) h->launches += launch_map_maintenance(h->stream, h->m, h->ctl, h->sm_count, o.need_maint);   // rare; runs before the next update
     return check_device_err(h, o.err);
 }
@@ -454,12 +457,12 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_cloud, sizeof(float4) * (size_t)nmax + 64, cudaHostAllocMapped));
     VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_cloud, h->h_cloud, 0));
     VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_sout, sizeof(StateOut), cudaHostAllocMapped));
-    VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_mout, sizeof(MapOut), cudaHostAllocMapped));
+    VMP_CUDA_CHECK(cudaHostAlloc((void**)&h->h_mout, 2 * sizeof(MapOut), cudaHostAllocMapped));
     VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_sout, h->h_sout, 0));
     VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_mout, h->h_mout, 0));
     std::memset(h->h_in, 0, sizeof(ScanIn));
     std::memset(h->h_sout, 0, sizeof(StateOut));
-    std::memset(h->h_mout, 0, sizeof(MapOut));
+    std::memset(h->h_mout, 0, 2 * sizeof(MapOut));
     for (int b = 0; b < 2; b++) { VMP_CUDA_CHECK(cudaEventCreate(&h->pe0[b])); VMP_CUDA_CHECK(cudaEventCreate(&h->pe1[b])); }
 
     launch_map_init(h->stream, m, h->ctl);
@@ -545,8 +548,9 @@ static int map_update_common(vmp_handle h, const double* pts, const double* cov,
         h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, nullptr, &h->side);
     }
     h->map_built = true;
+    h->map_seq = h->seq;
     r = finish_sync(h);
-    fill_update_stats(h->h_mout->st, st);
+    fill_update_stats(last_mout(h).st, st);
     return r;
 }
 
@@ -622,12 +626,11 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
     VMP_CUDA_CHECK(cudaEventRecord(h->pe1[eb], h->stream));
     h->n_last = n;
     if (!pipe) {
-        const bool had_pending = h->map_pending;        // (only right after pipelining was switched off)
+        h->map_seq = seq;
         int r = finish_sync(h);
-        (void)had_pending;
         read_state(h, x, P, stats);
         if (stats) {
-            fill_update_stats(h->h_mout->st, &stats->map);
+            fill_update_stats(last_mout(h).st, &stats->map);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, h->pe0[eb], h->pe1[eb]);
             stats->gpu_ms = ms;
@@ -637,10 +640,10 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
     int r = wait_state(h, seq);
     if (r) return r;
     read_state(h, x, P, stats);
-    // the stream has passed the previous scan's map update: its mailbox is complete (this scan's is not written before
-    // its own map update ends, long after this call returns)
+    // the stream has passed the previous scan's map update: its mailbox (the other parity) is complete; this scan's update
+    // writes its own mailbox, so nothing it does can tear what is read here
     if (h->map_pending) {
-        fill_update_stats(h->h_mout->st, &h->lag_map);
+        fill_update_stats(last_mout(h).st, &h->lag_map);
         r = finish_map(h);
         if (stats) {
             float ms = 0.f;
@@ -649,6 +652,7 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
     }
     if (stats) stats->map = h->lag_map;
     h->map_pending = true;
+    h->map_seq = seq;
     return r;
 }
 
@@ -782,8 +786,9 @@ int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const floa
     launch_world_points(h->stream, h->grid_pts, h->s, h->f, h->ctl, 1);
     h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true, true, h->a_mout, nullptr, &h->side);
     h->map_built = true;
+    h->map_seq = h->seq;
     r = finish_sync(h);
-    fill_update_stats(h->h_mout->st, st);
+    fill_update_stats(last_mout(h).st, st);
     return r;
 }
 
@@ -881,7 +886,7 @@ int64_t vmp_launch_count(vmp_handle h) { return h ? h->launches : 0; }
 int vmp_debug_counters(vmp_handle h, int* out8) {
     if (!h || !out8) return VMP_ERR_INVALID_ARG;
     if (drain(h)) return VMP_ERR_CUDA;
-    for (int q = 0; q < 8; q++) out8[q] = h->h_mout->dbg[q];
+    for (int q = 0; q < 8; q++) out8[q] = last_mout(h).dbg[q];
     return VMP_OK;
 }
 

@@ -36,7 +36,7 @@ constexpr int T_INF = INT_MAX;          // "never" for per-scan times (point ind
 constexpr unsigned SCAN_NEVER = 0xFFFFFFFFu;
 
 // error bits reported through DevCtl::err
-constexpr int E_KEY_RANGE = 1;          // voxel coordinate outside +-2^20
+constexpr int E_KEY_RANGE = 1;          // (no longer raised: points outside +-2^20 voxels / non-finite points are counted skips, n_skipped)
 constexpr int E_POOL = 2;               // slot pool exhausted
 constexpr int E_LRU_EXHAUSTED = 4;      // eviction would have to take a voxel touched in the same scan
 constexpr int E_REFIT_OVERFLOW = 8;     // refit of a voxel holding more than max_point_thresh points (build overflow + thresh 1)
@@ -48,7 +48,7 @@ constexpr int E_LOG_CAP = 256;          // LRU log full (compaction was not serv
 constexpr int E_FILL_CAP = 512;         // refit job / contribution staging exhausted
 
 struct DevStats {                       // == vmp_update_stats order
-    long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size, n_mergevox;
+    long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size, n_mergevox, n_skipped;
 };
 
 struct DevCtl {
@@ -232,9 +232,15 @@ __host__ __device__ __forceinline__ unsigned hash_key(unsigned long long k) {
 }
 
 // VoxelMap::index (voxel_map.cpp:194-198): true division, floor, cast
+// Points whose voxel coordinate cannot be packed (|k| >= 2^20, i.e. 262 km at 0.25 m voxels) and non-finite points have no
+// voxel here: the filter treats them like "voxel not in the map" (Q2), the map update skips and counts them (the reference
+// would give them isolated far-away voxels; (long long)floor(NaN) is INT64_MIN on x86 but 0 on the device, hence the
+// explicit range test on the floating-point value).
 __device__ __forceinline__ bool voxel_index(double x, double y, double z, double vs, unsigned long long& pk) {
-    const long long kx = (long long)floor(x / vs), ky = (long long)floor(y / vs), kz = (long long)floor(z / vs);
-    if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) { pk = KEY_EMPTY; return false; }
+    const double fx = floor(x / vs), fy = floor(y / vs), fz = floor(z / vs);
+    const double lim = 1048576.0;
+    if (!(fx >= -lim && fx < lim && fy >= -lim && fy < lim && fz >= -lim && fz < lim)) { pk = KEY_EMPTY; return false; }   // false for NaN
+    const long long kx = (long long)fx, ky = (long long)fy, kz = (long long)fz;
     pk = pack_key(kx, ky, kz);
     return true;
 }

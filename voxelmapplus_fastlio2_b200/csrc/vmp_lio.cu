@@ -218,6 +218,12 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
         if (initializeImu(package.imus)) { status = MAP_INIT; last_cloud_end_time = package.cloud_end_time; }
         return VMP_OK;
     }
+    // every branch below stages the RAW cloud on the device (the first scan is never filtered, lio_builder.cpp:188-208): reject
+    // a cloud that does not fit BEFORE the filter state, the IMU hand-over and the cloud itself are advanced
+    if ((int)package.size() > config.max_points_per_scan) {
+        set_error("LIOBuilder::process: %d points exceed max_points_per_scan=%d (it has to cover raw, unfiltered scans)", (int)package.size(), config.max_points_per_scan);
+        return VMP_ERR_INVALID_ARG;
+    }
     // MAP_INIT (once): everything on the host like the reference.  LIO_MAPPING: IMU propagation on the host, the point
     // loop of undistortCloud on the device in front of the update, one upload + one graph.
     const bool on_device = status == LIO_MAPPING && device_undistort && imu_poses_fit(package);
@@ -265,7 +271,6 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
         return VMP_OK;
     }
     // lio_builder.cpp:224-229 reads x y z out of the PCL points; here they go straight into the pinned staging of the scan
-    if (n > config.max_points_per_scan) { set_error("LIOBuilder::process: %d points exceed max_points_per_scan=%d", n, config.max_points_per_scan); return VMP_ERR_INVALID_ARG; }
     // host_ms of this branch covers the whole timed region lio_builder.cpp:224-246 as the caller sees it: reading the points out
     // of the caller's (pageable) cloud into the pinned staging, the upload, the graph, the results back in host memory
     const auto t_region = std::chrono::steady_clock::now();

@@ -110,6 +110,7 @@ __device__ void map_end(const DevMap& m, DevCtl* ctl, MapOut* out) {
     ctl->need_rehash = (atomicAdd(&ctl->tombstones, 0) > (int)((m.hmask + 1) / 8)) ? 1 : 0;     // (other CTAs' atomics)
     ctl->need_log_compact = (ctl->log_tail + 4ll * m.nmax + 4 > m.log_cap) ? 1 : 0;
     if (out) {
+        out += ctl->seq & 1ull;                       // double-buffered by scan parity: a pipelined host reads scan k-1's while scan k runs
         out->st = ctl->st;
         out->err = ctl->err;
         out->need_maint = (ctl->need_rehash ? 1 : 0) | (ctl->need_log_compact ? 2 : 0);
@@ -117,6 +118,7 @@ __device__ void map_end(const DevMap& m, DevCtl* ctl, MapOut* out) {
         __threadfence_system();
         *(volatile unsigned long long*)&out->seq = ctl->seq;
     }
+    ctl->err = 0;                                     // error bits are per update: reported once, then cleared
 }
 
 // ------------------------------------------------------------------------- rehash (tombstone purge)
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256) k_map_insert(DevMap m, DevScan s, DevCtl*
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned long long pk;
         if (!voxel_index(s.pw[3 * (size_t)i], s.pw[3 * (size_t)i + 1], s.pw[3 * (size_t)i + 2], m.voxel_size, pk)) {
-            atomicOr(&ctl->err, E_KEY_RANGE);
+            atomicAdd((unsigned long long*)&ctl->st.n_skipped, 1ull);     // counted skip (see voxel_index), not an error
             m.tpos[i] = 0xFFFFFFFFu;
             continue;
         }

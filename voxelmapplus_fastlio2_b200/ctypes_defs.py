@@ -108,7 +108,7 @@ F_INIT, F_PLANE, F_UPDATE_ENABLE, F_MERGED = 1, 2, 4, 8
 class VmpUpdateStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "n_points", "n_ins", "n_touch", "n_created", "n_refit", "refit_points", "n_full",
-        "n_mergeprobe", "n_merge", "n_evicted", "map_size", "n_mergevox")]
+        "n_mergeprobe", "n_merge", "n_evicted", "map_size", "n_mergevox", "n_skipped")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
