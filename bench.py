@@ -196,17 +196,16 @@ def algo_bytes(kernel, st_sum, n_pts_sum):
         return 84 * n_pts_sum
     if kernel == "k_map_insert":
         return 32 * st_sum["n_full"] + 8 * st_sum["n_touch"]          # points into full voxels (24 + 8 key); key of a touch
-    if kernel == "k_fill_state":
-        return 144 * st_sum["n_ins"] + 152 * st_sum["n_touch"]        # append (72 in + 72 out); n / mean / ppt read + write
-    if kernel in ("k_fill_refit", "k_fill_acc", "k_fill_planes"):
-        return 72 * st_sum["refit_points"] + 432 * st_sum["n_refit"]  # shared by the refit kernels (one kernel since round 2)
+    if kernel in ("k_fill", "k_fill_state"):
+        # one kernel since round 2: append (72 in + 72 out), n / mean / ppt read + write, and the refits (stored points re-read, 6x6 cov + normal)
+        return 144 * st_sum["n_ins"] + 152 * st_sum["n_touch"] + 72 * st_sum["refit_points"] + 432 * st_sum["n_refit"]
     if kernel in ("k_merge_prefilter", "k_merge_rounds"):
         return 192 * st_sum["n_mergevox"] + 672 * st_sum["n_merge"]
     return 0
 
 
-MAP_KERNELS = ("k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict", "k_fill_state", "k_fill_refit",
-               "k_fill_acc", "k_fill_planes", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize", "k_map_end")
+MAP_KERNELS = ("k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict", "k_fill", "k_fill_state", "k_fill_refit",
+               "k_fill_acc", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize", "k_map_end")
 
 
 def map_bytes(st_sum):
@@ -317,8 +316,8 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
     g.close()
 
     # ---------------- pass 1c: the whole host loop (IMU propagation + compensation + update), per rank
-    def lio_loop(pipelined, device_undistort=True):
-        lb = LIOBuilder(cfg, pipelined=pipelined, device_undistort=device_undistort)
+    def lio_loop(pipelined, device_undistort=True, writeback=True):
+        lb = LIOBuilder(cfg, pipelined=pipelined, device_undistort=device_undistort, cloud_writeback=writeback)
         cl = [pk.cloud.copy() for pk in pkgs]
         t0 = None
         done = 0
@@ -338,11 +337,13 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
         return world * n / replicas.max_over_ranks(dt, dev)
     sampler = ClockSampler(local)
     sampler.start()                      # streaming from here on; the reported window opens at the first timed step of pass 2
-    loop_host = loop_sync = loop_pipe = None
+    loop_host = loop_sync = loop_pipe = loop_sync_lazy = loop_pipe_lazy = None
     if full and not args.no_loops:
         loop_host = lio_loop(False, device_undistort=False)
         loop_sync = lio_loop(False)
         loop_pipe = lio_loop(True)
+        loop_sync_lazy = lio_loop(False, writeback=False)
+        loop_pipe_lazy = lio_loop(True, writeback=False)
 
     # ---------------- pass 2: resident replay (scan + prior already in HBM), timed per step with CUDA events
     g = HotPath(cfg)
@@ -361,6 +362,8 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
             sampler.mark_begin()
             launches0 = g.launch_count()
             t_wall0 = time.perf_counter()
+            if args.ncu_range:              # ncu --profile-from-start off: only the timed steps of this pass are captured
+                torch.cuda.cudart().cudaProfilerStart()
         flush.zero_()                       # L2 flush between steps (256 MiB > 126 MB L2), outside the events
         torch.cuda.synchronize()
         st = g.scan_dev(d_clouds[i].data_ptr(), clouds[i].shape[0], d_priors[i].data_ptr())
@@ -370,6 +373,8 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
             res_ms.append(st.gpu_ms)
             res_stats.append(st)
     torch.cuda.synchronize()
+    if args.ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     if world > 1:
         dist.barrier()
     t_wall1 = time.perf_counter()
@@ -383,7 +388,7 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
 
     # ---------------- pass 3 (rank 0): per-kernel CUDA-event timing of the same steps -> live roofline
     roof = None
-    if rank == 0 and full:
+    if rank == 0 and full and not args.ncu_range:
         gp = HotPath(cfg)
         gp.first_scan(*first)
         gp.profile_enable(True)
@@ -486,9 +491,11 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
             "host_loop": None if loop_host is None else {
                           "host_undistort_scans_per_s": round(loop_host, 1), "sync_scans_per_s": round(loop_sync, 1),
                           "pipelined_scans_per_s": round(loop_pipe, 1),
+                          "sync_no_writeback_scans_per_s": round(loop_sync_lazy, 1), "pipelined_no_writeback_scans_per_s": round(loop_pipe_lazy, 1),
                           "what": "wall clock of the whole LIOBuilder.process loop, lio_builder.cpp:65-246 (host IMU propagation, motion "
                                   "compensation, update), all ranks / max over ranks: compensation on the host + vmp_scan / on the device in the "
-                                  "scan's graph (vmp_scan_raw) / the same with vmp_set_pipelined"},
+                                  "scan's graph (vmp_scan_raw) / the same with vmp_set_pipelined; no_writeback: the compensated cloud is not copied back into the "
+                                  "caller's buffer (vmp_set_raw_writeback 0; it stays readable through vmp_get_lidar_cloud)"},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
             "roofline": roof,
@@ -563,6 +570,7 @@ def main():
     ap.add_argument("--cpu-scans", type=int, default=300, help="bound of the CPU sample (scans)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-loops", action="store_true", help="skip the whole-host-loop pass (profiling runs)")
+    ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps of the resident pass (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

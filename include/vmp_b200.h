@@ -198,6 +198,11 @@ typedef struct vmp_pose { double offset; double acc[3], gyro[3], vel[3], pos[3],
  * the end-of-scan pose = x, the propagated prior).  poses: 2 <= n_poses <= 64.  Then exactly vmp_scan. */
 int vmp_scan_raw(vmp_handle h, vmp_state* x_inout, double* P_inout, float* cloud_xyzt, int n,
                  const vmp_pose* poses, int n_poses, vmp_scan_stats* stats);
+/* The copy of the compensated cloud back into the caller's buffer (the reference edits package.cloud in place,
+ * lio_builder.cpp:145-147) is on by default; on = 0 leaves the caller's buffer untouched - the compensated (and, with
+ * scan_resolution > 0, filtered) cloud of the last raw scan is always available through vmp_get_lidar_cloud, which is what
+ * the reference's consumers read (LIOBuilder::lidar_cloud, lio_node.cpp:185-228). */
+int vmp_set_raw_writeback(vmp_handle h, int on);
 /* SURVEY.md 8(f) row 1, second half: scan_filter.filter() = pcl::VoxelGrid<PointXYZINormal>::filter with leaf size
  * (leaf, leaf, leaf) (lio_builder.cpp:13-14, 215-219) on the device.  cloud_xyzc: N x 4 float32 (x, y, z, curvature).
  * out_xyzc: up to cap leaf centroids (x, y, z, mean curvature) in ascending leaf-index order, *m = number of leaves.
@@ -257,6 +262,8 @@ int vmp_lio_state(vmp_lio l, vmp_state* x, double* P, int* status);
 vmp_handle vmp_lio_map(vmp_lio l);
 /* motion compensation on the device (vmp_scan_raw; default) or on the host like the reference */
 int vmp_lio_set_device_undistort(vmp_lio l, int on);
+/* vmp_set_raw_writeback of the builder's map handle: 0 = process() does not copy the compensated cloud back into `cloud_xyzc` */
+int vmp_lio_set_cloud_writeback(vmp_lio l, int on);
 /* the prior (x, P after IMU propagation) that the last process() handed to the device update */
 int vmp_lio_prior(vmp_lio l, vmp_state* x, double* P);
 

@@ -123,6 +123,25 @@ def test_many_recreations_in_one_scan(oracle_mod):
             assert so["n_evicted"] == 300 and so["n_created"] == 300
 
 
+def test_unkeyable_points_are_counted_skips(oracle_mod):
+    """NaN / inf / out-of-range (> 2^20 voxels) world points are skipped and counted, they neither corrupt voxel (0,0,0) nor leave a
+    sticky error behind: the device map fed scan + 4 bad points equals the oracle map fed the scan alone, later updates return OK."""
+    o, g = _pair(oracle_mod, max_point_thresh=30, update_size_thresh=5, map_capacity=100000, max_points_per_scan=4096)
+    bad = np.array([[np.nan, 0.1, 0.1], [np.inf, 1.0, 1.0], [1.0e9, 0.0, 0.0], [0.2, -np.inf, np.nan]])
+    cb = np.tile((np.eye(3) * 1e-4).reshape(1, 9), (len(bad), 1))
+    for s, (p, c) in enumerate(wall_workload(21, scans=6, pts=1500)):
+        so = o.map_update(p, c) if s else o.map_build(p, c)
+        if s in (1, 3):
+            pg, cg = np.concatenate([p, bad]), np.concatenate([c, cb])        # appended: the point indices of the real points are unchanged
+        else:
+            pg, cg = p, c
+        sg = g.map_update(pg, cg) if s else g.map_build(pg, cg)
+        assert sg["n_skipped"] == (len(bad) if s in (1, 3) else 0)
+        for f in ("n_ins", "n_touch", "n_created", "n_refit", "refit_points", "n_full", "n_mergeprobe", "n_merge", "n_evicted", "map_size"):
+            assert sg[f] == so[f], (s, f)
+        assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"unkeyable points, scan {s}")
+
+
 def test_capacity_smaller_than_scan_fails_loudly(oracle_mod):
     """documented restriction: the LRU victim must not have been touched in the same scan."""
     cfg = default_config(map_capacity=8, max_points_per_scan=1024)
@@ -131,6 +150,9 @@ def test_capacity_smaller_than_scan_fails_loudly(oracle_mod):
     p = np.concatenate([p, p])
     with pytest.raises(VmpError, match="map_capacity"):
         g.map_update(p, np.tile(np.eye(3).reshape(1, 9) * 1e-4, (len(p), 1)))
+    # error bits are per update: the condition is reported once, a later update that fits starts clean
+    q = np.stack([np.arange(4) * 0.5 + 0.25, np.zeros(4), np.zeros(4)], 1)
+    g.map_update(q, np.tile(np.eye(3).reshape(1, 9) * 1e-4, (len(q), 1)))
 
 
 # --------------------------------------------------------------------------- measurement model + whole scan

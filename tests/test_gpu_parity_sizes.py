@@ -30,12 +30,11 @@ def test_c2_teacher_forced_50_scans(oracle_mod):
     print(r)
 
 
-def test_c3_city_slice_capacity_100k(oracle_mod):
-    """configs[2]: city drive at map_capacity 100 000: evicted keys per scan and final map bit-exact.  The map is full around
-    scan 600; this slice runs 900 scans (~60 000 evictions); tools/parity_run.py runs the same procedure over 2000+ scans
-    (profiles/r02_parity_full.json) - the oracle needs ~0.07 s per scan on the host."""
-    r = pc.c3_city_eviction(oracle_mod, scans=int(900 * SCALE))
-    assert SCALE < 1 or r["evicted"] > 20000, r
+def test_c3_city_2000_scans_capacity_100k(oracle_mod):
+    """configs[2]: city drive at map_capacity 100 000, >= 2000 scans: evicted keys per scan and final map bit-exact (the map is
+    full around scan 600; ~450 000 evictions afterwards).  tools/parity_run.py runs the same procedure over the full 10 000 scans."""
+    r = pc.c3_city_eviction(oracle_mod, scans=int(2000 * SCALE))
+    assert SCALE < 1 or r["evicted"] > 100000, r
     print(r)
 
 

@@ -49,13 +49,13 @@ def test_algorithmic_bytes_model():
     assert bench.algo_bytes("k_measure", st, 1000) == 132 * 3000
     assert bench.algo_bytes("k_set_scan", st, 1000) == 84 * 1000
     assert bench.algo_bytes("k_world_points", st, 1000) == 84 * 1000
-    assert bench.algo_bytes("k_fill_planes", st, 1000) == 72 * 400 + 432 * 10
+    assert bench.algo_bytes("k_fill", st, 1000) == 144 * 100 + 152 * 50 + 72 * 400 + 432 * 10
     assert bench.algo_bytes("k_merge_rounds", st, 1000) == 192 * 7 + 672 * 2          # distinct (voxel, scan) probes, not merge() calls
     assert bench.algo_bytes("k_no_such_kernel", st, 1000) == 0
     assert bench.algo_bytes("k_seg_fill", st, 1000) == 0                              # bookkeeping of the implementation: no compulsory bytes
     total = 144 * 100 + 160 * 50 + 72 * 400 + 432 * 10 + 32 * 300 + 192 * 7 + 672 * 2
     assert bench.map_bytes(st) == total
-    assert sum(bench.algo_bytes(k, st, 1000) for k in ("k_map_insert", "k_fill_state", "k_fill_planes", "k_merge_rounds")) == total
+    assert sum(bench.algo_bytes(k, st, 1000) for k in ("k_map_insert", "k_fill", "k_merge_rounds")) == total
     from voxelmapplus_fastlio2_b200.ctypes_defs import map_update_bytes
     assert map_update_bytes(st) == total
     assert bench.config_dict(bench.WORKLOADS["c2"], 40) == bench.config_dict(bench.WORKLOADS["c2"], 40)

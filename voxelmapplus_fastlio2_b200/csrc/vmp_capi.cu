@@ -22,6 +22,7 @@
 #include "vmp_device.cuh"
 #include "vmp_kernels.h"
 #include "vmp_state.cuh"
+#include "vmp_stage.hpp"
 
 namespace vmp {
 
@@ -88,6 +89,8 @@ struct vmp_handle_t {
     StateOut* h_sout = nullptr; StateOut* a_sout = nullptr;
     MapOut* h_mout = nullptr;   MapOut* a_mout = nullptr;      // TWO mailboxes, indexed by scan parity (seq & 1)
     unsigned long long map_seq = 0;      // sequence number the last launched map update echoes in its mailbox
+    vmp::StagePool pool;                 // helper threads of the pageable -> pinned staging copy (vmp_stage.hpp)
+    bool raw_writeback = true;           // vmp_scan_raw copies the compensated cloud back into the caller's buffer (reference: package.cloud is edited in place)
     float* h_raw = nullptr;              // = h_stage + PTS_OFF
     float4* h_cloud = nullptr; float4* a_cloud = nullptr;    // undistorted cloud written by k_undistort (pinned, mapped)
     DevDown ds{};                        // pcl::VoxelGrid downsample scratch (vmp_downsample.cu)
@@ -388,14 +391,7 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     DALLOC(m.tpos, nmax); DALLOC(m.pslot, nmax); DALLOC(m.seg, nmax);
     DALLOC(m.touched, nmax); DALLOC(m.newlist, nmax); DALLOC(m.hotlist, nmax); DALLOC(m.ev_slot, nmax); DALLOC(m.ev_time, nmax); DALLOC(m.ev_key, nmax);
     DALLOC(m.ct, nmax); DALLOC(m.act_slot, nmax); DALLOC(m.act_t, nmax);
-    m.job_cap = 2 * nmax + 64;
-    m.contrib_cap = (long long)nmax * (m.maxpt / m.upt + 2) + 1024;
-    m.bat_cap = (int)(m.contrib_cap / 32) + m.job_cap + 64;
-    DALLOC(m.job_slot, m.job_cap); DALLOC(m.job_n, m.job_cap); DALLOC(m.job_nt, m.job_cap); DALLOC(m.job_off, m.job_cap);
-    DALLOC(m.job_src, m.job_cap); DALLOC(m.job_next, m.job_cap); DALLOC(m.job_plane, m.job_cap);
-    DALLOC(m.job_mean, (size_t)3 * m.job_cap); DALLOC(m.job_ppt, (size_t)6 * m.job_cap); DALLOC(m.job_norm, (size_t)3 * m.job_cap);
-    DALLOC(m.bat_job, m.bat_cap); DALLOC(m.bat_idx, m.bat_cap); DALLOC(m.vox_job, nmax);
-    DALLOC(m.contrib, (size_t)m.contrib_cap * 36);
+    VMP_CUDA_CHECK(map_configure_kernels(m));
     const int nblk = (nmax + PT_BLOCK - 1) / PT_BLOCK;
     DALLOC(m.blk_last, nblk); DALLOC(m.blk_new, nblk);
     m.log_cap = std::max<long long>(8ll * m.pool, 8ll * nmax + 4096);
@@ -673,7 +669,7 @@ int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp
     int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan") : check_n(h, n, "vmp_scan");
     if (r) return r;
     if (n > 0 && !pts) { set_error("vmp_scan: null argument"); return VMP_ERR_INVALID_ARG; }
-    std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);          // the previous scan's copy out of this buffer is long done
+    h->pool.copy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);         // the previous scan's copy out of this buffer is long done
     r = scan_staged(h, x, P, n, stats, "vmp_scan");
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
@@ -712,11 +708,10 @@ int vmp_scan_raw(vmp_handle h, vmp_state* x, double* P, float* cloud_xyzt, int n
     if (n_poses < 2 || n_poses > MAX_POSES) { set_error("vmp_scan_raw: n_poses=%d outside [2, %d]", n_poses, MAX_POSES); return VMP_ERR_INVALID_ARG; }
     if (!h->map_built) { set_error("vmp_scan_raw: no map yet (call vmp_first_scan or vmp_map_build first)"); return VMP_ERR_STATE; }
     static_assert(sizeof(vmp_pose) == sizeof(DevPose), "vmp_pose layout");
-    // one pass over the caller's cloud: copy into the pinned staging and check the time order (lio_builder.cpp:75)
+    // one pass over the caller's cloud: copy into the pinned staging and check the time order (lio_builder.cpp:75), split
+    // over the staging helpers
     float* dst = h->h_raw;
-    std::memcpy(dst, cloud_xyzt, sizeof(float) * 4 * (size_t)n);
-    bool sorted = true;
-    for (int i = 1; i < n; i++) sorted &= !(dst[4 * (size_t)i + 3] < dst[4 * (size_t)i - 1]);
+    const bool sorted = h->pool.copy(dst, cloud_xyzt, sizeof(float) * 4 * (size_t)n, 4);
     if (!sorted) {      // rare for real sensors (points arrive in time order); any order of equal keys is a valid std::sort result
         struct P4 { float x, y, z, t; };
         P4* q = reinterpret_cast<P4*>(dst);
@@ -728,8 +723,9 @@ int vmp_scan_raw(vmp_handle h, vmp_state* x, double* P, float* cloud_xyzt, int n
     std::memcpy(h->h_in->x, x, sizeof(double) * 36);
     std::memcpy(h->h_in->P, P, sizeof(double) * 529);
     r = scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 4 * (size_t)n, stats, true);
-    // the compensated cloud was written to mapped host memory by the first kernel of the graph, before the posterior
-    std::memcpy(cloud_xyzt, h->h_cloud, sizeof(float) * 4 * (size_t)n);
+    // the compensated cloud was written to mapped host memory by the first kernel of the graph, before the posterior; it
+    // stays available through vmp_get_lidar_cloud, the copy into the caller's buffer can be switched off (vmp_set_raw_writeback)
+    if (h->raw_writeback) h->pool.copy(cloud_xyzt, h->h_cloud, sizeof(float) * 4 * (size_t)n);
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
 }
@@ -771,6 +767,12 @@ int vmp_set_pipelined(vmp_handle h, int on) {
     return VMP_OK;
 }
 int vmp_sync(vmp_handle h) { return check_n(h, 0, "vmp_sync"); }
+int vmp_set_raw_writeback(vmp_handle h, int on) {
+    int r = check_n(h, 0, "vmp_set_raw_writeback");
+    if (r) return r;
+    h->raw_writeback = on != 0;
+    return VMP_OK;
+}
 
 int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const float* pts, int n, vmp_update_stats* st) {
     int r = check_n(h, n, "vmp_first_scan");
@@ -914,7 +916,7 @@ const char* vmp_kernel_name(int id) {
     static const char* names[VMP_K_COUNT] = {
         "k_scan_in", "k_set_scan", "k_update_begin", "k_measure", "k_ieskf_solve", "k_world_points",
         "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
-        "k_fill_state", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
+        "k_fill", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
         "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_refit", "k_fill_acc", "k_undistort", "k_downsample"};
     return (id >= 0 && id < VMP_K_COUNT) ? names[id] : "?";
 }

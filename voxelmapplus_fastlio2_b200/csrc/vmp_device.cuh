@@ -45,7 +45,7 @@ constexpr int E_HASH_FULL = 32;
 constexpr int E_MERGE_DEPTH = 64;       // a merge succeeded at cascade depth > 2 inside one scan (parallel rounds would not be exact)
 constexpr int E_MERGE_CAP = 128;        // more than MERGE_CAP voxels in the active set of the merge simulation
 constexpr int E_LOG_CAP = 256;          // LRU log full (compaction was not served in time)
-constexpr int E_FILL_CAP = 512;         // refit job / contribution staging exhausted
+constexpr int E_FILL_CAP = 512;         // (unused since the refits run out of shared memory)
 
 struct DevStats {                       // == vmp_update_stats order
     long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size, n_mergevox, n_skipped;
@@ -69,8 +69,7 @@ struct DevCtl {
     int err;
     int pad0;
     unsigned ticket;                    // arrival counter of k_measure's measurement CTAs (the solver CTA waits on it)
-    int n_jobs, n_batches;              // refit jobs / 32-point batches of this map update
-    unsigned long long contrib_top;     // staged contributions (points)
+    int fill_next;                      // next touched voxel to be handed to a warp of k_fill
     int dbg_it;                         // which IEKF iteration's solver phase cycles go to dbg[3..6]
     int dbg[8];                         // debug counters of the last map update: [0] active set after the prefilter, [1] merge events simulated, [2] re-examinations that activated a voxel
     DevStats st;
@@ -90,7 +89,7 @@ __device__ __forceinline__ void map_begin_reset(DevCtl* ctl) {
     DevStats z = {};
     ctl->st = z;
     ctl->n_touched = 0; ctl->n_new = 0; ctl->n_evict = 0; ctl->n_hot = 0; ctl->n_ghost = 0;
-    ctl->n_jobs = 0; ctl->n_batches = 0; ctl->contrib_top = 0;
+    ctl->fill_next = 0;
     for (int q = 0; q < 3; q++) ctl->dbg[q] = 0;          // [3..7] belong to the solver CTA
 }
 
@@ -166,12 +165,6 @@ struct DevMap {
     int* ct;                            // creation times (sorted) [nmax]
     int* blk_last; int* blk_new;        // per 1024-point block counts
     int* act_slot; int* act_t;          // serial merge active set [nmax]
-    // refit jobs of one map update (vmp_fill.cuh)
-    int* job_slot; int* job_n; int* job_nt; long long* job_off; int* job_src; int* job_next; int* job_plane;
-    double* job_mean; double* job_ppt; double* job_norm;
-    int* bat_job; int* bat_idx; int* vox_job;
-    double* contrib;                    // [contrib_cap][36] staged J Sigma J^T
-    int job_cap, bat_cap; long long contrib_cap;
     // LRU log (two buffers for compaction)
     int* log_slot[2];
     unsigned long long* log_stamp[2];

@@ -47,5 +47,6 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
                       const SideStream* side);
 int launch_map_maintenance(cudaStream_t st, const DevMap& m, DevCtl* ctl, int sm_count, int what);
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl);
+cudaError_t map_configure_kernels(const DevMap& m);      // per-handle kernel attributes (dynamic shared memory of k_fill)
 
 }  // namespace vmp

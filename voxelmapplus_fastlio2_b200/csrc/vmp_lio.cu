@@ -326,6 +326,10 @@ int vmp_lio_set_device_undistort(vmp_lio l, int on) {
     l->b.device_undistort = on != 0;
     return VMP_OK;
 }
+int vmp_lio_set_cloud_writeback(vmp_lio l, int on) {
+    if (!l) return VMP_ERR_INVALID_ARG;
+    return vmp_set_raw_writeback(l->b.map, on);
+}
 int vmp_lio_prior(vmp_lio l, vmp_state* x, double* P) {
     if (!l) return VMP_ERR_INVALID_ARG;
     if (x) *x = l->b.prior_x;

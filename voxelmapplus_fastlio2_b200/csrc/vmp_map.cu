@@ -93,6 +93,7 @@ __global__ void k_map_init(DevMap m, DevCtl* ctl) {
     }
 }
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl) { k_map_init<<<592, 256, 0, st>>>(m, ctl); }
+cudaError_t map_configure_kernels(const DevMap& m);
 
 __global__ void k_map_begin(DevCtl* ctl) { map_begin_reset(ctl); }     // only for updates that do not start with k_world_points
 
@@ -101,7 +102,6 @@ __device__ void map_end(const DevMap& m, DevCtl* ctl, MapOut* out) {
     ctl->st.n_points = ctl->n;
     ctl->st.n_touch = ctl->n_touched;
     ctl->st.map_size = ctl->n_live;
-    ctl->st.n_refit = ctl->n_jobs;                    // every job is one updatePlane() that reached the eigen solve
     ctl->log_tail += ctl->n_touched;                  // exactly one last-touch entry per touched voxel
     ctl->stamp_base += (unsigned long long)ctl->n;
     ctl->scan_id += 1;
@@ -571,9 +571,13 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
     k_seg_fill<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_FILL);
     if (fork) cudaStreamWaitEvent(st, side->ev[1], 0);
     else { k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LRU_EVICT); }
-    k_fill_state<<<sm_count * 4, 128, 0, st>>>(m, s, ctl, build ? 1 : 0); launches++; mark(mk, VMP_K_MAP_FILL);
-    k_fill_refit<<<sm_count * 4, 128, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_FILL_REFIT);
-    k_fill_acc<<<sm_count * 8, 64, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_FILL_ACC);
+    if (build) { k_fill_build<<<sm_count * 4, 128, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_FILL); }
+    else {
+        // resident warps take voxels dynamically; shared memory per CTA = FILL_WARPS x fill_warp_bytes (opt-in size, set at create)
+        const size_t smem = FILL_WARPS * fill_warp_bytes(m.maxpt);
+        const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
+        k_fill<<<sm_count * (per_sm > 4 ? 4 : per_sm), FILL_WARPS * 32, smem, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_FILL);
+    }
     // the LRU-log append only needs the last-touch times: side branch next to the merge simulation
     if (fork && !build) {
         cudaEventRecord(side->ev[2], st); cudaStreamWaitEvent(side->st, side->ev[2], 0);
@@ -588,6 +592,11 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
     else { k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND); }
     k_map_finalize<<<sm_count, 256, 0, st>>>(m, ctl, out); launches++; mark(mk, VMP_K_MAP_FINALIZE);
     return launches;
+}
+
+// opt-in shared memory size of k_fill (once per handle)
+cudaError_t map_configure_kernels(const DevMap& m) {
+    return cudaFuncSetAttribute(k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILL_WARPS * fill_warp_bytes(m.maxpt)));
 }
 
 // Rare maintenance, launched by the host between scans only when the previous scan asked for it

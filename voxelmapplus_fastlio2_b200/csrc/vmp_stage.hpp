@@ -1,0 +1,154 @@
+// vmp_stage.hpp — host side of the scan upload: copy of the caller's (pageable) cloud into the handle's pinned staging
+// area by a few helper threads, optionally checking the time order of a raw scan in the same pass.
+//
+// Why: a 200 000-point scan is 2.4 MB (3.2 MB raw); one host core moves it at ~10 GB/s = 0.2-0.3 ms, which is as long as
+// the whole device side of the scan.  The copy is embarrassingly parallel, so the handle keeps a small pool of helpers
+// (default 3 + the calling thread; VMP_COPY_THREADS=0 disables it).  Helpers spin briefly after a job (back-to-back scans
+// find them awake) and then sleep on a condition variable (at sensor rate they cost nothing).
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace vmp {
+
+class StagePool {
+public:
+    StagePool() = default;
+    ~StagePool() { shutdown(); }
+    StagePool(const StagePool&) = delete;
+    StagePool& operator=(const StagePool&) = delete;
+
+    // dst <- src (bytes).  check_stride > 0: src is an array of records of check_stride floats whose last float is a time
+    // offset; returns false if those are not non-decreasing (lio_builder.cpp:75 sorts in that case).
+    bool copy(void* dst, const void* src, size_t bytes, int check_stride = 0) {
+        constexpr size_t MIN_PAR = 512 * 1024;
+        if (bytes < MIN_PAR || !ensure_started()) return slice(dst, src, bytes, 0, bytes, check_stride);
+        const int parts = (int)workers_.size() + 1;
+        // whole records per part, cache-line friendly
+        const size_t rec = check_stride > 0 ? (size_t)check_stride * sizeof(float) : 64;
+        const size_t nrec = bytes / rec;
+        job_.dst = (char*)dst; job_.src = (const char*)src; job_.bytes = bytes; job_.rec = rec; job_.nrec = nrec; job_.parts = parts;
+        job_.check_stride = check_stride;
+        sorted_.store(true, std::memory_order_relaxed);
+        remaining_.store(parts - 1, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(mu_);        // generation bump under the lock: a helper about to sleep cannot miss it
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
+        bool ok = run_part(0);
+        while (remaining_.load(std::memory_order_acquire) != 0) cpu_relax();
+        return ok && sorted_.load(std::memory_order_relaxed);
+    }
+
+    void shutdown() {
+        if (workers_.empty()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+        workers_.clear();
+    }
+
+private:
+    struct Job { char* dst; const char* src; size_t bytes, rec, nrec; int parts, check_stride; };
+
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+
+    bool ensure_started() {
+        if (started_) return !workers_.empty();
+        started_ = true;
+        int n = 3;
+        if (const char* e = std::getenv("VMP_COPY_THREADS")) n = std::atoi(e);
+        const unsigned hc = std::thread::hardware_concurrency();
+        if (hc > 0 && (unsigned)n + 1 > hc) n = (int)hc - 1;
+        if (n <= 0) return false;
+        try {
+            for (int i = 0; i < n; i++) workers_.emplace_back([this, i] { worker(i + 1); });
+        } catch (...) {
+            shutdown();
+            return false;
+        }
+        return true;
+    }
+
+    // copy [b0, b1) of the job; with check_stride also verify the order inside the slice and across its left edge
+    static bool slice(void* dst, const void* src, size_t bytes, size_t b0, size_t b1, int check_stride) {
+        (void)bytes;
+        bool ok = true;
+        if (check_stride <= 0) {
+            std::memcpy((char*)dst + b0, (const char*)src + b0, b1 - b0);
+            return true;
+        }
+        // block-wise so that the order check reads what the copy just pulled into the cache
+        const size_t rec = (size_t)check_stride * sizeof(float);
+        constexpr size_t BLK = 64 * 1024;
+        for (size_t p = b0; p < b1; p += BLK - BLK % rec) {
+            const size_t e = std::min(b1, p + (BLK - BLK % rec));
+            std::memcpy((char*)dst + p, (const char*)src + p, e - p);
+            const float* f = reinterpret_cast<const float*>((const char*)dst + p);
+            const size_t n = (e - p) / rec;
+            float prev = p > 0 ? *reinterpret_cast<const float*>((const char*)src + p - sizeof(float)) : f[check_stride - 1];
+            bool o = true;
+            for (size_t i = 0; i < n; i++) { const float t = f[i * check_stride + check_stride - 1]; o &= !(t < prev); prev = t; }
+            ok &= o;
+        }
+        return ok;
+    }
+
+    bool run_part(int id) {
+        const Job& j = job_;
+        const size_t per = (j.nrec + j.parts - 1) / j.parts;
+        size_t r0 = std::min(j.nrec, per * (size_t)id), r1 = std::min(j.nrec, per * (size_t)(id + 1));
+        size_t b0 = r0 * j.rec, b1 = (id == j.parts - 1) ? j.bytes : r1 * j.rec;     // the last part takes the tail bytes
+        if (b1 <= b0) return true;
+        return slice(j.dst, j.src, j.bytes, b0, b1, j.check_stride);
+    }
+
+    void worker(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            // spin for a while, then sleep
+            unsigned long long g = gen_.load(std::memory_order_acquire);
+            for (int spin = 0; g == seen && spin < 40000; spin++) { cpu_relax(); g = gen_.load(std::memory_order_acquire); }
+            if (g == seen) {
+                std::unique_lock<std::mutex> lk(mu_);
+                sleepers_.fetch_add(1, std::memory_order_release);
+                cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                sleepers_.fetch_sub(1, std::memory_order_release);
+                g = gen_.load(std::memory_order_acquire);
+            }
+            seen = g;
+            if (stop_) return;
+            if (id < job_.parts) {
+                if (!run_part(id)) sorted_.store(false, std::memory_order_relaxed);
+                remaining_.fetch_sub(1, std::memory_order_release);
+            }
+        }
+    }
+
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::atomic<unsigned long long> gen_{0};
+    std::atomic<int> remaining_{0}, sleepers_{0};
+    std::atomic<bool> sorted_{true};
+    Job job_{};
+    bool started_ = false, stop_ = false;
+};
+
+}  // namespace vmp
