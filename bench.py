@@ -196,6 +196,8 @@ def algo_bytes(kernel, st_sum, n_pts_sum):
         return 84 * n_pts_sum
     if kernel == "k_map_insert":
         return 32 * st_sum["n_full"] + 8 * st_sum["n_touch"]          # points into full voxels (24 + 8 key); key of a touch
+    if kernel == "k_world_insert_count":                              # one kernel since round 2: pv_list production + find-or-create
+        return 84 * n_pts_sum + 32 * st_sum["n_full"] + 8 * st_sum["n_touch"]
     if kernel in ("k_fill", "k_fill_state"):
         # one kernel since round 2: append (72 in + 72 out), n / mean / ppt read + write, and the refits (stored points re-read, 6x6 cov + normal)
         return 144 * st_sum["n_ins"] + 152 * st_sum["n_touch"] + 72 * st_sum["refit_points"] + 432 * st_sum["n_refit"]
@@ -204,7 +206,7 @@ def algo_bytes(kernel, st_sum, n_pts_sum):
     return 0
 
 
-MAP_KERNELS = ("k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict", "k_fill", "k_fill_state", "k_fill_refit",
+MAP_KERNELS = ("k_world_insert_count", "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict", "k_fill", "k_fill_classify", "k_fill_state", "k_fill_refit",
                "k_fill_acc", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize", "k_map_end")
 
 
@@ -437,9 +439,9 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
                              "GBps": round(b / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None,
                              "frac": round(b / (v[0] * 1e-3) / 1e9 / peak, 5) if v[0] > 0 else None}
         map_ms = sum(v[0] for k, v in prof.items() if k in MAP_KERNELS)
-        mb = map_bytes(agg)
-        iekf_ms = sum(v[0] for k, v in prof.items() if k in ("k_set_scan", "k_measure", "k_iekf", "k_ieskf_solve", "k_scan_out", "k_world_points"))
-        ib = 132 * agg["pt_iters"] + 84 * n_pts_sum + 84 * n_pts_sum
+        mb = map_bytes(agg) + 84 * n_pts_sum              # + the pv_list production (84 B / point), which opens the map update (k_world_insert_count)
+        iekf_ms = sum(v[0] for k, v in prof.items() if k in ("k_set_scan", "k_measure", "k_iekf", "k_ieskf_solve", "k_scan_out"))
+        ib = 132 * agg["pt_iters"] + 84 * n_pts_sum
         roof = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 6), "traffic": traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
@@ -447,12 +449,12 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
                 "algorithmic_bytes_per_launch": round(bytes_total / eff_launches, 1),
                 "avg_launch_us": round(top_ms * 1e3 / eff_launches, 3),
                 "kernel_share_of_step": round(top_ms / tot, 4) if tot > 0 else None,
-                "map_update": {"what": "whole VoxelMap::update: 8(d) map bytes / summed time of all map-update kernels",
+                "map_update": {"what": "pv_list production (84 B / point) + whole VoxelMap::update: 8(d) map bytes / summed time of all map-update kernels",
                                "algorithmic_MB_per_step": round(mb / K / 1e6, 3), "us_per_step": round(map_ms * 1e3 / K, 2),
                                "achieved": round(mb / (map_ms * 1e-3) / 1e9, 2) if map_ms > 0 else None,
                                "frac": round(mb / (map_ms * 1e-3) / 1e9 / peak, 5) if map_ms > 0 else None,
                                "counters_per_step": {k: round(v / K, 1) for k, v in agg.items() if k != "pt_iters"}},
-                "iekf": {"what": "set_scan + all measurement iterations + world points: 132 B x point-iterations + 84 + 84 B x points",
+                "iekf": {"what": "set_scan + all measurement iterations: 132 B x point-iterations + 84 B x points",
                          "algorithmic_MB_per_step": round(ib / K / 1e6, 3), "us_per_step": round(iekf_ms * 1e3 / K, 2),
                          "achieved": round(ib / (iekf_ms * 1e-3) / 1e9, 2) if iekf_ms > 0 else None,
                          "frac": round(ib / (iekf_ms * 1e-3) / 1e9 / peak, 5) if iekf_ms > 0 else None},

@@ -56,6 +56,7 @@ def test_algorithmic_bytes_model():
     total = 144 * 100 + 160 * 50 + 72 * 400 + 432 * 10 + 32 * 300 + 192 * 7 + 672 * 2
     assert bench.map_bytes(st) == total
     assert sum(bench.algo_bytes(k, st, 1000) for k in ("k_map_insert", "k_fill", "k_merge_rounds")) == total
+    assert bench.algo_bytes("k_world_insert_count", st, 1000) == 84 * 1000 + bench.algo_bytes("k_map_insert", st, 1000)
     from voxelmapplus_fastlio2_b200.ctypes_defs import map_update_bytes
     assert map_update_bytes(st) == total
     assert bench.config_dict(bench.WORKLOADS["c2"], 40) == bench.config_dict(bench.WORKLOADS["c2"], 40)

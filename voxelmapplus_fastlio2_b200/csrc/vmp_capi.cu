@@ -177,9 +177,9 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw) {
     if (raw) {      // lio_builder.cpp:127-152 in front of the timed region: the points are compensated where they were uploaded
         launch_undistort(st, h->grid_pts, h->d_in, (const DevPose*)(h->d_stage + IN_HDR), (float4*)(h->d_stage + PTS_OFF), h->a_cloud); k++; mark(mk, VMP_K_UNDISTORT);
     }
-    launch_set_scan(st, h->grid_pts, h->s, h->d_in, h->f, h->ctl); k++; mark(mk, VMP_K_SET_SCAN);
+    // the first iteration stages the scan itself (calcBodyCov per point, prior from the header): no staging kernel in front
     for (int it = 0; it < h->cfg.opti_max_iter; it++) {
-        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1); k++; mark(mk, VMP_K_MEASURE);
+        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1, it == 0 ? h->d_in : nullptr); k++; mark(mk, VMP_K_MEASURE);
     }
     // posterior -> host mailbox on the side stream (joined after the map update, which must not overwrite anything it
     // reads: f->x / f->P / the iteration counters are only written by the next scan)
@@ -191,8 +191,7 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw) {
     } else {
         launch_state_out(st, h->f, h->ctl, h->a_sout); k++; mark(mk, VMP_K_SCAN_OUT);
     }
-    launch_world_points(st, h->grid_pts, h->s, h->f, h->ctl, 0); k++; mark(mk, VMP_K_WORLD_POINTS);
-    k += launch_map_update(st, h->m, h->s, h->ctl, h->sm_count, false, true, h->a_mout, mk, &h->side);
+    k += launch_map_update(st, h->m, h->s, h->f, h->ctl, h->sm_count, false, 0, h->a_mout, mk, &h->side);
     if (fork) cudaStreamWaitEvent(st, h->ev_so[1], 0);
     return k;
 }
@@ -377,6 +376,8 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     m.pool = cfg->map_capacity + nmax + 1024;
     m.maxpt = cfg->max_point_thresh; m.upt = cfg->update_size_thresh; m.capacity = cfg->map_capacity;
     m.plane_thresh = cfg->plane_thresh; m.voxel_size = cfg->voxel_size;
+    m.heavy_points = 160;
+    if (const char* e = getenv("VMP_FILL_HEAVY")) m.heavy_points = atoi(e);      // tuning knob (0 = warp path only)
     m.th_angle = cfg->merge_thresh_for_angle; m.th_dist = cfg->merge_thresh_for_distance;
     size_t hs = 1024;
     while (hs < (size_t)m.pool * 4) hs <<= 1;
@@ -388,8 +389,8 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     DALLOC(m.n_temp, m.pool); DALLOC(m.newly, m.pool); DALLOC(m.born_scan, m.pool); DALLOC(m.full_scan, m.pool); DALLOC(m.full_idx, m.pool);
     DALLOC(m.cnt, m.pool); DALLOC(m.cursor, m.pool); DALLOC(m.ft, m.pool); DALLOC(m.lt, m.pool); DALLOC(m.seg_off, m.pool);
     DALLOC(m.evict_t, m.pool); DALLOC(m.ghost, m.pool); DALLOC(m.evn, m.pool); DALLOC(m.free_slots, m.pool);
-    DALLOC(m.tpos, nmax); DALLOC(m.pslot, nmax); DALLOC(m.seg, nmax);
-    DALLOC(m.touched, nmax); DALLOC(m.newlist, nmax); DALLOC(m.hotlist, nmax); DALLOC(m.ev_slot, nmax); DALLOC(m.ev_time, nmax); DALLOC(m.ev_key, nmax);
+    DALLOC(m.pslot, nmax); DALLOC(m.seg, nmax);
+    DALLOC(m.touched, nmax); DALLOC(m.newlist, nmax); DALLOC(m.hotlist, nmax); DALLOC(m.vox_cls, nmax); DALLOC(m.ev_slot, nmax); DALLOC(m.ev_time, nmax); DALLOC(m.ev_key, nmax);
     DALLOC(m.ct, nmax); DALLOC(m.act_slot, nmax); DALLOC(m.act_t, nmax);
     VMP_CUDA_CHECK(map_configure_kernels(m));
     const int nblk = (nmax + PT_BLOCK - 1) / PT_BLOCK;
@@ -539,9 +540,9 @@ static int map_update_common(vmp_handle h, const double* pts, const double* cov,
         Marker mk{prof_mark, h};
         h->pev_n = 0;
         VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream));
-        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, &mk, nullptr);
+        h->launches += launch_map_update(h->stream, h->m, h->s, h->f, h->ctl, h->sm_count, build, 2, h->a_mout, &mk, nullptr);
     } else {
-        h->launches += launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, build, false, h->a_mout, nullptr, &h->side);
+        h->launches += launch_map_update(h->stream, h->m, h->s, h->f, h->ctl, h->sm_count, build, 2, h->a_mout, nullptr, &h->side);
     }
     h->map_built = true;
     h->map_seq = h->seq;
@@ -785,8 +786,7 @@ int vmp_first_scan(vmp_handle h, const vmp_state* x, const double* P, const floa
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->f->P, P, sizeof(double) * 529, cudaMemcpyHostToDevice, h->stream));
     if (n > 0) VMP_CUDA_CHECK(cudaMemcpyAsync(h->s.raw, pts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
     VMP_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-    launch_world_points(h->stream, h->grid_pts, h->s, h->f, h->ctl, 1);
-    h->launches += 1 + launch_map_update(h->stream, h->m, h->s, h->ctl, h->sm_count, true, true, h->a_mout, nullptr, &h->side);
+    h->launches += launch_map_update(h->stream, h->m, h->s, h->f, h->ctl, h->sm_count, true, 1, h->a_mout, nullptr, &h->side);
     h->map_built = true;
     h->map_seq = h->seq;
     r = finish_sync(h);
@@ -914,10 +914,10 @@ int vmp_profile_read(vmp_handle h, double* ms, int64_t* launches) {
 }
 const char* vmp_kernel_name(int id) {
     static const char* names[VMP_K_COUNT] = {
-        "k_scan_in", "k_set_scan", "k_update_begin", "k_measure", "k_ieskf_solve", "k_world_points",
+        "k_scan_in", "k_set_scan", "k_update_begin", "k_measure", "k_ieskf_solve", "k_world_insert_count",
         "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
         "k_fill", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
-        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_refit", "k_fill_acc", "k_undistort", "k_downsample"};
+        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_classify", "k_fill_acc", "k_undistort", "k_downsample"};
     return (id >= 0 && id < VMP_K_COUNT) ? names[id] : "?";
 }
 

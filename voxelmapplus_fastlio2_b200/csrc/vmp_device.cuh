@@ -70,6 +70,7 @@ struct DevCtl {
     int pad0;
     unsigned ticket;                    // arrival counter of k_measure's measurement CTAs (the solver CTA waits on it)
     int fill_next;                      // next touched voxel to be handed to a warp of k_fill
+    int n_heavy, heavy_next;            // voxels of this update that go to the CTA path of k_fill, and the next one to be handed out
     int dbg_it;                         // which IEKF iteration's solver phase cycles go to dbg[3..6]
     int dbg[8];                         // debug counters of the last map update: [0] active set after the prefilter, [1] merge events simulated, [2] re-examinations that activated a voxel
     DevStats st;
@@ -84,12 +85,13 @@ struct DevCtl {
     unsigned cnt_ticket;                // arrival counter of k_map_count's CTAs (the last one lays out the segments)
 };
 
-// start of a map update: per-update counters (single thread)
-__device__ __forceinline__ void map_begin_reset(DevCtl* ctl) {
+// per-update counters (single thread).  Called at the END of every update (map_end) so that the next one starts clean without a
+// "begin" kernel; n_evict / the eviction list stay readable until then (vmp_dump_evicted)
+__device__ __forceinline__ void map_counters_reset(DevCtl* ctl) {
     DevStats z = {};
     ctl->st = z;
-    ctl->n_touched = 0; ctl->n_new = 0; ctl->n_evict = 0; ctl->n_hot = 0; ctl->n_ghost = 0;
-    ctl->fill_next = 0;
+    ctl->n_touched = 0; ctl->n_new = 0; ctl->n_hot = 0; ctl->n_ghost = 0;
+    ctl->fill_next = 0; ctl->n_heavy = 0; ctl->heavy_next = 0;
     for (int q = 0; q < 3; q++) ctl->dbg[q] = 0;          // [3..7] belong to the solver CTA
 }
 
@@ -136,6 +138,7 @@ struct DevMap {
     unsigned hmask;
     // parameters
     int pool, maxpt, upt, capacity;
+    int heavy_points;                   // k_fill: voxels whose refits of a scan loop over at least this many stored points take the CTA path (0: never)
     double plane_thresh, voxel_size, th_angle, th_dist;
     // slots
     double* hot;                        // [pool][8]
@@ -156,11 +159,12 @@ struct DevMap {
     // free list
     int* free_slots;
     // per-point per-scan
-    unsigned* tpos; int* pslot; int* seg;
+    int* pslot; int* seg;
     // lists
     int* touched;                       // [nmax]
     int* newlist;                       // [nmax] slots created by this map update
-    int* hotlist;                       // [nmax]
+    int* hotlist;                       // [nmax] voxels for the CTA path of k_fill
+    int* vox_cls;                       // [nmax] per touched voxel: 1 = CTA path
     int* ev_slot; int* ev_time; unsigned long long* ev_key;   // eviction list [nmax]
     int* ct;                            // creation times (sorted) [nmax]
     int* blk_last; int* blk_new;        // per 1024-point block counts

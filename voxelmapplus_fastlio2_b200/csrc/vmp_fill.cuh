@@ -172,182 +172,293 @@ __device__ __forceinline__ void snap_eig(const double* sn, double* evals, M3& ev
     eig3_sym(c00, c10, c11, c20, c21, c22, evals, evecs);
 }
 
-// per-warp refit state that lives across the snapshot groups of one voxel
+// ---- one voxel's fill phase, by one warp (CTA = false) or by all warps of the CTA (CTA = true: a voxel that goes from empty to
+// full within one scan runs ~10 refits over 10 .. 100 stored points, ~22 chunks of 32 contributions; the chunks are independent,
+// only their accumulation is ordered, so the warps of the CTA compute a batch of chunks at a time and the leader warp adds them
+// up in order).  The leader (warp 0 of the CTA, or the warp itself) owns the sequential parts.
+constexpr int CH_MAX = 32 * 8;          // chunks of one group of 32 snapshots (max_point_thresh <= 256)
+
+struct FillWork {                       // control block of the voxel in shared memory (written by the leader)
+    int consumed, sb, nt0, closes, any_refit, overflow, need_cov, avail, nsnap, nchunks;
+    unsigned pmask;
+    int pad;
+    short chunk_k[CH_MAX], chunk_base[CH_MAX];
+    double ev[32][12];                  // eigenvalues (3) + eigenvectors (9) of the group's snapshots
+};
+
+struct FillCounters { long long ins, full, probe, pvox, refit, rpts; };
+
+// shared memory of one warp of k_fill: [sel] [hist] [FillWork] [pts: 12 x ld doubles] [tile] [snap]
+__host__ __device__ inline int fill_sel_len(int maxpt) { const int ld = (maxpt + 1) & ~1; return ld < 32 ? 32 : ld; }   // a small segment is sorted whole (<= 32)
+__host__ __device__ inline size_t fill_warp_bytes(int maxpt) {
+    const size_t ld = (size_t)((maxpt + 1) & ~1);
+    return (size_t)fill_sel_len(maxpt) * 4 + SEL_BINS * 4 + sizeof(FillWork) + 12 * ld * 8 + 32 * TILE_LD * 8 + 32 * SNAP_W * 8;
+}
+struct FillRegion { int* sel; int* hist; FillWork* W; double* pts; double* tile; double* snap; };
+__device__ __forceinline__ FillRegion fill_region(unsigned char* base, int maxpt) {
+    const int ld = (maxpt + 1) & ~1;
+    FillRegion r;
+    r.sel = reinterpret_cast<int*>(base);
+    r.hist = r.sel + fill_sel_len(maxpt);
+    r.W = reinterpret_cast<FillWork*>(r.hist + SEL_BINS);
+    r.pts = reinterpret_cast<double*>(r.W + 1);
+    r.tile = r.pts + 12 * ld;
+    r.snap = r.tile + 32 * TILE_LD;
+    return r;
+}
+
+template <bool CTA>
+__device__ __forceinline__ void fill_sync() { if (CTA) __syncthreads(); else __syncwarp(); }
+
+// updatePlane() for the snapshots snap[0..ns) of the voxel, in order.  Leader registers: acc0 / acc1 (plane->cov, lane e holds
+// entry e, lanes 0..3 also entry 32 + e), the normal / centre of the last refit that found a plane.
 struct RefitAcc {
-    double acc0, acc1;              // plane->cov: lane e holds entry e, lanes 0..3 also entry 32 + e
-    double nrm[3], ctr[3];          // normal / centre of the last refit that found a plane (warp-uniform)
+    double acc0, acc1;
+    double nrm[3], ctr[3];
     int loaded, any_plane, plane_final, n_refit;
     long long refit_points;
 };
 
-// updatePlane() for the snapshots snap[0..ns) of one voxel, in order (whole warp calls).  Points: component-major in
-// shared memory (pts[k * ld + q]: xyz k = 0..2, covariance k = 3..11), stored-point order.
-__device__ void refit_snapshots(const DevMap& m, DevCtl* ctl, int slot, const double* snap, int ns, const double* pts, int ld, int npts_avail,
-                                double* tile, RefitAcc& ra) {
-    const int lane = threadIdx.x & 31;
-    if (!ra.loaded) {
-        const double* cv = m.cov + (size_t)slot * 36;
-        ra.acc0 = cv[lane];
-        ra.acc1 = lane < 4 ? cv[32 + lane] : 0.0;
-        ra.loaded = 1;
-    }
-    // the eigen-solves of the group, one per lane
-    double evals[3] = {0.0, 0.0, 0.0};
-    M3 evecs = zeros<3, 3>();
-    int plane = 0;
-    if (lane < ns) {
-        snap_eig(snap + lane * SNAP_W, evals, evecs);
-        plane = !(evals[0] > m.plane_thresh);                     // Q13: otherwise norm / cov stay
-    }
-    const unsigned pmask = __ballot_sync(0xffffffffu, plane != 0);
-    ra.n_refit += ns;
-    for (int k = 0; k < ns; k++) {
-        ra.plane_final = (pmask >> k) & 1u;
-        if (!ra.plane_final) continue;
-        ra.any_plane = 1;
-        const double* sn = snap + k * SNAP_W;
-        const int n = (int)sn[0];
-        int nt = (int)sn[1];
-        const V3 mean = v3(sn[2], sn[3], sn[4]);
-        double ev[3];
-        M3 evc;
+template <bool CTA>
+__device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRegion& R, unsigned char* smem0, size_t warp_bytes, int ns, RefitAcc& ra) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const bool leader = !CTA || wib == 0;
+    const int nwarps = CTA ? FILL_WARPS : 1, wix = CTA ? wib : 0;
+    const int ld = (m.maxpt + 1) & ~1;
+    FillWork* W = R.W;
+    const double* snap = R.snap;
+    if (leader) {
+        if (!ra.loaded) {
+            const double* cv = m.cov + (size_t)slot * 36;
+            ra.acc0 = cv[lane];
+            ra.acc1 = lane < 4 ? cv[32 + lane] : 0.0;
+            ra.loaded = 1;
+        }
+        // the eigen-solves of the group, one per lane
+        int plane = 0, nch = 0;
+        if (lane < ns) {
+            double evals[3];
+            M3 evecs;
+            snap_eig(snap + lane * SNAP_W, evals, evecs);
+            plane = !(evals[0] > m.plane_thresh);                 // Q13: otherwise norm / cov stay
 #pragma unroll
-        for (int e = 0; e < 3; e++) ev[e] = __shfl_sync(0xffffffffu, evals[e], k);
+            for (int e = 0; e < 3; e++) W->ev[lane][e] = evals[e];
 #pragma unroll
-        for (int e = 0; e < 9; e++) evc.a[e] = __shfl_sync(0xffffffffu, evecs.a[e], k);
-        const V3 nrm = v3(evc(0, 0), evc(1, 0), evc(2, 0));
-        ra.refit_points += nt;
-        if (nt > npts_avail) { if (lane == 0) atomicOr(&ctl->err, E_REFIT_OVERFLOW); nt = npts_avail; }   // build overflow + thresh 1
-        for (int base = 0; base < nt; base += 32) {
+            for (int e = 0; e < 9; e++) W->ev[lane][3 + e] = evecs.a[e];
+            if (plane) {
+                int nt = (int)snap[lane * SNAP_W + 1];
+                if (nt > W->avail) { atomicOr(&ctl->err, E_REFIT_OVERFLOW); nt = W->avail; }      // build overflow + thresh 1
+                nch = (nt + 31) >> 5;
+            }
+        }
+        const unsigned pmask = __ballot_sync(0xffffffffu, plane != 0);
+        int incl = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const int first = incl - nch;
+        for (int b = 0; b < nch; b++) { W->chunk_k[first + b] = (short)lane; W->chunk_base[first + b] = (short)(32 * b); }
+        if (lane == 31) { W->nchunks = incl; W->pmask = pmask; }
+    }
+    fill_sync<CTA>();
+    const int nchunks = W->nchunks;
+    const unsigned pmask = W->pmask;
+    for (int batch = 0; batch < nchunks; batch += nwarps) {
+        const int ch = batch + wix;
+        if (ch < nchunks) {
+            const int k = W->chunk_k[ch], base = W->chunk_base[ch];
+            const double* sn = snap + k * SNAP_W;
+            const int n = (int)sn[0];
+            int nt = (int)sn[1];
+            if (nt > W->avail) nt = W->avail;
             const int q = base + lane;
             if (q < nt) {
-                const V3 p = v3(pts[q], pts[ld + q], pts[2 * ld + q]);
+                const V3 mean = v3(sn[2], sn[3], sn[4]);
+                double ev[3];
+                M3 evc;
+#pragma unroll
+                for (int e = 0; e < 3; e++) ev[e] = W->ev[k][e];
+#pragma unroll
+                for (int e = 0; e < 9; e++) evc.a[e] = W->ev[k][3 + e];
+                const V3 nrm = v3(evc(0, 0), evc(1, 0), evc(2, 0));
+                const V3 p = v3(R.pts[q], R.pts[ld + q], R.pts[2 * ld + q]);
                 M3 S;
 #pragma unroll
-                for (int e = 0; e < 9; e++) S.a[e] = pts[(3 + e) * ld + q];
+                for (int e = 0; e < 9; e++) S.a[e] = R.pts[(3 + e) * ld + q];
+                double* tile = CTA ? reinterpret_cast<double*>(smem0 + (size_t)wib * warp_bytes + (reinterpret_cast<unsigned char*>(R.tile) - smem0)) : R.tile;
                 plane_contrib(p, S, mean, n, ev, evc, nrm, tile + lane * TILE_LD);
             }
-            __syncwarp();
-            const int np = nt - base < 32 ? nt - base : 32;
-            for (int qq = 0; qq < np; qq++) {                     // strictly in stored-point order (Q7)
-                ra.acc0 += tile[qq * TILE_LD + lane];
-                if (lane < 4) ra.acc1 += tile[qq * TILE_LD + 32 + lane];
-            }
-            __syncwarp();
         }
-        V3 ns_ = nrm;
-        if (-dot(mean, nrm) < 0.0) ns_ = neg(nrm);
+        fill_sync<CTA>();
+        if (leader) {
+            const int nb = nchunks - batch < nwarps ? nchunks - batch : nwarps;
+            for (int w = 0; w < nb; w++) {                            // chunks in order, points in stored order (Q7)
+                const int k = W->chunk_k[batch + w], base = W->chunk_base[batch + w];
+                int nt = (int)snap[k * SNAP_W + 1];
+                if (nt > W->avail) nt = W->avail;
+                const int np = nt - base < 32 ? nt - base : 32;
+                const double* tile = CTA ? reinterpret_cast<const double*>(smem0 + (size_t)w * warp_bytes + (reinterpret_cast<unsigned char*>(R.tile) - smem0)) : R.tile;
+                for (int qq = 0; qq < np; qq++) {
+                    ra.acc0 += tile[qq * TILE_LD + lane];
+                    if (lane < 4) ra.acc1 += tile[qq * TILE_LD + 32 + lane];
+                }
+            }
+        }
+        fill_sync<CTA>();
+    }
+    if (leader) {
+        ra.n_refit += ns;
+        ra.plane_final = (pmask >> (ns - 1)) & 1u;
+        for (int k = 0; k < ns; k++) if ((pmask >> k) & 1u) ra.refit_points += (int)snap[k * SNAP_W + 1];
+        if (pmask) {
+            ra.any_plane = 1;
+            const int k = 31 - __clz(pmask);                          // the last refit that found a plane
+            const double* sn = snap + k * SNAP_W;
+            const V3 mean = v3(sn[2], sn[3], sn[4]);
+            const V3 nrm = v3(W->ev[k][3], W->ev[k][6], W->ev[k][9]);
+            V3 ns_ = nrm;
+            if (-dot(mean, nrm) < 0.0) ns_ = neg(nrm);
 #pragma unroll
-        for (int e = 0; e < 3; e++) { ra.nrm[e] = ns_[e]; ra.ctr[e] = mean[e]; }
+            for (int e = 0; e < 3; e++) { ra.nrm[e] = ns_[e]; ra.ctr[e] = mean[e]; }
+        }
     }
 }
 
-// shared memory of one warp of k_fill: [sel: maxpt ints (padded)] [hist: SEL_BINS ints] [pts: 12 x ld doubles] [tile] [snap]
-__host__ __device__ inline int fill_sel_len(int maxpt) { const int ld = (maxpt + 1) & ~1; return ld < 32 ? 32 : ld; }   // a small segment is sorted whole (<= 32)
-__host__ __device__ inline size_t fill_warp_bytes(int maxpt) {
-    const size_t ld = (size_t)((maxpt + 1) & ~1);
-    return (size_t)fill_sel_len(maxpt) * 4 + SEL_BINS * 4 + 12 * ld * 8 + 32 * TILE_LD * 8 + 32 * SNAP_W * 8;
-}
-
-__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, DevCtl* ctl) {
-    extern __shared__ __align__(16) unsigned char fill_smem[];
+// region0: the shared-memory region the voxel is staged in (the warp's own, or warp 0's for the CTA path)
+template <bool CTA>
+__device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int slot, unsigned char* smem0, size_t warp_bytes, int npts, unsigned scan_id,
+                           FillCounters& fc) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const bool leader = !CTA || wib == 0;
+    const int nth = CTA ? FILL_WARPS * 32 : 32, tix = CTA ? (int)threadIdx.x : lane;
     const int ld = (m.maxpt + 1) & ~1;
-    unsigned char* base = fill_smem + (size_t)wib * fill_warp_bytes(m.maxpt);
-    int* sel = reinterpret_cast<int*>(base);
-    int* hist = sel + fill_sel_len(m.maxpt);
-    double* pts = reinterpret_cast<double*>(hist + SEL_BINS);
-    double* tile = pts + 12 * ld;
-    double* snap = tile + 32 * TILE_LD;
-    int* cand = reinterpret_cast<int*>(tile);
-
-    const int V = ctl->n_touched, npts = ctl->n;
-    const unsigned scan_id = ctl->scan_id;
-    long long c_ins = 0, c_full = 0, c_probe = 0, c_pvox = 0, c_refit = 0, c_rpts = 0;
-    while (true) {
-        int vi = 0;
-        if (lane == 0) vi = atomicAdd(&ctl->fill_next, 1);
-        vi = __shfl_sync(0xffffffffu, vi, 0);
-        if (vi >= V) break;
-        const int slot = m.touched[vi];
-        const int c = m.cnt[slot], off = m.seg_off[slot];
-        uint32_t flags; int n;
+    const FillRegion R = fill_region(smem0 + (CTA ? 0 : (size_t)wib * warp_bytes), m.maxpt);
+    FillWork* W = R.W;
+    // ---- leader: counters of the voxel, closed-form control flow, selection of the consumed points
+    uint32_t flags = 0;
+    int n = 0, c = 0, nw0 = 0, n0 = 0, jA = 0, j_init = 0, jc = 0, next_refit = 0, K = 0;
+    bool init0 = false;
+    double mean_l = 0.0, ppt_l = 0.0;
+    // addToPlane (voxel_map.cpp:29-34) is a dependent chain per point; its nine scalar updates run on nine lanes' worth of
+    // registers instead of one lane's: lane l < 3 owns mean[l], lane l < 6 owns ppt[l] (xx, yx, yy, zx, zy, zz).
+    const int cm = lane < 3 ? lane : 0;
+    const int ia = lane == 0 ? 0 : lane < 3 ? 1 : lane < 6 ? 2 : 0;
+    const int ib = (lane == 2 || lane == 4) ? 1 : lane == 5 ? 2 : 0;
+    if (leader) {
+        c = m.cnt[slot];
+        const int off = m.seg_off[slot];
         hot_get_fn(m.hot, slot, flags, n);
-        int events = c;                                     // full before this scan: merge() or nothing per point
-        if (flags & F_UE) {
-            const int nt0 = m.n_temp[slot], nw0 = m.newly[slot];
-            // addToPlane (voxel_map.cpp:29-34) is a dependent chain per point; its nine scalar updates run on nine
-            // lanes' worth of registers instead of one lane's: lane l < 3 owns mean[l], lane l < 6 owns ppt[l]
-            // (xx, yx, yy, zx, zy, zz).  A lone warp pays per instruction, and the three divisions become one.
-            const int cm = lane < 3 ? lane : 0;
-            const int ia = lane == 0 ? 0 : lane < 3 ? 1 : lane < 6 ? 2 : 0;
-            const int ib = (lane == 2 || lane == 4) ? 1 : lane == 5 ? 2 : 0;
-            double mean_l = m.hot[(size_t)slot * 8 + cm];
-            double ppt_l = m.ppt[(size_t)slot * 6 + (lane < 6 ? lane : 0)];
+        if (!(flags & F_UE)) {
+            if (lane == 0) W->consumed = -1;                      // full before this scan: merge() or nothing per point
+        } else {
+            const int nt0 = m.n_temp[slot];
+            nw0 = m.newly[slot];
+            mean_l = m.hot[(size_t)slot * 8 + cm];
+            ppt_l = m.ppt[(size_t)slot * 6 + (lane < 6 ? lane : 0)];
             // the voxel consumes at most K points before it closes (never more than its free room, at least one)
             const int room = m.maxpt - nt0;
-            int K = room < 1 ? 1 : room;
+            K = room < 1 ? 1 : room;
             if (K > c) K = c;
             // a voxel that build() left with more than max_point_thresh stored points (Q18) consumes one point and closes; the
-            // shared staging then only holds that point (a refit of such a voxel is reported: E_REFIT_OVERFLOW)
+            // staging then only holds that point (a refit of such a voxel is reported: E_REFIT_OVERFLOW)
             const bool overflow = nt0 + K > m.maxpt;
-            const int sb = overflow ? 0 : nt0;                                 // where the consumed points go in the staging
-            warp_select_sorted(m.seg + off, c, K, npts, sel, hist, cand);      // K <= max_point_thresh
+            warp_select_sorted(m.seg + off, c, K, npts, R.sel, R.hist, reinterpret_cast<int*>(R.tile));      // K <= max_point_thresh
             // pushPoint's control flow (voxel_map.cpp:42-95) depends on the counters only, never on the points: which steps
             // refit, which step closes the voxel and the final counters have a closed form in (n, n_temp, newly_add_point, K)
             // (checked against the step-by-step state machine on 6.2e6 parameter combinations).
-            const bool init0 = (flags & F_INIT) != 0;
-            const int n0 = n;
-            const int jA = init0 ? -1 : (m.upt - 1 - n0 > 0 ? m.upt - 1 - n0 : 0);   // first updatePlane() past the early return (voxel not yet initialised)
-            const int j_init = init0 ? 0 : jA + 1;                                   // first step that sees is_init == true
-            int jc = m.maxpt - nt0 - 1;                                              // closing step: is_init before it, temp_points.size() >= max_point_thresh after it
+            init0 = (flags & F_INIT) != 0;
+            n0 = n;
+            jA = init0 ? -1 : (m.upt - 1 - n0 > 0 ? m.upt - 1 - n0 : 0);       // first updatePlane() past the early return (voxel not yet initialised)
+            j_init = init0 ? 0 : jA + 1;                                       // first step that sees is_init == true
+            jc = m.maxpt - nt0 - 1;                                            // closing step: is_init before it, temp_points.size() >= max_point_thresh after it
             if (jc < j_init) jc = j_init;
             const bool closes = jc <= K - 1;
             const int consumed = closes ? jc + 1 : K;
-            int next_refit = init0 ? m.upt - nw0 - 1 : jA;
+            next_refit = init0 ? m.upt - nw0 - 1 : jA;
             const bool any_refit = next_refit < consumed;
-            // gather the consumed points once, in parallel: xyz always, covariances when they will be read (refit) or kept (append)
-            const bool need_cov = any_refit || !closes;
-            __syncwarp();
-            for (int q = lane; q < consumed; q += 32) {
-                const size_t i = (size_t)sel[q];
-                pts[sb + q] = s.pw[3 * i]; pts[ld + sb + q] = s.pw[3 * i + 1]; pts[2 * ld + sb + q] = s.pw[3 * i + 2];
-                if (need_cov) {
+            if (lane == 0) {
+                W->consumed = consumed; W->sb = overflow ? 0 : nt0; W->nt0 = nt0; W->closes = closes; W->any_refit = any_refit;
+                W->overflow = overflow; W->need_cov = any_refit || !closes; W->avail = overflow ? 0 : nt0 + consumed;
+            }
+        }
+    }
+    fill_sync<CTA>();
+    const int consumed = W->consumed;
+    int events = 0;
+    if (consumed < 0) {
+        events = c;
+    } else {
+        const int sb = W->sb, nt0 = W->nt0;
+        const bool closes = W->closes != 0, any_refit = W->any_refit != 0, overflow = W->overflow != 0, need_cov = W->need_cov != 0;
+        // ---- gather the consumed points once, in parallel: xyz always, covariances when they will be read (refit) or kept
+        // (append); and the stored points of earlier scans when a refit will loop over them
+        // (every copy below issues its twelve loads before the first store: the data is cold, one memory latency per batch)
+        for (int q = tix; q < consumed; q += nth) {
+            const size_t i = (size_t)R.sel[q];
+            double v[12];
+            v[0] = s.pw[3 * i]; v[1] = s.pw[3 * i + 1]; v[2] = s.pw[3 * i + 2];
+            if (need_cov) {
 #pragma unroll
-                    for (int k = 0; k < 9; k++) pts[(3 + k) * ld + sb + q] = s.pcov[9 * i + k];
-                }
+                for (int k = 0; k < 9; k++) v[3 + k] = s.pcov[9 * i + k];
             }
-            if (any_refit && !overflow) {                                      // the stored points of earlier scans (coalesced rows)
-                const double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
-                for (int k = 0; k < 12; k++)
-                    for (int q = lane; q < nt0; q += 32) pts[k * ld + q] = tp[(size_t)k * m.maxpt + q];
+#pragma unroll
+            for (int k = 0; k < 3; k++) R.pts[k * ld + sb + q] = v[k];
+            if (need_cov) {
+#pragma unroll
+                for (int k = 3; k < 12; k++) R.pts[k * ld + sb + q] = v[k];
             }
-            __syncwarp();
-            RefitAcc ra;
-            ra.acc0 = ra.acc1 = 0.0; ra.loaded = 0; ra.any_plane = 0; ra.plane_final = 0; ra.n_refit = 0; ra.refit_points = 0;
-            for (int e = 0; e < 3; e++) { ra.nrm[e] = 0.0; ra.ctr[e] = 0.0; }
+        }
+        if (any_refit && !overflow) {
+            const double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
+            for (int q = tix; q < nt0; q += nth) {
+                double v[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) v[k] = tp[(size_t)k * m.maxpt + q];
+#pragma unroll
+                for (int k = 0; k < 12; k++) R.pts[k * ld + q] = v[k];
+            }
+        }
+        fill_sync<CTA>();
+        // ---- the state machine (leader); the refits of every 32 snapshots by everybody
+        RefitAcc ra;
+        ra.acc0 = ra.acc1 = 0.0; ra.loaded = 0; ra.any_plane = 0; ra.plane_final = 0; ra.n_refit = 0; ra.refit_points = 0;
+        for (int e = 0; e < 3; e++) { ra.nrm[e] = 0.0; ra.ctr[e] = 0.0; }
+        int j = 0;
+        while (true) {
             int nsnap = 0;
-            const int avail = overflow ? 0 : nt0 + consumed;
-            for (int j = 0; j < consumed; j++) {                           // point order
-                const double pm = pts[cm * ld + sb + j], pa = pts[ia * ld + sb + j], pb = pts[ib * ld + sb + j];
-                mean_l = mean_l + (pm - mean_l) / (double)(n0 + j + 1);
-                ppt_l += pa * pb;
-                if (j == next_refit) {
-                    next_refit = (!init0 && j == jA) ? j_init + (m.upt - nw0) - 1 : next_refit + m.upt;
-                    if (nsnap == 32) {
-                        __syncwarp();
-                        refit_snapshots(m, ctl, slot, snap, nsnap, pts, ld, avail, tile, ra);
-                        nsnap = 0;
+            if (leader) {
+                for (; j < consumed && nsnap < 32; j++) {                  // point order
+                    const double pm = R.pts[cm * ld + sb + j], pa = R.pts[ia * ld + sb + j], pb = R.pts[ib * ld + sb + j];
+                    mean_l = mean_l + (pm - mean_l) / (double)(n0 + j + 1);
+                    ppt_l += pa * pb;
+                    if (j == next_refit) {
+                        next_refit = (!init0 && j == jA) ? j_init + (m.upt - nw0) - 1 : next_refit + m.upt;
+                        double* sn = R.snap + nsnap * SNAP_W;
+                        if (lane == 0) { sn[0] = n0 + j + 1; sn[1] = nt0 + j + 1; }
+                        if (lane < 3) sn[2 + lane] = mean_l;
+                        if (lane < 6) sn[5 + lane] = ppt_l;
+                        nsnap++;
                     }
-                    double* sn = snap + nsnap * SNAP_W;
-                    if (lane == 0) { sn[0] = n0 + j + 1; sn[1] = nt0 + j + 1; }
-                    if (lane < 3) sn[2 + lane] = mean_l;
-                    if (lane < 6) sn[5 + lane] = ppt_l;
-                    nsnap++;
                 }
+                if (lane == 0) W->nsnap = nsnap;
             }
-            __syncwarp();
-            if (nsnap > 0) refit_snapshots(m, ctl, slot, snap, nsnap, pts, ld, avail, tile, ra);
+            fill_sync<CTA>();
+            nsnap = W->nsnap;
+            if (nsnap == 0) break;                                         // (the leader's loop has reached `consumed`)
+            refit_group<CTA>(m, ctl, slot, R, smem0, warp_bytes, nsnap, ra);
+            fill_sync<CTA>();
+        }
+        // ---- write-back
+        if (!closes) {                                                      // temp_points.push_back of the consumed points (coalesced rows)
+            double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
+            for (int q = tix; q < consumed; q += nth) {
+                double v[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) v[k] = R.pts[k * ld + sb + q];
+#pragma unroll
+                for (int k = 0; k < 12; k++) tp[(size_t)k * m.maxpt + nt0 + q] = v[k];
+            }
+        }
+        if (leader) {
             n = n0 + consumed;
             const int nt = closes ? 0 : nt0 + consumed;                    // closing frees temp_points
             int nw;
@@ -356,12 +467,6 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, D
             if (closes) flags &= ~F_UE;
             if (!closes && K < c && lane == 0) atomicOr(&ctl->err, E_QUEUE);          // cannot happen: K points always close the voxel
             if (ra.n_refit > 0) flags = ra.plane_final ? (flags | F_PLANE) : (flags & ~F_PLANE);
-            // ---- write-back
-            if (!closes) {                                                  // temp_points.push_back of the consumed points (coalesced rows)
-                double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
-                for (int k = 0; k < 12; k++)
-                    for (int q = lane; q < consumed; q += 32) tp[(size_t)k * m.maxpt + nt0 + q] = pts[k * ld + sb + q];
-            }
             if (lane < 3) m.hot[(size_t)slot * 8 + lane] = mean_l;
             if (lane < 6) m.ppt[(size_t)slot * 6 + lane] = ppt_l;
             if (ra.any_plane) {
@@ -373,26 +478,88 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, D
             if (lane == 0) {
                 hot_set_fn(m.hot, slot, flags, n);
                 m.n_temp[slot] = nt; m.newly[slot] = nw;
-                if (closes) { m.full_scan[slot] = scan_id; m.full_idx[slot] = sel[jc]; }
+                if (closes) { m.full_scan[slot] = scan_id; m.full_idx[slot] = R.sel[jc]; }
             }
-            c_ins += consumed;
-            c_refit += ra.n_refit;
-            c_rpts += ra.refit_points;
+            fc.ins += consumed;
+            fc.refit += ra.n_refit;
+            fc.rpts += ra.refit_points;
             events = c - consumed;
-            __syncwarp();
         }
-        c_full += events;
+    }
+    if (leader) {
+        fc.full += events;
         // merge() runs for the points that land in a full plane voxel (Q11); everything else is inert (Q12)
-        if (!(flags & F_UE) && (flags & F_PLANE)) { c_probe += events; c_pvox += events > 0 ? 1 : 0; } else events = 0;
+        if (!(flags & F_UE) && (flags & F_PLANE)) { fc.probe += events; fc.pvox += events > 0 ? 1 : 0; } else events = 0;
         if (lane == 0) m.evn[slot] = events;
     }
+    fill_sync<CTA>();
+}
+
+// which touched voxels go to the CTA path of k_fill: those whose refits of this scan loop over many stored points (estimated
+// from the counters alone; a hint - either path handles every voxel)
+__device__ __forceinline__ void fill_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ void fill_classify(const DevMap& m, DevCtl* ctl, int vi) {
+    {
+        const int slot = m.touched[vi];
+        uint32_t flags; int n;
+        hot_get_fn(m.hot, slot, flags, n);
+        int heavy = 0;
+        if (flags & F_UE) {
+            const int c = m.cnt[slot], nt0 = m.n_temp[slot], nw0 = m.newly[slot];
+            const int room = m.maxpt - nt0;
+            int K = room < 1 ? 1 : room;
+            if (K > c) K = c;
+            const int nref = (K + nw0) / m.upt;
+            heavy = m.heavy_points > 0 && nref * (nt0 + (K + 1) / 2) >= m.heavy_points;
+            // the map data of a voxel is cold at the start of a scan (the L2 does not keep a 100 000-voxel map between scans):
+            // pull what k_fill reads about a filling voxel into the L2 one kernel ahead (k_fill is a chain of dependent loads per voxel)
+            fill_prefetch_l2(m.ppt + (size_t)slot * 6);
+            if (nref > 0) {
+                const char* cv = reinterpret_cast<const char*>(m.cov + (size_t)slot * 36);
+                fill_prefetch_l2(cv); fill_prefetch_l2(cv + 128); fill_prefetch_l2(cv + 256);
+                const double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
+                for (int k = 0; k < 12; k++)
+                    for (int q = 0; q < nt0; q += 16) fill_prefetch_l2(tp + (size_t)k * m.maxpt + q);
+            }
+        }
+        m.vox_cls[vi] = heavy;
+        if (heavy) m.hotlist[atomicAdd(&ctl->n_heavy, 1)] = slot;
+    }
+}
+
+__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, DevCtl* ctl) {
+    extern __shared__ __align__(16) unsigned char fill_smem[];
+    __shared__ int s_vi;
+    const int lane = threadIdx.x & 31;
+    const size_t wbytes = fill_warp_bytes(m.maxpt);
+    const int V = ctl->n_touched, npts = ctl->n, NH = ctl->n_heavy;
+    const unsigned scan_id = ctl->scan_id;
+    FillCounters fc = {0, 0, 0, 0, 0, 0};
+    // heavy voxels first (longest jobs first), one per CTA at a time
+    while (true) {
+        if (threadIdx.x == 0) s_vi = atomicAdd(&ctl->heavy_next, 1);
+        __syncthreads();
+        const int hi = s_vi;
+        __syncthreads();
+        if (hi >= NH) break;
+        fill_voxel<true>(m, s, ctl, m.hotlist[hi], fill_smem, wbytes, npts, scan_id, fc);
+    }
+    // everything else: a warp per voxel
+    while (true) {
+        int vi = 0;
+        if (lane == 0) vi = atomicAdd(&ctl->fill_next, 1);
+        vi = __shfl_sync(0xffffffffu, vi, 0);
+        if (vi >= V) break;
+        if (m.vox_cls[vi]) continue;
+        fill_voxel<false>(m, s, ctl, m.touched[vi], fill_smem, wbytes, npts, scan_id, fc);
+    }
     if (lane == 0) {
-        if (c_ins) atomicAdd((unsigned long long*)&ctl->st.n_ins, (unsigned long long)c_ins);
-        if (c_full) atomicAdd((unsigned long long*)&ctl->st.n_full, (unsigned long long)c_full);
-        if (c_probe) atomicAdd((unsigned long long*)&ctl->st.n_mergeprobe, (unsigned long long)c_probe);
-        if (c_pvox) atomicAdd((unsigned long long*)&ctl->st.n_mergevox, (unsigned long long)c_pvox);
-        if (c_refit) atomicAdd((unsigned long long*)&ctl->st.n_refit, (unsigned long long)c_refit);
-        if (c_rpts) atomicAdd((unsigned long long*)&ctl->st.refit_points, (unsigned long long)c_rpts);
+        if (fc.ins) atomicAdd((unsigned long long*)&ctl->st.n_ins, (unsigned long long)fc.ins);
+        if (fc.full) atomicAdd((unsigned long long*)&ctl->st.n_full, (unsigned long long)fc.full);
+        if (fc.probe) atomicAdd((unsigned long long*)&ctl->st.n_mergeprobe, (unsigned long long)fc.probe);
+        if (fc.pvox) atomicAdd((unsigned long long*)&ctl->st.n_mergevox, (unsigned long long)fc.pvox);
+        if (fc.refit) atomicAdd((unsigned long long*)&ctl->st.n_refit, (unsigned long long)fc.refit);
+        if (fc.rpts) atomicAdd((unsigned long long*)&ctl->st.refit_points, (unsigned long long)fc.rpts);
     }
 }
 

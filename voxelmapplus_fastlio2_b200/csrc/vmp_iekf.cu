@@ -10,7 +10,7 @@
 //                   reduction of the partials, boxplus / boxminus, convergence flag, posterior covariance
 //   k_undistort     point loop of undistortCloud (lio_builder.cpp:127-152)
 //   k_state_out     posterior -> mapped host mailbox
-//   k_world_points  lidarToWorld + pv_list loop (lio_builder.cpp:155-163, 231-245)
+//   (lidarToWorld + the pv_list loop, lio_builder.cpp:155-163, 231-245, open the map update: k_world_insert_count in vmp_map.cu)
 //
 // Why no tensor cores: per point this is a 64-byte gather and ~1 kflop of 3x3 fp64
 // algebra followed by a 27-value reduction; there is no dense contraction to tile.
@@ -100,9 +100,12 @@ struct MeasShared {
 
 // Two resident CTAs per SM (four of the 128-thread estimate_ext variant): 128 registers, no spills.  Three (80 registers,
 // 196 B of spills) measured the same at 200 k points and slower at 20 k.
-template <bool EXT>
+// FIRST: the first iteration of a scan's graph.  It takes the scan straight from the header `in` (round 1 ran a staging kernel,
+// k_set_scan, in front): every thread evaluates calcBodyCov (commons.cpp:18-45, lio_builder.cpp:224-229) for its points, keeps
+// point_lidar / cov_lidar for the later iterations and the map update, and reads the prior from where the header says it is.
+template <bool EXT, bool FIRST>
 __global__ void __launch_bounds__(EXT ? 128 : 256, EXT ? 4 : 2)
-k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
+k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* __restrict__ in) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;                 // upper triangle of H, b, effect count
@@ -113,11 +116,11 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     // a CTA is either the solver or a measurement CTA: one overlay for both (static shared memory is limited to 48 KB)
     union Overlay { SolveShared<EXT> sol; MeasShared<EXT> meas; };
     __shared__ __align__(16) unsigned char sh_raw[sizeof(Overlay)];
-    if (ctl->done) return;
+    if (!FIRST && ctl->done) return;
     // launched with solve = 1 the grid has one more CTA: block 0 runs this iteration's 23-dof solve (IESKF::update body,
     // vmp_solve.cuh), starting with the part that needs no measurement while the other CTAs measure
     if (solve && blockIdx.x == 0) {
-        ieskf_solve_cta<EXT, EXT ? 128 : 256>(*reinterpret_cast<SolveShared<EXT>*>(sh_raw), f, ctl, partials, (int)gridDim.x - 1);
+        ieskf_solve_cta<EXT, EXT ? 128 : 256>(*reinterpret_cast<SolveShared<EXT>*>(sh_raw), f, ctl, partials, (int)gridDim.x - 1, FIRST ? in : nullptr);
         return;
     }
     MeasShared<EXT>& sh = *reinterpret_cast<MeasShared<EXT>*>(sh_raw);
@@ -125,9 +128,16 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     const int pb = (int)blockIdx.x - solve, npb = (int)gridDim.x - solve;      // measurement CTA index / count
     // the pose products and the two covariance blocks every point needs, one entry per thread (same evaluation order
     // as mul(): s = a0 b0; s += a1 b1; s += a2 b2)
+    const double* xsrc = f->x;
+    const double* Psrc = f->P;
+    if (FIRST) {
+        const int mode = in->mode;
+        if (mode & SCAN_STATE_HDR) { xsrc = in->x; Psrc = in->P; }
+        else if (mode & SCAN_STATE_DEV) { xsrc = in->prior; Psrc = in->prior + 36; }
+    }
     {
         const int t = threadIdx.x;
-        const double* x = f->x;                    // pos3 rot9 rot_ext9 pos_ext3 ...
+        const double* x = xsrc;                    // pos3 rot9 rot_ext9 pos_ext3 ...
         if (t < 9) {
             const int i = t / 3, j = t % 3;
             double sacc = x[3 + 3 * i] * x[12 + j];
@@ -143,10 +153,13 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
         } else if (t < 21) ms.R.a[t - 12] = x[3 + (t - 12)];
         else if (t < 30) ms.Rext.a[t - 21] = x[12 + (t - 21)];
         else if (t < 33) ms.pext[t - 30] = x[21 + (t - 30)];
-        else if (t < 42) { const int e = t - 33; ms.Prr.a[e] = f->P[(3 + e / 3) * 23 + 3 + e % 3]; }
-        else if (t < 51) { const int e = t - 42; ms.Ppp.a[e] = f->P[(e / 3) * 23 + e % 3]; }
+        else if (t < 42) { const int e = t - 33; ms.Prr.a[e] = Psrc[(3 + e / 3) * 23 + 3 + e % 3]; }
+        else if (t < 51) { const int e = t - 42; ms.Ppp.a[e] = Psrc[(e / 3) * 23 + e % 3]; }
     }
-    const int n = ctl->n;
+    const int n = FIRST ? in->n : ctl->n;
+    const float* pts = FIRST ? in->pts : nullptr;
+    const int stride = FIRST ? (in->stride == 4 ? 4 : 3) : 3;
+    const bool copy_raw = FIRST && pts != s.raw;
     __syncthreads();
     const size_t NM = (size_t)s.nmax;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -179,14 +192,29 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
         const int i = base + lane;
         bool valid = false;
         if (i < n) {
-            const V3 pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
+            V3 pl;
+            M3 cl;
+            if (FIRST) {
+                const float* pp = pts + (size_t)i * stride;
+                const float fx = pp[0], fy = pp[1], fz = pp[2];
+                if (copy_raw) { s.raw[3 * (size_t)i] = fx; s.raw[3 * (size_t)i + 1] = fy; s.raw[3 * (size_t)i + 2] = fz; }
+                pl = v3((double)fx, (double)fy, (double)fz);
+                calc_body_cov(pl, s.range_var, s.sn2, cl);            // (edits pl.z == 0 -> 0.001, Q16)
+#pragma unroll
+                for (int k = 0; k < 3; k++) s.pl[(size_t)k * NM + i] = pl[k];
+#pragma unroll
+                for (int k = 0; k < 9; k++) s.cl[(size_t)k * NM + i] = cl.a[k];
+            } else {
+                pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
+            }
             const V3 pw = add(mul(ms.r_wl, pl), ms.p_wl);
             unsigned long long pk;
             int slot = -1;
             if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk)) slot = hash_find(m, pk);
-            M3 cl;                                         // fetched up front: one memory latency less on the chain
+            if (!FIRST) {                                  // fetched up front: one memory latency less on the chain
 #pragma unroll
-            for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
+                for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
+            }
             V3 nrm;
             double res;
             uint8_t status = 0;
@@ -270,10 +298,15 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     if (threadIdx.x == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
-void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve) {
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* first) {
     const int g = grid + (solve ? 1 : 0);
-    if (ext) k_measure<true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve);
-    else k_measure<false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve);
+    if (first) {
+        if (ext) k_measure<true, true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, first);
+        else k_measure<false, true><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, first);
+    } else {
+        if (ext) k_measure<true, false><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, nullptr);
+        else k_measure<false, false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, nullptr);
+    }
 }
 // Motion compensation of a raw scan (LIOBuilder::undistortCloud, lio_builder.cpp:127-152) on the device: one thread per
 // point.  The scan is time-sorted; a point at offset t belongs to the last IMU pose `head` with head.offset < t (points at
@@ -337,50 +370,5 @@ __global__ void __launch_bounds__(256) k_state_out(const DevFilter* __restrict__
 void launch_state_out(cudaStream_t st, const DevFilter* f, const DevCtl* ctl, StateOut* out) { k_state_out<<<1, 256, 0, st>>>(f, ctl, out); }
 
 void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const ScanIn* in, DevFilter* f, DevCtl* ctl) { k_set_scan<<<grid, 256, 0, st>>>(s, in, f, ctl); }
-
-// ---------------------------------------------------------------------------- K3
-// float32 world transform with the association of PCL's SSE Transformer::se3
-// (x' = m00 x + (m01 y + (m02 z + tx)), separate mul/add), widened to fp64, plus
-// pv.cov with the posterior R and P.  first_scan: calcBodyCov on a local copy (lio_builder.cpp:196-198).
-__global__ void __launch_bounds__(256) k_world_points(DevScan s, const DevFilter* __restrict__ f, DevCtl* ctl, int first_scan) {
-    __shared__ MeasState ms;
-    __shared__ float mf[12];
-    if (blockIdx.x == 0 && threadIdx.x == 32) map_begin_reset(ctl);     // the map update that follows starts here
-    if (threadIdx.x == 0) {
-        const St x = st_load(f->x);
-        ms.r_wl = mul(x.rot, x.rot_ext);
-        ms.p_wl = add(mul(x.rot, x.pos_ext), x.pos);
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) { ms.Prr(i, j) = f->P[(3 + i) * 23 + 3 + j]; ms.Ppp(i, j) = f->P[i * 23 + j]; }
-        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) mf[i * 4 + j] = (float)ms.r_wl(i, j); mf[i * 4 + 3] = (float)ms.p_wl[i]; }
-    }
-    __syncthreads();
-    const int n = ctl->n;
-    const size_t NM = (size_t)s.nmax;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float x = s.raw[3 * i], y = s.raw[3 * i + 1], z = s.raw[3 * i + 2];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            const float p0 = __fmul_rn(mf[r * 4 + 0], x), p1 = __fmul_rn(mf[r * 4 + 1], y), p2 = __fmul_rn(mf[r * 4 + 2], z);
-            const float o = __fadd_rn(p0, __fadd_rn(p1, __fadd_rn(p2, mf[r * 4 + 3])));
-            s.pw[3 * (size_t)i + r] = (double)o;
-        }
-        V3 pl; M3 cl;
-        if (first_scan) {
-            pl = v3((double)x, (double)y, (double)z);
-            calc_body_cov(pl, s.range_var, s.sn2, cl);
-        } else {
-            pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
-#pragma unroll
-            for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
-        }
-        const M3 cw = world_cov(ms.r_wl, cl, pl, ms.Prr, ms.Ppp);
-#pragma unroll
-        for (int k = 0; k < 9; k++) s.pcov[9 * (size_t)i + k] = cw.a[k];
-    }
-}
-void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, DevCtl* ctl, int first_scan) {
-    k_world_points<<<grid, 256, 0, st>>>(s, f, ctl, first_scan);
-}
 
 }  // namespace vmp

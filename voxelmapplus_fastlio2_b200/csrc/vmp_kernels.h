@@ -15,12 +15,12 @@ constexpr int PT_BLOCK = 1024;          // points per block in the order-preserv
 void launch_undistort(cudaStream_t st, int grid, const ScanIn* in, const DevPose* poses, float4* cloud, float4* host_copy);
 // stages one scan from the mailbox `in` (device-accessible): points -> raw / body points / body covariances, prior, counters
 void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const ScanIn* in, DevFilter* f, DevCtl* ctl);
-// solve != 0: one extra CTA runs the 23-dof solve of the iteration (one launch per IEKF iteration)
-void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve);
+// solve != 0: one extra CTA runs the 23-dof solve of the iteration (one launch per IEKF iteration).  first != null: the first
+// iteration of a scan's graph, which stages the scan named by that header itself (no launch_set_scan in front)
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve,
+                    const ScanIn* first = nullptr);
 // posterior -> host mailbox (x, P, iteration counters, then seq behind a system-scope fence)
 void launch_state_out(cudaStream_t st, const DevFilter* f, const DevCtl* ctl, StateOut* out);
-// also resets the per-update counters of the map update that follows (begun = true for launch_map_update)
-void launch_world_points(cudaStream_t st, int grid, const DevScan& s, const DevFilter* f, DevCtl* ctl, int first_scan);
 
 // optional per-launch hook (profiling mode records a CUDA event after each kernel)
 struct Marker { void (*fn)(void* ctx, int id); void* ctx; };
@@ -43,8 +43,10 @@ void launch_dump_sort_gather(cudaStream_t st, int grid, const DevMap& m, const D
 
 // map: returns the number of kernels launched
 // `out`: mailbox written by the update's last kernel (counters, error bits, maintenance requests); may be null
-int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk,
-                      const SideStream* side);
+// world_mode: 0 = world points / covariances of the scan from the posterior in `f` (lio_builder.cpp:155-163, 231-245), 1 = the same
+// for the first scan (calcBodyCov on a local copy), 2 = s.pw / s.pcov were given by the caller
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, const DevFilter* f, DevCtl* ctl, int sm_count, bool build, int world_mode, MapOut* out,
+                      const Marker* mk, const SideStream* side);
 int launch_map_maintenance(cudaStream_t st, const DevMap& m, DevCtl* ctl, int sm_count, int what);
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl);
 cudaError_t map_configure_kernels(const DevMap& m);      // per-handle kernel attributes (dynamic shared memory of k_fill)

@@ -24,6 +24,7 @@
 // touched earlier in the same scan.
 #include "vmp_device.cuh"
 #include "vmp_kernels.h"
+#include "vmp_state.cuh"
 
 namespace vmp {
 
@@ -95,7 +96,6 @@ __global__ void k_map_init(DevMap m, DevCtl* ctl) {
 void launch_map_init(cudaStream_t st, const DevMap& m, DevCtl* ctl) { k_map_init<<<592, 256, 0, st>>>(m, ctl); }
 cudaError_t map_configure_kernels(const DevMap& m);
 
-__global__ void k_map_begin(DevCtl* ctl) { map_begin_reset(ctl); }     // only for updates that do not start with k_world_points
 
 // end of VoxelMap::update (single thread, the last CTA of k_map_finalize): counters, maintenance requests, host mailbox
 __device__ void map_end(const DevMap& m, DevCtl* ctl, MapOut* out) {
@@ -119,6 +119,7 @@ __device__ void map_end(const DevMap& m, DevCtl* ctl, MapOut* out) {
         *(volatile unsigned long long*)&out->seq = ctl->seq;
     }
     ctl->err = 0;                                     // error bits are per update: reported once, then cleared
+    map_counters_reset(ctl);                          // the next update starts from clean counters (there is no "begin" kernel)
 }
 
 // ------------------------------------------------------------------------- rehash (tombstone purge)
@@ -163,7 +164,13 @@ __global__ void __launch_bounds__(1024) k_logc_scatter(DevMap m, const DevCtl* c
     const int sel = ctl->log_sel;
     const long long len = ctl->log_tail - ctl->log_head;
     for (long long b = blockIdx.x; b * 1024 < len; b += gridDim.x) {
-        if (threadIdx.x == 0) { long long s = 0; for (long long q = 0; q < b; q++) s += m.log_blk[q]; base_sh = s; }
+        if (threadIdx.x < 32) {
+            long long s = 0;
+            for (long long q = threadIdx.x; q < b; q += 32) s += m.log_blk[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (threadIdx.x == 0) base_sh = s;
+        }
         const long long p = ctl->log_head + b * 1024 + threadIdx.x;
         int f = 0, sl = 0; unsigned long long stp = 0;
         if (p < ctl->log_tail) { sl = m.log_slot[sel][p]; stp = m.log_stamp[sel][p]; f = (m.stamp[sl] == stp) ? 1 : 0; }
@@ -181,68 +188,115 @@ __global__ void k_logc_end(DevMap m, DevCtl* ctl) {
     ctl->log_sel ^= 1; ctl->log_head = 0; ctl->log_tail = s; ctl->need_log_compact = 0;
 }
 
-// ------------------------------------------------------------------------- M1a: hash find-or-insert
-__global__ void __launch_bounds__(256) k_map_insert(DevMap m, DevScan s, DevCtl* ctl) {
-    const int n = ctl->n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        unsigned long long pk;
-        if (!voxel_index(s.pw[3 * (size_t)i], s.pw[3 * (size_t)i + 1], s.pw[3 * (size_t)i + 2], m.voxel_size, pk)) {
-            atomicAdd((unsigned long long*)&ctl->st.n_skipped, 1ull);     // counted skip (see voxel_index), not an error
-            m.tpos[i] = 0xFFFFFFFFu;
-            continue;
-        }
-        unsigned h = hash_key(pk) & m.hmask;
-        bool won = false, ok = false;
-        for (unsigned probe = 0; probe <= m.hmask; probe++) {
-            const unsigned long long cur = __ldcg(&m.tkey[h]);
-            if (cur == pk) { ok = true; break; }
-            if (cur == KEY_EMPTY) {
-                const unsigned long long old = atomicCAS(&m.tkey[h], KEY_EMPTY, pk);
-                if (old == KEY_EMPTY) { won = true; ok = true; break; }
-                if (old == pk) { ok = true; break; }
+// ------------------------------------------------------------------------- M1: world points, hash find-or-insert, counts, segment offsets
+// ONE pass over the points of the scan (round 1: k_world_points, k_map_insert, k_map_count):
+//   * lidarToWorld + pv_list loop (lio_builder.cpp:155-163, 231-245): float32 world transform with the association of PCL's SSE
+//     Transformer::se3 (x' = m00 x + (m01 y + (m02 z + tx)), separate mul / add, Q15), widened to fp64, and pv.cov with the posterior
+//     R, P (world_mode 0: a scan; 1: the first scan, calcBodyCov on a local copy, lio_builder.cpp:196-198; 2: pv_list given by the caller)
+//   * VoxelMap::index + featmap find-or-create (voxel_map.cpp:234-247): the lanes of a warp that hit the same voxel are grouped
+//     (match.any on the packed key; consecutive points of a scan share voxels) and their leader does ONE hash operation and ONE
+//     count / first-touch / last-touch update for the group.  A leader that finds a key whose creator (another warp) has not
+//     published the slot yet waits for it; the creator never waits for anybody.
+//   * its last CTA hands every touched voxel its segment of the per-voxel point lists (segments only have to be disjoint - they are
+//     selected / sorted by point index later - so there is no ordered scan: warp prefix + one shared atomic per warp).
+struct WorldState { M3 r_wl, Prr, Ppp; V3 p_wl; float mf[12]; };
+
+__device__ __forceinline__ int find_or_insert(const DevMap& m, DevCtl* ctl, unsigned long long pk) {
+    unsigned h = hash_key(pk) & m.hmask;
+    for (unsigned probe = 0; probe <= m.hmask; probe++) {
+        unsigned long long cur = __ldcg(&m.tkey[h]);
+        if (cur == KEY_EMPTY) {
+            cur = atomicCAS(&m.tkey[h], KEY_EMPTY, pk);
+            if (cur == KEY_EMPTY) {                                 // created (voxel_map.cpp:236-241)
+                const int slot = pop_free(m, ctl);
+                if (slot >= 0) {
+                    slot_init_fresh(m, ctl, slot, pk);
+                    m.newlist[atomicAdd(&ctl->n_new, 1)] = slot;
+                    __threadfence();                                // the slot is initialised before it becomes visible
+                }
+                *(volatile int*)&m.tval[h] = slot >= 0 ? slot : -2;
+                return slot;
             }
-            h = (h + 1) & m.hmask;
         }
-        if (!ok) { atomicOr(&ctl->err, E_HASH_FULL); m.tpos[i] = 0xFFFFFFFFu; continue; }
-        m.tpos[i] = h;
-        if (won) {
-            const int slot = pop_free(m, ctl);
-            if (slot >= 0) slot_init_fresh(m, ctl, slot, pk);
-            m.tval[h] = slot;
-            if (slot >= 0) m.newlist[atomicAdd(&ctl->n_new, 1)] = slot;
+        if (cur == pk) {
+            int v;
+            while ((v = *(volatile int*)&m.tval[h]) == -1) __nanosleep(20);      // being created by another warp right now
+            return v >= 0 ? v : -1;
         }
+        h = (h + 1) & m.hmask;
     }
+    atomicOr(&ctl->err, E_HASH_FULL);
+    return -1;
 }
 
-// ------------------------------------------------------------------------- M1b: counts / first / last touch, segment offsets
-// The last CTA to finish hands every touched voxel its segment of the per-voxel point lists.  Segments only have to be
-// disjoint (each is selected / sorted by point index later), so there is no ordered scan: warp prefix + one shared
-// atomic per warp.
-__global__ void __launch_bounds__(256) k_map_count(DevMap m, DevCtl* ctl) {
+__global__ void __launch_bounds__(256) k_world_insert_count(DevMap m, DevScan s, const DevFilter* __restrict__ f, DevCtl* ctl, int world_mode) {
+    __shared__ WorldState ws;
     __shared__ int s_top, s_last;
+    if (world_mode != 2) {
+        if (threadIdx.x == 0) {
+            const St x = st_load(f->x);
+            ws.r_wl = mul(x.rot, x.rot_ext);
+            ws.p_wl = add(mul(x.rot, x.pos_ext), x.pos);
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) { ws.Prr(i, j) = f->P[(3 + i) * 23 + 3 + j]; ws.Ppp(i, j) = f->P[i * 23 + j]; }
+            for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) ws.mf[i * 4 + j] = (float)ws.r_wl(i, j); ws.mf[i * 4 + 3] = (float)ws.p_wl[i]; }
+        }
+        __syncthreads();
+    }
     const int n = ctl->n;
-    {
-        // consecutive points of a scan fall into the same few voxels (a near voxel collects thousands of a 200 k-point scan):
-        // the lanes of a warp that hit the same voxel are grouped (match.any) and their leader issues ONE count / first /
-        // last-touch update for the group instead of four contended atomics per point
-        const int lane0 = threadIdx.x & 31;
-        for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane0; i0 < n; i0 += gridDim.x * blockDim.x) {    // warp-uniform trip count
-            const int i = i0 + lane0;
-            int slot = -1;
-            if (i < n) {
-                const unsigned h = m.tpos[i];
-                if (h != 0xFFFFFFFFu) slot = m.tval[h];
-                m.pslot[i] = slot;
+    const size_t NM = (size_t)s.nmax;
+    const int lane0 = threadIdx.x & 31;
+    unsigned long long skipped = 0;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane0; i0 < n; i0 += gridDim.x * blockDim.x) {    // warp-uniform trip count
+        const int i = i0 + lane0;
+        unsigned long long pk = KEY_EMPTY;
+        bool have = false;
+        if (i < n) {
+            double w[3];
+            if (world_mode != 2) {
+                const float x = s.raw[3 * (size_t)i], y = s.raw[3 * (size_t)i + 1], z = s.raw[3 * (size_t)i + 2];
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const float p0 = __fmul_rn(ws.mf[r * 4 + 0], x), p1 = __fmul_rn(ws.mf[r * 4 + 1], y), p2 = __fmul_rn(ws.mf[r * 4 + 2], z);
+                    const float o = __fadd_rn(p0, __fadd_rn(p1, __fadd_rn(p2, ws.mf[r * 4 + 3])));
+                    w[r] = (double)o;
+                    s.pw[3 * (size_t)i + r] = w[r];
+                }
+                V3 pl; M3 cl;
+                if (world_mode == 1) {
+                    pl = v3((double)x, (double)y, (double)z);
+                    calc_body_cov(pl, s.range_var, s.sn2, cl);
+                } else {
+                    pl = v3(s.pl[i], s.pl[NM + i], s.pl[2 * NM + i]);
+#pragma unroll
+                    for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
+                }
+                const M3 cw = world_cov(ws.r_wl, cl, pl, ws.Prr, ws.Ppp);
+#pragma unroll
+                for (int k = 0; k < 9; k++) s.pcov[9 * (size_t)i + k] = cw.a[k];
+            } else {
+                w[0] = s.pw[3 * (size_t)i]; w[1] = s.pw[3 * (size_t)i + 1]; w[2] = s.pw[3 * (size_t)i + 2];
             }
-            const unsigned grp = __match_any_sync(0xffffffffu, slot >= 0 ? slot : -1 - lane0);   // lanes without a voxel stay alone
-            if (slot >= 0 && lane0 == __ffs(grp) - 1) {
+            have = voxel_index(w[0], w[1], w[2], m.voxel_size, pk);
+            if (!have) skipped++;                                   // counted skip (see voxel_index), not an error
+        }
+        // keys are 63-bit, so the all-ones prefix makes the lanes without a voxel distinct from every key and from each other
+        const unsigned grp = __match_any_sync(0xffffffffu, have ? pk : (0xFFFFFFFF00000000ull | (unsigned long long)lane0));
+        const int leader = __ffs(grp) - 1;
+        int slot = -1;
+        if (have && lane0 == leader) {
+            slot = find_or_insert(m, ctl, pk);
+            if (slot >= 0) {
                 const int c = atomicAdd(&m.cnt[slot], __popc(grp));
                 if (c == 0) m.touched[atomicAdd(&ctl->n_touched, 1)] = slot;
                 atomicMin(&m.ft[slot], i);                         // the leader is the group's lowest lane = lowest point index
                 atomicMax(&m.lt[slot], i0 + 31 - __clz(grp));
             }
         }
+        slot = __shfl_sync(0xffffffffu, slot, leader);
+        if (i < n) m.pslot[i] = have ? slot : -1;
     }
+    if (skipped) atomicAdd((unsigned long long*)&ctl->st.n_skipped, skipped);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -274,8 +328,10 @@ __global__ void __launch_bounds__(256) k_map_count(DevMap m, DevCtl* ctl) {
     }
 }
 
+__device__ void fill_classify(const DevMap& m, DevCtl* ctl, int vi);      // vmp_fill.cuh
+
 // ------------------------------------------------------------------------- M3b: fill segments
-__global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl) {
+__global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl, int classify) {
     const int n = ctl->n;
     for (int b = blockIdx.x; b * PT_BLOCK < n; b += gridDim.x) {
         const int i = b * PT_BLOCK + threadIdx.x;
@@ -295,6 +351,11 @@ __global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl) {
         }
         const int cl = __syncthreads_count(is_last);
         if (threadIdx.x == 0) m.blk_last[b] = cl;
+    }
+    // which touched voxels go to the CTA path of k_fill (vmp_fill.cuh): one voxel per thread
+    if (classify) {
+        const int V = ctl->n_touched;
+        for (int vi = blockIdx.x * blockDim.x + threadIdx.x; vi < V; vi += gridDim.x * blockDim.x) fill_classify(m, ctl, vi);
     }
 }
 
@@ -381,7 +442,7 @@ __global__ void __launch_bounds__(1024) k_lru_evict(DevMap m, DevCtl* ctl) {
     const int n = ctl->n;
     const int n_live0 = ctl->n_live, n_new = ctl->n_new;
     if (n_live0 + n_new <= m.capacity) {
-        if (tid == 0) { ctl->n_live = n_live0 + n_new; ctl->st.n_created = n_new; }
+        if (tid == 0) { ctl->n_live = n_live0 + n_new; ctl->st.n_created = n_new; ctl->n_evict = 0; }
         return;
     }
     const unsigned scan_id = ctl->scan_id;
@@ -495,7 +556,13 @@ __global__ void __launch_bounds__(1024) k_log_append(DevMap m, DevCtl* ctl) {
     const long long tail = ctl->log_tail;
     const unsigned long long sb = ctl->stamp_base;
     for (int b = blockIdx.x; b * PT_BLOCK < n; b += gridDim.x) {
-        if (threadIdx.x == 0) { int sacc = 0; for (int q = 0; q < b; q++) sacc += m.blk_last[q]; base_sh = sacc; }
+        if (threadIdx.x < 32) {                             // last-touch points in the blocks before this one (one warp, strided)
+            int sacc = 0;
+            for (int q = threadIdx.x; q < b; q += 32) sacc += m.blk_last[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (threadIdx.x == 0) base_sh = sacc;
+        }
         const int i = b * PT_BLOCK + threadIdx.x;
         int f = 0, slot = -1;
         if (i < n) { slot = m.pslot[i]; if (slot >= 0) f = (m.lt[slot] == i); }
@@ -553,14 +620,12 @@ __global__ void __launch_bounds__(256) k_map_finalize(DevMap m, DevCtl* ctl, Map
 }
 
 // ------------------------------------------------------------------------- launcher
-int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl* ctl, int sm_count, bool build, bool begun, MapOut* out, const Marker* mk,
-                      const SideStream* side) {
+int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, const DevFilter* f, DevCtl* ctl, int sm_count, bool build, int world_mode, MapOut* out,
+                      const Marker* mk, const SideStream* side) {
     const int gpt = (m.nmax + PT_BLOCK - 1) / PT_BLOCK;               // order-preserving passes: 1024 points / block
     const int gstride = sm_count * 2;
     int launches = 0;
-    if (!begun) { k_map_begin<<<1, 1, 0, st>>>(ctl); launches++; mark(mk, VMP_K_MAP_BEGIN); }
-    k_map_insert<<<gstride, 256, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_INSERT);
-    k_map_count<<<gstride, 256, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MAP_COUNT);
+    k_world_insert_count<<<gstride, 256, 0, st>>>(m, s, f, ctl, world_mode); launches++; mark(mk, VMP_K_WORLD_POINTS);
     // the LRU eviction (one CTA) is independent of the segment build: side branch of the graph
     const bool fork = side != nullptr && mk == nullptr;
     if (fork) {
@@ -568,7 +633,7 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
         k_lru_evict<<<1, 1024, 0, side->st>>>(m, ctl); launches++;
         cudaEventRecord(side->ev[1], side->st);
     }
-    k_seg_fill<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_SEG_FILL);
+    k_seg_fill<<<gpt, 1024, 0, st>>>(m, ctl, build ? 0 : 1); launches++; mark(mk, VMP_K_SEG_FILL);
     if (fork) cudaStreamWaitEvent(st, side->ev[1], 0);
     else { k_lru_evict<<<1, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LRU_EVICT); }
     if (build) { k_fill_build<<<sm_count * 4, 128, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_FILL); }
@@ -585,7 +650,7 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, DevCtl
         cudaEventRecord(side->ev[3], side->st);
     }
     if (!build) {
-        k_merge_prefilter<<<sm_count, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
+        k_merge_prefilter<<<sm_count * 4, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
         k_merge_rounds<<<1, 512, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
     }
     if (fork && !build) cudaStreamWaitEvent(st, side->ev[3], 0);

@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
                 w += __popc(bal);
                 __syncwarp();
             }
-            if (lane == 0) { as.n = w; s_cnt = w; s_nready = 0; }
+            if (lane == 0) { as.n = w; s_cnt = w; s_nready = 0; atomicAdd(&ctl->dbg[2], 65536); }      // (rounds in the upper half of dbg[2])
         }
         __syncthreads();
         if (s_cnt == 0) break;

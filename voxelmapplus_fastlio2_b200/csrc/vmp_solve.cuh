@@ -146,8 +146,10 @@ struct SolveShared {
     int s_last, s_zero;
 };
 
+// first != null: the first iteration of a scan.  The solver then also opens IESKF::update (ieskf.cpp:127-130: predict_x = x_, iteration
+// counters) and stages the prior named by the scan header into the filter (round 1 did that in a kernel of its own, k_set_scan).
 template <bool EXT, int THREADS>
-__device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks) {
+__device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks, const ScanIn* first) {
     static_assert(THREADS >= 128, "the manifold pieces use four warps");
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
@@ -162,12 +164,23 @@ __device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, 
     auto& sJb = S.sJb; auto& sAb = S.sAb; auto& sLb = S.sLb; auto& sBb = S.sBb;
     int& s_last = S.s_last; int& s_zero = S.s_zero;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int it = ctl->iter;
+    const int it = first ? 0 : ctl->iter;
     const long long t0 = clock64();
 
     // ---- (A)
-    for (int q = tid; q < 36; q += THREADS) { sx[q] = f->x[q]; sxp[q] = f->xpred[q]; }
-    for (int q = tid; q < NE; q += THREADS) sP[q] = f->P[q];
+    if (first) {
+        const int mode = first->mode;
+        const bool staged = (mode & (SCAN_STATE_HDR | SCAN_STATE_DEV)) != 0;
+        const double* xs = (mode & SCAN_STATE_HDR) ? first->x : (mode & SCAN_STATE_DEV) ? first->prior : f->x;
+        const double* Ps = (mode & SCAN_STATE_HDR) ? first->P : (mode & SCAN_STATE_DEV) ? first->prior + 36 : f->P;
+        for (int q = tid; q < 36; q += THREADS) { const double v = xs[q]; sx[q] = v; sxp[q] = v; f->xpred[q] = v; }
+        for (int q = tid; q < NE; q += THREADS) { const double v = Ps[q]; sP[q] = v; if (staged) f->P[q] = v; }
+        if (tid == 0) { ctl->n = first->n; ctl->seq = first->seq; ctl->converged = 0; }
+        if (tid < 8) ctl->effect[tid] = 0;
+    } else {
+        for (int q = tid; q < 36; q += THREADS) { sx[q] = f->x[q]; sxp[q] = f->xpred[q]; }
+        for (int q = tid; q < NE; q += THREADS) sP[q] = f->P[q];
+    }
     if (tid == 0) s_zero = 0;
     __syncthreads();
     if (lane == 0) {
@@ -317,7 +330,7 @@ __device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, 
             int last = 0;
             if (mx < 0.001) { ctl->converged = 1; last = 1; }
             if (nit >= ctl->max_iter) last = 1;
-            if (last) ctl->done = 1;
+            ctl->done = last;                                   // (the first iteration of a scan clears the previous scan's flag)
             s_last = last;
         }
     }
