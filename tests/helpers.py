@@ -65,6 +65,13 @@ def assert_maps_equal(a, b, exact=True, rtol=1e-9, what=""):
                 assert (~ok).sum() <= 0.01 * len(x), f"{what}: field {f}: {(~ok).sum()} of {len(x)} voxels differ by more than 1e-4 relative"
 
 
+def cov_rel_err(a, b):
+    """max |a_ij - b_ij| / sqrt(b_ii b_jj): the error of a covariance entry relative to the scale of its row and column
+    (tests/test_posterior_precision.py pins both the oracle's and the device's posterior to ~1e-13 of the exact value this way)"""
+    sc = np.sqrt(np.abs(np.outer(np.diag(b), np.diag(b))))
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / sc))
+
+
 def plane_cloud(rng, n, origin, u, v, extent, noise):
     """n points on the rectangle origin + a u + b v, a,b in [0,extent), with gaussian noise along the normal."""
     u = np.asarray(u, float); v = np.asarray(v, float)

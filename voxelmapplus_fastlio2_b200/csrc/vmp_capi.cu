@@ -612,13 +612,41 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
 
 // launch the scan that h->h_in describes and collect its results: everything (default), or - pipelined - the posterior
 // only, with the map update still running and its counters / errors delivered by the next call
-static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t upload_bytes, vmp_scan_stats* stats, bool raw = false) {
+// src != null: the points are still in the caller's (pageable) buffer.  They are staged and uploaded in a few chunks, the DMA copy
+// of a chunk running while the helpers stage the next one; check_stride > 0 also checks the time order of a raw scan on the way
+// (*sorted).  src == null: everything is in the pinned staging already, one DMA copy.
+static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t upload_bytes, vmp_scan_stats* stats, bool raw = false,
+                       const void* src = nullptr, int check_stride = 0) {
     const bool pipe = h->pipelined && !h->prof_on;
     const unsigned long long seq = ++h->seq;
     h->h_in->seq = seq; h->h_in->n = n;
     const int eb = (int)(seq & 1);
     VMP_CUDA_CHECK(cudaEventRecord(h->pe0[eb], h->stream));
-    VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (!src) {
+        VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        const size_t pts_bytes = upload_bytes - PTS_OFF;
+        const size_t rec = check_stride > 0 ? sizeof(float) * (size_t)check_stride : sizeof(float) * 3;
+        const int nchunk = pts_bytes >= (4u << 20) ? 8 : pts_bytes >= (1u << 20) ? 4 : 1;
+        const size_t per = ((pts_bytes / rec + nchunk - 1) / nchunk) * rec;
+        bool sorted = true;
+        VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, PTS_OFF, cudaMemcpyHostToDevice, h->stream));      // header (+ prior, IMU poses)
+        for (size_t off = 0; off < pts_bytes; off += per) {
+            const size_t len = std::min(per, pts_bytes - off);
+            sorted &= h->pool.copy((char*)h->h_raw + off, (const char*)src + off, len, check_stride);
+            if (check_stride > 0 && off > 0) {      // order across the chunk boundary
+                const float* f = reinterpret_cast<const float*>((const char*)src + off);
+                sorted &= !(f[check_stride - 1] < f[-1]);
+            }
+            VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage + PTS_OFF + off, h->h_stage + PTS_OFF + off, len, cudaMemcpyHostToDevice, h->stream));
+        }
+        if (!sorted) {      // lio_builder.cpp:75; rare for real sensors (points arrive in time order); any order of equal keys is a valid std::sort result
+            struct P4 { float x, y, z, t; };
+            P4* q = reinterpret_cast<P4*>(h->h_raw);
+            std::stable_sort(q, q + n, [](const P4& a, const P4& b) { return a.t < b.t; });
+            VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage + PTS_OFF, h->h_stage + PTS_OFF, pts_bytes, cudaMemcpyHostToDevice, h->stream));
+        }
+    }
     { const int rr = run_scan(h, raw, n); if (rr) return rr; }
     VMP_CUDA_CHECK(cudaEventRecord(h->pe1[eb], h->stream));
     h->n_last = n;
@@ -655,14 +683,14 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
 
 // the scan is already in the pinned staging buffer (vmp_scan_buffer): header + prior + points go up in ONE DMA copy (SM
 // reads of host memory reach a fraction of the copy engine's PCIe rate, small ones cost a round trip each)
-static int scan_staged(vmp_handle h, vmp_state* x, double* P, int n, vmp_scan_stats* stats, const char* who) {
+static int scan_staged(vmp_handle h, vmp_state* x, double* P, int n, vmp_scan_stats* stats, const char* who, const float* src = nullptr) {
     if (!x || !P) { set_error("%s: null argument", who); return VMP_ERR_INVALID_ARG; }
     if (!h->map_built) { set_error("%s: no map yet (call vmp_first_scan or vmp_map_build first)", who); return VMP_ERR_STATE; }
     h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
     h->h_in->n_poses = 0; h->h_in->stride = 3;
     std::memcpy(h->h_in->x, x, sizeof(double) * 36);
     std::memcpy(h->h_in->P, P, sizeof(double) * 529);
-    return scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 3 * (size_t)n, stats);
+    return scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 3 * (size_t)n, stats, false, src);
 }
 
 int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp_scan_stats* stats) {
@@ -670,8 +698,7 @@ int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp
     int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan") : check_n(h, n, "vmp_scan");
     if (r) return r;
     if (n > 0 && !pts) { set_error("vmp_scan: null argument"); return VMP_ERR_INVALID_ARG; }
-    h->pool.copy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);         // the previous scan's copy out of this buffer is long done
-    r = scan_staged(h, x, P, n, stats, "vmp_scan");
+    r = scan_staged(h, x, P, n, stats, "vmp_scan", n > 0 ? pts : nullptr);          // staged + uploaded chunk by chunk
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
 }
@@ -709,21 +736,13 @@ int vmp_scan_raw(vmp_handle h, vmp_state* x, double* P, float* cloud_xyzt, int n
     if (n_poses < 2 || n_poses > MAX_POSES) { set_error("vmp_scan_raw: n_poses=%d outside [2, %d]", n_poses, MAX_POSES); return VMP_ERR_INVALID_ARG; }
     if (!h->map_built) { set_error("vmp_scan_raw: no map yet (call vmp_first_scan or vmp_map_build first)"); return VMP_ERR_STATE; }
     static_assert(sizeof(vmp_pose) == sizeof(DevPose), "vmp_pose layout");
-    // one pass over the caller's cloud: copy into the pinned staging and check the time order (lio_builder.cpp:75), split
-    // over the staging helpers
-    float* dst = h->h_raw;
-    const bool sorted = h->pool.copy(dst, cloud_xyzt, sizeof(float) * 4 * (size_t)n, 4);
-    if (!sorted) {      // rare for real sensors (points arrive in time order); any order of equal keys is a valid std::sort result
-        struct P4 { float x, y, z, t; };
-        P4* q = reinterpret_cast<P4*>(dst);
-        std::stable_sort(q, q + n, [](const P4& a, const P4& b) { return a.t < b.t; });
-    }
+    // the caller's cloud is staged, checked for time order (lio_builder.cpp:75) and uploaded chunk by chunk in scan_common
     std::memcpy(h->h_stage + IN_HDR, poses, sizeof(vmp_pose) * (size_t)n_poses);
     h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
     h->h_in->n_poses = n_poses; h->h_in->stride = 4;
     std::memcpy(h->h_in->x, x, sizeof(double) * 36);
     std::memcpy(h->h_in->P, P, sizeof(double) * 529);
-    r = scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 4 * (size_t)n, stats, true);
+    r = scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 4 * (size_t)n, stats, true, n > 0 ? cloud_xyzt : nullptr, 4);
     // the compensated cloud was written to mapped host memory by the first kernel of the graph, before the posterior; it
     // stays available through vmp_get_lidar_cloud, the copy into the caller's buffer can be switched off (vmp_set_raw_writeback)
     if (h->raw_writeback) h->pool.copy(cloud_xyzt, h->h_cloud, sizeof(float) * 4 * (size_t)n);

@@ -651,7 +651,7 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, const 
     }
     if (!build) {
         k_merge_prefilter<<<sm_count * 4, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
-        k_merge_rounds<<<1, 512, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
+        k_merge_rounds<<<1, 512, sizeof(MergeShared), st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
     }
     if (fork && !build) cudaStreamWaitEvent(st, side->ev[3], 0);
     else { k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND); }
@@ -661,6 +661,8 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, const 
 
 // opt-in shared memory size of k_fill (once per handle)
 cudaError_t map_configure_kernels(const DevMap& m) {
+    cudaError_t e = cudaFuncSetAttribute(k_merge_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeShared));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILL_WARPS * fill_warp_bytes(m.maxpt)));
 }
 

@@ -65,6 +65,69 @@ __device__ __forceinline__ VoxRec load_rec(const DevMap& m, int s) {
     r.flags = (uint32_t)(r.w6 & 0xFFFFFFFFll);
     return r;
 }
+struct CellRec {
+    double mean[3], nrm[3];
+    unsigned long long group;
+    long long w6;                       // raw flags | n word of the hot record
+    unsigned born_scan, full_scan;
+    int ft, full_idx, evict_t, ghost;
+    int slot, cnt, evn, pad;
+};
+constexpr int NCELL = 25;
+
+// cell numbering: 0 = A; 1 + d = neighbour d (-x -y -z +x +y +z); 7 + d = two steps along d; 13 + 4 p + 2 [sa > 0] + [sb > 0] =
+// one step along each axis of pair p (xy, xz, yz)
+__device__ __forceinline__ void cell_offset(int c, int& dx, int& dy, int& dz) {
+    dx = dy = dz = 0;
+    if (c == 0) return;
+    if (c < 13) {
+        const int d = (c - 1) % 6, len = c < 7 ? 1 : 2;
+        const int v = d < 3 ? -len : len;
+        const int ax = d % 3;
+        if (ax == 0) dx = v; else if (ax == 1) dy = v; else dz = v;
+        return;
+    }
+    const int q = c - 13, p = q >> 2, sa = (q & 2) ? 1 : -1, sb = (q & 1) ? 1 : -1;
+    if (p == 0) { dx = sa; dy = sb; } else if (p == 1) { dx = sa; dz = sb; } else { dy = sa; dz = sb; }
+}
+__device__ __forceinline__ int cell_index(int dx, int dy, int dz) {
+    const int ax = abs(dx), ay = abs(dy), az = abs(dz);
+    const int dist = ax + ay + az;
+    if (dist == 0) return 0;
+    if (ax == dist || ay == dist || az == dist) {                       // on an axis
+        const int a = ax ? 0 : ay ? 1 : 2;
+        const int v = a == 0 ? dx : a == 1 ? dy : dz;
+        const int d = a + (v > 0 ? 3 : 0);
+        return dist == 1 ? 1 + d : dist == 2 ? 7 + d : -1;
+    }
+    if (dist != 2) return -1;
+    int p, sa, sb;
+    if (az == 0) { p = 0; sa = dx; sb = dy; } else if (ay == 0) { p = 1; sa = dx; sb = dz; } else { p = 2; sa = dy; sb = dz; }
+    return 13 + 4 * p + (sa > 0 ? 2 : 0) + (sb > 0 ? 1 : 0);
+}
+// neighbour d of cell c (c <= 6), as a cell
+__device__ __forceinline__ int cell_neighbour(int c, int d) {
+    int dx, dy, dz;
+    cell_offset(c, dx, dy, dz);
+    const int v = d < 3 ? -1 : 1, ax = d % 3;
+    if (ax == 0) dx += v; else if (ax == 1) dy += v; else dz += v;
+    return cell_index(dx, dy, dz);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// pull everything merge() will ask about slot s into L2 (the fields of VoxRec, the covariance, the per-scan lists)
+__device__ __forceinline__ void prefetch_slot(const DevMap& m, int s, bool with_cov = true) {
+    const char* h = reinterpret_cast<const char*>(m.hot + (size_t)s * 8);
+    prefetch_l2(h); prefetch_l2(h + 32);
+    if (with_cov) {
+        const char* c = reinterpret_cast<const char*>(m.cov + (size_t)s * 36);
+        prefetch_l2(c); prefetch_l2(c + 128); prefetch_l2(c + 256);
+    }
+    prefetch_l2(m.sgroup + s); prefetch_l2(m.born_scan + s); prefetch_l2(m.full_scan + s); prefetch_l2(m.ft + s);
+    prefetch_l2(m.full_idx + s); prefetch_l2(m.evict_t + s); prefetch_l2(m.cnt + s); prefetch_l2(m.evn + s); prefetch_l2(m.seg_off + s);
+    prefetch_l2(m.skey + s);
+}
+
 // could merge(A) succeed against the (final state of) incarnation B at some time of this scan?
 __device__ __forceinline__ bool pair_static(const DevMap& m, const V3& mA, const V3& nA, unsigned long long gA, const VoxRec& B) {
     if ((B.flags & F_UE) || !(B.flags & F_PLANE)) return false;
@@ -136,6 +199,20 @@ __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) 
             const int k = atomicAdd(&ctl->n_hot, 1);
             m.act_slot[k] = A;
             m.act_t[k] = best;
+        }
+        if (best != T_INF) {
+            // an active voxel: its event will look at everything within Manhattan distance 2 (vmp_merge.cuh, "diamond"); pull those
+            // records (and the covariances merge() may blend) into the L2 now, many voxels at a time, instead of in the
+            // dependent chain of the single CTA that simulates the events
+            long long x, y, z;
+            unpack_key(m.skey[A], x, y, z);
+            for (int c = sub; c < NCELL; c += 8) {
+                int dx, dy, dz;
+                cell_offset(c, dx, dy, dz);
+                const long long cx = x + dx, cy = y + dy, cz = z + dz;
+                if (!(key_in_range(cx) && key_in_range(cy) && key_in_range(cz))) continue;
+                for (int X = c == 0 ? A : hash_find(m, pack_key(cx, cy, cz)); X >= 0; X = m.ghost[X]) prefetch_slot(m, X, c <= 6);
+            }
         }
     }
 }
@@ -424,22 +501,276 @@ __device__ void process_event(const DevMap& m, DevCtl* ctl, ActiveSet& as, WarpS
     __syncwarp();
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// pull everything merge() will ask about slot s into L2 (the fields of VoxRec, the covariance, the per-scan lists)
-__device__ __forceinline__ void prefetch_slot(const DevMap& m, int s) {
-    const char* h = reinterpret_cast<const char*>(m.hot + (size_t)s * 8);
-    prefetch_l2(h); prefetch_l2(h + 32);
-    const char* c = reinterpret_cast<const char*>(m.cov + (size_t)s * 36);
-    prefetch_l2(c); prefetch_l2(c + 128); prefetch_l2(c + 256);
-    prefetch_l2(m.sgroup + s); prefetch_l2(m.born_scan + s); prefetch_l2(m.full_scan + s); prefetch_l2(m.ft + s);
-    prefetch_l2(m.full_idx + s); prefetch_l2(m.evict_t + s); prefetch_l2(m.cnt + s); prefetch_l2(m.evn + s); prefetch_l2(m.seg_off + s);
-    prefetch_l2(m.skey + s);
+// ------------------------------------------------------------------------- fast path of one event: the "diamond"
+// Everything one merge() call and its follow-up work can look at lies within Manhattan distance 2 of the event's voxel A: A, its
+// six neighbours (what merge() reads and writes) and the eighteen voxels next to those (re-examined after a success).  The slow
+// path above walks that neighbourhood as ~13 dependent look-ups (hash probe -> slot -> record, one after the other); here the 25
+// cells are resolved by 25 lanes at once - one round trip for the hash probes, one for the records - into shared memory, and
+// the whole event (decisions in the reference's order, blend, re-examination) then runs on that copy.  Cells hold the CURRENT
+// incarnation of a voxel; if any cell has an older incarnation still visible in this scan (a ghost: evicted and re-created
+// within the scan), the event takes the slow path, which walks those chains.
+// could merge(P) succeed against Q after time `after`?  -> time bound (events with t > bound may succeed) or T_INF.
+// (pair_static + pair_window of the slow path on the shared copies; no older incarnations here.)
+__device__ __forceinline__ int cell_pair_bound(const DevMap& m, const CellRec& P, const CellRec& Q, int after, unsigned scan_id) {
+    if (Q.slot < 0) return T_INF;
+    const uint32_t fq = (uint32_t)(Q.w6 & 0xFFFFFFFFll);
+    if ((fq & F_UE) || !(fq & F_PLANE)) return T_INF;
+    if (Q.group == P.group) return T_INF;
+    if (!plane_thresholds(m, v3(P.mean[0], P.mean[1], P.mean[2]), v3(P.nrm[0], P.nrm[1], P.nrm[2]), v3(Q.mean[0], Q.mean[1], Q.mean[2]),
+                          v3(Q.nrm[0], Q.nrm[1], Q.nrm[2]))) return T_INF;
+    const int born = (Q.born_scan == scan_id) ? Q.ft : -1;
+    const int full = (Q.full_scan == scan_id) ? Q.full_idx : -1;
+    const int s0 = born > full ? born : full;
+    const int bound = s0 > after ? s0 : after;
+    return (bound + 1 < Q.evict_t) ? bound : T_INF;
+}
+__device__ __forceinline__ int cell_event_floor(const CellRec& A, unsigned scan_id) { return (A.full_scan == scan_id) ? A.full_idx : -1; }
+
+// merge() of the voxel in cell[0] at time t on the shared copies (same decisions, same arithmetic and the same global writes as
+// merge_at_warp).  changed[0..n): the neighbour CELLS that were modified.
+__device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t, unsigned scan_id, int* changed) {
+    const int lane = threadIdx.x & 31;
+    const int A = cell[0].slot;
+    double* ca = m.cov + (size_t)A * 36;
+    double a0 = ca[lane], a1 = lane < 4 ? ca[32 + lane] : 0.0;
+    const unsigned long long gA = cell[0].group;
+    V3 mA = v3(cell[0].mean[0], cell[0].mean[1], cell[0].mean[2]), nA = v3(cell[0].nrm[0], cell[0].nrm[1], cell[0].nrm[2]);
+    int B = -1;
+    bool elig = false;
+    if (lane < 6) {
+        const CellRec& r = cell[1 + lane];
+        if (r.slot >= 0) {
+            const int born = (r.born_scan == scan_id) ? r.ft : -1;
+            if (born <= t && t < r.evict_t) {                         // alive at time t
+                B = r.slot;
+                const uint32_t fl = (uint32_t)(r.w6 & 0xFFFFFFFFll);
+                const bool closed = !(fl & F_UE) && (r.full_scan != scan_id || r.full_idx < t);
+                elig = closed && (fl & F_PLANE) && r.group != gA;
+            }
+        }
+    }
+    const unsigned elmask = __ballot_sync(0xffffffffu, elig) & 0x3Fu;
+    double b0p[6], b1p[6];
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+        b0p[d] = 0.0; b1p[d] = 0.0;
+        const int Bd = __shfl_sync(0xffffffffu, B, d);
+        if ((elmask >> d) & 1u) {
+            const double* cb = m.cov + (size_t)Bd * 36;
+            b0p[d] = cb[lane];
+            if (lane < 4) b1p[d] = cb[32 + lane];
+        }
+    }
+    int nchg = 0;
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+        if (!((elmask >> d) & 1u)) continue;
+        const int Bd = __shfl_sync(0xffffffffu, B, d);
+        CellRec& rb = cell[1 + d];
+        const V3 mb = v3(rb.mean[0], rb.mean[1], rb.mean[2]), nb = v3(rb.nrm[0], rb.nrm[1], rb.nrm[2]);
+        if (!plane_thresholds(m, mA, nA, mb, nb)) continue;
+        double* cb = m.cov + (size_t)Bd * 36;
+        const double b0 = b0p[d], b1 = b1p[d];
+        const double tn0 = shfl_d(a0, 0) + shfl_d(a0, 7) + shfl_d(a0, 14);
+        const double tm0 = shfl_d(a0, 21) + shfl_d(a0, 28) + shfl_d(a1, 3);
+        const double tn1 = shfl_d(b0, 0) + shfl_d(b0, 7) + shfl_d(b0, 14);
+        const double tm1 = shfl_d(b0, 21) + shfl_d(b0, 28) + shfl_d(b1, 3);
+        const double tc0 = tn0 + tm0, tc1 = tn1 + tm1;
+        V3 nm, nn;
+        {       // Q9: operator precedence exactly as in voxel_map.cpp:166-167 (six divisions on six lanes, broadcast)
+            const int kk = lane % 3;
+            const bool isn = lane >= 3;
+            const double xb = isn ? (kk == 0 ? nb[0] : kk == 1 ? nb[1] : nb[2]) : (kk == 0 ? mb[0] : kk == 1 ? mb[1] : mb[2]);
+            const double xa = isn ? (kk == 0 ? nA[0] : kk == 1 ? nA[1] : nA[2]) : (kk == 0 ? mA[0] : kk == 1 ? mA[1] : mA[2]);
+            const double t0 = isn ? tn0 : tm0, t1 = isn ? tn1 : tm1;
+            const double v = xb * t0 + (xa * t1) / (t0 + t1);
+#pragma unroll
+            for (int k = 0; k < 3; k++) { nm[k] = shfl_d(v, k); nn[k] = shfl_d(v, 3 + k); }
+        }
+        const double w0 = tc0 * tc0, w1 = tc1 * tc1, den = (tc0 + tc1) * (tc0 + tc1);
+        const double c0 = (b0 * w0 + a0 * w1) / den;
+        a0 = c0; cb[lane] = c0;
+        if (lane < 4) { const double c1 = (b1 * w0 + a1 * w1) / den; a1 = c1; cb[32 + lane] = c1; }
+        if (-dot(nm, nn) < 0.0) nn = neg(nn);
+        mA = nm; nA = nn;
+        const long long w6b = rb.w6 | (long long)F_MERGED;
+        __syncwarp();
+        if (lane < 3) {
+            m.hot[(size_t)Bd * 8 + lane] = nm[lane]; m.hot[(size_t)Bd * 8 + 3 + lane] = nn[lane];
+            rb.mean[lane] = nm[lane]; rb.nrm[lane] = nn[lane];
+        }
+        if (lane == 0) {
+            m.sgroup[Bd] = gA;
+            rb.group = gA;
+            rb.w6 = w6b;
+            m.hot[(size_t)Bd * 8 + 6] = __longlong_as_double(w6b);
+            atomicAdd((unsigned long long*)&ctl->st.n_merge, 1ull);
+            changed[nchg] = 1 + d;
+        }
+        __syncwarp();
+        nchg++;
+    }
+    if (nchg > 0) {
+        ca[lane] = a0;
+        if (lane < 4) ca[32 + lane] = a1;
+        if (lane < 3) {
+            m.hot[(size_t)A * 8 + lane] = mA[lane]; m.hot[(size_t)A * 8 + 3 + lane] = nA[lane];
+            cell[0].mean[lane] = mA[lane]; cell[0].nrm[lane] = nA[lane];
+        }
+        if (lane == 0) {
+            cell[0].w6 |= (long long)F_MERGED;
+            m.hot[(size_t)A * 8 + 6] = __longlong_as_double(cell[0].w6);
+        }
+    }
+    __syncwarp();
+    return nchg;
 }
 
+// returns false (nothing touched) when the event needs the slow path
+__device__ bool process_event_fast(const DevMap& m, DevCtl* ctl, ActiveSet& as, WarpScratch& ws, CellRec* cell, int j, unsigned scan_id) {
+    const int lane = threadIdx.x & 31;
+    const int A = as.slot[j] & 0x0FFFFFFF, depth = as.slot[j] >> 28, t = as.t[j];
+    // ---- the 25 cells, one per lane: two dependent round trips (hash probe, record)
+    bool ghosts = false;
+    if (lane < NCELL) {
+        CellRec r;
+        r.slot = -1; r.ghost = -1; r.cnt = 0; r.evn = 0; r.pad = 0; r.group = 0; r.w6 = 0; r.born_scan = 0; r.full_scan = SCAN_NEVER;
+        r.ft = T_INF; r.full_idx = T_INF; r.evict_t = T_INF;
+        for (int k = 0; k < 3; k++) { r.mean[k] = 0.0; r.nrm[k] = 0.0; }
+        int X = -1;
+        if (lane == 0) X = A;
+        else {
+            long long x, y, z;
+            unpack_key(m.skey[A], x, y, z);
+            int dx, dy, dz;
+            cell_offset(lane, dx, dy, dz);
+            x += dx; y += dy; z += dz;
+            if (key_in_range(x) && key_in_range(y) && key_in_range(z)) X = hash_find(m, pack_key(x, y, z));
+        }
+        if (X >= 0) {
+            const VoxRec v = load_rec(m, X);
+            r.slot = X; r.cnt = m.cnt[X]; r.evn = m.evn[X];
+            for (int k = 0; k < 3; k++) { r.mean[k] = v.mean[k]; r.nrm[k] = v.nrm[k]; }
+            r.group = v.group; r.w6 = v.w6; r.born_scan = v.born_scan; r.full_scan = v.full_scan;
+            r.ft = v.ft; r.full_idx = v.full_idx; r.evict_t = v.evict_t; r.ghost = v.ghost;
+            ghosts = v.ghost >= 0;
+        }
+        cell[lane] = r;
+    }
+    if (__any_sync(0xffffffffu, ghosts)) return false;
+    __syncwarp();
+    int* chg = ws.chg;                                                   // modified neighbour CELLS (1..6)
+    const int nchg = merge_at_cells(m, ctl, cell, t, scan_id, chg);
+    if (nchg > 0 && depth > MERGE_MAX_DEPTH && lane == 0) atomicOr(&ctl->err, E_MERGE_DEPTH);
+    const int dn = depth + 1 > 7 ? 7 : depth + 1;
+    // ---- follow-up work on the shared copies.  X ranges over A and the modified neighbours:
+    //   wake(X):      earliest time one of X's own pairs can pass (again)             [A: always; a neighbour: if merge() is called for it in this scan]
+    //   cand(X, d):   the voxel Y next to X in direction d: can the pair (Y, X) pass now?  (only for Y that is neither A nor modified)
+    int nq = 0;
+    const int nx = nchg > 0 ? nchg + 1 : 1;
+    int* wmin = ws.res;                                                  // per X: earliest bound of its own pairs (reused below as result array)
+    if (lane < 8) wmin[lane] = T_INF;
+    __syncwarp();
+    for (int e0 = 0; e0 < nx * 6; e0 += 32) {
+        const int e = e0 + lane;
+        if (e < nx * 6) {
+            const int xi = e / 6, d = e % 6;
+            const int cx = xi == 0 ? 0 : chg[xi - 1];
+            const CellRec& X = cell[cx];
+            if (xi == 0 || (X.cnt != 0 && X.evn != 0)) {
+                int after = t;
+                if (xi > 0) { const int fl = cell_event_floor(X, scan_id); after = t > fl ? t : fl; }
+                const int cy = cell_neighbour(cx, d);
+                const int w = cy >= 0 ? cell_pair_bound(m, X, cell[cy], after, scan_id) : T_INF;
+                if (w != T_INF) atomicMin(&wmin[xi], w);
+            }
+        }
+    }
+    __syncwarp();
+    // queue: the wakes first (kind 0: A, kind 1: a modified neighbour with merge() calls in this scan) ...
+    for (int xi = 0; xi < nx; xi++) {                                     // warp-uniform, nx <= 7
+        const int cx = xi == 0 ? 0 : chg[xi - 1];
+        if (!(xi == 0 || (cell[cx].cnt != 0 && cell[cx].evn != 0))) continue;
+        if (lane == 0) { ws.tgt[nq] = cell[cx].slot; ws.aft[nq] = wmin[xi]; ws.kind[nq] = (unsigned char)(xi == 0 ? 0 : 1); }
+        nq++;
+    }
+    __syncwarp();
+    // ... then the candidates
+    if (nchg > 0) {
+        for (int e0 = 0; e0 < nx * 6; e0 += 32) {
+            const int e = e0 + lane;
+            int Y = -1, w = T_INF;
+            if (e < nx * 6) {
+                const int xi = e / 6, d = e % 6;
+                const int cx = xi == 0 ? 0 : chg[xi - 1];
+                const int cy = cell_neighbour(cx, d);
+                bool skip = cy <= 0;                                        // A itself (or outside the diamond: cannot happen for cx <= 6)
+                for (int q = 0; q < nchg && !skip; q++) if (chg[q] == cy) skip = true;      // handled as a wake
+                if (!skip) {
+                    const CellRec& Yc = cell[cy];
+                    if (Yc.slot >= 0 && Yc.cnt != 0 && Yc.evn != 0) {     // merge() is called for Y in this scan
+                        const int fl = cell_event_floor(Yc, scan_id);
+                        w = cell_pair_bound(m, Yc, cell[cx], t > fl ? t : fl, scan_id);
+                        if (w != T_INF) Y = Yc.slot;
+                    }
+                }
+            }
+            const bool q_me = Y >= 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, q_me);
+            if (q_me) {
+                const int pos = nq + __popc(bal & ((1u << lane) - 1));
+                if (pos < FOLLOW_CAP) { ws.tgt[pos] = Y; ws.aft[pos] = w; ws.kind[pos] = 2; }
+            }
+            nq += __popc(bal);
+        }
+    }
+    if (nq > FOLLOW_CAP) { if (lane == 0) atomicOr(&ctl->err, E_QUEUE); nq = FOLLOW_CAP; }
+    __syncwarp();
+    // first point index of each queued voxel after its bound: the whole warp scans the voxel's segment (coalesced)
+    for (int q = 0; q < nq; q++) {
+        const int Yq = ws.tgt[q], aq = ws.aft[q];
+        int best = T_INF;
+        if (aq != T_INF) {
+            const int c = m.cnt[Yq], off = m.seg_off[Yq];
+            for (int k = lane; k < c; k += 32) { const int i = m.seg[off + k]; if (i > aq && i < best) best = i; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
+        }
+        __syncwarp();
+        if (lane == 0) ws.res[q] = best;
+    }
+    __syncwarp();
+    // apply: activations / retirements of the neighbourhood, then A's own next event (as in the slow path)
+    int ntA = T_INF;
+    for (int q = 0; q < nq; q++) {
+        const int kind = ws.kind[q], Yq = ws.tgt[q], nt = ws.res[q];
+        if (kind == 0) ntA = nt;
+        else if (nt != T_INF) as_activate(m, ctl, as, Yq, nt, dn);
+        else if (kind == 1) {
+            const int n = as.n;
+            for (int k = lane; k < n; k += 32) if ((as.slot[k] & 0x0FFFFFFF) == Yq) as.t[k] = T_INF;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) { as.t[j] = ntA; atomicAdd(&ctl->dbg[1], 1); }
+    __syncwarp();
+    return true;
+}
+
+struct MergeShared {                    // dynamic shared memory of k_merge_rounds (opt-in size, map_configure_kernels)
+    ActiveSet as;
+    WarpScratch wsc[16];
+    CellRec cells[16][NCELL];
+    int s_cnt, s_nready;
+};
+
 __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
-    __shared__ ActiveSet as;
-    __shared__ WarpScratch wsc[16];
-    __shared__ int s_cnt, s_nready;
+    extern __shared__ __align__(16) unsigned char merge_smem[];
+    MergeShared& S = *reinterpret_cast<MergeShared*>(merge_smem);
+    ActiveSet& as = S.as;
+    WarpScratch* wsc = S.wsc;
+    int& s_cnt = S.s_cnt;
+    int& s_nready = S.s_nready;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = ctl->n_hot;                       // (voxel, first relevant event) pairs prepared by k_merge_prefilter
     if (n0 == 0) return;
@@ -460,20 +791,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
         as_set_key(as, k, m.skey[A]);
     }
     __syncthreads();
-    // The rounds below are chains of dependent look-ups (neighbour key -> hash -> slot -> record -> covariance) by a
-    // single CTA; after the fill kernels have streamed hundreds of MB through the L2 (200 k-point scans) every link of the
-    // chain is a DRAM round trip.  One parallel pass first resolves the six neighbours of every active voxel and
-    // prefetches what merge() reads about them, so that the serial part runs out of the L2.
-    for (int k = tid; k < n0 * 8; k += blockDim.x) {
-        const int j = k >> 3, d = k & 7;
-        const int A = as.slot[j];
-        if (d == 6) { prefetch_slot(m, A); continue; }
-        if (d == 7) continue;
-        bool ok;
-        const unsigned long long nk = nbr_key(m.skey[A], d, ok);
-        if (!ok) continue;
-        for (int X = hash_find(m, nk); X >= 0; X = m.ghost[X]) prefetch_slot(m, X);
-    }
+    // (everything the events will look at was pulled into the L2 by k_merge_prefilter, 25 cells around every active voxel)
     for (int round = 0; round < 100000; round++) {
         const int n = as.n;
         // readiness (one warp per entry, lanes over the others): no other entry with an earlier event within MERGE_R
@@ -488,7 +806,10 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
         }
         __syncthreads();
         const int nr = s_nready;
-        for (int q = wid; q < nr; q += 16) process_event(m, ctl, as, wsc[wid], as.rlist[q], scan_id);   // one ready event per warp
+        for (int q = wid; q < nr; q += 16) {                             // one ready event per warp
+            const int j = as.rlist[q];
+            if (!process_event_fast(m, ctl, as, wsc[wid], S.cells[wid], j, scan_id)) process_event(m, ctl, as, wsc[wid], j, scan_id);
+        }
         __syncthreads();
         // compaction of retired entries (one warp), keeps the rest in place order
         if (wid == 0) {
