@@ -318,8 +318,8 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
     g.close()
 
     # ---------------- pass 1c: the whole host loop (IMU propagation + compensation + update), per rank
-    def lio_loop(pipelined, device_undistort=True, writeback=True):
-        lb = LIOBuilder(cfg, pipelined=pipelined, device_undistort=device_undistort, cloud_writeback=writeback)
+    def lio_loop(pipelined, device_undistort=True, writeback=True, device_predict=False):
+        lb = LIOBuilder(cfg, pipelined=pipelined, device_undistort=device_undistort, cloud_writeback=writeback, device_predict=device_predict)
         cl = [pk.cloud.copy() for pk in pkgs]
         t0 = None
         done = 0
@@ -339,13 +339,15 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
         return world * n / replicas.max_over_ranks(dt, dev)
     sampler = ClockSampler(local)
     sampler.start()                      # streaming from here on; the reported window opens at the first timed step of pass 2
-    loop_host = loop_sync = loop_pipe = loop_sync_lazy = loop_pipe_lazy = None
+    loop_host = loop_sync = loop_pipe = loop_sync_lazy = loop_pipe_lazy = loop_sync_pred = loop_pipe_pred = None
     if full and not args.no_loops:
         loop_host = lio_loop(False, device_undistort=False)
         loop_sync = lio_loop(False)
         loop_pipe = lio_loop(True)
         loop_sync_lazy = lio_loop(False, writeback=False)
         loop_pipe_lazy = lio_loop(True, writeback=False)
+        loop_sync_pred = lio_loop(False, device_predict=True)
+        loop_pipe_pred = lio_loop(True, device_predict=True)
 
     # ---------------- pass 2: resident replay (scan + prior already in HBM), timed per step with CUDA events
     g = HotPath(cfg)
@@ -494,10 +496,12 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
                           "host_undistort_scans_per_s": round(loop_host, 1), "sync_scans_per_s": round(loop_sync, 1),
                           "pipelined_scans_per_s": round(loop_pipe, 1),
                           "sync_no_writeback_scans_per_s": round(loop_sync_lazy, 1), "pipelined_no_writeback_scans_per_s": round(loop_pipe_lazy, 1),
+                          "sync_device_predict_scans_per_s": round(loop_sync_pred, 1), "pipelined_device_predict_scans_per_s": round(loop_pipe_pred, 1),
                           "what": "wall clock of the whole LIOBuilder.process loop, lio_builder.cpp:65-246 (host IMU propagation, motion "
                                   "compensation, update), all ranks / max over ranks: compensation on the host + vmp_scan / on the device in the "
                                   "scan's graph (vmp_scan_raw) / the same with vmp_set_pipelined; no_writeback: the compensated cloud is not copied back into the "
-                                  "caller's buffer (vmp_set_raw_writeback 0; it stays readable through vmp_get_lidar_cloud)"},
+                                  "caller's buffer (vmp_set_raw_writeback 0; it stays readable through vmp_get_lidar_cloud); device_predict: IESKF::predict on the device too "
+                                  "(vmp_scan_raw_predict, SURVEY 8f row 2; A/B against the host propagation of the two lines above it)"},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
             "roofline": roof,

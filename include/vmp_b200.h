@@ -198,6 +198,18 @@ typedef struct vmp_pose { double offset; double acc[3], gyro[3], vel[3], pos[3],
  * the end-of-scan pose = x, the propagated prior).  poses: 2 <= n_poses <= 64.  Then exactly vmp_scan. */
 int vmp_scan_raw(vmp_handle h, vmp_state* x_inout, double* P_inout, float* cloud_xyzt, int n,
                  const vmp_pose* poses, int n_poses, vmp_scan_stats* stats);
+/* the IMU propagation IESKF::predict (ieskf.cpp:101-123, called at lio_builder.cpp:106,116) on the device as
+ * well.  The filter state and covariance stay RESIDENT on the device from scan to scan (after vmp_first_scan / a previous scan);
+ * the host only supplies the IMU input of every propagation step of LIOBuilder::undistortCloud (lio_builder.cpp:89-114): averaged
+ * gyro / acceleration (the latter rescaled by 9.81 / gravity_norm, :96), the step length dt, and the time offset of the IMU pose the
+ * step ends at (tail.timestamp - cloud_start_time; VMP_NO_POSE for the closing step to the end of the scan, which records no pose).
+ * Q: 12 x 12 process noise (lio_builder.cpp:9-12).  last_acc_gyro: LIODataGroup::last_acc, last_gyro (6 doubles) for the FIRST
+ * device-propagated scan (they come from the host propagation of the MAP_INIT scan); NULL afterwards (the device keeps them).
+ * Then exactly vmp_scan_raw: motion compensation, update; x_out / P_out receive the posterior. */
+#define VMP_NO_POSE (-1.0e300)
+typedef struct vmp_imu_step { double acc[3], gyro[3], dt, offset; } vmp_imu_step;
+int vmp_scan_raw_predict(vmp_handle h, vmp_state* x_out, double* P_out, float* cloud_xyzt, int n,
+                         const vmp_imu_step* steps, int n_steps, const double* Q, const double* last_acc_gyro, vmp_scan_stats* stats);
 /* The copy of the compensated cloud back into the caller's buffer (the reference edits package.cloud in place,
  * lio_builder.cpp:145-147) is on by default; on = 0 leaves the caller's buffer untouched - the compensated (and, with
  * scan_resolution > 0, filtered) cloud of the last raw scan is always available through vmp_get_lidar_cloud, which is what
@@ -211,6 +223,9 @@ int vmp_set_raw_writeback(vmp_handle h, int on);
  * the leaf centroids; vmp_get_lidar_cloud returns them (LIOBuilder::lidar_cloud, lio_builder.h:83). */
 int vmp_downsample(vmp_handle h, const float* cloud_xyzc, int n, double leaf, float* out_xyzc, int cap, int* m);
 int vmp_get_lidar_cloud(vmp_handle h, float* out_xyzc, int cap, int* m);
+/* the prior (x, P after the IMU propagation) of the last scan as the device saw it: what vmp_scan / vmp_scan_raw uploaded, or what
+ * the device-side propagation of vmp_scan_raw_predict produced */
+int vmp_get_prior(vmp_handle h, vmp_state* x, double* P);
 int vmp_set_state(vmp_handle h, const vmp_state* x, const double* P);
 int vmp_get_state(vmp_handle h, vmp_state* x, double* P);
 
@@ -264,6 +279,8 @@ vmp_handle vmp_lio_map(vmp_lio l);
 int vmp_lio_set_device_undistort(vmp_lio l, int on);
 /* vmp_set_raw_writeback of the builder's map handle: 0 = process() does not copy the compensated cloud back into `cloud_xyzc` */
 int vmp_lio_set_cloud_writeback(vmp_lio l, int on);
+/* IMU propagation on the device too (vmp_scan_raw_predict; off by default: on the host it overlaps with the device's map update) */
+int vmp_lio_set_device_predict(vmp_lio l, int on);
 /* the prior (x, P after IMU propagation) that the last process() handed to the device update */
 int vmp_lio_prior(vmp_lio l, vmp_state* x, double* P);
 

@@ -394,6 +394,43 @@ def test_device_undistortion_matches_host(oracle_mod):
     assert_maps_equal(o.dump_map(), dev.map.dump_map(), exact=False, rtol=1e-6, what="device-undistorted map")
 
 
+def test_device_imu_propagation_matches_host_and_oracle(oracle_mod):
+    """SURVEY 8(f) row 2: IESKF::predict + the IMU pose list on the device (vmp_scan_raw_predict, k_predict), state / P resident there.
+    Free-running against the host-propagating builder and the oracle: the propagated prior of every scan against the oracle's
+    (IESKF::predict, ieskf.cpp:101-123), the posteriors within tier 3, identical iteration counts."""
+    from helpers import cov_rel_err
+    cfg = default_config(max_points_per_scan=8192)
+    o = oracle_mod.Oracle(cfg)
+    dev = LIOBuilder(cfg, device_predict=True)
+    host = LIOBuilder(cfg)
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=5000))
+    worst_x = worst_P = worst_post = 0.0
+    n = 0
+    for pk in seq.packages(45):
+        so = o.lio_process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        sd = dev.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        sh = host.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        xo, _, s0 = o.lio_state()
+        xd, Pd, s1 = dev.state()
+        xh, Ph, s2 = host.state()
+        assert s0 == s1 == s2
+        if s0 < 2 or so.iters == 0:
+            continue
+        assert sd.iters == so.iters == sh.iters
+        xp_o, Pp_o = o.get_prior()
+        xp_d, Pp_d = dev.map.get_prior()
+        for f in ("pos", "rot", "vel", "bg", "ba", "g", "rot_ext", "pos_ext"):
+            worst_x = max(worst_x, float(np.abs(np.array(getattr(xp_d, f)[:]) - np.array(getattr(xp_o, f)[:])).max()))
+        worst_P = max(worst_P, cov_rel_err(Pp_d, Pp_o))
+        worst_post = max(worst_post, float(np.linalg.norm(np.array(xd.pos[:]) - np.array(xh.pos[:]))))
+        assert np.linalg.norm(np.array(xd.pos[:]) - np.array(xo.pos[:])) < 1e-3
+        n += 1
+    assert n >= 30
+    print(f"device IMU propagation over {n} scans: prior state vs oracle <= {worst_x:.1e}, prior P (relative) <= {worst_P:.1e}, posterior vs host-propagating builder <= {worst_post:.1e} m")
+    assert worst_x < 1e-8 and worst_P < 1e-7 and worst_post < 1e-6
+    assert_maps_equal(host.map.dump_map(), dev.map.dump_map(), exact=False, rtol=1e-6, what="device-propagated map")
+
+
 def test_city_run_with_continuous_eviction(oracle_mod):
     """C3 in small (BASELINE.json configs[2]): drive along a street of scene B at up to 5 m/s with a map capacity far below
     the voxels seen, so that LRU eviction runs in every scan (tens of thousands of victims over the run).

@@ -180,6 +180,14 @@ class HotPath:
         self._check(self._fn("first_scan")(self._h, C.byref(x), dptr(P), fptr(p), p.shape[0], C.byref(st)))
         return st.as_dict()
 
+    def get_prior(self):
+        """prior (x, P) of the last scan as the device saw it (uploaded, or propagated on the device by vmp_scan_raw_predict)"""
+        x = VmpState()
+        P = np.zeros((23, 23))
+        self._lib.vmp_get_prior.argtypes = [C.c_void_p, C.POINTER(VmpState), C.POINTER(C.c_double)]
+        self._check(self._lib.vmp_get_prior(self._h, C.byref(x), dptr(P)))
+        return x, P
+
     def set_state(self, x: VmpState, P):
         P = _f64(P, (23, 23))
         self._check(self._fn("set_state")(self._h, C.byref(x), dptr(P)))

@@ -102,6 +102,9 @@ struct vmp_handle_t {
     bool last_raw = false;               // the last scan was a vmp_scan_raw (its compensated cloud is in h_cloud)
     cudaGraphExec_t graph_raw = nullptr; // the scan graph with the motion compensation in front
     int graph_raw_kernels = 0;
+    cudaGraphExec_t graph_pred = nullptr;    // ... and with the IMU propagation (k_predict) in front of that
+    int graph_pred_kernels = 0;
+    DevPredictIn* h_pred = nullptr; DevPredictIn* d_pred = nullptr;      // IMU steps of the scan (pinned / device)
     unsigned long long seq = 0;
     bool pipelined = false;              // vmp_set_pipelined: vmp_scan returns when the posterior is out, the map update runs on
     bool map_pending = false;            // a map update whose MapOut has not been consumed yet
@@ -170,10 +173,13 @@ void prof_mark(void* ctx, int id) {
 
 // enqueue every kernel of one scan on h->stream (used both for graph capture and, in
 // profiling mode, directly with an event after each launch)
-int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw) {
+int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw, bool predict = false) {
     cudaStream_t st = h->stream;
     const bool ext = h->cfg.estimate_ext != 0;
     int k = 0;
+    if (predict) {  // ieskf.cpp:101-123 for every IMU step of the scan, from the state resident on the device
+        launch_predict(st, h->f, h->d_in, h->d_pred, (DevPose*)(h->d_stage + IN_HDR)); k++; mark(mk, VMP_K_UPDATE_BEGIN);
+    }
     if (raw) {      // lio_builder.cpp:127-152 in front of the timed region: the points are compensated where they were uploaded
         launch_undistort(st, h->grid_pts, h->d_in, (const DevPose*)(h->d_stage + IN_HDR), (float4*)(h->d_stage + PTS_OFF), h->a_cloud); k++; mark(mk, VMP_K_UNDISTORT);
     }
@@ -197,7 +203,7 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw) {
 }
 
 // run one scan: the instantiated graph, or (profiling) the same kernels one by one
-int run_scan(vmp_handle_t* h, bool raw, int n_raw = 0) {
+int run_scan(vmp_handle_t* h, bool raw, int n_raw = 0, bool predict = false) {
     const bool ds = raw && h->cfg.scan_resolution > 0.0;
     h->ds_valid = ds;
     h->last_raw = raw;
@@ -207,11 +213,12 @@ int run_scan(vmp_handle_t* h, bool raw, int n_raw = 0) {
         // (n, points, stride) to the leaf centroids and the plain scan graph follows
         Marker mk{prof_mark, h};
         if (h->prof_on) { h->pev_n = 0; VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream)); }
+        if (predict) { launch_predict(h->stream, h->f, h->d_in, h->d_pred, (DevPose*)(h->d_stage + IN_HDR)); h->launches++; if (h->prof_on) mark(&mk, VMP_K_UPDATE_BEGIN); }
         launch_undistort(h->stream, h->grid_pts, h->d_in, (const DevPose*)(h->d_stage + IN_HDR), (float4*)(h->d_stage + PTS_OFF), h->a_cloud);
         if (h->prof_on) mark(&mk, VMP_K_UNDISTORT);
         h->launches += 1 + launch_downsample(h->stream, h->ds, (const float4*)(h->d_stage + PTS_OFF), &h->d_in->n, n_raw, (float)h->cfg.scan_resolution,
                                              h->grid_pts, h->a_ds, h->a_ds_m, h->d_in, h->prof_on ? &mk : nullptr);
-        raw = false;
+        raw = false; predict = false;
         if (h->prof_on) {
             h->launches += enqueue_scan(h, &mk, false);
             VMP_CUDA_CHECK(cudaGetLastError());
@@ -219,14 +226,14 @@ int run_scan(vmp_handle_t* h, bool raw, int n_raw = 0) {
         }
     }
     if (!h->prof_on) {
-        VMP_CUDA_CHECK(cudaGraphLaunch(raw ? h->graph_raw : h->graph, h->stream));
-        h->launches += raw ? h->graph_raw_kernels : h->graph_kernels;
+        VMP_CUDA_CHECK(cudaGraphLaunch(predict ? h->graph_pred : raw ? h->graph_raw : h->graph, h->stream));
+        h->launches += predict ? h->graph_pred_kernels : raw ? h->graph_raw_kernels : h->graph_kernels;
         return VMP_OK;
     }
     Marker mk{prof_mark, h};
     h->pev_n = 0;
     VMP_CUDA_CHECK(cudaEventRecord(h->pev[0], h->stream));
-    h->launches += enqueue_scan(h, &mk, raw);
+    h->launches += enqueue_scan(h, &mk, raw, predict);
     VMP_CUDA_CHECK(cudaGetLastError());
     return VMP_OK;
 }
@@ -254,6 +261,11 @@ int build_graph(vmp_handle_t* h) {
     h->graph_raw_kernels = enqueue_scan(h, nullptr, true);
     VMP_CUDA_CHECK(cudaStreamEndCapture(h->stream, &g));
     VMP_CUDA_CHECK(cudaGraphInstantiate(&h->graph_raw, g, 0));
+    VMP_CUDA_CHECK(cudaGraphDestroy(g));
+    VMP_CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->graph_pred_kernels = enqueue_scan(h, nullptr, true, true);
+    VMP_CUDA_CHECK(cudaStreamEndCapture(h->stream, &g));
+    VMP_CUDA_CHECK(cudaGraphInstantiate(&h->graph_pred, g, 0));
     VMP_CUDA_CHECK(cudaGraphDestroy(g));
     return VMP_OK;
 }
@@ -435,7 +447,9 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
         VMP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->a_ds_m, h->h_ds_m, 0));
         *h->h_ds_m = 0;
     }
-    DALLOC(h->f, 1); DALLOC(h->ctl, 1);
+    DALLOC(h->f, 1); DALLOC(h->ctl, 1); DALLOC(h->d_pred, 1);
+    VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_pred, sizeof(DevPredictIn)));
+    std::memset(h->h_pred, 0, sizeof(DevPredictIn));
     VMP_CUDA_CHECK(cudaMemsetAsync(h->f, 0, sizeof(DevFilter), h->stream));
     VMP_CUDA_CHECK(cudaMemsetAsync(h->ctl, 0, sizeof(DevCtl), h->stream));
     h->grid_pts = std::max(1, std::min(h->sm_count * 2, (nmax + 255) / 256));
@@ -489,6 +503,8 @@ int vmp_destroy(vmp_handle h) {
     if (h->h_ds) cudaFreeHost(h->h_ds);
     if (h->h_ds_m) cudaFreeHost(h->h_ds_m);
     if (h->graph_raw) cudaGraphExecDestroy(h->graph_raw);
+    if (h->graph_pred) cudaGraphExecDestroy(h->graph_pred);
+    if (h->h_pred) cudaFreeHost(h->h_pred);
     if (h->h_sout) cudaFreeHost(h->h_sout);
     if (h->h_mout) cudaFreeHost(h->h_mout);
     for (int b = 0; b < 2; b++) { if (h->pe0[b]) cudaEventDestroy(h->pe0[b]); if (h->pe1[b]) cudaEventDestroy(h->pe1[b]); }
@@ -575,6 +591,16 @@ int vmp_get_state(vmp_handle h, vmp_state* x, double* P) {
     return VMP_OK;
 }
 
+int vmp_get_prior(vmp_handle h, vmp_state* x, double* P) {
+    int r = check_n(h, 0, "vmp_get_prior");
+    if (r) return r;
+    // the device copy of the last scan's header: uploaded by vmp_scan / vmp_scan_raw, written by k_predict for vmp_scan_raw_predict
+    if (x) VMP_CUDA_CHECK(cudaMemcpyAsync(x, h->d_in->x, sizeof(double) * 36, cudaMemcpyDeviceToHost, h->stream));
+    if (P) VMP_CUDA_CHECK(cudaMemcpyAsync(P, h->d_in->P, sizeof(double) * 529, cudaMemcpyDeviceToHost, h->stream));
+    VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return VMP_OK;
+}
+
 int vmp_set_scan(vmp_handle h, const float* pts, int n) {
     int r = check_n(h, n, "vmp_set_scan");
     if (r) return r;
@@ -616,12 +642,13 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
 // of a chunk running while the helpers stage the next one; check_stride > 0 also checks the time order of a raw scan on the way
 // (*sorted).  src == null: everything is in the pinned staging already, one DMA copy.
 static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t upload_bytes, vmp_scan_stats* stats, bool raw = false,
-                       const void* src = nullptr, int check_stride = 0) {
+                       const void* src = nullptr, int check_stride = 0, bool predict = false) {
     const bool pipe = h->pipelined && !h->prof_on;
     const unsigned long long seq = ++h->seq;
     h->h_in->seq = seq; h->h_in->n = n;
     const int eb = (int)(seq & 1);
     VMP_CUDA_CHECK(cudaEventRecord(h->pe0[eb], h->stream));
+    if (predict) VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_pred, h->h_pred, sizeof(DevPredictIn), cudaMemcpyHostToDevice, h->stream));
     if (!src) {
         VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
     } else {
@@ -647,7 +674,7 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
             VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage + PTS_OFF, h->h_stage + PTS_OFF, pts_bytes, cudaMemcpyHostToDevice, h->stream));
         }
     }
-    { const int rr = run_scan(h, raw, n); if (rr) return rr; }
+    { const int rr = run_scan(h, raw, n, predict); if (rr) return rr; }
     VMP_CUDA_CHECK(cudaEventRecord(h->pe1[eb], h->stream));
     h->n_last = n;
     if (!pipe) {
@@ -745,6 +772,29 @@ int vmp_scan_raw(vmp_handle h, vmp_state* x, double* P, float* cloud_xyzt, int n
     r = scan_common(h, x, P, n, PTS_OFF + sizeof(float) * 4 * (size_t)n, stats, true, n > 0 ? cloud_xyzt : nullptr, 4);
     // the compensated cloud was written to mapped host memory by the first kernel of the graph, before the posterior; it
     // stays available through vmp_get_lidar_cloud, the copy into the caller's buffer can be switched off (vmp_set_raw_writeback)
+    if (h->raw_writeback) h->pool.copy(cloud_xyzt, h->h_cloud, sizeof(float) * 4 * (size_t)n);
+    if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+    return r;
+}
+
+int vmp_scan_raw_predict(vmp_handle h, vmp_state* x_out, double* P_out, float* cloud_xyzt, int n, const vmp_imu_step* steps, int n_steps,
+                         const double* Q, const double* last_acc_gyro, vmp_scan_stats* stats) {
+    const auto t_enter = std::chrono::steady_clock::now();
+    int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan_raw_predict") : check_n(h, n, "vmp_scan_raw_predict");
+    if (r) return r;
+    if (!x_out || !P_out || (n > 0 && !cloud_xyzt) || !steps || !Q) { set_error("vmp_scan_raw_predict: null argument"); return VMP_ERR_INVALID_ARG; }
+    if (n_steps < 1 || n_steps > MAX_POSES) { set_error("vmp_scan_raw_predict: n_steps=%d outside [1, %d]", n_steps, MAX_POSES); return VMP_ERR_INVALID_ARG; }
+    if (!h->map_built) { set_error("vmp_scan_raw_predict: no map yet (call vmp_first_scan or vmp_map_build first)"); return VMP_ERR_STATE; }
+    static_assert(sizeof(vmp_imu_step) == sizeof(DevImuStep), "vmp_imu_step layout");
+    std::memcpy(h->h_pred->steps, steps, sizeof(vmp_imu_step) * (size_t)n_steps);
+    std::memcpy(h->h_pred->Q, Q, sizeof(double) * 144);
+    h->h_pred->n_steps = n_steps;
+    h->h_pred->use_last = last_acc_gyro ? 1 : 0;
+    if (last_acc_gyro) std::memcpy(h->h_pred->last, last_acc_gyro, sizeof(double) * 6);
+    // the prior (x, P) and the IMU poses are written into the device copy of the header / staging by k_predict
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE | SCAN_PREDICT;
+    h->h_in->n_poses = 0; h->h_in->stride = 4;
+    r = scan_common(h, x_out, P_out, n, PTS_OFF + sizeof(float) * 4 * (size_t)n, stats, true, n > 0 ? cloud_xyzt : nullptr, 4, true);
     if (h->raw_writeback) h->pool.copy(cloud_xyzt, h->h_cloud, sizeof(float) * 4 * (size_t)n);
     if (stats) stats->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return r;
@@ -933,7 +983,7 @@ int vmp_profile_read(vmp_handle h, double* ms, int64_t* launches) {
 }
 const char* vmp_kernel_name(int id) {
     static const char* names[VMP_K_COUNT] = {
-        "k_scan_in", "k_set_scan", "k_update_begin", "k_measure", "k_ieskf_solve", "k_world_insert_count",
+        "k_scan_in", "k_set_scan", "k_predict", "k_measure", "k_ieskf_solve", "k_world_insert_count",
         "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
         "k_fill", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
         "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_classify", "k_fill_acc", "k_undistort", "k_downsample"};

@@ -100,6 +100,7 @@ __device__ __forceinline__ void map_counters_reset(DevCtl* ctl) {
 constexpr int SCAN_STATE_HDR = 1;       // ScanIn::x / P hold the prior (vmp_scan)
 constexpr int SCAN_STATE_DEV = 2;       // ScanIn::prior points at 36 + 529 doubles in device memory (vmp_scan_dev)
 constexpr int SCAN_BEGIN_UPDATE = 4;    // start of IESKF::update: predict_x = x_, iteration counters (ieskf.cpp:127-130)
+constexpr int SCAN_PREDICT = 8;         // the prior and the IMU poses are produced on the device (k_predict) from the filter state resident there
 struct ScanIn {
     const float* pts;                   // n points, `stride` floats apart (3: xyz, 4: xyz + time offset), device memory
     const double* prior;
@@ -129,6 +130,16 @@ struct DevFilter {
     double x[36];                       // vmp_state layout: pos3 rot9 rot_ext9 pos_ext3 vel3 bg3 ba3 g3
     double xpred[36];
     double P[529];
+    double last[6];                     // LIODataGroup::last_acc / last_gyro (lio_builder.h:48-49), kept across scans by k_predict
+};
+// one propagation step of LIOBuilder::undistortCloud's IMU loop (lio_builder.cpp:89-111): averaged, rescaled IMU input, step length,
+// and the time offset of the pose it ends at (-1e300: the closing step to the end of the scan, :113-114, which records no pose)
+struct DevImuStep { double acc[3], gyro[3], dt, offset; };
+struct DevPredictIn {
+    DevImuStep steps[MAX_POSES];
+    double Q[144];                      // process noise (lio_builder.cpp:9-12)
+    double last[6];                     // last_acc / last_gyro to start from when use_last != 0 (first device-propagated scan)
+    int n_steps, use_last;
 };
 
 struct DevMap {

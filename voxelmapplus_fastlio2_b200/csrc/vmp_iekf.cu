@@ -348,6 +348,132 @@ __global__ void __launch_bounds__(256) k_undistort(const ScanIn* __restrict__ in
         if (host_copy) host_copy[i] = p;                              // mapped host memory: the caller's cloud is edited in place
     }
 }
+// ---------------------------------------------------------------------------- IMU propagation on the device
+// IESKF::predict (ieskf.cpp:101-123) for every IMU step of the scan, and the IMU pose list of LIOBuilder::undistortCloud
+// (lio_builder.cpp:78-116), by ONE CTA at the head of the raw scan's graph: the filter state and covariance stay resident on the
+// device from scan to scan.  F is the identity plus seven small blocks and G has four, so P = F P F^T + G Q G^T is evaluated on
+// the structural non-zeros only, in ascending column order - the same terms in the same order as the host / oracle evaluation
+// (x + 0 * y == x).  Writes the propagated prior into the scan header (where the motion compensation and the first IEKF
+// iteration read it) and the poses into the staging area.
+struct PredictRows { signed char n[23]; signed char col[23][9]; };
+__constant__ PredictRows c_frows = {
+    {2, 2, 2, 6, 6, 6, 1, 1, 1, 1, 1, 1, 9, 9, 9, 1, 1, 1, 1, 1, 1, 2, 2},
+    {{0, 12}, {1, 13}, {2, 14}, {3, 4, 5, 15, 16, 17}, {3, 4, 5, 15, 16, 17}, {3, 4, 5, 15, 16, 17}, {6}, {7}, {8}, {9}, {10}, {11},
+     {3, 4, 5, 12, 18, 19, 20, 21, 22}, {3, 4, 5, 13, 18, 19, 20, 21, 22}, {3, 4, 5, 14, 18, 19, 20, 21, 22},
+     {15}, {16}, {17}, {18}, {19}, {20}, {21, 22}, {21, 22}}};
+__constant__ PredictRows c_grows = {
+    {0, 0, 0, 3, 3, 3, 0, 0, 0, 0, 0, 0, 3, 3, 3, 1, 1, 1, 1, 1, 1, 0, 0},
+    {{0}, {0}, {0}, {0, 1, 2}, {0, 1, 2}, {0, 1, 2}, {0}, {0}, {0}, {0}, {0}, {0}, {3, 4, 5}, {3, 4, 5}, {3, 4, 5}, {6}, {7}, {8}, {9}, {10}, {11}, {0}, {0}}};
+
+__global__ void __launch_bounds__(256) k_predict(DevFilter* f, ScanIn* in, const DevPredictIn* __restrict__ pin, DevPose* poses) {
+    __shared__ double sx[36], sxn[36], sP[529], sF[529], sT1[529], sT2[529], sG[276], sT3[276], sQ[144], slast[6];
+    const int tid = threadIdx.x;
+    for (int q = tid; q < 36; q += 256) sx[q] = f->x[q];
+    for (int q = tid; q < 529; q += 256) sP[q] = f->P[q];
+    for (int q = tid; q < 144; q += 256) sQ[q] = pin->Q[q];
+    if (tid < 6) slast[tid] = pin->use_last ? pin->last[tid] : f->last[tid];
+    const int ns = pin->n_steps;
+    __syncthreads();
+    int npose = 0;
+    if (tid == 0) {         // Pose{0.0, last_acc, last_gyro, vel, pos, rot} (lio_builder.cpp:78-79)
+        DevPose& p = poses[0];
+        p.offset = 0.0;
+        for (int k = 0; k < 3; k++) { p.acc[k] = slast[k]; p.gyro[k] = slast[3 + k]; p.vel[k] = sx[24 + k]; p.pos[k] = sx[k]; }
+        for (int k = 0; k < 9; k++) p.rot[k] = sx[3 + k];
+    }
+    npose = 1;
+    for (int s = 0; s < ns; s++) {
+        const DevImuStep st = pin->steps[s];
+        const double dt = st.dt;
+        const St x = st_load(sx);
+        const V3 w = sub(v3(st.gyro[0], st.gyro[1], st.gyro[2]), x.bg);
+        const V3 a = sub(v3(st.acc[0], st.acc[1], st.acc[2]), x.ba);
+        // F = I + blocks, G (ieskf.cpp:104-117); five independent pieces on five warps
+        for (int q = tid; q < 529; q += 256) sF[q] = (q / 23 == q % 23) ? 1.0 : 0.0;
+        for (int q = tid; q < 276; q += 256) sG[q] = 0.0;
+        __syncthreads();
+        if (tid == 0) {
+            const M3 e = so3_exp(scale(neg(w), dt));
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) sF[(3 + i) * 23 + 3 + j] = e(i, j);
+            for (int i = 0; i < 3; i++) { sF[i * 23 + 12 + i] = dt; sG[(15 + i) * 12 + 6 + i] = dt; sG[(18 + i) * 12 + 9 + i] = dt; }
+        } else if (tid == 32) {
+            const M3 j = scale(neg(right_jacobian(scale(w, dt))), dt);
+            for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { sF[(3 + i) * 23 + 15 + k] = j(i, k); sG[(3 + i) * 12 + k] = j(i, k); }
+        } else if (tid == 64) {
+            const M3 ra = scale(mul(neg(x.rot), hat(a)), dt);
+            const M3 nr = scale(neg(x.rot), dt);
+            for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { sF[(12 + i) * 23 + 3 + k] = ra(i, k); sF[(12 + i) * 23 + 18 + k] = nr(i, k); sG[(12 + i) * 12 + 3 + k] = nr(i, k); }
+        } else if (tid == 96) {
+            const Mat<3, 2> mx = st_Mx(x.g);
+            const Mat<3, 2> mxd = scale(mx, dt);
+            const Mat<2, 2> nm = mul(st_Nx(x.g), mx);
+            for (int i = 0; i < 3; i++) for (int k = 0; k < 2; k++) sF[(12 + i) * 23 + 21 + k] = mxd(i, k);
+            for (int i = 0; i < 2; i++) for (int k = 0; k < 2; k++) sF[(21 + i) * 23 + 21 + k] = nm(i, k);
+        } else if (tid == 128) {
+            // x_ += delta (Vector24d variant, ieskf.cpp:23-33): only pos, rot, vel change (the other blocks add exact zeros)
+            St xn = x;
+            xn.pos = add(x.pos, scale(x.vel, dt));
+            xn.rot = mul(x.rot, so3_exp(scale(w, dt)));
+            xn.vel = add(x.vel, scale(add(mul(x.rot, a), x.g), dt));
+            st_store(xn, sxn);
+        }
+        __syncthreads();
+        for (int q = tid; q < 529; q += 256) {              // T1 = F P
+            const int i = q / 23, j = q % 23;
+            double acc = sF[i * 23 + c_frows.col[i][0]] * sP[c_frows.col[i][0] * 23 + j];
+            for (int e = 1; e < c_frows.n[i]; e++) { const int c = c_frows.col[i][e]; acc += sF[i * 23 + c] * sP[c * 23 + j]; }
+            sT1[q] = acc;
+        }
+        for (int q = tid; q < 276; q += 256) {              // T3 = G Q
+            const int i = q / 12, c = q % 12;
+            double acc = 0.0;
+            if (c_grows.n[i] > 0) {
+                acc = sG[i * 12 + c_grows.col[i][0]] * sQ[c_grows.col[i][0] * 12 + c];
+                for (int e = 1; e < c_grows.n[i]; e++) { const int k = c_grows.col[i][e]; acc += sG[i * 12 + k] * sQ[k * 12 + c]; }
+            }
+            sT3[q] = acc;
+        }
+        __syncthreads();
+        for (int q = tid; q < 529; q += 256) {              // T2 = T1 F^T ; P = T2 + T3 G^T
+            const int i = q / 23, j = q % 23;
+            double acc = sT1[i * 23 + c_frows.col[j][0]] * sF[j * 23 + c_frows.col[j][0]];
+            for (int e = 1; e < c_frows.n[j]; e++) { const int c = c_frows.col[j][e]; acc += sT1[i * 23 + c] * sF[j * 23 + c]; }
+            double g = 0.0;
+            if (c_grows.n[i] > 0 && c_grows.n[j] > 0) {
+                g = sT3[i * 12 + c_grows.col[j][0]] * sG[j * 12 + c_grows.col[j][0]];
+                for (int e = 1; e < c_grows.n[j]; e++) { const int c = c_grows.col[j][e]; g += sT3[i * 12 + c] * sG[j * 12 + c]; }
+            }
+            sT2[q] = acc + g;
+        }
+        __syncthreads();
+        for (int q = tid; q < 529; q += 256) sP[q] = sT2[q];
+        if (tid < 36) sx[tid] = sxn[tid];
+        __syncthreads();
+        if (st.offset > -1.0e299) {     // (the closing step carries -1e300) last_gyro / last_acc with the propagated state, pose at the end of the step (lio_builder.cpp:107-111)
+            if (tid == 0) {
+                const St xu = st_load(sx);
+                const V3 lg = sub(v3(st.gyro[0], st.gyro[1], st.gyro[2]), xu.bg);
+                const V3 la = add(mul(xu.rot, sub(v3(st.acc[0], st.acc[1], st.acc[2]), xu.ba)), xu.g);
+                for (int k = 0; k < 3; k++) { slast[k] = la[k]; slast[3 + k] = lg[k]; }
+                if (npose < MAX_POSES) {
+                    DevPose& p = poses[npose];
+                    p.offset = st.offset;
+                    for (int k = 0; k < 3; k++) { p.acc[k] = la[k]; p.gyro[k] = lg[k]; p.vel[k] = xu.vel[k]; p.pos[k] = xu.pos[k]; }
+                    for (int k = 0; k < 9; k++) p.rot[k] = xu.rot.a[k];
+                }
+            }
+            npose++;
+        }
+        __syncthreads();
+    }
+    // the propagated prior -> scan header (k_undistort, first IEKF iteration) and filter; last_acc / last_gyro for the next scan
+    for (int q = tid; q < 36; q += 256) { in->x[q] = sx[q]; f->x[q] = sx[q]; }
+    for (int q = tid; q < 529; q += 256) { in->P[q] = sP[q]; f->P[q] = sP[q]; }
+    if (tid < 6) f->last[tid] = slast[tid];
+    if (tid == 0) in->n_poses = npose < MAX_POSES ? npose : MAX_POSES;
+}
+void launch_predict(cudaStream_t st, DevFilter* f, ScanIn* in, const DevPredictIn* pin, DevPose* poses) { k_predict<<<1, 256, 0, st>>>(f, in, pin, poses); }
+
 void launch_undistort(cudaStream_t st, int grid, const ScanIn* in, const DevPose* poses, float4* cloud, float4* host_copy) {
     k_undistort<<<grid, 256, 0, st>>>(in, poses, cloud, host_copy);
 }

@@ -208,6 +208,39 @@ void LIOBuilder::undistortCloud(SyncPackage& package, bool compensate) {
     }
 }
 
+// lio_builder.cpp:65-116 without kf.predict: the averaged / rescaled IMU input, length and pose offset of every propagation step
+// (the propagation itself and the pose list are then produced on the device, vmp_scan_raw_predict)
+void LIOBuilder::collectImuSteps(SyncPackage& package, std::vector<vmp_imu_step>& steps) {
+    imu_cache.clear();
+    imu_cache.push_back(last_imu);
+    imu_cache.insert(imu_cache.end(), package.imus.begin(), package.imus.end());
+    const double imu_time_end = imu_cache.back().timestamp;
+    const double cloud_time_begin = package.cloud_start_time, cloud_time_end = package.cloud_end_time;
+    steps.clear();
+    V3 acc_val = zeros<3, 1>(), gyro_val = zeros<3, 1>();
+    double dt = 0.0;
+    auto push = [&](double step_dt, double offset) {
+        vmp_imu_step s;
+        for (int c = 0; c < 3; c++) { s.acc[c] = acc_val[c]; s.gyro[c] = gyro_val[c]; }
+        s.dt = step_dt; s.offset = offset;
+        steps.push_back(s);
+    };
+    for (size_t i = 0; i + 1 < imu_cache.size(); i++) {
+        const IMUData& head = imu_cache[i];
+        const IMUData& tail = imu_cache[i + 1];
+        if (tail.timestamp < last_cloud_end_time) continue;
+        gyro_val = scale(add(head.gyro, tail.gyro), 0.5);
+        acc_val = scale(add(head.acc, tail.acc), 0.5);
+        acc_val = divs(scale(acc_val, 9.81), gravity_norm);
+        if (head.timestamp < last_cloud_end_time) dt = tail.timestamp - last_cloud_end_time;
+        else dt = tail.timestamp - head.timestamp;
+        push(dt, tail.timestamp - cloud_time_begin);
+    }
+    push(cloud_time_end - imu_time_end, VMP_NO_POSE);
+    last_imu = package.imus.back();
+    last_cloud_end_time = cloud_time_end;
+}
+
 // the device path takes 2..64 poses (one per IMU sample of the scan)
 bool LIOBuilder::imu_poses_fit(const SyncPackage& package) const { return package.imus.size() + 1 >= 2 && package.imus.size() + 1 <= 64; }
 
@@ -227,6 +260,21 @@ int LIOBuilder::process(SyncPackage& package, vmp_scan_stats* stats) {
     // MAP_INIT (once): everything on the host like the reference.  LIO_MAPPING: IMU propagation on the host, the point
     // loop of undistortCloud on the device in front of the update, one upload + one graph.
     const bool on_device = status == LIO_MAPPING && device_undistort && imu_poses_fit(package);
+    if (on_device && device_predict) {
+        // IMU propagation, motion compensation and update in one graph; the host only assembles the IMU input of the steps
+        collectImuSteps(package, steps_);
+        double last6[6];
+        for (int c = 0; c < 3; c++) { last6[c] = last_acc[c]; last6[3 + c] = last_gyro[c]; }
+        vmp_state xs;
+        static_assert(sizeof(CloudPoint) == 16, "CloudPoint is x y z t");
+        const int r = vmp_scan_raw_predict(map, &xs, kf.P(), reinterpret_cast<float*>(package.pts()), (int)package.size(), steps_.data(), (int)steps_.size(), Q,
+                                           predict_started ? nullptr : last6, stats);
+        if (r) return r;
+        predict_started = true;
+        kf.x() = st_load(reinterpret_cast<const double*>(&xs));
+        return VMP_OK;
+    }
+    if (predict_started) { set_error("LIOBuilder::process: the IMU tail (last_acc / last_gyro) lives on the device once device_predict has run; it cannot be switched off mid-run"); return VMP_ERR_STATE; }
     undistortCloud(package, !on_device);
     const int n = (int)package.size();
     vmp_state xs;
@@ -329,6 +377,11 @@ int vmp_lio_set_device_undistort(vmp_lio l, int on) {
 int vmp_lio_set_cloud_writeback(vmp_lio l, int on) {
     if (!l) return VMP_ERR_INVALID_ARG;
     return vmp_set_raw_writeback(l->b.map, on);
+}
+int vmp_lio_set_device_predict(vmp_lio l, int on) {
+    if (!l) return VMP_ERR_INVALID_ARG;
+    l->b.device_predict = on != 0;
+    return VMP_OK;
 }
 int vmp_lio_prior(vmp_lio l, vmp_state* x, double* P) {
     if (!l) return VMP_ERR_INVALID_ARG;

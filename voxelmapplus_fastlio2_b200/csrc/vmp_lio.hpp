@@ -48,6 +48,7 @@ public:
     bool initializeImu(std::vector<IMUData>& imus);            // lio_builder.cpp:28-63
     void undistortCloud(SyncPackage& package, bool compensate = true);   // lio_builder.cpp:65-153 (compensate = false: IMU propagation only)
     bool imu_poses_fit(const SyncPackage& package) const;
+    void collectImuSteps(SyncPackage& package, std::vector<vmp_imu_step>& steps);   // the IMU loop of undistortCloud without the propagation itself
     int process(SyncPackage& package, vmp_scan_stats* stats);  // lio_builder.cpp:175-248
 
     IESKF kf;
@@ -63,11 +64,14 @@ public:
     double gravity_norm = 0.0;
     double Q[144];
     bool device_undistort = true;                              // motion compensation on the device (vmp_scan_raw) once the map exists
+    bool device_predict = false;                               // IMU propagation on the device too (vmp_scan_raw_predict): state / P stay resident there
+    bool predict_started = false;                              // the device holds last_acc / last_gyro
     vmp_state prior_x{};                                       // what the last process() handed to the device update
     double prior_P[529] = {};
 private:
     std::vector<float> xyz_, ds_;
     std::vector<vmp_pose> poses_;
+    std::vector<vmp_imu_step> steps_;
 };
 
 }  // namespace vmp

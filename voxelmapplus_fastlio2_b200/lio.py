@@ -28,7 +28,8 @@ class _BorrowedHotPath(HotPath):
 
 
 class LIOBuilder:
-    def __init__(self, cfg: VmpConfig, pipelined: bool = False, device_undistort: bool = True, cloud_writeback: bool = True):
+    def __init__(self, cfg: VmpConfig, pipelined: bool = False, device_undistort: bool = True, cloud_writeback: bool = True,
+                 device_predict: bool = False):
         """pipelined: process() returns with the posterior of the scan while its map update still runs on the device
         (vmp_set_pipelined); the map counters in the returned stats then describe the previous scan."""
         self._lib = load_library()
@@ -47,6 +48,9 @@ class LIOBuilder:
         self.map = _BorrowedHotPath(L, cfg, L.vmp_lio_map(self._h))
         if pipelined:
             self.map.set_pipelined(True)
+        if device_predict:              # IESKF::predict on the device as well (vmp_scan_raw_predict): state / P resident there
+            L.vmp_lio_set_device_predict.argtypes = [C.c_void_p, C.c_int]
+            self._check(L.vmp_lio_set_device_predict(self._h, 1))
         if not cloud_writeback:         # process() leaves the caller's cloud as it is; the compensated cloud stays readable (lidar_cloud)
             L.vmp_lio_set_cloud_writeback.argtypes = [C.c_void_p, C.c_int]
             self._check(L.vmp_lio_set_cloud_writeback(self._h, 0))
