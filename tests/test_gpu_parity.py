@@ -123,6 +123,44 @@ def test_many_recreations_in_one_scan(oracle_mod):
             assert so["n_evicted"] == 300 and so["n_created"] == 300
 
 
+def test_merge_serial_redo_is_exact(oracle_mod, monkeypatch):
+    """The exact fallback of the merge phase (vmp_merge.cuh): with VMP_MERGE_MAX_DEPTH=-1 every scan in which a merge succeeds takes the
+    parallel rounds back from the undo log and redoes its merge() calls one at a time in strict event order.  Same bit-exact map."""
+    monkeypatch.setenv("VMP_MERGE_MAX_DEPTH", "-1")
+    o, g = _pair(oracle_mod, max_point_thresh=30, update_size_thresh=5, map_capacity=100000, max_points_per_scan=4096)
+    monkeypatch.delenv("VMP_MERGE_MAX_DEPTH")
+    merges = redone = 0
+    for s, (p, c) in enumerate(wall_workload(2, scans=14)):
+        so, sg = (o.map_update(p, c), g.map_update(p, c)) if s else (o.map_build(p, c), g.map_build(p, c))
+        assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"
+        merges += so["n_merge"]
+        redone += (g.debug_counters()[2] >> 30) & 1
+        assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"serial redo, scan {s}")
+    assert merges > 0 and redone > 0, (merges, redone)
+
+
+def test_merge_active_set_beyond_the_shared_arrays(oracle_mod, monkeypatch):
+    """~7700 coplanar voxels close and start merging within the same two scans: more than a thousand voxels are active in the merge phase at
+    once.  With the shared arrays of the parallel rounds limited to 256 entries (VMP_MERGE_CAP; 2048 in production) such scans run in the
+    exact serial mode from the start, and scans whose set outgrows the arrays on the way are taken back and redone (round 1: E_MERGE_CAP)."""
+    monkeypatch.setenv("VMP_MERGE_CAP", "256")
+    o, g = _pair(oracle_mod, max_point_thresh=20, update_size_thresh=5, map_capacity=100000, max_points_per_scan=65536)
+    monkeypatch.delenv("VMP_MERGE_CAP")
+    rng = np.random.Generator(np.random.Philox(key=77))
+    merges = 0
+    peak_active = 0
+    for s in range(4):
+        n = 60000
+        p = np.stack([rng.uniform(0, 48, n), rng.uniform(0, 40, n), rng.normal(0.12, 0.004, n)], 1).astype(np.float32).astype(np.float64)
+        c = np.tile((np.eye(3) * 1e-4).reshape(1, 9), (n, 1))
+        so, sg = (o.map_update(p, c), g.map_update(p, c)) if s else (o.map_build(p, c), g.map_build(p, c))
+        assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"
+        merges += so["n_merge"]
+        peak_active = max(peak_active, g.debug_counters()[0])
+        assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"large active set, scan {s}")
+    assert merges > 1000 and peak_active > 1000, (merges, peak_active)
+
+
 def test_unkeyable_points_are_counted_skips(oracle_mod):
     """NaN / inf / out-of-range (> 2^20 voxels) world points are skipped and counted, they neither corrupt voxel (0,0,0) nor leave a
     sticky error behind: the device map fed scan + 4 bad points equals the oracle map fed the scan alone, later updates return OK."""
@@ -220,8 +258,10 @@ def test_measure_and_scan_teacher_forced(oracle_mod, estimate_ext):
         assert np.abs(np.array(xg.pos[:]) - np.array(x_post.pos[:])).max() < 1e-9
         assert np.abs(np.array(xg.rot[:]) - np.array(x_post.rot[:])).max() < 1e-10
         # posterior covariance: the device evaluates IESKF::update through the matrix-inversion lemma (vmp_solve.cuh), an algebraically
-        # identical form; both are within ~1e-13 of the 50-digit value (tests/test_posterior_precision.py): tier-2 tolerance
-        assert cov_rel_err(Pg, P_post) <= RTOL_T2, cov_rel_err(Pg, P_post)
+        # identical form; on identical inputs both are within ~1e-13 of the 50-digit value (tests/test_posterior_precision.py).  g_fr keeps
+        # its OWN map (float32 world points of its own posteriors), so its H differs from the oracle's in the 8th digit in these first
+        # scans (P = identity at the start, five iterations): measured <= 1e-8 here, 1e-7 asserted (round 1: rtol 2e-5)
+        assert cov_rel_err(Pg, P_post) <= 1e-7, cov_rel_err(Pg, P_post)
     assert checked_iters > 15
     # SURVEY.md 8(c) safeguard (iii): none of the bit-exact decisions above was a tie of the arithmetic
     assert min(o.gate_margins().values()) > 1e-10, o.gate_margins()

@@ -148,8 +148,8 @@ int check_device_err(vmp_handle_t* h, int err) {
               (err & E_REFIT_OVERFLOW) ? " refit of a voxel holding more than max_point_thresh points;" : "",
               (err & E_QUEUE) ? " internal queue overflow;" : "",
               (err & E_HASH_FULL) ? " hash table full;" : "",
-              (err & E_MERGE_DEPTH) ? " merge cascade deeper than 2 inside one scan;" : "",
-              (err & E_MERGE_CAP) ? " merge simulation: active set overflow;" : "",
+              (err & E_MERGE_DEPTH) ? " merge phase: serial redo needed but the undo log had overflowed;" : "",
+              (err & E_MERGE_CAP) ? " (merge cap);" : "",
               (err & E_LOG_CAP) ? " LRU log full;" : "",
               (err & E_FILL_CAP) ? " refit job / contribution staging exhausted;" : "");
     (void)h;
@@ -388,6 +388,12 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     m.pool = cfg->map_capacity + nmax + 1024;
     m.maxpt = cfg->max_point_thresh; m.upt = cfg->update_size_thresh; m.capacity = cfg->map_capacity;
     m.plane_thresh = cfg->plane_thresh; m.voxel_size = cfg->voxel_size;
+    m.merge_cap = 2048;
+    if (const char* e = getenv("VMP_MERGE_CAP")) m.merge_cap = std::max(1, std::min(2048, atoi(e)));      // test knob
+    m.merge_max_depth = 2;
+    if (const char* e = getenv("VMP_MERGE_MAX_DEPTH")) m.merge_max_depth = atoi(e);     // test knob: -1 forces the exact serial redo after the first merge
+    m.undo_cap = 16384;
+    DALLOC(m.undo_slot, m.undo_cap); DALLOC(m.undo_rec, (size_t)m.undo_cap * 44);
     m.heavy_points = 160;
     if (const char* e = getenv("VMP_FILL_HEAVY")) m.heavy_points = atoi(e);      // tuning knob (0 = warp path only)
     m.th_angle = cfg->merge_thresh_for_angle; m.th_dist = cfg->merge_thresh_for_distance;

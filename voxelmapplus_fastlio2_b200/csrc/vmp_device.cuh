@@ -42,8 +42,8 @@ constexpr int E_LRU_EXHAUSTED = 4;      // eviction would have to take a voxel t
 constexpr int E_REFIT_OVERFLOW = 8;     // refit of a voxel holding more than max_point_thresh points (build overflow + thresh 1)
 constexpr int E_QUEUE = 16;             // internal queue overflow in the serial merge / eviction kernels
 constexpr int E_HASH_FULL = 32;
-constexpr int E_MERGE_DEPTH = 64;       // a merge succeeded at cascade depth > 2 inside one scan (parallel rounds would not be exact)
-constexpr int E_MERGE_CAP = 128;        // more than MERGE_CAP voxels in the active set of the merge simulation
+constexpr int E_MERGE_DEPTH = 64;       // the merge phase had to be redone serially AND its undo log had overflowed (> 16384 modifications in one scan)
+constexpr int E_MERGE_CAP = 128;        // (unused: a large active set runs in the exact serial mode)
 constexpr int E_LOG_CAP = 256;          // LRU log full (compaction was not served in time)
 constexpr int E_FILL_CAP = 512;         // (unused since the refits run out of shared memory)
 
@@ -70,6 +70,7 @@ struct DevCtl {
     int pad0;
     unsigned ticket;                    // arrival counter of k_measure's measurement CTAs (the solver CTA waits on it)
     int fill_next;                      // next touched voxel to be handed to a warp of k_fill
+    int n_undo;                         // entries of the merge undo log of this update
     int n_heavy, heavy_next;            // voxels of this update that go to the CTA path of k_fill, and the next one to be handed out
     int dbg_it;                         // which IEKF iteration's solver phase cycles go to dbg[3..6]
     int dbg[8];                         // debug counters of the last map update: [0] active set after the prefilter, [1] merge events simulated, [2] re-examinations that activated a voxel
@@ -91,7 +92,7 @@ __device__ __forceinline__ void map_counters_reset(DevCtl* ctl) {
     DevStats z = {};
     ctl->st = z;
     ctl->n_touched = 0; ctl->n_new = 0; ctl->n_hot = 0; ctl->n_ghost = 0;
-    ctl->fill_next = 0; ctl->n_heavy = 0; ctl->heavy_next = 0;
+    ctl->fill_next = 0; ctl->n_heavy = 0; ctl->heavy_next = 0; ctl->n_undo = 0;
     for (int q = 0; q < 3; q++) ctl->dbg[q] = 0;          // [3..7] belong to the solver CTA
 }
 
@@ -149,6 +150,9 @@ struct DevMap {
     unsigned hmask;
     // parameters
     int pool, maxpt, upt, capacity;
+    int merge_cap;                      // active-set size up to which the merge phase runs its parallel rounds (<= MERGE_CAP); beyond: serial mode
+    int merge_max_depth;                // cascade depth up to which the parallel merge rounds are exact (2); beyond: serial redo
+    int* undo_slot; double* undo_rec; int undo_cap;      // undo log of the merge phase (vmp_merge.cuh)
     int heavy_points;                   // k_fill: voxels whose refits of a scan loop over at least this many stored points take the CTA path (0: never)
     double plane_thresh, voxel_size, th_angle, th_dist;
     // slots

@@ -217,6 +217,23 @@ __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) 
     }
 }
 
+// ---- undo log of the merge phase: the state of a voxel before its modification (covariance, mean / normal / flags word, group), so
+// that the parallel rounds can be taken back and the scan's merge() calls redone in strict event order (k_merge_rounds)
+constexpr int UNDO_W = 44;              // doubles per entry: cov[36], mean[3], nrm[3], w6 bits, group bits
+__device__ __forceinline__ void undo_log(const DevMap& m, DevCtl* ctl, int slot, double c0, double c1, const double* mean, const double* nrm, long long w6,
+                                         unsigned long long group) {
+    const int lane = threadIdx.x & 31;
+    int e = 0;
+    if (lane == 0) e = atomicAdd(&ctl->n_undo, 1);
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (e >= m.undo_cap) return;                                            // (a redo would then be reported instead of performed)
+    double* r = m.undo_rec + (size_t)e * UNDO_W;
+    r[lane] = c0;
+    if (lane < 4) r[32 + lane] = c1;
+    if (lane < 3) { r[36 + lane] = mean[lane]; r[39 + lane] = nrm[lane]; }
+    if (lane == 0) { r[42] = __longlong_as_double(w6); r[43] = __longlong_as_double((long long)group); m.undo_slot[e] = slot; }
+}
+
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // VoxelGrid::merge() of voxel A at time t, executed by the whole warp.  Returns the number of
@@ -298,6 +315,15 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
             for (int k = 0; k < 3; k++) { nm[k] = shfl_d(v, k); nn[k] = shfl_d(v, 3 + k); }
         }
         const double w0 = tc0 * tc0, w1 = tc1 * tc1, den = (tc0 + tc1) * (tc0 + tc1);
+        {       // undo log: A before its first modification of this event, B before this one
+            double m3[3], n3[3];
+            if (nchg == 0) {
+                for (int k = 0; k < 3; k++) { m3[k] = ra.mean[k]; n3[k] = ra.nrm[k]; }
+                undo_log(m, ctl, A, a0, a1, m3, n3, ra.w6, gA);
+            }
+            for (int k = 0; k < 3; k++) { m3[k] = mb[k]; n3[k] = nb[k]; }
+            undo_log(m, ctl, Bd, b0, b1, m3, n3, __shfl_sync(0xffffffffu, rb.w6, d), __shfl_sync(0xffffffffu, rb.group, d));
+        }
         const double c0 = (b0 * w0 + a0 * w1) / den;
         a0 = c0; cb[lane] = c0;                                    // A's copy stays in registers until the end
         if (lane < 4) { const double c1 = (b1 * w0 + a1 * w1) / den; a1 = c1; cb[32 + lane] = c1; }
@@ -333,7 +359,7 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
 // same result as the reference's strictly sequential order.  A successful merge at depth 3 would
 // leave that guarantee; it is reported (E_MERGE_DEPTH) instead of being silently reordered.
 constexpr int MERGE_R = 8;
-constexpr int MERGE_CAP = 2048;
+constexpr int MERGE_CAP = 2048;          // (DevMap::merge_cap <= MERGE_CAP)
 constexpr int MERGE_MAX_DEPTH = 2;
 
 struct ActiveSet {
@@ -355,26 +381,39 @@ __device__ __forceinline__ void as_set_key(ActiveSet& as, int k, unsigned long l
     as.kz[k] = (short)(dz < -30000 ? -30000 : dz > 30000 ? 30000 : dz);
 }
 
+// What the event code sees of the active set: the shared-memory arrays of the parallel rounds, or (exact serial mode, see
+// k_merge_rounds) the global arrays the prefilter filled.  redo: set when the parallel rounds cannot guarantee the reference's
+// order any more (a merge succeeded deeper in a cascade than max_depth, or the shared arrays are full).
+struct SetView {
+    int* slot;                  // voxel slot | depth << 28
+    int* t;                     // next event (point index), T_INF = retired
+    int* n;                     // entries
+    int cap;
+    ActiveSet* keys;            // voxel coordinates for the readiness test (null in serial mode)
+    int* redo;
+    int max_depth;
+};
+
 // insert voxel Y (first relevant event nt, cascade depth) or pull its pending event earlier; whole warp calls
-__device__ void as_activate(const DevMap& m, DevCtl* ctl, ActiveSet& as, int Y, int nt, int depth) {
+__device__ void as_activate(const DevMap& m, DevCtl* ctl, const SetView& sv, int Y, int nt, int depth) {
     const int lane = threadIdx.x & 31;
-    const int n = as.n;                                   // entries appended concurrently by other warps are never Y:
+    const int n = *sv.n;                                  // entries appended concurrently by other warps are never Y:
     int found = -1;                                       // they lie > MERGE_R - 4 away from this warp's footprint
-    for (int k = lane; k < n; k += 32) if ((as.slot[k] & 0x0FFFFFFF) == Y && as.t[k] != T_INF) found = k;
+    for (int k = lane; k < n; k += 32) if ((sv.slot[k] & 0x0FFFFFFF) == Y && sv.t[k] != T_INF) found = k;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, found, o); found = y > found ? y : found; }
     if (lane == 0) {
         if (found >= 0) {
-            atomicMin(&as.t[found], nt);
-            const int d0 = as.slot[found] >> 28;
-            if (depth > d0) as.slot[found] = Y | (depth << 28);
+            atomicMin(&sv.t[found], nt);
+            const int d0 = sv.slot[found] >> 28;
+            if (depth > d0) sv.slot[found] = Y | (depth << 28);
         } else {
-            const int k = atomicAdd(&as.n, 1);
-            if (k >= MERGE_CAP) { atomicOr(&ctl->err, E_MERGE_CAP); atomicSub(&as.n, 1); }
+            const int k = atomicAdd(sv.n, 1);
+            if (k >= sv.cap) { *sv.redo = 1; atomicSub(sv.n, 1); }          // shared arrays full: the scan is redone in serial mode
             else {
-                as.slot[k] = Y | (depth << 28);
-                as.t[k] = nt;
-                as_set_key(as, k, m.skey[Y]);
+                sv.slot[k] = Y | (depth << 28);
+                sv.t[k] = nt;
+                if (sv.keys) as_set_key(*sv.keys, k, m.skey[Y]);
                 atomicAdd(&ctl->dbg[2], 1);
             }
         }
@@ -394,11 +433,11 @@ struct WarpScratch {
 // The follow-up look-ups are independent chains of dependent global loads (hash probe -> slot -> plane ...), so
 // they run one per lane, eight lanes per voxel: which voxels around the event can merge now, and when is their
 // next merge() call.  The results are applied afterwards in the order of the reference.
-__device__ void process_event(const DevMap& m, DevCtl* ctl, ActiveSet& as, WarpScratch& ws, int j, unsigned scan_id) {
+__device__ void process_event(const DevMap& m, DevCtl* ctl, const SetView& sv, WarpScratch& ws, int j, unsigned scan_id) {
     const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
-    const int A = as.slot[j] & 0x0FFFFFFF, depth = as.slot[j] >> 28, t = as.t[j];
+    const int A = sv.slot[j] & 0x0FFFFFFF, depth = sv.slot[j] >> 28, t = sv.t[j];
     const int nchg = merge_at_warp(m, ctl, A, t, scan_id, ws.chg);
-    if (nchg > 0 && depth > MERGE_MAX_DEPTH && lane == 0) atomicOr(&ctl->err, E_MERGE_DEPTH);
+    if (nchg > 0 && depth > sv.max_depth && lane == 0) *sv.redo = 1;
     const int dn = depth + 1 > 7 ? 7 : depth + 1;
     // task groups of 8 lanes (6 used, one neighbour direction each):
     //   g = 0            the event's own voxel: earliest time one of its pairs can pass again
@@ -487,17 +526,17 @@ __device__ void process_event(const DevMap& m, DevCtl* ctl, ActiveSet& as, WarpS
     for (int q = 0; q < nq; q++) {
         const int kind = ws.kind[q], Yq = ws.tgt[q], nt = ws.res[q];
         if (kind == 0) ntA = nt;
-        else if (nt != T_INF) as_activate(m, ctl, as, Yq, nt, dn);
+        else if (nt != T_INF) as_activate(m, ctl, sv, Yq, nt, dn);
         else if (kind == 1) {
             // the partner has no pair left that can pass (typically: it now shares A's group): retire its
             // pending entry right away instead of spending a round on a no-op.  Its entry is not being
             // processed concurrently: it lies within 1 of A and has a later event.
-            const int n = as.n;
-            for (int k = lane; k < n; k += 32) if ((as.slot[k] & 0x0FFFFFFF) == Yq) as.t[k] = T_INF;
+            const int n = *sv.n;
+            for (int k = lane; k < n; k += 32) if ((sv.slot[k] & 0x0FFFFFFF) == Yq) sv.t[k] = T_INF;
             __syncwarp();
         }
     }
-    if (lane == 0) { as.t[j] = ntA; atomicAdd(&ctl->dbg[1], 1); }
+    if (lane == 0) { sv.t[j] = ntA; atomicAdd(&ctl->dbg[1], 1); }
     __syncwarp();
 }
 
@@ -588,6 +627,9 @@ __device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t
             for (int k = 0; k < 3; k++) { nm[k] = shfl_d(v, k); nn[k] = shfl_d(v, 3 + k); }
         }
         const double w0 = tc0 * tc0, w1 = tc1 * tc1, den = (tc0 + tc1) * (tc0 + tc1);
+        // undo log: A before its first modification of this event (cell[0] still holds its original record), B before this one
+        if (nchg == 0) undo_log(m, ctl, A, a0, a1, cell[0].mean, cell[0].nrm, cell[0].w6, gA);
+        undo_log(m, ctl, Bd, b0, b1, rb.mean, rb.nrm, rb.w6, rb.group);
         const double c0 = (b0 * w0 + a0 * w1) / den;
         a0 = c0; cb[lane] = c0;
         if (lane < 4) { const double c1 = (b1 * w0 + a1 * w1) / den; a1 = c1; cb[32 + lane] = c1; }
@@ -627,9 +669,9 @@ __device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t
 }
 
 // returns false (nothing touched) when the event needs the slow path
-__device__ bool process_event_fast(const DevMap& m, DevCtl* ctl, ActiveSet& as, WarpScratch& ws, CellRec* cell, int j, unsigned scan_id) {
+__device__ bool process_event_fast(const DevMap& m, DevCtl* ctl, const SetView& sv, WarpScratch& ws, CellRec* cell, int j, unsigned scan_id) {
     const int lane = threadIdx.x & 31;
-    const int A = as.slot[j] & 0x0FFFFFFF, depth = as.slot[j] >> 28, t = as.t[j];
+    const int A = sv.slot[j] & 0x0FFFFFFF, depth = sv.slot[j] >> 28, t = sv.t[j];
     // ---- the 25 cells, one per lane: two dependent round trips (hash probe, record)
     bool ghosts = false;
     if (lane < NCELL) {
@@ -661,7 +703,7 @@ __device__ bool process_event_fast(const DevMap& m, DevCtl* ctl, ActiveSet& as, 
     __syncwarp();
     int* chg = ws.chg;                                                   // modified neighbour CELLS (1..6)
     const int nchg = merge_at_cells(m, ctl, cell, t, scan_id, chg);
-    if (nchg > 0 && depth > MERGE_MAX_DEPTH && lane == 0) atomicOr(&ctl->err, E_MERGE_DEPTH);
+    if (nchg > 0 && depth > sv.max_depth && lane == 0) *sv.redo = 1;
     const int dn = depth + 1 > 7 ? 7 : depth + 1;
     // ---- follow-up work on the shared copies.  X ranges over A and the modified neighbours:
     //   wake(X):      earliest time one of X's own pairs can pass (again)             [A: always; a neighbour: if merge() is called for it in this scan]
@@ -745,14 +787,14 @@ __device__ bool process_event_fast(const DevMap& m, DevCtl* ctl, ActiveSet& as, 
     for (int q = 0; q < nq; q++) {
         const int kind = ws.kind[q], Yq = ws.tgt[q], nt = ws.res[q];
         if (kind == 0) ntA = nt;
-        else if (nt != T_INF) as_activate(m, ctl, as, Yq, nt, dn);
+        else if (nt != T_INF) as_activate(m, ctl, sv, Yq, nt, dn);
         else if (kind == 1) {
-            const int n = as.n;
-            for (int k = lane; k < n; k += 32) if ((as.slot[k] & 0x0FFFFFFF) == Yq) as.t[k] = T_INF;
+            const int n = *sv.n;
+            for (int k = lane; k < n; k += 32) if ((sv.slot[k] & 0x0FFFFFFF) == Yq) sv.t[k] = T_INF;
             __syncwarp();
         }
     }
-    if (lane == 0) { as.t[j] = ntA; atomicAdd(&ctl->dbg[1], 1); }
+    if (lane == 0) { sv.t[j] = ntA; atomicAdd(&ctl->dbg[1], 1); }
     __syncwarp();
     return true;
 }
@@ -761,9 +803,19 @@ struct MergeShared {                    // dynamic shared memory of k_merge_roun
     ActiveSet as;
     WarpScratch wsc[16];
     CellRec cells[16][NCELL];
-    int s_cnt, s_nready;
+    int s_cnt, s_nready, s_redo, s_n;
+    unsigned long long s_best[16];
 };
 
+// The merge() calls of one scan.
+//   parallel rounds (the normal case): the active set lives in shared memory; every round executes the events that have no
+//     earlier pending event within MERGE_R, one per warp (footprint argument above: exact as long as no merge succeeds deeper than
+//     MERGE_MAX_DEPTH in a cascade and the set fits).  Every modification is recorded in an undo log.
+//   exact serial mode: if one of those two conditions fails (never observed on the BASELINE workloads; forced by the tests through
+//     VMP_MERGE_MAX_DEPTH=-1) the modifications of the parallel rounds are taken back from the undo log and the scan's events are
+//     executed again one at a time in strict event order - the reference's own order, restricted to the events that can do
+//     something - on the global arrays the prefilter filled (no capacity limit).  Scans whose active set does not fit the shared
+//     arrays start in that mode.
 __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
     extern __shared__ __align__(16) unsigned char merge_smem[];
     MergeShared& S = *reinterpret_cast<MergeShared*>(merge_smem);
@@ -774,62 +826,114 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = ctl->n_hot;                       // (voxel, first relevant event) pairs prepared by k_merge_prefilter
     if (n0 == 0) return;
-    if (n0 > MERGE_CAP) { if (tid == 0) atomicOr(&ctl->err, E_MERGE_CAP); return; }
     const unsigned scan_id = ctl->scan_id;
-    if (tid == 0) {
-        long long x, y, z;
-        unpack_key(m.skey[m.act_slot[0]], x, y, z);
-        as.ox = (int)x; as.oy = (int)y; as.oz = (int)z;
-        as.n = n0; s_nready = 0;
-        ctl->dbg[0] = n0;
-    }
-    __syncthreads();
-    for (int k = tid; k < n0; k += blockDim.x) {
-        const int A = m.act_slot[k];
-        as.slot[k] = A;
-        as.t[k] = m.act_t[k];
-        as_set_key(as, k, m.skey[A]);
-    }
-    __syncthreads();
-    // (everything the events will look at was pulled into the L2 by k_merge_prefilter, 25 cells around every active voxel)
-    for (int round = 0; round < 100000; round++) {
-        const int n = as.n;
-        // readiness (one warp per entry, lanes over the others): no other entry with an earlier event within MERGE_R
-        for (int j = wid; j < n; j += 16) {
-            const int tj = as.t[j];
-            if (tj == T_INF) continue;
-            const int x = as.kx[j], y = as.ky[j], z = as.kz[j];
-            bool conflict = false;
-            for (int i = lane; i < n; i += 32)
-                if (as.t[i] < tj && abs(as.kx[i] - x) + abs(as.ky[i] - y) + abs(as.kz[i] - z) <= MERGE_R) conflict = true;
-            if (!__any_sync(0xffffffffu, conflict) && lane == 0) as.rlist[atomicAdd(&s_nready, 1)] = (short)j;
+    bool serial = n0 > m.merge_cap;
+    if (tid == 0) { S.s_redo = 0; ctl->dbg[0] = n0; }
+    if (!serial) {
+        if (tid == 0) {
+            long long x, y, z;
+            unpack_key(m.skey[m.act_slot[0]], x, y, z);
+            as.ox = (int)x; as.oy = (int)y; as.oz = (int)z;
+            as.n = n0; s_nready = 0;
         }
         __syncthreads();
-        const int nr = s_nready;
-        for (int q = wid; q < nr; q += 16) {                             // one ready event per warp
-            const int j = as.rlist[q];
-            if (!process_event_fast(m, ctl, as, wsc[wid], S.cells[wid], j, scan_id)) process_event(m, ctl, as, wsc[wid], j, scan_id);
+        for (int k = tid; k < n0; k += blockDim.x) {
+            const int A = m.act_slot[k];
+            as.slot[k] = A;
+            as.t[k] = m.act_t[k];
+            as_set_key(as, k, m.skey[A]);
         }
         __syncthreads();
-        // compaction of retired entries (one warp), keeps the rest in place order
+        // (everything the events will look at was pulled into the L2 by k_merge_prefilter, 25 cells around every active voxel)
+        SetView sv;
+        sv.slot = as.slot; sv.t = as.t; sv.n = &as.n; sv.cap = m.merge_cap; sv.keys = &as; sv.redo = &S.s_redo; sv.max_depth = m.merge_max_depth;
+        for (int round = 0; round < 100000; round++) {
+            const int n = as.n;
+            // readiness (one warp per entry, lanes over the others): no other entry with an earlier event within MERGE_R
+            for (int j = wid; j < n; j += 16) {
+                const int tj = as.t[j];
+                if (tj == T_INF) continue;
+                const int x = as.kx[j], y = as.ky[j], z = as.kz[j];
+                bool conflict = false;
+                for (int i = lane; i < n; i += 32)
+                    if (as.t[i] < tj && abs(as.kx[i] - x) + abs(as.ky[i] - y) + abs(as.kz[i] - z) <= MERGE_R) conflict = true;
+                if (!__any_sync(0xffffffffu, conflict) && lane == 0) as.rlist[atomicAdd(&s_nready, 1)] = (short)j;
+            }
+            __syncthreads();
+            const int nr = s_nready;
+            for (int q = wid; q < nr; q += 16) {                             // one ready event per warp
+                const int j = as.rlist[q];
+                if (!process_event_fast(m, ctl, sv, wsc[wid], S.cells[wid], j, scan_id)) process_event(m, ctl, sv, wsc[wid], j, scan_id);
+            }
+            __syncthreads();
+            if (S.s_redo) break;
+            // compaction of retired entries (one warp), keeps the rest in place order
+            if (wid == 0) {
+                const int nn = as.n;
+                int w = 0;
+                for (int base = 0; base < nn; base += 32) {
+                    const int k = base + lane;
+                    const bool live = k < nn && as.t[k] != T_INF;
+                    const int sl = live ? as.slot[k] : 0, tt = live ? as.t[k] : 0;
+                    const short kx = live ? as.kx[k] : 0, ky = live ? as.ky[k] : 0, kz = live ? as.kz[k] : 0;
+                    const unsigned bal = __ballot_sync(0xffffffffu, live);
+                    const int pos = w + __popc(bal & ((1u << lane) - 1));
+                    __syncwarp();
+                    if (live) { as.slot[pos] = sl; as.t[pos] = tt; as.kx[pos] = kx; as.ky[pos] = ky; as.kz[pos] = kz; }
+                    w += __popc(bal);
+                    __syncwarp();
+                }
+                if (lane == 0) { as.n = w; s_cnt = w; s_nready = 0; atomicAdd(&ctl->dbg[2], 65536); }      // (rounds in the upper half of dbg[2])
+            }
+            __syncthreads();
+            if (s_cnt == 0) break;
+        }
+        if (!S.s_redo) return;
+        // ---- take the parallel rounds back (undo log in reverse order: the oldest record of a voxel is restored last)
+        __threadfence();
+        __syncthreads();
+        const int nu = ctl->n_undo;
+        if (nu > m.undo_cap) { if (tid == 0) atomicOr(&ctl->err, E_MERGE_DEPTH); return; }      // log overflowed: cannot be redone exactly, reported
         if (wid == 0) {
-            const int nn = as.n;
-            int w = 0;
-            for (int base = 0; base < nn; base += 32) {
-                const int k = base + lane;
-                const bool live = k < nn && as.t[k] != T_INF;
-                const int sl = live ? as.slot[k] : 0, tt = live ? as.t[k] : 0;
-                const short kx = live ? as.kx[k] : 0, ky = live ? as.ky[k] : 0, kz = live ? as.kz[k] : 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, live);
-                const int pos = w + __popc(bal & ((1u << lane) - 1));
-                __syncwarp();
-                if (live) { as.slot[pos] = sl; as.t[pos] = tt; as.kx[pos] = kx; as.ky[pos] = ky; as.kz[pos] = kz; }
-                w += __popc(bal);
+            for (int e = nu - 1; e >= 0; e--) {
+                const int slot = m.undo_slot[e];
+                const double* r = m.undo_rec + (size_t)e * UNDO_W;
+                m.cov[(size_t)slot * 36 + lane] = r[lane];
+                if (lane < 4) m.cov[(size_t)slot * 36 + 32 + lane] = r[32 + lane];
+                if (lane < 6) m.hot[(size_t)slot * 8 + lane] = r[36 + lane];
+                if (lane == 0) { m.hot[(size_t)slot * 8 + 6] = r[42]; m.sgroup[slot] = (unsigned long long)__double_as_longlong(r[43]); }
                 __syncwarp();
             }
-            if (lane == 0) { as.n = w; s_cnt = w; s_nready = 0; atomicAdd(&ctl->dbg[2], 65536); }      // (rounds in the upper half of dbg[2])
+            if (lane == 0) { ctl->st.n_merge = 0; ctl->dbg[1] = 0; ctl->dbg[2] = 1 << 30; }     // (dbg[2] bit 30: the scan was redone serially)
         }
+        __threadfence();
         __syncthreads();
-        if (s_cnt == 0) break;
+        serial = true;
+    }
+    // ---- exact serial mode on the prefilter's global arrays
+    if (tid == 0) S.s_n = n0;
+    __syncthreads();
+    SetView sv;
+    sv.slot = m.act_slot; sv.t = m.act_t; sv.n = &S.s_n; sv.cap = m.nmax; sv.keys = nullptr; sv.redo = &S.s_redo; sv.max_depth = INT_MAX;
+    for (int step = 0; step < 100000000; step++) {
+        const int n = S.s_n;
+        unsigned long long best = ~0ull;                                     // (time << 32 | entry): the earliest pending event
+        for (int k = tid; k < n; k += blockDim.x) {
+            const int t = m.act_t[k];
+            if (t != T_INF) { const unsigned long long v = ((unsigned long long)(unsigned)t << 32) | (unsigned)k; best = v < best ? v : best; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
+        if (lane == 0) S.s_best[wid] = best;
+        __syncthreads();
+        best = S.s_best[0];
+        for (int w = 1; w < 16; w++) best = S.s_best[w] < best ? S.s_best[w] : best;
+        if (best == ~0ull) break;
+        const int j = (int)(best & 0xFFFFFFFFull);
+        if (wid == 0) {
+            if (!process_event_fast(m, ctl, sv, wsc[0], S.cells[0], j, scan_id)) process_event(m, ctl, sv, wsc[0], j, scan_id);
+        }
+        __threadfence();
+        __syncthreads();
     }
 }
