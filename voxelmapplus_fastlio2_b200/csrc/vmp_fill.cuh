@@ -178,10 +178,11 @@ __device__ __forceinline__ void snap_eig(const double* sn, double* evals, M3& ev
 // up in order).  The leader (warp 0 of the CTA, or the warp itself) owns the sequential parts.
 constexpr int CH_MAX = 32 * 8;          // chunks of one group of 32 snapshots (max_point_thresh <= 256)
 
-struct FillWork {                       // control block of the voxel in shared memory (written by the leader)
+struct alignas(16) FillWork {           // control block of the voxel in shared memory (written by the leader)
+    unsigned long long bar;             // mbarrier of the bulk copies into this region (warp path)
     int consumed, sb, nt0, closes, any_refit, overflow, need_cov, avail, nsnap, nchunks;
     unsigned pmask;
-    int pad;
+    int bulk;                           // the stored points of the voxel are arriving through cp.async.bulk (wait on the mbarrier before reading them)
     short chunk_k[CH_MAX], chunk_base[CH_MAX];
     double ev[32][12];                  // eigenvalues (3) + eigenvectors (9) of the group's snapshots
 };
@@ -189,11 +190,33 @@ struct FillWork {                       // control block of the voxel in shared 
 struct FillCounters { long long ins, full, probe, pvox, refit, rpts; };
 
 // shared memory of one warp of k_fill: [sel] [hist] [FillWork] [pts: 12 x ld doubles] [tile] [snap]
-__host__ __device__ inline int fill_sel_len(int maxpt) { const int ld = (maxpt + 1) & ~1; return ld < 32 ? 32 : ld; }   // a small segment is sorted whole (<= 32)
+__host__ __device__ inline int fill_sel_len(int maxpt) { const int ld = (maxpt + 3) & ~3; return ld < 32 ? 32 : ld; }   // a small segment is sorted whole (<= 32); 16-byte granules
 __host__ __device__ inline size_t fill_warp_bytes(int maxpt) {
     const size_t ld = (size_t)((maxpt + 1) & ~1);
-    return (size_t)fill_sel_len(maxpt) * 4 + SEL_BINS * 4 + sizeof(FillWork) + 12 * ld * 8 + 32 * TILE_LD * 8 + 32 * SNAP_W * 8;
+    return (size_t)fill_sel_len(maxpt) * 4 + SEL_BINS * 4 + sizeof(FillWork) + 12 * ld * 8 + 32 * TILE_LD * 8 + 32 * SNAP_W * 8;     // every term a multiple of 16
 }
+
+// ---- TMA-style bulk copies (cp.async.bulk, sm_90+ / sm_100a) of a voxel's stored points: twelve contiguous rows of the slot's
+// component-major block go global -> shared asynchronously, completion counted in bytes on an mbarrier, while the warp selects and
+// gathers the points of the scan; no registers, no LSU instructions per element (SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 struct FillRegion { int* sel; int* hist; FillWork* W; double* pts; double* tile; double* snap; };
 __device__ __forceinline__ FillRegion fill_region(unsigned char* base, int maxpt) {
     const int ld = (maxpt + 1) & ~1;
@@ -326,7 +349,7 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
 // region0: the shared-memory region the voxel is staged in (the warp's own, or warp 0's for the CTA path)
 template <bool CTA>
 __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int slot, unsigned char* smem0, size_t warp_bytes, int npts, unsigned scan_id,
-                           FillCounters& fc) {
+                           FillCounters& fc, unsigned long long* bar, unsigned& phase) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool leader = !CTA || wib == 0;
     const int nth = CTA ? FILL_WARPS * 32 : 32, tix = CTA ? (int)threadIdx.x : lane;
@@ -375,9 +398,21 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
             const int consumed = closes ? jc + 1 : K;
             next_refit = init0 ? m.upt - nw0 - 1 : jA;
             const bool any_refit = next_refit < consumed;
+            // the stored points of earlier scans (needed when a refit will loop over them): twelve bulk copies, issued now so that
+            // they fly while the points of this scan are gathered.  Rows start 16-byte aligned when max_point_thresh is even.
+            const bool bulk = any_refit && !overflow && nt0 >= 2 && (m.maxpt & 1) == 0;
             if (lane == 0) {
                 W->consumed = consumed; W->sb = overflow ? 0 : nt0; W->nt0 = nt0; W->closes = closes; W->any_refit = any_refit;
                 W->overflow = overflow; W->need_cov = any_refit || !closes; W->avail = overflow ? 0 : nt0 + consumed;
+                W->bulk = bulk;
+                if (bulk) {
+                    const unsigned bytes = (unsigned)((nt0 & ~1) * 8);                // whole 16-byte granules; an odd last point is copied by hand below
+                    const double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
+                    fence_proxy_async();                                           // earlier generic-proxy writes to the staging before the async ones
+                    mbar_expect_tx(bar, 12 * bytes);
+#pragma unroll
+                    for (int k = 0; k < 12; k++) bulk_g2s(R.pts + k * ld, tp + (size_t)k * m.maxpt, bytes, bar);
+                }
             }
         }
     }
@@ -407,7 +442,11 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
                 for (int k = 3; k < 12; k++) R.pts[k * ld + sb + q] = v[k];
             }
         }
-        if (any_refit && !overflow) {
+        if (W->bulk) {                                              // wait for the twelve rows (byte count on the mbarrier)
+            if ((nt0 & 1) && tix < 12) R.pts[tix * ld + nt0 - 1] = m.tp[(size_t)slot * 12 * m.maxpt + (size_t)tix * m.maxpt + nt0 - 1];
+            while (!mbar_try_wait(bar, phase)) {}
+            phase ^= 1u;
+        } else if (any_refit && !overflow) {
             const double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
             for (int q = tix; q < nt0; q += nth) {
                 double v[12];
@@ -530,8 +569,15 @@ __device__ void fill_classify(const DevMap& m, DevCtl* ctl, int vi) {
 __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, DevCtl* ctl) {
     extern __shared__ __align__(16) unsigned char fill_smem[];
     __shared__ int s_vi;
+    __shared__ __align__(8) unsigned long long s_bar;         // mbarrier of the CTA path's bulk copies
     const int lane = threadIdx.x & 31;
     const size_t wbytes = fill_warp_bytes(m.maxpt);
+    unsigned long long* wbar = &fill_region(fill_smem + (size_t)(threadIdx.x >> 5) * wbytes, m.maxpt).W->bar;
+    if (lane == 0) mbar_init(wbar, 1);
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    fence_proxy_async();
+    __syncthreads();
+    unsigned phase_w = 0, phase_c = 0;
     const int V = ctl->n_touched, npts = ctl->n, NH = ctl->n_heavy;
     const unsigned scan_id = ctl->scan_id;
     FillCounters fc = {0, 0, 0, 0, 0, 0};
@@ -542,7 +588,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, D
         const int hi = s_vi;
         __syncthreads();
         if (hi >= NH) break;
-        fill_voxel<true>(m, s, ctl, m.hotlist[hi], fill_smem, wbytes, npts, scan_id, fc);
+        fill_voxel<true>(m, s, ctl, m.hotlist[hi], fill_smem, wbytes, npts, scan_id, fc, &s_bar, phase_c);
     }
     // everything else: a warp per voxel
     while (true) {
@@ -551,7 +597,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, D
         vi = __shfl_sync(0xffffffffu, vi, 0);
         if (vi >= V) break;
         if (m.vox_cls[vi]) continue;
-        fill_voxel<false>(m, s, ctl, m.touched[vi], fill_smem, wbytes, npts, scan_id, fc);
+        fill_voxel<false>(m, s, ctl, m.touched[vi], fill_smem, wbytes, npts, scan_id, fc, wbar, phase_w);
     }
     if (lane == 0) {
         if (fc.ins) atomicAdd((unsigned long long*)&ctl->st.n_ins, (unsigned long long)fc.ins);
