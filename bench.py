@@ -198,6 +198,8 @@ def algo_bytes(kernel, st_sum, n_pts_sum):
         return 32 * st_sum["n_full"] + 8 * st_sum["n_touch"]          # points into full voxels (24 + 8 key); key of a touch
     if kernel == "k_world_insert_count":                              # one kernel since round 2: pv_list production + find-or-create
         return 84 * n_pts_sum + 32 * st_sum["n_full"] + 8 * st_sum["n_touch"]
+    if kernel == "k_fill_heavy":
+        return 0                                                      # (the CTA-path launch of k_fill: its bytes are counted with "k_fill")
     if kernel in ("k_fill", "k_fill_state"):
         # one kernel since round 2: append (72 in + 72 out), n / mean / ppt read + write, and the refits (stored points re-read, 6x6 cov + normal)
         return 144 * st_sum["n_ins"] + 152 * st_sum["n_touch"] + 72 * st_sum["refit_points"] + 432 * st_sum["n_refit"]
@@ -206,7 +208,7 @@ def algo_bytes(kernel, st_sum, n_pts_sum):
     return 0
 
 
-MAP_KERNELS = ("k_world_insert_count", "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict", "k_fill", "k_fill_classify", "k_fill_state", "k_fill_refit",
+MAP_KERNELS = ("k_world_insert_count", "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict", "k_fill", "k_fill_heavy", "k_fill_classify", "k_fill_state", "k_fill_refit",
                "k_fill_acc", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize", "k_map_end")
 
 

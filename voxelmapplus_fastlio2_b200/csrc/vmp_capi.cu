@@ -992,7 +992,7 @@ const char* vmp_kernel_name(int id) {
         "k_scan_in", "k_set_scan", "k_predict", "k_measure", "k_ieskf_solve", "k_world_insert_count",
         "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
         "k_fill", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
-        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_classify", "k_fill_acc", "k_undistort", "k_downsample"};
+        "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_classify", "k_fill_heavy", "k_undistort", "k_downsample"};
     return (id >= 0 && id < VMP_K_COUNT) ? names[id] : "?";
 }
 

@@ -28,7 +28,7 @@ constexpr int FILL_WARPS = 4;           // warps per CTA of k_fill
 constexpr int TILE_LD = 37;             // doubles per point in the contribution tile (odd: conflict-free both ways)
 constexpr int SNAP_W = 12;              // doubles per snapshot: n, nt, mean[3], ppt[6], pad
 constexpr int SEL_BINS = 256;
-constexpr int CAND_CAP = 32 * TILE_LD * 2;      // ints that fit in the tile (selection candidates overlay it)
+constexpr int CAND_CAP = 32 * TILE_LD * 2 - SEL_BINS;      // ints that fit in the tile behind the histogram (selection scratch overlays the tile)
 
 // ascending in-place sort of a[0..c) by one warp (distinct values); a may be shared or global
 __device__ void warp_sort(int* a, int c) {
@@ -176,29 +176,38 @@ __device__ __forceinline__ void snap_eig(const double* sn, double* evals, M3& ev
 // full within one scan runs ~10 refits over 10 .. 100 stored points, ~22 chunks of 32 contributions; the chunks are independent,
 // only their accumulation is ordered, so the warps of the CTA compute a batch of chunks at a time and the leader warp adds them
 // up in order).  The leader (warp 0 of the CTA, or the warp itself) owns the sequential parts.
-constexpr int CH_MAX = 32 * 8;          // chunks of one group of 32 snapshots (max_point_thresh <= 256)
+// Where the stored points come from: the warp path reads them straight from the voxel's block in HBM / L2 (twelve coalesced loads
+// per chunk; its shared-memory footprint is what limits how many voxels an SM works on at a time), the CTA path stages them in
+// shared memory once (cp.async.bulk) for its four warps.
+constexpr int FILL_GROUP = 6;                       // snapshots refitted together (their eigen-solves run one per lane)
+constexpr int CH_MAX = FILL_GROUP * 8;              // chunks of one group (max_point_thresh <= 256)
 
 struct alignas(16) FillWork {           // control block of the voxel in shared memory (written by the leader)
-    unsigned long long bar;             // mbarrier of the bulk copies into this region (warp path)
-    int consumed, sb, nt0, closes, any_refit, overflow, need_cov, avail, nsnap, nchunks;
+    unsigned long long bar;             // (unused slot, keeps the layout 16-byte granular)
+    int consumed, nt0, closes, any_refit, overflow, avail, nsnap, nchunks;
     unsigned pmask;
     int bulk;                           // the stored points of the voxel are arriving through cp.async.bulk (wait on the mbarrier before reading them)
     short chunk_k[CH_MAX], chunk_base[CH_MAX];
-    double ev[32][12];                  // eigenvalues (3) + eigenvectors (9) of the group's snapshots
+    double ev[FILL_GROUP][12];          // eigenvalues (3) + eigenvectors (9) of the group's snapshots
 };
 
 struct FillCounters { long long ins, full, probe, pvox, refit, rpts; };
 
-// shared memory of one warp of k_fill: [sel] [hist] [FillWork] [pts: 12 x ld doubles] [tile] [snap]
+// shared memory of one warp of k_fill: [sel] [FillWork] [cx: xyz of the consumed points, 3 x ld] [tile (+ selection scratch)] [snap];
+// the CTA path appends [pts: 12 x ld, the voxel's stored + consumed points] [tiles of warps 1 ..]
 __host__ __device__ inline int fill_sel_len(int maxpt) { const int ld = (maxpt + 3) & ~3; return ld < 32 ? 32 : ld; }   // a small segment is sorted whole (<= 32); 16-byte granules
 __host__ __device__ inline size_t fill_warp_bytes(int maxpt) {
     const size_t ld = (size_t)((maxpt + 1) & ~1);
-    return (size_t)fill_sel_len(maxpt) * 4 + SEL_BINS * 4 + sizeof(FillWork) + 12 * ld * 8 + 32 * TILE_LD * 8 + 32 * SNAP_W * 8;     // every term a multiple of 16
+    return (size_t)fill_sel_len(maxpt) * 4 + sizeof(FillWork) + 3 * ld * 8 + 32 * TILE_LD * 8 + FILL_GROUP * SNAP_W * 8;     // every term a multiple of 16
+}
+__host__ __device__ inline size_t fill_heavy_bytes(int maxpt) {
+    const size_t ld = (size_t)((maxpt + 1) & ~1);
+    return fill_warp_bytes(maxpt) + 12 * ld * 8 + (size_t)(FILL_WARPS - 1) * 32 * TILE_LD * 8;
 }
 
-// ---- TMA-style bulk copies (cp.async.bulk, sm_90+ / sm_100a) of a voxel's stored points: twelve contiguous rows of the slot's
-// component-major block go global -> shared asynchronously, completion counted in bytes on an mbarrier, while the warp selects and
-// gathers the points of the scan; no registers, no LSU instructions per element (SASS: UBLKCP / SYNCS)
+// ---- TMA-style bulk copies (cp.async.bulk, sm_90+ / sm_100a) of a voxel's stored points (CTA path): twelve contiguous rows of the
+// slot's component-major block go global -> shared asynchronously, completion counted in bytes on an mbarrier, while the leader
+// selects and gathers the points of the scan; no registers, no LSU instructions per element (SASS: UBLKCP / SYNCS)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -217,21 +226,28 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
     return ok != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-struct FillRegion { int* sel; int* hist; FillWork* W; double* pts; double* tile; double* snap; };
+
+struct FillRegion { int* sel; FillWork* W; double* cx; double* tile; double* snap; double* pts; double* tiles_rest; int* hist; int* cand; };
+constexpr int CAND_OFF = SEL_BINS;                  // selection scratch inside the tile: [hist: SEL_BINS ints] [cand]
 __device__ __forceinline__ FillRegion fill_region(unsigned char* base, int maxpt) {
     const int ld = (maxpt + 1) & ~1;
     FillRegion r;
     r.sel = reinterpret_cast<int*>(base);
-    r.hist = r.sel + fill_sel_len(maxpt);
-    r.W = reinterpret_cast<FillWork*>(r.hist + SEL_BINS);
-    r.pts = reinterpret_cast<double*>(r.W + 1);
-    r.tile = r.pts + 12 * ld;
+    r.W = reinterpret_cast<FillWork*>(r.sel + fill_sel_len(maxpt));
+    r.cx = reinterpret_cast<double*>(r.W + 1);
+    r.tile = r.cx + 3 * ld;
     r.snap = r.tile + 32 * TILE_LD;
+    r.pts = r.snap + FILL_GROUP * SNAP_W;           // (CTA path only)
+    r.tiles_rest = r.pts + 12 * ld;                 // (CTA path only)
+    r.hist = reinterpret_cast<int*>(r.tile);
+    r.cand = r.hist + CAND_OFF;
     return r;
 }
 
 template <bool CTA>
 __device__ __forceinline__ void fill_sync() { if (CTA) __syncthreads(); else __syncwarp(); }
+// CTA path: the contribution tile of warp w
+__device__ __forceinline__ double* cta_tile(const FillRegion& R, int w) { return w == 0 ? R.tile : R.tiles_rest + (size_t)(w - 1) * 32 * TILE_LD; }
 
 // updatePlane() for the snapshots snap[0..ns) of the voxel, in order.  Leader registers: acc0 / acc1 (plane->cov, lane e holds
 // entry e, lanes 0..3 also entry 32 + e), the normal / centre of the last refit that found a plane.
@@ -242,12 +258,12 @@ struct RefitAcc {
     long long refit_points;
 };
 
+// P / pstride: the voxel's points, component-major (P[k * pstride + q]: xyz k = 0..2, covariance k = 3..11), stored-point order
 template <bool CTA>
-__device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRegion& R, unsigned char* smem0, size_t warp_bytes, int ns, RefitAcc& ra) {
+__device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRegion& R, const double* P, int pstride, int ns, RefitAcc& ra) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool leader = !CTA || wib == 0;
     const int nwarps = CTA ? FILL_WARPS : 1, wix = CTA ? wib : 0;
-    const int ld = (m.maxpt + 1) & ~1;
     FillWork* W = R.W;
     const double* snap = R.snap;
     if (leader) {
@@ -295,6 +311,11 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
             if (nt > W->avail) nt = W->avail;
             const int q = base + lane;
             if (q < nt) {
+                V3 p;
+                M3 S;
+                p[0] = P[q]; p[1] = P[pstride + q]; p[2] = P[2 * pstride + q];
+#pragma unroll
+                for (int e = 0; e < 9; e++) S.a[e] = P[(3 + e) * pstride + q];
                 const V3 mean = v3(sn[2], sn[3], sn[4]);
                 double ev[3];
                 M3 evc;
@@ -303,11 +324,7 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
 #pragma unroll
                 for (int e = 0; e < 9; e++) evc.a[e] = W->ev[k][3 + e];
                 const V3 nrm = v3(evc(0, 0), evc(1, 0), evc(2, 0));
-                const V3 p = v3(R.pts[q], R.pts[ld + q], R.pts[2 * ld + q]);
-                M3 S;
-#pragma unroll
-                for (int e = 0; e < 9; e++) S.a[e] = R.pts[(3 + e) * ld + q];
-                double* tile = CTA ? reinterpret_cast<double*>(smem0 + (size_t)wib * warp_bytes + (reinterpret_cast<unsigned char*>(R.tile) - smem0)) : R.tile;
+                double* tile = CTA ? cta_tile(R, wib) : R.tile;
                 plane_contrib(p, S, mean, n, ev, evc, nrm, tile + lane * TILE_LD);
             }
         }
@@ -319,7 +336,7 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
                 int nt = (int)snap[k * SNAP_W + 1];
                 if (nt > W->avail) nt = W->avail;
                 const int np = nt - base < 32 ? nt - base : 32;
-                const double* tile = CTA ? reinterpret_cast<const double*>(smem0 + (size_t)w * warp_bytes + (reinterpret_cast<unsigned char*>(R.tile) - smem0)) : R.tile;
+                const double* tile = CTA ? cta_tile(R, w) : R.tile;
                 for (int qq = 0; qq < np; qq++) {
                     ra.acc0 += tile[qq * TILE_LD + lane];
                     if (lane < 4) ra.acc1 += tile[qq * TILE_LD + 32 + lane];
@@ -346,16 +363,17 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
     }
 }
 
-// region0: the shared-memory region the voxel is staged in (the warp's own, or warp 0's for the CTA path)
+// region: the shared-memory region the voxel is staged in (the warp's own, or the CTA's)
 template <bool CTA>
-__device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int slot, unsigned char* smem0, size_t warp_bytes, int npts, unsigned scan_id,
+__device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int slot, unsigned char* region, int npts, unsigned scan_id,
                            FillCounters& fc, unsigned long long* bar, unsigned& phase) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool leader = !CTA || wib == 0;
     const int nth = CTA ? FILL_WARPS * 32 : 32, tix = CTA ? (int)threadIdx.x : lane;
     const int ld = (m.maxpt + 1) & ~1;
-    const FillRegion R = fill_region(smem0 + (CTA ? 0 : (size_t)wib * warp_bytes), m.maxpt);
+    const FillRegion R = fill_region(region, m.maxpt);
     FillWork* W = R.W;
+    double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
     // ---- leader: counters of the voxel, closed-form control flow, selection of the consumed points
     uint32_t flags = 0;
     int n = 0, c = 0, nw0 = 0, n0 = 0, jA = 0, j_init = 0, jc = 0, next_refit = 0, K = 0;
@@ -381,10 +399,9 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
             const int room = m.maxpt - nt0;
             K = room < 1 ? 1 : room;
             if (K > c) K = c;
-            // a voxel that build() left with more than max_point_thresh stored points (Q18) consumes one point and closes; the
-            // staging then only holds that point (a refit of such a voxel is reported: E_REFIT_OVERFLOW)
+            // a voxel that build() left with more than max_point_thresh stored points (Q18) consumes one point and closes; a refit
+            // of such a voxel cannot be served (its points beyond max_point_thresh are not kept) and is reported: E_REFIT_OVERFLOW
             const bool overflow = nt0 + K > m.maxpt;
-            warp_select_sorted(m.seg + off, c, K, npts, R.sel, R.hist, reinterpret_cast<int*>(R.tile));      // K <= max_point_thresh
             // pushPoint's control flow (voxel_map.cpp:42-95) depends on the counters only, never on the points: which steps
             // refit, which step closes the voxel and the final counters have a closed form in (n, n_temp, newly_add_point, K)
             // (checked against the step-by-step state machine on 6.2e6 parameter combinations).
@@ -398,22 +415,22 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
             const int consumed = closes ? jc + 1 : K;
             next_refit = init0 ? m.upt - nw0 - 1 : jA;
             const bool any_refit = next_refit < consumed;
-            // the stored points of earlier scans (needed when a refit will loop over them): twelve bulk copies, issued now so that
-            // they fly while the points of this scan are gathered.  Rows start 16-byte aligned when max_point_thresh is even.
-            const bool bulk = any_refit && !overflow && nt0 >= 2 && (m.maxpt & 1) == 0;
+            // CTA path: the stored points of earlier scans go to shared memory through twelve bulk copies, issued now so that they fly
+            // while the points of this scan are selected and gathered.  Rows start 16-byte aligned when max_point_thresh is even.
+            const bool bulk = CTA && any_refit && !overflow && nt0 >= 2 && (m.maxpt & 1) == 0;
             if (lane == 0) {
-                W->consumed = consumed; W->sb = overflow ? 0 : nt0; W->nt0 = nt0; W->closes = closes; W->any_refit = any_refit;
-                W->overflow = overflow; W->need_cov = any_refit || !closes; W->avail = overflow ? 0 : nt0 + consumed;
+                W->consumed = consumed; W->nt0 = nt0; W->closes = closes; W->any_refit = any_refit;
+                W->overflow = overflow; W->avail = overflow ? 0 : nt0 + consumed;
                 W->bulk = bulk;
                 if (bulk) {
                     const unsigned bytes = (unsigned)((nt0 & ~1) * 8);                // whole 16-byte granules; an odd last point is copied by hand below
-                    const double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
                     fence_proxy_async();                                           // earlier generic-proxy writes to the staging before the async ones
                     mbar_expect_tx(bar, 12 * bytes);
 #pragma unroll
                     for (int k = 0; k < 12; k++) bulk_g2s(R.pts + k * ld, tp + (size_t)k * m.maxpt, bytes, bar);
                 }
             }
+            warp_select_sorted(m.seg + off, c, K, npts, R.sel, R.hist, R.cand);      // K <= max_point_thresh
         }
     }
     fill_sync<CTA>();
@@ -422,42 +439,47 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
     if (consumed < 0) {
         events = c;
     } else {
-        const int sb = W->sb, nt0 = W->nt0;
-        const bool closes = W->closes != 0, any_refit = W->any_refit != 0, overflow = W->overflow != 0, need_cov = W->need_cov != 0;
-        // ---- gather the consumed points once, in parallel: xyz always, covariances when they will be read (refit) or kept
-        // (append); and the stored points of earlier scans when a refit will loop over them
-        // (every copy below issues its twelve loads before the first store: the data is cold, one memory latency per batch)
+        const int nt0 = W->nt0;
+        const bool closes = W->closes != 0, any_refit = W->any_refit != 0, overflow = W->overflow != 0;
+        // ---- gather the consumed points once, in parallel (twelve loads in flight per point): xyz -> shared (the state machine walks them
+        // in order), point + covariance -> behind the voxel's stored points (temp_points.push_back; also when the voxel closes in this
+        // scan - its refits of this scan read them from there) and, CTA path, into the shared staging
         for (int q = tix; q < consumed; q += nth) {
             const size_t i = (size_t)R.sel[q];
             double v[12];
             v[0] = s.pw[3 * i]; v[1] = s.pw[3 * i + 1]; v[2] = s.pw[3 * i + 2];
-            if (need_cov) {
 #pragma unroll
-                for (int k = 0; k < 9; k++) v[3 + k] = s.pcov[9 * i + k];
-            }
+            for (int k = 0; k < 9; k++) v[3 + k] = s.pcov[9 * i + k];
 #pragma unroll
-            for (int k = 0; k < 3; k++) R.pts[k * ld + sb + q] = v[k];
-            if (need_cov) {
+            for (int k = 0; k < 3; k++) R.cx[k * ld + q] = v[k];
+            if (!overflow) {
 #pragma unroll
-                for (int k = 3; k < 12; k++) R.pts[k * ld + sb + q] = v[k];
+                for (int k = 0; k < 12; k++) tp[(size_t)k * m.maxpt + nt0 + q] = v[k];
+                if (CTA) {
+#pragma unroll
+                    for (int k = 0; k < 12; k++) R.pts[k * ld + nt0 + q] = v[k];
+                }
             }
         }
-        if (W->bulk) {                                              // wait for the twelve rows (byte count on the mbarrier)
-            if ((nt0 & 1) && tix < 12) R.pts[tix * ld + nt0 - 1] = m.tp[(size_t)slot * 12 * m.maxpt + (size_t)tix * m.maxpt + nt0 - 1];
-            while (!mbar_try_wait(bar, phase)) {}
-            phase ^= 1u;
-        } else if (any_refit && !overflow) {
-            const double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
-            for (int q = tix; q < nt0; q += nth) {
-                double v[12];
+        if (CTA && any_refit && !overflow) {
+            if (W->bulk) {                                          // wait for the twelve rows (byte count on the mbarrier)
+                if ((nt0 & 1) && tix < 12) R.pts[tix * ld + nt0 - 1] = tp[(size_t)tix * m.maxpt + nt0 - 1];
+                while (!mbar_try_wait(bar, phase)) {}
+                phase ^= 1u;
+            } else {
+                for (int q = tix; q < nt0; q += nth) {
+                    double v[12];
 #pragma unroll
-                for (int k = 0; k < 12; k++) v[k] = tp[(size_t)k * m.maxpt + q];
+                    for (int k = 0; k < 12; k++) v[k] = tp[(size_t)k * m.maxpt + q];
 #pragma unroll
-                for (int k = 0; k < 12; k++) R.pts[k * ld + q] = v[k];
+                    for (int k = 0; k < 12; k++) R.pts[k * ld + q] = v[k];
+                }
             }
         }
         fill_sync<CTA>();
-        // ---- the state machine (leader); the refits of every 32 snapshots by everybody
+        const double* P = CTA ? R.pts : tp;
+        const int pstride = CTA ? ld : m.maxpt;
+        // ---- the state machine (leader); the refits of every FILL_GROUP snapshots by everybody
         RefitAcc ra;
         ra.acc0 = ra.acc1 = 0.0; ra.loaded = 0; ra.any_plane = 0; ra.plane_final = 0; ra.n_refit = 0; ra.refit_points = 0;
         for (int e = 0; e < 3; e++) { ra.nrm[e] = 0.0; ra.ctr[e] = 0.0; }
@@ -465,8 +487,8 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
         while (true) {
             int nsnap = 0;
             if (leader) {
-                for (; j < consumed && nsnap < 32; j++) {                  // point order
-                    const double pm = R.pts[cm * ld + sb + j], pa = R.pts[ia * ld + sb + j], pb = R.pts[ib * ld + sb + j];
+                for (; j < consumed && nsnap < FILL_GROUP; j++) {          // point order
+                    const double pm = R.cx[cm * ld + j], pa = R.cx[ia * ld + j], pb = R.cx[ib * ld + j];
                     mean_l = mean_l + (pm - mean_l) / (double)(n0 + j + 1);
                     ppt_l += pa * pb;
                     if (j == next_refit) {
@@ -483,20 +505,10 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
             fill_sync<CTA>();
             nsnap = W->nsnap;
             if (nsnap == 0) break;                                         // (the leader's loop has reached `consumed`)
-            refit_group<CTA>(m, ctl, slot, R, smem0, warp_bytes, nsnap, ra);
+            refit_group<CTA>(m, ctl, slot, R, P, pstride, nsnap, ra);
             fill_sync<CTA>();
         }
         // ---- write-back
-        if (!closes) {                                                      // temp_points.push_back of the consumed points (coalesced rows)
-            double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
-            for (int q = tix; q < consumed; q += nth) {
-                double v[12];
-#pragma unroll
-                for (int k = 0; k < 12; k++) v[k] = R.pts[k * ld + sb + q];
-#pragma unroll
-                for (int k = 0; k < 12; k++) tp[(size_t)k * m.maxpt + nt0 + q] = v[k];
-            }
-        }
         if (leader) {
             n = n0 + consumed;
             const int nt = closes ? 0 : nt0 + consumed;                    // closing frees temp_points
@@ -566,38 +578,38 @@ __device__ void fill_classify(const DevMap& m, DevCtl* ctl, int vi) {
     }
 }
 
-__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, DevCtl* ctl) {
+// heavy != 0: the CTA path over the voxels classified heavy (shared memory: fill_heavy_bytes); heavy == 0: a warp per voxel over the
+// rest (FILL_WARPS x fill_warp_bytes).  The two launches run side by side on two streams of the scan's graph.
+__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, DevCtl* ctl, int heavy) {
     extern __shared__ __align__(16) unsigned char fill_smem[];
     __shared__ int s_vi;
     __shared__ __align__(8) unsigned long long s_bar;         // mbarrier of the CTA path's bulk copies
     const int lane = threadIdx.x & 31;
     const size_t wbytes = fill_warp_bytes(m.maxpt);
-    unsigned long long* wbar = &fill_region(fill_smem + (size_t)(threadIdx.x >> 5) * wbytes, m.maxpt).W->bar;
-    if (lane == 0) mbar_init(wbar, 1);
     if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     fence_proxy_async();
     __syncthreads();
-    unsigned phase_w = 0, phase_c = 0;
+    unsigned phase_c = 0;
     const int V = ctl->n_touched, npts = ctl->n, NH = ctl->n_heavy;
     const unsigned scan_id = ctl->scan_id;
     FillCounters fc = {0, 0, 0, 0, 0, 0};
-    // heavy voxels first (longest jobs first), one per CTA at a time
-    while (true) {
+    // heavy voxels: one per CTA at a time
+    while (heavy) {
         if (threadIdx.x == 0) s_vi = atomicAdd(&ctl->heavy_next, 1);
         __syncthreads();
         const int hi = s_vi;
         __syncthreads();
         if (hi >= NH) break;
-        fill_voxel<true>(m, s, ctl, m.hotlist[hi], fill_smem, wbytes, npts, scan_id, fc, &s_bar, phase_c);
+        fill_voxel<true>(m, s, ctl, m.hotlist[hi], fill_smem, npts, scan_id, fc, &s_bar, phase_c);
     }
     // everything else: a warp per voxel
-    while (true) {
+    while (!heavy) {
         int vi = 0;
         if (lane == 0) vi = atomicAdd(&ctl->fill_next, 1);
         vi = __shfl_sync(0xffffffffu, vi, 0);
         if (vi >= V) break;
         if (m.vox_cls[vi]) continue;
-        fill_voxel<false>(m, s, ctl, m.touched[vi], fill_smem, wbytes, npts, scan_id, fc, wbar, phase_w);
+        fill_voxel<false>(m, s, ctl, m.touched[vi], fill_smem + (size_t)(threadIdx.x >> 5) * wbytes, npts, scan_id, fc, &s_bar, phase_c);
     }
     if (lane == 0) {
         if (fc.ins) atomicAdd((unsigned long long*)&ctl->st.n_ins, (unsigned long long)fc.ins);

@@ -30,7 +30,7 @@ inline void mark(const Marker* mk, int id) { if (mk && mk->fn) mk->fn(mk->ctx, i
 
 // second stream + events for the two side branches of a map update (eviction next to the segment build, LRU-log append
 // next to the merge simulation); null = everything on one stream
-struct SideStream { cudaStream_t st; cudaEvent_t ev[4]; };
+struct SideStream { cudaStream_t st; cudaEvent_t ev[6]; };
 
 // pcl::VoxelGrid leaf-centroid filter of `cloud` (n_sort points, the same count on the device at *n_ptr) -> d.out / d.m
 // (+ mapped host copies); patch != null: the scan header is redirected to the filtered cloud.  Returns the kernel count.

@@ -639,9 +639,19 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, const 
     if (build) { k_fill_build<<<sm_count * 4, 128, 0, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_FILL); }
     else {
         // resident warps take voxels dynamically; shared memory per CTA = FILL_WARPS x fill_warp_bytes (opt-in size, set at create)
-        const size_t smem = FILL_WARPS * fill_warp_bytes(m.maxpt);
-        const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
-        k_fill<<<sm_count * (per_sm > 4 ? 4 : per_sm), FILL_WARPS * 32, smem, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_FILL);
+        // the heavy voxels (CTA path) and the rest (a warp per voxel) are two launches of k_fill on two streams: different shared-memory
+        // footprints, disjoint voxels
+        const size_t smem = FILL_WARPS * fill_warp_bytes(m.maxpt), smem_h = fill_heavy_bytes(m.maxpt);
+        auto per_sm = [](size_t b) { const int q = (int)((227 * 1024) / (b + 1024)); return q < 1 ? 1 : q > 8 ? 8 : q; };
+        if (fork) {
+            cudaEventRecord(side->ev[4], st); cudaStreamWaitEvent(side->st, side->ev[4], 0);
+            k_fill<<<sm_count * per_sm(smem_h), FILL_WARPS * 32, smem_h, side->st>>>(m, s, ctl, 1); launches++;
+            cudaEventRecord(side->ev[5], side->st);
+        } else {
+            k_fill<<<sm_count * per_sm(smem_h), FILL_WARPS * 32, smem_h, st>>>(m, s, ctl, 1); launches++; mark(mk, VMP_K_FILL_ACC);
+        }
+        k_fill<<<sm_count * per_sm(smem), FILL_WARPS * 32, smem, st>>>(m, s, ctl, 0); launches++; mark(mk, VMP_K_MAP_FILL);
+        if (fork) cudaStreamWaitEvent(st, side->ev[5], 0);
     }
     // the LRU-log append only needs the last-touch times: side branch next to the merge simulation
     if (fork && !build) {
