@@ -185,7 +185,7 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw, bool predict = fal
     }
     // the first iteration stages the scan itself (calcBodyCov per point, prior from the header): no staging kernel in front
     for (int it = 0; it < h->cfg.opti_max_iter; it++) {
-        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1, it == 0 ? h->d_in : nullptr); k++; mark(mk, VMP_K_MEASURE);
+        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1, it == 0 ? h->d_in : nullptr, it > 0); k++; mark(mk, VMP_K_MEASURE);
     }
     // posterior -> host mailbox on the side stream (joined after the map update, which must not overwrite anything it
     // reads: f->x / f->P / the iteration counters are only written by the next scan)
@@ -421,7 +421,7 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     s.nmax = nmax;
     DALLOC(s.pl, (size_t)3 * nmax); DALLOC(s.cl, (size_t)9 * nmax);
     DALLOC(s.rnorm, (size_t)3 * nmax); DALLOC(s.rmean, (size_t)3 * nmax); DALLOC(s.rres, nmax);
-    DALLOC(s.rvalid, nmax); DALLOC(s.rstatus, nmax); DALLOC(s.rkey, nmax);
+    DALLOC(s.rvalid, nmax); DALLOC(s.rstatus, nmax); DALLOC(s.rkey, nmax); DALLOC(s.rslot, nmax);
     DALLOC(s.pw, (size_t)3 * nmax); DALLOC(s.pcov, (size_t)9 * nmax);
     DALLOC(h->d_stage, PTS_OFF + sizeof(float) * 4 * (size_t)nmax + 64);
     h->d_in = (ScanIn*)h->d_stage;

@@ -202,6 +202,7 @@ struct DevScan {                        // persistent residual buffer, SoA over 
     uint8_t* rvalid;                    // [nmax] is_valid
     uint8_t* rstatus;                   // [nmax] bit0 found bit1 plane bit2 valid
     unsigned long long* rkey;           // [nmax] packed key of point_world
+    int* rslot;                         // [nmax] voxel slot found for rkey (valid between the iterations of one scan: the map does not change)
     double* pw;                         // [nmax][3] pv.point  (float32 world widened), AoS: gathered per voxel
     double* pcov;                       // [nmax][9] pv.cov
     float* raw;                         // [nmax][3] staged raw scan

@@ -105,7 +105,7 @@ struct MeasShared {
 // point_lidar / cov_lidar for the later iterations and the map update, and reads the prior from where the header says it is.
 template <bool EXT, bool FIRST>
 __global__ void __launch_bounds__(EXT ? 128 : 256, EXT ? 4 : 2)
-k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* __restrict__ in) {
+k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* __restrict__ in, int reuse_slots) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;                 // upper triangle of H, b, effect count
@@ -194,6 +194,11 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
         if (i < n) {
             V3 pl;
             M3 cl;
+            // later iterations of a scan: the voxel found for this point in the previous iteration (the map does not change between the
+            // iterations, and the state moves by far less than a voxel: the key is almost always the same and the hash probe is skipped)
+            unsigned long long pk_prev = KEY_EMPTY;
+            int slot_prev = -1;
+            if (!FIRST && reuse_slots) { pk_prev = s.rkey[i]; slot_prev = s.rslot[i]; }
             if (FIRST) {
                 const float* pp = pts + (size_t)i * stride;
                 const float fx = pp[0], fy = pp[1], fz = pp[2];
@@ -210,7 +215,8 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
             const V3 pw = add(mul(ms.r_wl, pl), ms.p_wl);
             unsigned long long pk;
             int slot = -1;
-            if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk)) slot = hash_find(m, pk);
+            if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk)) slot = (pk == pk_prev) ? slot_prev : hash_find(m, pk);
+            if (FIRST || slot != slot_prev) s.rslot[i] = slot;
             if (!FIRST) {                                  // fetched up front: one memory latency less on the chain
 #pragma unroll
                 for (int k = 0; k < 9; k++) cl.a[k] = s.cl[(size_t)k * NM + i];
@@ -298,14 +304,15 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     if (threadIdx.x == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
-void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* first) {
+void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* first,
+                    bool reuse_slots) {
     const int g = grid + (solve ? 1 : 0);
     if (first) {
-        if (ext) k_measure<true, true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, first);
-        else k_measure<false, true><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, first);
+        if (ext) k_measure<true, true><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, first, 0);
+        else k_measure<false, true><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, first, 0);
     } else {
-        if (ext) k_measure<true, false><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, nullptr);
-        else k_measure<false, false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, nullptr);
+        if (ext) k_measure<true, false><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, nullptr, reuse_slots ? 1 : 0);
+        else k_measure<false, false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, nullptr, reuse_slots ? 1 : 0);
     }
 }
 // Motion compensation of a raw scan (LIOBuilder::undistortCloud, lio_builder.cpp:127-152) on the device: one thread per

@@ -76,43 +76,12 @@ struct CellRec {
 constexpr int NCELL = 25;
 
 // cell numbering: 0 = A; 1 + d = neighbour d (-x -y -z +x +y +z); 7 + d = two steps along d; 13 + 4 p + 2 [sa > 0] + [sb > 0] =
-// one step along each axis of pair p (xy, xz, yz)
-__device__ __forceinline__ void cell_offset(int c, int& dx, int& dy, int& dz) {
-    dx = dy = dz = 0;
-    if (c == 0) return;
-    if (c < 13) {
-        const int d = (c - 1) % 6, len = c < 7 ? 1 : 2;
-        const int v = d < 3 ? -len : len;
-        const int ax = d % 3;
-        if (ax == 0) dx = v; else if (ax == 1) dy = v; else dz = v;
-        return;
-    }
-    const int q = c - 13, p = q >> 2, sa = (q & 2) ? 1 : -1, sb = (q & 1) ? 1 : -1;
-    if (p == 0) { dx = sa; dy = sb; } else if (p == 1) { dx = sa; dz = sb; } else { dy = sa; dz = sb; }
-}
-__device__ __forceinline__ int cell_index(int dx, int dy, int dz) {
-    const int ax = abs(dx), ay = abs(dy), az = abs(dz);
-    const int dist = ax + ay + az;
-    if (dist == 0) return 0;
-    if (ax == dist || ay == dist || az == dist) {                       // on an axis
-        const int a = ax ? 0 : ay ? 1 : 2;
-        const int v = a == 0 ? dx : a == 1 ? dy : dz;
-        const int d = a + (v > 0 ? 3 : 0);
-        return dist == 1 ? 1 + d : dist == 2 ? 7 + d : -1;
-    }
-    if (dist != 2) return -1;
-    int p, sa, sb;
-    if (az == 0) { p = 0; sa = dx; sb = dy; } else if (ay == 0) { p = 1; sa = dx; sb = dz; } else { p = 2; sa = dy; sb = dz; }
-    return 13 + 4 * p + (sa > 0 ? 2 : 0) + (sb > 0 ? 1 : 0);
-}
+// one step along each axis of pair p (xy, xz, yz).  Offsets and the neighbour-of-a-cell relation as constant tables.
+__constant__ signed char c_cell_off[NCELL][3] = {{0, 0, 0}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-2, 0, 0}, {0, -2, 0}, {0, 0, -2}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1}, {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1}};
+__constant__ signed char c_cell_nb[7][6] = {{1, 2, 3, 4, 5, 6}, {7, 13, 17, 0, 14, 18}, {13, 8, 21, 15, 0, 22}, {17, 21, 9, 19, 23, 0}, {0, 15, 19, 10, 16, 20}, {14, 0, 23, 16, 11, 24}, {18, 22, 0, 20, 24, 12}};
+__device__ __forceinline__ void cell_offset(int c, int& dx, int& dy, int& dz) { dx = c_cell_off[c][0]; dy = c_cell_off[c][1]; dz = c_cell_off[c][2]; }
 // neighbour d of cell c (c <= 6), as a cell
-__device__ __forceinline__ int cell_neighbour(int c, int d) {
-    int dx, dy, dz;
-    cell_offset(c, dx, dy, dz);
-    const int v = d < 3 ? -1 : 1, ax = d % 3;
-    if (ax == 0) dx += v; else if (ax == 1) dy += v; else dz += v;
-    return cell_index(dx, dy, dz);
-}
+__device__ __forceinline__ int cell_neighbour(int c, int d) { return c_cell_nb[c][d]; }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // pull everything merge() will ask about slot s into L2 (the fields of VoxRec, the covariance, the per-scan lists)
