@@ -261,6 +261,31 @@ int vmp_profile_reset(vmp_handle h);
 int vmp_profile_read(vmp_handle h, double* ms /*VMP_K_COUNT*/, int64_t* launches /*VMP_K_COUNT*/);
 const char* vmp_kernel_name(int id);
 
+/* ---- the voxelisation front end of the loop-closure package ----
+ * STDManager::buildVoxels (std_matcher/src/std_manager/descriptor.cpp:70-122) on the device: a stateless pass over one cloud
+ * (N x 4 float32: x y z intensity, pcl::PointXYZI).  One record per voxel (VoxelKey::index with `voxel_size`, descriptor.cpp:40-45), in the
+ * order of the voxels' first points (the reference iterates an unordered_map: its order is unobservable).  sum / ppt are accumulated in
+ * point order like the reference's (bit-exact); voxels with more than voxel_min_point points are VALID-sized and get mean, and, if the
+ * smallest eigenvalue of their covariance is below voxel_plane_thresh, PLANE with lamdas = (min, mid, max) and norms[3 k + r] =
+ * component r of the unit eigenvector k (the reference's VoxelNode::norms.col(k); signs are those of the solver, i.e. undefined).
+ * Not bound to a map handle; needs a B200 like everything else. */
+#define VMP_STD_F_VALID 1u   /* cloud->size() > voxel_min_point (descriptor.cpp:93) */
+#define VMP_STD_F_PLANE 2u   /* VoxelNode::is_plane */
+typedef struct vmp_std_voxel {
+    int64_t  key[3];
+    int32_t  count;
+    uint32_t flags;
+    double   sum[3];
+    double   ppt[9];
+    double   mean[3];
+    double   lamdas[3];
+    double   norms[9];
+} vmp_std_voxel;
+int vmp_std_build_voxels(const float* cloud_xyzi, int n, double voxel_size, int voxel_min_point, double voxel_plane_thresh,
+                         vmp_std_voxel* out, int cap, int* count);
+/* device time (ms, CUDA events around the kernels; copies excluded) of this thread's last vmp_std_build_voxels call */
+double vmp_std_last_device_ms(void);
+
 /* ---- host-side LIOBuilder (C++ class lio::LIOBuilder in vmp_lio.hpp) through C ---- */
 typedef struct vmp_lio_t* vmp_lio;
 typedef struct vmp_imu { double acc[3]; double gyro[3]; double timestamp; } vmp_imu;   /* lio::IMUData, commons.h:12-20 */

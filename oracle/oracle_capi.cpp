@@ -337,4 +337,58 @@ void orc_voxel_key(void* h, const double* p, int64_t* key) {
     key[0] = k.x; key[1] = k.y; key[2] = k.z;
 }
 
+// ---- STDManager::buildVoxels (std_matcher/src/std_manager/descriptor.cpp:70-122), restated ----
+// Pass 1 (:72-89): every point, in cloud order, into temp_voxels[VoxelKey::index(p, voxel_size)] (:42-47): sum += p, ppt += p p^T, count.
+// Pass 2 (:91-121): voxels with count > voxel_min_point get mean = sum / n, cov = ppt / n - mean mean^T, an eigen-decomposition and
+// is_plane = lambda_min < voxel_plane_thresh; plane voxels keep lamdas (min, mid, max) and the eigenvectors as norms' columns.
+// The reference iterates an unordered_map (order unobservable): records come out in first-touch order.  Eigen::EigenSolver (general
+// real Schur) is replaced by the symmetric solver of this oracle; tests/test_std_voxels.py pins eigenvalues and eigenvectors (up to
+// sign) against LAPACK's general solver (numpy.linalg.eig, dgeev), which is the algorithm class EigenSolver implements.
+int orc_std_build_voxels(const float* cloud_xyzi, int n, double voxel_size, int voxel_min_point, double voxel_plane_thresh,
+                         vmp_std_voxel* out, int cap, int* count) {
+    struct Node { V3 sum = V3::zero(); M3 ppt = M3::zero(); int n = 0; int order = 0; };
+    std::unordered_map<VoxelKey, Node, VoxelKey::Hasher> temp_voxels;
+    std::vector<VoxelKey> order;
+    for (int i = 0; i < n; i++) {
+        const float* p = cloud_xyzi + 4 * (size_t)i;
+        const double x = (double)p[0], y = (double)p[1], z = (double)p[2];
+        VoxelKey k{(int64_t)std::floor(x / voxel_size + 0.0), (int64_t)std::floor(y / voxel_size + 0.0), (int64_t)std::floor(z / voxel_size + 0.0)};
+        auto it = temp_voxels.find(k);
+        if (it == temp_voxels.end()) {
+            it = temp_voxels.emplace(k, Node{}).first;
+            it->second.order = (int)order.size();
+            order.push_back(k);
+        }
+        Node& v = it->second;
+        V3 pv = v3(x, y, z);
+        v.sum = add(v.sum, pv);
+        v.ppt = add(v.ppt, outer(pv, pv));
+        v.n++;
+    }
+    if (count) *count = (int)order.size();
+    for (int i = 0; i < (int)order.size() && i < cap; i++) {
+        const Node& v = temp_voxels[order[i]];
+        vmp_std_voxel& o = out[i];
+        std::memset(&o, 0, sizeof(o));
+        o.key[0] = order[i].x; o.key[1] = order[i].y; o.key[2] = order[i].z;
+        o.count = v.n;
+        for (int k = 0; k < 3; k++) o.sum[k] = v.sum.a[k];
+        for (int k = 0; k < 9; k++) o.ppt[k] = v.ppt.a[k];
+        if (!(v.n > voxel_min_point)) continue;
+        o.flags |= VMP_STD_F_VALID;
+        const double nd = (double)v.n;
+        V3 mean = divs(v.sum, nd);
+        M3 cov = sub(divs(v.ppt, nd), outer(mean, mean));
+        double ev[3];
+        M3 evec;
+        eig3_sym(cov, ev, evec);
+        for (int k = 0; k < 3; k++) o.mean[k] = mean.a[k];
+        if (ev[0] < voxel_plane_thresh) {
+            o.flags |= VMP_STD_F_PLANE;
+            for (int k = 0; k < 3; k++) { o.lamdas[k] = ev[k]; for (int q = 0; q < 3; q++) o.norms[3 * k + q] = evec(q, k); }
+        }
+    }
+    return VMP_OK;
+}
+
 }  // extern "C"

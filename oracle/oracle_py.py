@@ -138,6 +138,12 @@ class Oracle(HotPath):
         return sec, st.as_dict()
 
 
+def std_build_voxels(cloud_xyzi, voxel_size=1.0, voxel_min_point=10, voxel_plane_thresh=0.01):
+    """orc_std_build_voxels: STDManager::buildVoxels restated (descriptor.cpp:70-122)."""
+    from voxelmapplus_fastlio2_b200.bindings import std_build_voxels as _call
+    return _call(cloud_xyzi, voxel_size, voxel_min_point, voxel_plane_thresh, lib=lib(), prefix="orc_")
+
+
 # ---- small math, for unit tests against numpy -------------------------------------
 def eig3(A):
     A = np.ascontiguousarray(A, np.float64).reshape(3, 3)

@@ -54,6 +54,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(VmpUpdateStats) == 13 * 8
     assert C.sizeof(VmpPlane) == 3 * 8 + (3 + 9 + 3 + 36 + 3) * 8 + 4 * 4 + 2 * 8
     assert C.sizeof(VmpScanStats) == 4 + 32 + 4 + 104 + 4 + 4
+    from voxelmapplus_fastlio2_b200.ctypes_defs import VmpStdVoxel
+    assert C.sizeof(VmpStdVoxel) == 3 * 8 + 4 + 4 + (3 + 9 + 3 + 3 + 9) * 8      # static_assert of the same number in vmp_std.cu
     lib = bindings.load_library()
     lib.vmp_config_default.argtypes = [C.POINTER(VmpConfig)]
     c = VmpConfig()

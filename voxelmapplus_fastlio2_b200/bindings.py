@@ -17,8 +17,8 @@ import os
 
 import numpy as np
 
-from .ctypes_defs import (IMU_DTYPE, PLANE_DTYPE, VmpConfig, VmpImu, VmpPlane, VmpScanStats, VmpState,
-                          VmpUpdateStats, dptr, fptr)
+from .ctypes_defs import (IMU_DTYPE, PLANE_DTYPE, STD_VOXEL_DTYPE, VmpConfig, VmpImu, VmpPlane, VmpScanStats, VmpState,
+                          VmpStdVoxel, VmpUpdateStats, dptr, fptr)
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libvmp_b200.so")
@@ -299,6 +299,29 @@ class HotPath:
         self._lib.vmp_kernel_name.restype = C.c_char_p
         self._check(self._lib.vmp_profile_read(self._h, dptr(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
         return {self._lib.vmp_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(K_COUNT)}
+
+
+def std_build_voxels(cloud_xyzi, voxel_size: float = 1.0, voxel_min_point: int = 10, voxel_plane_thresh: float = 0.01,
+                     lib: C.CDLL | None = None, prefix: str = "vmp_") -> np.ndarray:
+    """STDManager::buildVoxels (std_matcher/src/std_manager/descriptor.cpp:70-122; defaults: descriptor.h Config) on the device.
+    Returns one STD_VOXEL_DTYPE record per voxel, in the order of the voxels' first points."""
+    lib = lib or load_library()
+    fn = getattr(lib, prefix + "std_build_voxels")
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(VmpStdVoxel), C.c_int, C.POINTER(C.c_int)]
+    cloud = np.ascontiguousarray(cloud_xyzi, np.float32).reshape(-1, 4)
+    n = cloud.shape[0]
+    out = np.zeros(max(n, 1), STD_VOXEL_DTYPE)
+    c = C.c_int(0)
+    rc = fn(cloud.ctypes.data_as(C.POINTER(C.c_float)), n, voxel_size, voxel_min_point, voxel_plane_thresh,
+            out.ctypes.data_as(C.POINTER(VmpStdVoxel)), n, C.byref(c))
+    if rc != 0:
+        msg = ""
+        if prefix == "vmp_":
+            lib.vmp_last_error.restype = C.c_char_p
+            msg = (lib.vmp_last_error() or b"").decode()
+        raise VmpError(f"{prefix}std_build_voxels: rc={rc} {msg}")
+    return out[:c.value].copy()
 
 
 def imu_array(n: int) -> np.ndarray:

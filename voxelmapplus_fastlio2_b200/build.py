@@ -16,7 +16,7 @@ import sys
 _DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_DIR, "csrc")
 LIB = os.path.join(_DIR, "libvmp_b200.so")
-SOURCES = ["vmp_iekf.cu", "vmp_map.cu", "vmp_downsample.cu", "vmp_readback.cu", "vmp_capi.cu", "vmp_lio.cu"]
+SOURCES = ["vmp_iekf.cu", "vmp_map.cu", "vmp_downsample.cu", "vmp_readback.cu", "vmp_std.cu", "vmp_capi.cu", "vmp_lio.cu"]
 HEADERS = ["vmp_math.cuh", "vmp_state.cuh", "vmp_device.cuh", "vmp_kernels.h", "vmp_lio.hpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 

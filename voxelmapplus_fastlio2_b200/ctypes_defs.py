@@ -105,6 +105,22 @@ assert PLANE_DTYPE.itemsize == C.sizeof(VmpPlane), (PLANE_DTYPE.itemsize, C.size
 F_INIT, F_PLANE, F_UPDATE_ENABLE, F_MERGED = 1, 2, 4, 8
 
 
+class VmpStdVoxel(C.Structure):
+    """vmp_std_voxel: one VoxelNode of STDManager::buildVoxels (std_matcher/src/std_manager/descriptor.h:79-95)."""
+    _fields_ = [
+        ("key", C.c_int64 * 3), ("count", C.c_int32), ("flags", C.c_uint32), ("sum", C.c_double * 3), ("ppt", C.c_double * 9),
+        ("mean", C.c_double * 3), ("lamdas", C.c_double * 3), ("norms", C.c_double * 9),
+    ]
+
+
+STD_VOXEL_DTYPE = np.dtype([
+    ("key", np.int64, 3), ("count", np.int32), ("flags", np.uint32), ("sum", np.float64, 3), ("ppt", np.float64, 9),
+    ("mean", np.float64, 3), ("lamdas", np.float64, 3), ("norms", np.float64, 9),
+])
+assert STD_VOXEL_DTYPE.itemsize == C.sizeof(VmpStdVoxel), (STD_VOXEL_DTYPE.itemsize, C.sizeof(VmpStdVoxel))
+STD_F_VALID, STD_F_PLANE = 1, 2
+
+
 class VmpUpdateStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "n_points", "n_ins", "n_touch", "n_created", "n_refit", "refit_points", "n_full",
