@@ -14,8 +14,9 @@ fi
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --workload $WL --steps 8 --warmup 3 --no-cpu --no-c1 --no-loops --ncu-range > gpurun_out/${TAG}_ncu_launch.log 2>&1
 if [ "${SKIP_FULL:-0}" != "1" ]; then
-# two scans of the resident pass with the full metric set
-ncu --set full --clock-control none --import-source on --profile-from-start off -c 40 -o gpurun_out/${TAG}_prof -f \
+# one scan of the resident pass with the full metric set (a report with source counters is ~2 MB per launch; gpurun brings back <= 64 MiB)
+ncu --set full --clock-control none --import-source on --profile-from-start off -c ${FULL_COUNT:-20} -o gpurun_out/${TAG}_prof -f \
     python bench.py --workload $WL --steps 3 --warmup 3 --no-cpu --no-c1 --no-loops --ncu-range > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_full.csv 2>/dev/null
 fi
 ls -la gpurun_out | tail -8

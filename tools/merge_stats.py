@@ -25,9 +25,9 @@ for p in pk:
     if st.iters == 0:
         continue
     d = lio.map.debug_counters()
-    rows.append((p.index, st.iters, st.map.n_touch, st.map.n_full, st.map.n_mergevox, st.map.n_merge, d[0], d[1], d[2] & 0xFFFF, d[2] >> 16, st.gpu_ms))
+    rows.append((p.index, st.iters, st.map.n_touch, st.map.n_full, st.map.n_mergevox, st.map.n_merge, d[0], d[1], d[2] & 0xFFFF, (d[2] >> 16) & 0x3FFF, st.gpu_ms, (d[2] >> 30) & 1))
     if p.index % 3 == 0:
-        print("scan %3d iters %d touch %5d full %6d mergevox %5d merges %3d | active0 %4d events %4d react %3d rounds %3d | gpu %.3f ms" % rows[-1])
+        print("scan %3d iters %d touch %5d full %6d mergevox %5d merges %3d | active0 %4d events %4d react %3d rounds %3d | gpu %.3f ms | serial redo %d" % rows[-1])
 a = np.array(rows, float)
 s = a[a[:, 0] >= 45]
-print("mean (scans >= 45): merges %.1f active0 %.1f events %.1f react %.1f rounds %.1f gpu_ms %.3f" % tuple(s[:, k].mean() for k in (5, 6, 7, 8, 9, 10)))
+print("mean (scans >= 45): merges %.1f active0 %.1f events %.1f react %.1f rounds %.1f gpu_ms %.3f; scans redone serially: %d of %d" % (tuple(s[:, k].mean() for k in (5, 6, 7, 8, 9, 10)) + (int(a[:, 11].sum()), len(a))))

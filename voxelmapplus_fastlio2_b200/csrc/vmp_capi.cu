@@ -390,7 +390,7 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     m.plane_thresh = cfg->plane_thresh; m.voxel_size = cfg->voxel_size;
     m.merge_cap = 2048;
     if (const char* e = getenv("VMP_MERGE_CAP")) m.merge_cap = std::max(1, std::min(2048, atoi(e)));      // test knob
-    m.merge_max_depth = 2;
+    m.merge_max_depth = 7;          // (cascade depths saturate at 7: the depth test of the merge rounds is off unless the test knob sets it)
     if (const char* e = getenv("VMP_MERGE_MAX_DEPTH")) m.merge_max_depth = atoi(e);     // test knob: -1 forces the exact serial redo after the first merge
     m.undo_cap = 16384;
     DALLOC(m.undo_slot, m.undo_cap); DALLOC(m.undo_rec, (size_t)m.undo_cap * 44);

@@ -151,7 +151,7 @@ struct DevMap {
     // parameters
     int pool, maxpt, upt, capacity;
     int merge_cap;                      // active-set size up to which the merge phase runs its parallel rounds (<= MERGE_CAP); beyond: serial mode
-    int merge_max_depth;                // cascade depth up to which the parallel merge rounds are exact (2); beyond: serial redo
+    int merge_max_depth;                // test knob (VMP_MERGE_MAX_DEPTH): a merge deeper than this in a cascade sends the scan to the serial redo
     int* undo_slot; double* undo_rec; int undo_cap;      // undo log of the merge phase (vmp_merge.cuh)
     int heavy_points;                   // k_fill: voxels whose refits of a scan loop over at least this many stored points take the CTA path (0: never)
     double plane_thresh, voxel_size, th_angle, th_dist;

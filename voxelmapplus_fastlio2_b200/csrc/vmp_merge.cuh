@@ -318,37 +318,43 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
 }
 
 // ------------------------------------------------------------------------- event simulation in rounds
-// Active set in shared memory.  An entry is READY when no other entry has an earlier event within
-// Manhattan distance MERGE_R of its voxel.  One event touches its voxel and the six neighbours
-// (writes) and looks at the neighbours' neighbours (reads): footprint radius 2.  A voxel that is
-// activated by an event lies within 2 of it, so a cascade of depth l stays within 2l + 2 of the
-// root; with MERGE_R = 8 every event of depth <= 2 of one root is disjoint from the footprint of
-// any entry that ran concurrently with (or before) that root.  Ready entries therefore commute
-// with everything they do not wait for, and processing them in parallel (one warp each) gives the
-// same result as the reference's strictly sequential order.  A successful merge at depth 3 would
-// leave that guarantee; it is reported (E_MERGE_DEPTH) instead of being silently reordered.
-constexpr int MERGE_R = 8;
+// Active set in shared memory.  One event touches its voxel and the six neighbours (writes) and looks at the
+// neighbours' neighbours (reads): footprint radius 2, so two events commute when their voxels are more than
+// MERGE_R = 4 apart (Manhattan).  An entry is READY when no other PENDING entry has an earlier event within MERGE_R
+// of its voxel; ready entries are executed in parallel, one warp each.  That is the reference's sequential order as
+// long as the set of pending events is complete - but an event can create new ones (a merge changes planes, after
+// which the voxels around them are re-examined: as_activate).  A new event (Y, nt) comes too late if an event E with
+// t_E > nt and |E - Y| <= MERGE_R has already been started (earlier round, or the same round on another warp): the
+// reference would have run (Y, nt) first.  Every started event is therefore kept in a history, every activation is
+// checked against it, and a hit - rare: an activation happens in one scan of three on the BASELINE workloads, and
+// then it has to land next to a later event - takes the whole scan to the exact serial mode below (undo log).
+// (Round 2 first used MERGE_R = 8 with a cascade-depth bound instead: 6.7 rounds per C2 scan; 4.5 with this rule.)
+constexpr int MERGE_R = 4;
 constexpr int MERGE_CAP = 2048;          // (DevMap::merge_cap <= MERGE_CAP)
-constexpr int MERGE_MAX_DEPTH = 2;
+constexpr int MERGE_HIST = 4096;         // started events per scan the parallel rounds can remember (more: serial mode)
 
 struct ActiveSet {
     int slot[MERGE_CAP];        // voxel slot | depth << 28
     int t[MERGE_CAP];           // next event (point index), T_INF = retired
     short kx[MERGE_CAP], ky[MERGE_CAP], kz[MERGE_CAP];   // voxel coordinate relative to the first entry (clamped)
     short rlist[MERGE_CAP];     // entries that are ready in the current round
+    int ht[MERGE_HIST];         // history of started events: time ...
+    short hx[MERGE_HIST], hy[MERGE_HIST], hz[MERGE_HIST];      // ... and voxel
     int n;                      // entries (including retired ones until compaction)
+    int hn;
     int ox, oy, oz;
 };
 
-__device__ __forceinline__ void as_set_key(ActiveSet& as, int k, unsigned long long pk) {
+__device__ __forceinline__ void as_rel_key(const ActiveSet& as, unsigned long long pk, short& rx, short& ry, short& rz) {
     long long x, y, z;
     unpack_key(pk, x, y, z);
     const long long dx = x - as.ox, dy = y - as.oy, dz = z - as.oz;
     // clamping only ever makes two voxels look closer -> more waiting, never less
-    as.kx[k] = (short)(dx < -30000 ? -30000 : dx > 30000 ? 30000 : dx);
-    as.ky[k] = (short)(dy < -30000 ? -30000 : dy > 30000 ? 30000 : dy);
-    as.kz[k] = (short)(dz < -30000 ? -30000 : dz > 30000 ? 30000 : dz);
+    rx = (short)(dx < -30000 ? -30000 : dx > 30000 ? 30000 : dx);
+    ry = (short)(dy < -30000 ? -30000 : dy > 30000 ? 30000 : dy);
+    rz = (short)(dz < -30000 ? -30000 : dz > 30000 ? 30000 : dz);
 }
+__device__ __forceinline__ void as_set_key(ActiveSet& as, int k, unsigned long long pk) { as_rel_key(as, pk, as.kx[k], as.ky[k], as.kz[k]); }
 
 // What the event code sees of the active set: the shared-memory arrays of the parallel rounds, or (exact serial mode, see
 // k_merge_rounds) the global arrays the prefilter filled.  redo: set when the parallel rounds cannot guarantee the reference's
@@ -366,11 +372,22 @@ struct SetView {
 // insert voxel Y (first relevant event nt, cascade depth) or pull its pending event earlier; whole warp calls
 __device__ void as_activate(const DevMap& m, DevCtl* ctl, const SetView& sv, int Y, int nt, int depth) {
     const int lane = threadIdx.x & 31;
-    const int n = *sv.n;                                  // entries appended concurrently by other warps are never Y:
-    int found = -1;                                       // they lie > MERGE_R - 4 away from this warp's footprint
+    const int n = *sv.n;                                  // entries appended concurrently by other warps are never Y: concurrent
+    int found = -1;                                       // events are > MERGE_R = 4 apart and activate voxels within 2 of themselves
     for (int k = lane; k < n; k += 32) if ((sv.slot[k] & 0x0FFFFFFF) == Y && sv.t[k] != T_INF) found = k;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, found, o); found = y > found ? y : found; }
+    if (sv.keys) {                                        // parallel rounds: does (Y, nt) come too late for an event that has already been started?
+        const ActiveSet& as = *sv.keys;
+        short yx = 0, yy = 0, yz = 0;
+        if (lane == 0) as_rel_key(as, m.skey[Y], yx, yy, yz);
+        yx = (short)__shfl_sync(0xffffffffu, (int)yx, 0); yy = (short)__shfl_sync(0xffffffffu, (int)yy, 0); yz = (short)__shfl_sync(0xffffffffu, (int)yz, 0);
+        const int hn = as.hn < MERGE_HIST ? as.hn : MERGE_HIST;
+        bool late = false;
+        for (int k = lane; k < hn; k += 32)
+            if (as.ht[k] > nt && abs(as.hx[k] - yx) + abs(as.hy[k] - yy) + abs(as.hz[k] - yz) <= MERGE_R) late = true;
+        if (late) *sv.redo = 1;
+    }
     if (lane == 0) {
         if (found >= 0) {
             atomicMin(&sv.t[found], nt);
@@ -381,8 +398,9 @@ __device__ void as_activate(const DevMap& m, DevCtl* ctl, const SetView& sv, int
             if (k >= sv.cap) { *sv.redo = 1; atomicSub(sv.n, 1); }          // shared arrays full: the scan is redone in serial mode
             else {
                 sv.slot[k] = Y | (depth << 28);
-                sv.t[k] = nt;
                 if (sv.keys) as_set_key(*sv.keys, k, m.skey[Y]);
+                __threadfence_block();                                       // the entry becomes visible (t != T_INF) after its voxel
+                *(volatile int*)&sv.t[k] = nt;
                 atomicAdd(&ctl->dbg[2], 1);
             }
         }
@@ -778,10 +796,10 @@ struct MergeShared {                    // dynamic shared memory of k_merge_roun
 
 // The merge() calls of one scan.
 //   parallel rounds (the normal case): the active set lives in shared memory; every round executes the events that have no
-//     earlier pending event within MERGE_R, one per warp (footprint argument above: exact as long as no merge succeeds deeper than
-//     MERGE_MAX_DEPTH in a cascade and the set fits).  Every modification is recorded in an undo log.
-//   exact serial mode: if one of those two conditions fails (never observed on the BASELINE workloads; forced by the tests through
-//     VMP_MERGE_MAX_DEPTH=-1) the modifications of the parallel rounds are taken back from the undo log and the scan's events are
+//     earlier pending event within MERGE_R, one per warp (footprint argument above: exact as long as no activation comes too late
+//     and the set and the history fit).  Every modification is recorded in an undo log.
+//   exact serial mode: if one of those conditions fails (forced by the tests through VMP_MERGE_MAX_DEPTH=-1, which declares every
+//     successful merge a failure) the modifications of the parallel rounds are taken back from the undo log and the scan's events are
 //     executed again one at a time in strict event order - the reference's own order, restricted to the events that can do
 //     something - on the global arrays the prefilter filled (no capacity limit).  Scans whose active set does not fit the shared
 //     arrays start in that mode.
@@ -803,7 +821,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
             long long x, y, z;
             unpack_key(m.skey[m.act_slot[0]], x, y, z);
             as.ox = (int)x; as.oy = (int)y; as.oz = (int)z;
-            as.n = n0; s_nready = 0;
+            as.n = n0; as.hn = 0; s_nready = 0;
         }
         __syncthreads();
         for (int k = tid; k < n0; k += blockDim.x) {
@@ -812,6 +830,9 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
             as.t[k] = m.act_t[k];
             as_set_key(as, k, m.skey[A]);
         }
+        // positions outside the live range always read as retired: a warp that scans the set while another one appends (n already
+        // counted, entry not yet written) must not match whatever an earlier entry left there
+        for (int k = n0 + tid; k < MERGE_CAP; k += blockDim.x) as.t[k] = T_INF;
         __syncthreads();
         // (everything the events will look at was pulled into the L2 by k_merge_prefilter, 25 cells around every active voxel)
         SetView sv;
@@ -826,7 +847,12 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
                 bool conflict = false;
                 for (int i = lane; i < n; i += 32)
                     if (as.t[i] < tj && abs(as.kx[i] - x) + abs(as.ky[i] - y) + abs(as.kz[i] - z) <= MERGE_R) conflict = true;
-                if (!__any_sync(0xffffffffu, conflict) && lane == 0) as.rlist[atomicAdd(&s_nready, 1)] = (short)j;
+                if (!__any_sync(0xffffffffu, conflict) && lane == 0) {
+                    as.rlist[atomicAdd(&s_nready, 1)] = (short)j;
+                    const int h = atomicAdd(&as.hn, 1);                       // started: remembered for the activation check
+                    if (h < MERGE_HIST) { as.ht[h] = tj; as.hx[h] = (short)x; as.hy[h] = (short)y; as.hz[h] = (short)z; }
+                    else S.s_redo = 1;
+                }
             }
             __syncthreads();
             const int nr = s_nready;
@@ -852,6 +878,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
                     w += __popc(bal);
                     __syncwarp();
                 }
+                for (int k = w + lane; k < nn; k += 32) as.t[k] = T_INF;     // (the moved entries' old copies)
                 if (lane == 0) { as.n = w; s_cnt = w; s_nready = 0; atomicAdd(&ctl->dbg[2], 65536); }      // (rounds in the upper half of dbg[2])
             }
             __syncthreads();
