@@ -113,6 +113,7 @@ struct vmp_handle_t {
     double* d_up = nullptr;              // staging for vmp_map_update uploads (reuses s.pw / s.pcov)
     std::vector<void*> allocs;
     int grid_pts = 148, grid_meas = 148;
+    bool iekf_loop = false;     // the IEKF iterations of a scan as one resident launch (needs grid_meas + 1 co-resident CTAs)
     int n_last = 0;
     bool map_built = false;
     int64_t launches = 0;
@@ -184,8 +185,12 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw, bool predict = fal
         launch_undistort(st, h->grid_pts, h->d_in, (const DevPose*)(h->d_stage + IN_HDR), (float4*)(h->d_stage + PTS_OFF), h->a_cloud); k++; mark(mk, VMP_K_UNDISTORT);
     }
     // the first iteration stages the scan itself (calcBodyCov per point, prior from the header): no staging kernel in front
-    for (int it = 0; it < h->cfg.opti_max_iter; it++) {
-        launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1, it == 0 ? h->d_in : nullptr, it > 0); k++; mark(mk, VMP_K_MEASURE);
+    if (h->iekf_loop) {     // all iterations in one resident launch (k_iekf_loop)
+        launch_iekf_loop(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, h->d_in, true); k++; mark(mk, VMP_K_MEASURE);
+    } else {
+        for (int it = 0; it < h->cfg.opti_max_iter; it++) {
+            launch_measure(st, ext, h->grid_meas, h->m, h->s, h->f, h->ctl, h->partials, 1, it == 0 ? h->d_in : nullptr, it > 0); k++; mark(mk, VMP_K_MEASURE);
+        }
     }
     // posterior -> host mailbox on the side stream (joined after the map update, which must not overwrite anything it
     // reads: f->x / f->P / the iteration counters are only written by the next scan)
@@ -392,7 +397,7 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     if (const char* e = getenv("VMP_MERGE_CAP")) m.merge_cap = std::max(1, std::min(2048, atoi(e)));      // test knob
     m.merge_max_depth = 7;          // (cascade depths saturate at 7: the depth test of the merge rounds is off unless the test knob sets it)
     if (const char* e = getenv("VMP_MERGE_MAX_DEPTH")) m.merge_max_depth = atoi(e);     // test knob: -1 forces the exact serial redo after the first merge
-    m.undo_cap = 16384;
+    m.undo_cap = 65536;             // seven entries per executed event
     DALLOC(m.undo_slot, m.undo_cap); DALLOC(m.undo_rec, (size_t)m.undo_cap * 44);
     m.heavy_points = 160;
     if (const char* e = getenv("VMP_FILL_HEAVY")) m.heavy_points = atoi(e);      // tuning knob (0 = warp path only)
@@ -466,6 +471,8 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
         // and ran as a second wave of its own (the measurement of 200 000 points took twice as long as it had to)
         h->grid_meas = std::max(1, std::min(h->sm_count * occ - 1, (nmax + tpb - 1) / tpb));
     }
+    h->iekf_loop = cfg->opti_max_iter <= 8 && iekf_loop_fits(cfg->estimate_ext != 0, h->grid_meas, h->sm_count);
+    if (const char* e = getenv("VMP_IEKF_LOOP")) h->iekf_loop = h->iekf_loop && atoi(e) != 0;      // A/B knob: 0 = one launch per iteration
     DALLOC(h->partials, (size_t)h->grid_meas * PARTIAL_STRIDE);
     DALLOC(h->meas_out, 160);
     VMP_CUDA_CHECK(cudaMallocHost((void**)&h->h_stage, PTS_OFF + sizeof(float) * 4 * (size_t)nmax + 64));

@@ -98,14 +98,11 @@ struct MeasShared {
     double stage[NW][32 * SP];
 };
 
-// Two resident CTAs per SM (four of the 128-thread estimate_ext variant): 128 registers, no spills.  Three (80 registers,
-// 196 B of spills) measured the same at 200 k points and slower at 20 k.
-// FIRST: the first iteration of a scan's graph.  It takes the scan straight from the header `in` (round 1 ran a staging kernel,
-// k_set_scan, in front): every thread evaluates calcBodyCov (commons.cpp:18-45, lio_builder.cpp:224-229) for its points, keeps
-// point_lidar / cov_lidar for the later iterations and the map update, and reads the prior from where the header says it is.
+// One measurement pass of one CTA (pb of npb) over the scan: LIOBuilder::sharedUpdateFunc (lio_builder.cpp:250-311) for its points,
+// partial sums of H^T R^-1 H / H^T R^-1 z / effect count into partials[pb].
 template <bool EXT, bool FIRST>
-__global__ void __launch_bounds__(EXT ? 128 : 256, EXT ? 4 : 2)
-k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* __restrict__ in, int reuse_slots) {
+__device__ __forceinline__ void measure_pass(MeasShared<EXT>& sh, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int pb, int npb,
+                                             const ScanIn* __restrict__ in, int reuse_slots) {
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
     constexpr int NV = NH + D + 1;                 // upper triangle of H, b, effect count
@@ -113,19 +110,7 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     constexpr int SP = MeasShared<EXT>::SP;
     constexpr int NW = MeasShared<EXT>::NW;
     constexpr int VPL = (NA + 31) / 32;            // accumulated values per lane
-    // a CTA is either the solver or a measurement CTA: one overlay for both (static shared memory is limited to 48 KB)
-    union Overlay { SolveShared<EXT> sol; MeasShared<EXT> meas; };
-    __shared__ __align__(16) unsigned char sh_raw[sizeof(Overlay)];
-    if (!FIRST && ctl->done) return;
-    // launched with solve = 1 the grid has one more CTA: block 0 runs this iteration's 23-dof solve (IESKF::update body,
-    // vmp_solve.cuh), starting with the part that needs no measurement while the other CTAs measure
-    if (solve && blockIdx.x == 0) {
-        ieskf_solve_cta<EXT, EXT ? 128 : 256>(*reinterpret_cast<SolveShared<EXT>*>(sh_raw), f, ctl, partials, (int)gridDim.x - 1, FIRST ? in : nullptr);
-        return;
-    }
-    MeasShared<EXT>& sh = *reinterpret_cast<MeasShared<EXT>*>(sh_raw);
     MeasState& ms = sh.ms;
-    const int pb = (int)blockIdx.x - solve, npb = (int)gridDim.x - solve;      // measurement CTA index / count
     // the pose products and the two covariance blocks every point needs, one entry per thread (same evaluation order
     // as mul(): s = a0 b0; s += a1 b1; s += a2 b2)
     const double* xsrc = f->x;
@@ -137,24 +122,25 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
     }
     {
         const int t = threadIdx.x;
-        const double* x = xsrc;                    // pos3 rot9 rot_ext9 pos_ext3 ...
+        // pos3 rot9 rot_ext9 pos_ext3 ...  (L2 loads: inside k_iekf_loop the state was written by another SM during this launch)
+        auto x = [&](int q) { return __ldcg(xsrc + q); };
         if (t < 9) {
             const int i = t / 3, j = t % 3;
-            double sacc = x[3 + 3 * i] * x[12 + j];
-            sacc += x[3 + 3 * i + 1] * x[15 + j];
-            sacc += x[3 + 3 * i + 2] * x[18 + j];
+            double sacc = x(3 + 3 * i) * x(12 + j);
+            sacc += x(3 + 3 * i + 1) * x(15 + j);
+            sacc += x(3 + 3 * i + 2) * x(18 + j);
             ms.r_wl.a[t] = sacc;
         } else if (t < 12) {
             const int i = t - 9;
-            double sacc = x[3 + 3 * i] * x[21];
-            sacc += x[3 + 3 * i + 1] * x[22];
-            sacc += x[3 + 3 * i + 2] * x[23];
-            ms.p_wl[i] = sacc + x[i];
-        } else if (t < 21) ms.R.a[t - 12] = x[3 + (t - 12)];
-        else if (t < 30) ms.Rext.a[t - 21] = x[12 + (t - 21)];
-        else if (t < 33) ms.pext[t - 30] = x[21 + (t - 30)];
-        else if (t < 42) { const int e = t - 33; ms.Prr.a[e] = Psrc[(3 + e / 3) * 23 + 3 + e % 3]; }
-        else if (t < 51) { const int e = t - 42; ms.Ppp.a[e] = Psrc[(e / 3) * 23 + e % 3]; }
+            double sacc = x(3 + 3 * i) * x(21);
+            sacc += x(3 + 3 * i + 1) * x(22);
+            sacc += x(3 + 3 * i + 2) * x(23);
+            ms.p_wl[i] = sacc + x(i);
+        } else if (t < 21) ms.R.a[t - 12] = x(3 + (t - 12));
+        else if (t < 30) ms.Rext.a[t - 21] = x(12 + (t - 21));
+        else if (t < 33) ms.pext[t - 30] = x(21 + (t - 30));
+        else if (t < 42) { const int e = t - 33; ms.Prr.a[e] = __ldcg(Psrc + (3 + e / 3) * 23 + 3 + e % 3); }
+        else if (t < 51) { const int e = t - 42; ms.Ppp.a[e] = __ldcg(Psrc + (e / 3) * 23 + e % 3); }
     }
     const int n = FIRST ? in->n : ctl->n;
     const float* pts = FIRST ? in->pts : nullptr;
@@ -297,11 +283,72 @@ k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int 
         for (int w = 1; w < NW; w++) t += sh.red[w][v];
         partials[(size_t)pb * PARTIAL_STRIDE + v] = t;
     }
+}
+
+// Two resident CTAs per SM (four of the 128-thread estimate_ext variant): 128 registers, no spills.  Three (80 registers,
+// 196 B of spills) measured the same at 200 k points and slower at 20 k.
+// FIRST: the first iteration of a scan.  It takes the scan straight from the header `in` (round 1 ran a staging kernel,
+// k_set_scan, in front): every thread evaluates calcBodyCov (commons.cpp:18-45, lio_builder.cpp:224-229) for its points, keeps
+// point_lidar / cov_lidar for the later iterations and the map update, and reads the prior from where the header says it is.
+// One launch = one iteration (the S1 seam vmp_measure with solve = 0, and the scan graph when VMP_IEKF_LOOP=0).
+template <bool EXT, bool FIRST>
+__global__ void __launch_bounds__(EXT ? 128 : 256, EXT ? 4 : 2)
+k_measure(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* __restrict__ in, int reuse_slots) {
+    // a CTA is either the solver or a measurement CTA: one overlay for both (static shared memory is limited to 48 KB)
+    union Overlay { SolveShared<EXT> sol; MeasShared<EXT> meas; };
+    __shared__ __align__(16) unsigned char sh_raw[sizeof(Overlay)];
+    if (!FIRST && ctl->done) return;
+    // launched with solve = 1 the grid has one more CTA: block 0 runs this iteration's 23-dof solve (IESKF::update body,
+    // vmp_solve.cuh), starting with the part that needs no measurement while the other CTAs measure
+    if (solve && blockIdx.x == 0) {
+        ieskf_solve_cta<EXT, EXT ? 128 : 256>(*reinterpret_cast<SolveShared<EXT>*>(sh_raw), f, ctl, partials, (int)gridDim.x - 1, FIRST ? in : nullptr, 0ull);
+        return;
+    }
+    measure_pass<EXT, FIRST>(*reinterpret_cast<MeasShared<EXT>*>(sh_raw), m, s, f, ctl, partials, (int)blockIdx.x - solve, (int)gridDim.x - solve, in, reuse_slots);
     if (!solve) return;
     // release this CTA's partial sums to the solver CTA
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(&ctl->ticket, 1u);
+}
+
+// The whole iteration loop of IESKF::update (ieskf.cpp:125-156) as ONE launch: the measurement CTAs and the solver CTA stay resident,
+// the solver publishes every new state through ctl->iter_pub (release) and the measurement CTAs pick it up (acquire) - no kernel
+// boundary, no launch ramp and no empty launches for the iterations a converged scan does not run.  All CTAs must be co-resident
+// (grid = 2 per SM, checked at create with the occupancy API; vmp_capi.cu falls back to one launch per iteration otherwise).
+template <bool EXT>
+__global__ void __launch_bounds__(EXT ? 128 : 256, EXT ? 4 : 2)
+k_iekf_loop(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, const ScanIn* __restrict__ in, int reuse_slots) {
+    union Overlay { SolveShared<EXT> sol; MeasShared<EXT> meas; };
+    __shared__ __align__(16) unsigned char sh_raw[sizeof(Overlay)];
+    __shared__ int s_stop;
+    const unsigned long long base = in->seq * 8ull;             // iter_pub values of this scan: base + executed iterations
+    if (blockIdx.x == 0) {
+        SolveShared<EXT>& S = *reinterpret_cast<SolveShared<EXT>*>(sh_raw);
+        for (int it = 0; it < 8; it++) {
+            ieskf_solve_cta<EXT, EXT ? 128 : 256>(S, f, ctl, partials, (int)gridDim.x - 1, it == 0 ? in : nullptr, base + (unsigned long long)it + 1ull);
+            if (S.s_last) break;
+            __syncthreads();
+        }
+        return;
+    }
+    MeasShared<EXT>& sh = *reinterpret_cast<MeasShared<EXT>*>(sh_raw);
+    const int pb = (int)blockIdx.x - 1, npb = (int)gridDim.x - 1;
+    for (int it = 0; it < 8; it++) {
+        if (it == 0) measure_pass<EXT, true>(sh, m, s, f, ctl, partials, pb, npb, in, 0);
+        else {
+            if (threadIdx.x == 0) {
+                while (ld_acquire_u64(&ctl->iter_pub) < base + (unsigned long long)it) __nanosleep(20);
+                s_stop = *(volatile int*)&ctl->done;
+            }
+            __syncthreads();
+            if (s_stop) break;
+            measure_pass<EXT, false>(sh, m, s, f, ctl, partials, pb, npb, nullptr, reuse_slots);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(&ctl->ticket, 1u);
+    }
 }
 
 void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve, const ScanIn* first,
@@ -314,6 +361,18 @@ void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const 
         if (ext) k_measure<true, false><<<g, 128, 0, st>>>(m, s, f, ctl, partials, solve, nullptr, reuse_slots ? 1 : 0);
         else k_measure<false, false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, nullptr, reuse_slots ? 1 : 0);
     }
+}
+void launch_iekf_loop(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, const ScanIn* in, bool reuse_slots) {
+    if (ext) k_iekf_loop<true><<<grid + 1, 128, 0, st>>>(m, s, f, ctl, partials, in, reuse_slots ? 1 : 0);
+    else k_iekf_loop<false><<<grid + 1, 256, 0, st>>>(m, s, f, ctl, partials, in, reuse_slots ? 1 : 0);
+}
+// can grid + 1 CTAs of the loop kernel be resident at once?  (they wait for each other: anything less would never finish)
+bool iekf_loop_fits(bool ext, int grid, int sm_count) {
+    int per_sm = 0;
+    const cudaError_t e = ext ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_iekf_loop<true>, 128, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_iekf_loop<false>, 256, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return (long long)per_sm * sm_count >= (long long)grid + 1;
 }
 // Motion compensation of a raw scan (LIOBuilder::undistortCloud, lio_builder.cpp:127-152) on the device: one thread per
 // point.  The scan is time-sorted; a point at offset t belongs to the last IMU pose `head` with head.offset < t (points at

@@ -22,9 +22,13 @@
 // to a changed one is re-examined.  LRU recency changes only through insertion (Q17), so the
 // victim of the j-th over-capacity creation is the oldest log entry whose voxel has not been
 // touched earlier in the same scan.
+#include <cooperative_groups.h>
+
 #include "vmp_device.cuh"
 #include "vmp_kernels.h"
 #include "vmp_state.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace vmp {
 
@@ -661,7 +665,16 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, const 
     }
     if (!build) {
         k_merge_prefilter<<<sm_count * 4, 128, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_PREFILTER);
-        k_merge_rounds<<<1, 512, sizeof(MergeShared), st>>>(m, ctl); launches++; mark(mk, VMP_K_MERGE_SERIAL);
+        {   // one thread-block cluster (vmp_merge.cuh)
+            cudaLaunchConfig_t lc{};
+            lc.gridDim = dim3(MERGE_CLUSTER); lc.blockDim = dim3(512); lc.dynamicSmemBytes = sizeof(MergeShared); lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = MERGE_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            cudaLaunchKernelEx(&lc, k_merge_rounds, m, ctl);
+        }
+        launches++; mark(mk, VMP_K_MERGE_SERIAL);
     }
     if (fork && !build) cudaStreamWaitEvent(st, side->ev[3], 0);
     else { k_log_append<<<gpt, 1024, 0, st>>>(m, ctl); launches++; mark(mk, VMP_K_LOG_APPEND); }

@@ -188,13 +188,21 @@ __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) 
 
 // ---- undo log of the merge phase: the state of a voxel before its modification (covariance, mean / normal / flags word, group), so
 // that the parallel rounds can be taken back and the scan's merge() calls redone in strict event order (k_merge_rounds)
+// An event reserves its UNDO_EVENT entries (its own voxel + six neighbours) with ONE atomic at its start - the index comes back while
+// the event is still fetching its neighbourhood; a returning atomic per record was two dependent L2 round trips per merge - and marks
+// the ones it did not use (slot -1).  Events that touch the same voxel run in different rounds, so their entries are in time order.
 constexpr int UNDO_W = 44;              // doubles per entry: cov[36], mean[3], nrm[3], w6 bits, group bits
-__device__ __forceinline__ void undo_log(const DevMap& m, DevCtl* ctl, int slot, double c0, double c1, const double* mean, const double* nrm, long long w6,
+constexpr int UNDO_EVENT = 7;
+__device__ __forceinline__ int undo_reserve(DevCtl* ctl) {                  // lane 0's value counts
+    return (threadIdx.x & 31) == 0 ? atomicAdd(&ctl->n_undo, UNDO_EVENT) : 0;
+}
+__device__ __forceinline__ void undo_close(const DevMap& m, int base, int used) {
+    const int lane = threadIdx.x & 31;
+    if (lane >= used && lane < UNDO_EVENT && base + lane < m.undo_cap) m.undo_slot[base + lane] = -1;
+}
+__device__ __forceinline__ void undo_log(const DevMap& m, int e, int slot, double c0, double c1, const double* mean, const double* nrm, long long w6,
                                          unsigned long long group) {
     const int lane = threadIdx.x & 31;
-    int e = 0;
-    if (lane == 0) e = atomicAdd(&ctl->n_undo, 1);
-    e = __shfl_sync(0xffffffffu, e, 0);
     if (e >= m.undo_cap) return;                                            // (a redo would then be reported instead of performed)
     double* r = m.undo_rec + (size_t)e * UNDO_W;
     r[lane] = c0;
@@ -211,6 +219,7 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
     const int lane = threadIdx.x & 31;
     // A's own record and covariance (issued first: these loads overlap the neighbour look-ups below);
     // lanes hold the 36 covariance entries (lane e: entry e, lanes 0..3 also entry 32+e)
+    const int ubase_l0 = undo_reserve(ctl);
     const unsigned long long keyA = m.skey[A];
     const VoxRec ra = load_rec(m, A);
     double* ca = m.cov + (size_t)A * 36;
@@ -286,12 +295,13 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
         const double w0 = tc0 * tc0, w1 = tc1 * tc1, den = (tc0 + tc1) * (tc0 + tc1);
         {       // undo log: A before its first modification of this event, B before this one
             double m3[3], n3[3];
+            const int ubase = __shfl_sync(0xffffffffu, ubase_l0, 0);
             if (nchg == 0) {
                 for (int k = 0; k < 3; k++) { m3[k] = ra.mean[k]; n3[k] = ra.nrm[k]; }
-                undo_log(m, ctl, A, a0, a1, m3, n3, ra.w6, gA);
+                undo_log(m, ubase, A, a0, a1, m3, n3, ra.w6, gA);
             }
             for (int k = 0; k < 3; k++) { m3[k] = mb[k]; n3[k] = nb[k]; }
-            undo_log(m, ctl, Bd, b0, b1, m3, n3, __shfl_sync(0xffffffffu, rb.w6, d), __shfl_sync(0xffffffffu, rb.group, d));
+            undo_log(m, ubase + 1 + nchg, Bd, b0, b1, m3, n3, __shfl_sync(0xffffffffu, rb.w6, d), __shfl_sync(0xffffffffu, rb.group, d));
         }
         const double c0 = (b0 * w0 + a0 * w1) / den;
         a0 = c0; cb[lane] = c0;                                    // A's copy stays in registers until the end
@@ -313,6 +323,7 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
         if (lane < 3) { m.hot[(size_t)A * 8 + lane] = mA[lane]; m.hot[(size_t)A * 8 + 3 + lane] = nA[lane]; }
         if (lane == 0) m.hot[(size_t)A * 8 + 6] = __longlong_as_double(ra.w6 | (long long)F_MERGED);
     }
+    undo_close(m, __shfl_sync(0xffffffffu, ubase_l0, 0), nchg > 0 ? nchg + 1 : 0);
     __syncwarp();
     return nchg;
 }
@@ -399,7 +410,7 @@ __device__ void as_activate(const DevMap& m, DevCtl* ctl, const SetView& sv, int
             else {
                 sv.slot[k] = Y | (depth << 28);
                 if (sv.keys) as_set_key(*sv.keys, k, m.skey[Y]);
-                __threadfence_block();                                       // the entry becomes visible (t != T_INF) after its voxel
+                __threadfence();                                             // the entry becomes visible (t != T_INF) after its voxel (to the whole cluster)
                 *(volatile int*)&sv.t[k] = nt;
                 atomicAdd(&ctl->dbg[2], 1);
             }
@@ -554,8 +565,9 @@ __device__ __forceinline__ int cell_event_floor(const CellRec& A, unsigned scan_
 
 // merge() of the voxel in cell[0] at time t on the shared copies (same decisions, same arithmetic and the same global writes as
 // merge_at_warp).  changed[0..n): the neighbour CELLS that were modified.
-__device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t, unsigned scan_id, int* changed) {
+__device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t, unsigned scan_id, int* changed, int ubase_l0) {
     const int lane = threadIdx.x & 31;
+    const int ubase = __shfl_sync(0xffffffffu, ubase_l0, 0);                 // (reserved at the start of the event: long since back)
     const int A = cell[0].slot;
     double* ca = m.cov + (size_t)A * 36;
     double a0 = ca[lane], a1 = lane < 4 ? ca[32 + lane] : 0.0;
@@ -615,8 +627,8 @@ __device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t
         }
         const double w0 = tc0 * tc0, w1 = tc1 * tc1, den = (tc0 + tc1) * (tc0 + tc1);
         // undo log: A before its first modification of this event (cell[0] still holds its original record), B before this one
-        if (nchg == 0) undo_log(m, ctl, A, a0, a1, cell[0].mean, cell[0].nrm, cell[0].w6, gA);
-        undo_log(m, ctl, Bd, b0, b1, rb.mean, rb.nrm, rb.w6, rb.group);
+        if (nchg == 0) undo_log(m, ubase, A, a0, a1, cell[0].mean, cell[0].nrm, cell[0].w6, gA);
+        undo_log(m, ubase + 1 + nchg, Bd, b0, b1, rb.mean, rb.nrm, rb.w6, rb.group);
         const double c0 = (b0 * w0 + a0 * w1) / den;
         a0 = c0; cb[lane] = c0;
         if (lane < 4) { const double c1 = (b1 * w0 + a1 * w1) / den; a1 = c1; cb[32 + lane] = c1; }
@@ -651,6 +663,7 @@ __device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t
             m.hot[(size_t)A * 8 + 6] = __longlong_as_double(cell[0].w6);
         }
     }
+    undo_close(m, ubase, nchg > 0 ? nchg + 1 : 0);
     __syncwarp();
     return nchg;
 }
@@ -661,6 +674,7 @@ __device__ bool process_event_fast(const DevMap& m, DevCtl* ctl, const SetView& 
     const int A = sv.slot[j] & 0x0FFFFFFF, depth = sv.slot[j] >> 28, t = sv.t[j];
     // ---- the 25 cells, one per lane: two dependent round trips (hash probe, record)
     bool ghosts = false;
+    int ubase_l0 = 0;
     if (lane < NCELL) {
         CellRec r;
         r.slot = -1; r.ghost = -1; r.cnt = 0; r.evn = 0; r.pad = 0; r.group = 0; r.w6 = 0; r.born_scan = 0; r.full_scan = SCAN_NEVER;
@@ -687,9 +701,10 @@ __device__ bool process_event_fast(const DevMap& m, DevCtl* ctl, const SetView& 
         cell[lane] = r;
     }
     if (__any_sync(0xffffffffu, ghosts)) return false;
+    ubase_l0 = undo_reserve(ctl);
     __syncwarp();
     int* chg = ws.chg;                                                   // modified neighbour CELLS (1..6)
-    const int nchg = merge_at_cells(m, ctl, cell, t, scan_id, chg);
+    const int nchg = merge_at_cells(m, ctl, cell, t, scan_id, chg, ubase_l0);
     if (nchg > 0 && depth > sv.max_depth && lane == 0) *sv.redo = 1;
     const int dn = depth + 1 > 7 ? 7 : depth + 1;
     // ---- follow-up work on the shared copies.  X ranges over A and the modified neighbours:
@@ -803,88 +818,113 @@ struct MergeShared {                    // dynamic shared memory of k_merge_roun
 //     executed again one at a time in strict event order - the reference's own order, restricted to the events that can do
 //     something - on the global arrays the prefilter filled (no capacity limit).  Scans whose active set does not fit the shared
 //     arrays start in that mode.
+// Launched as ONE thread-block cluster of MERGE_CLUSTER CTAs (16 warps each): the active set, the history and the round counters
+// live in the shared memory of CTA rank 0 and are reached by the other CTAs through distributed shared memory; every CTA has its own
+// per-warp scratch (WarpScratch, the 25-cell copies).  A round's ready events are dealt to the 16 x MERGE_CLUSTER warps of the
+// cluster, so that a round is one event time long instead of ceil(ready / 16) (the first round of a C2 scan has ~40 ready events).
+// Rank 0 alone does the bookkeeping between the rounds (readiness, compaction) and, if it comes to that, the serial redo.
+constexpr int MERGE_CLUSTER = 4;
+
+__device__ __forceinline__ void merge_cluster_sync(cg::cluster_group& cluster) {
+    __threadfence();            // the events write voxels (global memory) that events on the other SMs of the cluster read in later rounds
+    cluster.sync();
+    __threadfence();
+}
+
 __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
     extern __shared__ __align__(16) unsigned char merge_smem[];
     MergeShared& S = *reinterpret_cast<MergeShared*>(merge_smem);
-    ActiveSet& as = S.as;
-    WarpScratch* wsc = S.wsc;
-    int& s_cnt = S.s_cnt;
-    int& s_nready = S.s_nready;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), nrank = (int)cluster.num_blocks();
+    MergeShared& S0 = *cluster.map_shared_rank(&S, 0);
+    ActiveSet& as = S0.as;                           // rank 0's, for everybody
+    WarpScratch* wsc = S.wsc;                        // this CTA's
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = ctl->n_hot;                       // (voxel, first relevant event) pairs prepared by k_merge_prefilter
     if (n0 == 0) return;
     const unsigned scan_id = ctl->scan_id;
     bool serial = n0 > m.merge_cap;
-    if (tid == 0) { S.s_redo = 0; ctl->dbg[0] = n0; }
+    if (serial && rank != 0) return;
+    if (rank == 0 && tid == 0) { S.s_redo = 0; ctl->dbg[0] = n0; }
     if (!serial) {
-        if (tid == 0) {
-            long long x, y, z;
-            unpack_key(m.skey[m.act_slot[0]], x, y, z);
-            as.ox = (int)x; as.oy = (int)y; as.oz = (int)z;
-            as.n = n0; as.hn = 0; s_nready = 0;
-        }
-        __syncthreads();
-        for (int k = tid; k < n0; k += blockDim.x) {
-            const int A = m.act_slot[k];
-            as.slot[k] = A;
-            as.t[k] = m.act_t[k];
-            as_set_key(as, k, m.skey[A]);
-        }
-        // positions outside the live range always read as retired: a warp that scans the set while another one appends (n already
-        // counted, entry not yet written) must not match whatever an earlier entry left there
-        for (int k = n0 + tid; k < MERGE_CAP; k += blockDim.x) as.t[k] = T_INF;
-        __syncthreads();
-        // (everything the events will look at was pulled into the L2 by k_merge_prefilter, 25 cells around every active voxel)
-        SetView sv;
-        sv.slot = as.slot; sv.t = as.t; sv.n = &as.n; sv.cap = m.merge_cap; sv.keys = &as; sv.redo = &S.s_redo; sv.max_depth = m.merge_max_depth;
-        for (int round = 0; round < 100000; round++) {
-            const int n = as.n;
-            // readiness (one warp per entry, lanes over the others): no other entry with an earlier event within MERGE_R
-            for (int j = wid; j < n; j += 16) {
-                const int tj = as.t[j];
-                if (tj == T_INF) continue;
-                const int x = as.kx[j], y = as.ky[j], z = as.kz[j];
-                bool conflict = false;
-                for (int i = lane; i < n; i += 32)
-                    if (as.t[i] < tj && abs(as.kx[i] - x) + abs(as.ky[i] - y) + abs(as.kz[i] - z) <= MERGE_R) conflict = true;
-                if (!__any_sync(0xffffffffu, conflict) && lane == 0) {
-                    as.rlist[atomicAdd(&s_nready, 1)] = (short)j;
-                    const int h = atomicAdd(&as.hn, 1);                       // started: remembered for the activation check
-                    if (h < MERGE_HIST) { as.ht[h] = tj; as.hx[h] = (short)x; as.hy[h] = (short)y; as.hz[h] = (short)z; }
-                    else S.s_redo = 1;
-                }
+        if (rank == 0) {
+            if (tid == 0) {
+                long long x, y, z;
+                unpack_key(m.skey[m.act_slot[0]], x, y, z);
+                S.as.ox = (int)x; S.as.oy = (int)y; S.as.oz = (int)z;
+                S.as.n = n0; S.as.hn = 0; S.s_nready = 0;
             }
             __syncthreads();
-            const int nr = s_nready;
-            for (int q = wid; q < nr; q += 16) {                             // one ready event per warp
+            for (int k = tid; k < n0; k += blockDim.x) {
+                const int A = m.act_slot[k];
+                S.as.slot[k] = A;
+                S.as.t[k] = m.act_t[k];
+                as_set_key(S.as, k, m.skey[A]);
+            }
+            // positions outside the live range always read as retired: a warp that scans the set while another one appends (n already
+            // counted, entry not yet written) must not match whatever an earlier entry left there
+            for (int k = n0 + tid; k < MERGE_CAP; k += blockDim.x) S.as.t[k] = T_INF;
+            __syncthreads();
+        }
+        // (everything the events will look at was pulled into the L2 by k_merge_prefilter, 25 cells around every active voxel)
+        SetView sv;
+        sv.slot = as.slot; sv.t = as.t; sv.n = &as.n; sv.cap = m.merge_cap; sv.keys = &as; sv.redo = &S0.s_redo; sv.max_depth = m.merge_max_depth;
+        // Two cluster barriers per round.  Rank 0 prepares the round (compaction of the previous one, readiness) while the other CTAs
+        // wait at barrier A; everybody executes events up to barrier B.  The shared counters are written by rank 0 between B and the
+        // next A only, and read by the others between A and B only.
+        for (int round = 0; round < 100000; round++) {
+            if (rank == 0) {
+                if (round == 0) { if (tid == 0) S.s_cnt = n0; }
+                else if (wid == 0) {
+                    // compaction of retired entries (one warp), keeps the rest in place order
+                    const int nn = S.as.n;
+                    int w = 0;
+                    for (int base = 0; base < nn; base += 32) {
+                        const int k = base + lane;
+                        const bool live = k < nn && S.as.t[k] != T_INF;
+                        const int sl = live ? S.as.slot[k] : 0, tt = live ? S.as.t[k] : 0;
+                        const short kx = live ? S.as.kx[k] : 0, ky = live ? S.as.ky[k] : 0, kz = live ? S.as.kz[k] : 0;
+                        const unsigned bal = __ballot_sync(0xffffffffu, live);
+                        const int pos = w + __popc(bal & ((1u << lane) - 1));
+                        __syncwarp();
+                        if (live) { S.as.slot[pos] = sl; S.as.t[pos] = tt; S.as.kx[pos] = kx; S.as.ky[pos] = ky; S.as.kz[pos] = kz; }
+                        w += __popc(bal);
+                        __syncwarp();
+                    }
+                    for (int k = w + lane; k < nn; k += 32) S.as.t[k] = T_INF;     // (the moved entries' old copies)
+                    if (lane == 0) { S.as.n = w; S.s_cnt = w; S.s_nready = 0; atomicAdd(&ctl->dbg[2], 65536); }      // (rounds in the upper half of dbg[2])
+                }
+                __syncthreads();
+                const int n = S.as.n;
+                // readiness (one warp per entry, lanes over the others): no other entry with an earlier event within MERGE_R
+                for (int j = wid; j < n; j += 16) {
+                    const int tj = S.as.t[j];
+                    if (tj == T_INF) continue;
+                    const int x = S.as.kx[j], y = S.as.ky[j], z = S.as.kz[j];
+                    bool conflict = false;
+                    for (int i = lane; i < n; i += 32)
+                        if (S.as.t[i] < tj && abs(S.as.kx[i] - x) + abs(S.as.ky[i] - y) + abs(S.as.kz[i] - z) <= MERGE_R) conflict = true;
+                    if (!__any_sync(0xffffffffu, conflict) && lane == 0) {
+                        S.as.rlist[atomicAdd(&S.s_nready, 1)] = (short)j;
+                        const int h = atomicAdd(&S.as.hn, 1);                     // started: remembered for the activation check
+                        if (h < MERGE_HIST) { S.as.ht[h] = tj; S.as.hx[h] = (short)x; S.as.hy[h] = (short)y; S.as.hz[h] = (short)z; }
+                        else S.s_redo = 1;
+                    }
+                }
+            }
+            cluster.sync();                                                   // A (shared memory only)
+            if (S0.s_cnt == 0) break;
+            const int nr = S0.s_nready;
+            for (int q = rank * 16 + wid; q < nr; q += 16 * nrank) {           // one ready event per warp of the cluster
                 const int j = as.rlist[q];
                 if (!process_event_fast(m, ctl, sv, wsc[wid], S.cells[wid], j, scan_id)) process_event(m, ctl, sv, wsc[wid], j, scan_id);
             }
-            __syncthreads();
-            if (S.s_redo) break;
-            // compaction of retired entries (one warp), keeps the rest in place order
-            if (wid == 0) {
-                const int nn = as.n;
-                int w = 0;
-                for (int base = 0; base < nn; base += 32) {
-                    const int k = base + lane;
-                    const bool live = k < nn && as.t[k] != T_INF;
-                    const int sl = live ? as.slot[k] : 0, tt = live ? as.t[k] : 0;
-                    const short kx = live ? as.kx[k] : 0, ky = live ? as.ky[k] : 0, kz = live ? as.kz[k] : 0;
-                    const unsigned bal = __ballot_sync(0xffffffffu, live);
-                    const int pos = w + __popc(bal & ((1u << lane) - 1));
-                    __syncwarp();
-                    if (live) { as.slot[pos] = sl; as.t[pos] = tt; as.kx[pos] = kx; as.ky[pos] = ky; as.kz[pos] = kz; }
-                    w += __popc(bal);
-                    __syncwarp();
-                }
-                for (int k = w + lane; k < nn; k += 32) as.t[k] = T_INF;     // (the moved entries' old copies)
-                if (lane == 0) { as.n = w; s_cnt = w; s_nready = 0; atomicAdd(&ctl->dbg[2], 65536); }      // (rounds in the upper half of dbg[2])
-            }
-            __syncthreads();
-            if (s_cnt == 0) break;
+            merge_cluster_sync(cluster);                                      // B (the events' global writes)
+            if (S0.s_redo) break;
         }
-        if (!S.s_redo) return;
+        const int redo = S0.s_redo;
+        cluster.sync();                              // nobody leaves while another CTA may still be reading rank 0's shared memory
+        if (rank != 0 || !redo) return;
         // ---- take the parallel rounds back (undo log in reverse order: the oldest record of a voxel is restored last)
         __threadfence();
         __syncthreads();
@@ -893,6 +933,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
         if (wid == 0) {
             for (int e = nu - 1; e >= 0; e--) {
                 const int slot = m.undo_slot[e];
+                if (slot < 0) continue;                                     // (reserved by an event, not used)
                 const double* r = m.undo_rec + (size_t)e * UNDO_W;
                 m.cov[(size_t)slot * 36 + lane] = r[lane];
                 if (lane < 4) m.cov[(size_t)slot * 36 + 32 + lane] = r[32 + lane];

@@ -86,6 +86,14 @@ __device__ __forceinline__ long long stamp(const volatile int* flag) {
     if (*flag == 0) t = clock64();
     return t;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -146,10 +154,11 @@ struct SolveShared {
     int s_last, s_zero;
 };
 
+// publish != 0: called from the resident loop kernel; the value is released to ctl->iter_pub once x_ and the loop flags are written.
 // first != null: the first iteration of a scan.  The solver then also opens IESKF::update (ieskf.cpp:127-130: predict_x = x_, iteration
 // counters) and stages the prior named by the scan header into the filter (round 1 did that in a kernel of its own, k_set_scan).
 template <bool EXT, int THREADS>
-__device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks, const ScanIn* first) {
+__device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, const double* partials, int nblocks, const ScanIn* first, unsigned long long publish) {
     static_assert(THREADS >= 128, "the manifold pieces use four warps");
     constexpr int D = EXT ? 12 : 6;
     constexpr int NH = D * (D + 1) / 2;
@@ -337,6 +346,10 @@ __device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, 
     __syncthreads();
     const long long tX = stamp(&s_zero);
     if (tid < 36) f->x[tid] = sx[tid];
+    if (publish) {      // k_iekf_loop: hand the new state (and ctl->done) to the measurement CTAs spinning on iter_pub
+        __syncthreads();
+        if (tid == 0) { __threadfence(); st_release_u64(&ctl->iter_pub, publish); }
+    }
     long long tC = tX;
     if (s_last) {
         // ---- (C) L blocks from the final delta_x and the updated state (ieskf.cpp:151-154), B = L A,
