@@ -337,6 +337,13 @@ __device__ void fill_classify(const DevMap& m, DevCtl* ctl, int vi);      // vmp
 // ------------------------------------------------------------------------- M3b: fill segments
 __global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl, int classify) {
     const int n = ctl->n;
+    // which touched voxels go to the CTA path of k_fill (vmp_fill.cuh): one voxel per thread, dealt round-robin to the CTAs and done
+    // first (a few thousand voxels on the first CTAs alone were the tail of this kernel; the L2 prefetches they issue for k_fill
+    // also get the time of the segment pass to land)
+    if (classify) {
+        const int V = ctl->n_touched;
+        for (int vi = blockIdx.x + gridDim.x * threadIdx.x; vi < V; vi += gridDim.x * blockDim.x) fill_classify(m, ctl, vi);
+    }
     for (int b = blockIdx.x; b * PT_BLOCK < n; b += gridDim.x) {
         const int i = b * PT_BLOCK + threadIdx.x;
         const int lane = threadIdx.x & 31;
@@ -355,11 +362,6 @@ __global__ void __launch_bounds__(1024) k_seg_fill(DevMap m, DevCtl* ctl, int cl
         }
         const int cl = __syncthreads_count(is_last);
         if (threadIdx.x == 0) m.blk_last[b] = cl;
-    }
-    // which touched voxels go to the CTA path of k_fill (vmp_fill.cuh): one voxel per thread
-    if (classify) {
-        const int V = ctl->n_touched;
-        for (int vi = blockIdx.x * blockDim.x + threadIdx.x; vi < V; vi += gridDim.x * blockDim.x) fill_classify(m, ctl, vi);
     }
 }
 

@@ -150,8 +150,10 @@ VMP_HD M3 so3_exp(const V3& w) {
     } else {
         const double th = sqrt(th2);
         const double half = 0.5 * th;
-        im = sin(half) / th;
-        re = cos(half);
+        double sh, ch;
+        sincos(half, &sh, &ch);          // (one argument reduction for both; same values as sin() and cos())
+        im = sh / th;
+        re = ch;
     }
     Quat q; q.w = re; q.x = im * w[0]; q.y = im * w[1]; q.z = im * w[2];
     return quat_to_rot(q);
@@ -181,8 +183,10 @@ VMP_HD M3 so3_left_jacobian(const V3& w) {
     if (th2 < 1e-10 * 1e-10) return add(I, scale(Om, 0.5));
     const double th = sqrt(th2);
     const M3 Om2 = mul(Om, Om);
-    const double c1 = (1.0 - cos(th)) / th2;
-    const double c2 = (th - sin(th)) / (th2 * th);
+    double st, ct;
+    sincos(th, &st, &ct);
+    const double c1 = (1.0 - ct) / th2;
+    const double c2 = (th - st) / (th2 * th);
     return add(add(I, scale(Om, c1)), scale(Om2, c2));
 }
 VMP_HD M3 right_jacobian(const V3& w) { return tr(so3_left_jacobian(w)); }

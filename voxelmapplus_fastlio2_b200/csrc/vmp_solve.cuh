@@ -214,20 +214,22 @@ __device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, 
     __syncthreads();
     const long long tW = stamp(&s_zero);
     // fixed-order reduction of the per-CTA partial sums: RP interleaved block subsets per value; a subset is summed in
-    // block order, eight independent loads in flight at a time (the loop used to wait for one L2 round trip per two blocks)
+    // block order.  All loads of a subset are in flight at once (RED_INFLIGHT x RP blocks per L2 round trip: two trips for a whole B200 grid;
+    // the loop used to take one round trip per eight blocks, five of them on the path of every iteration)
+    constexpr int RED_INFLIGHT = 20;
     for (int q = tid; q < NVP * RP; q += THREADS) {
         const int v = q % NVP, part = q / NVP;
         double t = 0.0;
         if (v < NV) {
-            for (int b = part; b < nblocks; b += 8 * RP) {
-                double xs[8];
+            for (int b = part; b < nblocks; b += RED_INFLIGHT * RP) {
+                double xs[RED_INFLIGHT];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < RED_INFLIGHT; u++) {
                     const int bb = b + u * RP;
                     xs[u] = bb < nblocks ? __ldcg(&partials[(size_t)bb * PARTIAL_STRIDE + v]) : 0.0;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) t += xs[u];
+                for (int u = 0; u < RED_INFLIGHT; u++) t += xs[u];
             }
         }
         sRed[part][v] = t;
