@@ -31,7 +31,7 @@ constexpr int SEL_BINS = 256;
 constexpr int CAND_CAP = 32 * TILE_LD * 2 - SEL_BINS;      // ints that fit in the tile behind the histogram (selection scratch overlays the tile)
 
 // ascending in-place sort of a[0..c) by one warp (distinct values); a may be shared or global
-__device__ void warp_sort(int* a, int c) {
+__device__ __noinline__ void warp_sort(int* a, int c) {
     const int lane = threadIdx.x & 31;
     if (c <= 1) return;
     if (c <= 32) {
@@ -44,20 +44,41 @@ __device__ void warp_sort(int* a, int c) {
         __syncwarp();
         return;
     }
-    int npow = 64;
-    while (npow < c) npow <<= 1;
+    if (c <= 128) {
+        // rank sort: every lane keeps up to four values and counts the smaller ones while the array is read once, broadcast
+        // (c loads and 4 c compares, no exchange stages: the bitonic network below took ~16 k cycles for the hundred indices of
+        // a voxel that fills in one scan - 28 stages of shared-memory exchanges with a barrier each)
+        int v[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int q = lane + 32 * u; v[u] = q < c ? a[q] : INT_MAX; r[u] = 0; }
+        __syncwarp();
+#pragma unroll 2
+        for (int l = 0; l < c; l++) {
+            const int o = a[l];
+#pragma unroll
+            for (int u = 0; u < 4; u++) r[u] += (o < v[u]) ? 1 : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (lane + 32 * u < c) a[r[u]] = v[u];
+        __syncwarp();
+        return;
+    }
+    int npow = 256, lnp = 8;
+    while (npow < c) { npow <<= 1; lnp++; }
     const int half = npow >> 1;
-    for (int k = 2; k <= npow; k <<= 1) {
-        const int hk = k >> 1;
+    for (int lk = 1; lk <= lnp; lk++) {                         // k = 2^lk (shifts: the divisions by k and j were most of a stage)
+        const int k = 1 << lk, hk = k >> 1;
         for (int t = lane; t < half; t += 32) {                 // flip stage: all comparators ascending
-            const int blk = t / hk, o = t % hk;
+            const int blk = t >> (lk - 1), o = t & (hk - 1);
             const int lo = blk * k + o, hi = blk * k + k - 1 - o;
             if (hi < c) { const int x = a[lo], y = a[hi]; if (x > y) { a[lo] = y; a[hi] = x; } }
         }
         __syncwarp();
-        for (int j = k >> 2; j >= 1; j >>= 1) {
+        for (int lj = lk - 2; lj >= 0; lj--) {
+            const int j = 1 << lj;
             for (int t = lane; t < half; t += 32) {
-                const int lo = (t / j) * 2 * j + (t % j), hi = lo + j;
+                const int lo = ((t >> lj) << (lj + 1)) + (t & (j - 1)), hi = lo + j;
                 if (hi < c) { const int x = a[lo], y = a[hi]; if (x > y) { a[lo] = y; a[hi] = x; } }
             }
             __syncwarp();
@@ -83,7 +104,16 @@ __device__ void warp_select_sorted(const int* seg, int c, int K, int n, int* sel
         // bisection below takes log2(n) of them: a near voxel collects thousands of points of a 200 k-point scan)
         for (int q = lane; q < SEL_BINS; q += 32) hist[q] = 0;
         __syncwarp();
-        for (int q = lane; q < c; q += 32) atomicAdd(&hist[seg[q] >> S], 1);
+        // (both passes fetch SEL_U x 32 indices per round trip: one load per iteration made a near voxel's few thousand indices
+        // a chain of ~100 global-memory latencies, twice)
+        constexpr int SEL_U = 8;
+        for (int base = 0; base < c; base += 32 * SEL_U) {
+            int v[SEL_U];
+#pragma unroll
+            for (int u = 0; u < SEL_U; u++) { const int q = base + 32 * u + lane; v[u] = q < c ? seg[q] : -1; }
+#pragma unroll
+            for (int u = 0; u < SEL_U; u++) if (v[u] >= 0) atomicAdd(&hist[v[u] >> S], 1);
+        }
         __syncwarp();
         constexpr int BPL = SEL_BINS / 32;
         int h[BPL], s = 0;
@@ -100,15 +130,20 @@ __device__ void warp_select_sorted(const int* seg, int c, int K, int n, int* sel
         kb = __shfl_sync(0xffffffffu, kb, src);
         below = __shfl_sync(0xffffffffu, below, src);
         int w = 0, wc = 0;
-        for (int base = 0; base < c; base += 32) {
-            const int q = base + lane;
-            const int v = q < c ? seg[q] : 0;
-            const int b = q < c ? (v >> S) : SEL_BINS;
-            const unsigned ba = __ballot_sync(0xffffffffu, b < kb), bc = __ballot_sync(0xffffffffu, b == kb);
-            const unsigned lt = (1u << lane) - 1u;
-            if (b < kb) sel[w + __popc(ba & lt)] = v;
-            if (b == kb) cand[wc + __popc(bc & lt)] = v;
-            w += __popc(ba); wc += __popc(bc);
+        for (int base0 = 0; base0 < c; base0 += 32 * SEL_U) {
+            int vv[SEL_U];
+#pragma unroll
+            for (int u = 0; u < SEL_U; u++) { const int q = base0 + 32 * u + lane; vv[u] = q < c ? seg[q] : -1; }
+#pragma unroll
+            for (int u = 0; u < SEL_U; u++) {
+                const int v = vv[u];
+                const int b = v >= 0 ? (v >> S) : SEL_BINS;
+                const unsigned ba = __ballot_sync(0xffffffffu, b < kb), bc = __ballot_sync(0xffffffffu, b == kb);
+                const unsigned lt = (1u << lane) - 1u;
+                if (b < kb) sel[w + __popc(ba & lt)] = v;
+                if (b == kb) cand[wc + __popc(bc & lt)] = v;
+                w += __popc(ba); wc += __popc(bc);
+            }
         }
         __syncwarp();
         warp_sort(cand, wc);                                     // wc <= 2^S <= CAND_CAP
