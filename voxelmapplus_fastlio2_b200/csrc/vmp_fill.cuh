@@ -24,7 +24,8 @@
 // k_fill_build is the build() variant (no cap, one updatePlane() at the end, Q18); it runs once per map.
 #pragma once
 
-constexpr int FILL_WARPS = 4;           // warps per CTA of k_fill
+constexpr int FILL_WARPS = 4;           // warps per CTA of k_fill, warp path (a voxel per warp)
+constexpr int HEAVY_WARPS = 4;          // warps per CTA of the CTA path (a voxel per CTA): chunks of a refit group evaluated side by side
 constexpr int TILE_LD = 37;             // doubles per point in the contribution tile (odd: conflict-free both ways)
 constexpr int SNAP_W = 12;              // doubles per snapshot: n, nt, mean[3], ppt[6], pad
 constexpr int SEL_BINS = 256;
@@ -214,8 +215,18 @@ __device__ __forceinline__ void snap_eig(const double* sn, double* evals, M3& ev
 // Where the stored points come from: the warp path reads them straight from the voxel's block in HBM / L2 (twelve coalesced loads
 // per chunk; its shared-memory footprint is what limits how many voxels an SM works on at a time), the CTA path stages them in
 // shared memory once (cp.async.bulk) for its four warps.
-constexpr int FILL_GROUP = 6;                       // snapshots refitted together (their eigen-solves run one per lane)
+// Snapshots refitted together (their eigen-solves run one per lane, and an eigen-solve - ~25 k cycles on one lane - is the longest
+// single step of a voxel).  The warp path keeps six (its shared-memory footprint decides how many voxels an SM works on at a time);
+// the CTA path takes twelve, the ten refits of a voxel that fills up within one scan in ONE pass instead of two: -10 us on the
+// longest voxel of a C2 scan, which is what the CTA launch lasts.
+constexpr int FILL_GROUP = 6;
+constexpr int HEAVY_GROUP = 12;
+template <bool CTA> struct FillGroup { static constexpr int N = CTA ? HEAVY_GROUP : FILL_GROUP; };
 constexpr int CH_MAX = FILL_GROUP * 8;              // chunks of one group (max_point_thresh <= 256)
+constexpr int CH_MAX_HEAVY = HEAVY_GROUP * 8;
+// group tables of the CTA path (its own area behind the tiles): chunk_k / chunk_base [CH_MAX_HEAVY] shorts, ev [HEAVY_GROUP][12], snap [HEAVY_GROUP][SNAP_W]
+constexpr size_t HEAVY_TABLE_BYTES = 2 * CH_MAX_HEAVY * 2 + HEAVY_GROUP * 12 * 8 + HEAVY_GROUP * SNAP_W * 8;
+static_assert(HEAVY_TABLE_BYTES % 16 == 0, "16-byte granules");
 
 struct alignas(16) FillWork {           // control block of the voxel in shared memory (written by the leader)
     unsigned long long bar;             // (unused slot, keeps the layout 16-byte granular)
@@ -237,7 +248,7 @@ __host__ __device__ inline size_t fill_warp_bytes(int maxpt) {
 }
 __host__ __device__ inline size_t fill_heavy_bytes(int maxpt) {
     const size_t ld = (size_t)((maxpt + 1) & ~1);
-    return fill_warp_bytes(maxpt) + 12 * ld * 8 + (size_t)(FILL_WARPS - 1) * 32 * TILE_LD * 8;
+    return fill_warp_bytes(maxpt) + 12 * ld * 8 + (size_t)(HEAVY_WARPS - 1) * 32 * TILE_LD * 8 + HEAVY_TABLE_BYTES;
 }
 
 // ---- TMA-style bulk copies (cp.async.bulk, sm_90+ / sm_100a) of a voxel's stored points (CTA path): twelve contiguous rows of the
@@ -262,8 +273,10 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-struct FillRegion { int* sel; FillWork* W; double* cx; double* tile; double* snap; double* pts; double* tiles_rest; int* hist; int* cand; };
+struct FillRegion { int* sel; FillWork* W; double* cx; double* tile; double* snap; double* pts; double* tiles_rest; int* hist; int* cand;
+                    short* chunk_k; short* chunk_base; double (*ev)[12]; };
 constexpr int CAND_OFF = SEL_BINS;                  // selection scratch inside the tile: [hist: SEL_BINS ints] [cand]
+template <bool CTA>
 __device__ __forceinline__ FillRegion fill_region(unsigned char* base, int maxpt) {
     const int ld = (maxpt + 1) & ~1;
     FillRegion r;
@@ -276,6 +289,14 @@ __device__ __forceinline__ FillRegion fill_region(unsigned char* base, int maxpt
     r.tiles_rest = r.pts + 12 * ld;                 // (CTA path only)
     r.hist = reinterpret_cast<int*>(r.tile);
     r.cand = r.hist + CAND_OFF;
+    r.chunk_k = r.W->chunk_k; r.chunk_base = r.W->chunk_base; r.ev = r.W->ev;
+    if (CTA) {                                      // the bigger group tables of the CTA path
+        double* t = r.tiles_rest + (size_t)(HEAVY_WARPS - 1) * 32 * TILE_LD;
+        r.ev = reinterpret_cast<double (*)[12]>(t);
+        r.snap = t + HEAVY_GROUP * 12;
+        r.chunk_k = reinterpret_cast<short*>(r.snap + HEAVY_GROUP * SNAP_W);
+        r.chunk_base = r.chunk_k + CH_MAX_HEAVY;
+    }
     return r;
 }
 
@@ -298,7 +319,7 @@ template <bool CTA>
 __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRegion& R, const double* P, int pstride, int ns, RefitAcc& ra) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool leader = !CTA || wib == 0;
-    const int nwarps = CTA ? FILL_WARPS : 1, wix = CTA ? wib : 0;
+    const int nwarps = CTA ? HEAVY_WARPS : 1, wix = CTA ? wib : 0;
     FillWork* W = R.W;
     const double* snap = R.snap;
     if (leader) {
@@ -316,9 +337,9 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
             snap_eig(snap + lane * SNAP_W, evals, evecs);
             plane = !(evals[0] > m.plane_thresh);                 // Q13: otherwise norm / cov stay
 #pragma unroll
-            for (int e = 0; e < 3; e++) W->ev[lane][e] = evals[e];
+            for (int e = 0; e < 3; e++) R.ev[lane][e] = evals[e];
 #pragma unroll
-            for (int e = 0; e < 9; e++) W->ev[lane][3 + e] = evecs.a[e];
+            for (int e = 0; e < 9; e++) R.ev[lane][3 + e] = evecs.a[e];
             if (plane) {
                 int nt = (int)snap[lane * SNAP_W + 1];
                 if (nt > W->avail) { atomicOr(&ctl->err, E_REFIT_OVERFLOW); nt = W->avail; }      // build overflow + thresh 1
@@ -330,7 +351,7 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
         const int first = incl - nch;
-        for (int b = 0; b < nch; b++) { W->chunk_k[first + b] = (short)lane; W->chunk_base[first + b] = (short)(32 * b); }
+        for (int b = 0; b < nch; b++) { R.chunk_k[first + b] = (short)lane; R.chunk_base[first + b] = (short)(32 * b); }
         if (lane == 31) { W->nchunks = incl; W->pmask = pmask; }
     }
     fill_sync<CTA>();
@@ -339,7 +360,7 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
     for (int batch = 0; batch < nchunks; batch += nwarps) {
         const int ch = batch + wix;
         if (ch < nchunks) {
-            const int k = W->chunk_k[ch], base = W->chunk_base[ch];
+            const int k = R.chunk_k[ch], base = R.chunk_base[ch];
             const double* sn = snap + k * SNAP_W;
             const int n = (int)sn[0];
             int nt = (int)sn[1];
@@ -355,9 +376,9 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
                 double ev[3];
                 M3 evc;
 #pragma unroll
-                for (int e = 0; e < 3; e++) ev[e] = W->ev[k][e];
+                for (int e = 0; e < 3; e++) ev[e] = R.ev[k][e];
 #pragma unroll
-                for (int e = 0; e < 9; e++) evc.a[e] = W->ev[k][3 + e];
+                for (int e = 0; e < 9; e++) evc.a[e] = R.ev[k][3 + e];
                 const V3 nrm = v3(evc(0, 0), evc(1, 0), evc(2, 0));
                 double* tile = CTA ? cta_tile(R, wib) : R.tile;
                 plane_contrib(p, S, mean, n, ev, evc, nrm, tile + lane * TILE_LD);
@@ -367,7 +388,7 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
         if (leader) {
             const int nb = nchunks - batch < nwarps ? nchunks - batch : nwarps;
             for (int w = 0; w < nb; w++) {                            // chunks in order, points in stored order (Q7)
-                const int k = W->chunk_k[batch + w], base = W->chunk_base[batch + w];
+                const int k = R.chunk_k[batch + w], base = R.chunk_base[batch + w];
                 int nt = (int)snap[k * SNAP_W + 1];
                 if (nt > W->avail) nt = W->avail;
                 const int np = nt - base < 32 ? nt - base : 32;
@@ -389,7 +410,7 @@ __device__ void refit_group(const DevMap& m, DevCtl* ctl, int slot, const FillRe
             const int k = 31 - __clz(pmask);                          // the last refit that found a plane
             const double* sn = snap + k * SNAP_W;
             const V3 mean = v3(sn[2], sn[3], sn[4]);
-            const V3 nrm = v3(W->ev[k][3], W->ev[k][6], W->ev[k][9]);
+            const V3 nrm = v3(R.ev[k][3], R.ev[k][6], R.ev[k][9]);
             V3 ns_ = nrm;
             if (-dot(mean, nrm) < 0.0) ns_ = neg(nrm);
 #pragma unroll
@@ -404,9 +425,9 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
                            FillCounters& fc, unsigned long long* bar, unsigned& phase) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool leader = !CTA || wib == 0;
-    const int nth = CTA ? FILL_WARPS * 32 : 32, tix = CTA ? (int)threadIdx.x : lane;
+    const int nth = CTA ? HEAVY_WARPS * 32 : 32, tix = CTA ? (int)threadIdx.x : lane;
     const int ld = (m.maxpt + 1) & ~1;
-    const FillRegion R = fill_region(region, m.maxpt);
+    const FillRegion R = fill_region<CTA>(region, m.maxpt);
     FillWork* W = R.W;
     double* tp = m.tp + (size_t)slot * 12 * m.maxpt;
     // ---- leader: counters of the voxel, closed-form control flow, selection of the consumed points
@@ -514,7 +535,7 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
         fill_sync<CTA>();
         const double* P = CTA ? R.pts : tp;
         const int pstride = CTA ? ld : m.maxpt;
-        // ---- the state machine (leader); the refits of every FILL_GROUP snapshots by everybody
+        // ---- the state machine (leader); the refits of every FillGroup<CTA>::N snapshots by everybody
         RefitAcc ra;
         ra.acc0 = ra.acc1 = 0.0; ra.loaded = 0; ra.any_plane = 0; ra.plane_final = 0; ra.n_refit = 0; ra.refit_points = 0;
         for (int e = 0; e < 3; e++) { ra.nrm[e] = 0.0; ra.ctr[e] = 0.0; }
@@ -522,7 +543,7 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
         while (true) {
             int nsnap = 0;
             if (leader) {
-                for (; j < consumed && nsnap < FILL_GROUP; j++) {          // point order
+                for (; j < consumed && nsnap < FillGroup<CTA>::N; j++) {   // point order
                     const double pm = R.cx[cm * ld + j], pa = R.cx[ia * ld + j], pb = R.cx[ib * ld + j];
                     mean_l = mean_l + (pm - mean_l) / (double)(n0 + j + 1);
                     ppt_l += pa * pb;
@@ -615,7 +636,9 @@ __device__ void fill_classify(const DevMap& m, DevCtl* ctl, int vi) {
 
 // heavy != 0: the CTA path over the voxels classified heavy (shared memory: fill_heavy_bytes); heavy == 0: a warp per voxel over the
 // rest (FILL_WARPS x fill_warp_bytes).  The two launches run side by side on two streams of the scan's graph.
-__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(DevMap m, DevScan s, DevCtl* ctl, int heavy) {
+template <bool HEAVY>
+__global__ void __launch_bounds__(HEAVY ? HEAVY_WARPS * 32 : FILL_WARPS * 32, 3) k_fill(DevMap m, DevScan s, DevCtl* ctl) {
+    constexpr int heavy = HEAVY ? 1 : 0;
     extern __shared__ __align__(16) unsigned char fill_smem[];
     __shared__ int s_vi;
     __shared__ __align__(8) unsigned long long s_bar;         // mbarrier of the CTA path's bulk copies

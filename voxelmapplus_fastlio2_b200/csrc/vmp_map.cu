@@ -651,12 +651,12 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, const 
         auto per_sm = [](size_t b) { const int q = (int)((227 * 1024) / (b + 1024)); return q < 1 ? 1 : q > 8 ? 8 : q; };
         if (fork) {
             cudaEventRecord(side->ev[4], st); cudaStreamWaitEvent(side->st, side->ev[4], 0);
-            k_fill<<<sm_count * per_sm(smem_h), FILL_WARPS * 32, smem_h, side->st>>>(m, s, ctl, 1); launches++;
+            k_fill<true><<<sm_count * per_sm(smem_h), HEAVY_WARPS * 32, smem_h, side->st>>>(m, s, ctl); launches++;
             cudaEventRecord(side->ev[5], side->st);
         } else {
-            k_fill<<<sm_count * per_sm(smem_h), FILL_WARPS * 32, smem_h, st>>>(m, s, ctl, 1); launches++; mark(mk, VMP_K_FILL_ACC);
+            k_fill<true><<<sm_count * per_sm(smem_h), HEAVY_WARPS * 32, smem_h, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_FILL_ACC);
         }
-        k_fill<<<sm_count * per_sm(smem), FILL_WARPS * 32, smem, st>>>(m, s, ctl, 0); launches++; mark(mk, VMP_K_MAP_FILL);
+        k_fill<false><<<sm_count * per_sm(smem), FILL_WARPS * 32, smem, st>>>(m, s, ctl); launches++; mark(mk, VMP_K_MAP_FILL);
         if (fork) cudaStreamWaitEvent(st, side->ev[5], 0);
     }
     // the LRU-log append only needs the last-touch times: side branch next to the merge simulation
@@ -688,7 +688,9 @@ int launch_map_update(cudaStream_t st, const DevMap& m, const DevScan& s, const 
 cudaError_t map_configure_kernels(const DevMap& m) {
     cudaError_t e = cudaFuncSetAttribute(k_merge_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeShared));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILL_WARPS * fill_warp_bytes(m.maxpt)));
+    e = cudaFuncSetAttribute(k_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_heavy_bytes(m.maxpt));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_fill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILL_WARPS * fill_warp_bytes(m.maxpt)));
 }
 
 // Rare maintenance, launched by the host between scans only when the previous scan asked for it
