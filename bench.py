@@ -188,7 +188,7 @@ def config_dict(wl, prime):
 # The map formula is split over the kernels that carry the respective term; kernels that only do the implementation's
 # own bookkeeping (segment build, LRU log, finalize) have NO algorithmic bytes and only count in the map update's time.
 def algo_bytes(kernel, st_sum, n_pts_sum):
-    if kernel in ("k_measure", "k_iekf"):
+    if kernel in ("k_iekf_loop", "k_measure", "k_iekf"):      # all IEKF iterations of a scan (one resident launch since round 2)
         return 132 * st_sum["pt_iters"]
     if kernel == "k_set_scan":
         return 84 * n_pts_sum                       # 12 B in, point_lidar 24 + cov_lidar 48 out
@@ -370,7 +370,8 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
             t_wall0 = time.perf_counter()
             if args.ncu_range:              # ncu --profile-from-start off: only the timed steps of this pass are captured
                 torch.cuda.cudart().cudaProfilerStart()
-        flush.zero_()                       # L2 flush between steps (256 MiB > 126 MB L2), outside the events
+        if not args.no_l2_flush:
+            flush.zero_()                   # L2 flush between steps (256 MiB > 126 MB L2), outside the events
         torch.cuda.synchronize()
         st = g.scan_dev(d_clouds[i].data_ptr(), clouds[i].shape[0], d_priors[i].data_ptr())
         assert st.iters == e2e_stats[i][0] and sum(st.effect_num[:st.iters]) == e2e_stats[i][1], \
@@ -403,7 +404,8 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
         for i in range(S0 + K):
             if i == S0:
                 gp.profile_reset()
-            flush.zero_()
+            if not args.no_l2_flush:
+                flush.zero_()
             torch.cuda.synchronize()
             st = gp.scan_dev(d_clouds[i].data_ptr(), clouds[i].shape[0], d_priors[i].data_ptr())
             if i >= S0:
@@ -419,7 +421,7 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
         ranked = sorted(prof.items(), key=lambda kv: -kv[1][0])
         top, (top_ms, top_launches) = ranked[0]
         # launches that do work: early-exited IEKF iterations are counted with the executed ones
-        eff_launches = iters_sum if top == "k_measure" else max(1, top_launches)
+        eff_launches = max(1, top_launches)         # (k_iekf_loop: one launch per scan, all its iterations inside)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -444,7 +446,7 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
                              "frac": round(b / (v[0] * 1e-3) / 1e9 / peak, 5) if v[0] > 0 else None}
         map_ms = sum(v[0] for k, v in prof.items() if k in MAP_KERNELS)
         mb = map_bytes(agg) + 84 * n_pts_sum              # + the pv_list production (84 B / point), which opens the map update (k_world_insert_count)
-        iekf_ms = sum(v[0] for k, v in prof.items() if k in ("k_set_scan", "k_measure", "k_iekf", "k_ieskf_solve", "k_scan_out"))
+        iekf_ms = sum(v[0] for k, v in prof.items() if k in ("k_set_scan", "k_iekf_loop", "k_measure", "k_iekf", "k_ieskf_solve", "k_scan_out"))
         ib = 132 * agg["pt_iters"] + 84 * n_pts_sum
         roof = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 6), "traffic": traffic,
@@ -477,7 +479,8 @@ def measure_workload(args, wl, pkgs, W, K, PR, rank, world, local, full=True):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(wl, PR),
             "protocol": {"parallelism": f"replicas x{world} (one independent sequence and map per GPU, no collective on the path)",
-                         "l2": "flushed between steps (256 MiB memset, outside the timed events)",
+                         "l2": ("NOT flushed between steps (--no-l2-flush: diagnostic run, not a bench value)" if args.no_l2_flush
+                                else "flushed between steps (256 MiB memset, outside the timed events)"),
                          "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
                          "window": f"{PR} untimed priming scans (the trajectory stands still for its first 20) + {W} warm-up scans, "
                                    f"then {K} timed scans of a moving sensor"},
@@ -578,6 +581,7 @@ def main():
     ap.add_argument("--cpu-scans", type=int, default=300, help="bound of the CPU sample (scans)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-loops", action="store_true", help="skip the whole-host-loop pass (profiling runs)")
+    ap.add_argument("--no-l2-flush", action="store_true", help="diagnostic: leave the L2 as the previous scan left it (the default flushes it between steps)")
     ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps of the resident pass (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.warmup < 3:

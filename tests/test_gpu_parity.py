@@ -354,6 +354,31 @@ def test_pipelined_mode_is_identical():
     assert_maps_equal(a.map.dump_map(), b.map.dump_map(), exact=True, what="pipelined map")
 
 
+@pytest.mark.parametrize("estimate_ext", [False, True])
+def test_resident_iteration_loop_is_identical(monkeypatch, estimate_ext):
+    """The IEKF iterations of a scan as ONE resident launch (k_iekf_loop: solver CTA and measurement CTAs hand the state over through
+    a release / acquire flag) against one launch per iteration (VMP_IEKF_LOOP=0): same arithmetic in the same order, so the
+    posteriors, the iteration counts, effect_num and the map are identical bit for bit (ieskf.cpp:125-156)."""
+    cfg = default_config(max_points_per_scan=8192, estimate_ext=1 if estimate_ext else 0)
+    a = LIOBuilder(cfg)
+    monkeypatch.setenv("VMP_IEKF_LOOP", "0")
+    b = LIOBuilder(cfg)
+    monkeypatch.delenv("VMP_IEKF_LOOP")
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=6000))
+    iters = []
+    for pk in seq.packages(40):
+        sa = a.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        sb = b.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        xa, Pa, s1 = a.state()
+        xb, Pb, s2 = b.state()
+        assert s1 == s2 and bytes(xa) == bytes(xb) and np.array_equal(Pa, Pb)
+        assert sa.iters == sb.iters and list(sa.effect_num) == list(sb.effect_num) and sa.converged == sb.converged
+        assert sa.map.as_dict() == sb.map.as_dict()
+        iters.append(sa.iters)
+    assert len(set(i for i in iters if i)) >= 2          # scans that stop early and scans that do not
+    assert_maps_equal(a.map.dump_map(), b.map.dump_map(), exact=True, what="resident loop vs one launch per iteration")
+
+
 def test_staged_scan_is_identical():
     """vmp_scan_buffer + vmp_scan_staged (points written straight into the pinned staging) == vmp_scan, bit for bit."""
     cfg = default_config(max_points_per_scan=8192)

@@ -46,7 +46,7 @@ def test_algorithmic_bytes_model():
     and the map formula split over the kernels that carry each term (the per-kernel terms add up to the formula)."""
     import bench
     st = dict(pt_iters=3 * 1000, n_ins=100, n_touch=50, refit_points=400, n_refit=10, n_merge=2, n_mergevox=7, n_full=300, n_mergeprobe=250)
-    assert bench.algo_bytes("k_measure", st, 1000) == 132 * 3000
+    assert bench.algo_bytes("k_iekf_loop", st, 1000) == 132 * 3000
     assert bench.algo_bytes("k_set_scan", st, 1000) == 84 * 1000
     assert bench.algo_bytes("k_world_points", st, 1000) == 84 * 1000
     assert bench.algo_bytes("k_fill", st, 1000) == 144 * 100 + 152 * 50 + 72 * 400 + 432 * 10

@@ -499,6 +499,27 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
         VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     }
     VMP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (const char* e = getenv("VMP_L2_PERSIST_MB")) {
+        // experiment: an L2 persisting access-policy window on the hot plane records (mean / normal / flags word, 64 B per
+        // voxel: what k_measure gathers per point); set on the stream before the capture, the graph's kernel nodes inherit it
+        const size_t want = (size_t)std::max(0, atoi(e)) << 20;
+        int max_persist = 0, max_window = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t persist = std::min(want, (size_t)max_persist);
+        if (persist > 0) {
+            VMP_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+            cudaStreamAttrValue v{};
+            const size_t bytes = std::min((size_t)h->m.pool * 64, (size_t)max_window);
+            v.accessPolicyWindow.base_ptr = h->m.hot;
+            v.accessPolicyWindow.num_bytes = bytes;
+            v.accessPolicyWindow.hitRatio = bytes <= persist ? 1.0f : (float)((double)persist / (double)bytes);
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            VMP_CUDA_CHECK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v));
+        }
+    }
     int r = build_graph(h);
     if (r) return r;
     VMP_CUDA_CHECK(cudaGetLastError());
@@ -996,7 +1017,7 @@ int vmp_profile_read(vmp_handle h, double* ms, int64_t* launches) {
 }
 const char* vmp_kernel_name(int id) {
     static const char* names[VMP_K_COUNT] = {
-        "k_scan_in", "k_set_scan", "k_predict", "k_measure", "k_ieskf_solve", "k_world_insert_count",
+        "k_scan_in", "k_set_scan", "k_predict", "k_iekf_loop", "k_ieskf_solve", "k_world_insert_count",
         "k_map_begin", "k_map_insert", "k_map_count", "k_seg_scan", "k_seg_fill", "k_lru_evict",
         "k_fill", "k_merge_prefilter", "k_merge_rounds", "k_log_append", "k_map_finalize",
         "k_map_end", "k_rehash", "k_log_compact", "k_scan_out", "k_fill_classify", "k_fill_heavy", "k_undistort", "k_downsample"};

@@ -2,15 +2,17 @@
 // semantics (VoxelMap::update / build, voxel_map.cpp:200-256; VoxelGrid::pushPoint /
 // addToPlane / updatePlane / merge, voxel_map.cpp:29-186), decomposed into parallel phases:
 //
-//   k_map_insert     key (VoxelMap::index) + find-or-insert in the open-addressing hash
-//   k_map_count      per-voxel point count, first/last touching point index, touched list; its last CTA lays out the
-//                    per-voxel segments (disjoint, unordered: no scan kernel)
-//   k_seg_fill       point indices grouped by voxel (+ per-block counts for ordered compaction)
+//   k_world_insert_count   world point + covariance of every scan point (lio_builder.cpp:233-245), key (VoxelMap::index) +
+//                    find-or-insert in the open-addressing hash, per-voxel point count, first / last touching point index,
+//                    touched list; its last CTA lays out the per-voxel segments (disjoint, unordered: no scan kernel)
+//   k_seg_fill       which touched voxels take the CTA path of k_fill (+ L2 prefetch of what k_fill will read), then the point
+//                    indices grouped by voxel (+ per-block counts for ordered compaction)
 //   k_lru_evict      exact LRU victims in creation order (cache.back() semantics, Q17); side branch of the graph
-//   k_fill_state / k_fill_refit / k_fill_acc   (vmp_fill.cuh) pushPoint state machine per touched voxel, the refits it
-//                    triggers as concurrent jobs (3x3 eigen solve, J Sigma J^T per stored point), ordered accumulation
+//   k_fill<false> / k_fill<true>   (vmp_fill.cuh) pushPoint state machine per touched voxel and the refits it triggers (3x3
+//                    eigen-solves one per lane, J Sigma J^T per stored point, ordered accumulation): a warp per voxel, and a
+//                    CTA per voxel for the voxels whose refits loop over many points; two launches side by side
 //   k_merge_prefilter / k_merge_rounds          (vmp_merge.cuh) merge(): parallel static candidate filter, then an event
-//                    simulation in rounds of spatially independent events over the (few) voxels whose merge can succeed
+//                    simulation in rounds of spatially independent events on a 4-CTA cluster, exact serial redo behind it
 //   k_log_append     LRU log append in last-touch order, new stamps; side branch
 //   k_map_finalize   apply evictions (tombstones, free list), reset per-scan scratch; its last CTA closes the update
 //                    (counters, maintenance requests, host mailbox)
