@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--capacity", type=int, default=100000)
     ap.add_argument("--pipelined", type=int, default=0)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--profile-from", type=int, default=-1, help="per-kernel device times (profiling mode: kernels launched one by one) from this scan on")
     a = ap.parse_args()
     # 2240 m per period, mean speed 5 m/s (peak 7.9 m/s)
     traj = synth.Trajectory(centre=(600.0, 600.0, 1.8), ax=560.0, ay=2.0, period=448.0)   # mid-street (facades at y = 588 and 612)
@@ -60,6 +61,11 @@ def main():
     align = None
     failed = None
     for pk in pkgs:
+        if a.profile_from >= 0 and pk.index == a.profile_from:
+            lio.map.sync()
+            lio.map.profile_enable(True)
+            lio.map.profile_reset()
+            n_prof0 = len(gpu_ms)
         try:
             st = lio.process(pk.imus, pk.cloud, pk.t0, pk.t1)
         except Exception as e:          # a capacity condition reported by the device: record where, keep what was measured
@@ -102,6 +108,11 @@ def main():
            "note": "device time = CUDA events around upload + graph of vmp_scan_raw (motion compensation, IEKF, map update); "
                    "the loop adds host IMU propagation and synthetic-package handling; err_m = |estimated - ground-truth position| "
                    "after aligning the estimator's gravity-aligned start frame to the ground truth"}
+    if a.profile_from >= 0:
+        prof = lio.map.profile_read()
+        k = max(1, n - n_prof0)
+        res["per_kernel_us_per_scan"] = {name: round(ms * 1e3 / k, 2) for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]) if cnt > 0}
+        res["profiled_scans"] = k
     txt = json.dumps(res, indent=1)
     print(txt)
     if a.out:

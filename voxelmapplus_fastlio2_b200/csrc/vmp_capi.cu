@@ -72,7 +72,7 @@ struct vmp_handle_t {
     int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
     SideStream side{};                   // second stream of the map update's side branches
-    cudaEvent_t ev_so[2] = {nullptr, nullptr};   // fork / join of the posterior write-out
+    cudaEvent_t ev_so[3] = {nullptr, nullptr, nullptr};   // fork / join of the posterior write-out; [2]: fork of the compensated cloud's copy to the host
     cudaGraphExec_t graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevMap m{};
@@ -182,7 +182,16 @@ int enqueue_scan(vmp_handle_t* h, const Marker* mk, bool raw, bool predict = fal
         launch_predict(st, h->f, h->d_in, h->d_pred, (DevPose*)(h->d_stage + IN_HDR)); k++; mark(mk, VMP_K_UPDATE_BEGIN);
     }
     if (raw) {      // lio_builder.cpp:127-152 in front of the timed region: the points are compensated where they were uploaded
-        launch_undistort(st, h->grid_pts, h->d_in, (const DevPose*)(h->d_stage + IN_HDR), (float4*)(h->d_stage + PTS_OFF), h->a_cloud); k++; mark(mk, VMP_K_UNDISTORT);
+        // the compensated cloud goes back to the host (reference: package.cloud is edited in place) from a side branch that runs beside
+        // the IEKF: written from k_undistort itself, the stores to mapped host memory were half of that kernel (10 of 20 us at 20 000 points)
+        const bool fork_cloud = mk == nullptr;
+        launch_undistort(st, h->grid_pts, h->d_in, (const DevPose*)(h->d_stage + IN_HDR), (float4*)(h->d_stage + PTS_OFF), nullptr); k++; mark(mk, VMP_K_UNDISTORT);
+        if (fork_cloud) {
+            cudaEventRecord(h->ev_so[2], st); cudaStreamWaitEvent(h->side.st, h->ev_so[2], 0);
+            launch_cloud_out(h->side.st, h->grid_pts, h->d_in, (const float4*)(h->d_stage + PTS_OFF), h->a_cloud); k++;
+        } else {
+            launch_cloud_out(st, h->grid_pts, h->d_in, (const float4*)(h->d_stage + PTS_OFF), h->a_cloud); k++; mark(mk, VMP_K_UNDISTORT);
+        }
     }
     // the first iteration stages the scan itself (calcBodyCov per point, prior from the header): no staging kernel in front
     if (h->iekf_loop) {     // all iterations in one resident launch (k_iekf_loop)

@@ -390,7 +390,46 @@ __global__ void __launch_bounds__(256) k_undistort(const ScanIn* __restrict__ in
     M3 cur_rot, cur_ext;
     for (int k = 0; k < 9; k++) { cur_rot.a[k] = sx[3 + k]; cur_ext.a[k] = sx[12 + k]; }
     const V3 cur_pos = v3(sx[0], sx[1], sx[2]), cur_pext = v3(sx[21], sx[22], sx[23]);
+    // Point 0 is carried through EVERY pose interval before its own (the quirk above): up to n_poses dependent steps, each with an
+    // Exp() - one thread doing that was the length of the whole kernel (20 us for a 20 000-point scan).  The pose part of a step
+    // (point_rot, point_pos) depends on the point's time only, so the lanes of one warp evaluate the steps' pose parts side by side
+    // and lane 0 then applies them in the reference's order: the same operations on the same operands.
+    __shared__ double s_pr[MAX_POSES][9], s_pp[MAX_POSES][3];
+    if (blockIdx.x == 0 && threadIdx.x < 32 && n > 0) {
+        const int lane = threadIdx.x;
+        float4 p = cloud[0];
+        const double t = (double)p.w / double(1000);
+        int h0 = -1;
+        for (int k = 0; k + 1 < K; k++) if (sp[k].offset < t) h0 = k;
+        for (int h = lane; h <= h0; h += 32) {
+            const DevPose& head = sp[h];
+            const DevPose& tail = sp[h + 1];
+            const double dt = t - head.offset;
+            M3 hr;
+            for (int k = 0; k < 9; k++) hr.a[k] = head.rot[k];
+            const M3 point_rot = mul(hr, so3_exp(scale(v3(tail.gyro[0], tail.gyro[1], tail.gyro[2]), dt)));
+            const V3 point_pos = add(add(v3(head.pos[0], head.pos[1], head.pos[2]), scale(v3(head.vel[0], head.vel[1], head.vel[2]), dt)),
+                                     scale(scale(scale(v3(tail.acc[0], tail.acc[1], tail.acc[2]), 0.5), dt), dt));
+            for (int k = 0; k < 9; k++) s_pr[h][k] = point_rot.a[k];
+            for (int k = 0; k < 3; k++) s_pp[h][k] = point_pos[k];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int h = h0; h >= 0; h--) {
+                const V3 point = v3((double)p.x, (double)p.y, (double)p.z);
+                M3 point_rot;
+                for (int k = 0; k < 9; k++) point_rot.a[k] = s_pr[h][k];
+                const V3 point_pos = v3(s_pp[h][0], s_pp[h][1], s_pp[h][2]);
+                const V3 inner = sub(add(mul(point_rot, add(mul(cur_ext, point), cur_pext)), point_pos), cur_pos);
+                const V3 pc = mul(tr(cur_ext), sub(mul(tr(cur_rot), inner), cur_pext));
+                p.x = (float)pc[0]; p.y = (float)pc[1]; p.z = (float)pc[2];
+            }
+            cloud[0] = p;
+            if (host_copy) host_copy[0] = p;
+        }
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i == 0) continue;                                         // (done above)
         float4 p = cloud[i];
         const double t = (double)p.w / double(1000);
         int h = -1;
@@ -408,7 +447,7 @@ __global__ void __launch_bounds__(256) k_undistort(const ScanIn* __restrict__ in
             const V3 inner = sub(add(mul(point_rot, add(mul(cur_ext, point), cur_pext)), point_pos), cur_pos);
             const V3 pc = mul(tr(cur_ext), sub(mul(tr(cur_rot), inner), cur_pext));
             p.x = (float)pc[0]; p.y = (float)pc[1]; p.z = (float)pc[2];
-            if (i != 0) break;                                        // only the first point is revisited
+            break;                                                    // only the first point is revisited (above)
         }
         cloud[i] = p;
         if (host_copy) host_copy[i] = p;                              // mapped host memory: the caller's cloud is edited in place
@@ -540,6 +579,13 @@ __global__ void __launch_bounds__(256) k_predict(DevFilter* f, ScanIn* in, const
 }
 void launch_predict(cudaStream_t st, DevFilter* f, ScanIn* in, const DevPredictIn* pin, DevPose* poses) { k_predict<<<1, 256, 0, st>>>(f, in, pin, poses); }
 
+__global__ void __launch_bounds__(256) k_cloud_out(const ScanIn* __restrict__ in, const float4* __restrict__ cloud, float4* host_copy) {
+    const int n = in->n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) host_copy[i] = cloud[i];
+}
+void launch_cloud_out(cudaStream_t st, int grid, const ScanIn* in, const float4* cloud, float4* host_copy) {
+    k_cloud_out<<<grid, 256, 0, st>>>(in, cloud, host_copy);
+}
 void launch_undistort(cudaStream_t st, int grid, const ScanIn* in, const DevPose* poses, float4* cloud, float4* host_copy) {
     k_undistort<<<grid, 256, 0, st>>>(in, poses, cloud, host_copy);
 }

@@ -13,6 +13,7 @@ constexpr int PT_BLOCK = 1024;          // points per block in the order-preserv
 // IEKF
 // motion compensation of a time-sorted raw scan in place (+ a copy into mapped host memory)
 void launch_undistort(cudaStream_t st, int grid, const ScanIn* in, const DevPose* poses, float4* cloud, float4* host_copy);
+void launch_cloud_out(cudaStream_t st, int grid, const ScanIn* in, const float4* cloud, float4* host_copy);
 // IESKF::predict for every IMU step of a scan + the IMU pose list, from the filter state resident on the device (one CTA)
 void launch_predict(cudaStream_t st, DevFilter* f, ScanIn* in, const DevPredictIn* pin, DevPose* poses);
 // stages one scan from the mailbox `in` (device-accessible): points -> raw / body points / body covariances, prior, counters
