@@ -118,10 +118,28 @@ __global__ void __launch_bounds__(128) k_ds_centroid(const float4* __restrict__ 
         if (!head[j]) continue;
         const unsigned k = skeys[j];
         float sx = 0.0f, sy = 0.0f, sz = 0.0f, sc = 0.0f;
+        // The float sums are order-dependent (pcl::VoxelGrid adds the points of a leaf in their original order), so a leaf stays one
+        // sequential chain of adds - but not of memory latencies: eight points are fetched per round trip (keys, indices, then the
+        // scattered points), then added in order.  A dense near-field leaf holds thousands of points.
         int l = j;
-        for (; l < n_sort && skeys[l] == k; l++) {
-            const float4 p = cloud[svals[l]];
-            sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sc = __fadd_rn(sc, p.w);
+        bool more = true;
+        while (more) {
+            unsigned kk[8];
+            int vv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { kk[u] = (l + u < n_sort) ? skeys[l + u] : DS_INVALID; vv[u] = (l + u < n_sort) ? svals[l + u] : 0; }
+            float4 pp[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) pp[u] = (l + u < n_sort && kk[u] == k) ? cloud[vv[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+            int took = 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (more && l + u < n_sort && kk[u] == k) {
+                    sx = __fadd_rn(sx, pp[u].x); sy = __fadd_rn(sy, pp[u].y); sz = __fadd_rn(sz, pp[u].z); sc = __fadd_rn(sc, pp[u].w);
+                    took++;
+                } else more = false;
+            }
+            l += took;
         }
         const float cnt = (float)(l - j);
         const float4 c = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(sc, cnt));
