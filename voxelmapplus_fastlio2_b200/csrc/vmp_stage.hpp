@@ -3,7 +3,8 @@
 //
 // Why: a 200 000-point scan is 2.4 MB (3.2 MB raw); one host core moves it at ~10 GB/s = 0.2-0.3 ms, which is as long as
 // the whole device side of the scan.  The copy is embarrassingly parallel, so the handle keeps a small pool of helpers
-// (default 3 + the calling thread; VMP_COPY_THREADS=0 disables it).  Helpers spin briefly after a job (back-to-back scans
+// (default: up to 11 + the calling thread, two cores left alone, parts of at least 32 KB; VMP_COPY_THREADS=n sets the number of helpers, 0
+// disables them.  Measured on the C2 scan, 2.4 MB, 16-core host: vmp_scan end to end 2446 scans/s with 3 helpers, 2588 with 7, 2681 with 11).  Helpers spin briefly after a job (back-to-back scans
 // find them awake) and then sleep on a condition variable (at sensor rate they cost nothing).
 #pragma once
 #include <atomic>
@@ -28,7 +29,9 @@ public:
     bool copy(void* dst, const void* src, size_t bytes, int check_stride = 0) {
         constexpr size_t MIN_PAR = 512 * 1024;
         if (bytes < MIN_PAR || !ensure_started()) return slice(dst, src, bytes, 0, bytes, check_stride);
-        const int parts = (int)workers_.size() + 1;
+        int parts = (int)workers_.size() + 1;
+        const int by_size = (int)(bytes / (32 * 1024));                   // no more parts than 32 KB pieces
+        if (parts > by_size) parts = by_size < 2 ? 2 : by_size;
         // whole records per part, cache-line friendly
         const size_t rec = check_stride > 0 ? (size_t)check_stride * sizeof(float) : 64;
         const size_t nrec = bytes / rec;
@@ -72,9 +75,9 @@ private:
     bool ensure_started() {
         if (started_) return !workers_.empty();
         started_ = true;
-        int n = 3;
-        if (const char* e = std::getenv("VMP_COPY_THREADS")) n = std::atoi(e);
         const unsigned hc = std::thread::hardware_concurrency();
+        int n = hc >= 4 ? (int)std::min(11u, hc - 2) : 1;
+        if (const char* e = std::getenv("VMP_COPY_THREADS")) n = std::atoi(e);
         if (hc > 0 && (unsigned)n + 1 > hc) n = (int)hc - 1;
         if (n <= 0) return false;
         try {
