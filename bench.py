@@ -260,7 +260,7 @@ def run_ours(args):
                           "iters_mean": l1["iters_mean"], "e2e": l1["e2e"], "e2e_lio": l1["e2e_lio"], "cpu_baseline": l1["cpu_baseline"],
                           "gpu_launches": l1["gpu_launches"]}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -565,10 +565,32 @@ def run_reference(args):
                              "sample": cb["sample"] + "; OpenMP on the one loop the reference parallelises, the rest of the path is serial by construction"},
             "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL: 'NCCL version ...' at communicator creation when
+    NCCL_DEBUG is set in the environment), so the process's stdout is kept aside for the line and everything else goes to stderr."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
