@@ -239,6 +239,8 @@ def run_ours(args):
     assert replicas.rank_seed(rank) == seed
     if world != args.gpus and world > 1:
         log(f"[bench] warning: WORLD_SIZE={world} but --gpus {args.gpus}")
+    # the staging helpers of a handle (vmp_stage.hpp: up to 11 + the caller) share the host with the other ranks of the node
+    os.environ.setdefault("VMP_COPY_THREADS", str(max(1, min(11, (os.cpu_count() or 4) // max(1, world) - 2))))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
