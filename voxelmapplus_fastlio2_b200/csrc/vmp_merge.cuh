@@ -146,20 +146,21 @@ __global__ void __launch_bounds__(128) k_merge_prefilter(DevMap m, DevCtl* ctl) 
     const int ngroups = (gridDim.x * blockDim.x) >> 3;
     const int vend = (V + ngroups - 1) / ngroups * ngroups;          // keep the 8-lane groups converged
     for (int vi = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; vi < vend; vi += ngroups) {
-        int w = T_INF, A = -1;
+        int w = T_INF, A = -1, c = 0, off = 0;
         if (vi < V) {
             A = m.touched[vi];
-            if (m.evn[A] > 0 && sub < 6) {
-                const unsigned long long keyA = m.skey[A];
-                const VoxRec ra = load_rec(m, A);
-                w = wake_dir(m, keyA, ra.mean, ra.nrm, ra.group, sub, event_floor(ra, scan_id), scan_id);
-            }
+            // everything about A in ONE round trip (the kernel is a chain of dependent look-ups per voxel: each one it does not wait for
+            // separately is ~1 us off a launch that lasts 17): event count, key, record, segment
+            const int evn = m.evn[A];
+            const unsigned long long keyA = m.skey[A];
+            const VoxRec ra = load_rec(m, A);
+            c = m.cnt[A]; off = m.seg_off[A];
+            if (evn > 0 && sub < 6) w = wake_dir(m, keyA, ra.mean, ra.nrm, ra.group, sub, event_floor(ra, scan_id), scan_id);
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) { const int y = __shfl_xor_sync(gmask, w, o); w = y < w ? y : w; }
         if (w == T_INF) continue;                                   // uniform within the 8-lane group
         // first merge() call of A after the earliest time one of its pairs can pass
-        const int c = m.cnt[A], off = m.seg_off[A];
         int best = T_INF;
         for (int q = sub; q < c; q += 8) { const int i = m.seg[off + q]; if (i > w && i < best) best = i; }
 #pragma unroll
