@@ -545,3 +545,32 @@ def test_free_running_with_eviction(oracle_mod):
             evicted_total += so.map.n_evicted
     assert evicted_total > 1000, evicted_total
     assert worst_p < 1e-3, f"trajectory deviates {worst_p} m"
+
+
+def test_two_trajectories_on_one_gpu_from_two_threads():
+    """Two handles driven concurrently from two host threads: the resident iteration loop of each (CTAs that wait for each other) is
+    launched cooperatively, so neither can occupy half of the GPU and starve the other; the results are those of the same scans run alone."""
+    import threading
+    cfg = default_config(max_points_per_scan=8192)
+    seqs = [list(synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=6000), seed=sd).packages(45)) for sd in (11, 12)]
+
+    def run(pkgs, out):
+        lio = LIOBuilder(cfg)
+        for pk in pkgs:
+            lio.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        x, P, _ = lio.state()
+        out.append((bytes(x), P.copy(), lio.map.dump_map()))
+
+    alone = [[], []]
+    for k in range(2):
+        run(seqs[k], alone[k])
+    both = [[], []]
+    th = [threading.Thread(target=run, args=(seqs[k], both[k])) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in th), "two concurrent handles did not finish (dead-locked resident kernels?)"
+    for k in range(2):
+        assert both[k][0][0] == alone[k][0][0] and np.array_equal(both[k][0][1], alone[k][0][1])
+        assert_maps_equal(alone[k][0][2], both[k][0][2], exact=True, what="concurrent handle %d" % k)

@@ -530,6 +530,11 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
         }
     }
     int r = build_graph(h);
+    if (r != VMP_OK && h->iekf_loop) {      // the cooperative loop kernel could not be captured on this driver: one launch per iteration instead
+        cudaGetLastError();
+        h->iekf_loop = false;
+        r = build_graph(h);
+    }
     if (r) return r;
     VMP_CUDA_CHECK(cudaGetLastError());
     return VMP_OK;

@@ -362,9 +362,19 @@ void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const 
         else k_measure<false, false><<<g, 256, 0, st>>>(m, s, f, ctl, partials, solve, nullptr, reuse_slots ? 1 : 0);
     }
 }
-void launch_iekf_loop(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, const ScanIn* in, bool reuse_slots) {
-    if (ext) k_iekf_loop<true><<<grid + 1, 128, 0, st>>>(m, s, f, ctl, partials, in, reuse_slots ? 1 : 0);
-    else k_iekf_loop<false><<<grid + 1, 256, 0, st>>>(m, s, f, ctl, partials, in, reuse_slots ? 1 : 0);
+// Cooperative launch: the CTAs of this kernel wait for each other, so the grid has to be resident as a whole.  On an otherwise idle GPU a
+// plain launch of a grid that fits would do; the cooperative attribute makes the driver gang-schedule it, which is what keeps two
+// handles (two trajectories on one GPU, driven from two host threads) from starving each other's half-resident grids.
+cudaError_t launch_iekf_loop(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, const ScanIn* in, bool reuse_slots) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid + 1); lc.blockDim = dim3(ext ? 128 : 256); lc.dynamicSmemBytes = 0; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    const int reuse = reuse_slots ? 1 : 0;
+    return ext ? cudaLaunchKernelEx(&lc, k_iekf_loop<true>, m, s, f, ctl, partials, in, reuse)
+               : cudaLaunchKernelEx(&lc, k_iekf_loop<false>, m, s, f, ctl, partials, in, reuse);
 }
 // can grid + 1 CTAs of the loop kernel be resident at once?  (they wait for each other: anything less would never finish)
 bool iekf_loop_fits(bool ext, int grid, int sm_count) {

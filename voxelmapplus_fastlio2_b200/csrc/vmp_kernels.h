@@ -22,7 +22,7 @@ void launch_set_scan(cudaStream_t st, int grid, const DevScan& s, const ScanIn* 
 // iteration of a scan's graph, which stages the scan named by that header itself (no launch_set_scan in front)
 void launch_measure(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, int solve,
                     const ScanIn* first = nullptr, bool reuse_slots = false);
-void launch_iekf_loop(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, const ScanIn* in, bool reuse_slots);
+cudaError_t launch_iekf_loop(cudaStream_t st, bool ext, int grid, const DevMap& m, const DevScan& s, DevFilter* f, DevCtl* ctl, double* partials, const ScanIn* in, bool reuse_slots);
 bool iekf_loop_fits(bool ext, int grid, int sm_count);      // reuse_slots: later iterations inside a scan's graph (same map, same points)
 // posterior -> host mailbox (x, P, iteration counters, then seq behind a system-scope fence)
 void launch_state_out(cudaStream_t st, const DevFilter* f, const DevCtl* ctl, StateOut* out);
