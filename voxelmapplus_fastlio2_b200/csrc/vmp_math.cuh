@@ -223,14 +223,17 @@ VMP_HD void eig3_sym(double a00, double a10, double a11, double a20, double a21,
     if (sc == 0.0) sc = 1.0;
     a00 /= sc; a10 /= sc; a11 /= sc; a20 /= sc; a21 /= sc; a22 /= sc;
 
-    double diag[3], sub[2];
+    // diag / sub / Q live in scalars with compile-time indices (the iteration only ever works on rows (0,1), (1,2) or (0,1,2)): with
+    // arrays indexed by the loop variables they sat in local memory, and the eigen-solve - one lane per refit, the longest single step
+    // of a voxel in k_fill - was a chain of local loads and stores.  Every expression is the one of Eigen's tridiagonal QR step.
+    double d0, d1, d2, s0, s1;
     M3 Q;
     const double tiny = 2.2250738585072014e-308;
-    diag[0] = a00;
+    d0 = a00;
     const double v1norm2 = a20 * a20;
     if (v1norm2 <= tiny) {
-        diag[1] = a11; diag[2] = a22;
-        sub[0] = a10; sub[1] = a21;
+        d1 = a11; d2 = a22;
+        s0 = a10; s1 = a21;
         Q = eye<3>();
     } else {
         const double beta = sqrt(a10 * a10 + v1norm2);
@@ -238,28 +241,44 @@ VMP_HD void eig3_sym(double a00, double a10, double a11, double a20, double a21,
         const double m01 = a10 * invBeta;
         const double m02 = a20 * invBeta;
         const double q = 2.0 * m01 * a21 + m02 * (a22 - a11);
-        diag[1] = a11 + m02 * q;
-        diag[2] = a22 - m02 * q;
-        sub[0] = beta;
-        sub[1] = a21 - m01 * q;
+        d1 = a11 + m02 * q;
+        d2 = a22 - m02 * q;
+        s0 = beta;
+        s1 = a21 - m01 * q;
         Q(0, 0) = 1; Q(0, 1) = 0;   Q(0, 2) = 0;
         Q(1, 0) = 0; Q(1, 1) = m01; Q(1, 2) = m02;
         Q(2, 0) = 0; Q(2, 1) = m02; Q(2, 2) = -m01;
     }
     int end = 2, start = 0, iter = 0;
     const double precision = 2.0 * 2.220446049250313e-16;
+#define VMP_EIG_ROT(DK, DK1, SK, CK, CK1)                                                      \
+    {                                                                                           \
+        const double sdk = s * DK + c * SK;                                                     \
+        const double dkp1 = s * SK + c * DK1;                                                   \
+        const double ndk = c * (c * DK - s * SK) - s * (c * SK - s * DK1);                      \
+        DK = ndk;                                                                               \
+        DK1 = s * sdk + c * dkp1;                                                               \
+        SK = c * sdk - s * dkp1;                                                                \
+    }
+#define VMP_EIG_QCOL(CK, CK1)                                                                   \
+    for (int i = 0; i < 3; i++) {                                                               \
+        const double xi = Q(i, CK), yi = Q(i, CK1);                                             \
+        Q(i, CK) = c * xi - s * yi;                                                             \
+        Q(i, CK1) = s * xi + c * yi;                                                            \
+    }
     while (end > 0) {
-        for (int i = start; i < end; ++i)
-            if (fabs(sub[i]) <= (fabs(diag[i]) + fabs(diag[i + 1])) * precision || fabs(sub[i]) <= tiny) sub[i] = 0.0;
-        while (end > 0 && sub[end - 1] == 0.0) end--;
+        if (start <= 0 && 0 < end) { if (fabs(s0) <= (fabs(d0) + fabs(d1)) * precision || fabs(s0) <= tiny) s0 = 0.0; }
+        if (start <= 1 && 1 < end) { if (fabs(s1) <= (fabs(d1) + fabs(d2)) * precision || fabs(s1) <= tiny) s1 = 0.0; }
+        while (end > 0 && (end == 2 ? s1 : s0) == 0.0) end--;
         if (end <= 0) break;
         iter++;
         if (iter > 90) break;
         start = end - 1;
-        while (start > 0 && sub[start - 1] != 0.0) start--;
-        const double td = (diag[end - 1] - diag[end]) * 0.5;
-        const double e = sub[end - 1];
-        double mu = diag[end];
+        if (start == 1 && s0 != 0.0) start = 0;
+        const double dEm1 = end == 2 ? d1 : d0, dE = end == 2 ? d2 : d1;
+        const double td = (dEm1 - dE) * 0.5;
+        const double e = end == 2 ? s1 : s0;
+        double mu = dE;
         if (td == 0.0) {
             mu -= fabs(e);
         } else if (e != 0.0) {
@@ -271,8 +290,8 @@ VMP_HD void eig3_sym(double a00, double a10, double a11, double a20, double a21,
             if (e2 == 0.0) mu -= e / ((td + (td > 0.0 ? h : -h)) / e);
             else mu -= e2 / (td + (td > 0.0 ? h : -h));
         }
-        double x = diag[start] - mu;
-        double z = sub[start];
+        double x = (start == 0 ? d0 : d1) - mu;
+        double z = start == 0 ? s0 : s1;
         for (int k = start; k < end && z != 0.0; ++k) {
             double c, s;
             if (z == 0.0) { c = x < 0.0 ? -1.0 : 1.0; s = 0.0; }
@@ -284,33 +303,32 @@ VMP_HD void eig3_sym(double a00, double a10, double a11, double a20, double a21,
                 const double t = x / z; double u = sqrt(1.0 + t * t); if (z < 0.0) u = -u;
                 s = -1.0 / u; c = -t * s;
             }
-            const double sdk = s * diag[k] + c * sub[k];
-            const double dkp1 = s * sub[k] + c * diag[k + 1];
-            diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
-            diag[k + 1] = s * sdk + c * dkp1;
-            sub[k] = c * sdk - s * dkp1;
-            if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
-            x = sub[k];
-            if (k < end - 1) { z = -s * sub[k + 1]; sub[k + 1] = c * sub[k + 1]; }
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const double xi = Q(i, k), yi = Q(i, k + 1);
-                Q(i, k) = c * xi - s * yi;
-                Q(i, k + 1) = s * xi + c * yi;
+            if (k == 0) {
+                VMP_EIG_ROT(d0, d1, s0, 0, 1)
+                x = s0;
+                if (end == 2) { z = -s * s1; s1 = c * s1; }          // k < end - 1
+                VMP_EIG_QCOL(0, 1)
+            } else {
+                VMP_EIG_ROT(d1, d2, s1, 1, 2)
+                if (start == 0) s0 = c * s0 - s * z;                  // k > start
+                x = s1;
+                VMP_EIG_QCOL(1, 2)
             }
         }
     }
+#undef VMP_EIG_ROT
+#undef VMP_EIG_QCOL
     if (iter <= 90) {
-        for (int i = 0; i < 2; ++i) {
-            int k = 0; double best = diag[i];
-            for (int j = 1; j < 3 - i; ++j) if (diag[i + j] < best) { best = diag[i + j]; k = j; }
-            if (k > 0) {
-                const double t = diag[i]; diag[i] = diag[k + i]; diag[k + i] = t;
-#pragma unroll
-                for (int r = 0; r < 3; r++) { const double u = Q(r, i); Q(r, i) = Q(r, k + i); Q(r, k + i) = u; }
-            }
+        {   // i = 0: the smallest of (d0, d1, d2) to the front
+            int k = 0; double best = d0;
+            if (d1 < best) { best = d1; k = 1; }
+            if (d2 < best) { best = d2; k = 2; }
+            if (k == 1) { const double t = d0; d0 = d1; d1 = t; for (int r = 0; r < 3; r++) { const double u = Q(r, 0); Q(r, 0) = Q(r, 1); Q(r, 1) = u; } }
+            if (k == 2) { const double t = d0; d0 = d2; d2 = t; for (int r = 0; r < 3; r++) { const double u = Q(r, 0); Q(r, 0) = Q(r, 2); Q(r, 2) = u; } }
         }
+        if (d2 < d1) { const double t = d1; d1 = d2; d2 = t; for (int r = 0; r < 3; r++) { const double u = Q(r, 1); Q(r, 1) = Q(r, 2); Q(r, 2) = u; } }
     }
+    double diag[3] = {d0, d1, d2};
     evals[0] = diag[0] * sc; evals[1] = diag[1] * sc; evals[2] = diag[2] * sc;
     evecs = Q;
 }
