@@ -213,6 +213,8 @@ __device__ __forceinline__ void undo_log(const DevMap& m, int e, int slot, doubl
 }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// component i of a vector held in registers (v[i] with a run-time i would move the vector to local memory)
+__device__ __forceinline__ double sel3(const V3& v, int i) { return i == 0 ? v[0] : i == 1 ? v[1] : v[2]; }
 
 // VoxelGrid::merge() of voxel A at time t, executed by the whole warp.  Returns the number of
 // successful pair merges; changed[0..n) (warp-uniform) are the neighbour slots that were modified.
@@ -309,7 +311,7 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
         if (lane < 4) { const double c1 = (b1 * w0 + a1 * w1) / den; a1 = c1; cb[32 + lane] = c1; }
         if (-dot(nm, nn) < 0.0) nn = neg(nn);
         mA = nm; nA = nn;
-        if (lane < 3) { m.hot[(size_t)Bd * 8 + lane] = nm[lane]; m.hot[(size_t)Bd * 8 + 3 + lane] = nn[lane]; }
+        if (lane < 3) { m.hot[(size_t)Bd * 8 + lane] = sel3(nm, lane); m.hot[(size_t)Bd * 8 + 3 + lane] = sel3(nn, lane); }
         if (lane == 0) {
             m.sgroup[Bd] = gA;
             atomicAdd((unsigned long long*)&ctl->st.n_merge, 1ull);
@@ -321,7 +323,7 @@ __device__ int merge_at_warp(const DevMap& m, DevCtl* ctl, int A, int t, unsigne
     if (nchg > 0) {
         ca[lane] = a0;
         if (lane < 4) ca[32 + lane] = a1;
-        if (lane < 3) { m.hot[(size_t)A * 8 + lane] = mA[lane]; m.hot[(size_t)A * 8 + 3 + lane] = nA[lane]; }
+        if (lane < 3) { m.hot[(size_t)A * 8 + lane] = sel3(mA, lane); m.hot[(size_t)A * 8 + 3 + lane] = sel3(nA, lane); }
         if (lane == 0) m.hot[(size_t)A * 8 + 6] = __longlong_as_double(ra.w6 | (long long)F_MERGED);
     }
     undo_close(m, __shfl_sync(0xffffffffu, ubase_l0, 0), nchg > 0 ? nchg + 1 : 0);
@@ -638,8 +640,9 @@ __device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t
         const long long w6b = rb.w6 | (long long)F_MERGED;
         __syncwarp();
         if (lane < 3) {
-            m.hot[(size_t)Bd * 8 + lane] = nm[lane]; m.hot[(size_t)Bd * 8 + 3 + lane] = nn[lane];
-            rb.mean[lane] = nm[lane]; rb.nrm[lane] = nn[lane];
+            const double nml = sel3(nm, lane), nnl = sel3(nn, lane);
+            m.hot[(size_t)Bd * 8 + lane] = nml; m.hot[(size_t)Bd * 8 + 3 + lane] = nnl;
+            rb.mean[lane] = nml; rb.nrm[lane] = nnl;
         }
         if (lane == 0) {
             m.sgroup[Bd] = gA;
@@ -656,8 +659,9 @@ __device__ int merge_at_cells(const DevMap& m, DevCtl* ctl, CellRec* cell, int t
         ca[lane] = a0;
         if (lane < 4) ca[32 + lane] = a1;
         if (lane < 3) {
-            m.hot[(size_t)A * 8 + lane] = mA[lane]; m.hot[(size_t)A * 8 + 3 + lane] = nA[lane];
-            cell[0].mean[lane] = mA[lane]; cell[0].nrm[lane] = nA[lane];
+            const double mal = sel3(mA, lane), nal = sel3(nA, lane);
+            m.hot[(size_t)A * 8 + lane] = mal; m.hot[(size_t)A * 8 + 3 + lane] = nal;
+            cell[0].mean[lane] = mal; cell[0].nrm[lane] = nal;
         }
         if (lane == 0) {
             cell[0].w6 |= (long long)F_MERGED;
