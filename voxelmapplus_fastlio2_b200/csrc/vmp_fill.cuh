@@ -580,7 +580,10 @@ __device__ void fill_voxel(const DevMap& m, const DevScan& s, DevCtl* ctl, int s
                 double* cv = m.cov + (size_t)slot * 36;
                 cv[lane] = ra.acc0;
                 if (lane < 4) cv[32 + lane] = ra.acc1;
-                if (lane < 3) { m.hot[(size_t)slot * 8 + 3 + lane] = ra.nrm[lane]; m.center[(size_t)slot * 3 + lane] = ra.ctr[lane]; }
+                if (lane < 3) {      // (selects: a lane-indexed ra.nrm[lane] would move the accumulator struct to local memory)
+                    m.hot[(size_t)slot * 8 + 3 + lane] = lane == 0 ? ra.nrm[0] : lane == 1 ? ra.nrm[1] : ra.nrm[2];
+                    m.center[(size_t)slot * 3 + lane] = lane == 0 ? ra.ctr[0] : lane == 1 ? ra.ctr[1] : ra.ctr[2];
+                }
             }
             if (lane == 0) {
                 hot_set_fn(m.hot, slot, flags, n);
