@@ -45,6 +45,31 @@ def test_map_update_bitexact_merge(oracle_mod, seed):
     assert merges > 0, "workload did not exercise merge()"
 
 
+@pytest.mark.parametrize("voxel_size", [0.3, 0.7])
+def test_voxel_sizes_that_are_not_powers_of_two(oracle_mod, voxel_size):
+    """The voxel key is floor(p / voxel_size) (voxel_map.cpp:194-198).  For the power-of-two sizes of the BASELINE configurations the
+    device multiplies by the exact reciprocal (the same value bit for bit); any other size takes the division.  Keys, correspondences and
+    maps stay bit-exact on that path too: map update on the oracle's world points, and one measurement pass per scan."""
+    o, g = _pair(oracle_mod, voxel_size=voxel_size, max_points_per_scan=4096)
+    for s, (p, c) in enumerate(wall_workload(21, scans=14, pts=3000)):
+        so, sg = (o.map_update(p, c), g.map_update(p, c)) if s else (o.map_build(p, c), g.map_build(p, c))
+        assert so == sg, f"scan {s}: counters differ\n{so}\n{sg}"
+    assert_maps_equal(o.dump_map(), g.dump_map(), exact=True, what=f"voxel_size {voxel_size}")
+    # points on and next to voxel faces: the keys of the measurement pass
+    rng = np.random.default_rng(5)
+    k = rng.integers(-12, 12, (3000, 3)).astype(np.float64)
+    pts = (k * voxel_size + rng.choice([0.0, 1e-7, -1e-7, 0.4 * voxel_size], (3000, 3))).astype(np.float32)
+    from voxelmapplus_fastlio2_b200.ctypes_defs import VmpState
+    x0 = VmpState.identity()
+    P0 = np.eye(23) * 1e-4
+    for h in (o, g):
+        h.set_scan(pts)
+        h.measure(x0, P0)
+    co, cg = o.dump_correspondences(len(pts)), g.dump_correspondences(len(pts))
+    assert np.array_equal(co["keys"], cg["keys"]) and np.array_equal(co["status"], cg["status"])
+    assert (co["status"] & 1).any()                       # some of the probes hit voxels of the map
+
+
 def test_map_update_default_thresholds(oracle_mod):
     o, g = _pair(oracle_mod, max_points_per_scan=4096)
     for s, (p, c) in enumerate(wall_workload(11, scans=25, pts=3000)):

@@ -402,6 +402,11 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     m.pool = cfg->map_capacity + nmax + 1024;
     m.maxpt = cfg->max_point_thresh; m.upt = cfg->update_size_thresh; m.capacity = cfg->map_capacity;
     m.plane_thresh = cfg->plane_thresh; m.voxel_size = cfg->voxel_size;
+    {   // power-of-two voxel size: the key's divisions are exact scalings (vmp_device.cuh voxel_index)
+        int ex = 0;
+        const double mant = std::frexp(cfg->voxel_size, &ex);
+        m.voxel_inv = (mant == 0.5 && ex > -60 && ex < 60) ? 1.0 / cfg->voxel_size : 0.0;
+    }
     m.merge_cap = 2048;
     if (const char* e = getenv("VMP_MERGE_CAP")) m.merge_cap = std::max(1, std::min(2048, atoi(e)));      // test knob
     m.merge_max_depth = 7;          // (cascade depths saturate at 7: the depth test of the merge rounds is off unless the test knob sets it)

@@ -154,6 +154,7 @@ struct DevMap {
     int merge_cap;                      // active-set size up to which the merge phase runs its parallel rounds (<= MERGE_CAP); beyond: serial mode
     int merge_max_depth;                // test knob (VMP_MERGE_MAX_DEPTH): a merge deeper than this in a cascade sends the scan to the serial redo
     int* undo_slot; double* undo_rec; int undo_cap;      // undo log of the merge phase (vmp_merge.cuh)
+    double voxel_inv;                   // 1 / voxel_size when voxel_size is a power of two (exact), else 0 (voxel_index divides)
     int heavy_points;                   // k_fill: voxels whose refits of a scan loop over at least this many stored points take the CTA path (0: never)
     double plane_thresh, voxel_size, th_angle, th_dist;
     // slots
@@ -250,8 +251,13 @@ __host__ __device__ __forceinline__ unsigned hash_key(unsigned long long k) {
 // voxel here: the filter treats them like "voxel not in the map" (Q2), the map update skips and counts them (the reference
 // would give them isolated far-away voxels; (long long)floor(NaN) is INT64_MIN on x86 but 0 on the device, hence the
 // explicit range test on the floating-point value).
-__device__ __forceinline__ bool voxel_index(double x, double y, double z, double vs, unsigned long long& pk) {
-    const double fx = floor(x / vs), fy = floor(y / vs), fz = floor(z / vs);
+// inv != 0: voxel_size is a power of two (0.5 m, 0.25 m ... the BASELINE configurations) and inv = 1 / voxel_size, itself a power of
+// two: x * inv IS x / voxel_size, bit for bit (both are exact scalings), and three division sequences per point and iteration - a tenth
+// of the measurement pass's instructions - become three multiplications.  Any other voxel size takes the division (inv = 0).
+__device__ __forceinline__ bool voxel_index(double x, double y, double z, double vs, unsigned long long& pk, double inv = 0.0) {
+    double fx, fy, fz;
+    if (inv != 0.0) { fx = floor(x * inv); fy = floor(y * inv); fz = floor(z * inv); }
+    else { fx = floor(x / vs); fy = floor(y / vs); fz = floor(z / vs); }
     const double lim = 1048576.0;
     if (!(fx >= -lim && fx < lim && fy >= -lim && fy < lim && fz >= -lim && fz < lim)) { pk = KEY_EMPTY; return false; }   // false for NaN
     const long long kx = (long long)fx, ky = (long long)fy, kz = (long long)fz;

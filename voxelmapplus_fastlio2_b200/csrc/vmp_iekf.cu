@@ -201,7 +201,7 @@ __device__ __forceinline__ void measure_pass(MeasShared<EXT>& sh, const DevMap& 
             const V3 pw = add(mul(ms.r_wl, pl), ms.p_wl);
             unsigned long long pk;
             int slot = -1;
-            if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk)) slot = (pk == pk_prev) ? slot_prev : hash_find(m, pk);
+            if (voxel_index(pw[0], pw[1], pw[2], m.voxel_size, pk, m.voxel_inv)) slot = (pk == pk_prev) ? slot_prev : hash_find(m, pk);
             if (FIRST || slot != slot_prev) s.rslot[i] = slot;
             if (!FIRST) {                                  // fetched up front: one memory latency less on the chain
 #pragma unroll

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) k_world_insert_count(DevMap m, DevScan s,
             } else {
                 w[0] = s.pw[3 * (size_t)i]; w[1] = s.pw[3 * (size_t)i + 1]; w[2] = s.pw[3 * (size_t)i + 2];
             }
-            have = voxel_index(w[0], w[1], w[2], m.voxel_size, pk);
+            have = voxel_index(w[0], w[1], w[2], m.voxel_size, pk, m.voxel_inv);
             if (!have) skipped++;                                   // counted skip (see voxel_index), not an error
         }
         // keys are 63-bit, so the all-ones prefix makes the lanes without a voxel distinct from every key and from each other
