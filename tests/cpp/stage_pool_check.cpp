@@ -1,0 +1,49 @@
+// CPU check of vmp::StagePool (voxelmapplus_fastlio2_b200/csrc/vmp_stage.hpp): the helper-thread copy of a scan into the staging
+// area and the time-order check of a raw scan that rides along (lio_builder.cpp:75 sorts a scan whose points are out of order).
+// Built and run by tests/test_stage_pool.py; prints "ok" or the first failed expectation.
+#include <cstdint>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+#include "../../voxelmapplus_fastlio2_b200/csrc/vmp_stage.hpp"
+
+static int fails = 0;
+#define EXPECT(c) do { if (!(c)) { std::printf("FAILED line %d: %s\n", __LINE__, #c); fails++; } } while (0)
+
+int main() {
+    std::mt19937_64 rng(7);
+    for (int threads : {0, 1, 3, 11}) {
+        setenv("VMP_COPY_THREADS", std::to_string(threads).c_str(), 1);
+        vmp::StagePool pool;
+        // plain copies of every size class: below the parallel threshold, odd tails, several MB
+        for (size_t bytes : {size_t(0), size_t(1), size_t(4095), size_t(512 * 1024 - 1), size_t(512 * 1024), size_t(600 * 1024 + 7), size_t(3200000), size_t(9999991)}) {
+            std::vector<uint8_t> src(bytes + 8), dst(bytes + 8, 0xAB);
+            for (auto& b : src) b = (uint8_t)rng();
+            EXPECT(pool.copy(dst.data(), src.data(), bytes));
+            EXPECT(std::memcmp(dst.data(), src.data(), bytes) == 0);
+            for (size_t k = bytes; k < bytes + 8; k++) EXPECT(dst[k] == 0xAB);          // nothing past the end
+        }
+        // raw scans: records of 4 floats, the last one a time offset
+        for (int n : {1, 2, 1000, 40000, 200000, 333333}) {
+            std::vector<float> src(4 * (size_t)n), dst(4 * (size_t)n);
+            for (int i = 0; i < n; i++) { src[4 * i] = (float)i; src[4 * i + 1] = 1.f; src[4 * i + 2] = 2.f; src[4 * i + 3] = (float)(i / 3) * 0.01f; }   // non-decreasing, with ties
+            EXPECT(pool.copy(dst.data(), src.data(), src.size() * 4, 4));
+            EXPECT(dst == src);
+            if (n >= 2) {
+                // one inversion anywhere (also across the boundary of two helpers' parts) is found
+                for (int trial = 0; trial < 6; trial++) {
+                    const int k = trial == 0 ? 1 : trial == 1 ? n - 1 : 1 + (int)(rng() % (uint64_t)(n - 1));
+                    const float keep = src[4 * k + 3];
+                    src[4 * k + 3] = src[4 * (k - 1) + 3] - 1.0f;
+                    EXPECT(!pool.copy(dst.data(), src.data(), src.size() * 4, 4));
+                    EXPECT(dst == src);                                             // the copy itself is complete either way
+                    src[4 * k + 3] = keep;
+                }
+                EXPECT(pool.copy(dst.data(), src.data(), src.size() * 4, 4));
+            }
+        }
+    }
+    if (!fails) std::printf("ok\n");
+    return fails ? 1 : 0;
+}

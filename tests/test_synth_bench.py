@@ -61,3 +61,16 @@ def test_algorithmic_bytes_model():
     assert map_update_bytes(st) == total
     assert bench.config_dict(bench.WORKLOADS["c2"], 40) == bench.config_dict(bench.WORKLOADS["c2"], 40)
     assert bench.DEFAULT_WORKLOAD == "c2" and bench.WORKLOADS["c2"]["pts"] == 200000 and bench.WORKLOADS["c2"]["max_iter"] == 4
+
+
+def test_bench_stdout_carries_only_the_json_line():
+    """bench.py's contract is ONE JSON line on stdout; whatever libraries print there (NCCL's version banner under torchrun) is sent to
+    stderr by claim_stdout()."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); print('library noise'); os.write(1, b'raw noise\\n'); "
+            "bench.emit_line({'metric': 'scans_per_s', 'value': 1.0})" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout == '{"metric": "scans_per_s", "value": 1.0}\n'
+    assert "library noise" in r.stderr and "raw noise" in r.stderr
