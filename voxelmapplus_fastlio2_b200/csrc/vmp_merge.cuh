@@ -830,11 +830,10 @@ struct MergeShared {                    // dynamic shared memory of k_merge_roun
 // Rank 0 alone does the bookkeeping between the rounds (readiness, compaction) and, if it comes to that, the serial redo.
 constexpr int MERGE_CLUSTER = 4;
 
-__device__ __forceinline__ void merge_cluster_sync(cg::cluster_group& cluster) {
-    __threadfence();            // the events write voxels (global memory) that events on the other SMs of the cluster read in later rounds
-    cluster.sync();
-    __threadfence();
-}
+// The events write voxels (global memory) that events on the other SMs of the cluster read in later rounds.  cluster.sync() is
+// barrier.cluster.arrive.release + wait.acquire: in SASS MEMBAR.ALL.GPU in front of UCGABAR_ARV and CCTL.IVALL (L1 invalidate) behind
+// UCGABAR_WAIT (profiles/sass_r02_k_merge_rounds.txt) - a __threadfence() on either side of it only repeated that.
+__device__ __forceinline__ void merge_cluster_sync(cg::cluster_group& cluster) { cluster.sync(); }
 
 __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
     extern __shared__ __align__(16) unsigned char merge_smem[];
