@@ -409,6 +409,8 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     }
     m.merge_cap = 2048;
     if (const char* e = getenv("VMP_MERGE_CAP")) m.merge_cap = std::max(1, std::min(2048, atoi(e)));      // test knob
+    m.merge_r = 4;                  // MERGE_R of vmp_merge.cuh
+    if (const char* e = getenv("VMP_MERGE_R")) m.merge_r = std::max(3, std::min(8, atoi(e)));      // test knob: 3 = exact radius (late activations do occur)
     m.merge_max_depth = 7;          // (cascade depths saturate at 7: the depth test of the merge rounds is off unless the test knob sets it)
     if (const char* e = getenv("VMP_MERGE_MAX_DEPTH")) m.merge_max_depth = atoi(e);     // test knob: -1 forces the exact serial redo after the first merge
     m.undo_cap = 65536;             // seven entries per executed event

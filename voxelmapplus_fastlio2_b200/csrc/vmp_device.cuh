@@ -152,6 +152,7 @@ struct DevMap {
     // parameters
     int pool, maxpt, upt, capacity;
     int merge_cap;                      // active-set size up to which the merge phase runs its parallel rounds (<= MERGE_CAP); beyond: serial mode
+    int merge_r;                        // conflict radius of the merge rounds (MERGE_R = 4; test knob VMP_MERGE_R = 3 is the exact radius and makes late activations happen)
     int merge_max_depth;                // test knob (VMP_MERGE_MAX_DEPTH): a merge deeper than this in a cascade sends the scan to the serial redo
     int* undo_slot; double* undo_rec; int undo_cap;      // undo log of the merge phase (vmp_merge.cuh)
     double voxel_inv;                   // 1 / voxel_size when voxel_size is a power of two (exact), else 0 (voxel_index divides)

@@ -401,7 +401,7 @@ __device__ void as_activate(const DevMap& m, DevCtl* ctl, const SetView& sv, int
         const int hn = as.hn < MERGE_HIST ? as.hn : MERGE_HIST;
         bool late = false;
         for (int k = lane; k < hn; k += 32)
-            if (as.ht[k] > nt && abs(as.hx[k] - yx) + abs(as.hy[k] - yy) + abs(as.hz[k] - yz) <= MERGE_R) late = true;
+            if (as.ht[k] > nt && abs(as.hx[k] - yx) + abs(as.hy[k] - yy) + abs(as.hz[k] - yz) <= m.merge_r) late = true;
         if (late) *sv.redo = 1;
     }
     if (lane == 0) {
@@ -878,6 +878,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
         // Two cluster barriers per round.  Rank 0 prepares the round (compaction of the previous one, readiness) while the other CTAs
         // wait at barrier A; everybody executes events up to barrier B.  The shared counters are written by rank 0 between B and the
         // next A only, and read by the others between A and B only.
+        const int merge_r = m.merge_r;
         for (int round = 0; round < 100000; round++) {
             if (rank == 0) {
                 if (round == 0) { if (tid == 0) S.s_cnt = n0; }
@@ -909,7 +910,7 @@ __global__ void __launch_bounds__(512) k_merge_rounds(DevMap m, DevCtl* ctl) {
                     const int x = S.as.kx[j], y = S.as.ky[j], z = S.as.kz[j];
                     bool conflict = false;
                     for (int i = lane; i < n; i += 32)
-                        if (S.as.t[i] < tj && abs(S.as.kx[i] - x) + abs(S.as.ky[i] - y) + abs(S.as.kz[i] - z) <= MERGE_R) conflict = true;
+                        if (S.as.t[i] < tj && abs(S.as.kx[i] - x) + abs(S.as.ky[i] - y) + abs(S.as.kz[i] - z) <= merge_r) conflict = true;
                     if (!__any_sync(0xffffffffu, conflict) && lane == 0) {
                         S.as.rlist[atomicAdd(&S.s_nready, 1)] = (short)j;
                         const int h = atomicAdd(&S.as.hn, 1);                     // started: remembered for the activation check
