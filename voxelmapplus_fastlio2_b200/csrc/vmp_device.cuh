@@ -69,7 +69,7 @@ struct DevCtl {
     int err;
     int pad0;
     unsigned ticket;                    // arrival counter of k_measure's measurement CTAs (the solver CTA waits on it)
-    unsigned long long iter_pub;        // k_iekf_loop: 8 * scan sequence number + executed iterations, released by the solver CTA
+    unsigned long long iter_pub;        // k_iekf_loop: 2 * (8 * scan sequence number + executed iterations) + stop flag, released by the solver CTA
     int fill_next;                      // next touched voxel to be handed to a warp of k_fill
     int n_undo;                         // entries of the merge undo log of this update
     int n_heavy, heavy_next;            // voxels of this update that go to the CTA path of k_fill, and the next one to be handed out

@@ -337,9 +337,10 @@ k_iekf_loop(DevMap m, DevScan s, DevFilter* f, DevCtl* ctl, double* partials, co
     for (int it = 0; it < 8; it++) {
         if (it == 0) measure_pass<EXT, true>(sh, m, s, f, ctl, partials, pb, npb, in, 0);
         else {
-            if (threadIdx.x == 0) {
-                while (ld_acquire_u64(&ctl->iter_pub) < base + (unsigned long long)it) __nanosleep(20);
-                s_stop = *(volatile int*)&ctl->done;
+            if (threadIdx.x == 0) {       // iter_pub = 2 * (base + executed iterations) + stop flag: one look-up tells both
+                unsigned long long v;
+                while (((v = ld_acquire_u64(&ctl->iter_pub)) >> 1) < base + (unsigned long long)it) __nanosleep(20);
+                s_stop = (int)(v & 1ull);
             }
             __syncthreads();
             if (s_stop) break;

@@ -350,7 +350,7 @@ __device__ void ieskf_solve_cta(SolveShared<EXT>& S, DevFilter* f, DevCtl* ctl, 
     if (tid < 36) f->x[tid] = sx[tid];
     if (publish) {      // k_iekf_loop: hand the new state (and ctl->done) to the measurement CTAs spinning on iter_pub
         __syncthreads();
-        if (tid == 0) { __threadfence(); st_release_u64(&ctl->iter_pub, publish); }
+        if (tid == 0) { __threadfence(); st_release_u64(&ctl->iter_pub, publish * 2ull + (s_last ? 1ull : 0ull)); }      // (the loop's stop flag rides in bit 0)
     }
     long long tC = tX;
     if (s_last) {
