@@ -24,6 +24,37 @@ int main() {
             EXPECT(std::memcmp(dst.data(), src.data(), bytes) == 0);
             for (size_t k = bytes; k < bytes + 8; k++) EXPECT(dst[k] == 0xAB);          // nothing past the end
         }
+        // the same copy in two halves (vmp_scan launches the graph between them): the helpers' parts run while the caller is elsewhere
+        for (size_t bytes : {size_t(100), size_t(600 * 1024 + 7), size_t(3200000)}) {
+            std::vector<uint8_t> src(bytes + 8), dst(bytes + 8, 0xCD);
+            for (auto& b : src) b = (uint8_t)rng();
+            for (int rep = 0; rep < 20; rep++) {
+                pool.begin(dst.data(), src.data(), bytes);
+                volatile uint64_t sink = 0;
+                for (int k = 0; k < 1000 * (rep % 4); k++) sink += rng();                 // the caller's own work of varying length
+                EXPECT(pool.end());
+                EXPECT(std::memcmp(dst.data(), src.data(), bytes) == 0);
+                src[rep % bytes] ^= 0x5A;
+            }
+            for (size_t k = bytes; k < bytes + 8; k++) EXPECT(dst[k] == 0xCD);
+        }
+        // chunked copy: the helpers run through all chunks on their own, the caller picks the chunks up in order
+        for (size_t bytes : {size_t(1000), size_t(300 * 1024 + 5), size_t(2400000), size_t(9999991)}) {
+            for (size_t chunk : {size_t(384) * 800, size_t(1) << 20, bytes + 1}) {
+                std::vector<uint8_t> src(bytes + 8), dst(bytes + 8, 0xEF);
+                for (auto& b : src) b = (uint8_t)rng();
+                pool.begin_chunks(dst.data(), src.data(), bytes, chunk);
+                int c = 0;
+                for (size_t off = 0; off < bytes; off += chunk, c++) {
+                    pool.wait_chunk(c);
+                    const size_t len = std::min(chunk, bytes - off);
+                    EXPECT(std::memcmp(dst.data() + off, src.data() + off, len) == 0);         // chunk c is complete once wait_chunk returns
+                }
+                pool.end_chunks();
+                for (size_t k = bytes; k < bytes + 8; k++) EXPECT(dst[k] == 0xEF);
+                EXPECT(pool.copy(dst.data(), src.data(), bytes));                              // the other kinds of job still work afterwards
+            }
+        }
         // raw scans: records of 4 floats, the last one a time offset
         for (int n : {1, 2, 1000, 40000, 200000, 333333}) {
             std::vector<float> src(4 * (size_t)n), dst(4 * (size_t)n);

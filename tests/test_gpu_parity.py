@@ -404,6 +404,50 @@ def test_resident_iteration_loop_is_identical(monkeypatch, estimate_ext):
     assert_maps_equal(a.map.dump_map(), b.map.dump_map(), exact=True, what="resident loop vs one launch per iteration")
 
 
+@pytest.mark.parametrize("chunk_min,pipelined,loop", [(32768, False, "1"), (4096, False, "1"), (4096, True, "1"), (4096, False, "0")])
+def test_streamed_upload_is_identical(monkeypatch, chunk_min, pipelined, loop):
+    """Streamed upload (VMP_UPLOAD_GATE=1; an experiment that is off by default): vmp_scan with a pageable pointer launches the
+    graph behind the FIRST chunk of points; the other chunks travel on their own stream while the first measurement pass runs and
+    release its waiting warps one by one (DevCtl::up_pub, written by a stream memory operation behind each chunk).  Only loads are
+    delayed: posterior, counters and map are those of the plain upload (the graph waits for all of it), bit for bit.
+    VMP_UPLOAD_CHUNK_MIN makes small scans travel in chunks."""
+    cfg = default_config(max_points_per_scan=8192)
+    monkeypatch.setenv("VMP_UPLOAD_CHUNK_MIN", str(chunk_min))
+    monkeypatch.setenv("VMP_IEKF_LOOP", loop)
+    monkeypatch.setenv("VMP_UPLOAD_GATE", "1")
+    a = HotPath(cfg)
+    monkeypatch.delenv("VMP_UPLOAD_GATE")
+    b = HotPath(cfg)
+    monkeypatch.delenv("VMP_UPLOAD_CHUNK_MIN"); monkeypatch.delenv("VMP_IEKF_LOOP")
+    if pipelined:
+        a.set_pipelined(True)
+    lio = LIOBuilder(cfg, device_undistort=False)          # produces priors and compensated clouds
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=6000))
+    n = 0
+    for pk in seq.packages(30):
+        cloud = pk.cloud.copy()
+        st = lio.process(pk.imus, cloud, pk.t0, pk.t1)
+        _, _, status = lio.state()
+        if status < 2:
+            continue
+        x0, P0 = lio.prior()
+        xyz = np.ascontiguousarray(cloud[:, :3])
+        if st.iters == 0:
+            a.first_scan(x0, P0, xyz); b.first_scan(x0, P0, xyz)
+            continue
+        xa, Pa, sa = a.scan(x0, P0, xyz)
+        xb, Pb, sb = b.scan(x0, P0, xyz)
+        assert bytes(xa) == bytes(xb) and np.array_equal(Pa, Pb) and sa.iters == sb.iters
+        assert list(sa.effect_num) == list(sb.effect_num)
+        if not pipelined:
+            assert sa.map.as_dict() == sb.map.as_dict()
+        n += 1
+    assert n >= 20
+    if pipelined:
+        a.sync()
+    assert_maps_equal(a.dump_map(), b.dump_map(), exact=True, what="streamed upload")
+
+
 def test_staged_scan_is_identical():
     """vmp_scan_buffer + vmp_scan_staged (points written straight into the pinned staging) == vmp_scan, bit for bit."""
     cfg = default_config(max_points_per_scan=8192)

@@ -106,6 +106,14 @@ struct vmp_handle_t {
     int graph_pred_kernels = 0;
     DevPredictIn* h_pred = nullptr; DevPredictIn* d_pred = nullptr;      // IMU steps of the scan (pinned / device)
     unsigned long long seq = 0;
+    // streamed upload of vmp_scan (pageable pointer): chunk 0 and the graph go to `stream`, the other chunks to `up_st`, each followed by a
+    // stream memory operation (cuStreamWriteValue64, taken from the driver at run time) that tells the running first measurement pass it is there
+    cudaStream_t up_st = nullptr;
+    void* write_value64 = nullptr;
+    bool upload_gate = false;
+    int gate_chunks = 8;                 // chunks of a streamed upload (VMP_UPLOAD_CHUNKS)
+    bool upload_trace = false;           // VMP_UPLOAD_TRACE=1: host-side timeline of every 16th streamed upload on stderr
+    size_t chunk_min = 1u << 20;         // point bytes from which a pageable scan is staged / uploaded in 4 chunks (8 from four times that)
     bool pipelined = false;              // vmp_set_pipelined: vmp_scan returns when the posterior is out, the map update runs on
     bool map_pending = false;            // a map update whose MapOut has not been consumed yet
     cudaEvent_t pe0[2] = {nullptr, nullptr}, pe1[2] = {nullptr, nullptr};
@@ -142,7 +150,7 @@ int dalloc(vmp_handle_t* h, T** p, size_t count) {
 
 int check_device_err(vmp_handle_t* h, int err) {
     if (!err) return VMP_OK;
-    set_error("device reported error bits 0x%x:%s%s%s%s%s%s%s%s%s%s", err,
+    set_error("device reported error bits 0x%x:%s%s%s%s%s%s%s%s%s%s%s", err,
               (err & E_KEY_RANGE) ? " (key range);" : "",
               (err & E_POOL) ? " voxel slot pool exhausted;" : "",
               (err & E_LRU_EXHAUSTED) ? " map_capacity smaller than the voxels one scan touches (LRU victim was touched in the same scan);" : "",
@@ -152,7 +160,8 @@ int check_device_err(vmp_handle_t* h, int err) {
               (err & E_MERGE_DEPTH) ? " merge phase: serial redo needed but the undo log had overflowed;" : "",
               (err & E_MERGE_CAP) ? " (merge cap);" : "",
               (err & E_LOG_CAP) ? " LRU log full;" : "",
-              (err & E_FILL_CAP) ? " refit job / contribution staging exhausted;" : "");
+              (err & E_FILL_CAP) ? " refit job / contribution staging exhausted;" : "",
+              (err & E_UPLOAD) ? " a chunk of the streamed scan upload never arrived;" : "");
     (void)h;
     return VMP_ERR_CAPACITY;
 }
@@ -391,6 +400,18 @@ int vmp_create(const vmp_config* cfg, vmp_handle* out) {
     *out = h;       // so that a failed create can still be destroyed by the caller
     VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side.st, cudaStreamNonBlocking));
+    VMP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->up_st, cudaStreamNonBlocking));
+    {
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) h->write_value64 = fn;
+        else cudaGetLastError();
+        h->upload_gate = false;
+        if (const char* e = getenv("VMP_UPLOAD_CHUNK_MIN")) { const long v = atol(e); if (v >= 4096) h->chunk_min = (size_t)v; }      // test knob: chunked uploads of small scans
+        if (const char* e = getenv("VMP_UPLOAD_CHUNKS")) { const int v = atoi(e); if (v >= 2 && v <= 16) h->gate_chunks = v; }
+        if (const char* e = getenv("VMP_UPLOAD_TRACE")) h->upload_trace = atoi(e) != 0;
+        if (const char* e = getenv("VMP_UPLOAD_GATE")) h->upload_gate = h->write_value64 != nullptr && atoi(e) != 0;       // A/B and test knob: 1 = streamed upload
+    }
     for (auto& e : h->side.ev) VMP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : h->ev_so) VMP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     VMP_CUDA_CHECK(cudaEventCreate(&h->ev0));
@@ -569,6 +590,7 @@ int vmp_destroy(vmp_handle h) {
     for (auto& e : h->side.ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_so) if (e) cudaEventDestroy(e);
     if (h->side.st) cudaStreamDestroy(h->side.st);
+    if (h->up_st) cudaStreamDestroy(h->up_st);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VMP_OK;
@@ -661,7 +683,7 @@ int vmp_set_scan(vmp_handle h, const float* pts, int n) {
     if (r) return r;
     if (n > 0 && !pts) { set_error("vmp_set_scan: null input"); return VMP_ERR_INVALID_ARG; }
     std::memcpy(h->h_raw, pts, sizeof(float) * 3 * (size_t)n);
-    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->seq = ++h->seq; h->h_in->n = n; h->h_in->mode = 0;
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->gate_pts = 0; h->h_in->seq = ++h->seq; h->h_in->n = n; h->h_in->mode = 0;
     h->h_in->n_poses = 0; h->h_in->stride = 3;
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, PTS_OFF + sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     h->n_last = n;
@@ -699,20 +721,74 @@ int vmp_measure(vmp_handle h, const vmp_state* x, const double* P, double* H, do
 static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t upload_bytes, vmp_scan_stats* stats, bool raw = false,
                        const void* src = nullptr, int check_stride = 0, bool predict = false) {
     const bool pipe = h->pipelined && !h->prof_on;
+    const auto t_call = std::chrono::steady_clock::now();
     const unsigned long long seq = ++h->seq;
-    h->h_in->seq = seq; h->h_in->n = n;
+    h->h_in->seq = seq; h->h_in->n = n; h->h_in->gate_pts = 0;
     const int eb = (int)(seq & 1);
     VMP_CUDA_CHECK(cudaEventRecord(h->pe0[eb], h->stream));
     if (predict) VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_pred, h->h_pred, sizeof(DevPredictIn), cudaMemcpyHostToDevice, h->stream));
+    bool launched = false;
     if (!src) {
         VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
     } else {
         const size_t pts_bytes = upload_bytes - PTS_OFF;
         const size_t rec = check_stride > 0 ? sizeof(float) * (size_t)check_stride : sizeof(float) * 3;
-        const int nchunk = pts_bytes >= (4u << 20) ? 8 : pts_bytes >= (1u << 20) ? 4 : 1;
-        const size_t per = ((pts_bytes / rec + nchunk - 1) / nchunk) * rec;
+        int nchunk = pts_bytes >= 4 * h->chunk_min ? 8 : pts_bytes >= h->chunk_min ? 4 : 1;
+        // Plain scans: the helpers stage chunk after chunk WITHOUT waiting for this thread (begin_chunks), which only ships what is ready.
+        // STREAMED upload (VMP_UPLOAD_GATE=1, off by default - measured, it does not pay): the graph is launched behind chunk 0; the
+        // other chunks travel on their own stream while the first measurement pass is already running, and a stream memory operation behind each
+        // of them (DevCtl::up_pub) releases the warps that wait for its points.
+        const bool chunked = nchunk > 1 && check_stride == 0;
+        const bool gate = chunked && h->upload_gate && !raw && !predict && !h->prof_on;
+        if (gate) nchunk = h->gate_chunks;
+        size_t nrec_per = (pts_bytes / rec + nchunk - 1) / nchunk;
+        if (gate) nrec_per = (nrec_per + 31) / 32 * 32;                 // a warp's 32 points never straddle two chunks
+        const size_t per = nrec_per * rec;
+        if (gate) h->h_in->gate_pts = (int)nrec_per;
         bool sorted = true;
         VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, PTS_OFF, cudaMemcpyHostToDevice, h->stream));      // header (+ prior, IMU poses)
+        if (chunked) {
+            typedef int (*WriteValue64)(cudaStream_t, unsigned long long, unsigned long long, unsigned);
+            const WriteValue64 write_value = reinterpret_cast<WriteValue64>(h->write_value64);
+            const bool trace = h->upload_trace && (seq & 15ull) == 0;
+            cudaStream_t later = gate ? h->up_st : h->stream;
+            const auto tr0 = std::chrono::steady_clock::now();
+            float tr_ready[16] = {}, tr_enq[16] = {}, tr_graph = 0.f;
+            auto tr_us = [&] { return std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - tr0).count(); };
+            h->pool.begin_chunks(h->h_raw, src, pts_bytes, per);
+            int c = 0, rr = VMP_OK;
+            cudaError_t ce = cudaSuccess;
+            for (size_t off = 0; off < pts_bytes && rr == VMP_OK && ce == cudaSuccess; off += per, c++) {
+                const size_t len = std::min(per, pts_bytes - off);
+                h->pool.wait_chunk(c);
+                if (trace) tr_ready[c] = tr_us();
+                ce = cudaMemcpyAsync(h->d_stage + PTS_OFF + off, h->h_stage + PTS_OFF + off, len, cudaMemcpyHostToDevice, c ? later : h->stream);
+                if (ce != cudaSuccess) break;
+                if (!gate) {
+                } else if (c == 0) {
+                    ce = cudaStreamWaitEvent(h->up_st, h->pe0[eb], 0);     // (pipelined mode: the previous scan's map update still reads the old points)
+                    if (ce == cudaSuccess) rr = run_scan(h, raw, n, predict);
+                    launched = true;
+                    if (trace) tr_graph = tr_us();
+                } else if (write_value(h->up_st, (unsigned long long)(uintptr_t)&h->ctl->up_pub, seq * 64ull + (unsigned long long)c, 0u) != 0) {
+                    set_error("vmp_scan: cuStreamWriteValue64 failed during the streamed upload");
+                    h->upload_gate = false;
+                    rr = VMP_ERR_CUDA;
+                }
+                if (trace) tr_enq[c] = tr_us();
+            }
+            h->pool.end_chunks();
+            if (trace) {
+                std::fprintf(stderr, "[vmp upload trace] seq %llu, %d chunks of %zu B; graph launched %.1f us; chunk ready / shipped (us):", seq, c, per, tr_graph);
+                for (int q = 0; q < c; q++) std::fprintf(stderr, " %.1f/%.1f", tr_ready[q], tr_enq[q]);
+                std::fprintf(stderr, "\n");
+            }
+            if (ce != cudaSuccess || rr != VMP_OK) {        // a launched scan gives up by itself after 2 s (E_UPLOAD)
+                cudaStreamSynchronize(h->stream);
+                if (ce != cudaSuccess) { set_error("vmp_scan: streamed upload failed: %s", cudaGetErrorString(ce)); return VMP_ERR_CUDA; }
+                return rr;
+            }
+        } else
         for (size_t off = 0; off < pts_bytes; off += per) {
             const size_t len = std::min(per, pts_bytes - off);
             sorted &= h->pool.copy((char*)h->h_raw + off, (const char*)src + off, len, check_stride);
@@ -729,12 +805,18 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
             VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage + PTS_OFF, h->h_stage + PTS_OFF, pts_bytes, cudaMemcpyHostToDevice, h->stream));
         }
     }
-    { const int rr = run_scan(h, raw, n, predict); if (rr) return rr; }
+    if (!launched) { const int rr = run_scan(h, raw, n, predict); if (rr) return rr; }
     VMP_CUDA_CHECK(cudaEventRecord(h->pe1[eb], h->stream));
     h->n_last = n;
     if (!pipe) {
         h->map_seq = seq;
         int r = finish_sync(h);
+        if (h->upload_trace && (seq & 15ull) == 0) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->pe0[eb], h->pe1[eb]);
+            std::fprintf(stderr, "[vmp upload trace] seq %llu: scan finished %.1f us after the call started; first event -> end of graph on the device %.1f us\n", seq,
+                         std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t_call).count(), ms * 1000.f);
+        }
         read_state(h, x, P, stats);
         if (stats) {
             fill_update_stats(last_mout(h).st, &stats->map);
@@ -768,7 +850,7 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
 static int scan_staged(vmp_handle h, vmp_state* x, double* P, int n, vmp_scan_stats* stats, const char* who, const float* src = nullptr) {
     if (!x || !P) { set_error("%s: null argument", who); return VMP_ERR_INVALID_ARG; }
     if (!h->map_built) { set_error("%s: no map yet (call vmp_first_scan or vmp_map_build first)", who); return VMP_ERR_STATE; }
-    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->gate_pts = 0; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
     h->h_in->n_poses = 0; h->h_in->stride = 3;
     std::memcpy(h->h_in->x, x, sizeof(double) * 36);
     std::memcpy(h->h_in->P, P, sizeof(double) * 529);
@@ -820,7 +902,7 @@ int vmp_scan_raw(vmp_handle h, vmp_state* x, double* P, float* cloud_xyzt, int n
     static_assert(sizeof(vmp_pose) == sizeof(DevPose), "vmp_pose layout");
     // the caller's cloud is staged, checked for time order (lio_builder.cpp:75) and uploaded chunk by chunk in scan_common
     std::memcpy(h->h_stage + IN_HDR, poses, sizeof(vmp_pose) * (size_t)n_poses);
-    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->gate_pts = 0; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE;
     h->h_in->n_poses = n_poses; h->h_in->stride = 4;
     std::memcpy(h->h_in->x, x, sizeof(double) * 36);
     std::memcpy(h->h_in->P, P, sizeof(double) * 529);
@@ -847,7 +929,7 @@ int vmp_scan_raw_predict(vmp_handle h, vmp_state* x_out, double* P_out, float* c
     h->h_pred->use_last = last_acc_gyro ? 1 : 0;
     if (last_acc_gyro) std::memcpy(h->h_pred->last, last_acc_gyro, sizeof(double) * 6);
     // the prior (x, P) and the IMU poses are written into the device copy of the header / staging by k_predict
-    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE | SCAN_PREDICT;
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->gate_pts = 0; h->h_in->mode = SCAN_STATE_HDR | SCAN_BEGIN_UPDATE | SCAN_PREDICT;
     h->h_in->n_poses = 0; h->h_in->stride = 4;
     r = scan_common(h, x_out, P_out, n, PTS_OFF + sizeof(float) * 4 * (size_t)n, stats, true, n > 0 ? cloud_xyzt : nullptr, 4, true);
     if (h->raw_writeback) h->pool.copy(cloud_xyzt, h->h_cloud, sizeof(float) * 4 * (size_t)n);
@@ -861,7 +943,7 @@ int vmp_downsample(vmp_handle h, const float* cloud_xyzc, int n, double leaf, fl
     if ((n > 0 && !cloud_xyzc) || !(leaf > 0.0) || cap < 0 || (cap > 0 && !out_xyzc)) { set_error("vmp_downsample: invalid argument"); return VMP_ERR_INVALID_ARG; }
     std::memcpy(h->h_raw, cloud_xyzc, sizeof(float) * 4 * (size_t)n);
     h->h_in->n = n; h->h_in->stride = 4; h->h_in->n_poses = 0; h->h_in->mode = 0;
-    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr;
+    h->h_in->pts = (const float*)(h->d_stage + PTS_OFF); h->h_in->prior = nullptr; h->h_in->gate_pts = 0;
     VMP_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, h->h_stage, PTS_OFF + sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     h->launches += launch_downsample(h->stream, h->ds, (const float4*)(h->d_stage + PTS_OFF), &h->d_in->n, n, (float)leaf, h->grid_pts,
                                      h->a_ds, h->a_ds_m, nullptr, nullptr);

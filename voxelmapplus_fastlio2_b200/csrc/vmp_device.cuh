@@ -46,6 +46,7 @@ constexpr int E_MERGE_DEPTH = 64;       // the merge phase had to be redone seri
 constexpr int E_MERGE_CAP = 128;        // (unused: a large active set runs in the exact serial mode)
 constexpr int E_LOG_CAP = 256;          // LRU log full (compaction was not served in time)
 constexpr int E_FILL_CAP = 512;         // (unused since the refits run out of shared memory)
+constexpr int E_UPLOAD = 1024;          // a chunk of a streamed scan upload did not arrive within 2 s (the host side of the call failed half-way)
 
 struct DevStats {                       // == vmp_update_stats order
     long long n_points, n_ins, n_touch, n_created, n_refit, refit_points, n_full, n_mergeprobe, n_merge, n_evicted, map_size, n_mergevox, n_skipped;
@@ -85,6 +86,8 @@ struct DevCtl {
     unsigned long long seq;             // sequence number of the current scan (echoed in StateOut / MapOut)
     unsigned fin_ticket;                // arrival counter of k_map_finalize's CTAs (the last one closes the update)
     unsigned cnt_ticket;                // arrival counter of k_map_count's CTAs (the last one lays out the segments)
+    unsigned long long up_pub;          // streamed upload (vmp_scan with a pageable pointer): 64 * scan sequence number + chunks of points that have
+                                        // arrived after the first one; written IN STREAM ORDER behind each chunk's DMA copy, read by the first measurement pass
 };
 
 // per-update counters (single thread).  Called at the END of every update (map_end) so that the next one starts clean without a
@@ -109,6 +112,8 @@ struct ScanIn {
     unsigned long long seq;
     int n, mode;
     int n_poses, stride;                // raw scans (vmp_scan_raw): IMU poses for the motion compensation follow the header
+    int gate_pts, pad_gate;             // > 0: the points arrive in chunks of gate_pts (a multiple of 32) WHILE the first measurement pass runs: point i may be
+                                        // read once DevCtl::up_pub >= 64 * seq + i / gate_pts (chunk 0 is there before the launch)
     double x[36];
     double P[529];
 };

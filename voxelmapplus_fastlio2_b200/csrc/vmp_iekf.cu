@@ -98,6 +98,27 @@ struct MeasShared {
     double stage[NW][32 * SP];
 };
 
+// Streamed upload (ScanIn::gate_pts > 0): the points of the scan arrive chunk by chunk while the first measurement pass is already running.
+// A warp about to read points of chunk `need` (>= 1) waits until DevCtl::up_pub - written in stream order behind that chunk's DMA copy - says
+// it has landed.  Returns the number of chunks (after the first) known to be there.  The wait only delays loads: sums and their order are untouched.
+__device__ __forceinline__ unsigned long long wait_upload(DevCtl* ctl, unsigned long long base, unsigned long long need) {
+    unsigned long long v = 0;
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long t0 = 0;
+        for (;;) {
+            v = *(volatile unsigned long long*)&ctl->up_pub;        // relaxed poll (an acquire at system scope per poll is a MEMBAR.SYS per poll, on 2 000 warps)
+            if (v >= base + need && v < base + 64ull) { __threadfence(); break; }     // the loads of the points stay behind the flag
+            __nanosleep(400);
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (!t0) t0 = t;
+            else if (t - t0 > 2000000000ull) { atomicOr(&ctl->err, E_UPLOAD); v = base + 63ull; break; }    // never hang the device on a host that gave up
+        }
+    }
+    v = __shfl_sync(0xffffffffu, v, 0);
+    return v - base;
+}
+
 // One measurement pass of one CTA (pb of npb) over the scan: LIOBuilder::sharedUpdateFunc (lio_builder.cpp:250-311) for its points,
 // partial sums of H^T R^-1 H / H^T R^-1 z / effect count into partials[pb].
 template <bool EXT, bool FIRST>
@@ -146,6 +167,8 @@ __device__ __forceinline__ void measure_pass(MeasShared<EXT>& sh, const DevMap& 
     const float* pts = FIRST ? in->pts : nullptr;
     const int stride = FIRST ? (in->stride == 4 ? 4 : 3) : 3;
     const bool copy_raw = FIRST && pts != s.raw;
+    int gate_next = 0x7fffffff;                    // streamed upload: first point this warp does not know to have arrived yet
+    if (FIRST) { const int g = in->gate_pts; if (g > 0) gate_next = g; }
     __syncthreads();
     const size_t NM = (size_t)s.nmax;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -177,6 +200,13 @@ __device__ __forceinline__ void measure_pass(MeasShared<EXT>& sh, const DevMap& 
     for (int base = (pb * NW + wid) * 32; base < n; base += npb * NW * 32) {
         const int i = base + lane;
         bool valid = false;
+        if (FIRST) {
+            const int last = min(base + 31, n - 1);
+            if (last >= gate_next) {
+                const int g = in->gate_pts;
+                gate_next = ((int)wait_upload(ctl, in->seq * 64ull, (unsigned long long)(last / g)) + 1) * g;
+            }
+        }
         if (i < n) {
             V3 pl;
             M3 cl;
@@ -187,7 +217,7 @@ __device__ __forceinline__ void measure_pass(MeasShared<EXT>& sh, const DevMap& 
             if (!FIRST && reuse_slots) { pk_prev = s.rkey[i]; slot_prev = s.rslot[i]; }
             if (FIRST) {
                 const float* pp = pts + (size_t)i * stride;
-                const float fx = pp[0], fy = pp[1], fz = pp[2];
+                const float fx = __ldcg(pp), fy = __ldcg(pp + 1), fz = __ldcg(pp + 2);      // L2: with a streamed upload the DMA engine wrote them during this launch
                 if (copy_raw) { s.raw[3 * (size_t)i] = fx; s.raw[3 * (size_t)i + 1] = fy; s.raw[3 * (size_t)i + 2] = fz; }
                 pl = v3((double)fx, (double)fy, (double)fz);
                 calc_body_cov(pl, s.range_var, s.sn2, cl);            // (edits pl.z == 0 -> 0.001, Q16)

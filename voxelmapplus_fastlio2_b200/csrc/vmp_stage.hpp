@@ -27,16 +27,26 @@ public:
     // dst <- src (bytes).  check_stride > 0: src is an array of records of check_stride floats whose last float is a time
     // offset; returns false if those are not non-decreasing (lio_builder.cpp:75 sorts in that case).
     bool copy(void* dst, const void* src, size_t bytes, int check_stride = 0) {
+        begin(dst, src, bytes, check_stride);
+        return end();
+    }
+
+    // The same copy in two halves: begin() hands the helpers their parts and returns at once, end() does the caller's own part and
+    // waits for the helpers.  In between the caller is free (vmp_scan launches the scan's graph there).  A copy too small for
+    // the helpers is done in end().
+    void begin(void* dst, const void* src, size_t bytes, int check_stride = 0) {
         constexpr size_t MIN_PAR = 512 * 1024;
-        if (bytes < MIN_PAR || !ensure_started()) return slice(dst, src, bytes, 0, bytes, check_stride);
+        drain();
+        job_.chunked = false;
+        job_.dst = (char*)dst; job_.src = (const char*)src; job_.bytes = bytes; job_.check_stride = check_stride;
+        inline_ = bytes < MIN_PAR || !ensure_started();
+        if (inline_) return;
         int parts = (int)workers_.size() + 1;
         const int by_size = (int)(bytes / (32 * 1024));                   // no more parts than 32 KB pieces
         if (parts > by_size) parts = by_size < 2 ? 2 : by_size;
         // whole records per part, cache-line friendly
         const size_t rec = check_stride > 0 ? (size_t)check_stride * sizeof(float) : 64;
-        const size_t nrec = bytes / rec;
-        job_.dst = (char*)dst; job_.src = (const char*)src; job_.bytes = bytes; job_.rec = rec; job_.nrec = nrec; job_.parts = parts;
-        job_.check_stride = check_stride;
+        job_.rec = rec; job_.nrec = bytes / rec; job_.parts = parts;
         sorted_.store(true, std::memory_order_relaxed);
         remaining_.store(parts - 1, std::memory_order_relaxed);
         {
@@ -44,10 +54,43 @@ public:
             gen_.fetch_add(1, std::memory_order_release);
         }
         if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
+    }
+    bool end() {
+        if (inline_) return slice(job_.dst, job_.src, job_.bytes, 0, job_.bytes, job_.check_stride);
         bool ok = run_part(0);
         while (remaining_.load(std::memory_order_acquire) != 0) cpu_relax();
         return ok && sorted_.load(std::memory_order_relaxed);
     }
+
+    // A copy the helpers run through WITHOUT the caller: chunk after chunk, every helper its piece of each, one arrival counter per chunk.
+    // The caller only waits for chunk c (wait_chunk) and ships it while the helpers are already on the next ones - no barrier and no
+    // wake-up between chunks (vmp_scan: the DMA copies of a streamed upload).  Without helpers wait_chunk copies the chunk itself.
+    static constexpr int MAX_CHUNKS = 16;
+    void begin_chunks(void* dst, const void* src, size_t bytes, size_t chunk_bytes) {
+        drain();
+        job_.dst = (char*)dst; job_.src = (const char*)src; job_.bytes = bytes; job_.check_stride = 0;
+        job_.chunk = chunk_bytes; job_.nchunks = (int)((bytes + chunk_bytes - 1) / chunk_bytes);
+        inline_ = bytes < 256 * 1024 || job_.nchunks > MAX_CHUNKS || !ensure_started();
+        if (inline_) return;
+        job_.chunked = true;
+        job_.parts = (int)workers_.size();
+        for (int c = 0; c < job_.nchunks; c++) done_[c].store(0, std::memory_order_relaxed);
+        remaining_.store(job_.parts, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
+    }
+    void wait_chunk(int c) {
+        if (inline_) {
+            const size_t b0 = (size_t)c * job_.chunk, b1 = std::min(job_.bytes, b0 + job_.chunk);
+            if (b1 > b0) std::memcpy(job_.dst + b0, job_.src + b0, b1 - b0);
+            return;
+        }
+        while (done_[c].load(std::memory_order_acquire) != job_.parts) cpu_relax();
+    }
+    void end_chunks() { drain(); job_.chunked = false; }
 
     void shutdown() {
         if (workers_.empty()) return;
@@ -62,7 +105,21 @@ public:
     }
 
 private:
-    struct Job { char* dst; const char* src; size_t bytes, rec, nrec; int parts, check_stride; };
+    struct Job { char* dst; const char* src; size_t bytes, rec, nrec; int parts, check_stride; size_t chunk; int nchunks; bool chunked; };
+
+    void drain() { while (remaining_.load(std::memory_order_acquire) != 0) cpu_relax(); }
+
+    // helper `part` of `parts`: its 64-byte-aligned piece of every chunk, in chunk order
+    void run_chunks(int part) {
+        const Job& j = job_;
+        for (int c = 0; c < j.nchunks; c++) {
+            const size_t c0 = (size_t)c * j.chunk, c1 = std::min(j.bytes, c0 + j.chunk), len = c1 - c0;
+            const size_t per = ((len + j.parts - 1) / j.parts + 63) / 64 * 64;
+            const size_t b0 = std::min(len, per * (size_t)part), b1 = std::min(len, per * (size_t)(part + 1));
+            if (b1 > b0) std::memcpy(j.dst + c0 + b0, j.src + c0 + b0, b1 - b0);
+            done_[c].fetch_add(1, std::memory_order_release);
+        }
+    }
 
     static void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
@@ -137,7 +194,9 @@ private:
             }
             seen = g;
             if (stop_) return;
-            if (id < job_.parts) {
+            if (job_.chunked) {
+                if (id <= job_.parts) { run_chunks(id - 1); remaining_.fetch_sub(1, std::memory_order_release); }
+            } else if (id < job_.parts) {
                 if (!run_part(id)) sorted_.store(false, std::memory_order_relaxed);
                 remaining_.fetch_sub(1, std::memory_order_release);
             }
@@ -149,9 +208,10 @@ private:
     std::condition_variable cv_;
     std::atomic<unsigned long long> gen_{0};
     std::atomic<int> remaining_{0}, sleepers_{0};
+    std::atomic<int> done_[MAX_CHUNKS] = {};
     std::atomic<bool> sorted_{true};
     Job job_{};
-    bool started_ = false, stop_ = false;
+    bool started_ = false, stop_ = false, inline_ = true;
 };
 
 }  // namespace vmp
