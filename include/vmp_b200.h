@@ -170,6 +170,10 @@ int vmp_scan(vmp_handle h, vmp_state* x_inout, double* P_inout,
  * with the header and the prior) and runs the scan.  The buffer may be refilled as soon as the call has returned
  * (also in pipelined mode). */
 float* vmp_scan_buffer(vmp_handle h);
+/* That extraction loop done by the handle's staging helpers: x y z of n records that lie stride_floats apart at src (>= 3; 4 for
+ * x y z t, 12 for the 48-byte pcl::PointXYZINormal read as floats) go into the staging area; vmp_scan_staged follows.
+ * (One host core moves a 200 000-point scan in ~0.3 ms - as long as the device side of the scan.) */
+int vmp_scan_buffer_fill(vmp_handle h, const float* src, int stride_floats, int n);
 int vmp_scan_staged(vmp_handle h, vmp_state* x_inout, double* P_inout, int n, vmp_scan_stats* stats);
 
 /* Same work with every input already resident in device memory: pts_lidar_dev = device

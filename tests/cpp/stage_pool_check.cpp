@@ -55,6 +55,19 @@ int main() {
                 EXPECT(pool.copy(dst.data(), src.data(), bytes));                              // the other kinds of job still work afterwards
             }
         }
+        // x y z out of records of 4 / 8 floats
+        for (int stride : {3, 4, 8}) {
+            for (int n : {0, 1, 1000, 30000, 200000}) {
+                std::vector<float> src((size_t)stride * n + 1), dst(3 * (size_t)n + 1, -7.f);
+                for (auto& v : src) v = (float)(rng() % 100000) * 0.01f;
+                pool.gather_xyz(dst.data(), src.data(), stride, (size_t)n);
+                bool same = true;
+                for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) same &= dst[3 * (size_t)i + k] == src[(size_t)stride * i + k];
+                EXPECT(same);
+                EXPECT(dst[3 * (size_t)n] == -7.f);
+            }
+        }
+        { std::vector<uint8_t> a(700000, 3), b(700000, 0); EXPECT(pool.copy(b.data(), a.data(), a.size())); EXPECT(a == b); }       // a plain copy after a gather
         // raw scans: records of 4 floats, the last one a time offset
         for (int n : {1, 2, 1000, 40000, 200000, 333333}) {
             std::vector<float> src(4 * (size_t)n), dst(4 * (size_t)n);

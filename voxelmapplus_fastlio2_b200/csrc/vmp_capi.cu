@@ -869,6 +869,14 @@ int vmp_scan(vmp_handle h, vmp_state* x, double* P, const float* pts, int n, vmp
 
 float* vmp_scan_buffer(vmp_handle h) { return h ? h->h_raw : nullptr; }
 
+int vmp_scan_buffer_fill(vmp_handle h, const float* src, int stride_floats, int n) {
+    const int r = check_n(h, n, "vmp_scan_buffer_fill");
+    if (r) return r;
+    if ((n > 0 && !src) || stride_floats < 3) { set_error("vmp_scan_buffer_fill: invalid argument"); return VMP_ERR_INVALID_ARG; }
+    h->pool.gather_xyz(h->h_raw, src, stride_floats, (size_t)n);
+    return VMP_OK;
+}
+
 int vmp_scan_staged(vmp_handle h, vmp_state* x, double* P, int n, vmp_scan_stats* stats) {
     const auto t_enter = std::chrono::steady_clock::now();
     int r = h && h->pipelined && !h->prof_on ? check_args(h, n, "vmp_scan_staged") : check_n(h, n, "vmp_scan_staged");

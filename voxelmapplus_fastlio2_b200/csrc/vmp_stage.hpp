@@ -37,7 +37,7 @@ public:
     void begin(void* dst, const void* src, size_t bytes, int check_stride = 0) {
         constexpr size_t MIN_PAR = 512 * 1024;
         drain();
-        job_.chunked = false;
+        job_.chunked = false; job_.gather = 0;
         job_.dst = (char*)dst; job_.src = (const char*)src; job_.bytes = bytes; job_.check_stride = check_stride;
         inline_ = bytes < MIN_PAR || !ensure_started();
         if (inline_) return;
@@ -62,12 +62,36 @@ public:
         return ok && sorted_.load(std::memory_order_relaxed);
     }
 
+    // dst[3 i .. 3 i + 2] <- src[stride i .. stride i + 2] for n records (x y z out of the caller's point type, lio_builder.cpp:224-229), by
+    // the helpers and the caller together
+    void gather_xyz(float* dst, const float* src, int stride, size_t n) {
+        drain();
+        job_.chunked = false;
+        job_.dst = (char*)dst; job_.src = (const char*)src; job_.nrec = n; job_.rec = (size_t)stride * sizeof(float); job_.bytes = n * job_.rec;
+        job_.check_stride = 0; job_.gather = stride;
+        if (n * 12 < 256 * 1024 || !ensure_started()) { gather_slice(job_, 0, n); job_.gather = 0; return; }
+        int parts = (int)workers_.size() + 1;
+        const int by_size = (int)(n * 12 / (32 * 1024));
+        if (parts > by_size) parts = by_size < 2 ? 2 : by_size;
+        job_.parts = parts;
+        remaining_.store(parts - 1, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
+        run_part(0);
+        drain();
+        job_.gather = 0;
+    }
+
     // A copy the helpers run through WITHOUT the caller: chunk after chunk, every helper its piece of each, one arrival counter per chunk.
     // The caller only waits for chunk c (wait_chunk) and ships it while the helpers are already on the next ones - no barrier and no
     // wake-up between chunks (vmp_scan: the DMA copies of a streamed upload).  Without helpers wait_chunk copies the chunk itself.
     static constexpr int MAX_CHUNKS = 16;
     void begin_chunks(void* dst, const void* src, size_t bytes, size_t chunk_bytes) {
         drain();
+        job_.gather = 0;
         job_.dst = (char*)dst; job_.src = (const char*)src; job_.bytes = bytes; job_.check_stride = 0;
         job_.chunk = chunk_bytes; job_.nchunks = (int)((bytes + chunk_bytes - 1) / chunk_bytes);
         inline_ = bytes < 256 * 1024 || job_.nchunks > MAX_CHUNKS || !ensure_started();
@@ -105,7 +129,14 @@ public:
     }
 
 private:
-    struct Job { char* dst; const char* src; size_t bytes, rec, nrec; int parts, check_stride; size_t chunk; int nchunks; bool chunked; };
+    struct Job { char* dst; const char* src; size_t bytes, rec, nrec; int parts, check_stride; size_t chunk; int nchunks; bool chunked; int gather; };
+
+    static void gather_slice(const Job& j, size_t r0, size_t r1) {
+        float* d = reinterpret_cast<float*>(j.dst);
+        const float* s = reinterpret_cast<const float*>(j.src);
+        const size_t st = (size_t)j.gather;
+        for (size_t i = r0; i < r1; i++) { d[3 * i] = s[st * i]; d[3 * i + 1] = s[st * i + 1]; d[3 * i + 2] = s[st * i + 2]; }
+    }
 
     void drain() { while (remaining_.load(std::memory_order_acquire) != 0) cpu_relax(); }
 
@@ -174,6 +205,7 @@ private:
         const Job& j = job_;
         const size_t per = (j.nrec + j.parts - 1) / j.parts;
         size_t r0 = std::min(j.nrec, per * (size_t)id), r1 = std::min(j.nrec, per * (size_t)(id + 1));
+        if (j.gather) { gather_slice(j, r0, r1); return true; }
         size_t b0 = r0 * j.rec, b1 = (id == j.parts - 1) ? j.bytes : r1 * j.rec;     // the last part takes the tail bytes
         if (b1 <= b0) return true;
         return slice(j.dst, j.src, j.bytes, b0, b1, j.check_stride);
