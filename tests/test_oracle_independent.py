@@ -70,3 +70,119 @@ def test_update_plane_matches_numpy_eigh(oracle_mod):
     assert checked >= 40, checked
     print(f"updatePlane vs numpy.linalg.eigh over {checked} plane voxels: {worst}")
     assert worst["mean"] < 1e-12 and worst["norm"] < 1e-8 and worst["diag"] < 1e-8 and worst["off"] < 1e-8, worst
+
+
+# --------------------------------------------------------------------------- the measurement model, end to end
+def _hat(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+
+def _rot(axis_angle):
+    from scipy.spatial.transform import Rotation
+    return Rotation.from_rotvec(axis_angle).as_matrix()
+
+
+def _body_cov_numpy(p, range_cov=0.04, angle_cov=0.1):
+    """commons.cpp:18-45 (tests/test_oracle_math.py::test_calc_body_cov pins the oracle's version against the same formulas)"""
+    q = p.copy()
+    if q[2] == 0:
+        q[2] = 0.001
+    r = np.linalg.norm(q); d = q / r
+    b1 = np.array([1, 1, -(d[0] + d[1]) / d[2]]); b1 /= np.linalg.norm(b1)
+    b2 = np.cross(b1, d); b2 /= np.linalg.norm(b2)
+    A = r * _hat(d) @ np.stack([b1, b2], 1)
+    return q, np.outer(d, d) * range_cov ** 2 + A @ (np.eye(2) * np.sin(angle_cov * 0.017453293) ** 2) @ A.T
+
+
+def _measure_numpy(planes, voxel_size, x, P, pts, estimate_ext):
+    """LIOBuilder::sharedUpdateFunc + VoxelMap::buildResidual (lio_builder.cpp:250-311, voxel_map.cpp:258-276) written from the reference's
+    formulas with numpy matrices; plane_cov is the zero matrix the reference never assigns (Q1).  planes: {key tuple: (is_plane, mean, norm)}."""
+    R, Rext, pos, pext = x["rot"], x["rot_ext"], x["pos"], x["pos_ext"]
+    r_wl = R @ Rext
+    p_wl = R @ pext + pos
+    H = np.zeros((12, 12)); b = np.zeros(12)
+    status = np.zeros(len(pts), np.uint8); res = np.zeros(len(pts)); keys = np.zeros((len(pts), 3), np.int64)
+    eff = 0
+    for i, p in enumerate(pts):
+        pl, cl = _body_cov_numpy(p.astype(np.float64))
+        pw = r_wl @ pl + p_wl
+        cw = r_wl @ cl @ r_wl.T + _hat(pl) @ P[3:6, 3:6] @ _hat(pl).T + P[0:3, 0:3]
+        key = tuple(int(k) for k in np.floor(pw / voxel_size))
+        keys[i] = key
+        if key not in planes:
+            continue                                            # fresh records: is_valid = false
+        status[i] |= 1
+        is_plane, mean, nrm = planes[key]
+        if not is_plane:
+            continue
+        status[i] |= 2
+        r = nrm @ (pw - mean)
+        res[i] = r
+        if not abs(r) < 3.0 * np.sqrt(nrm @ cw @ nrm):
+            continue
+        status[i] |= 4
+        eff += 1
+        r_cov = nrm @ r_wl @ cl @ r_wl.T @ nrm
+        w = 5000.0 if r_cov < 0.0002 else 1.0 / r_cov
+        J = np.zeros(12)
+        J[0:3] = nrm
+        J[3:6] = -nrm @ R @ _hat(Rext @ pl + pext)
+        if estimate_ext:
+            J[6:9] = -nrm @ r_wl @ _hat(pl)
+            J[9:12] = nrm @ R
+        H += np.outer(J, J) * w
+        b += J * w * r
+    return H, b, eff, keys, status, res
+
+
+def _measurement_case(oracle_mod, estimate_ext, seed):
+    from voxelmapplus_fastlio2_b200.ctypes_defs import VmpState
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    cfg = default_config(max_points_per_scan=8192, voxel_size=0.5, estimate_ext=1 if estimate_ext else 0)
+    o = oracle_mod.Oracle(cfg)
+    # a map of tilted planes + clutter (voxels that exist but are no planes)
+    world = np.concatenate([plane_cloud(rng, 3000, (0.3, 0.2, 1.0), (1, 0.2, 0.1), (0, 1, 0.3), (4.0, 3.0), 0.004),
+                            plane_cloud(rng, 3000, (-3.0, 1.0, 0.2), (0, 1, 0), (0.1, 0, 1), (3.0, 3.0), 0.004),
+                            rng.uniform(-1.0, 0.0, (300, 3)) + np.array([0.0, -2.0, 0.0])]).astype(np.float32).astype(np.float64)
+    o.map_build(world, random_cov(rng, len(world), scale=1e-4))
+    planes = {tuple(int(k) for k in v["key"]): (bool(v["flags"] & F_PLANE), v["mean"].copy(), v["norm"].copy()) for v in o.dump_map()}
+    # a state away from the identity in every block the model reads, and a dense P
+    x = VmpState.identity()
+    R, Rext = _rot(rng.normal(0, 0.05, 3)), _rot(rng.normal(0, 0.03, 3))
+    x.rot[:] = R.ravel(); x.rot_ext[:] = Rext.ravel()
+    x.pos[:] = rng.normal(0, 0.05, 3); x.pos_ext[:] = rng.normal(0, 0.05, 3)
+    A = rng.normal(0, 1, (23, 23))
+    P = (A @ A.T) * 1e-5 + np.eye(23) * 1e-5
+    # the scan: new samples of the same surfaces (+ clutter, + points off the map), expressed in the lidar frame
+    scan_w = np.concatenate([plane_cloud(rng, 1500, (0.3, 0.2, 1.0), (1, 0.2, 0.1), (0, 1, 0.3), (4.0, 3.0), 0.02),
+                             plane_cloud(rng, 1500, (-3.0, 1.0, 0.2), (0, 1, 0), (0.1, 0, 1), (3.0, 3.0), 0.02),
+                             plane_cloud(rng, 400, (0.3, 0.2, 1.0), (1, 0.2, 0.1), (0, 1, 0.3), (4.0, 3.0), 0.12),      # outliers for the gate
+                             rng.uniform(-1.0, 0.0, (200, 3)) + np.array([0.0, -2.0, 0.0]), rng.uniform(20, 30, (100, 3))])
+    r_wl, p_wl = R @ Rext, R @ np.array(x.pos_ext[:]) + np.array(x.pos[:])
+    pts = ((scan_w - p_wl) @ r_wl).astype(np.float32)            # r_wl^T (p - p_wl)
+    o.set_scan(pts)
+    H, b, eff = o.measure(x, P)
+    c = o.dump_correspondences(len(pts))
+    xd = dict(rot=R, rot_ext=Rext, pos=np.array(x.pos[:]), pos_ext=np.array(x.pos_ext[:]))
+    return (H, b, eff, c), _measure_numpy(planes, cfg.voxel_size, xd, P, pts, estimate_ext)
+
+
+def test_measurement_model_matches_numpy_restatement(oracle_mod):
+    """The oracle's sharedUpdateFunc / buildResidual against a numpy restatement written from the reference's formulas (matrix products by
+    numpy, rotations by scipy): voxel keys, found / plane / valid flags and effect_num identical, residuals, H and b to 1e-9 relative.
+    A misreading of the model - which rotation multiplies which hat matrix, the sign of the Jacobian blocks, the gate's covariance, the
+    weight clamp - would show here, independently of the CUDA-vs-oracle tests."""
+    for estimate_ext in (False, True):
+        for seed in (41, 42):
+            (H, b, eff, c), (Hn, bn, effn, keys, status, res) = _measurement_case(oracle_mod, estimate_ext, seed)
+            assert eff == effn and eff > 1000
+            assert np.array_equal(c["keys"], keys)
+            assert np.array_equal(c["status"], status)
+            assert (status == 1).any() and (status == 0).any() and (status == 3).any()      # non-plane voxel, off the map, gated out
+            v = (status & 4) != 0
+            np.testing.assert_allclose(c["residual"][v], res[v], rtol=1e-9, atol=1e-12)
+            H = np.asarray(H).reshape(12, 12); b = np.asarray(b).ravel()
+            np.testing.assert_allclose(H, Hn, rtol=1e-9, atol=1e-9 * np.abs(Hn).max())
+            np.testing.assert_allclose(b, bn, rtol=1e-9, atol=1e-9 * np.abs(bn).max())
+            if not estimate_ext:
+                assert not H[6:, :].any() and not H[:, 6:].any()
