@@ -186,3 +186,70 @@ def test_measurement_model_matches_numpy_restatement(oracle_mod):
             np.testing.assert_allclose(b, bn, rtol=1e-9, atol=1e-9 * np.abs(bn).max())
             if not estimate_ext:
                 assert not H[6:, :].any() and not H[:, 6:].any()
+
+
+# --------------------------------------------------------------------------- the whole voxel map, second reading
+def _compare_with_pyref(o, py, what):
+    d = o.dump_map()
+    keys = [tuple(k) for k in d["key"].tolist()]
+    assert len(keys) == len(py.feat), what
+    order = list(py.cache.keys())
+    assert keys == order[::-1] or keys == order, f"{what}: LRU order differs"
+    F_INIT, F_UPD, F_MERGED = 1, 4, 8
+    worst = dict(mean=0.0, norm=0.0, cov=0.0)
+    groups_o, groups_p = {}, {}
+    for v, k in zip(d, keys):
+        g = py.feat[k]
+        fl = (F_INIT if g.is_init else 0) | (F_PLANE if g.is_plane else 0) | (F_UPD if g.update_enable else 0) | (F_MERGED if g.merged else 0)
+        assert int(v["flags"]) == fl, f"{what}: flags of {k}: {int(v['flags'])} vs {fl}"
+        assert int(v["n"]) == g.n and int(v["n_temp"]) == len(g.temp) and int(v["newly_add_point"]) == g.newly, f"{what}: counts of {k}"
+        groups_o.setdefault(int(v["group"]), []).append(k); groups_p.setdefault(g.group_id, []).append(k)
+        worst["mean"] = max(worst["mean"], np.abs(v["mean"] - g.mean).max())
+        np.testing.assert_allclose(v["ppt"].reshape(3, 3), g.ppt, rtol=1e-13, atol=0)
+        if g.is_plane:
+            worst["norm"] = max(worst["norm"], np.abs(v["norm"] - g.norm).max())
+            Co, C = v["cov"].reshape(6, 6), g.cov
+            sc = max(np.abs(C).max(), 1e-300)
+            # the diagonal blocks do not depend on the eigenvectors' signs (the off-diagonal ones flip with the raw normal's, refit by refit)
+            worst["cov"] = max(worst["cov"], np.abs(Co[:3, :3] - C[:3, :3]).max() / sc, np.abs(Co[3:, 3:] - C[3:, 3:]).max() / sc)
+    assert sorted(sorted(v) for v in groups_o.values()) == sorted(sorted(v) for v in groups_p.values()), f"{what}: merge groups differ"
+    assert worst["mean"] < 1e-12 and worst["norm"] < 1e-7 and worst["cov"] < 1e-6, (what, worst)
+    return worst
+
+
+def test_voxel_map_matches_python_second_reading(oracle_mod):
+    """VoxelMap::build / update / pushPoint / addToPlane / updatePlane / merge / the LRU cache: the C++ oracle against tests/voxelmap_pyref.py,
+    a plain-Python reading of voxel_map.cpp with LAPACK's eigen-solver.  Identical: keys, LRU order, evicted keys per scan, init / plane /
+    update_enable / merged flags, point counts, refit counters, merge groups; means to 1e-12, normals to 1e-7, the sign-independent blocks
+    of the plane covariance to 1e-6 relative - through fills, refits, closes, merges and evictions."""
+    from helpers import wall_workload
+    from voxelmap_pyref import VoxelMapPy
+    merges = evictions = 0
+    for seed, cap, mk_work in ((1, 100000, None), (2, 100000, None), (5, 400, "moving")):
+        cfg = default_config(max_point_thresh=30 if cap > 400 else 20, update_size_thresh=5, map_capacity=cap, max_points_per_scan=4096)
+        o = oracle_mod.Oracle(cfg)
+        py = VoxelMapPy(cfg.max_point_thresh, cfg.update_size_thresh, cfg.plane_thresh, cfg.voxel_size, cfg.map_capacity)
+        if mk_work is None:
+            work = wall_workload(seed)
+        else:
+            rng = np.random.Generator(np.random.Philox(key=seed))
+            work = []
+            for s in range(25):                     # a corridor that advances 1 m per scan: old voxels fall out of the map
+                x0 = 1.0 * s
+                p = np.concatenate([np.stack([rng.uniform(x0, x0 + 6, 500), rng.normal(0.25, 0.01, 500), rng.uniform(0, 2, 500)], 1),
+                                    np.stack([rng.uniform(x0, x0 + 6, 500), rng.uniform(0, 3, 500), rng.normal(0.1, 0.01, 500)], 1)])
+                p = p[rng.permutation(len(p))].astype(np.float32).astype(np.float64)
+                work.append((p, np.tile((np.eye(3) * 1e-4).reshape(1, 9), (len(p), 1))))
+        for s, (p, c) in enumerate(work):
+            c3 = c.reshape(-1, 3, 3)
+            if s == 0:
+                so = o.map_build(p, c); py.build(p, c3)
+            else:
+                so = o.map_update(p, c); py.update(p, c3)
+            merges += so["n_merge"]
+            ev = [tuple(k) for k in o.dump_evicted().tolist()]
+            assert ev == py.evicted, f"seed {seed} scan {s}: evicted keys differ"
+            evictions += len(ev)
+            if s % 4 == 3 or s == len(work) - 1:
+                _compare_with_pyref(o, py, f"seed {seed} scan {s}")
+    assert merges > 0 and evictions > 100, (merges, evictions)
