@@ -253,3 +253,129 @@ def test_voxel_map_matches_python_second_reading(oracle_mod):
             if s % 4 == 3 or s == len(work) - 1:
                 _compare_with_pyref(o, py, f"seed {seed} scan {s}")
     assert merges > 0 and evictions > 100, (merges, evictions)
+
+
+# --------------------------------------------------------------------------- IMU initialisation + motion compensation
+def _so3_exp(v):
+    from scipy.spatial.transform import Rotation
+    return Rotation.from_rotvec(v).as_matrix()
+
+
+class _LioNumpy:
+    """initializeImu + undistortCloud (lio_builder.cpp:28-153) restated with numpy / scipy from the reference's source: IMU cache, mean
+    acceleration -> gravity norm, gravity alignment, the mid-point propagation of pos / rot / vel per IMU step, the pose list, and the backward
+    loop that compensates every point into the frame of the scan's end.  The filter's covariance is not needed for any of it."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.cache = []
+        self.last_acc = np.zeros(3); self.last_gyro = np.zeros(3)
+        self.last_end = 0.0
+
+    def initialize(self, imus, t_end):
+        self.cache += [(np.array(i["acc"]), np.array(i["gyro"]), float(i["timestamp"])) for i in imus]
+        if len(self.cache) < self.cfg.imu_init_num:
+            return None
+        acc_mean = sum(c[0] for c in self.cache) / float(len(self.cache))
+        gyro_mean = sum(c[1] for c in self.cache) / float(len(self.cache))
+        self.gravity_norm = np.linalg.norm(acc_mean)
+        x = dict(pos=np.zeros(3), vel=np.zeros(3), ba=np.zeros(3), bg=gyro_mean, rot=np.eye(3),
+                 rot_ext=np.array(self.cfg.r_il[:]).reshape(3, 3), pos_ext=np.array(self.cfg.p_il[:]))
+        assert self.cfg.gravity_align
+        a, b = -acc_mean / np.linalg.norm(acc_mean), np.array([0.0, 0.0, -1.0])          # Quaterniond::FromTwoVectors(a, b): the shortest rotation a -> b
+        axis = np.cross(a, b)
+        s, c = np.linalg.norm(axis), a @ b
+        x["rot"] = _so3_exp(axis / s * np.arctan2(s, c)) if s > 1e-12 else np.eye(3)
+        x["g"] = np.array([0.0, 0.0, -1.0]) * 9.81                                       # State::initG: direction scaled to 9.81 (ieskf.h)
+        self.last_imu = self.cache[-1]
+        self.last_end = t_end
+        return x
+
+    def undistort(self, x, imus, cloud, t0, t1):
+        """x: state at the start (dict of arrays; pos / rot / vel are advanced in place), cloud: n x 4 float32 (x y z, time offset in ms), sorted."""
+        cache = [self.last_imu] + [(np.array(i["acc"]), np.array(i["gyro"]), float(i["timestamp"])) for i in imus]
+        poses = [(0.0, self.last_acc.copy(), self.last_gyro.copy(), x["vel"].copy(), x["pos"].copy(), x["rot"].copy())]
+        acc = gyro = None
+
+        def predict(acc, gyro, dt):                                  # IESKF::predict, state part (ieskf.cpp:101-108)
+            w, a = gyro - x["bg"], acc - x["ba"]
+            pos = x["pos"] + x["vel"] * dt
+            vel = x["vel"] + (x["rot"] @ a + x["g"]) * dt
+            x["rot"] = x["rot"] @ _so3_exp(w * dt)
+            x["pos"], x["vel"] = pos, vel
+
+        for head, tail in zip(cache[:-1], cache[1:]):
+            if tail[2] < self.last_end:
+                continue
+            gyro = 0.5 * (head[1] + tail[1])
+            acc = 0.5 * (head[0] + tail[0]) * 9.81 / self.gravity_norm
+            dt = tail[2] - self.last_end if head[2] < self.last_end else tail[2] - head[2]
+            predict(acc, gyro, dt)
+            self.last_gyro = gyro - x["bg"]
+            self.last_acc = x["rot"] @ (acc - x["ba"]) + x["g"]
+            poses.append((tail[2] - t0, self.last_acc.copy(), self.last_gyro.copy(), x["vel"].copy(), x["pos"].copy(), x["rot"].copy()))
+        predict(acc, gyro, t1 - cache[-1][2])
+        self.last_imu = cache[-1]
+        self.last_end = t1
+        R, p, Re, pe = x["rot"], x["pos"], x["rot_ext"], x["pos_ext"]
+        out = cloud.copy()
+        i = len(cloud) - 1
+        for k in range(len(poses) - 1, 0, -1):
+            h_off, _, _, h_vel, h_pos, h_rot = poses[k - 1]
+            _, t_acc, t_gyro = poses[k][:3]
+            # the points are edited IN PLACE and the iterator stays on the first point once it gets there: a first point later than the head of
+            # an earlier pose pair is compensated again, from its already compensated coordinates (the reference's loop, literally)
+            while float(out[i, 3]) / 1000.0 > h_off:
+                dt = float(out[i, 3]) / 1000.0 - h_off
+                pt = out[i, :3].astype(np.float64)
+                point_rot = h_rot @ _so3_exp(t_gyro * dt)
+                point_pos = h_pos + h_vel * dt + 0.5 * t_acc * dt * dt
+                out[i, :3] = (Re.T @ (R.T @ (point_rot @ (Re @ pt + pe) + point_pos - p) - pe)).astype(np.float32)
+                if i == 0:
+                    break
+                i -= 1
+        return out
+
+
+def test_imu_init_and_motion_compensation_match_numpy_restatement(oracle_mod):
+    """The oracle's initializeImu / undistortCloud (and with them the priors it feeds the update) against the numpy restatement above, scan by
+    scan along a moving synthetic sequence, each scan started from the oracle's own posterior: propagated prior to 1e-11, compensated
+    points equal up to one float32 rounding (the result is stored as float32 on both sides)."""
+    from voxelmapplus_fastlio2_b200 import synth
+    cfg = default_config(max_points_per_scan=4096)
+    o = oracle_mod.Oracle(cfg)
+    ref = _LioNumpy(cfg)
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=1500))
+    checked = moved = 0
+    x = None
+    for pk in seq.packages(34):
+        raw = pk.cloud.copy()
+        assert np.all(np.diff(raw[:, 3]) >= 0)                      # already in time order: the sort of lio_builder.cpp:75 is the identity
+        _, _, status = o.lio_state()
+        cloud = pk.cloud.copy()
+        o.lio_process(pk.imus, cloud, pk.t0, pk.t1)
+        xo, _, _ = o.lio_state()
+        if status == 0:
+            x = ref.initialize(pk.imus, pk.t1)
+            if x is not None:
+                d = xo.as_dict()
+                np.testing.assert_allclose(d["rot"].reshape(3, 3), x["rot"], atol=1e-12)
+                np.testing.assert_allclose(d["bg"], x["bg"], atol=1e-15)
+                np.testing.assert_allclose(d["g"], x["g"], atol=1e-12)
+            continue
+        mine = ref.undistort(x, pk.imus, raw, pk.t0, pk.t1)
+        x0, _ = o.get_prior() if status == 2 else (None, None)
+        if x0 is not None:                                           # the prior of the update = the propagated state
+            d0 = x0.as_dict()
+            np.testing.assert_allclose(d0["pos"], x["pos"], atol=1e-11); np.testing.assert_allclose(d0["vel"], x["vel"], atol=1e-11)
+            np.testing.assert_allclose(d0["rot"].reshape(3, 3), x["rot"], atol=1e-11)
+        scale = float(np.abs(mine[:, :3]).max())
+        dev = np.abs(mine[:, :3].astype(np.float64) - cloud[:, :3].astype(np.float64)).max()
+        assert dev <= 2 * float(np.finfo(np.float32).eps) * scale, (pk.index, dev)
+        assert (mine[:, :3] == cloud[:, :3]).mean() > 0.99
+        moved = max(moved, float(np.abs(mine[:, :3] - raw[:, :3]).max()))
+        checked += 1
+        # next scan starts from the oracle's posterior (the numpy side restates the propagation, not the update)
+        d = xo.as_dict()
+        x = dict(pos=d["pos"], vel=d["vel"], ba=d["ba"], bg=d["bg"], g=d["g"], rot=d["rot"].reshape(3, 3), rot_ext=d["rot_ext"].reshape(3, 3), pos_ext=d["pos_ext"])
+    assert checked >= 25 and moved > 0.01, (checked, moved)         # the compensation really moves points (centimetres)
