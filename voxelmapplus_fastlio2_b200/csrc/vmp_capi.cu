@@ -738,7 +738,7 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
         // STREAMED upload (VMP_UPLOAD_GATE=1, off by default - measured, it does not pay): the graph is launched behind chunk 0; the
         // other chunks travel on their own stream while the first measurement pass is already running, and a stream memory operation behind each
         // of them (DevCtl::up_pub) releases the warps that wait for its points.
-        const bool chunked = nchunk > 1 && check_stride == 0;
+        const bool chunked = nchunk > 1 && check_stride == 0 && (h->pool.helpers() >= 3 || h->upload_gate);     // (with one or two helpers the caller's own share of a copy matters: pool.copy)
         const bool gate = chunked && h->upload_gate && !raw && !predict && !h->prof_on;
         if (gate) nchunk = h->gate_chunks;
         size_t nrec_per = (pts_bytes / rec + nchunk - 1) / nchunk;

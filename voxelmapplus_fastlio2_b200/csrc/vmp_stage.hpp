@@ -89,6 +89,7 @@ public:
     // The caller only waits for chunk c (wait_chunk) and ships it while the helpers are already on the next ones - no barrier and no
     // wake-up between chunks (vmp_scan: the DMA copies of a streamed upload).  Without helpers wait_chunk copies the chunk itself.
     static constexpr int MAX_CHUNKS = 16;
+    int helpers() { ensure_started(); return (int)workers_.size(); }
     void begin_chunks(void* dst, const void* src, size_t bytes, size_t chunk_bytes) {
         drain();
         job_.gather = 0;
