@@ -379,3 +379,39 @@ def test_imu_init_and_motion_compensation_match_numpy_restatement(oracle_mod):
         d = xo.as_dict()
         x = dict(pos=d["pos"], vel=d["vel"], ba=d["ba"], bg=d["bg"], g=d["g"], rot=d["rot"].reshape(3, 3), rot_ext=d["rot_ext"].reshape(3, 3), pos_ext=d["pos_ext"])
     assert checked >= 25 and moved > 0.01, (checked, moved)         # the compensation really moves points (centimetres)
+
+
+# --------------------------------------------------------------------------- lidarToWorld + pv_list (what the map update is fed)
+def test_world_points_and_pv_cov_match_numpy_restatement(oracle_mod):
+    """The tail of LIOBuilder::process (lio_builder.cpp:155-163, 231-245): the float32 world transform and pv.cov with the POSTERIOR pose and
+    covariance, restated with numpy.  The transform is evaluated in float32 with the association of pcl::transformPointCloud's SSE path
+    (x' = m0 x + (m1 y + (m2 z + t)), the one assumption about PCL the oracle makes - stated here, not verified: PCL is not in the image); with it the
+    world points are identical bit for bit; pv.cov to 1e-12 relative."""
+    from voxelmapplus_fastlio2_b200 import synth
+    cfg = default_config(max_points_per_scan=4096)
+    o = oracle_mod.Oracle(cfg)
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=1200))
+    checked = 0
+    for pk in seq.packages(30):
+        cloud = pk.cloud.copy()
+        st = o.lio_process(pk.imus, cloud, pk.t0, pk.t1)
+        x, P, status = o.lio_state()
+        if status < 2 or st.iters == 0 or pk.index < 22:
+            continue
+        d = x.as_dict()
+        R, Re = d["rot"].reshape(3, 3), d["rot_ext"].reshape(3, 3)
+        r_wl, p_wl = R @ Re, R @ d["pos_ext"] + d["pos"]
+        m, t = r_wl.astype(np.float32), p_wl.astype(np.float32)
+        px, py, pz = cloud[:, 0], cloud[:, 1], cloud[:, 2]                   # the compensated cloud (float32), scan_resolution = 0
+        w = np.stack([m[r, 0] * px + (m[r, 1] * py + (m[r, 2] * pz + t[r])) for r in range(3)], 1)
+        assert w.dtype == np.float32
+        pw, cw = o.dump_world_points(len(cloud))
+        assert np.array_equal(pw, w.astype(np.float64)), f"scan {pk.index}: world points differ"
+        worst = 0.0
+        for i in range(0, len(cloud), 7):
+            pl, cl = _body_cov_numpy(cloud[i, :3].astype(np.float64))
+            ref = r_wl @ cl @ r_wl.T + _hat(pl) @ P[3:6, 3:6] @ _hat(pl).T + P[0:3, 0:3]
+            worst = max(worst, np.abs(cw[i].reshape(3, 3) - ref).max() / np.abs(ref).max())
+        assert worst < 1e-12, (pk.index, worst)
+        checked += 1
+    assert checked >= 5
