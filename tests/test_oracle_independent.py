@@ -418,14 +418,18 @@ def test_world_points_and_pv_cov_match_numpy_restatement(oracle_mod):
 
 
 # --------------------------------------------------------------------------- everything together, free-running
-def test_free_running_python_lio_tracks_the_oracle(oracle_mod):
+import pytest
+
+
+@pytest.mark.parametrize("estimate_ext", [0, 1])
+def test_free_running_python_lio_tracks_the_oracle(oracle_mod, estimate_ext):
     """tests/lio_pyref.py - the pieces above composed into a second, free-running implementation of LIOBuilder::process (numpy / scipy / LAPACK,
     dict + OrderedDict map, persistent residual records) - beside the C++ oracle from the first IMU sample on, neither side ever seeing the other's
     state: iteration counts and effect_num per iteration identical, position within 1e-10 m, rotation matrix within 1e-10, posterior covariance 1e-8
     relative (measured: 2e-13 / 1.5e-13 / 1e-12 over 30 updates), and at the end the same voxels with the same flags and counts."""
     from lio_pyref import LioPy
     from voxelmapplus_fastlio2_b200 import synth
-    cfg = default_config(max_points_per_scan=2048, map_capacity=100000)
+    cfg = default_config(max_points_per_scan=2048, map_capacity=100000, estimate_ext=estimate_ext)
     o = oracle_mod.Oracle(cfg)
     py = LioPy(cfg)
     seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=700))
