@@ -357,6 +357,33 @@ def test_lio_trajectory(oracle_mod):
     assert_maps_equal(o.dump_map(), b.map.dump_map(), exact=False, rtol=1e-6, what="free-running map")
 
 
+def test_lio_trajectory_against_the_python_implementation():
+    """Tier 3 without the C++ oracle in the loop: the CUDA path (device compensation + update, host IMU propagation) free-running beside
+    tests/lio_pyref.py, the independent Python / numpy / LAPACK implementation of LIOBuilder::process that pins the oracle on the CPU
+    (tests/test_oracle_independent.py).  Same iteration counts, pose within 1 mm / 0.01 deg, and the measured deviation printed."""
+    from lio_pyref import LioPy
+    cfg = default_config(max_points_per_scan=2048, map_capacity=100000)
+    b = LIOBuilder(cfg)
+    py = LioPy(cfg)
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=700))
+    worst_p = worst_r = 0.0
+    updates = same_effect = 0
+    for pk in seq.packages(32):
+        sb = b.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        py.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        xb, Pb, s2 = b.state()
+        assert s2 == py.status
+        if s2 == 2 and sb.iters:
+            assert sb.iters == py.iters
+            same_effect += list(sb.effect_num[:sb.iters]) == py.effect
+            worst_p = max(worst_p, float(np.linalg.norm(np.array(xb.pos[:]) - py.x["pos"])))
+            worst_r = max(worst_r, synth.rot_angle_deg(np.array(xb.rot[:]).reshape(3, 3), py.x["rot"]))
+            updates += 1
+    print(f"CUDA path vs python LIO over {updates} updates: position {worst_p:.3e} m, attitude {worst_r:.3e} deg, effect_num equal in {same_effect}")
+    assert updates >= 20 and same_effect >= updates - 2
+    assert worst_p < 1e-3 and worst_r < 1e-2, (worst_p, worst_r)
+
+
 def test_pipelined_mode_is_identical():
     """vmp_set_pipelined: the same posteriors and the same map bit for bit; map counters arrive one scan late."""
     cfg = default_config(max_points_per_scan=8192)
