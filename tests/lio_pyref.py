@@ -147,7 +147,11 @@ class LioPy:
             self.map.build(w, covs)
             self.status = self.LIO_MAPPING
             return comp
-        self._update(comp)
-        w, covs = self._pv_list(comp)
+        lidar = comp
+        if self.cfg.scan_resolution > 0.0:                           # scan_filter.filter(*lidar_cloud), lio_builder.cpp:215-219 (MAP_INIT builds from the unfiltered cloud)
+            from test_downsample import np_voxel_grid
+            lidar = np_voxel_grid(comp, self.cfg.scan_resolution)
+        self._update(lidar)
+        w, covs = self._pv_list(lidar)
         self.map.update(w, covs)
         return comp

@@ -421,18 +421,18 @@ def test_world_points_and_pv_cov_match_numpy_restatement(oracle_mod):
 import pytest
 
 
-@pytest.mark.parametrize("estimate_ext", [0, 1])
-def test_free_running_python_lio_tracks_the_oracle(oracle_mod, estimate_ext):
+@pytest.mark.parametrize("estimate_ext,scan_resolution", [(0, 0.0), (1, 0.0), (0, 0.1)])
+def test_free_running_python_lio_tracks_the_oracle(oracle_mod, estimate_ext, scan_resolution):
     """tests/lio_pyref.py - the pieces above composed into a second, free-running implementation of LIOBuilder::process (numpy / scipy / LAPACK,
     dict + OrderedDict map, persistent residual records) - beside the C++ oracle from the first IMU sample on, neither side ever seeing the other's
     state: iteration counts and effect_num per iteration identical, position within 1e-10 m, rotation matrix within 1e-10, posterior covariance 1e-8
     relative (measured: 2e-13 / 1.5e-13 / 1e-12 over 30 updates), and at the end the same voxels with the same flags and counts."""
     from lio_pyref import LioPy
     from voxelmapplus_fastlio2_b200 import synth
-    cfg = default_config(max_points_per_scan=2048, map_capacity=100000, estimate_ext=estimate_ext)
+    cfg = default_config(max_points_per_scan=2048, map_capacity=100000, estimate_ext=estimate_ext, scan_resolution=scan_resolution)
     o = oracle_mod.Oracle(cfg)
     py = LioPy(cfg)
-    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=700))
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=1500 if scan_resolution > 0 else 700))    # (0.1 is the reference's default filter: pcl::VoxelGrid in the loop)
     updates = 0
     worst = dict(pos=0.0, rot=0.0, P=0.0)
     for pk in seq.packages(32):
