@@ -421,23 +421,24 @@ def test_world_points_and_pv_cov_match_numpy_restatement(oracle_mod):
 import pytest
 
 
-@pytest.mark.parametrize("estimate_ext,scan_resolution", [(0, 0.0), (1, 0.0), (0, 0.1)])
-def test_free_running_python_lio_tracks_the_oracle(oracle_mod, estimate_ext, scan_resolution):
+@pytest.mark.parametrize("estimate_ext,scan_resolution,capacity", [(0, 0.0, 100000), (1, 0.0, 100000), (0, 0.1, 100000), (0, 0.0, 500)])
+def test_free_running_python_lio_tracks_the_oracle(oracle_mod, estimate_ext, scan_resolution, capacity):
     """tests/lio_pyref.py - the pieces above composed into a second, free-running implementation of LIOBuilder::process (numpy / scipy / LAPACK,
     dict + OrderedDict map, persistent residual records) - beside the C++ oracle from the first IMU sample on, neither side ever seeing the other's
     state: iteration counts and effect_num per iteration identical, position within 1e-10 m, rotation matrix within 1e-10, posterior covariance 1e-8
     relative (measured: 2e-13 / 1.5e-13 / 1e-12 over 30 updates), and at the end the same voxels with the same flags and counts."""
     from lio_pyref import LioPy
     from voxelmapplus_fastlio2_b200 import synth
-    cfg = default_config(max_points_per_scan=2048, map_capacity=100000, estimate_ext=estimate_ext, scan_resolution=scan_resolution)
+    cfg = default_config(max_points_per_scan=2048, map_capacity=capacity, estimate_ext=estimate_ext, scan_resolution=scan_resolution)
     o = oracle_mod.Oracle(cfg)
     py = LioPy(cfg)
     seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=1500 if scan_resolution > 0 else 700))    # (0.1 is the reference's default filter: pcl::VoxelGrid in the loop)
-    updates = 0
+    updates = evictions = 0
     worst = dict(pos=0.0, rot=0.0, P=0.0)
     for pk in seq.packages(32):
         st = o.lio_process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
         py.process(pk.imus, pk.cloud.copy(), pk.t0, pk.t1)
+        evictions += len(py.map.evicted)
         xo, Po, status = o.lio_state()
         assert status == py.status
         if status < 2 or st.iters == 0:
@@ -449,10 +450,12 @@ def test_free_running_python_lio_tracks_the_oracle(oracle_mod, estimate_ext, sca
         worst["P"] = max(worst["P"], np.abs(Po - py.P).max() / np.abs(Po).max())
         updates += 1
     print(f"python LIO vs oracle over {updates} updates: {worst}")
-    assert updates >= 20
+    assert updates >= 20 and (capacity > 500 or evictions > 500), (updates, evictions)     # the small map evicts continuously (LRU order is part of the state)
     assert worst["pos"] < 1e-10 and worst["rot"] < 1e-10 and worst["P"] < 1e-8, worst
     dm = o.dump_map()
     keys = [tuple(k) for k in dm["key"].tolist()]
     assert set(keys) == set(py.map.feat.keys())
+    if capacity <= 500:
+        assert keys == list(py.map.cache.keys())[::-1]              # the same LRU order, front first
     same = sum(int(v["n"]) == py.map.feat[k].n and bool(v["flags"] & F_PLANE) == py.map.feat[k].is_plane for v, k in zip(dm, keys))
     assert same >= 0.995 * len(keys), (same, len(keys))             # (a float32 world coordinate may round differently in the 9th digit of the pose)
