@@ -475,6 +475,37 @@ def test_streamed_upload_is_identical(monkeypatch, chunk_min, pipelined, loop):
     assert_maps_equal(a.dump_map(), b.dump_map(), exact=True, what="streamed upload")
 
 
+def test_scan_buffer_fill_is_identical():
+    """vmp_scan_buffer_fill (x y z out of the caller's 4- or 12-float point records, by the staging helpers) + vmp_scan_staged == vmp_scan on the
+    packed x y z, bit for bit; a stride below 3 is rejected."""
+    cfg = default_config(max_points_per_scan=8192)
+    a, b = HotPath(cfg), HotPath(cfg)
+    lio = LIOBuilder(cfg, device_undistort=False)          # produces priors and compensated clouds
+    seq = synth.Sequence(sensor=synth.SensorConfig(pts_per_scan=5000))
+    n = 0
+    for pk in seq.packages(10):
+        cloud = pk.cloud.copy()
+        st = lio.process(pk.imus, cloud, pk.t0, pk.t1)
+        _, _, status = lio.state()
+        if status < 2:
+            continue
+        x0, P0 = lio.prior()
+        xyz = np.ascontiguousarray(cloud[:, :3])
+        if st.iters == 0:
+            a.first_scan(x0, P0, xyz); b.first_scan(x0, P0, xyz)
+            continue
+        rec = cloud if n % 2 == 0 else np.concatenate([cloud[:, :3], np.full((len(cloud), 9), 7.0, np.float32)], 1)     # x y z t  /  a 48-byte PCL-style record
+        xa, Pa, sa = a.scan(x0, P0, xyz)
+        xb, Pb, sb = b.scan_filled(x0, P0, rec)
+        assert bytes(xa) == bytes(xb) and np.array_equal(Pa, Pb) and sa.iters == sb.iters
+        assert sa.map.as_dict() == sb.map.as_dict()
+        n += 1
+    assert n >= 5
+    assert_maps_equal(a.dump_map(), b.dump_map(), exact=True, what="filled scan")
+    with pytest.raises(VmpError):
+        b.scan_filled(x0, P0, cloud, stride=2)
+
+
 def test_staged_scan_is_identical():
     """vmp_scan_buffer + vmp_scan_staged (points written straight into the pinned staging) == vmp_scan, bit for bit."""
     cfg = default_config(max_points_per_scan=8192)

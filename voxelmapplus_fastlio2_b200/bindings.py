@@ -171,6 +171,23 @@ class HotPath:
         self._check(self._lib.vmp_scan_staged(self._h, C.byref(x), dptr(P), n, C.byref(st)))
         return x, P, st
 
+    def scan_filled(self, x: VmpState, P, records, stride=None):
+        """vmp_scan_buffer_fill + vmp_scan_staged: x y z are taken out of the caller's point records (n x stride float32) by the handle's staging helpers."""
+        r = np.ascontiguousarray(records, dtype=np.float32)
+        stride = r.shape[1] if stride is None else stride
+        n = r.shape[0]
+        self._lib.vmp_scan_buffer_fill.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int]
+        self._lib.vmp_scan_buffer_fill.restype = C.c_int
+        self._lib.vmp_scan_staged.argtypes = [C.c_void_p, C.POINTER(VmpState), C.POINTER(C.c_double), C.c_int, C.POINTER(VmpScanStats)]
+        self._lib.vmp_scan_staged.restype = C.c_int
+        self._check(self._lib.vmp_scan_buffer_fill(self._h, fptr(r), stride, n))
+        self._n = n
+        x = x.copy()
+        P = _f64(P, (23, 23)).copy()
+        st = VmpScanStats()
+        self._check(self._lib.vmp_scan_staged(self._h, C.byref(x), dptr(P), n, C.byref(st)))
+        return x, P, st
+
     def first_scan(self, x: VmpState, P, pts_lidar) -> dict:
         """MAP_INIT branch (lio_builder.cpp:185-211)."""
         p = np.ascontiguousarray(pts_lidar, dtype=np.float32).reshape(-1, 3)
