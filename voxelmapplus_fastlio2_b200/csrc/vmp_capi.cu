@@ -764,13 +764,12 @@ static int scan_common(vmp_handle h, vmp_state* x, double* P, int n, size_t uplo
                 if (trace) tr_ready[c] = tr_us();
                 ce = cudaMemcpyAsync(h->d_stage + PTS_OFF + off, h->h_stage + PTS_OFF + off, len, cudaMemcpyHostToDevice, c ? later : h->stream);
                 if (ce != cudaSuccess) break;
-                if (!gate) {
-                } else if (c == 0) {
+                if (gate && c == 0) {
                     ce = cudaStreamWaitEvent(h->up_st, h->pe0[eb], 0);     // (pipelined mode: the previous scan's map update still reads the old points)
                     if (ce == cudaSuccess) rr = run_scan(h, raw, n, predict);
                     launched = true;
                     if (trace) tr_graph = tr_us();
-                } else if (write_value(h->up_st, (unsigned long long)(uintptr_t)&h->ctl->up_pub, seq * 64ull + (unsigned long long)c, 0u) != 0) {
+                } else if (gate && write_value(h->up_st, (unsigned long long)(uintptr_t)&h->ctl->up_pub, seq * 64ull + (unsigned long long)c, 0u) != 0) {
                     set_error("vmp_scan: cuStreamWriteValue64 failed during the streamed upload");
                     h->upload_gate = false;
                     rr = VMP_ERR_CUDA;
